@@ -1,0 +1,339 @@
+"""CPU oracle: a NumPy/SciPy restatement of pyTDGL's per-step hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it, and only as the checker / the CPU baseline — never as a fallback of
+the CUDA path (the product fails loudly when ``libtdgl_b200.so`` is missing).
+
+Parity pinning: the reference's own tests hold no golden vectors for this path
+(SURVEY.md §4); this restatement is pinned against the UNMODIFIED reference code
+executed in the build container through ``oracle/ref_loader.py`` — see
+``tests/test_oracle_vs_reference.py`` (runs where ``/root/reference`` exists) and the
+committed fixtures ``tests/golden/*.npz`` produced by ``oracle/make_golden.py`` from the
+reference itself (checked on every box by ``tests/test_oracle_golden.py``).
+
+Each function cites the reference file:line it follows (paths relative to
+``/root/reference/``).  Like the reference, the mu system is solved with SuperLU through
+``scipy.sparse.linalg.factorized`` on the *singular* pure-Neumann Laplacian
+(``tdgl/finite_volume/operators.py:285,306-308``), so raw ``mu`` carries an arbitrary
+additive constant and raw ``psi`` an arbitrary global phase: compare through
+``gauge_fix``.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, NamedTuple, Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+class TerminalInfo(NamedTuple):
+    """reference ``tdgl/device/device.py:30-46``"""
+
+    name: str
+    site_indices: Sequence[int]
+    edge_indices: Sequence[int]
+    boundary_edge_indices: Sequence[int]
+    length: float
+
+
+# ------------------------------------------------------------------ operators (L0)
+
+def divergence_matrix(edges, areas, dual_len, n_sites) -> sp.csr_array:
+    """(e0, e) = s_e / a[e0], (e1, e) = -s_e / a[e1]  — operators.py:59-84"""
+    E = len(edges)
+    e = np.arange(E)
+    i0, i1 = edges[:, 0], edges[:, 1]
+    return sp.csr_array(
+        (np.concatenate([dual_len / areas[i0], -dual_len / areas[i1]]),
+         (np.concatenate([i0, i1]), np.concatenate([e, e]))),
+        shape=(n_sites, E))
+
+
+def link_variables(A, directions) -> np.ndarray:
+    """U_e = exp(-i A_e . d_e)  — operators.py:109-111,153-155"""
+    return np.exp(-1j * np.einsum("ij, ij -> i", A, directions))
+
+
+def gradient_matrix(edges, edge_len, n_sites, U=None) -> sp.csr_array:
+    """(e, e1) = U_e / l_e, (e, e0) = -1 / l_e  — operators.py:87-117"""
+    E = len(edges)
+    e = np.arange(E)
+    w = 1 / edge_len
+    link = np.ones(E) if U is None else U
+    return sp.csr_array(
+        (np.concatenate([link * w, -w]),
+         (np.concatenate([e, e]), np.concatenate([edges[:, 1], edges[:, 0]]))),
+        shape=(E, n_sites))
+
+
+def laplacian_matrix(edges, areas, edge_len, dual_len, n_sites, U=None,
+                     fixed_sites=None) -> sp.csc_array:
+    """Off-diagonals w_e U_e / a[e0], w_e conj(U_e) / a[e1]; diagonals -w_e / a
+    accumulated; rows of ``fixed_sites`` replaced by a unit diagonal
+    — operators.py:120-185"""
+    i0, i1 = edges[:, 0], edges[:, 1]
+    w = dual_len / edge_len
+    link = np.ones(len(edges)) if U is None else U
+    rows = np.concatenate([i0, i1, i0, i1])
+    cols = np.concatenate([i1, i0, i0, i1])
+    vals = np.concatenate([w * link / areas[i0], w * link.conjugate() / areas[i1],
+                           -w / areas[i0], -w / areas[i1]])
+    if fixed_sites is None:
+        fixed_sites = np.array([], dtype=np.int64)
+    free = np.isin(rows, fixed_sites, invert=True)
+    rows = np.concatenate([rows[free], fixed_sites])
+    cols = np.concatenate([cols[free], fixed_sites])
+    vals = np.concatenate([vals[free], np.ones(len(fixed_sites))])
+    return sp.csc_array((vals, (rows, cols)), shape=(n_sites, n_sites))
+
+
+def neumann_boundary_matrix(edges, areas, edge_len, boundary_edge_indices,
+                            n_sites) -> sp.csr_array:
+    """(i, b) = (j, b) = l_b / (2 a) for boundary edge b = (i, j)  — operators.py:188-230"""
+    nb = len(boundary_edge_indices)
+    b = np.arange(nb)
+    be = edges[boundary_edge_indices]
+    bl = edge_len[boundary_edge_indices]
+    return sp.csr_array(
+        (np.concatenate([bl / (2 * areas[be[:, 0]]), bl / (2 * areas[be[:, 1]])]),
+         (np.concatenate([be[:, 0], be[:, 1]]), np.concatenate([b, b]))),
+        shape=(n_sites, nb))
+
+
+class OracleOperators:
+    """reference ``MeshOperators`` (operators.py:233-394) for the SuperLU path."""
+
+    def __init__(self, mesh, fixed_sites=None, fix_psi: bool = True):
+        em = mesh.edge_mesh
+        self.n = len(mesh.sites)
+        self.edges = np.asarray(em.edges)
+        self.areas = np.asarray(mesh.areas)
+        self.edge_len = np.asarray(em.edge_lengths)
+        self.dual_len = np.asarray(em.dual_edge_lengths)
+        self.directions = np.asarray(em.directions)
+        self.boundary_edge_indices = np.asarray(em.boundary_edge_indices)
+        self.fixed_sites = (np.array([], dtype=np.int64) if fixed_sites is None
+                            else np.asarray(fixed_sites, dtype=np.int64))
+        self.fix_psi = fix_psi
+        a = (self.edges, self.areas, self.edge_len, self.dual_len, self.n)
+        # build_operators — operators.py:282-308 (mu Laplacian has NO fixed sites)
+        self.mu_laplacian = laplacian_matrix(*a)
+        self.mu_boundary_laplacian = neumann_boundary_matrix(
+            self.edges, self.areas, self.edge_len, self.boundary_edge_indices, self.n)
+        self.mu_gradient = gradient_matrix(self.edges, self.edge_len, self.n)
+        self.divergence = divergence_matrix(self.edges, self.areas, self.dual_len, self.n)
+        spla.use_solver(useUmfpack=False)
+        self.mu_laplacian_lu = spla.factorized(self.mu_laplacian)
+        self.psi_gradient = None
+        self.psi_laplacian = None
+
+    def set_link_exponents(self, A) -> None:
+        """operators.py:310-383.  (Rebuilding gives the same matrices as the in-place
+        value rewrite of :346-383.)"""
+        U = link_variables(np.asarray(A, float), self.directions)
+        self.psi_gradient = gradient_matrix(self.edges, self.edge_len, self.n, U)
+        self.psi_laplacian = laplacian_matrix(
+            self.edges, self.areas, self.edge_len, self.dual_len, self.n, U,
+            self.fixed_sites if self.fix_psi else None)
+
+    def get_supercurrent(self, psi):
+        """J_s[e] = Im(conj(psi[e0]) * (grad_psi @ psi)[e])  — operators.py:385-394"""
+        return (psi.conjugate()[self.edges[:, 0]] * (self.psi_gradient @ psi)).imag
+
+
+# ------------------------------------------------------------------ step physics (L1)
+
+def solve_for_psi_squared(psi, abs_sq_psi, mu, epsilon, gamma, u, dt, psi_laplacian):
+    """psi^n, mu^n -> psi^{n+1}, |psi^{n+1}|^2 (quadratic root), or None
+    — solver.py:383-439 (expression order kept)."""
+    U = np.exp(-1j * mu * dt)
+    z = U * gamma**2 / 2 * psi
+    with np.errstate(all="raise"):
+        try:
+            w = z * abs_sq_psi + U * (
+                psi + (dt / u) * np.sqrt(1 + gamma**2 * abs_sq_psi)
+                * ((epsilon - abs_sq_psi) * psi + psi_laplacian @ psi))
+            c = w.real * z.real + w.imag * z.imag
+            two_c_1 = 2 * c + 1
+            w2 = np.absolute(w) ** 2
+            disc = two_c_1**2 - 4 * np.absolute(z) ** 2 * w2
+        except Exception:
+            return None
+    if np.any(disc < 0):
+        return None
+    new_sq = (2 * w2) / (two_c_1 + np.sqrt(disc))
+    return w - z * new_sq, new_sq
+
+
+@dataclass
+class OracleOptions:
+    """The ``SolverOptions`` fields the hot path reads (options.py:66-89)."""
+
+    solve_time: float = 1.0
+    skip_time: float = 0.0
+    dt_init: float = 1e-6
+    dt_max: float = 1e-1
+    adaptive: bool = True
+    adaptive_window: int = 10
+    max_solve_retries: int = 10
+    adaptive_time_step_multiplier: float = 0.25
+    terminal_psi: Optional[complex] = 0.0
+    save_every: int = 100
+
+
+@dataclass
+class OracleSolver:
+    """State + one-step update of reference ``TDGLSolver`` (solver.py:88-714) with the
+    pint/Device layer stripped: all inputs are already dimensionless."""
+
+    mesh: object
+    options: OracleOptions
+    A_applied: np.ndarray                      # [E, 2], already A_scale-d (solver.py:185)
+    epsilon: np.ndarray                        # [N]
+    u: float = 5.79
+    gamma: float = 10.0
+    terminal_info: Sequence[TerminalInfo] = ()
+    current_func: Optional[Callable[[float], Dict[str, float]]] = None  # J_scale-d
+    probe_points: Optional[Sequence[int]] = None
+    d_psi_sq_vals: List[float] = field(default_factory=list)
+
+    def __post_init__(self):
+        o = self.options
+        idx = [np.asarray(t.site_indices, dtype=np.int64) for t in self.terminal_info]
+        self.fixed_sites = (np.concatenate(idx) if idx else np.array([], dtype=np.int64))
+        self.terminal_names = [t.name for t in self.terminal_info]
+        if self.current_func is None:
+            zero = {n: 0.0 for n in self.terminal_names}
+            self.current_func = lambda t: zero
+        self.terminal_current_densities = {n: 0 for n in self.terminal_names}
+        self.operators = OracleOperators(self.mesh, self.fixed_sites,
+                                         fix_psi=(o.terminal_psi is not None))
+        self.operators.set_link_exponents(self.A_applied)
+        n = len(self.mesh.sites)
+        self.psi_init = np.ones(n, dtype=np.complex128)       # solver.py:285-287
+        if o.terminal_psi is not None:
+            self.psi_init[self.fixed_sites] = o.terminal_psi
+        self.mu_init = np.zeros(n)
+        self.mu_boundary = np.zeros(len(self.mesh.edge_mesh.boundary_edge_indices))
+        self.tentative_dt = o.dt_init                          # solver.py:318-320
+        self.dt_max = o.dt_max if o.adaptive else o.dt_init
+        self.epsilon = np.asarray(self.epsilon, float)
+
+    def update_mu_boundary(self, time: float) -> None:
+        """J_ext,k = -(1/L_k) sum_{j != k} I_j  — solver.py:325-345"""
+        currents = self.current_func(time)
+        for term in self.terminal_info:
+            dens = (-1 / term.length) * sum(
+                currents.get(name, 0) for name in self.terminal_names if name != term.name)
+            if dens != self.terminal_current_densities[term.name]:
+                self.terminal_current_densities[term.name] = dens
+                self.mu_boundary[np.asarray(term.boundary_edge_indices)] = dens
+
+    def adaptive_euler_step(self, step, psi, abs_sq_psi, mu, dt):
+        """solver.py:441-487"""
+        o = self.options
+        L = self.operators.psi_laplacian
+        res = solve_for_psi_squared(psi, abs_sq_psi, mu, self.epsilon, self.gamma, self.u,
+                                    dt, L)
+        retries = 0
+        while res is None:
+            if not o.adaptive or retries > o.max_solve_retries:
+                raise RuntimeError(
+                    f"Solver failed to converge in {o.max_solve_retries}"
+                    f" retries at step {step} with dt = {dt:.2e}."
+                    f" Try using a smaller dt_init.")
+            dt = dt * o.adaptive_time_step_multiplier
+            res = solve_for_psi_squared(psi, abs_sq_psi, mu, self.epsilon, self.gamma,
+                                        self.u, dt, L)
+            retries += 1
+        return res[0], res[1], dt
+
+    def solve_for_observables(self, psi, dA_dt=0.0):
+        """solver.py:489-520"""
+        ops = self.operators
+        js = ops.get_supercurrent(psi)
+        rhs = ops.divergence @ (js - dA_dt) - ops.mu_boundary_laplacian @ self.mu_boundary
+        mu = ops.mu_laplacian_lu(rhs)
+        jn = -(ops.mu_gradient @ mu) - dA_dt
+        return mu, js, jn
+
+    def update(self, step: int, time: float, psi, mu):
+        """One time step — solver.py:580-714 (static A and epsilon, no screening).
+        Returns (dt, psi', mu', J_s, J_n)."""
+        o = self.options
+        self.update_mu_boundary(time)
+        old_sq = np.absolute(psi) ** 2                                   # :649
+        dt = self.tentative_dt                                           # :668
+        psi, new_sq, dt = self.adaptive_euler_step(step, psi, old_sq, mu, dt)
+        mu, js, jn = self.solve_for_observables(psi)
+        if o.adaptive:                                                   # :698-707
+            self.d_psi_sq_vals.append(float(np.absolute(new_sq - old_sq).max()))
+            if step > o.adaptive_window:
+                new_dt = o.dt_init / max(
+                    1e-10, np.mean(self.d_psi_sq_vals[-o.adaptive_window:]))
+                self.tentative_dt = np.clip(0.5 * (new_dt + dt), 0, self.dt_max)
+        return dt, psi, mu, js, jn
+
+
+def run(solver: OracleSolver, *, end_time: float, max_steps: Optional[int] = None,
+        psi0=None, mu0=None):
+    """The loop of ``Runner._run_stage`` (runner.py:379-433) without disk output: one more
+    update is performed after ``time >= end_time`` is first reached, ``dt <- new_dt``,
+    ``time += dt``.  Returns final fields, the dt sequence and the probe traces."""
+    psi = solver.psi_init.copy() if psi0 is None else np.array(psi0, complex)
+    mu = solver.mu_init.copy() if mu0 is None else np.array(mu0, float)
+    time = 0.0
+    dts, mus, thetas = [], [], []
+    i = 0
+    while True:
+        dt, psi, mu, js, jn = solver.update(i, time, psi, mu)
+        dts.append(float(dt))
+        if solver.probe_points is not None:                      # solver.py:691-694
+            mus.append(mu[list(solver.probe_points)])
+            thetas.append(np.angle(psi[list(solver.probe_points)]))
+        if time >= end_time or (max_steps is not None and i + 1 >= max_steps):
+            break
+        time += dt
+        i += 1
+    out = dict(psi=psi, mu=mu, supercurrent=js, normal_current=jn, dt=np.array(dts),
+               steps=i + 1, time=time)
+    if solver.probe_points is not None:
+        out["running"] = dict(mu=np.array(mus).T, theta=np.array(thetas).T)
+    return out
+
+
+# ------------------------------------------------------------------ gauge-fixed comparison
+
+def gauge_fix(psi, mu, areas, psi_ref=None):
+    """Remove what no correct solver can reproduce: the additive constant of mu (the
+    reference's is SuperLU roundoff on a singular system) and the global phase of psi
+    it integrates to.  mu -> mu - area-weighted mean; psi -> psi * exp(-i phi) with
+    phi = arg<psi_ref, psi> (or arg of the area-weighted mean if no reference)."""
+    mu0 = mu - np.dot(areas, mu) / areas.sum()
+    if psi_ref is None:
+        phi = np.angle(np.dot(areas, psi))
+    else:
+        phi = np.angle(np.vdot(psi_ref, psi))
+    return psi * np.exp(-1j * phi), mu0
+
+
+def compare(a: dict, b: dict, areas) -> dict:
+    """Gauge-fixed relative differences (max-norm, relative to the max magnitude)."""
+    pa, ma = gauge_fix(a["psi"], a["mu"], areas, b["psi"])
+    pb, mb = gauge_fix(b["psi"], b["mu"], areas, b["psi"])
+
+    def rel(x, y):
+        return float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))
+
+    out = dict(psi=rel(pa, pb), abs_psi=rel(np.abs(a["psi"]), np.abs(b["psi"])),
+               mu=rel(ma, mb))
+    for k in ("supercurrent", "normal_current"):
+        if k in a and k in b and a[k] is not None and b[k] is not None:
+            out[k] = rel(a[k], b[k])
+    if "dt" in a and "dt" in b and len(a["dt"]) == len(b["dt"]):
+        out["dt"] = rel(np.asarray(a["dt"]), np.asarray(b["dt"]))
+    return out

@@ -1,0 +1,307 @@
+"""Finite-volume mesh arrays: the input contract of the hot path.
+
+Mirrors the *data* of the reference's ``tdgl.finite_volume.Mesh`` / ``EdgeMesh``
+(reference ``tdgl/finite_volume/mesh.py:24-69``, ``edge_mesh.py:9-42``): same attribute
+names, shapes, dtypes, units (lengths in units of xi) and ordering (edge rows sorted and
+lexicographically unique, ``util.py:15-28``).  The construction here is vectorised
+NumPy (the reference loops over edges and sites in Python, ``util.py:59-97,169-255``;
+108 s at 1M sites); it is setup-time code, not part of the timed path.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+
+class EdgeMesh:
+    """Edges of the triangulation (reference ``edge_mesh.py:9-42``)."""
+
+    def __init__(self, centers, edges, boundary_edge_indices, directions,
+                 edge_lengths, dual_edge_lengths):
+        self.centers = np.asarray(centers, dtype=np.float64)
+        self.edges = np.asarray(edges, dtype=np.int64)
+        self.boundary_edge_indices = np.asarray(boundary_edge_indices, dtype=np.int64)
+        self.directions = np.asarray(directions, dtype=np.float64)
+        self.normalized_directions = (
+            self.directions / np.linalg.norm(self.directions, axis=1)[:, np.newaxis]
+        )
+        self.edge_lengths = np.asarray(edge_lengths, dtype=np.float64)
+        self.dual_edge_lengths = np.asarray(dual_edge_lengths, dtype=np.float64)
+
+    @property
+    def x(self):
+        return self.centers[:, 0]
+
+    @property
+    def y(self):
+        return self.centers[:, 1]
+
+
+def get_edges(elements: np.ndarray, num_sites: Optional[int] = None):
+    """Unique sorted edges and the is-boundary mask (same result as reference
+    ``util.py:15-28``; done on a packed 64-bit key instead of a row-wise unique)."""
+    elements = np.asarray(elements, dtype=np.int64)
+    if num_sites is None:
+        num_sites = int(elements.max()) + 1
+    pairs = np.concatenate([elements[:, [0, 1]], elements[:, [1, 2]], elements[:, [2, 0]]])
+    lo = pairs.min(axis=1)
+    hi = pairs.max(axis=1)
+    key = lo * np.int64(num_sites) + hi
+    ukey, counts = np.unique(key, return_counts=True)
+    edges = np.stack([ukey // num_sites, ukey % num_sites], axis=1)
+    return edges, counts == 1, key, ukey
+
+
+def circumcenters(sites: np.ndarray, elements: np.ndarray) -> np.ndarray:
+    """Voronoi vertices = triangle circumcentres (reference ``util.py:100-124``)."""
+    A = sites[elements[:, 0]]
+    B = sites[elements[:, 1]] - A
+    C = sites[elements[:, 2]] - A
+    D = 2 * B[:, 0] * C[:, 1] - 2 * B[:, 1] * C[:, 0]
+    b2 = (B**2).sum(axis=1)
+    c2 = (C**2).sum(axis=1)
+    Ux = (C[:, 1] * b2 - B[:, 1] * c2) / D
+    Uy = (B[:, 0] * c2 - C[:, 0] * b2) / D
+    return np.array([Ux, Uy]).T + A
+
+
+class Mesh:
+    """Triangular mesh + Voronoi dual (reference ``mesh.py:24-69``)."""
+
+    def __init__(self, sites, elements, boundary_indices, areas=None, dual_sites=None,
+                 edge_mesh: Optional[EdgeMesh] = None, voronoi_polygons=None):
+        self.sites = np.asarray(sites, dtype=np.float64)
+        self.elements = np.asarray(elements, dtype=np.int64)
+        self.boundary_indices = np.asarray(boundary_indices, dtype=np.int64)
+        self.areas = None if areas is None else np.asarray(areas, dtype=np.float64)
+        self.dual_sites = None if dual_sites is None else np.asarray(dual_sites)
+        self.edge_mesh = edge_mesh
+        self.voronoi_polygons = voronoi_polygons
+
+    @property
+    def x(self):
+        return self.sites[:, 0]
+
+    @property
+    def y(self):
+        return self.sites[:, 1]
+
+    def closest_site(self, xy) -> int:
+        """reference ``mesh.py:92-101``"""
+        return int(np.argmin(np.linalg.norm(self.sites - np.atleast_2d(xy), axis=1)))
+
+    @staticmethod
+    def from_triangulation(sites, elements, create_submesh: bool = True) -> "Mesh":
+        """Vectorised equivalent of reference ``Mesh.from_triangulation``
+        (``mesh.py:104-151``) + ``EdgeMesh.from_mesh`` (``edge_mesh.py:54-92``)."""
+        sites = np.asarray(sites, dtype=np.float64).squeeze()
+        elements = np.asarray(elements, dtype=np.int64).squeeze()
+        if sites.ndim != 2 or sites.shape[1] != 2:
+            raise ValueError(
+                f"The site coordinates must have shape (n, 2), got {sites.shape!r}")
+        if elements.ndim != 2 or elements.shape[1] != 3:
+            raise ValueError(f"The elements must have shape (m, 3), got {elements.shape!r}.")
+        n = len(sites)
+        edges, is_boundary, tri_keys, ukey = get_edges(elements, n)
+        boundary_edge_indices = np.where(is_boundary)[0]
+        boundary_indices = np.unique(edges[is_boundary].ravel())
+        if not create_submesh:
+            return Mesh(sites, elements, boundary_indices)
+        dual = circumcenters(sites, elements)
+        coords = sites[edges]
+        centers = coords.mean(axis=1)
+        directions = coords[:, 1] - coords[:, 0]
+        lengths = np.linalg.norm(directions, axis=1)
+        # triangles adjacent to each edge (one for boundary edges, two otherwise)
+        T = len(elements)
+        tri_of_key = np.tile(np.arange(T, dtype=np.int64), 3)
+        eidx = np.searchsorted(ukey, tri_keys)
+        order = np.argsort(eidx, kind="stable")
+        eidx_s = eidx[order]
+        tri_s = tri_of_key[order]
+        first = np.searchsorted(eidx_s, np.arange(len(edges)))
+        t0 = tri_s[first]
+        t1 = tri_s[np.minimum(first + 1, len(tri_s) - 1)]
+        dual_len = np.where(
+            is_boundary,
+            np.linalg.norm(dual[t0] - centers, axis=1),
+            np.linalg.norm(dual[t0] - dual[t1], axis=1),
+        )
+        edge_mesh = EdgeMesh(centers, edges, boundary_edge_indices, directions, lengths,
+                             dual_len)
+        areas = _voronoi_areas(sites, dual, elements, edges, lengths, dual_len,
+                               boundary_indices, boundary_edge_indices)
+        return Mesh(sites, elements, boundary_indices, areas=areas, dual_sites=dual,
+                    edge_mesh=edge_mesh)
+
+
+def _voronoi_areas(sites, dual, elements, edges, lengths, dual_len, boundary_indices,
+                   boundary_edge_indices) -> np.ndarray:
+    """Voronoi cell areas.
+
+    Interior sites: the cell is the convex polygon of the surrounding circumcentres,
+    whose area is the sum over incident edges of the triangle (site, dual edge) =
+    ``edge_length * dual_edge_length / 4`` (every edge at an interior site is interior).
+    Boundary sites follow the reference's convention (``util.py:205-254``): convex hull
+    of circumcentres + the two adjacent boundary-edge midpoints + the site, minus the
+    (midpoint, midpoint, site) triangle when the site is not a hull vertex.  There are
+    only O(sqrt(N)) of them, so that loop stays in Python.
+    """
+    from scipy.spatial import ConvexHull, QhullError
+
+    n = len(sites)
+    quarter = 0.25 * lengths * dual_len
+    areas = np.bincount(edges[:, 0], quarter, n) + np.bincount(edges[:, 1], quarter, n)
+    if len(boundary_indices) == 0:
+        return areas
+    # incident triangles of boundary sites
+    is_b = np.zeros(n, dtype=bool)
+    is_b[boundary_indices] = True
+    flat = elements.ravel()
+    sel = np.nonzero(is_b[flat])[0]
+    site_of = flat[sel]
+    tri_of = sel // 3
+    order = np.argsort(site_of, kind="stable")
+    site_of = site_of[order]
+    tri_of = tri_of[order]
+    starts = np.searchsorted(site_of, boundary_indices)
+    ends = np.searchsorted(site_of, boundary_indices, side="right")
+    bedges = edges[boundary_edge_indices]
+    bmid = sites[bedges].mean(axis=1)
+    # the two boundary edges at each boundary site
+    bflat = bedges.ravel()
+    border = np.argsort(bflat, kind="stable")
+    bsite = bflat[border]
+    bedge_of = border // 2
+    bstarts = np.searchsorted(bsite, boundary_indices)
+    bends = np.searchsorted(bsite, boundary_indices, side="right")
+
+    def hull_area(pts):
+        try:
+            hull = ConvexHull(pts)
+        except QhullError:
+            return 0.0, True
+        return hull.volume, len(hull.vertices) == len(pts)
+
+    for k, s in enumerate(boundary_indices):
+        mids = bmid[bedge_of[bstarts[k]:bends[k]]]
+        pts = np.concatenate([dual[tri_of[starts[k]:ends[k]]], mids, sites[s][None, :]])
+        a, convex = hull_area(pts)
+        if not convex:
+            tri, _ = hull_area(np.concatenate([mids, sites[s][None, :]]))
+            a -= tri
+        areas[s] = a
+    return areas
+
+
+# ----------------------------------------------------------------------------------------
+# Synthetic meshes: jittered hexagonal lattice + exact boundary points,
+# Delaunay-triangulated.  meshpy/Triangle (reference device/meshing.py) is not available.
+# ----------------------------------------------------------------------------------------
+
+def _hex_lattice(xmin, xmax, ymin, ymax, h):
+    dy = h * np.sqrt(3) / 2
+    ny = int(np.floor((ymax - ymin) / dy)) + 1
+    nx = int(np.floor((xmax - xmin) / h)) + 2
+    y0 = ymin + 0.5 * ((ymax - ymin) - (ny - 1) * dy)
+    ys = y0 + dy * np.arange(ny)
+    xs = xmin + h * np.arange(-1, nx)
+    X, Y = np.meshgrid(xs, ys)
+    X = X + (np.arange(ny) % 2)[:, None] * (h / 2)
+    return np.stack([X.ravel(), Y.ravel()], axis=1)
+
+
+def make_film_points(width: float, height: float, h: float,
+                     holes: Sequence[Tuple[float, float, float]] = (),
+                     jitter: float = 0.15, seed: int = 0):
+    """Points of a ``width x height`` rectangular film centred at the origin with
+    circular ``holes`` [(cx, cy, r), ...]: exact, evenly spaced boundary points and a
+    jittered hexagonal interior lattice of pitch ``h``."""
+    rng = np.random.default_rng(seed)
+    x0, x1 = -width / 2, width / 2
+    y0, y1 = -height / 2, height / 2
+    nx = max(int(round(width / h)), 2)
+    ny = max(int(round(height / h)), 2)
+    bx = np.linspace(x0, x1, nx + 1)
+    by = np.linspace(y0, y1, ny + 1)
+    boundary = [
+        np.stack([bx[:-1], np.full(nx, y0)], 1),
+        np.stack([np.full(ny, x1), by[:-1]], 1),
+        np.stack([bx[:0:-1], np.full(nx, y1)], 1),
+        np.stack([np.full(ny, x0), by[:0:-1]], 1),
+    ]
+    for (cx, cy, r) in holes:
+        m = max(int(round(2 * np.pi * r / h)), 8)
+        th = 2 * np.pi * np.arange(m) / m
+        boundary.append(np.stack([cx + r * np.cos(th), cy + r * np.sin(th)], 1))
+    pts = _hex_lattice(x0, x1, y0, y1, h)
+    pts = pts + rng.uniform(-jitter * h, jitter * h, size=pts.shape)
+    margin = 0.6 * h
+    keep = ((pts[:, 0] > x0 + margin) & (pts[:, 0] < x1 - margin)
+            & (pts[:, 1] > y0 + margin) & (pts[:, 1] < y1 - margin))
+    for (cx, cy, r) in holes:
+        keep &= np.hypot(pts[:, 0] - cx, pts[:, 1] - cy) > r + margin
+    return np.concatenate(boundary + [pts[keep]])
+
+
+def triangulate(points: np.ndarray, holes: Sequence[Tuple[float, float, float]] = ()):
+    """Delaunay triangulation (Qhull); triangles inside holes and degenerate slivers on
+    straight boundaries are dropped; triangles are oriented counter-clockwise."""
+    from scipy.spatial import Delaunay
+
+    tri = Delaunay(points).simplices.astype(np.int64)
+    p = points[tri]
+    area2 = ((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
+             - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0]))
+    flip = area2 < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    keep = np.abs(area2) > 1e-10 * np.abs(area2).max()
+    cen = p.mean(axis=1)
+    for (cx, cy, r) in holes:
+        keep &= np.hypot(cen[:, 0] - cx, cen[:, 1] - cy) > r * (1 - 1e-9) - 1e-12
+    tri = tri[keep]
+    # drop unused points (none expected) and renumber
+    used = np.zeros(len(points), dtype=bool)
+    used[tri.ravel()] = True
+    if not used.all():
+        remap = np.cumsum(used) - 1
+        points = points[used]
+        tri = remap[tri]
+    return points, tri
+
+
+def make_film_mesh(width: float, height: float, h: float,
+                   holes: Sequence[Tuple[float, float, float]] = (),
+                   jitter: float = 0.15, seed: int = 0, reorder: bool = True) -> Mesh:
+    """Synthetic film mesh; ``reorder`` sorts the sites along a space-filling (Morton)
+    curve so that CSR rows that are close in memory are close in space."""
+    pts = make_film_points(width, height, h, holes, jitter, seed)
+    pts, tri = triangulate(pts, holes)
+    if reorder:
+        perm = morton_order(pts)
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        pts = pts[perm]
+        tri = inv[tri]
+    return Mesh.from_triangulation(pts, tri)
+
+
+def morton_order(points: np.ndarray, bits: int = 20) -> np.ndarray:
+    """Permutation sorting 2D points along a Z-order curve."""
+    p = points - points.min(axis=0)
+    span = p.max()
+    q = np.minimum((p / span * ((1 << bits) - 1)).astype(np.uint64), (1 << bits) - 1)
+
+    def spread(v):
+        v = v & np.uint64(0xFFFFFFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return v
+
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    return np.argsort(code, kind="stable")
