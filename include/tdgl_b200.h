@@ -1,0 +1,181 @@
+/*
+ * tdgl_b200 — C ABI of the B200-native TDGL time stepper.
+ *
+ * This is the drop-in boundary for ONE path of pyTDGL (loganbvh/py-tdgl v0.8.3): the
+ * per-step hot path of the adaptive-Euler solver.  The reference has no FFI layer; its
+ * only backend seam is the Python call `TDGLSolver.update(state, running_state, dt,
+ * **values)` made once per step by `Runner._run_stage` (tdgl/solver/runner.py:417-423)
+ * plus the operator container `MeshOperators` (tdgl/finite_volume/operators.py:233-394).
+ * The entry points below are what a ctypes binding inside the reference would call
+ * instead (see INTEGRATION.md for that stub).
+ *
+ * Conventions
+ *   - plain C types only; every pointer argument is a caller-owned HOST buffer that is
+ *     copied during the call; the handle owns all device memory.
+ *   - all quantities are dimensionless exactly as inside the reference after
+ *     TDGLSolver.__init__ (lengths in xi, A in xi*Bc2, current density in K0/4).
+ *   - complex arrays are interleaved (re, im) doubles, i.e. numpy complex128.
+ *   - index arrays are int64 like the reference's (finite_volume/mesh.py:59-60,
+ *     edge_mesh.py:36).
+ *   - every call returns 0 on success or a TDGL_E_* code; tdgl_last_error() gives text.
+ *   - one host thread per handle; handles are independent (no global state).
+ */
+#ifndef TDGL_B200_H
+#define TDGL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tdgl_handle tdgl_handle;
+
+enum {
+  TDGL_OK = 0,
+  TDGL_E_STEP_FAILED = 1,  /* |psi|^2 solve failed max_solve_retries times
+                              (reference RuntimeError, solver/solver.py:478-483) */
+  TDGL_E_MU_SOLVER = 2,    /* mu solver did not reach tolerance in max iterations */
+  TDGL_E_CUDA = 3,         /* CUDA / NCCL runtime error */
+  TDGL_E_INVALID = 4       /* bad argument */
+};
+
+/* Engine knobs that have no counterpart in the reference.  Zero-initialise and set
+ * struct_size = sizeof(tdgl_config); fields left 0 take the default in brackets. */
+typedef struct tdgl_config {
+  int32_t struct_size;
+  int32_t device;           /* CUDA device ordinal [0] */
+  double mu_rtol;           /* ||r|| <= mu_rtol * ||b|| for the mu solve [1e-10] */
+  int32_t mu_max_iter;      /* CG iteration cap [500] */
+  double amg_theta;         /* strength threshold of the aggregation [0.08] */
+  int32_t amg_max_coarse;   /* stop coarsening at this size [200] */
+  int32_t use_graph;        /* 1: one CUDA graph with device-side loops per advance();
+                               2: host-driven launches (debug) [1] */
+  int32_t reorder;          /* 1: renumber sites along a Z-order curve when coordinates
+                               are given; 2: keep the caller's numbering [1] */
+  int32_t running_capacity; /* steps of running state kept per advance() [4096] */
+} tdgl_config;
+
+/* Mesh + material -> device-resident operators.  Replaces MeshOperators.__init__ +
+ * build_operators (operators.py:245-308): mu Laplacian (no fixed sites), Neumann
+ * boundary matrix, gradient, divergence; the SuperLU factorisation (operators.py:306-308)
+ * is replaced by the setup of an algebraic-multigrid preconditioner.
+ *   edges[E][2], areas[N], edge_lengths[E], dual_edge_lengths[E], directions[E][2],
+ *   boundary_edge_indices[Eb]: Mesh / EdgeMesh arrays (mesh.py:24-69, edge_mesh.py:9-42)
+ *   fixed_sites[n_fixed], fix_psi: MeshOperators(fixed_sites=, fix_psi=)  (solver.py:270-276)
+ *   sites_xy[N][2]: optional (may be NULL) coordinates, used only for memory locality
+ *   gamma, u: Layer parameters (solver.py:152-153)
+ *   probe_sites[n_probe]: device.probe_point_indices (solver.py:142)                 */
+int tdgl_create(tdgl_handle** out, int64_t n_sites, int64_t n_edges, int64_t n_boundary_edges,
+                const int64_t* edges, const double* areas, const double* edge_lengths,
+                const double* dual_edge_lengths, const double* directions,
+                const int64_t* boundary_edge_indices, const int64_t* fixed_sites,
+                int64_t n_fixed, int32_t fix_psi, const double* sites_xy, double gamma,
+                double u, const int64_t* probe_sites, int64_t n_probe,
+                const tdgl_config* config);
+
+void tdgl_destroy(tdgl_handle* h);
+
+const char* tdgl_last_error(const tdgl_handle* h);
+
+/* MeshOperators.set_link_exponents (operators.py:310-383): (re)builds the values of the
+ * covariant Laplacian and gradient from A[E][2] (dimensionless, at edge centres). */
+int tdgl_set_link_exponents(tdgl_handle* h, const double* A);
+
+/* epsilon[N] (solver.py:191-216, 644-646). */
+int tdgl_set_epsilon(tdgl_handle* h, const double* epsilon);
+
+/* mu_boundary[Eb]: the terminal current densities on boundary edges written by
+ * TDGLSolver.update_mu_boundary (solver.py:325-345). */
+int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary);
+
+/* psi[N] (complex128) and mu[N]: the `psi`, `mu` values Runner threads through update(). */
+int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu);
+
+/* The SolverOptions fields the step reads (options.py:66-89) and the controller state
+ * TDGLSolver keeps between steps (solver.py:316-320): resets tentative_dt = dt_init and
+ * clears the |psi|^2-change history. */
+int tdgl_set_stepper(tdgl_handle* h, double dt_init, double dt_max, int32_t adaptive,
+                     int32_t adaptive_window, int32_t max_solve_retries,
+                     double adaptive_time_step_multiplier);
+
+typedef struct tdgl_advance_info {
+  int64_t steps_done;      /* update() calls performed by this advance() */
+  int64_t step;            /* Runner's step index after the call */
+  double time;             /* Runner's time after the call */
+  double dt;               /* dt used by the last step (SolverResult.dt) */
+  double tentative_dt;     /* TDGLSolver.tentative_dt for the next step */
+  int32_t finished;        /* 1 if time >= t_end was reached (Runner breaks) */
+  int32_t status;          /* TDGL_OK or the failure that stopped the stepping */
+  int64_t failed_step;     /* step index at which status was raised */
+  double failed_dt;        /* dt at that point (for the reference's error text) */
+  int64_t retries;         /* total dt-shrinking retries in this call */
+  int64_t mu_iterations;   /* total CG iterations in this call */
+  double mu_rel_residual;  /* ||r||/||b|| of the last mu solve */
+} tdgl_advance_info;
+
+/* Runs the loop of Runner._run_stage (runner.py:379-433) on the device: up to
+ * `max_steps` calls of update(); after each one stops if time >= t_end (the reference
+ * performs that last update and then breaks), else dt <- new_dt, time += dt, step += 1.
+ * `step`/`time` are the Runner's current values (they restart at 0 for each stage,
+ * runner.py:294-318, while the solver's adaptive history persists). */
+int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, double time,
+                 tdgl_advance_info* info);
+
+/* Current psi[N] (complex128) and mu[N]. */
+int tdgl_get_state(tdgl_handle* h, double* psi, double* mu);
+
+/* Supercurrent and normal current on the edges for the current state
+ * (operators.py:385-394, solver.py:519); computed on demand (save steps). */
+int tdgl_get_currents(tdgl_handle* h, double* supercurrent, double* normal_current);
+
+/* Running state of the last advance(): dt[k], mu[n_probe][k], theta[n_probe][k] for
+ * k < steps_done (solver.py:690-694); `capacity` is the row stride of the outputs. */
+int tdgl_get_running(tdgl_handle* h, int64_t capacity, double* dt, double* mu_probe,
+                     double* theta_probe);
+
+/* ---- single operators, for parity tests and microbenchmarks ------------------------- */
+
+/* y = psi_laplacian @ x  (complex CSR SpMV, fixed rows are identity; solver.py:426) */
+int tdgl_op_psi_laplacian(tdgl_handle* h, const double* x, double* y);
+/* TDGLSolver.solve_for_psi_squared (solver.py:383-439) for one dt; returns new psi and
+ * the |psi|^2 root; *failed = 1 where the reference would return None. */
+int tdgl_op_psi_step(tdgl_handle* h, const double* psi, const double* mu, double dt,
+                     double* psi_out, double* sq_out, int32_t* failed);
+/* rhs = divergence @ supercurrent(psi) - mu_boundary_laplacian @ mu_boundary
+ * (solver.py:507-510). */
+int tdgl_op_mu_rhs(tdgl_handle* h, const double* psi, double* rhs);
+/* y = mu_laplacian @ x (operators.py:285). */
+int tdgl_op_mu_laplacian(tdgl_handle* h, const double* x, double* y);
+/* Solve mu_laplacian @ mu = rhs (solver.py:513-516) to mu_rtol; the result has
+ * area-weighted mean zero.  *iterations / *rel_residual may be NULL. */
+int tdgl_op_mu_solve(tdgl_handle* h, const double* rhs, double* mu, int32_t* iterations,
+                     double* rel_residual);
+
+/* Time `reps` back-to-back launches of one kernel with CUDA events on the engine's
+ * stream; which: 0 psi step (fused SpMV + update), 1 mu rhs, 2 mu SpMV (A p with dot),
+ * 3 one V-cycle, 4 one full mu solve from a zero guess.  Returns mean milliseconds. */
+int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, double* mean_ms);
+
+/* Sizes and setup facts: [0] N, [1] E, [2] nnz of a site operator, [3] AMG levels,
+ * [4] sum of level nnz, [5] coarsest size, [6] kernels launched so far (host count),
+ * [7] graph mode actually in use (1/2). */
+int tdgl_get_info(tdgl_handle* h, int64_t* out, int32_t n);
+
+/* ---- host-only helpers (no GPU needed): used by CPU tests ---------------------------- */
+
+/* Builds the AMG hierarchy on the host and reports per-level sizes; optionally applies
+ * `n_cycles` of preconditioned CG on the host to rhs to validate the hierarchy.
+ * level_rows/level_nnz have room for 32 entries. */
+int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
+                        const double* edge_lengths, const double* dual_edge_lengths,
+                        double theta, int32_t max_coarse, int32_t* n_levels,
+                        int64_t* level_rows, int64_t* level_nnz, const double* rhs,
+                        double* x, int32_t max_iter, double rtol, int32_t* iterations);
+
+const char* tdgl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDGL_B200_H */

@@ -1,0 +1,221 @@
+// Host side of the engine: device-memory ownership, operator upload, launch sequences and
+// the CUDA-graph form of Runner._run_stage (reference tdgl/solver/runner.py:379-433).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "amg_setup.h"
+#include "kernels.cuh"
+
+namespace tdgl {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define TDGL_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      char buf__[512];                                                                    \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call,                       \
+               cudaGetErrorString(err__), __FILE__, __LINE__);                            \
+      throw ::tdgl::CudaError(buf__);                                                     \
+    }                                                                                     \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) TDGL_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void zero(cudaStream_t s) { if (n) TDGL_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    if (count > n) alloc(count);
+    if (count) TDGL_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void download(T* h, size_t count, cudaStream_t s) const {
+    if (count) TDGL_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+};
+
+struct CsrView {
+  int rows = 0, lpr = 8;
+  const int* ptr = nullptr;
+  const int* idx = nullptr;
+  const double* val = nullptr;
+};
+
+struct DevCsr {
+  int rows = 0, cols = 0, lpr = 8;
+  int64_t nnz = 0;
+  DevBuf<int> ptr, idx;
+  DevBuf<double> val;
+  CsrView view() const { return CsrView{rows, lpr, ptr.p, idx.p, val.p}; }
+};
+
+struct DevLevel {
+  int n = 0;
+  DevCsr A, P, R;       // P: n x n_coarse, R: n_coarse x n
+  DevBuf<double> dinv;
+  double omega = 0.0;   // Jacobi weight (4/3) / rho(D^-1 A)
+  DevBuf<double> b, x, y, r;  // work vectors (level 0 aliases CG vectors instead of b / y)
+};
+
+inline int pick_lpr(int64_t nnz, int64_t rows) {
+  const double avg = rows ? static_cast<double>(nnz) / rows : 0.0;
+  if (avg <= 3.0) return 4;
+  if (avg <= 8.5) return 8;
+  if (avg <= 18.0) return 16;
+  return 32;
+}
+
+struct Config {
+  int device = 0;
+  double mu_rtol = 1e-10;
+  int mu_max_iter = 500;
+  double amg_theta = 0.08;
+  int amg_max_coarse = 200;
+  int use_graph = 1;
+  int reorder = 1;
+  int running_capacity = 4096;
+};
+
+class Engine {
+ public:
+  Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t* edges,
+         const double* areas, const double* edge_len, const double* dual_len,
+         const double* directions, const int64_t* bedge_idx, const int64_t* fixed_sites,
+         int64_t n_fixed, int fix_psi, const double* sites_xy, double gamma, double u,
+         const int64_t* probe_sites, int64_t n_probe, const Config& cfg);
+  ~Engine();
+
+  void set_link_exponents(const double* A);
+  void set_epsilon(const double* eps);
+  void set_mu_boundary(const double* mub);
+  void set_state(const double* psi, const double* mu);
+  void set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
+                   double multiplier);
+  struct AdvanceInfo {
+    int64_t steps_done, step; double time, dt, tentative_dt; int finished, status;
+    int64_t failed_step; double failed_dt; int64_t retries, mu_iterations; double mu_rel_residual;
+  };
+  AdvanceInfo advance(int64_t max_steps, double t_end, int64_t step, double time);
+  void get_state(double* psi, double* mu);
+  void get_currents(double* js, double* jn);
+  void get_running(int64_t capacity, double* dt, double* mu_probe, double* theta_probe);
+
+  void op_psi_laplacian(const double* x, double* y);
+  void op_psi_step(const double* psi, const double* mu, double dt, double* psi_out,
+                   double* sq_out, int* failed);
+  void op_mu_rhs(const double* psi, double* rhs);
+  void op_mu_laplacian(const double* x, double* y);
+  void op_mu_solve(const double* rhs, double* mu, int* iterations, double* rel_res);
+  double time_kernel(int which, int reps);
+  void get_info(int64_t* out, int n);
+
+  std::string last_error;
+
+ private:
+  // ---- sizes / host copies --------------------------------------------------------------
+  Config cfg_;
+  int N_ = 0, E_ = 0, Eb_ = 0, nprobe_ = 0;
+  int64_t nnz_ = 0;
+  double gamma_, u_, total_area_ = 0.0;
+  std::vector<int> perm_;      // internal index -> caller index
+  std::vector<int> inv_perm_;  // caller index -> internal index
+  std::vector<double> h_dirs_; // [E,2] caller edge order
+  int64_t launches_ = 0;
+  int graph_mode_ = 2;
+  int64_t last_steps_done_ = 0;
+
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+
+  // ---- site operators (shared structure) --------------------------------------------------
+  DevBuf<int> ptr_, idx_, eidx_;
+  DevBuf<signed char> head_;
+  DevBuf<double2> lval_;           // covariant Laplacian values (all rows kept)
+  DevBuf<unsigned char> fixed_;    // rows the reference replaces by identity
+  DevBuf<double> areas_, eps_, bterm_;
+  int lpr0_ = 8;
+  // ---- edges (caller edge order, internal site indices) -----------------------------------
+  DevBuf<int> e0_, e1_;
+  DevBuf<double> elen_, weight_, theta_;
+  DevBuf<int> be0_, be1_;
+  DevBuf<double> blen_, mub_;
+  // ---- state ------------------------------------------------------------------------------
+  DevBuf<double2> psi_[2];
+  DevBuf<double> mu_;
+  DevBuf<int> dperm_, probes_;
+  DevBuf<double> run_dt_, run_mu_, run_theta_;
+  // ---- mu solver ----------------------------------------------------------------------------
+  std::vector<DevLevel> levels_;
+  DevBuf<double> coarse_inv_;
+  int nc_ = 0;
+  int64_t amg_nnz_ = 0;
+  DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_;
+  DevBuf<double> partials_;
+  DevBuf<unsigned int> counter_;
+  // ---- scratch for IO ------------------------------------------------------------------------
+  DevBuf<double2> tmp_c_;
+  DevBuf<double> tmp_d_, tmp_d2_, tmp_e_, tmp_e2_;
+  // ---- control ------------------------------------------------------------------------------
+  DevBuf<Ctl> ctl_;
+  Ctl* h_ctl_ = nullptr;  // pinned mirror
+  cudaGraph_t graph_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  cudaGraphConditionalHandle h_step_ = 0, h_psi_ = 0, h_cg_ = 0;
+
+  // ---- launch sequences ------------------------------------------------------------------
+  int grid_rows(int rows, int lpr) const { return (static_cast<int64_t>(rows) * lpr + kBlock - 1) / kBlock; }
+  int grid_flat(int n) const {
+    int g = (n + kBlock - 1) / kBlock;
+    return g < 1 ? 1 : (g > 1184 ? 1184 : g);  // 148 SMs x 8 resident blocks
+  }
+  void upload_csr(const HostCsr<double>& h, DevCsr& d);
+  void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);
+  void launch_plain(const CsrView& A, const double* x, double* y, bool add);
+  void launch_presmooth(const CsrView& A, const double* dinv, double omega, const double* b,
+                        double* x, double* r);
+  void launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
+                     const double* x, double* y, const double* w, double* dot_out);
+  void launch_residual(const CsrView& A, const double* x, const double* b, double* r, double* rr);
+  void enqueue_vcycle(const double* r_in, double* z_out, double* rz_out);
+  void enqueue_psi_step(double* sq_out, double dt_override);
+  void enqueue_mu_rhs(double* rhs_raw);
+  void enqueue_cg_iteration(cudaGraphConditionalHandle cond);
+  void enqueue_mu_finish();
+  void host_solve_loop();   // host-driven CG loop on the current b/r
+  void build_graph();
+  void sync_ctl_to_host();
+  void push_ctl();
+  DevBuf<double> aval_;  // level-0 mu matrix values; structure shared with ptr_/idx_
+  CsrView A0() const { return CsrView{N_, lpr0_, ptr_.p, idx_.p, aval_.p}; }
+  CsrView levelA(size_t l) const { return l == 0 ? A0() : levels_[l].A.view(); }
+};
+
+}  // namespace tdgl

@@ -1,0 +1,187 @@
+// Host-side CSR containers and the setup-time algebra of the engine (no CUDA here).
+//
+// Everything in this header runs once per tdgl_create(): building the finite-volume
+// operators from the mesh arrays (reference tdgl/finite_volume/operators.py:59-230) and
+// the smoothed-aggregation hierarchy that preconditions the mu solve.  The per-step work
+// is in kernels.cuh.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+#include <vector>
+
+namespace tdgl {
+
+template <typename T>
+struct HostCsr {
+  int64_t rows = 0, cols = 0;
+  std::vector<int32_t> ptr;  // rows + 1
+  std::vector<int32_t> idx;  // nnz, sorted within a row
+  std::vector<T> val;        // nnz
+  int64_t nnz() const { return static_cast<int64_t>(idx.size()); }
+};
+
+// Site adjacency of the triangulation: for every site the incident edges, sorted by
+// neighbour index, plus a leading diagonal slot.  All site operators (covariant
+// Laplacian, mu Laplacian, divergence) share this one structure.
+struct SiteGraph {
+  int64_t n = 0;
+  std::vector<int32_t> ptr;   // n + 1
+  std::vector<int32_t> nbr;   // neighbour site (the row itself for the diagonal slot)
+  std::vector<int32_t> edge;  // edge index of the slot (-1 for the diagonal slot)
+  std::vector<int8_t> head;   // 1 if the row is edges[e,0] (link variable U_e), 0 if
+                              // edges[e,1] (conj U_e); 0 on the diagonal slot
+};
+
+inline SiteGraph build_site_graph(int64_t n, int64_t n_edges, const int32_t* e0,
+                                  const int32_t* e1) {
+  SiteGraph g;
+  g.n = n;
+  g.ptr.assign(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) g.ptr[i + 1] = 1;  // diagonal slot
+  for (int64_t e = 0; e < n_edges; ++e) {
+    if (e0[e] < 0 || e0[e] >= n || e1[e] < 0 || e1[e] >= n || e0[e] == e1[e])
+      throw std::invalid_argument("edge index out of range");
+    g.ptr[e0[e] + 1]++;
+    g.ptr[e1[e] + 1]++;
+  }
+  for (int64_t i = 0; i < n; ++i) g.ptr[i + 1] += g.ptr[i];
+  const int64_t nnz = g.ptr[n];
+  g.nbr.resize(nnz);
+  g.edge.resize(nnz);
+  g.head.resize(nnz);
+  std::vector<int32_t> fill(g.ptr.begin(), g.ptr.end() - 1);
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t k = fill[i]++;
+    g.nbr[k] = static_cast<int32_t>(i);
+    g.edge[k] = -1;
+    g.head[k] = 0;
+  }
+  for (int64_t e = 0; e < n_edges; ++e) {
+    int32_t k = fill[e0[e]]++;
+    g.nbr[k] = e1[e];
+    g.edge[k] = static_cast<int32_t>(e);
+    g.head[k] = 1;
+    k = fill[e1[e]]++;
+    g.nbr[k] = e0[e];
+    g.edge[k] = static_cast<int32_t>(e);
+    g.head[k] = 0;
+  }
+  // sort every row by neighbour index (diagonal lands in its natural position)
+  std::vector<int32_t> order;
+  std::vector<int32_t> tn, te;
+  std::vector<int8_t> th;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t b = g.ptr[i], len = g.ptr[i + 1] - b;
+    order.resize(len);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(),
+              [&](int32_t a, int32_t c) { return g.nbr[b + a] < g.nbr[b + c]; });
+    tn.resize(len); te.resize(len); th.resize(len);
+    for (int32_t k = 0; k < len; ++k) {
+      tn[k] = g.nbr[b + order[k]]; te[k] = g.edge[b + order[k]]; th[k] = g.head[b + order[k]];
+    }
+    for (int32_t k = 0; k < len; ++k) {
+      if (k > 0 && tn[k] == tn[k - 1]) throw std::invalid_argument("duplicate edge");
+      g.nbr[b + k] = tn[k]; g.edge[b + k] = te[k]; g.head[b + k] = th[k];
+    }
+  }
+  return g;
+}
+
+// y = A x
+template <typename T>
+inline void spmv(const HostCsr<T>& A, const std::vector<T>& x, std::vector<T>& y) {
+  y.resize(A.rows);
+  for (int64_t i = 0; i < A.rows; ++i) {
+    T s = T(0);
+    for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) s += A.val[k] * x[A.idx[k]];
+    y[i] = s;
+  }
+}
+
+template <typename T>
+inline HostCsr<T> transpose(const HostCsr<T>& A) {
+  HostCsr<T> B;
+  B.rows = A.cols; B.cols = A.rows;
+  B.ptr.assign(B.rows + 1, 0);
+  for (int64_t k = 0; k < A.nnz(); ++k) B.ptr[A.idx[k] + 1]++;
+  for (int64_t i = 0; i < B.rows; ++i) B.ptr[i + 1] += B.ptr[i];
+  B.idx.resize(A.nnz()); B.val.resize(A.nnz());
+  std::vector<int32_t> fill(B.ptr.begin(), B.ptr.end() - 1);
+  for (int64_t i = 0; i < A.rows; ++i)
+    for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+      int32_t d = fill[A.idx[k]]++;
+      B.idx[d] = static_cast<int32_t>(i);
+      B.val[d] = A.val[k];
+    }
+  return B;  // rows come out sorted because i ascends
+}
+
+// C = A * B (Gustavson, dense accumulator over B.cols); rows of C sorted.
+template <typename T>
+inline HostCsr<T> spgemm(const HostCsr<T>& A, const HostCsr<T>& B) {
+  if (A.cols != B.rows) throw std::invalid_argument("spgemm shape");
+  HostCsr<T> C;
+  C.rows = A.rows; C.cols = B.cols;
+  C.ptr.assign(C.rows + 1, 0);
+  std::vector<T> acc(B.cols, T(0));
+  std::vector<int32_t> mark(B.cols, -1), touched;
+  for (int64_t i = 0; i < A.rows; ++i) {
+    touched.clear();
+    for (int32_t ka = A.ptr[i]; ka < A.ptr[i + 1]; ++ka) {
+      const int32_t j = A.idx[ka];
+      const T a = A.val[ka];
+      for (int32_t kb = B.ptr[j]; kb < B.ptr[j + 1]; ++kb) {
+        const int32_t c = B.idx[kb];
+        if (mark[c] != i) { mark[c] = static_cast<int32_t>(i); acc[c] = T(0); touched.push_back(c); }
+        acc[c] += a * B.val[kb];
+      }
+    }
+    std::sort(touched.begin(), touched.end());
+    for (int32_t c : touched) { C.idx.push_back(c); C.val.push_back(acc[c]); }
+    C.ptr[i + 1] = static_cast<int32_t>(C.idx.size());
+  }
+  return C;
+}
+
+template <typename T>
+inline std::vector<T> diagonal(const HostCsr<T>& A) {
+  std::vector<T> d(A.rows, T(0));
+  for (int64_t i = 0; i < A.rows; ++i)
+    for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k)
+      if (A.idx[k] == i) d[i] = A.val[k];
+  return d;
+}
+
+// Largest eigenvalue of D^-1 A by power iteration (deterministic start vector).
+inline double rho_dinv_a(const HostCsr<double>& A, const std::vector<double>& d, int iters = 30) {
+  const int64_t n = A.rows;
+  std::vector<double> x(n), y(n);
+  uint64_t s = 0x9E3779B97F4A7C15ull;
+  for (int64_t i = 0; i < n; ++i) {  // splitmix64 -> uniform(-1, 1)
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    x[i] = (static_cast<double>(z >> 11) / 9007199254740992.0) * 2.0 - 1.0;
+  }
+  double lam = 2.0;
+  for (int it = 0; it < iters; ++it) {
+    spmv(A, x, y);
+    double ny = 0, nx = 0;
+    for (int64_t i = 0; i < n; ++i) { y[i] /= d[i]; ny += y[i] * y[i]; nx += x[i] * x[i]; }
+    if (ny == 0 || nx == 0) return 2.0;
+    lam = std::sqrt(ny / nx);
+    const double inv = 1.0 / std::sqrt(ny);
+    for (int64_t i = 0; i < n; ++i) x[i] = y[i] * inv;
+  }
+  return lam;
+}
+
+}  // namespace tdgl

@@ -1,0 +1,797 @@
+// Device kernels of the TDGL stepper (sm_100a).  Everything here is HBM-bound fp64 /
+// complex128 streaming over CSR row windows: no dense contraction, hence no tensor cores.
+//
+// Conventions
+//  * all per-step scalars (dt, CG alpha/beta, loop conditions) live in the device-resident
+//    control block `Ctl`, so the same kernels run from a host-driven launch sequence or
+//    from inside one CUDA graph with device-side WHILE loops (no host round trips);
+//  * reductions are deterministic: per-block partials, last block to finish adds them in
+//    a fixed order (the reference is bitwise deterministic run to run);
+//  * every kernel returns immediately once `ctl->status != 0`.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tdgl {
+
+constexpr int kMaxWindow = 1024;   // adaptive_window cap
+constexpr int kMaxProbes = 64;
+constexpr int kBlock = 256;
+constexpr int kMaxPartials = 8192;  // grid-size cap of reducing kernels
+
+struct Ctl {
+  // --- configuration (host writes) -----------------------------------------------------
+  double dt_init, dt_max, multiplier, gamma, u, mu_rtol;
+  int adaptive, window, max_retries, cg_max_iter;
+  int n_probe, running_capacity;
+  // --- Runner state ----------------------------------------------------------------------
+  double time, t_end, dt, tentative_dt;
+  long long step;
+  long long steps_left;
+  long long steps_done;
+  int finished, status;
+  long long failed_step;
+  double failed_dt;
+  // --- psi step ---------------------------------------------------------------------------
+  int cur;            // index of the buffer holding the current psi
+  int retries;
+  int psi_go;         // loop condition of the dt-retry loop
+  int disc_flag;
+  unsigned long long max_dpsi_bits;
+  long long total_retries;
+  // --- adaptive controller (solver.py:698-707) -------------------------------------------
+  double dpsi_hist[kMaxWindow];
+  long long n_hist;
+  // --- CG ---------------------------------------------------------------------------------
+  double rz_new, rz_prev, pAp, rr, bb;
+  int cg_it, cg_go;
+  long long total_cg_it;
+  int step_go;
+  // --- scratch for means ------------------------------------------------------------------
+  double mu_mean;
+};
+
+// ------------------------------------------------------------------------------------------
+// helpers
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int W>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, W);
+  return v;
+}
+
+// Block-wide sum of `v` (every thread contributes); result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double* smem /* >= 32 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double t = 0.0;
+  if (warp == 0) {
+    t = (lane < nw) ? smem[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;
+}
+
+// Deterministic grid reduction.  Each block calls this with its partial (thread 0's value
+// is used); returns true in ALL threads of the last block to arrive, with *total holding
+// the sum of all partials added in block order.  `counter` must be zero on entry and is
+// re-armed on exit.
+__device__ __forceinline__ bool grid_sum_last(double partial, double* partials,
+                                              unsigned int* counter, double* smem,
+                                              double* total) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = partial;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double acc = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+    acc += reinterpret_cast<volatile double*>(partials)[i];
+  acc = block_sum(acc, smem);
+  if (threadIdx.x == 0) {
+    *total = acc;
+    *counter = 0u;
+  }
+  return true;
+}
+
+#define TDGL_COND_ARG cudaGraphConditionalHandle
+
+__device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
+  if (h != 0) cudaGraphSetConditional(h, v ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic CSR kernels, LPR lanes cooperate on one row (warp-shuffle reduction per row)
+
+// y = A x ; optionally dot(x, y) -> *dot_out (deterministic)
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_spmv(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+       const int* __restrict__ idx, const double* __restrict__ val,
+       const double* __restrict__ x, double* __restrict__ y, double* partials,
+       unsigned int* counter, double* dot_out) {
+  __shared__ double red[32];
+  if (ctl->status != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < n) {
+    const int b = ptr[row], e = ptr[row + 1];
+    for (int k = b + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
+  }
+  s = group_sum<LPR>(s);
+  double d = 0.0;
+  if (row < n && lane == 0) {
+    y[row] = s;
+    d = s * x[row];
+  }
+  if (dot_out != nullptr) {
+    const double bs = block_sum(d, red);
+    double total;
+    if (grid_sum_last(bs, partials, counter, red, &total)) {
+      if (threadIdx.x == 0) *dot_out = total;
+    }
+  }
+}
+
+// r = b - A x ; optionally ||r||^2 -> *rr_out
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_residual(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+           const int* __restrict__ idx, const double* __restrict__ val,
+           const double* __restrict__ x, const double* __restrict__ b,
+           double* __restrict__ r, double* partials, unsigned int* counter, double* rr_out) {
+  __shared__ double red[32];
+  if (ctl->status != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < n) {
+    const int bg = ptr[row], e = ptr[row + 1];
+    for (int k = bg + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
+  }
+  s = group_sum<LPR>(s);
+  double d = 0.0;
+  if (row < n && lane == 0) {
+    const double ri = b[row] - s;
+    r[row] = ri;
+    d = ri * ri;
+  }
+  if (rr_out != nullptr) {
+    const double bs = block_sum(d, red);
+    double total;
+    if (grid_sum_last(bs, partials, counter, red, &total)) {
+      if (threadIdx.x == 0) *rr_out = total;
+    }
+  }
+}
+
+// Pre-smoothing from a zero guess fused with the residual:
+//   x = omega D^-1 b ;  r = b - A x
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_presmooth_residual(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+                     const int* __restrict__ idx, const double* __restrict__ val,
+                     const double* __restrict__ dinv, double omega,
+                     const double* __restrict__ b, double* __restrict__ x,
+                     double* __restrict__ r) {
+  if (ctl->status != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < n) {
+    const int bg = ptr[row], e = ptr[row + 1];
+    for (int k = bg + lane; k < e; k += LPR) {
+      const int j = idx[k];
+      s += val[k] * (omega * __ldg(dinv + j) * __ldg(b + j));
+    }
+  }
+  s = group_sum<LPR>(s);
+  if (row < n && lane == 0) {
+    const double bi = b[row];
+    x[row] = omega * dinv[row] * bi;
+    r[row] = bi - s;
+  }
+}
+
+// Weighted-Jacobi sweep  y = x + omega D^-1 (b - A x) ; optionally dot(w, y) -> *dot_out
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_jacobi(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+         const int* __restrict__ idx, const double* __restrict__ val,
+         const double* __restrict__ dinv, double omega, const double* __restrict__ b,
+         const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ w,
+         double* partials, unsigned int* counter, double* dot_out) {
+  __shared__ double red[32];
+  if (ctl->status != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < n) {
+    const int bg = ptr[row], e = ptr[row + 1];
+    for (int k = bg + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
+  }
+  s = group_sum<LPR>(s);
+  double d = 0.0;
+  if (row < n && lane == 0) {
+    const double yi = x[row] + omega * dinv[row] * (b[row] - s);
+    y[row] = yi;
+    if (w != nullptr) d = w[row] * yi;
+  }
+  if (dot_out != nullptr) {
+    const double bs = block_sum(d, red);
+    double total;
+    if (grid_sum_last(bs, partials, counter, red, &total)) {
+      if (threadIdx.x == 0) *dot_out = total;
+    }
+  }
+}
+
+// y (+)= A x   (restriction: y = R r ; prolongation: x_fine += P x_coarse)
+template <int LPR, bool ADD>
+__global__ void __launch_bounds__(kBlock)
+k_spmv_plain(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+             const int* __restrict__ idx, const double* __restrict__ val,
+             const double* __restrict__ x, double* __restrict__ y) {
+  if (ctl->status != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < n) {
+    const int bg = ptr[row], e = ptr[row + 1];
+    for (int k = bg + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
+  }
+  s = group_sum<LPR>(s);
+  if (row < n && lane == 0) {
+    if (ADD) y[row] += s; else y[row] = s;
+  }
+}
+
+// Coarsest level: x = Minv b with a dense row-major nc x nc matrix; one warp per row.
+__global__ void __launch_bounds__(kBlock)
+k_dense_matvec(const Ctl* __restrict__ ctl, int nc, const double* __restrict__ M,
+               const double* __restrict__ b, double* __restrict__ x) {
+  if (ctl->status != 0) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nc) return;
+  const double* row = M + static_cast<size_t>(warp) * nc;
+  double s = 0.0;
+  for (int j = lane; j < nc; j += 32) s += row[j] * b[j];
+  s = warp_sum(s);
+  if (lane == 0) x[warp] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// CG vector kernels
+
+// p = z + beta p   (beta = rz_new / rz_prev, 0 on the first iteration)
+__global__ void __launch_bounds__(kBlock)
+k_cg_direction(const Ctl* __restrict__ ctl, int n, const double* __restrict__ z,
+               double* __restrict__ p) {
+  if (ctl->status != 0) return;
+  const double beta = (ctl->cg_it == 0) ? 0.0 : ctl->rz_new / ctl->rz_prev;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = z[i] + beta * p[i];
+}
+
+// alpha = rz_new / pAp ; x += alpha p ; r -= alpha Ap ; rr = ||r||^2 ;
+// last block: bookkeeping + loop condition of the CG loop.
+__global__ void __launch_bounds__(kBlock)
+k_cg_update(Ctl* ctl, int n, const double* __restrict__ p, const double* __restrict__ Ap,
+            double* __restrict__ x, double* __restrict__ r, double* partials,
+            unsigned int* counter, cudaGraphConditionalHandle cond) {
+  __shared__ double red[32];
+  if (ctl->status != 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) set_cond(cond, 0);
+    return;
+  }
+  const double alpha = ctl->rz_new / ctl->pAp;
+  double d = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    d += ri * ri;
+  }
+  const double bs = block_sum(d, red);
+  double total;
+  if (grid_sum_last(bs, partials, counter, red, &total)) {
+    if (threadIdx.x == 0) {
+      ctl->rr = total;
+      ctl->rz_prev = ctl->rz_new;
+      const int it = ctl->cg_it + 1;
+      ctl->cg_it = it;
+      ctl->total_cg_it += 1;
+      const double tol2 = ctl->mu_rtol * ctl->mu_rtol * ctl->bb;
+      int go = (total > tol2) ? 1 : 0;
+      if (!(total == total)) {  // NaN: breakdown
+        ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
+      } else if (go && it >= ctl->cg_max_iter) {
+        ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
+      }
+      ctl->cg_go = go;
+      set_cond(cond, go);
+    }
+  }
+}
+
+// Decide whether the CG loop has to run at all (warm start may already satisfy the
+// tolerance) and arm its counters.
+__global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int go = 0;
+  if (ctl->status == 0) {
+    const double tol2 = ctl->mu_rtol * ctl->mu_rtol * ctl->bb;
+    go = (ctl->rr > tol2) ? 1 : 0;
+    if (!(ctl->rr == ctl->rr) || !(ctl->bb == ctl->bb)) {
+      ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
+    }
+  }
+  ctl->cg_it = 0;
+  ctl->cg_go = go;
+  set_cond(cond, go);
+}
+
+// ------------------------------------------------------------------------------------------
+// psi step: fused complex CSR SpMV (covariant Laplacian) + closed-form |psi|^2 update
+// (reference TDGLSolver.solve_for_psi_squared, tdgl/solver/solver.py:418-438)
+
+struct PsiOut {
+  double2 psi;
+  double sq;
+  int failed;
+};
+
+__device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu, double eps,
+                                             double gamma, double u, double dt) {
+  // U = exp(-i mu dt)
+  double s, c;
+  sincos(-mu * dt, &s, &c);
+  const double2 U = make_double2(c, s);
+  const double abs2 = psi.x * psi.x + psi.y * psi.y;
+  // z = U * gamma^2 / 2 * psi
+  const double g2h = gamma * gamma / 2.0;
+  const double2 Ug = make_double2(U.x * g2h, U.y * g2h);
+  const double2 z = make_double2(Ug.x * psi.x - Ug.y * psi.y, Ug.x * psi.y + Ug.y * psi.x);
+  // w = z |psi|^2 + U (psi + dt/u sqrt(1 + gamma^2 |psi|^2) ((eps - |psi|^2) psi + L psi))
+  const double f = (dt / u) * sqrt(1.0 + gamma * gamma * abs2);
+  const double e = eps - abs2;
+  const double2 inner = make_double2(psi.x + f * (e * psi.x + lap.x),
+                                     psi.y + f * (e * psi.y + lap.y));
+  const double2 w = make_double2(z.x * abs2 + (U.x * inner.x - U.y * inner.y),
+                                 z.y * abs2 + (U.x * inner.y + U.y * inner.x));
+  const double cc = w.x * z.x + w.y * z.y;
+  const double two_c_1 = 2.0 * cc + 1.0;
+  const double w2 = w.x * w.x + w.y * w.y;
+  const double z2 = z.x * z.x + z.y * z.y;
+  const double disc = two_c_1 * two_c_1 - 4.0 * z2 * w2;
+  PsiOut o;
+  // the reference gives up on disc < 0 or any floating-point error (solver.py:420-436)
+  o.failed = !(disc >= 0.0) || !isfinite(w2) || !isfinite(disc);
+  const double sq = (2.0 * w2) / (two_c_1 + sqrt(disc));
+  o.sq = sq;
+  o.psi = make_double2(w.x - z.x * sq, w.y - z.y * sq);
+  if (!o.failed && !(isfinite(sq) && isfinite(o.psi.x) && isfinite(o.psi.y))) o.failed = 1;
+  return o;
+}
+
+// One block covers kBlock/LPR rows.  LPR lanes gather one row of L psi; the pointwise
+// update is then done by one thread per row (full lanes) after a shared-memory handoff.
+//   fixed[i] != 0 marks rows that the reference replaces by the identity
+//   (operators.py:170-184): there (L psi)_i = psi_i.
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_psi_step(Ctl* ctl, int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+           const double2* __restrict__ lval, const unsigned char* __restrict__ fixed,
+           const double2* __restrict__ psi_buf0, const double2* __restrict__ psi_buf1,
+           double2* out_buf0, double2* out_buf1, const double* __restrict__ mu,
+           const double* __restrict__ eps, double* __restrict__ sq_out /* may be null */,
+           double dt_override /* < 0: use ctl->dt */) {
+  constexpr int ROWS = kBlock / LPR;
+  __shared__ double2 s_lap[ROWS];
+  __shared__ int s_flag;
+  __shared__ double s_max[32];
+  if (ctl->status != 0) return;
+  const int cur = ctl->cur;
+  const double2* __restrict__ psi = cur ? psi_buf1 : psi_buf0;
+  double2* __restrict__ out = cur ? out_buf0 : out_buf1;
+  const double dt = dt_override >= 0.0 ? dt_override : ctl->dt;
+  const int row0 = blockIdx.x * ROWS;
+  const int lrow = threadIdx.x / LPR;
+  const int row = row0 + lrow;
+  const int lane = threadIdx.x % LPR;
+  if (threadIdx.x == 0) s_flag = 0;
+  double sx = 0.0, sy = 0.0;
+  if (row < n) {
+    const int b = ptr[row], e = ptr[row + 1];
+    for (int k = b + lane; k < e; k += LPR) {
+      const double2 v = lval[k];
+      const double2 x = psi[idx[k]];
+      sx += v.x * x.x - v.y * x.y;
+      sy += v.x * x.y + v.y * x.x;
+    }
+  }
+  sx = group_sum<LPR>(sx);
+  sy = group_sum<LPR>(sy);
+  if (lane == 0) s_lap[lrow] = make_double2(sx, sy);
+  __syncthreads();
+  double dmax = 0.0;
+  int failed = 0;
+  if (threadIdx.x < ROWS) {
+    const int i = row0 + threadIdx.x;
+    if (i < n) {
+      const double2 p = psi[i];
+      double2 lap = s_lap[threadIdx.x];
+      if (fixed[i]) lap = p;
+      const PsiOut o = psi_update(p, lap, mu[i], eps[i], ctl->gamma, ctl->u, dt);
+      out[i] = o.psi;
+      if (sq_out != nullptr) sq_out[i] = o.sq;
+      failed = o.failed;
+      const double d = fabs(o.sq - (p.x * p.x + p.y * p.y));
+      dmax = (d == d) ? d : 0.0;
+    }
+  }
+  // block reduction of max / any, then one atomic per block (max and or are order-free)
+  // reduce over the first ROWS threads via warp shuffles
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    failed |= __shfl_xor_sync(0xffffffffu, failed, o);
+  }
+  if (lane32 == 0 && warp < (ROWS + 31) / 32) {
+    s_max[warp] = dmax;
+    if (failed) atomicOr(&s_flag, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = s_max[0];
+    for (int wv = 1; wv < (ROWS + 31) / 32; ++wv) m = fmax(m, s_max[wv]);
+    if (m > 0.0) atomicMax(&ctl->max_dpsi_bits, (unsigned long long)__double_as_longlong(m));
+    if (s_flag) atomicOr(&ctl->disc_flag, 1);
+  }
+}
+
+// Start of TDGLSolver.update (solver.py:649-668): dt <- tentative_dt, retries <- 0.
+__global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->dt = ctl->tentative_dt;
+  ctl->retries = 0;
+  ctl->disc_flag = 0;
+  ctl->max_dpsi_bits = 0ull;
+  const int go = (ctl->status == 0) ? 1 : 0;
+  ctl->psi_go = go;
+  set_cond(cond_psi, go);
+}
+
+// adaptive_euler_step's retry logic (solver.py:475-485)
+__global__ void k_psi_control(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int go = 0;
+  if (ctl->status == 0) {
+    if (ctl->disc_flag) {
+      if (!ctl->adaptive || ctl->retries > ctl->max_retries) {
+        ctl->status = 1;
+        ctl->failed_step = ctl->step;
+        ctl->failed_dt = ctl->dt;
+      } else {
+        ctl->dt = ctl->dt * ctl->multiplier;
+        ctl->retries += 1;
+        ctl->total_retries += 1;
+        ctl->disc_flag = 0;
+        ctl->max_dpsi_bits = 0ull;
+        go = 1;
+      }
+    } else {
+      ctl->cur ^= 1;  // accept: the freshly written buffer becomes the current psi
+    }
+  }
+  ctl->psi_go = go;
+  set_cond(cond_psi, go);
+}
+
+// Right-hand side of the mu system in symmetrised form:
+//   rhs_i = (divergence @ J_s)_i - (mu_boundary_laplacian @ mu_boundary)_i
+//         = Im(conj(psi_i) (L~ psi)_i) - bterm_i          (L~: Laplacian without fixed rows)
+//   b_i   = -areas_i * rhs_i ;   r_i = b_i - (A mu)_i ;  bb = ||b||^2, rr = ||r||^2
+// (reference solve_for_observables, solver.py:507-510; identity SURVEY.md appendix A)
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_mu_rhs(Ctl* ctl, int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+         const double2* __restrict__ lval, const double* __restrict__ aval,
+         const double2* __restrict__ psi_buf0, const double2* __restrict__ psi_buf1,
+         const double* __restrict__ mu, const double* __restrict__ areas,
+         const double* __restrict__ bterm, double* __restrict__ b, double* __restrict__ r,
+         double* __restrict__ rhs_raw /* may be null: un-symmetrised rhs */,
+         double* partials, unsigned int* counter) {
+  __shared__ double red[32];
+  if (ctl->status != 0) return;
+  const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double sx = 0.0, sy = 0.0, am = 0.0;
+  if (row < n) {
+    const int bg = ptr[row], e = ptr[row + 1];
+    for (int k = bg + lane; k < e; k += LPR) {
+      const int j = idx[k];
+      const double2 v = lval[k];
+      const double2 x = psi[j];
+      sx += v.x * x.x - v.y * x.y;
+      sy += v.x * x.y + v.y * x.x;
+      am += aval[k] * __ldg(mu + j);
+    }
+  }
+  sx = group_sum<LPR>(sx);
+  sy = group_sum<LPR>(sy);
+  am = group_sum<LPR>(am);
+  double dbb = 0.0, drr = 0.0;
+  if (row < n && lane == 0) {
+    const double2 p = psi[row];
+    const double rhs = (p.x * sy - p.y * sx) - bterm[row];
+    if (rhs_raw != nullptr) rhs_raw[row] = rhs;
+    const double bi = -areas[row] * rhs;
+    const double ri = bi - am;
+    b[row] = bi;
+    r[row] = ri;
+    dbb = bi * bi;
+    drr = ri * ri;
+  }
+  // two sums through one deterministic reduction: interleave as pairs
+  const double sb = block_sum(dbb, red);
+  const double sr = block_sum(drr, red);
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = sb;
+    partials[2 * blockIdx.x + 1] = sr;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
+      a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
+    }
+    a0 = block_sum(a0, red);
+    a1 = block_sum(a1, red);
+    if (threadIdx.x == 0) {
+      ctl->bb = a0;
+      ctl->rr = a1;
+      *counter = 0u;
+    }
+  }
+}
+
+// area-weighted mean of mu (deterministic), then mu -= mean
+__global__ void __launch_bounds__(kBlock)
+k_weighted_sum(Ctl* ctl, int n, const double* __restrict__ w, const double* __restrict__ x,
+               double* partials, unsigned int* counter, double inv_total_weight) {
+  __shared__ double red[32];
+  if (ctl->status != 0) return;
+  double d = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    d += w[i] * x[i];
+  const double bs = block_sum(d, red);
+  double total;
+  if (grid_sum_last(bs, partials, counter, red, &total)) {
+    if (threadIdx.x == 0) ctl->mu_mean = total * inv_total_weight;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_shift(const Ctl* __restrict__ ctl, int n, double* __restrict__ x) {
+  if (ctl->status != 0) return;
+  const double m = ctl->mu_mean;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] -= m;
+}
+
+// End of update() + the Runner bookkeeping (solver.py:690-707, runner.py:429-433).
+// Thread p < n_probe records the probe values; thread 0 runs the controller.
+__global__ void k_step_end(Ctl* ctl, const double2* __restrict__ psi_buf0,
+                           const double2* __restrict__ psi_buf1, const double* __restrict__ mu,
+                           const int* __restrict__ probes, double* run_dt, double* run_mu,
+                           double* run_theta, cudaGraphConditionalHandle cond_step) {
+  if (blockIdx.x != 0) return;
+  if (ctl->status != 0) {
+    if (threadIdx.x == 0) { ctl->step_go = 0; set_cond(cond_step, 0); }
+    return;
+  }
+  const long long pos = ctl->steps_done;
+  const int cap = ctl->running_capacity;
+  if (pos < cap && threadIdx.x < ctl->n_probe) {
+    const double2* psi = ctl->cur ? psi_buf1 : psi_buf0;
+    const int s = probes[threadIdx.x];
+    run_mu[(size_t)threadIdx.x * cap + pos] = mu[s];
+    const double2 p = psi[s];
+    run_theta[(size_t)threadIdx.x * cap + pos] = atan2(p.y, p.x);
+  }
+  if (threadIdx.x != 0) return;
+  const double dt = ctl->dt;
+  if (pos < cap) run_dt[pos] = dt;
+  if (ctl->adaptive) {
+    const double d = __longlong_as_double((long long)ctl->max_dpsi_bits);
+    ctl->dpsi_hist[ctl->n_hist % kMaxWindow] = d;
+    ctl->n_hist += 1;
+    const int win = ctl->window;
+    if (ctl->step > win) {
+      // mean of the last `win` entries (fewer only if the history is shorter)
+      long long cnt = ctl->n_hist < win ? ctl->n_hist : win;
+      double sum = 0.0;
+      for (long long k = ctl->n_hist - cnt; k < ctl->n_hist; ++k)
+        sum += ctl->dpsi_hist[k % kMaxWindow];
+      const double mean = sum / (double)cnt;
+      const double new_dt = ctl->dt_init / fmax(1e-10, mean);
+      double t = 0.5 * (new_dt + dt);
+      t = fmin(fmax(t, 0.0), ctl->dt_max);
+      ctl->tentative_dt = t;
+    }
+  }
+  ctl->steps_done = pos + 1;
+  ctl->steps_left -= 1;
+  int go = 0;
+  if (ctl->time >= ctl->t_end) {
+    ctl->finished = 1;
+  } else {
+    ctl->time += dt;
+    ctl->step += 1;
+    go = ctl->steps_left > 0 ? 1 : 0;
+  }
+  ctl->step_go = go;
+  set_cond(cond_step, go);
+}
+
+// ------------------------------------------------------------------------------------------
+// setup / IO kernels
+
+// bterm_i = sum over boundary edges b=(i,j) of  l_b / (2 a_i) * mu_boundary[b]
+// (mu_boundary_laplacian @ mu_boundary, operators.py:188-230).  Each boundary site has
+// two boundary edges and a + b == b + a, so the atomics are order-independent.
+__global__ void k_boundary_term(int nb, const int* __restrict__ be0, const int* __restrict__ be1,
+                                const double* __restrict__ blen, const double* __restrict__ areas,
+                                const double* __restrict__ mub, double* bterm) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const double v = blen[b] * mub[b];
+  const int i = be0[b], j = be1[b];
+  atomicAdd(bterm + i, v / (2.0 * areas[i]));
+  atomicAdd(bterm + j, v / (2.0 * areas[j]));
+}
+
+// Values of the covariant Laplacian (all rows kept, see k_mu_rhs) from the link variables
+//   U_e = exp(-i A_e . d_e) ; off-diagonals w_e U_e / a_i (row = edges[e,0]) or
+//   w_e conj(U_e) / a_i (row = edges[e,1]) ; diagonal -sum w_e / a_i
+// (operators.py:149-169, 346-383).
+__global__ void k_link_values(int n, const int* __restrict__ ptr, const int* __restrict__ eidx,
+                              const signed char* __restrict__ head,
+                              const double* __restrict__ weight /* w_e */,
+                              const double* __restrict__ theta /* A_e . d_e */,
+                              const double* __restrict__ areas, double2* __restrict__ lval) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double inv_a = 1.0 / areas[row];
+  double diag = 0.0;
+  int kd = -1;
+  for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
+    const int e = eidx[k];
+    if (e < 0) { kd = k; continue; }
+    const double w = weight[e];
+    double s, c;
+    sincos(-theta[e], &s, &c);
+    if (!head[k]) s = -s;
+    lval[k] = make_double2(w * c / areas[row], w * s / areas[row]);
+    diag += -w / areas[row];
+  }
+  (void)inv_a;
+  if (kd >= 0) lval[kd] = make_double2(diag, 0.0);
+}
+
+// J_s[e] = Im(conj(psi[e0]) (U_e psi[e1] - psi[e0]) / l_e)      (operators.py:385-394)
+// J_n[e] = -(mu[e1] - mu[e0]) / l_e                              (solver.py:519, static A)
+// Edge arrays are in the caller's edge order, site indices are internal.
+__global__ void k_currents(int ne, const int* __restrict__ e0, const int* __restrict__ e1,
+                           const double* __restrict__ elen, const double* __restrict__ theta,
+                           const double2* __restrict__ psi, const double* __restrict__ mu,
+                           double* __restrict__ js, double* __restrict__ jn) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int i = e0[e], j = e1[e];
+  const double inv_l = 1.0 / elen[e];
+  double s, c;
+  sincos(-theta[e], &s, &c);
+  const double2 pi = psi[i], pj = psi[j];
+  // g = (U psi_j) * (1/l) + psi_i * (-1/l)   as the CSR gradient row computes it
+  const double gx = (c * pj.x - s * pj.y) * inv_l - pi.x * inv_l;
+  const double gy = (c * pj.y + s * pj.x) * inv_l - pi.y * inv_l;
+  js[e] = pi.x * gy - pi.y * gx;
+  jn[e] = -(mu[j] * inv_l - mu[i] * inv_l);
+}
+
+template <typename T>
+__global__ void k_gather(int n, const int* __restrict__ perm, const T* __restrict__ src,
+                         T* __restrict__ dst) {  // dst[i] = src[perm[i]]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+
+template <typename T>
+__global__ void k_scatter(int n, const int* __restrict__ perm, const T* __restrict__ src,
+                          T* __restrict__ dst) {  // dst[perm[i]] = src[i]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[perm[i]] = src[i];
+}
+
+__global__ void k_scale_neg_area(int n, const double* __restrict__ areas,
+                                 const double* __restrict__ rhs, double* __restrict__ b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = -areas[i] * rhs[i];
+}
+
+// *out = dot(a, b)   (deterministic)
+__global__ void __launch_bounds__(kBlock)
+k_dot(const Ctl* __restrict__ ctl, int n, const double* __restrict__ a,
+      const double* __restrict__ b, double* partials, unsigned int* counter, double* out) {
+  __shared__ double red[32];
+  if (ctl->status != 0) return;
+  double d = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    d += a[i] * b[i];
+  const double bs = block_sum(d, red);
+  double total;
+  if (grid_sum_last(bs, partials, counter, red, &total)) {
+    if (threadIdx.x == 0) *out = total;
+  }
+}
+
+// y = psi_laplacian @ x with the reference's fixed rows (identity)  — parity/microbench op
+template <int LPR>
+__global__ void __launch_bounds__(kBlock)
+k_psi_laplacian(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                const double2* __restrict__ lval, const unsigned char* __restrict__ fixed,
+                const double2* __restrict__ x, double2* __restrict__ y) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double sx = 0.0, sy = 0.0;
+  if (row < n) {
+    const int b = ptr[row], e = ptr[row + 1];
+    for (int k = b + lane; k < e; k += LPR) {
+      const double2 v = lval[k];
+      const double2 xv = x[idx[k]];
+      sx += v.x * xv.x - v.y * xv.y;
+      sy += v.x * xv.y + v.y * xv.x;
+    }
+  }
+  sx = group_sum<LPR>(sx);
+  sy = group_sum<LPR>(sy);
+  if (row < n && lane == 0) y[row] = fixed[row] ? x[row] : make_double2(sx, sy);
+}
+
+// y = -y / areas   (A -> mu_laplacian)
+__global__ void k_neg_div(int n, const double* __restrict__ areas, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = -y[i] / areas[i];
+}
+
+}  // namespace tdgl

@@ -1,0 +1,1131 @@
+// tdgl_b200: engine implementation + C ABI (see include/tdgl_b200.h).
+#include "../../include/tdgl_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "engine.h"
+
+namespace tdgl {
+
+// ============================================================================================
+// helpers
+
+static std::vector<int> morton_permutation(const double* xy, int64_t n) {
+  double xmin = xy[0], xmax = xy[0], ymin = xy[1], ymax = xy[1];
+  for (int64_t i = 0; i < n; ++i) {
+    xmin = std::min(xmin, xy[2 * i]); xmax = std::max(xmax, xy[2 * i]);
+    ymin = std::min(ymin, xy[2 * i + 1]); ymax = std::max(ymax, xy[2 * i + 1]);
+  }
+  const double span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-300);
+  auto spread = [](uint64_t v) {
+    v &= 0xFFFFFFFFull;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+  };
+  std::vector<std::pair<uint64_t, int>> key(n);
+  const double scale = static_cast<double>((1u << 20) - 1) / span;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t qx = static_cast<uint64_t>((xy[2 * i] - xmin) * scale);
+    const uint64_t qy = static_cast<uint64_t>((xy[2 * i + 1] - ymin) * scale);
+    key[i] = {spread(qx) | (spread(qy) << 1), static_cast<int>(i)};
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int> perm(n);
+  for (int64_t i = 0; i < n; ++i) perm[i] = key[i].second;
+  return perm;
+}
+
+void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
+  d.rows = static_cast<int>(h.rows);
+  d.cols = static_cast<int>(h.cols);
+  d.nnz = h.nnz();
+  d.lpr = pick_lpr(h.nnz(), h.rows);
+  d.ptr.upload(h.ptr, stream_);
+  d.idx.upload(h.idx, stream_);
+  d.val.upload(h.val, stream_);
+}
+
+// ============================================================================================
+// construction
+
+Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t* edges,
+               const double* areas, const double* edge_len, const double* dual_len,
+               const double* directions, const int64_t* bedge_idx, const int64_t* fixed_sites,
+               int64_t n_fixed, int fix_psi, const double* sites_xy, double gamma, double u,
+               const int64_t* probe_sites, int64_t n_probe, const Config& cfg)
+    : cfg_(cfg), gamma_(gamma), u_(u) {
+  if (n_sites < 3 || n_edges < 3) throw std::invalid_argument("mesh too small");
+  if (n_sites > 0x7FFFFFF0ll / 32 || n_edges > 0x7FFFFFF0ll / 8)
+    throw std::invalid_argument("mesh too large for 32-bit device indices");
+  if (n_probe > kMaxProbes) throw std::invalid_argument("too many probe points");
+  N_ = static_cast<int>(n_sites);
+  E_ = static_cast<int>(n_edges);
+  Eb_ = static_cast<int>(n_bedges);
+  nprobe_ = static_cast<int>(n_probe);
+
+  int ndev = 0;
+  TDGL_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg_.device < 0 || cfg_.device >= ndev) throw std::invalid_argument("bad CUDA device ordinal");
+  TDGL_CUDA(cudaSetDevice(cfg_.device));
+  TDGL_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  TDGL_CUDA(cudaEventCreate(&ev0_));
+  TDGL_CUDA(cudaEventCreate(&ev1_));
+  TDGL_CUDA(cudaMallocHost(&h_ctl_, sizeof(Ctl)));
+
+  // ---- site numbering ---------------------------------------------------------------------
+  if (cfg_.reorder == 1 && sites_xy != nullptr) {
+    perm_ = morton_permutation(sites_xy, N_);
+  } else {
+    perm_.resize(N_);
+    for (int i = 0; i < N_; ++i) perm_[i] = i;
+  }
+  inv_perm_.resize(N_);
+  for (int i = 0; i < N_; ++i) inv_perm_[perm_[i]] = i;
+
+  std::vector<int> e0(E_), e1(E_);
+  std::vector<double> w(E_), len(E_);
+  h_dirs_.assign(directions, directions + 2 * static_cast<size_t>(E_));
+  for (int e = 0; e < E_; ++e) {
+    const int64_t a = edges[2 * e], b = edges[2 * e + 1];
+    if (a < 0 || a >= N_ || b < 0 || b >= N_) throw std::invalid_argument("edge index out of range");
+    e0[e] = inv_perm_[a];
+    e1[e] = inv_perm_[b];
+    if (!(edge_len[e] > 0)) throw std::invalid_argument("non-positive edge length");
+    len[e] = edge_len[e];
+    w[e] = dual_len[e] / edge_len[e];
+  }
+  std::vector<double> a_int(N_);
+  total_area_ = 0.0;
+  for (int i = 0; i < N_; ++i) {
+    a_int[i] = areas[perm_[i]];
+    if (!(a_int[i] > 0)) throw std::invalid_argument("non-positive site area");
+  }
+  for (int i = 0; i < N_; ++i) total_area_ += a_int[i];
+
+  SiteGraph g = build_site_graph(N_, E_, e0.data(), e1.data());
+  nnz_ = g.ptr[N_];
+  lpr0_ = pick_lpr(nnz_, N_);
+
+  // ---- mu operator (symmetrised) + AMG hierarchy on the host ----------------------------
+  HostCsr<double> A0;
+  A0.rows = A0.cols = N_;
+  A0.ptr = g.ptr;
+  A0.idx = g.nbr;
+  A0.val.assign(nnz_, 0.0);
+  for (int i = 0; i < N_; ++i) {
+    double diag = 0.0;
+    int kd = -1;
+    for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
+      if (g.edge[k] < 0) { kd = k; continue; }
+      A0.val[k] = -w[g.edge[k]];
+      diag += w[g.edge[k]];
+    }
+    A0.val[kd] = diag;
+  }
+  std::vector<double> aval_host = A0.val;
+  AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24);
+  if (H.nc > 4096) throw std::runtime_error("AMG coarsening stalled (coarsest level too large)");
+
+  // ---- uploads --------------------------------------------------------------------------
+  ptr_.upload(g.ptr, stream_);
+  idx_.upload(g.nbr, stream_);
+  eidx_.upload(g.edge, stream_);
+  {
+    std::vector<signed char> hd(g.head.begin(), g.head.end());
+    head_.upload(hd, stream_);
+  }
+  aval_.upload(aval_host, stream_);
+  lval_.alloc(nnz_);
+  areas_.upload(a_int, stream_);
+  {
+    std::vector<unsigned char> fx(N_, 0);
+    if (fix_psi)
+      for (int64_t k = 0; k < n_fixed; ++k) {
+        if (fixed_sites[k] < 0 || fixed_sites[k] >= N_) throw std::invalid_argument("fixed site out of range");
+        fx[inv_perm_[fixed_sites[k]]] = 1;
+      }
+    fixed_.upload(fx, stream_);
+  }
+  {
+    std::vector<double> ones(N_, 1.0);
+    eps_.upload(ones, stream_);
+  }
+  bterm_.alloc(N_);
+  bterm_.zero(stream_);
+  e0_.upload(e0, stream_);
+  e1_.upload(e1, stream_);
+  elen_.upload(len, stream_);
+  weight_.upload(w, stream_);
+  theta_.alloc(E_);
+  theta_.zero(stream_);
+  {
+    std::vector<int> b0(Eb_), b1(Eb_);
+    std::vector<double> bl(Eb_);
+    for (int b = 0; b < Eb_; ++b) {
+      const int64_t e = bedge_idx[b];
+      if (e < 0 || e >= E_) throw std::invalid_argument("boundary edge index out of range");
+      b0[b] = e0[e]; b1[b] = e1[e]; bl[b] = len[e];
+    }
+    be0_.upload(b0, stream_);
+    be1_.upload(b1, stream_);
+    blen_.upload(bl, stream_);
+    mub_.alloc(Eb_ > 0 ? Eb_ : 1);
+    mub_.zero(stream_);
+  }
+  dperm_.upload(perm_, stream_);
+  {
+    std::vector<int> pr(std::max(nprobe_, 1), 0);
+    for (int k = 0; k < nprobe_; ++k) {
+      if (probe_sites[k] < 0 || probe_sites[k] >= N_) throw std::invalid_argument("probe site out of range");
+      pr[k] = inv_perm_[probe_sites[k]];
+    }
+    probes_.upload(pr, stream_);
+  }
+  const size_t cap = static_cast<size_t>(cfg_.running_capacity);
+  run_dt_.alloc(cap);
+  run_mu_.alloc(cap * std::max(nprobe_, 1));
+  run_theta_.alloc(cap * std::max(nprobe_, 1));
+
+  psi_[0].alloc(N_);
+  psi_[1].alloc(N_);
+  mu_.alloc(N_);
+  mu_.zero(stream_);
+  {
+    std::vector<double2> one(N_, make_double2(1.0, 0.0));
+    psi_[0].upload(one, stream_);
+    psi_[1].upload(one, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  // hierarchy
+  levels_.resize(H.levels.size());
+  amg_nnz_ = 0;
+  int max_rows_lpr = N_ * lpr0_;
+  for (size_t l = 0; l < H.levels.size(); ++l) {
+    AmgLevel& hl = H.levels[l];
+    DevLevel& dl = levels_[l];
+    dl.n = static_cast<int>(hl.A.rows);
+    amg_nnz_ += hl.A.nnz();
+    if (l > 0) {
+      upload_csr(hl.A, dl.A);
+      max_rows_lpr = std::max(max_rows_lpr, dl.A.rows * dl.A.lpr);
+    }
+    dl.dinv.upload(hl.dinv, stream_);
+    dl.omega = (4.0 / 3.0) / hl.rho;
+    if (l + 1 < H.levels.size()) {
+      upload_csr(hl.P, dl.P);
+      upload_csr(hl.R, dl.R);
+      max_rows_lpr = std::max(max_rows_lpr, dl.P.rows * dl.P.lpr);
+      max_rows_lpr = std::max(max_rows_lpr, dl.R.rows * dl.R.lpr);
+    }
+    dl.x.alloc(dl.n);
+    dl.r.alloc(dl.n);
+    if (l > 0) { dl.b.alloc(dl.n); dl.y.alloc(dl.n); }
+    TDGL_CUDA(cudaStreamSynchronize(stream_));  // host vectors die with H
+  }
+  nc_ = static_cast<int>(H.nc);
+  coarse_inv_.upload(H.coarse_inv, stream_);
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+
+  cg_b_.alloc(N_); cg_r_.alloc(N_); cg_p_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_);
+  cg_p_.zero(stream_);
+  const size_t max_grid = static_cast<size_t>(max_rows_lpr) / kBlock + 2;
+  partials_.alloc(2 * std::max<size_t>(max_grid, 4096));
+  counter_.alloc(4);
+  counter_.zero(stream_);
+  tmp_c_.alloc(N_);
+  tmp_d_.alloc(N_);
+  tmp_d2_.alloc(N_);
+  tmp_e_.alloc(E_);
+  tmp_e2_.alloc(E_);
+
+  // control block
+  std::memset(h_ctl_, 0, sizeof(Ctl));
+  h_ctl_->dt_init = 1e-6; h_ctl_->dt_max = 1e-1; h_ctl_->multiplier = 0.25;
+  h_ctl_->gamma = gamma_; h_ctl_->u = u_; h_ctl_->mu_rtol = cfg_.mu_rtol;
+  h_ctl_->adaptive = 1; h_ctl_->window = 10; h_ctl_->max_retries = 10;
+  h_ctl_->cg_max_iter = cfg_.mu_max_iter;
+  h_ctl_->n_probe = nprobe_; h_ctl_->running_capacity = cfg_.running_capacity;
+  h_ctl_->tentative_dt = 1e-6; h_ctl_->dt = 1e-6;
+  ctl_.alloc(1);
+  push_ctl();
+
+  // link variables for A = 0
+  {
+    std::vector<double> zeroA(2 * static_cast<size_t>(E_), 0.0);
+    set_link_exponents(zeroA.data());
+  }
+
+  graph_mode_ = 2;
+  if (cfg_.use_graph == 1) {
+    try {
+      build_graph();
+      graph_mode_ = 1;
+    } catch (const std::exception& ex) {
+      // still the CUDA path, only host-driven; keep the reason for tdgl_last_error()
+      last_error = std::string("CUDA graph with device-side loops unavailable, using host-driven launches: ") + ex.what();
+      cudaGetLastError();
+      if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+      if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+      h_step_ = h_psi_ = h_cg_ = 0;
+      if (std::getenv("TDGL_B200_VERBOSE")) fprintf(stderr, "[tdgl_b200] %s\n", last_error.c_str());
+    }
+  }
+}
+
+Engine::~Engine() {
+  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+  if (graph_) cudaGraphDestroy(graph_);
+  if (h_ctl_) cudaFreeHost(h_ctl_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::push_ctl() {
+  TDGL_CUDA(cudaMemcpyAsync(ctl_.p, h_ctl_, sizeof(Ctl), cudaMemcpyHostToDevice, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::sync_ctl_to_host() {
+  TDGL_CUDA(cudaMemcpyAsync(h_ctl_, ctl_.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ============================================================================================
+// launch wrappers
+
+#define TDGL_LPR_SWITCH(lpr, CALL)                                                         \
+  switch (lpr) {                                                                           \
+    case 4: { constexpr int LPR = 4; CALL; } break;                                        \
+    case 8: { constexpr int LPR = 8; CALL; } break;                                        \
+    case 16: { constexpr int LPR = 16; CALL; } break;                                      \
+    default: { constexpr int LPR = 32; CALL; } break;                                      \
+  }
+
+#define TDGL_LAUNCH_CHECK()                                                                \
+  do { ++launches_; TDGL_CUDA(cudaGetLastError()); } while (0)
+
+void Engine::launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out) {
+  const int grid = grid_rows(A.rows, A.lpr);
+  TDGL_LPR_SWITCH(A.lpr, (k_spmv<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, A.rows, A.ptr, A.idx, A.val, x, y, partials_.p, counter_.p, dot_out)));
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::launch_plain(const CsrView& A, const double* x, double* y, bool add) {
+  const int grid = grid_rows(A.rows, A.lpr);
+  if (add) {
+    TDGL_LPR_SWITCH(A.lpr, (k_spmv_plain<LPR, true><<<grid, kBlock, 0, stream_>>>(
+        ctl_.p, A.rows, A.ptr, A.idx, A.val, x, y)));
+  } else {
+    TDGL_LPR_SWITCH(A.lpr, (k_spmv_plain<LPR, false><<<grid, kBlock, 0, stream_>>>(
+        ctl_.p, A.rows, A.ptr, A.idx, A.val, x, y)));
+  }
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::launch_presmooth(const CsrView& A, const double* dinv, double omega,
+                              const double* b, double* x, double* r) {
+  const int grid = grid_rows(A.rows, A.lpr);
+  TDGL_LPR_SWITCH(A.lpr, (k_presmooth_residual<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, A.rows, A.ptr, A.idx, A.val, dinv, omega, b, x, r)));
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
+                           const double* x, double* y, const double* w, double* dot_out) {
+  const int grid = grid_rows(A.rows, A.lpr);
+  TDGL_LPR_SWITCH(A.lpr, (k_jacobi<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, A.rows, A.ptr, A.idx, A.val, dinv, omega, b, x, y, w, partials_.p, counter_.p,
+      dot_out)));
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::launch_residual(const CsrView& A, const double* x, const double* b, double* r,
+                             double* rr) {
+  const int grid = grid_rows(A.rows, A.lpr);
+  TDGL_LPR_SWITCH(A.lpr, (k_residual<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, A.rows, A.ptr, A.idx, A.val, x, b, r, partials_.p, counter_.p, rr)));
+  TDGL_LAUNCH_CHECK();
+}
+
+// z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
+// smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
+void Engine::enqueue_vcycle(const double* r_in, double* z_out, double* rz_out) {
+  const size_t L = levels_.size();
+  if (L == 1) {
+    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
+    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, coarse_inv_.p, r_in, z_out);
+    TDGL_LAUNCH_CHECK();
+    k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, r_in, z_out, partials_.p, counter_.p, rz_out);
+    TDGL_LAUNCH_CHECK();
+    return;
+  }
+  for (size_t l = 0; l + 1 < L; ++l) {
+    DevLevel& lv = levels_[l];
+    const double* b = (l == 0) ? r_in : lv.b.p;
+    launch_presmooth(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, lv.r.p);
+    launch_plain(lv.R.view(), lv.r.p, levels_[l + 1].b.p, false);
+  }
+  {
+    DevLevel& c = levels_[L - 1];
+    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
+    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, coarse_inv_.p, c.b.p, c.y.p);
+    TDGL_LAUNCH_CHECK();
+  }
+  for (size_t l = L - 1; l-- > 0;) {
+    DevLevel& lv = levels_[l];
+    const double* b = (l == 0) ? r_in : lv.b.p;
+    double* y = (l == 0) ? z_out : lv.y.p;
+    launch_plain(lv.P.view(), levels_[l + 1].y.p, lv.x.p, true);
+    launch_jacobi(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, y, (l == 0) ? r_in : nullptr,
+                  (l == 0) ? rz_out : nullptr);
+  }
+}
+
+void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
+  constexpr int dummy = 0; (void)dummy;
+  const int rows_per_block = kBlock / lpr0_;
+  const int grid = (N_ + rows_per_block - 1) / rows_per_block;
+  TDGL_LPR_SWITCH(lpr0_, (k_psi_step<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, fixed_.p, psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p,
+      mu_.p, eps_.p, sq_out, dt_override)));
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::enqueue_mu_rhs(double* rhs_raw) {
+  const int grid = grid_rows(N_, lpr0_);
+  TDGL_LPR_SWITCH(lpr0_, (k_mu_rhs<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p,
+      bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p)));
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
+  enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new);
+  k_cg_direction<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, cg_z_.p, cg_p_.p);
+  TDGL_LAUNCH_CHECK();
+  launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp);
+  k_cg_update<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_p_.p, cg_Ap_.p, mu_.p, cg_r_.p,
+                                                   partials_.p, counter_.p, cond);
+  TDGL_LAUNCH_CHECK();
+}
+
+// project mu to area-weighted mean zero (fixes the gauge the reference leaves to SuperLU
+// roundoff)
+void Engine::enqueue_mu_finish() {
+  k_weighted_sum<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, areas_.p, mu_.p, partials_.p,
+                                                      counter_.p, 1.0 / total_area_);
+  TDGL_LAUNCH_CHECK();
+  k_shift<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, mu_.p);
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::host_solve_loop() {
+  k_cg_begin<<<1, 32, 0, stream_>>>(ctl_.p, 0);
+  TDGL_LAUNCH_CHECK();
+  sync_ctl_to_host();
+  while (h_ctl_->cg_go) {
+    enqueue_cg_iteration(0);
+    sync_ctl_to_host();
+  }
+}
+
+// ============================================================================================
+// the device-side loop: one CUDA graph = Runner._run_stage for up to max_steps steps
+
+namespace {
+struct GraphBuilder {
+  cudaGraph_t graph;
+  cudaStream_t stream;
+  std::vector<cudaGraphNode_t> tail;
+
+  void capture(const std::function<void()>& body) {
+    TDGL_CUDA(cudaStreamBeginCaptureToGraph(stream, graph, tail.empty() ? nullptr : tail.data(),
+                                            nullptr, tail.size(), cudaStreamCaptureModeRelaxed));
+    try {
+      body();
+    } catch (...) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(stream, &g);
+      throw;
+    }
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t nd = 0;
+    TDGL_CUDA(cudaStreamGetCaptureInfo_v2(stream, &st, nullptr, nullptr, &deps, &nd));
+    std::vector<cudaGraphNode_t> t(deps, deps + nd);
+    cudaGraph_t g = nullptr;
+    TDGL_CUDA(cudaStreamEndCapture(stream, &g));
+    tail.swap(t);
+  }
+
+  cudaGraph_t add_while(cudaGraphConditionalHandle handle) {
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = handle;
+    p.conditional.type = cudaGraphCondTypeWhile;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    TDGL_CUDA(cudaGraphAddNode(&node, graph, tail.empty() ? nullptr : tail.data(), tail.size(), &p));
+    tail.assign(1, node);
+    return p.conditional.phGraph_out[0];
+  }
+};
+}  // namespace
+
+void Engine::build_graph() {
+  TDGL_CUDA(cudaGraphCreate(&graph_, 0));
+  TDGL_CUDA(cudaGraphConditionalHandleCreate(&h_step_, graph_, 1, cudaGraphCondAssignDefault));
+  TDGL_CUDA(cudaGraphConditionalHandleCreate(&h_psi_, graph_, 0, cudaGraphCondAssignDefault));
+  TDGL_CUDA(cudaGraphConditionalHandleCreate(&h_cg_, graph_, 0, cudaGraphCondAssignDefault));
+  const int64_t launches_before = launches_;
+
+  GraphBuilder root{graph_, stream_, {}};
+  cudaGraph_t step_body = root.add_while(h_step_);
+
+  GraphBuilder sb{step_body, stream_, {}};
+  sb.capture([&] {
+    k_step_begin<<<1, 32, 0, stream_>>>(ctl_.p, h_psi_);
+    TDGL_LAUNCH_CHECK();
+  });
+  cudaGraph_t psi_body = sb.add_while(h_psi_);
+  {
+    GraphBuilder pb{psi_body, stream_, {}};
+    pb.capture([&] {
+      enqueue_psi_step(nullptr, -1.0);
+      k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, h_psi_);
+      TDGL_LAUNCH_CHECK();
+    });
+  }
+  sb.capture([&] {
+    enqueue_mu_rhs(nullptr);
+    k_cg_begin<<<1, 32, 0, stream_>>>(ctl_.p, h_cg_);
+    TDGL_LAUNCH_CHECK();
+  });
+  cudaGraph_t cg_body = sb.add_while(h_cg_);
+  {
+    GraphBuilder cb{cg_body, stream_, {}};
+    cb.capture([&] { enqueue_cg_iteration(h_cg_); });
+  }
+  sb.capture([&] {
+    enqueue_mu_finish();
+    k_step_end<<<1, kMaxProbes, 0, stream_>>>(ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
+                                            run_dt_.p, run_mu_.p, run_theta_.p, h_step_);
+    TDGL_LAUNCH_CHECK();
+  });
+  launches_ = launches_before;  // captured, not launched
+  TDGL_CUDA(cudaGraphInstantiate(&graph_exec_, graph_, 0));
+}
+
+// ============================================================================================
+// public operations
+
+void Engine::set_link_exponents(const double* A) {
+  std::vector<double> th(E_);
+  for (int e = 0; e < E_; ++e)
+    th[e] = A[2 * e] * h_dirs_[2 * e] + A[2 * e + 1] * h_dirs_[2 * e + 1];
+  theta_.upload(th, stream_);
+  k_link_values<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+      N_, ptr_.p, eidx_.p, head_.p, weight_.p, theta_.p, areas_.p, lval_.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::set_epsilon(const double* eps) {
+  tmp_d_.upload(eps, N_, stream_);
+  k_gather<double><<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, eps_.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::set_mu_boundary(const double* mub) {
+  if (Eb_ == 0) return;
+  mub_.upload(mub, Eb_, stream_);
+  bterm_.zero(stream_);
+  k_boundary_term<<<(Eb_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+      Eb_, be0_.p, be1_.p, blen_.p, areas_.p, mub_.p, bterm_.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::set_state(const double* psi, const double* mu) {
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
+  k_gather<double2><<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_c_.p, psi_[cur].p);
+  TDGL_LAUNCH_CHECK();
+  tmp_d_.upload(mu, N_, stream_);
+  k_gather<double><<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, mu_.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
+                         double multiplier) {
+  if (window < 1 || window > kMaxWindow) throw std::invalid_argument("adaptive_window out of range");
+  sync_ctl_to_host();
+  h_ctl_->dt_init = dt_init;
+  h_ctl_->dt_max = adaptive ? dt_max : dt_init;  // solver.py:320
+  h_ctl_->adaptive = adaptive ? 1 : 0;
+  h_ctl_->window = window;
+  h_ctl_->max_retries = max_retries;
+  h_ctl_->multiplier = multiplier;
+  h_ctl_->tentative_dt = dt_init;              // solver.py:319
+  h_ctl_->dt = dt_init;
+  h_ctl_->n_hist = 0;                          // solver.py:318
+  push_ctl();
+}
+
+Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t step, double time) {
+  if (max_steps < 1) throw std::invalid_argument("max_steps must be >= 1");
+  sync_ctl_to_host();
+  h_ctl_->steps_left = max_steps;
+  h_ctl_->steps_done = 0;
+  h_ctl_->t_end = t_end;
+  h_ctl_->time = time;
+  h_ctl_->step = step;
+  h_ctl_->finished = 0;
+  h_ctl_->status = 0;
+  h_ctl_->failed_step = -1;
+  h_ctl_->failed_dt = 0.0;
+  h_ctl_->total_retries = 0;
+  h_ctl_->total_cg_it = 0;
+  TDGL_CUDA(cudaMemcpyAsync(ctl_.p, h_ctl_, sizeof(Ctl), cudaMemcpyHostToDevice, stream_));
+  if (graph_mode_ == 1) {
+    TDGL_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+    ++launches_;
+    sync_ctl_to_host();
+    // the graph's kernels were launched by the device-side loops; account for them
+    launches_ += h_ctl_->steps_done * 6 + h_ctl_->total_retries * 2 +
+                 h_ctl_->total_cg_it * (3 + 4 * (static_cast<int64_t>(levels_.size()) - 1) + 1);
+  } else {
+    while (true) {
+      k_step_begin<<<1, 32, 0, stream_>>>(ctl_.p, 0);
+      TDGL_LAUNCH_CHECK();
+      do {
+        enqueue_psi_step(nullptr, -1.0);
+        k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, 0);
+        TDGL_LAUNCH_CHECK();
+        sync_ctl_to_host();
+      } while (h_ctl_->psi_go);
+      if (h_ctl_->status != 0) break;
+      enqueue_mu_rhs(nullptr);
+      host_solve_loop();
+      enqueue_mu_finish();
+      k_step_end<<<1, kMaxProbes, 0, stream_>>>(ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
+                                              run_dt_.p, run_mu_.p, run_theta_.p, 0);
+      TDGL_LAUNCH_CHECK();
+      sync_ctl_to_host();
+      if (!h_ctl_->step_go) break;
+    }
+  }
+  last_steps_done_ = h_ctl_->steps_done;
+  AdvanceInfo info;
+  info.steps_done = h_ctl_->steps_done;
+  info.step = h_ctl_->step;
+  info.time = h_ctl_->time;
+  info.dt = h_ctl_->dt;
+  info.tentative_dt = h_ctl_->tentative_dt;
+  info.finished = h_ctl_->finished;
+  info.status = h_ctl_->status;
+  info.failed_step = h_ctl_->failed_step;
+  info.failed_dt = h_ctl_->failed_dt;
+  info.retries = h_ctl_->total_retries;
+  info.mu_iterations = h_ctl_->total_cg_it;
+  info.mu_rel_residual = h_ctl_->bb > 0 ? std::sqrt(h_ctl_->rr / h_ctl_->bb) : 0.0;
+  return info;
+}
+
+void Engine::get_state(double* psi, double* mu) {
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  const int g = (N_ + kBlock - 1) / kBlock;
+  if (psi != nullptr) {
+    k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, psi_[cur].p, tmp_c_.p);
+    TDGL_LAUNCH_CHECK();
+    TDGL_CUDA(cudaMemcpyAsync(psi, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+  }
+  if (mu != nullptr) {
+    k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
+    TDGL_LAUNCH_CHECK();
+    tmp_d_.download(mu, N_, stream_);
+  }
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::get_currents(double* js, double* jn) {
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, tmp_e_.p, tmp_e2_.p);
+  TDGL_LAUNCH_CHECK();
+  if (js != nullptr) tmp_e_.download(js, E_, stream_);
+  if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::get_running(int64_t capacity, double* dt, double* mu_probe, double* theta_probe) {
+  const int64_t k = std::min<int64_t>(last_steps_done_, cfg_.running_capacity);
+  if (capacity < k) throw std::invalid_argument("running-state output too small");
+  if (dt != nullptr) run_dt_.download(dt, k, stream_);
+  for (int p = 0; p < nprobe_; ++p) {
+    if (mu_probe != nullptr)
+      TDGL_CUDA(cudaMemcpyAsync(mu_probe + p * capacity, run_mu_.p + static_cast<size_t>(p) * cfg_.running_capacity,
+                                sizeof(double) * k, cudaMemcpyDeviceToHost, stream_));
+    if (theta_probe != nullptr)
+      TDGL_CUDA(cudaMemcpyAsync(theta_probe + p * capacity, run_theta_.p + static_cast<size_t>(p) * cfg_.running_capacity,
+                                sizeof(double) * k, cudaMemcpyDeviceToHost, stream_));
+  }
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ---- single operators ------------------------------------------------------------------------
+
+void Engine::op_psi_laplacian(const double* x, double* y) {
+  // complex SpMV through the psi-step kernel's gather path is not exposed separately; use
+  // the rhs kernel's building block: run k_psi_lap (fixed rows -> identity)
+  const int g = (N_ + kBlock - 1) / kBlock;
+  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, x, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
+  DevBuf<double2> xin, yout;
+  xin.alloc(N_); yout.alloc(N_);
+  k_gather<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_c_.p, xin.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_LPR_SWITCH(lpr0_, (k_psi_laplacian<LPR><<<grid_rows(N_, lpr0_), kBlock, 0, stream_>>>(
+      N_, ptr_.p, idx_.p, lval_.p, fixed_.p, xin.p, yout.p)));
+  TDGL_LAUNCH_CHECK();
+  k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, yout.p, tmp_c_.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaMemcpyAsync(y, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::op_psi_step(const double* psi, const double* mu, double dt, double* psi_out,
+                         double* sq_out, int* failed) {
+  const int g = (N_ + kBlock - 1) / kBlock;
+  DevBuf<double2> pin, pout;
+  DevBuf<double> muin, sq;
+  pin.alloc(N_); pout.alloc(N_); muin.alloc(N_); sq.alloc(N_);
+  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
+  k_gather<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_c_.p, pin.p);
+  TDGL_LAUNCH_CHECK();
+  tmp_d_.upload(mu, N_, stream_);
+  k_gather<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, muin.p);
+  TDGL_LAUNCH_CHECK();
+  sync_ctl_to_host();
+  const int saved_flag = h_ctl_->disc_flag;
+  const unsigned long long saved_max = h_ctl_->max_dpsi_bits;
+  h_ctl_->disc_flag = 0;
+  h_ctl_->status = 0;
+  push_ctl();
+  const int rows_per_block = kBlock / lpr0_;
+  const int grid = (N_ + rows_per_block - 1) / rows_per_block;
+  TDGL_LPR_SWITCH(lpr0_, (k_psi_step<LPR><<<grid, kBlock, 0, stream_>>>(
+      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, fixed_.p, pin.p, pin.p, pout.p, pout.p, muin.p, eps_.p,
+      sq.p, dt)));
+  TDGL_LAUNCH_CHECK();
+  k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, pout.p, tmp_c_.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaMemcpyAsync(psi_out, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+  k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, sq.p, tmp_d_.p);
+  TDGL_LAUNCH_CHECK();
+  tmp_d_.download(sq_out, N_, stream_);
+  sync_ctl_to_host();
+  if (failed != nullptr) *failed = h_ctl_->disc_flag;
+  h_ctl_->disc_flag = saved_flag;
+  h_ctl_->max_dpsi_bits = saved_max;
+  push_ctl();
+}
+
+void Engine::op_mu_rhs(const double* psi, double* rhs) {
+  const int g = (N_ + kBlock - 1) / kBlock;
+  DevBuf<double2> pin;
+  DevBuf<double> raw, b, r;
+  pin.alloc(N_); raw.alloc(N_); b.alloc(N_); r.alloc(N_);
+  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
+  k_gather<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_c_.p, pin.p);
+  TDGL_LAUNCH_CHECK();
+  sync_ctl_to_host();
+  const double bb = h_ctl_->bb, rr = h_ctl_->rr;
+  TDGL_LPR_SWITCH(lpr0_, (k_mu_rhs<LPR><<<grid_rows(N_, lpr0_), kBlock, 0, stream_>>>(
+      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p,
+      r.p, raw.p, partials_.p, counter_.p)));
+  TDGL_LAUNCH_CHECK();
+  k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
+  TDGL_LAUNCH_CHECK();
+  tmp_d_.download(rhs, N_, stream_);
+  sync_ctl_to_host();
+  h_ctl_->bb = bb; h_ctl_->rr = rr;
+  push_ctl();
+}
+
+void Engine::op_mu_laplacian(const double* x, double* y) {
+  // mu_laplacian = -diag(1/areas) A
+  const int g = (N_ + kBlock - 1) / kBlock;
+  DevBuf<double> xin, yout;
+  xin.alloc(N_); yout.alloc(N_);
+  tmp_d_.upload(x, N_, stream_);
+  k_gather<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, xin.p);
+  TDGL_LAUNCH_CHECK();
+  launch_spmv(A0(), xin.p, yout.p, nullptr);
+  k_neg_div<<<g, kBlock, 0, stream_>>>(N_, areas_.p, yout.p);
+  TDGL_LAUNCH_CHECK();
+  k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, yout.p, tmp_d_.p);
+  TDGL_LAUNCH_CHECK();
+  tmp_d_.download(y, N_, stream_);
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::op_mu_solve(const double* rhs, double* mu, int* iterations, double* rel_res) {
+  const int g = (N_ + kBlock - 1) / kBlock;
+  DevBuf<double> saved;
+  saved.alloc(N_);
+  TDGL_CUDA(cudaMemcpyAsync(saved.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+  tmp_d_.upload(rhs, N_, stream_);
+  k_gather<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, tmp_d2_.p);
+  TDGL_LAUNCH_CHECK();
+  k_scale_neg_area<<<g, kBlock, 0, stream_>>>(N_, areas_.p, tmp_d2_.p, cg_b_.p);
+  TDGL_LAUNCH_CHECK();
+  mu_.zero(stream_);
+  TDGL_CUDA(cudaMemcpyAsync(cg_r_.p, cg_b_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+  sync_ctl_to_host();
+  h_ctl_->status = 0;
+  h_ctl_->total_cg_it = 0;
+  push_ctl();
+  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_b_.p, cg_b_.p, partials_.p, counter_.p, &ctl_.p->bb);
+  TDGL_LAUNCH_CHECK();
+  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
+  TDGL_LAUNCH_CHECK();
+  host_solve_loop();
+  enqueue_mu_finish();
+  k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
+  TDGL_LAUNCH_CHECK();
+  tmp_d_.download(mu, N_, stream_);
+  sync_ctl_to_host();
+  if (iterations != nullptr) *iterations = static_cast<int>(h_ctl_->total_cg_it);
+  if (rel_res != nullptr) *rel_res = h_ctl_->bb > 0 ? std::sqrt(h_ctl_->rr / h_ctl_->bb) : 0.0;
+  const int status = h_ctl_->status;
+  h_ctl_->status = 0;
+  push_ctl();
+  TDGL_CUDA(cudaMemcpyAsync(mu_.p, saved.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  if (status != 0) throw std::runtime_error("mu solver did not converge");
+}
+
+double Engine::time_kernel(int which, int reps) {
+  if (reps < 1) reps = 1;
+  sync_ctl_to_host();
+  Ctl saved = *h_ctl_;
+  DevBuf<double> mu_saved;
+  mu_saved.alloc(N_);
+  TDGL_CUDA(cudaMemcpyAsync(mu_saved.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+  h_ctl_->status = 0;
+  push_ctl();
+  auto one = [&]() {
+    switch (which) {
+      case 0: enqueue_psi_step(nullptr, 1e-6); break;
+      case 1: enqueue_mu_rhs(nullptr); break;
+      case 2: launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp); break;
+      case 3: enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new); break;
+      case 4:
+        mu_.zero(stream_);
+        TDGL_CUDA(cudaMemcpyAsync(cg_r_.p, cg_b_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+        k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
+        TDGL_LAUNCH_CHECK();
+        host_solve_loop();
+        break;
+      default: throw std::invalid_argument("unknown kernel id");
+    }
+  };
+  one();  // warm-up
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  TDGL_CUDA(cudaEventRecord(ev0_, stream_));
+  for (int i = 0; i < reps; ++i) one();
+  TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+  TDGL_CUDA(cudaEventSynchronize(ev1_));
+  float ms = 0.f;
+  TDGL_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  // restore
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  *h_ctl_ = saved;
+  h_ctl_->cur = cur;
+  push_ctl();
+  TDGL_CUDA(cudaMemcpyAsync(mu_.p, mu_saved.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  return static_cast<double>(ms) / reps;
+}
+
+void Engine::get_info(int64_t* out, int n) {
+  const int64_t vals[8] = {N_, E_, nnz_, static_cast<int64_t>(levels_.size()), amg_nnz_, nc_,
+                           launches_, graph_mode_};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = vals[i];
+}
+
+}  // namespace tdgl
+
+// ================================================================================================
+// C ABI
+
+struct tdgl_handle {
+  std::unique_ptr<tdgl::Engine> engine;
+  std::string error;
+};
+
+namespace {
+thread_local std::string g_create_error;
+
+template <typename F>
+int guarded(tdgl_handle* h, F&& f) {
+  if (h == nullptr || !h->engine) return TDGL_E_INVALID;
+  try {
+    f(*h->engine);
+    return TDGL_OK;
+  } catch (const tdgl::CudaError& e) {
+    h->error = e.what();
+    return TDGL_E_CUDA;
+  } catch (const std::invalid_argument& e) {
+    h->error = e.what();
+    return TDGL_E_INVALID;
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return TDGL_E_MU_SOLVER;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* tdgl_version(void) { return "tdgl_b200 0.1.0 (sm_100a)"; }
+
+int tdgl_create(tdgl_handle** out, int64_t n_sites, int64_t n_edges, int64_t n_boundary_edges,
+                const int64_t* edges, const double* areas, const double* edge_lengths,
+                const double* dual_edge_lengths, const double* directions,
+                const int64_t* boundary_edge_indices, const int64_t* fixed_sites,
+                int64_t n_fixed, int32_t fix_psi, const double* sites_xy, double gamma,
+                double u, const int64_t* probe_sites, int64_t n_probe,
+                const tdgl_config* config) {
+  if (out == nullptr) return TDGL_E_INVALID;
+  *out = nullptr;
+  tdgl::Config cfg;
+  if (config != nullptr) {
+    if (config->struct_size != static_cast<int32_t>(sizeof(tdgl_config))) {
+      g_create_error = "tdgl_config.struct_size mismatch";
+      return TDGL_E_INVALID;
+    }
+    cfg.device = config->device;
+    if (config->mu_rtol > 0) cfg.mu_rtol = config->mu_rtol;
+    if (config->mu_max_iter > 0) cfg.mu_max_iter = config->mu_max_iter;
+    if (config->amg_theta > 0) cfg.amg_theta = config->amg_theta;
+    if (config->amg_max_coarse > 0) cfg.amg_max_coarse = config->amg_max_coarse;
+    if (config->use_graph > 0) cfg.use_graph = config->use_graph;
+    if (config->reorder > 0) cfg.reorder = config->reorder;
+    if (config->running_capacity > 0) cfg.running_capacity = config->running_capacity;
+  }
+  auto h = std::make_unique<tdgl_handle>();
+  try {
+    if (!edges || !areas || !edge_lengths || !dual_edge_lengths || !directions ||
+        (n_boundary_edges > 0 && !boundary_edge_indices) || (n_fixed > 0 && !fixed_sites) ||
+        (n_probe > 0 && !probe_sites))
+      throw std::invalid_argument("null array argument");
+    h->engine = std::make_unique<tdgl::Engine>(
+        n_sites, n_edges, n_boundary_edges, edges, areas, edge_lengths, dual_edge_lengths,
+        directions, boundary_edge_indices, fixed_sites, n_fixed, fix_psi, sites_xy, gamma, u,
+        probe_sites, n_probe, cfg);
+    h->error = h->engine->last_error;
+  } catch (const tdgl::CudaError& e) {
+    g_create_error = e.what();
+    return TDGL_E_CUDA;
+  } catch (const std::invalid_argument& e) {
+    g_create_error = e.what();
+    return TDGL_E_INVALID;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return TDGL_E_MU_SOLVER;
+  }
+  *out = h.release();
+  return TDGL_OK;
+}
+
+void tdgl_destroy(tdgl_handle* h) { delete h; }
+
+const char* tdgl_last_error(const tdgl_handle* h) {
+  return h == nullptr ? g_create_error.c_str() : h->error.c_str();
+}
+
+int tdgl_set_link_exponents(tdgl_handle* h, const double* A) {
+  return guarded(h, [&](tdgl::Engine& e) { e.set_link_exponents(A); });
+}
+int tdgl_set_epsilon(tdgl_handle* h, const double* epsilon) {
+  return guarded(h, [&](tdgl::Engine& e) { e.set_epsilon(epsilon); });
+}
+int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary) {
+  return guarded(h, [&](tdgl::Engine& e) { e.set_mu_boundary(mu_boundary); });
+}
+int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu) {
+  return guarded(h, [&](tdgl::Engine& e) { e.set_state(psi, mu); });
+}
+int tdgl_set_stepper(tdgl_handle* h, double dt_init, double dt_max, int32_t adaptive,
+                     int32_t adaptive_window, int32_t max_solve_retries,
+                     double adaptive_time_step_multiplier) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    e.set_stepper(dt_init, dt_max, adaptive, adaptive_window, max_solve_retries,
+                  adaptive_time_step_multiplier);
+  });
+}
+
+int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, double time,
+                 tdgl_advance_info* info) {
+  int status = TDGL_OK;
+  const int rc = guarded(h, [&](tdgl::Engine& e) {
+    const auto r = e.advance(max_steps, t_end, step, time);
+    if (info != nullptr) {
+      info->steps_done = r.steps_done; info->step = r.step; info->time = r.time; info->dt = r.dt;
+      info->tentative_dt = r.tentative_dt; info->finished = r.finished; info->status = r.status;
+      info->failed_step = r.failed_step; info->failed_dt = r.failed_dt; info->retries = r.retries;
+      info->mu_iterations = r.mu_iterations; info->mu_rel_residual = r.mu_rel_residual;
+    }
+    status = r.status;
+  });
+  if (rc != TDGL_OK) return rc;
+  if (status == 1) { h->error = "Solver failed to converge (|psi|^2 discriminant < 0 after max_solve_retries)"; return TDGL_E_STEP_FAILED; }
+  if (status == 2) { h->error = "mu solver did not reach tolerance within mu_max_iter iterations"; return TDGL_E_MU_SOLVER; }
+  return TDGL_OK;
+}
+
+int tdgl_get_state(tdgl_handle* h, double* psi, double* mu) {
+  return guarded(h, [&](tdgl::Engine& e) { e.get_state(psi, mu); });
+}
+int tdgl_get_currents(tdgl_handle* h, double* supercurrent, double* normal_current) {
+  return guarded(h, [&](tdgl::Engine& e) { e.get_currents(supercurrent, normal_current); });
+}
+int tdgl_get_running(tdgl_handle* h, int64_t capacity, double* dt, double* mu_probe,
+                     double* theta_probe) {
+  return guarded(h, [&](tdgl::Engine& e) { e.get_running(capacity, dt, mu_probe, theta_probe); });
+}
+
+int tdgl_op_psi_laplacian(tdgl_handle* h, const double* x, double* y) {
+  return guarded(h, [&](tdgl::Engine& e) { e.op_psi_laplacian(x, y); });
+}
+int tdgl_op_psi_step(tdgl_handle* h, const double* psi, const double* mu, double dt,
+                     double* psi_out, double* sq_out, int32_t* failed) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    int f = 0;
+    e.op_psi_step(psi, mu, dt, psi_out, sq_out, &f);
+    if (failed != nullptr) *failed = f;
+  });
+}
+int tdgl_op_mu_rhs(tdgl_handle* h, const double* psi, double* rhs) {
+  return guarded(h, [&](tdgl::Engine& e) { e.op_mu_rhs(psi, rhs); });
+}
+int tdgl_op_mu_laplacian(tdgl_handle* h, const double* x, double* y) {
+  return guarded(h, [&](tdgl::Engine& e) { e.op_mu_laplacian(x, y); });
+}
+int tdgl_op_mu_solve(tdgl_handle* h, const double* rhs, double* mu, int32_t* iterations,
+                     double* rel_residual) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    int it = 0;
+    double rr = 0;
+    e.op_mu_solve(rhs, mu, &it, &rr);
+    if (iterations != nullptr) *iterations = it;
+    if (rel_residual != nullptr) *rel_residual = rr;
+  });
+}
+int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, double* mean_ms) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    const double ms = e.time_kernel(which, reps);
+    if (mean_ms != nullptr) *mean_ms = ms;
+  });
+}
+int tdgl_get_info(tdgl_handle* h, int64_t* out, int32_t n) {
+  return guarded(h, [&](tdgl::Engine& e) { e.get_info(out, n); });
+}
+
+int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
+                        const double* edge_lengths, const double* dual_edge_lengths,
+                        double theta, int32_t max_coarse, int32_t* n_levels,
+                        int64_t* level_rows, int64_t* level_nnz, const double* rhs, double* x,
+                        int32_t max_iter, double rtol, int32_t* iterations) {
+  using namespace tdgl;
+  try {
+    std::vector<int32_t> e0(n_edges), e1(n_edges);
+    for (int64_t e = 0; e < n_edges; ++e) { e0[e] = static_cast<int32_t>(edges[2 * e]); e1[e] = static_cast<int32_t>(edges[2 * e + 1]); }
+    SiteGraph g = build_site_graph(n_sites, n_edges, e0.data(), e1.data());
+    HostCsr<double> A;
+    A.rows = A.cols = n_sites;
+    A.ptr = g.ptr; A.idx = g.nbr; A.val.assign(g.nbr.size(), 0.0);
+    for (int64_t i = 0; i < n_sites; ++i) {
+      double diag = 0; int kd = -1;
+      for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
+        if (g.edge[k] < 0) { kd = k; continue; }
+        const double w = dual_edge_lengths[g.edge[k]] / edge_lengths[g.edge[k]];
+        A.val[k] = -w; diag += w;
+      }
+      A.val[kd] = diag;
+    }
+    HostCsr<double> A0 = A;
+    AmgHierarchy H = build_amg(std::move(A), theta, max_coarse, 24);
+    const int L = static_cast<int>(H.levels.size());
+    if (n_levels) *n_levels = L;
+    for (int l = 0; l < L && l < 32; ++l) {
+      if (level_rows) level_rows[l] = H.levels[l].A.rows;
+      if (level_nnz) level_nnz[l] = H.levels[l].A.nnz();
+    }
+    if (rhs == nullptr || x == nullptr) return TDGL_OK;
+    // host PCG with the same V(1,1) cycle the device runs (validation of the hierarchy)
+    std::vector<std::vector<double>> bx(L), xx(L), rr(L), yy(L);
+    for (int l = 0; l < L; ++l) { const size_t n = H.levels[l].A.rows; bx[l].resize(n); xx[l].resize(n); rr[l].resize(n); yy[l].resize(n); }
+    std::vector<double> tmp;
+    std::function<void(int)> cycle = [&](int l) {
+      const AmgLevel& lv = H.levels[l];
+      const int64_t n = lv.A.rows;
+      if (l == L - 1) {
+        for (int64_t i = 0; i < n; ++i) { double s = 0; for (int64_t j = 0; j < n; ++j) s += H.coarse_inv[i * n + j] * bx[l][j]; yy[l][i] = s; }
+        return;
+      }
+      const double om = (4.0 / 3.0) / lv.rho;
+      for (int64_t i = 0; i < n; ++i) xx[l][i] = om * lv.dinv[i] * bx[l][i];
+      spmv(lv.A, xx[l], tmp);
+      for (int64_t i = 0; i < n; ++i) rr[l][i] = bx[l][i] - tmp[i];
+      spmv(lv.R, rr[l], bx[l + 1]);
+      cycle(l + 1);
+      spmv(lv.P, yy[l + 1], tmp);
+      for (int64_t i = 0; i < n; ++i) xx[l][i] += tmp[i];
+      spmv(lv.A, xx[l], tmp);
+      for (int64_t i = 0; i < n; ++i) yy[l][i] = xx[l][i] + om * lv.dinv[i] * (bx[l][i] - tmp[i]);
+    };
+    const int64_t n = n_sites;
+    std::vector<double> r(rhs, rhs + n), p(n, 0.0), Ap, sol(n, 0.0);
+    double bb = 0; for (int64_t i = 0; i < n; ++i) bb += r[i] * r[i];
+    double rz_prev = 1.0; int it = 0;
+    double rnorm2 = bb;
+    while (rnorm2 > rtol * rtol * bb && it < max_iter) {
+      bx[0] = r; cycle(0);
+      const std::vector<double>& z = yy[0];
+      double rz = 0; for (int64_t i = 0; i < n; ++i) rz += r[i] * z[i];
+      const double beta = it == 0 ? 0.0 : rz / rz_prev;
+      for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+      spmv(A0, p, Ap);
+      double pAp = 0; for (int64_t i = 0; i < n; ++i) pAp += p[i] * Ap[i];
+      const double alpha = rz / pAp;
+      rnorm2 = 0;
+      for (int64_t i = 0; i < n; ++i) { sol[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rnorm2 += r[i] * r[i]; }
+      rz_prev = rz; ++it;
+    }
+    for (int64_t i = 0; i < n; ++i) x[i] = sol[i];
+    if (iterations) *iterations = it;
+    return TDGL_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return TDGL_E_INVALID;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+"""``DeviceEngine``: thin Python owner of one ``tdgl_handle`` (see include/tdgl_b200.h).
+
+It plays the role of the reference's ``MeshOperators`` (tdgl/finite_volume/operators.py:
+233-394) plus the arrays ``TDGLSolver.update`` threads through the Runner — but all of
+them live in HBM; Python only sees them at save steps.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_c128, as_f64, as_i64, ptr
+
+
+class StepFailed(RuntimeError):
+    """|psi|^2 solve failed ``max_solve_retries`` times (reference RuntimeError,
+    solver.py:478-483)."""
+
+
+class AdvanceInfo(NamedTuple):
+    steps_done: int
+    step: int
+    time: float
+    dt: float
+    tentative_dt: float
+    finished: bool
+    status: int
+    failed_step: int
+    failed_dt: float
+    retries: int
+    mu_iterations: int
+    mu_rel_residual: float
+
+
+class DeviceEngine:
+    def __init__(self, mesh, *, fixed_sites: Optional[Sequence[int]] = None,
+                 fix_psi: bool = True, gamma: float = 10.0, u: float = 5.79,
+                 probe_sites: Optional[Sequence[int]] = None, device: int = 0,
+                 mu_rtol: float = 0.0, mu_max_iter: int = 0, amg_theta: float = 0.0,
+                 amg_max_coarse: int = 0, use_graph: int = 0, reorder: int = 0,
+                 running_capacity: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        em = mesh.edge_mesh
+        self.n_sites = len(mesh.sites)
+        self.n_edges = len(em.edges)
+        self.n_boundary_edges = len(em.boundary_edge_indices)
+        self.n_probe = 0 if probe_sites is None else len(probe_sites)
+        edges = as_i64(em.edges)
+        areas = as_f64(mesh.areas, (self.n_sites,))
+        elen = as_f64(em.edge_lengths, (self.n_edges,))
+        dlen = as_f64(em.dual_edge_lengths, (self.n_edges,))
+        dirs = as_f64(em.directions, (self.n_edges, 2))
+        bidx = as_i64(em.boundary_edge_indices)
+        fixed = as_i64([] if fixed_sites is None else fixed_sites)
+        probes = as_i64([] if probe_sites is None else probe_sites)
+        xy = as_f64(mesh.sites, (self.n_sites, 2))
+        cfg = _lib.tdgl_config()
+        cfg.struct_size = C.sizeof(_lib.tdgl_config)
+        cfg.device = device
+        cfg.mu_rtol = mu_rtol
+        cfg.mu_max_iter = mu_max_iter
+        cfg.amg_theta = amg_theta
+        cfg.amg_max_coarse = amg_max_coarse
+        cfg.use_graph = use_graph
+        cfg.reorder = reorder
+        cfg.running_capacity = running_capacity
+        self.running_capacity = running_capacity or 4096
+        rc = self._lib.tdgl_create(
+            C.byref(self._h), self.n_sites, self.n_edges, self.n_boundary_edges, ptr(edges),
+            ptr(areas), ptr(elen), ptr(dlen), ptr(dirs), ptr(bidx), ptr(fixed), len(fixed),
+            1 if fix_psi else 0, ptr(xy), float(gamma), float(u), ptr(probes), len(probes),
+            C.byref(cfg))
+        if rc != _lib.TDGL_OK:
+            msg = self._lib.tdgl_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise _lib.TDGLLibraryError(f"tdgl_create failed ({rc}): {msg}")
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.tdgl_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc == _lib.TDGL_OK:
+            return
+        msg = self._lib.tdgl_last_error(self._h).decode()
+        if rc == _lib.TDGL_E_INVALID:
+            raise ValueError(msg)
+        raise _lib.TDGLLibraryError(f"tdgl_b200 error {rc}: {msg}")
+
+    @property
+    def message(self) -> str:
+        return self._lib.tdgl_last_error(self._h).decode()
+
+    # -- inputs ---------------------------------------------------------------------------
+    def set_link_exponents(self, A) -> None:
+        self._check(self._lib.tdgl_set_link_exponents(self._h, ptr(as_f64(A, (self.n_edges, 2)))))
+
+    def set_epsilon(self, eps) -> None:
+        self._check(self._lib.tdgl_set_epsilon(self._h, ptr(as_f64(eps, (self.n_sites,)))))
+
+    def set_mu_boundary(self, mu_boundary) -> None:
+        self._check(self._lib.tdgl_set_mu_boundary(
+            self._h, ptr(as_f64(mu_boundary, (self.n_boundary_edges,)))))
+
+    def set_state(self, psi, mu) -> None:
+        self._check(self._lib.tdgl_set_state(
+            self._h, ptr(as_c128(psi, (self.n_sites,))), ptr(as_f64(mu, (self.n_sites,)))))
+
+    def set_stepper(self, *, dt_init, dt_max, adaptive=True, adaptive_window=10,
+                    max_solve_retries=10, adaptive_time_step_multiplier=0.25) -> None:
+        self._check(self._lib.tdgl_set_stepper(
+            self._h, float(dt_init), float(dt_max), int(bool(adaptive)), int(adaptive_window),
+            int(max_solve_retries), float(adaptive_time_step_multiplier)))
+
+    # -- stepping -------------------------------------------------------------------------
+    def advance(self, max_steps: int, t_end: float, step: int, time: float) -> AdvanceInfo:
+        info = _lib.tdgl_advance_info()
+        rc = self._lib.tdgl_advance(self._h, int(max_steps), float(t_end), int(step),
+                                    float(time), C.byref(info))
+        out = AdvanceInfo(info.steps_done, info.step, info.time, info.dt, info.tentative_dt,
+                          bool(info.finished), info.status, info.failed_step, info.failed_dt,
+                          info.retries, info.mu_iterations, info.mu_rel_residual)
+        if rc == _lib.TDGL_E_STEP_FAILED:
+            raise StepFailed(f"step {out.failed_step} dt {out.failed_dt:.2e}", out)
+        self._check(rc)
+        return out
+
+    # -- outputs --------------------------------------------------------------------------
+    def get_state(self):
+        psi = np.empty(self.n_sites, dtype=np.complex128)
+        mu = np.empty(self.n_sites, dtype=np.float64)
+        self._check(self._lib.tdgl_get_state(self._h, ptr(psi), ptr(mu)))
+        return psi, mu
+
+    def get_currents(self):
+        js = np.empty(self.n_edges)
+        jn = np.empty(self.n_edges)
+        self._check(self._lib.tdgl_get_currents(self._h, ptr(js), ptr(jn)))
+        return js, jn
+
+    def get_running(self, steps: int):
+        cap = max(int(steps), 1)
+        dt = np.zeros(cap)
+        mu = np.zeros((max(self.n_probe, 1), cap))
+        th = np.zeros((max(self.n_probe, 1), cap))
+        self._check(self._lib.tdgl_get_running(self._h, cap, ptr(dt), ptr(mu), ptr(th)))
+        return dt[:steps], mu[: self.n_probe, :steps], th[: self.n_probe, :steps]
+
+    # -- single operators -------------------------------------------------------------------
+    def psi_laplacian(self, x):
+        y = np.empty(self.n_sites, dtype=np.complex128)
+        self._check(self._lib.tdgl_op_psi_laplacian(self._h, ptr(as_c128(x, (self.n_sites,))), ptr(y)))
+        return y
+
+    def psi_step(self, psi, mu, dt):
+        out = np.empty(self.n_sites, dtype=np.complex128)
+        sq = np.empty(self.n_sites)
+        failed = C.c_int32(0)
+        self._check(self._lib.tdgl_op_psi_step(
+            self._h, ptr(as_c128(psi, (self.n_sites,))), ptr(as_f64(mu, (self.n_sites,))),
+            float(dt), ptr(out), ptr(sq), C.byref(failed)))
+        return out, sq, bool(failed.value)
+
+    def mu_rhs(self, psi):
+        rhs = np.empty(self.n_sites)
+        self._check(self._lib.tdgl_op_mu_rhs(self._h, ptr(as_c128(psi, (self.n_sites,))), ptr(rhs)))
+        return rhs
+
+    def mu_laplacian(self, x):
+        y = np.empty(self.n_sites)
+        self._check(self._lib.tdgl_op_mu_laplacian(self._h, ptr(as_f64(x, (self.n_sites,))), ptr(y)))
+        return y
+
+    def mu_solve(self, rhs):
+        mu = np.empty(self.n_sites)
+        it = C.c_int32(0)
+        rr = C.c_double(0)
+        self._check(self._lib.tdgl_op_mu_solve(self._h, ptr(as_f64(rhs, (self.n_sites,))), ptr(mu),
+                                               C.byref(it), C.byref(rr)))
+        return mu, it.value, rr.value
+
+    def time_kernel(self, which: int, reps: int = 20) -> float:
+        ms = C.c_double(0)
+        self._check(self._lib.tdgl_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
+        return ms.value
+
+    def info(self) -> dict:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.tdgl_get_info(self._h, out, 8))
+        keys = ["n_sites", "n_edges", "nnz", "amg_levels", "amg_nnz", "amg_coarsest",
+                "launches", "graph_mode"]
+        return dict(zip(keys, [int(v) for v in out]))
+
+
+def host_amg_probe(mesh, theta=0.08, max_coarse=200, rhs=None, max_iter=200, rtol=1e-10):
+    """Host-only: build the AMG hierarchy in C++ and (optionally) run host PCG with it."""
+    lib = _lib.load()
+    em = mesh.edge_mesh
+    n, E = len(mesh.sites), len(em.edges)
+    nl = C.c_int32(0)
+    rows = (C.c_int64 * 32)()
+    nnz = (C.c_int64 * 32)()
+    it = C.c_int32(0)
+    x = None
+    if rhs is not None:
+        rhs = as_f64(rhs, (n,))
+        x = np.zeros(n)
+    rc = lib.tdgl_host_amg_probe(n, E, ptr(as_i64(em.edges)), ptr(as_f64(em.edge_lengths)),
+                                 ptr(as_f64(em.dual_edge_lengths)), theta, max_coarse,
+                                 C.byref(nl), rows, nnz, ptr(rhs), ptr(x), max_iter, rtol,
+                                 C.byref(it))
+    if rc != 0:
+        raise _lib.TDGLLibraryError(lib.tdgl_last_error(None).decode())
+    L = nl.value
+    return dict(levels=L, rows=[int(rows[i]) for i in range(L)],
+                nnz=[int(nnz[i]) for i in range(L)], x=x, iterations=it.value)

@@ -1,0 +1,214 @@
+"""``Solution`` / ``TDGLData`` / ``DynamicsData``: the output format of the path.
+
+Field names, shapes and the per-save grouping follow the reference's HDF5 layout
+(``DataHandler.save_time_step`` tdgl/solver/runner.py:155-183; ``TDGLData``
+tdgl/solution/data.py:68-93; ``DynamicsData`` data.py:146-168, 385-425).  h5py/libhdf5 are
+not in this image, so saves are kept in memory and ``Solution.to_npz`` writes the same
+tree (keys ``data/<k>/psi`` ...) to one ``.npz``; post-processing (fluxoids, Biot-Savart,
+plotting) is outside the hot path and not re-implemented.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from datetime import datetime
+from typing import Any, Dict, List, Optional, Union
+
+import numpy as np
+
+
+@dataclasses.dataclass(eq=False)
+class TDGLData:
+    """Raw solver data at one saved step (reference data.py:68-93)."""
+
+    step: int
+    epsilon: np.ndarray
+    psi: np.ndarray
+    mu: np.ndarray
+    applied_vector_potential: np.ndarray
+    induced_vector_potential: np.ndarray
+    supercurrent: np.ndarray
+    normal_current: np.ndarray
+    state: Dict[str, Any]
+
+
+@dataclasses.dataclass(eq=False)
+class DynamicsData:
+    """Per-step scalars (reference data.py:146-228): ``time = cumsum(dt)``."""
+
+    dt: np.ndarray
+    time: np.ndarray = dataclasses.field(init=False)
+    mu: Union[np.ndarray, None] = None
+    theta: Union[np.ndarray, None] = None
+    screening_iterations: Union[np.ndarray, None] = None
+
+    def __post_init__(self):
+        self.time = np.cumsum(self.dt)
+
+    def time_slice(self, tmin: float = -np.inf, tmax: float = np.inf) -> np.ndarray:
+        ts = self.time
+        (indices,) = np.where((ts >= tmin) & (ts <= tmax))
+        return indices
+
+    def closest_time(self, time: float) -> int:
+        return int(np.argmin(np.abs(self.time - time)))
+
+    def voltage(self, i: int = 0, j: int = 1) -> np.ndarray:
+        if self.mu is None:
+            raise ValueError("No voltage data available.")
+        if self.mu.shape[0] == 1:
+            raise ValueError("The solution has only one probe point.")
+        return self.mu[i] - self.mu[j]
+
+    def phase_difference(self, i: int = 0, j: int = 1) -> np.ndarray:
+        if self.theta is None:
+            raise ValueError("No phase data available.")
+        if self.theta.shape[0] == 1:
+            raise ValueError("The solution has only one probe point.")
+        return self.theta[i] - self.theta[j]
+
+    def mean_voltage(self, i: int = 0, j: int = 1, tmin: float = -np.inf,
+                     tmax: float = np.inf) -> float:
+        if self.mu is None:
+            raise ValueError("No voltage data available.")
+        indices = self.time_slice(tmin, tmax)
+        return float(np.average(self.voltage(i, j)[indices], weights=self.dt[indices]))
+
+
+class SavedSteps:
+    """In-memory stand-in for the reference's output file: ``fixed`` holds the arrays
+    saved once at the root, ``groups[k]`` the k-th ``data/<k>`` group."""
+
+    def __init__(self):
+        self.fixed: Dict[str, np.ndarray] = {}
+        self.groups: List[Dict[str, Any]] = []
+
+    def save_fixed_values(self, fixed: Dict[str, np.ndarray]) -> None:
+        for k, v in fixed.items():
+            self.fixed[k] = np.array(v)
+
+    def save_time_step(self, state: Dict[str, Any], data: Dict[str, np.ndarray],
+                       running_state: Optional[Dict[str, np.ndarray]]) -> None:
+        grp: Dict[str, Any] = {"attrs": dict(state, timestamp=datetime.now().isoformat())}
+        for k, v in data.items():
+            grp[k] = np.array(v)
+        if running_state is not None:
+            grp["running_state"] = {k: np.squeeze(np.array(v)) for k, v in running_state.items()}
+        self.groups.append(grp)
+
+    def dynamics(self) -> Optional[DynamicsData]:
+        """Concatenate the running-state buffers exactly as ``DynamicsData.from_hdf5``
+        does (data.py:396-425): unfilled entries have dt == 0 and are dropped."""
+        dts, mus, thetas = [], [], []
+        for grp in self.groups:
+            rs = grp.get("running_state")
+            if rs is None:
+                continue
+            dts.append(np.atleast_1d(rs["dt"]))
+            if "mu" in rs:
+                mus.append(np.atleast_2d(rs["mu"]))
+            if "theta" in rs:
+                thetas.append(np.atleast_2d(rs["theta"]))
+        if not dts:
+            return None
+        dt = np.concatenate(dts)
+        mask = dt > 0
+        mu = np.concatenate(mus, axis=1)[..., mask] if mus else None
+        theta = np.concatenate(thetas, axis=1)[..., mask] if thetas else None
+        return DynamicsData(dt=dt[mask], mu=mu, theta=theta)
+
+
+class Solution:
+    """Results of a simulation (reference solution/solution.py:59-196, data access only)."""
+
+    def __init__(self, *, device, options, saved: SavedSteps, applied_vector_potential=None,
+                 terminal_currents=None, disorder_epsilon=None, total_seconds: float = 0.0,
+                 path: Optional[str] = None, solver_stats: Optional[dict] = None):
+        self.device = device
+        self.options = options
+        self.path = path
+        self.applied_vector_potential = applied_vector_potential
+        self.terminal_currents = terminal_currents
+        self.disorder_epsilon = disorder_epsilon
+        self.total_seconds = total_seconds
+        self.solver_stats = solver_stats or {}
+        self._saved = saved
+        self._time_created = datetime.now()
+        self.data_range = (0, len(saved.groups) - 1)
+        self.dynamics = saved.dynamics()
+        self.tdgl_data: Optional[TDGLData] = None
+        self._solve_step = -1
+        self.load_tdgl_data(-1)
+
+    def load_tdgl_data(self, solve_step: int = -1) -> None:
+        step_min, step_max = self.data_range
+        if solve_step == 0:
+            step = step_min
+        elif solve_step < 0:
+            step = step_max + 1 + solve_step
+        else:
+            step = solve_step
+        grp = self._saved.groups[step]
+
+        def get(key):
+            if key in self._saved.fixed:
+                return self._saved.fixed[key]
+            return grp.get(key)
+
+        self.tdgl_data = TDGLData(
+            step=step, epsilon=get("epsilon"), psi=get("psi"), mu=get("mu"),
+            applied_vector_potential=get("applied_vector_potential"),
+            induced_vector_potential=get("induced_vector_potential"),
+            supercurrent=get("supercurrent"), normal_current=get("normal_current"),
+            state={k: v for k, v in grp["attrs"].items()})
+        self._solve_step = step
+
+    @property
+    def solve_step(self) -> int:
+        return self._solve_step
+
+    @solve_step.setter
+    def solve_step(self, step: int) -> None:
+        self.load_tdgl_data(step)
+
+    @property
+    def times(self) -> Optional[np.ndarray]:
+        """reference solution.py:134-146"""
+        if self.dynamics is None:
+            return None
+        times = self.dynamics.time
+        saved_times = times[:: self.options.save_every]
+        if saved_times[-1] == times[-1]:
+            return saved_times.copy()
+        return np.concatenate([saved_times, times[-1:]])
+
+    def closest_solve_step(self, time: float) -> int:
+        return int(np.argmin(np.abs(self.times - time)))
+
+    @property
+    def field_units(self) -> str:
+        return str(self.options.field_units)
+
+    @property
+    def current_units(self) -> str:
+        return str(self.options.current_units)
+
+    def to_npz(self, path: str) -> str:
+        """Write the reference's output tree (root fixed arrays, ``data/<k>/...`` groups with
+        ``step/time/dt`` attributes and ``running_state``) to one compressed ``.npz``."""
+        out: Dict[str, np.ndarray] = {}
+        for k, v in self._saved.fixed.items():
+            out[k] = v
+        for i, grp in enumerate(self._saved.groups):
+            for k, v in grp.items():
+                if k == "attrs":
+                    for ak, av in v.items():
+                        out[f"data/{i}/attrs/{ak}"] = np.array(av)
+                elif k == "running_state":
+                    for rk, rv in v.items():
+                        out[f"data/{i}/running_state/{rk}"] = rv
+                else:
+                    out[f"data/{i}/{k}"] = v
+        np.savez_compressed(path, **out)
+        self.path = path if path.endswith(".npz") else path + ".npz"
+        return self.path

@@ -1,0 +1,394 @@
+"""``TDGLSolver`` / ``solve``: the reference's public solve API for the hot path, with the
+per-step work done by the CUDA engine.
+
+Mirrors ``tdgl.solve`` (tdgl/solver/solve.py:9-52), ``TDGLSolver.__init__`` / ``.solve``
+(tdgl/solver/solver.py:117-323, 716-827) and the loop and save cadence of
+``Runner.run`` / ``_run_stage`` (tdgl/solver/runner.py:288-454).  What the reference
+does per step in NumPy/SciPy (``TDGLSolver.update`` solver.py:580-714) happens inside
+``tdgl_advance`` on the device; Python wakes up only at save steps and for
+time-dependent terminal currents / epsilon.
+"""
+
+from __future__ import annotations
+
+import inspect
+import logging
+from datetime import datetime
+from typing import Callable, Dict, NamedTuple, Optional, Sequence, Union
+
+import numpy as np
+
+from .engine import DeviceEngine, StepFailed
+from .options import SolverOptions
+from .solution import SavedSteps, Solution
+from .synthetic import TerminalInfo
+
+logger = logging.getLogger("solver")
+
+
+class SolverResult(NamedTuple):
+    """Same tuple as the reference's ``SolverResult`` (solver.py:63-85)."""
+
+    dt: float
+    psi: np.ndarray
+    mu: np.ndarray
+    supercurrent: np.ndarray
+    normal_current: np.ndarray
+    A_induced: np.ndarray
+    A_applied: Optional[np.ndarray] = None
+    epsilon: Optional[np.ndarray] = None
+
+
+def validate_terminal_currents(terminal_currents, terminal_info, solver_options,
+                               num_evals: int = 100) -> None:
+    """Current conservation check, same errors as the reference (solver.py:35-60)."""
+
+    def check_total_current(currents: Dict[str, float]):
+        names = set(t.name for t in terminal_info)
+        if unknown := set(currents).difference(names):
+            raise ValueError(f"Unknown terminal(s) in terminal currents: {list(unknown)}.")
+        total_current = sum(currents.values())
+        if total_current:
+            raise ValueError(
+                f"The sum of all terminal currents must be 0 (got {total_current:.2e}).")
+
+    if callable(terminal_currents):
+        times = np.random.default_rng().random(num_evals) * solver_options.solve_time
+        for t in times:
+            check_total_current(terminal_currents(t))
+    else:
+        check_total_current(terminal_currents)
+
+
+class _RunningState:
+    """reference ``RunningState`` (runner.py:186-221)."""
+
+    def __init__(self, names_and_sizes: Dict[str, int], buffer_size: int):
+        self.step = 0
+        self.buffer_size = buffer_size
+        self.names_and_sizes = names_and_sizes
+        self.clear()
+
+    def clear(self) -> None:
+        self.step = 0
+        self.values = {name: np.zeros((size, self.buffer_size))
+                       for name, size in self.names_and_sizes.items()}
+
+
+class TDGLSolver:
+    """Drop-in for ``tdgl.TDGLSolver`` on the B200 engine.
+
+    Use ``TDGLSolver(device, options, ...)`` exactly as in the reference, or
+    ``TDGLSolver.from_dimensionless(...)`` when the inputs are already dimensionless
+    mesh-level arrays (synthetic workloads, tests).
+    """
+
+    def __init__(self, device, options: SolverOptions,
+                 applied_vector_potential: Union[Callable, float] = 0.0,
+                 terminal_currents: Union[Callable, Dict[str, float], None] = None,
+                 disorder_epsilon: Union[Callable, float] = 1.0, seed_solution=None):
+        from .device import constant_field_vector_potential, unit_scales
+
+        self.device = device
+        self.options = options
+        options.validate()
+        self.terminal_currents = terminal_currents
+        self.seed_solution = seed_solution
+        mesh = device.mesh
+        if mesh is None:
+            raise ValueError("The device has no mesh: call device.make_mesh() first.")
+        xi = device.layer.coherence_length
+        scales = unit_scales(device, options.field_units, options.current_units)
+        sites = xi * mesh.sites
+        edge_centers = xi * mesh.edge_mesh.centers
+        z0 = device.layer.z0 * np.ones(len(edge_centers))
+        # applied vector potential at the edge centres (solver.py:164-189)
+        if getattr(applied_vector_potential, "time_dependent", False):
+            raise NotImplementedError(
+                "time-dependent applied_vector_potential is not on the B200 path yet")
+        if not callable(applied_vector_potential):
+            b = float(applied_vector_potential)
+
+            def applied_vector_potential(x, y, z, _b=b):
+                return constant_field_vector_potential(x, y, z, Bz=_b)
+
+        self.applied_vector_potential = applied_vector_potential
+        A = np.asarray(applied_vector_potential(edge_centers[:, 0], edge_centers[:, 1], z0))
+        A = scales.A_scale * A[:, :2]
+        if A.shape != edge_centers.shape:
+            raise ValueError(f"Unexpected shape for vector_potential: {A.shape}.")
+        # epsilon at the sites (solver.py:191-216)
+        dynamic_epsilon = False
+        if callable(disorder_epsilon):
+            argspec = inspect.getfullargspec(disorder_epsilon)
+            dynamic_epsilon = "t" in argspec.kwonlyargs
+            vectorized = (argspec.kwonlydefaults is not None
+                          and argspec.kwonlydefaults.get("vectorized", False))
+            eps_func = disorder_epsilon
+        else:
+            value = float(disorder_epsilon)
+            vectorized = True
+
+            def eps_func(r, _v=value):
+                return _v * np.ones(len(r), dtype=float)
+
+        self.disorder_epsilon = disorder_epsilon
+
+        def eval_eps(t=None):
+            kw = dict(t=t) if dynamic_epsilon else {}
+            if vectorized:
+                return np.asarray(eps_func(sites, **kw), dtype=float)
+            return np.array([float(eps_func(r, **kw)) for r in sites])
+
+        terminal_info = device.terminal_info()
+        names = [t.name for t in terminal_info]
+        if terminal_currents is None:
+            terminal_currents = {name: 0 for name in names}
+        if callable(terminal_currents):
+            user_func = terminal_currents
+            static_currents = False
+        else:
+            filled = {name: terminal_currents.get(name, 0) for name in names}
+            unknown = set(terminal_currents).difference(names)
+            if unknown:
+                raise ValueError(f"Unknown terminal(s) in terminal currents: {list(unknown)}.")
+
+            def user_func(t, _c=filled):
+                return _c
+
+            static_currents = True
+        J_scale = scales.J_scale
+        self._setup(mesh, options, A, eval_eps, dynamic_epsilon, terminal_info,
+                    lambda t: {k: J_scale * v for k, v in user_func(t).items()},
+                    static_currents, device.probe_point_indices, device.layer.u,
+                    device.layer.gamma)
+
+    @classmethod
+    def from_dimensionless(cls, mesh, options: SolverOptions, *, A_applied, epsilon,
+                           terminal_info: Sequence[TerminalInfo] = (),
+                           terminal_currents: Union[Callable, Dict[str, float], None] = None,
+                           probe_point_indices: Optional[Sequence[int]] = None,
+                           u: float = 5.79, gamma: float = 10.0, device=None) -> "TDGLSolver":
+        """Inputs as the reference holds them after ``__init__``: ``A_applied`` [E, 2] in
+        units of xi*Bc2, currents already multiplied by ``J_scale``."""
+        self = object.__new__(cls)
+        self.device = device
+        self.options = options
+        options.validate()
+        self.terminal_currents = terminal_currents
+        self.seed_solution = None
+        self.applied_vector_potential = None
+        self.disorder_epsilon = None
+        eps = np.asarray(epsilon, dtype=float)
+        names = [t.name for t in terminal_info]
+        if terminal_currents is None:
+            terminal_currents = {n: 0.0 for n in names}
+        if callable(terminal_currents):
+            func, static = terminal_currents, False
+        else:
+            filled = {n: terminal_currents.get(n, 0) for n in names}
+            func, static = (lambda t, _c=filled: _c), True
+        self._setup(mesh, options, np.asarray(A_applied, float), lambda t=None: eps, False,
+                    tuple(terminal_info), func, static, probe_point_indices, u, gamma)
+        return self
+
+    # ------------------------------------------------------------------------------------
+    def _setup(self, mesh, options, A, eval_eps, dynamic_epsilon, terminal_info, current_func,
+               static_currents, probe_points, u, gamma):
+        self.mesh = mesh
+        self.u, self.gamma = u, gamma
+        self.num_edges = len(mesh.edge_mesh.edges)
+        self.current_A_applied = A
+        self._eval_eps = eval_eps
+        self.dynamic_epsilon = dynamic_epsilon
+        self.dynamic_vector_potential = False
+        epsilon = eval_eps(0.0) if dynamic_epsilon else eval_eps()
+        if np.any(epsilon > 1):
+            raise ValueError("The disorder parameter epsilon must be <= 1")
+        self.epsilon = epsilon
+        self.terminal_info = tuple(terminal_info)
+        self.terminal_names = [t.name for t in self.terminal_info]
+        for term in self.terminal_info:
+            if term.length == 0:
+                raise ValueError(
+                    f"Terminal {term.name!r} does not contain any points"
+                    " on the boundary of the mesh.")
+        self.current_func = current_func
+        self.static_currents = static_currents
+        validate_terminal_currents(current_func, self.terminal_info, options)
+        idx = [np.asarray(t.site_indices, dtype=np.int64) for t in self.terminal_info]
+        fixed = np.concatenate(idx) if idx else np.array([], dtype=np.int64)
+        self.terminal_current_densities = {name: 0 for name in self.terminal_names}
+        self.probe_points = None if probe_points is None else [int(p) for p in probe_points]
+        terminal_psi = options.terminal_psi
+        n = len(mesh.sites)
+        self.psi_init = np.ones(n, dtype=np.complex128)            # solver.py:285-287
+        if terminal_psi is not None:
+            self.psi_init[fixed] = terminal_psi
+        self.mu_init = np.zeros(n)
+        self.mu_boundary = np.zeros(len(mesh.edge_mesh.boundary_edge_indices))
+        self.engine = DeviceEngine(
+            mesh, fixed_sites=fixed, fix_psi=(terminal_psi is not None), gamma=gamma, u=u,
+            probe_sites=self.probe_points, device=options.cuda_device, mu_rtol=options.mu_rtol,
+            mu_max_iter=options.mu_max_iterations,
+            use_graph=1 if options.use_cuda_graph else 2,
+            running_capacity=max(int(options.save_every), 1))
+        self.engine.set_link_exponents(A)
+        self.engine.set_epsilon(epsilon)
+        self.engine.set_stepper(
+            dt_init=options.dt_init, dt_max=options.dt_max, adaptive=options.adaptive,
+            adaptive_window=options.adaptive_window,
+            max_solve_retries=options.max_solve_retries,
+            adaptive_time_step_multiplier=options.adaptive_time_step_multiplier)
+        self.stats = dict(steps=0, retries=0, mu_iterations=0)
+
+    def update_mu_boundary(self, time: float) -> None:
+        """reference solver.py:325-345; uploads only when a density changed."""
+        currents = self.current_func(time)
+        changed = False
+        for term in self.terminal_info:
+            dens = (-1 / term.length) * sum(
+                currents.get(name, 0) for name in self.terminal_names if name != term.name)
+            if dens != self.terminal_current_densities[term.name]:
+                self.terminal_current_densities[term.name] = dens
+                self.mu_boundary[np.asarray(term.boundary_edge_indices)] = dens
+                changed = True
+        if changed:
+            self.engine.set_mu_boundary(self.mu_boundary)
+
+    # ------------------------------------------------------------------------------------
+    def _values(self) -> Dict[str, np.ndarray]:
+        psi, mu = self.engine.get_state()
+        js, jn = self.engine.get_currents()
+        out = {"psi": psi, "mu": mu, "supercurrent": js, "normal_current": jn,
+               "induced_vector_potential": np.zeros((self.num_edges, 2))}
+        if self.dynamic_epsilon:
+            out["epsilon"] = self.epsilon
+        return out
+
+    def _run_stage(self, name: str, end_time: float, save: bool, saved: SavedSteps,
+                   running: _RunningState, first_values: Optional[dict]) -> bool:
+        """The loop of ``Runner._run_stage`` (runner.py:379-453) in chunks that end at the
+        next save step (or after one step when a host callback is time-dependent)."""
+        opts = self.options
+        every = max(int(opts.save_every), 1)
+        per_step_host = (not self.static_currents) or self.dynamic_epsilon
+        i, time = 0, 0.0
+        cancelled = False
+
+        def save_step(step):
+            state = {"step": step, "time": time, "dt": self._prev_dt}
+            values = first_values if (step == 0 and first_values is not None) else self._values()
+            saved.save_time_step(state, values, None if step == 0 else running.values)
+
+        try:
+            while True:
+                if i % every == 0:
+                    if save:
+                        save_step(i)
+                    running.clear()
+                self.update_mu_boundary(time)
+                if self.dynamic_epsilon:
+                    self.epsilon = self._eval_eps(time)
+                    self.engine.set_epsilon(self.epsilon)
+                chunk = 1 if per_step_host else every - (i % every)
+                try:
+                    info = self.engine.advance(chunk, end_time, i, time)
+                except StepFailed as exc:
+                    fi = exc.args[1]
+                    raise RuntimeError(
+                        f"Solver failed to converge in {opts.max_solve_retries}"
+                        f" retries at step {fi.failed_step} with dt = {fi.failed_dt:.2e}."
+                        f" Try using a smaller dt_init.") from None
+                k = info.steps_done
+                dt, mu_p, th_p = self.engine.get_running(k)
+                pos = running.step
+                running.values["dt"][0, pos:pos + k] = dt
+                if self.probe_points is not None:
+                    running.values["mu"][:, pos:pos + k] = mu_p
+                    running.values["theta"][:, pos:pos + k] = th_p
+                running.step = pos + (k - 1 if info.finished else k)
+                self._prev_dt = info.dt
+                self.stats["steps"] += k
+                self.stats["retries"] += info.retries
+                self.stats["mu_iterations"] += info.mu_iterations
+                i, time = info.step, info.time
+                if opts.progress_interval and (i // opts.progress_interval
+                                               != (i - k) // opts.progress_interval):
+                    logger.info(f"{name}: Time {time}/{end_time}, dt={info.dt:.2e}")
+                if info.finished:
+                    break
+        except KeyboardInterrupt:
+            logger.warning(f"Cancelling simulation at step {i} of stage {name!r}.")
+            cancelled = True
+        if save and (i % every):
+            save_step(i)
+        return not cancelled
+
+    def solve(self) -> Optional[Solution]:
+        """reference ``TDGLSolver.solve`` (solver.py:716-827) + ``Runner.run``
+        (runner.py:288-328)."""
+        start_time = datetime.now()
+        opts = self.options
+        opts.validate()
+        if self.seed_solution is None:
+            psi0, mu0 = self.psi_init, self.mu_init
+            first = {"psi": psi0.copy(), "mu": mu0.copy(),
+                     "supercurrent": np.zeros(self.num_edges),
+                     "normal_current": np.zeros(self.num_edges),
+                     "induced_vector_potential": np.zeros((self.num_edges, 2))}
+        else:
+            if self.device is not None and self.seed_solution.device != self.device:
+                raise ValueError(
+                    "The seed_solution.device must be equal to the device being simulated.")
+            seed = self.seed_solution.tdgl_data
+            psi0, mu0 = seed.psi, seed.mu
+            first = {"psi": np.array(seed.psi), "mu": np.array(seed.mu),
+                     "supercurrent": np.array(seed.supercurrent),
+                     "normal_current": np.array(seed.normal_current),
+                     "induced_vector_potential": np.array(seed.induced_vector_potential)}
+        self.engine.set_state(psi0, mu0)
+        saved = SavedSteps()
+        fixed = {"applied_vector_potential": self.current_A_applied}
+        if self.dynamic_epsilon:
+            first["epsilon"] = self.epsilon
+        else:
+            fixed["epsilon"] = self.epsilon
+        saved.save_fixed_values(fixed)
+        names = {"dt": 1}
+        if self.probe_points is not None:
+            names["mu"] = len(self.probe_points)
+            names["theta"] = len(self.probe_points)
+        running = _RunningState(names, max(int(opts.save_every), 1))
+        self._prev_dt = float(opts.dt_init)
+        ok = True
+        if opts.skip_time:
+            ok = self._run_stage("Thermalizing", opts.skip_time, False, saved, running, None)
+            running.clear()
+            first = None
+        if not ok:
+            return None
+        self._run_stage("Simulating", opts.solve_time, True, saved, running, first)
+        end_time = datetime.now()
+        logger.info(f"Simulation took {end_time - start_time}")
+        solution = Solution(
+            device=self.device, options=opts, saved=saved,
+            applied_vector_potential=self.applied_vector_potential,
+            terminal_currents=self.terminal_currents, disorder_epsilon=self.disorder_epsilon,
+            total_seconds=(end_time - start_time).total_seconds(),
+            solver_stats=dict(self.stats, **self.engine.info()))
+        if opts.output_file is not None:
+            solution.to_npz(opts.output_file)
+        return solution
+
+
+def solve(device, options: SolverOptions,
+          applied_vector_potential: Union[Callable, float] = 0,
+          terminal_currents: Union[Callable, Dict[str, float], None] = None,
+          disorder_epsilon: Union[float, Callable] = 1, seed_solution=None):
+    """Same signature as ``tdgl.solve`` (tdgl/solver/solve.py:9-52)."""
+    solver = TDGLSolver(device=device, options=options,
+                        applied_vector_potential=applied_vector_potential,
+                        terminal_currents=terminal_currents, disorder_epsilon=disorder_epsilon,
+                        seed_solution=seed_solution)
+    return solver.solve()

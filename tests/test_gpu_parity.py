@@ -1,0 +1,232 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's numbers.
+
+Golden fixtures come from the unmodified reference (oracle/make_golden.py).  Raw mu carries
+an arbitrary constant in the reference (SuperLU on a singular system) and raw psi the
+global phase it integrates to, so trajectories are compared gauge-fixed
+(oracle.tdgl_oracle.gauge_fix).
+
+Tolerances (written here, per BASELINE.json "psi within 1e-6 rel-tol after 1000 steps"):
+  * single operators: 1e-12 relative (only summation order / libm differ);
+  * smooth trajectories (film20_fixed, 1000 steps): 1e-6 required, 1e-8 asserted;
+  * trajectories with vortex nucleation (chaotic amplification of roundoff): 1e-6 on the
+    early snapshot, physics-level agreement at the end.
+"""
+import numpy as np
+import pytest
+
+from helpers import CASES, load_case
+from oracle import tdgl_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(c, **kw):
+    from tdgl_b200.engine import DeviceEngine
+
+    fixed = (np.concatenate([np.asarray(t.site_indices) for t in c.terminals])
+             if c.terminals else None)
+    eng = DeviceEngine(c.mesh, fixed_sites=fixed, fix_psi=True, gamma=c.gamma, u=c.u,
+                       probe_sites=c.probes, **kw)
+    eng.set_link_exponents(c.A)
+    eng.set_epsilon(c.eps)
+    return eng
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_operators_match_reference(name):
+    c = load_case(name)
+    g = c.g
+    with _engine(c) as eng:
+        psi, mu, dt = g["op_psi"], g["op_mu"], float(g["op_dt"])
+        assert _rel(eng.psi_laplacian(psi), g["op_lap_psi"]) < 1e-12
+        new_psi, new_sq, failed = eng.psi_step(psi, mu, dt)
+        assert not failed
+        assert _rel(new_psi, g["op_psi_new"]) < 1e-12
+        assert _rel(new_sq, g["op_sq_new"]) < 1e-12
+        eng.set_mu_boundary(g["op_mu_boundary"])
+        assert _rel(eng.mu_rhs(psi), g["op_rhs"]) < 1e-12
+        assert _rel(eng.mu_laplacian(mu), g["op_lap_mu"]) < 1e-12
+        # mu solve: L mu = rhs for a compatible rhs; compare with the rhs it reproduces and
+        # with the known solution up to the constant
+        rhs = g["op_lap_mu"]
+        sol, its, res = eng.mu_solve(rhs)
+        assert res < 1e-10 and 0 < its < 100
+        a = c.mesh.areas
+        ref = mu - np.dot(a, mu) / a.sum()
+        assert _rel(sol, ref) < 1e-8
+        assert abs(np.dot(a, sol)) / a.sum() < 1e-12
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_psi_step_failure_flag(name):
+    """disc < 0 must be reported like the reference's ``None`` (solver.py:435-436)."""
+    c = load_case(name)
+    g = c.g
+    with _engine(c) as eng:
+        psi = g["op_psi"]
+        # a huge dt makes the discriminant negative somewhere
+        res = orc.solve_for_psi_squared(psi, np.abs(psi) ** 2, g["op_mu"], c.eps, c.gamma, c.u,
+                                        50.0, _oracle(c).operators.psi_laplacian)
+        _, _, failed = eng.psi_step(psi, g["op_mu"], 50.0)
+        assert failed == (res is None)
+
+
+def _oracle(c):
+    kw = {k: v for k, v in c.opts.items() if k in orc.OracleOptions.__dataclass_fields__}
+    cf = (lambda t: c.currents) if c.currents else None
+    return orc.OracleSolver(c.mesh, orc.OracleOptions(**kw), c.A, c.eps, u=c.u, gamma=c.gamma,
+                            terminal_info=[orc.TerminalInfo(*t) for t in c.terminals],
+                            current_func=cf, probe_points=c.probes)
+
+
+def _run_cuda(c, use_graph=True, mu_rtol=1e-10, snapshots=()):
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    kw = dict(c.opts)
+    solve_time = kw.pop("solve_time")
+    save_every = 250
+    opts = SolverOptions(solve_time=solve_time if c.max_steps is None else 1e9,
+                         save_every=save_every, use_cuda_graph=use_graph, mu_rtol=mu_rtol, **kw)
+    solver = TDGLSolver.from_dimensionless(
+        c.mesh, opts, A_applied=c.A, epsilon=c.eps, terminal_info=c.terminals,
+        terminal_currents=c.currents or None, probe_point_indices=c.probes, u=c.u,
+        gamma=c.gamma)
+    if c.max_steps is not None:
+        # fixed number of updates: drive the engine like Runner would, without an end time
+        eng = solver.engine
+        eng.set_state(solver.psi_init, solver.mu_init)
+        solver.update_mu_boundary(0.0)
+        snaps = {}
+        step, time, dts = 0, 0.0, []
+        while step < c.max_steps:
+            n = min(save_every, c.max_steps - step)
+            if step in snapshots:
+                snaps[step] = eng.get_state()
+            info = eng.advance(n, 1e300, step, time)
+            dts.append(eng.get_running(info.steps_done)[0])
+            step, time = info.step, info.time
+        psi, mu = eng.get_state()
+        js, jn = eng.get_currents()
+        return dict(psi=psi, mu=mu, supercurrent=js, normal_current=jn,
+                    dt=np.concatenate(dts), steps=step, snaps=snaps, stats=eng.info())
+    sol = solver.solve()
+    snaps = {}
+    for k in range(sol.data_range[1] + 1):
+        sol.solve_step = k
+        snaps[int(sol.tdgl_data.state["step"])] = (sol.tdgl_data.psi, sol.tdgl_data.mu)
+    sol.solve_step = -1
+    d = sol.tdgl_data
+    return dict(psi=d.psi, mu=d.mu, supercurrent=d.supercurrent,
+                normal_current=d.normal_current, dt=sol.dynamics.dt, steps=len(sol.dynamics.dt),
+                snaps=snaps, stats=sol.solver_stats, dynamics=sol.dynamics)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_smooth_trajectory_1000_steps(use_graph):
+    """BASELINE.json: psi within 1e-6 of the reference after 1000 steps."""
+    c = load_case("film20_fixed")
+    g = c.g
+    out = _run_cuda(c, use_graph=use_graph)
+    assert out["steps"] == int(g["steps"]) == 1000
+    ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
+               normal_current=g["normal_current"], dt=g["dt"])
+    d = orc.compare(out, ref, c.mesh.areas)
+    print("film20_fixed", "graph" if use_graph else "host", d, out["stats"])
+    for k in ("psi", "abs_psi", "mu", "supercurrent", "normal_current"):
+        assert d[k] < 1e-8, (k, d)
+    np.testing.assert_allclose(out["dt"], g["dt"], rtol=1e-12)
+    if use_graph:
+        assert out["stats"]["graph_mode"] == 1, "device-side-loop graph was not used"
+
+
+def test_adaptive_vortex_trajectory():
+    c = load_case("film20_adaptive")
+    g = c.g
+    out = _run_cuda(c)
+    a = c.mesh.areas
+    # early snapshot (step 250): roundoff has not been amplified yet
+    k = list(g["snap_steps"]).index(250)
+    psi250, mu250 = out["snaps"][250]
+    d = orc.compare(dict(psi=psi250, mu=mu250), dict(psi=g["snap_psi"][k], mu=g["snap_mu"][k]), a)
+    print("film20_adaptive step 250", d)
+    assert d["psi"] < 1e-6 and d["mu"] < 1e-6, d
+    n = min(250, len(out["dt"]))
+    np.testing.assert_allclose(out["dt"][:n], g["dt"][:n], rtol=1e-6)
+    # end of run: same physics (vortex dynamics amplify 1e-16 differences)
+    ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
+               normal_current=g["normal_current"])
+    dd = orc.compare(out, ref, a)
+    print("film20_adaptive end", dd, "steps", out["steps"], int(g["steps"]), out["stats"])
+    assert abs(out["steps"] - int(g["steps"])) <= max(3, int(0.01 * int(g["steps"])))
+    assert dd["abs_psi"] < 1e-3, dd
+
+
+def test_transport_trajectory():
+    c = load_case("strip_transport")
+    g = c.g
+    out = _run_cuda(c)
+    ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
+               normal_current=g["normal_current"], dt=g["dt"])
+    d = orc.compare(out, ref, c.mesh.areas)
+    print("strip_transport", d, "steps", out["steps"], int(g["steps"]), out["stats"])
+    assert out["steps"] == int(g["steps"])
+    for k in ("psi", "abs_psi", "mu", "supercurrent", "normal_current"):
+        assert d[k] < 1e-6, (k, d)
+    np.testing.assert_allclose(out["dt"], g["dt"], rtol=1e-6)
+    # probe traces: only gauge-invariant combinations are comparable
+    dyn = out["dynamics"]
+    v_ref = g["running_mu"][0] - g["running_mu"][1]
+    np.testing.assert_allclose(dyn.voltage(0, 1), v_ref, atol=1e-6 * np.abs(v_ref).max())
+    # fixed terminal sites keep psi = 0
+    fixed = np.concatenate([np.asarray(t.site_indices) for t in c.terminals])
+    assert np.abs(out["psi"][fixed]).max() == 0.0
+
+
+def test_step_failure_raises_like_reference():
+    """Non-adaptive run with a too-large dt: RuntimeError with the reference's text."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    c = load_case("film20_fixed")
+    opts = SolverOptions(solve_time=10.0, adaptive=False, dt_init=0.5, dt_max=0.5)
+    solver = TDGLSolver.from_dimensionless(c.mesh, opts, A_applied=c.A, epsilon=c.eps)
+    with pytest.raises(RuntimeError, match="Solver failed to converge in 10 retries at step"):
+        solver.solve()
+    o = _oracle(c)
+    o.options.adaptive = False
+    o.options.dt_init = o.tentative_dt = 0.5
+    with pytest.raises(RuntimeError):
+        orc.run(o, end_time=10.0)
+
+
+def test_large_mesh_properties():
+    """Size-independent properties at a size the oracle would not finish quickly: the
+    operator identities of SURVEY.md appendix A on a 250k-site mesh."""
+    from tdgl_b200.engine import DeviceEngine
+    from tdgl_b200.synthetic import film_problem
+
+    mesh, A, eps, _ = film_problem(200, 200, 0.43, b=0.1)
+    n = len(mesh.sites)
+    rng = np.random.default_rng(0)
+    with DeviceEngine(mesh) as eng:
+        eng.set_link_exponents(A)
+        psi = (0.5 + 0.5 * rng.random(n)) * np.exp(2j * np.pi * rng.random(n))
+        a = mesh.areas
+        # linearity of the covariant Laplacian
+        x, y = psi, np.conj(psi[::-1])
+        lhs = eng.psi_laplacian(2.0 * x + 3j * y)
+        rhs = 2.0 * eng.psi_laplacian(x) + 3j * eng.psi_laplacian(y)
+        assert _rel(lhs, rhs) < 1e-12
+        # divergence theorem: the area-weighted sum of div J_s vanishes
+        r = eng.mu_rhs(psi)
+        assert abs(np.dot(a, r)) / np.abs(a * r).sum() < 1e-12
+        # constants are in the null space of the mu Laplacian; solve(L x) returns x - mean
+        assert np.abs(eng.mu_laplacian(np.ones(n))).max() < 1e-9
+        x = rng.normal(size=n)
+        sol, its, res = eng.mu_solve(eng.mu_laplacian(x))
+        assert res < 1e-10 and its < 60, (its, res)
+        assert _rel(sol, x - np.dot(a, x) / a.sum()) < 1e-7
+        print("250k mesh: mu solve iterations", its, "info", eng.info())

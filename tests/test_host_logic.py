@@ -1,0 +1,123 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host-side
+setup (C++ AMG hierarchy) is sound, and the Python mirror of the reference interface
+behaves like the reference (option validation, errors, Runner bookkeeping containers)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tdgl_b200 as tdgl
+from tdgl_b200 import _lib
+from tdgl_b200.engine import host_amg_probe
+from tdgl_b200.mesh import make_film_mesh
+from tdgl_b200.solution import SavedSteps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "tdgl_b200.h")).read()
+    declared = set(re.findall(r"\b(tdgl_[a-z_0-9]+)\s*\(", header))
+    declared -= {"tdgl_handle", "tdgl_config", "tdgl_advance_info"}
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.tdgl_version()
+    assert ctypes.sizeof(_lib.tdgl_config) == 48
+    assert ctypes.sizeof(_lib.tdgl_advance_info) == 88
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    mesh = make_film_mesh(6, 6, 0.5)
+    with pytest.raises(_lib.TDGLLibraryError):
+        tdgl.DeviceEngine(mesh)
+
+
+def test_host_amg_hierarchy_converges():
+    mesh = make_film_mesh(60, 40, 0.43, holes=((5.0, 3.0, 6.0),))
+    n = len(mesh.sites)
+    rng = np.random.default_rng(0)
+    b = rng.normal(size=n)
+    b -= b.mean()
+    r = host_amg_probe(mesh, rhs=b, rtol=1e-10)
+    assert r["levels"] >= 3 and r["rows"][0] == n and r["rows"][-1] <= 200
+    assert sum(r["nnz"]) / r["nnz"][0] < 1.6          # operator complexity
+    assert 0 < r["iterations"] <= 30, r["iterations"]
+    # residual of the symmetrised system
+    em = mesh.edge_mesh
+    w = em.dual_edge_lengths / em.edge_lengths
+    x = r["x"]
+    Ax = np.zeros(n)
+    d = x[em.edges[:, 0]] - x[em.edges[:, 1]]
+    np.add.at(Ax, em.edges[:, 0], w * d)
+    np.add.at(Ax, em.edges[:, 1], -w * d)
+    assert np.linalg.norm(b - Ax) / np.linalg.norm(b) < 1e-9
+
+
+def test_solver_options_validation_matches_reference():
+    with pytest.raises(tdgl.SolverOptionsError, match="dt_init must be less than"):
+        tdgl.SolverOptions(solve_time=1, dt_init=1.0, dt_max=0.1).validate()
+    with pytest.raises(tdgl.SolverOptionsError, match="terminal_psi"):
+        tdgl.SolverOptions(solve_time=1, terminal_psi=2.0).validate()
+    with pytest.raises(tdgl.SolverOptionsError, match="adaptive_time_step_multiplier"):
+        tdgl.SolverOptions(solve_time=1, adaptive_time_step_multiplier=1.5).validate()
+    with pytest.raises(tdgl.SolverOptionsError, match="sparse solver must be one of"):
+        tdgl.SolverOptions(solve_time=1, sparse_solver="magic").validate()
+    o = tdgl.SolverOptions(solve_time=1, sparse_solver="superlu")
+    o.validate()
+    assert o.sparse_solver is tdgl.SparseSolver.SUPERLU
+    assert issubclass(tdgl.SolverOptionsError, ValueError)
+    # the reference's 24 fields come first, in order, with the same defaults
+    import dataclasses
+
+    names = [f.name for f in dataclasses.fields(tdgl.SolverOptions)][:24]
+    assert names == [
+        "solve_time", "skip_time", "dt_init", "dt_max", "adaptive", "adaptive_window",
+        "max_solve_retries", "adaptive_time_step_multiplier", "output_file", "terminal_psi",
+        "gpu", "sparse_solver", "pause_on_interrupt", "save_every", "progress_interval",
+        "monitor", "monitor_update_interval", "field_units", "current_units",
+        "include_screening", "max_iterations_per_step", "screening_tolerance",
+        "screening_step_size", "screening_step_drag"]
+
+
+def test_device_terminals_and_units():
+    layer = tdgl.Layer(london_lambda=2.0, coherence_length=0.5, thickness=0.1)
+    film = tdgl.Polygon("film", points=tdgl.box(10, 4))
+    src = tdgl.Polygon("source", points=tdgl.box(0.1, 4, center=(-5, 0)))
+    drn = tdgl.Polygon("drain", points=tdgl.box(0.1, 4, center=(5, 0)))
+    hole = tdgl.Polygon("hole", points=tdgl.circle(0.8, points=40))
+    dev = tdgl.Device("bar", layer=layer, film=film, holes=[hole], terminals=[src, drn],
+                      probe_points=[(-3, 0), (3, 0)])
+    dev.make_mesh(max_edge_length=0.25)
+    mesh = dev.mesh
+    assert len(mesh.sites) > 500
+    assert abs(mesh.areas.sum() * 0.25 - (40 - np.pi * 0.8**2)) < 0.05   # areas in xi^2
+    info = dev.terminal_info()
+    assert [t.name for t in info] in (["source", "drain"], ["drain", "source"])
+    for t in info:
+        assert abs(t.length - 4.0) < 1e-9
+        assert len(t.site_indices) == len(t.boundary_edge_indices) + 1
+    # Bc2 = Phi0 / (2 pi xi^2) with xi = 0.5 um
+    assert abs(dev.Bc2 - 2.067833848e-15 / (2 * np.pi * (0.5e-6) ** 2)) < 1e-12
+    assert len(dev.probe_point_indices) == 2
+    assert dev == dev.copy()
+
+
+def test_saved_steps_dynamics_matches_reference_layout():
+    s = SavedSteps()
+    s.save_fixed_values({"epsilon": np.ones(4)})
+    s.save_time_step({"step": 0, "time": 0.0, "dt": 1e-3}, {"psi": np.ones(4, complex)}, None)
+    rs = {"dt": np.array([[1e-3, 2e-3, 0.0]]), "mu": np.array([[1.0, 2.0, 0.0], [3.0, 4.0, 0.0]])}
+    s.save_time_step({"step": 2, "time": 3e-3, "dt": 2e-3}, {"psi": np.ones(4, complex)}, rs)
+    dyn = s.dynamics()
+    np.testing.assert_allclose(dyn.dt, [1e-3, 2e-3])
+    np.testing.assert_allclose(dyn.time, [1e-3, 3e-3])
+    np.testing.assert_allclose(dyn.voltage(0, 1), [-2.0, -2.0])
