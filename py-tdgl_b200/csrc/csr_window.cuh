@@ -1,0 +1,411 @@
+// CSR row-window kernels (sm_100a): every sparse operator of the step streams its CSR
+// arrays through shared memory with the TMA engine and does the per-row arithmetic there.
+//
+//   one CTA  = one window of blockDim.x consecutive rows, one thread per row
+//   thread 0 = reads the two row pointers that bound the window and issues one
+//              cp.async.bulk (global -> shared, mbarrier complete_tx) per CSR array for
+//              the window's whole nnz extent: the matrix moves in a few multi-KB
+//              transactions that need no registers, several CTAs per SM keep > 100 KB in
+//              flight per SM, which is what saturating HBM3e takes;
+//   others   = meanwhile fetch their own row pointers and row-local vector entries;
+//   then     = every thread walks its row out of shared memory, gathers x[col] through
+//              L1/L2 (sites are numbered along a Z-order curve, so a window's columns are
+//              mostly the window itself) and applies the operator's epilogue.
+//
+// The CSR arrays are static for a whole solve; only the vectors change.  All streaming
+// traffic of a kernel is therefore issued BEFORE griddep_wait(): under programmatic
+// dependent launch the next kernel's matrix windows are already in flight while the
+// previous kernel drains.
+//
+// Alignment: cp.async.bulk needs 16-byte aligned addresses and sizes, so a window stages
+// the nnz range [ptr[r0] & ~3, (ptr[r1] + 3) & ~3); the arrays carry 4 padding elements.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace tdgl {
+
+constexpr int kWinRows = 256;  // default rows per window (= threads per CTA)
+
+struct WinCsr {
+  int rows = 0;
+  int cap = 0;               // max over windows of the aligned nnz extent (elements)
+  const int* ptr = nullptr;  // rows + 1
+  const int* idx = nullptr;  // nnz (+4 padding)
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Programmatic dependent launch: block until the kernels this launch depends on have
+// completed and flushed (a no-op for an ordinary launch).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ---- staging ---------------------------------------------------------------------------------
+
+struct WinRow {
+  int row;     // global row of this thread (may be >= rows)
+  int kb, ke;  // extent of the row inside the staged arrays
+};
+
+// Issues the window's bulk copies and returns this thread's row extent.  SA / SB are the
+// element sizes of up to two value arrays that share the matrix structure (SB = 0: one).
+// Shared layout: [valA: cap*SA][valB: cap*SB][idx: cap*4].  Ends with __syncthreads().
+template <int SA, int SB>
+__device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA,
+                                               const void* valB, unsigned char* smem,
+                                               uint64_t* bar) {
+  const int r0 = blockIdx.x * blockDim.x;
+  const int r1 = min(r0 + static_cast<int>(blockDim.x), m.rows);
+  const int k0a = __ldg(m.ptr + r0) & ~3;
+  if (threadIdx.x == 0) {
+    const int k1a = (__ldg(m.ptr + r1) + 3) & ~3;
+    const uint32_t n = static_cast<uint32_t>(k1a - k0a);
+    mbar_init(bar, 1);
+    mbar_arrive_expect_tx(bar, n * (SA + SB + 4));
+    if (n > 0) {
+      bulk_g2s(smem, static_cast<const unsigned char*>(valA) + static_cast<size_t>(k0a) * SA,
+               n * SA, bar);
+      if (SB > 0)
+        bulk_g2s(smem + static_cast<size_t>(m.cap) * SA,
+                 static_cast<const unsigned char*>(valB) + static_cast<size_t>(k0a) * SB, n * SB,
+                 bar);
+      bulk_g2s(smem + static_cast<size_t>(m.cap) * (SA + SB), m.idx + k0a, n * 4, bar);
+    }
+  }
+  WinRow w;
+  w.row = r0 + threadIdx.x;
+  w.kb = w.ke = 0;
+  if (w.row < m.rows) {
+    w.kb = __ldg(m.ptr + w.row) - k0a;
+    w.ke = __ldg(m.ptr + w.row + 1) - k0a;
+  }
+  __syncthreads();  // the initialised barrier is visible to every waiter
+  return w;
+}
+
+// sum_k val[k] * x[idx[k]] over the staged row, four gathers in flight per thread, added in
+// column order.
+__device__ __forceinline__ double row_dot(const double* __restrict__ sv,
+                                          const int* __restrict__ si, int kb, int ke,
+                                          const double* __restrict__ x) {
+  double s = 0.0;
+  const int last = ke - 1;
+#pragma unroll 2
+  for (int k = kb; k < ke; k += 4) {
+    const int k1 = min(k + 1, last), k2 = min(k + 2, last), k3 = min(k + 3, last);
+    const double x0 = __ldg(x + si[k]), x1 = __ldg(x + si[k1]), x2 = __ldg(x + si[k2]),
+                 x3 = __ldg(x + si[k3]);
+    const double v0 = sv[k], v1 = (k + 1 < ke) ? sv[k1] : 0.0, v2 = (k + 2 < ke) ? sv[k2] : 0.0,
+                 v3 = (k + 3 < ke) ? sv[k3] : 0.0;
+    s = fma(v0, x0, s);
+    s = fma(v1, x1, s);
+    s = fma(v2, x2, s);
+    s = fma(v3, x3, s);
+  }
+  return s;
+}
+
+// complex: sum_k val[k] * x[idx[k]]
+__device__ __forceinline__ double2 row_dot_c(const double2* __restrict__ sv,
+                                             const int* __restrict__ si, int kb, int ke,
+                                             const double2* __restrict__ x) {
+  double sx = 0.0, sy = 0.0;
+  const int last = ke - 1;
+#pragma unroll 2
+  for (int k = kb; k < ke; k += 2) {
+    const int k1 = min(k + 1, last);
+    const double2 x0 = __ldg(x + si[k]), x1 = __ldg(x + si[k1]);
+    const double2 v0 = sv[k];
+    double2 v1 = sv[k1];
+    if (k + 1 >= ke) v1 = make_double2(0.0, 0.0);
+    sx += v0.x * x0.x - v0.y * x0.y;
+    sy += v0.x * x0.y + v0.y * x0.x;
+    sx += v1.x * x1.x - v1.y * x1.y;
+    sy += v1.x * x1.y + v1.y * x1.x;
+  }
+  return make_double2(sx, sy);
+}
+
+// ---- real operators (mu system, AMG levels) ----------------------------------------------------
+
+enum : int { kOpSpmvDot = 0, kOpResidual, kOpPresmooth, kOpJacobi, kOpPlain, kOpPlainAdd };
+
+struct RealArgs {
+  const double* val = nullptr;
+  const double* x = nullptr;     // gathered vector
+  double* y = nullptr;           // row output
+  const double* b = nullptr;     // right-hand side (residual / smoothers)
+  const double* dinv = nullptr;  // 1 / diag (smoothers)
+  const double* w = nullptr;     // kOpJacobi: dot(w, y) -> *red_out
+  double* r = nullptr;           // kOpPresmooth: residual output
+  double omega = 0.0;
+  double* red_out = nullptr;     // reduction result (deterministic), may be null
+};
+
+//  kOpSpmvDot   y = A x ;                         red = dot(x, y)
+//  kOpResidual  y = b - A x ;                     red = ||y||^2
+//  kOpPresmooth y = omega D^-1 b ; r = b - A y    (smoothing from a zero guess + residual)
+//  kOpJacobi    y = x + omega D^-1 (b - A x) ;    red = dot(w, y)
+//  kOpPlain     y = A x ;  kOpPlainAdd  y += A x  (restriction / prolongation)
+template <int OP>
+__global__ void __launch_bounds__(kWinRows)
+kw_real(const Ctl* __restrict__ ctl, WinCsr m, RealArgs a, double* partials,
+        unsigned int* counter) {
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  __shared__ uint64_t bar;
+  __shared__ double red[32];
+  const WinRow w = window_stage<8, 0>(m, a.val, nullptr, win_smem, &bar);
+  const double* sv = reinterpret_cast<const double*>(win_smem);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 8);
+  griddep_wait();
+  const bool live = (ctl->status == 0);
+  const bool in = live && w.row < m.rows;
+  // row-local operands travel while the window lands
+  double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
+  if (in) {
+    if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi) bi = a.b[w.row];
+    if (OP == kOpPresmooth || OP == kOpJacobi) di = a.dinv[w.row];
+    if (OP == kOpSpmvDot || OP == kOpJacobi) xi = a.x[w.row];
+    if (OP == kOpPlainAdd) xi = a.y[w.row];
+    if (OP == kOpJacobi && a.w != nullptr) wi = a.w[w.row];
+  }
+  mbar_wait(&bar, 0);
+  if (!live) return;
+  double d = 0.0;
+  if (in) {
+    double s;
+    if (OP == kOpPresmooth) {
+      // x_j = omega dinv_j b_j on the fly
+      s = 0.0;
+      const int last = w.ke - 1;
+      for (int k = w.kb; k < w.ke; k += 2) {
+        const int k1 = min(k + 1, last);
+        const int j0 = si[k], j1 = si[k1];
+        const double t0 = __ldg(a.dinv + j0) * __ldg(a.b + j0);
+        const double t1 = __ldg(a.dinv + j1) * __ldg(a.b + j1);
+        s = fma(sv[k], a.omega * t0, s);
+        s = fma((k + 1 < w.ke) ? sv[k1] : 0.0, a.omega * t1, s);
+      }
+    } else {
+      s = row_dot(sv, si, w.kb, w.ke, a.x);
+    }
+    if (OP == kOpSpmvDot) {
+      a.y[w.row] = s;
+      d = s * xi;
+    } else if (OP == kOpResidual) {
+      const double ri = bi - s;
+      a.y[w.row] = ri;
+      d = ri * ri;
+    } else if (OP == kOpPresmooth) {
+      a.y[w.row] = a.omega * di * bi;
+      a.r[w.row] = bi - s;
+    } else if (OP == kOpJacobi) {
+      const double yi = xi + a.omega * di * (bi - s);
+      a.y[w.row] = yi;
+      d = wi * yi;
+    } else if (OP == kOpPlain) {
+      a.y[w.row] = s;
+    } else {
+      a.y[w.row] = xi + s;
+    }
+  }
+  if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
+    const double bs = block_sum(d, red);
+    double total;
+    if (grid_sum_last(bs, partials, counter, red, &total)) {
+      if (threadIdx.x == 0) *a.red_out = total;
+    }
+  }
+}
+
+// ---- psi step ----------------------------------------------------------------------------------
+// Fused covariant-Laplacian SpMV + closed-form |psi|^2 update (reference
+// TDGLSolver.solve_for_psi_squared, tdgl/solver/solver.py:418-438); fixed[i] != 0 marks rows
+// the reference replaces by the identity (operators.py:170-184): there (L psi)_i = psi_i.
+__global__ void __launch_bounds__(kWinRows)
+kw_psi_step(Ctl* ctl, WinCsr m, const double2* __restrict__ lval,
+            const unsigned char* __restrict__ fixed, const double2* psi_buf0,
+            const double2* psi_buf1, double2* out_buf0, double2* out_buf1,
+            const double* __restrict__ mu, const double* __restrict__ eps,
+            double* __restrict__ sq_out /* may be null */, double dt_override /* < 0: ctl->dt */) {
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  __shared__ uint64_t bar;
+  __shared__ double s_max[8];
+  __shared__ int s_flag;
+  const WinRow w = window_stage<16, 0>(m, lval, nullptr, win_smem, &bar);
+  const double2* sv = reinterpret_cast<const double2*>(win_smem);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 16);
+  if (threadIdx.x == 0) s_flag = 0;
+  griddep_wait();
+  const bool live = (ctl->status == 0);
+  const int cur = ctl->cur;
+  const double2* __restrict__ psi = cur ? psi_buf1 : psi_buf0;
+  double2* __restrict__ out = cur ? out_buf0 : out_buf1;
+  const double dt = dt_override >= 0.0 ? dt_override : ctl->dt;
+  const bool in = live && w.row < m.rows;
+  double2 p = make_double2(0.0, 0.0);
+  double mui = 0.0, epsi = 0.0;
+  bool fx = false;
+  if (in) {
+    p = psi[w.row];
+    mui = mu[w.row];
+    epsi = eps[w.row];
+    fx = fixed[w.row] != 0;
+  }
+  mbar_wait(&bar, 0);
+  if (!live) return;
+  double dmax = 0.0;
+  int failed = 0;
+  if (in) {
+    double2 lap = row_dot_c(sv, si, w.kb, w.ke, psi);
+    if (fx) lap = p;
+    const PsiOut o = psi_update(p, lap, mui, epsi, ctl->gamma, ctl->u, dt);
+    out[w.row] = o.psi;
+    if (sq_out != nullptr) sq_out[w.row] = o.sq;
+    failed = o.failed;
+    const double d = fabs(o.sq - (p.x * p.x + p.y * p.y));
+    dmax = (d == d) ? d : 0.0;
+  }
+  // max / any are order-free: warp shuffle, then one atomic per block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    failed |= __shfl_xor_sync(0xffffffffu, failed, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_max[warp] = dmax;
+    if (failed) atomicOr(&s_flag, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = s_max[0];
+    for (int k = 1; k < static_cast<int>(blockDim.x >> 5); ++k) mx = fmax(mx, s_max[k]);
+    if (mx > 0.0) atomicMax(&ctl->max_dpsi_bits, (unsigned long long)__double_as_longlong(mx));
+    if (s_flag) atomicOr(&ctl->disc_flag, 1);
+  }
+}
+
+// ---- right-hand side of the mu system ------------------------------------------------------------
+//   rhs_i = (divergence @ J_s)_i - (mu_boundary_laplacian @ mu_boundary)_i
+//         = Im(conj(psi_i) (L~ psi)_i) - bterm_i          (L~: Laplacian without fixed rows)
+//   b_i   = -areas_i * rhs_i ;   r_i = b_i - (A mu)_i ;  bb = ||b||^2, rr = ||r||^2
+// (reference solve_for_observables, solver.py:507-510; identity: SURVEY.md appendix A).
+// The complex and the real matrix share one CSR structure and are staged together.
+__global__ void __launch_bounds__(kWinRows)
+kw_mu_rhs(Ctl* ctl, WinCsr m, const double2* __restrict__ lval, const double* __restrict__ aval,
+          const double2* psi_buf0, const double2* psi_buf1, const double* __restrict__ mu,
+          const double* __restrict__ areas, const double* __restrict__ bterm,
+          double* __restrict__ b, double* __restrict__ r,
+          double* __restrict__ rhs_raw /* may be null: un-symmetrised rhs */, double* partials,
+          unsigned int* counter) {
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  __shared__ uint64_t bar;
+  __shared__ double red[32];
+  __shared__ int s_last;
+  const WinRow w = window_stage<16, 8>(m, lval, aval, win_smem, &bar);
+  const double2* sl = reinterpret_cast<const double2*>(win_smem);
+  const double* sa = reinterpret_cast<const double*>(win_smem + static_cast<size_t>(m.cap) * 16);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 24);
+  griddep_wait();
+  const bool live = (ctl->status == 0);
+  const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
+  const bool in = live && w.row < m.rows;
+  double2 p = make_double2(0.0, 0.0);
+  double ai = 0.0, bt = 0.0;
+  if (in) {
+    p = psi[w.row];
+    ai = areas[w.row];
+    bt = bterm[w.row];
+  }
+  mbar_wait(&bar, 0);
+  if (!live) return;
+  double dbb = 0.0, drr = 0.0;
+  if (in) {
+    const double2 lap = row_dot_c(sl, si, w.kb, w.ke, psi);
+    const double am = row_dot(sa, si, w.kb, w.ke, mu);
+    const double rhs = (p.x * lap.y - p.y * lap.x) - bt;
+    if (rhs_raw != nullptr) rhs_raw[w.row] = rhs;
+    const double bi = -ai * rhs;
+    const double ri = bi - am;
+    b[w.row] = bi;
+    r[w.row] = ri;
+    dbb = bi * bi;
+    drr = ri * ri;
+  }
+  // two sums through one deterministic reduction
+  const double sb = block_sum(dbb, red);
+  const double sr = block_sum(drr, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = sb;
+    partials[2 * blockIdx.x + 1] = sr;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
+      a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
+    }
+    a0 = block_sum(a0, red);
+    a1 = block_sum(a1, red);
+    if (threadIdx.x == 0) {
+      ctl->bb = a0;
+      ctl->rr = a1;
+      *counter = 0u;
+    }
+  }
+}
+
+// y = psi_laplacian @ x with the reference's fixed rows (identity)  — parity / microbench op
+__global__ void __launch_bounds__(kWinRows)
+kw_psi_laplacian(WinCsr m, const double2* __restrict__ lval,
+                 const unsigned char* __restrict__ fixed, const double2* __restrict__ x,
+                 double2* __restrict__ y) {
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  __shared__ uint64_t bar;
+  const WinRow w = window_stage<16, 0>(m, lval, nullptr, win_smem, &bar);
+  const double2* sv = reinterpret_cast<const double2*>(win_smem);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 16);
+  griddep_wait();
+  mbar_wait(&bar, 0);
+  if (w.row < m.rows) {
+    const double2 lap = row_dot_c(sv, si, w.kb, w.ke, x);
+    y[w.row] = fixed[w.row] ? x[w.row] : lap;
+  }
+}
+
+}  // namespace tdgl

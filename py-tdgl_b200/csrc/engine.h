@@ -14,6 +14,7 @@
 
 #include "amg_setup.h"
 #include "kernels.cuh"
+#include "csr_window.cuh"
 
 namespace tdgl {
 
@@ -62,19 +63,19 @@ struct DevBuf {
   }
 };
 
+// A real CSR matrix as the window kernels see it: structure + values + rows per CTA.
 struct CsrView {
-  int rows = 0, lpr = 8;
-  const int* ptr = nullptr;
-  const int* idx = nullptr;
+  WinCsr m;
   const double* val = nullptr;
+  int win = kWinRows;  // rows per window = threads per CTA
 };
 
 struct DevCsr {
-  int rows = 0, cols = 0, lpr = 8;
+  int rows = 0, cols = 0, win = kWinRows, cap = 0;
   int64_t nnz = 0;
-  DevBuf<int> ptr, idx;
+  DevBuf<int> ptr, idx;   // idx / val carry 4 padding elements (see csr_window.cuh)
   DevBuf<double> val;
-  CsrView view() const { return CsrView{rows, lpr, ptr.p, idx.p, val.p}; }
+  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p}, val.p, win}; }
 };
 
 struct DevLevel {
@@ -85,11 +86,29 @@ struct DevLevel {
   DevBuf<double> b, x, y, r;  // work vectors (level 0 aliases CG vectors instead of b / y)
 };
 
-inline int pick_lpr(int64_t nnz, int64_t rows) {
-  const double avg = rows ? static_cast<double>(nnz) / rows : 0.0;
-  if (avg <= 3.0) return 4;
-  if (avg <= 8.5) return 8;
-  if (avg <= 18.0) return 16;
+// Largest aligned nnz extent of any window of `win` rows (shared-memory elements a CTA
+// needs per CSR array).
+inline int window_cap(const std::vector<int32_t>& ptr, int64_t rows, int win) {
+  int cap = 4;
+  for (int64_t r0 = 0; r0 < rows; r0 += win) {
+    const int64_t r1 = std::min<int64_t>(r0 + win, rows);
+    cap = std::max(cap, ((ptr[r1] + 3) & ~3) - (ptr[r0] & ~3));
+  }
+  return cap;
+}
+
+// Rows per window: as many as fit `budget` bytes of shared memory at `bytes_per_nnz`.
+inline int pick_window(const std::vector<int32_t>& ptr, int64_t rows, int bytes_per_nnz,
+                       int budget, int* cap_out) {
+  for (int win = kWinRows; win >= 32; win /= 2) {
+    const int cap = window_cap(ptr, rows, win);
+    if (static_cast<int64_t>(cap) * bytes_per_nnz <= budget || win == 32) {
+      if (static_cast<int64_t>(cap) * bytes_per_nnz > 200 * 1024)
+        throw std::runtime_error("a CSR row window does not fit in shared memory");
+      *cap_out = cap;
+      return win;
+    }
+  }
   return 32;
 }
 
@@ -161,7 +180,7 @@ class Engine {
   DevBuf<double2> lval_;           // covariant Laplacian values (all rows kept)
   DevBuf<unsigned char> fixed_;    // rows the reference replaces by identity
   DevBuf<double> areas_, eps_, bterm_;
-  int lpr0_ = 8;
+  int win0_ = kWinRows, cap0_ = 0;  // window geometry of the site operators
   // ---- edges (caller edge order, internal site indices) -----------------------------------
   DevBuf<int> e0_, e1_;
   DevBuf<double> elen_, weight_, theta_;
@@ -191,7 +210,10 @@ class Engine {
   cudaGraphConditionalHandle h_step_ = 0, h_psi_ = 0, h_cg_ = 0;
 
   // ---- launch sequences ------------------------------------------------------------------
-  int grid_rows(int rows, int lpr) const { return (static_cast<int64_t>(rows) * lpr + kBlock - 1) / kBlock; }
+  static int grid_win(int rows, int win) { return (rows + win - 1) / win; }
+  WinCsr site_csr() const { return WinCsr{N_, cap0_, ptr_.p, idx_.p}; }
+  template <int OP>
+  void launch_real(const CsrView& A, const RealArgs& a);
   int grid_flat(int n) const {
     int g = (n + kBlock - 1) / kBlock;
     return g < 1 ? 1 : (g > 1184 ? 1184 : g);  // 148 SMs x 8 resident blocks
@@ -210,11 +232,12 @@ class Engine {
   void enqueue_cg_iteration(cudaGraphConditionalHandle cond);
   void enqueue_mu_finish();
   void host_solve_loop();   // host-driven CG loop on the current b/r
+  void configure_kernels();
   void build_graph();
   void sync_ctl_to_host();
   void push_ctl();
   DevBuf<double> aval_;  // level-0 mu matrix values; structure shared with ptr_/idx_
-  CsrView A0() const { return CsrView{N_, lpr0_, ptr_.p, idx_.p, aval_.p}; }
+  CsrView A0() const { return CsrView{site_csr(), aval_.p, win0_}; }
   CsrView levelA(size_t l) const { return l == 0 ? A0() : levels_[l].A.view(); }
 };
 

