@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the TDGL per-step hot path (BASELINE.json metric: TDGL time-steps/sec and
+mesh-sites x steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload film1m_holes_transport|film250k_field|film20_cpu]
+
+One bench "step" = one TDGL time step (one ``TDGLSolver.update``): fused psi update, right
+hand side, mu solve, step controller.  Default workload = BASELINE.json configs[2], the
+configuration the metric's 1-GPU target is quoted on: ~1.0M-site square film with four
+circular holes, source/drain terminals and a transport current, adaptive dt.
+
+b200 arm
+  value   whole-job steps/s with the state resident in HBM, timed with CUDA events on the
+          engine's stream (tdgl_advance_info.device_ms), barrier + synchronize on both
+          sides, max over ranks.
+  e2e     the same steps taken one by one through ``TDGLSolver.update`` — the reference's
+          own step seam (tdgl/solver/runner.py:417-423) — with host psi/mu in pinned
+          memory copied to the device and psi', mu', J_s, J_n copied back EVERY step.
+  roofline  dominant kernel of the step, timed on its own with CUDA events after an L2
+          flush; algorithmic bytes per DESIGN.md.
+  cpu_baseline  the oracle port of the reference's scipy.sparse/SuperLU step on this
+          box's host cores (N=1 only; bounded number of steps of the same workload).
+reference arm (--impl reference): that CPU path alone, same workload/metric.
+
+With N > 1 ranks (torchrun) every rank steps a full replica of the workload on its own GPU
+(no data-path collective; "scaling": "weak") — domain decomposition across GPUs is the
+next row of the scope table.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+WORKLOADS = {
+    # BASELINE.json configs[2]
+    "film1m_holes_transport": dict(
+        width=400.0, height=400.0, h=0.4225, b=0.0,
+        holes=((100.0, 100.0, 20.0), (-100.0, 100.0, 20.0), (100.0, -100.0, 20.0),
+               (-100.0, -100.0, 20.0)),
+        terminals=True, current=80.0, opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    # BASELINE.json configs[1]
+    "film250k_field": dict(
+        width=200.0, height=200.0, h=0.43, b=0.1, holes=(), terminals=False, current=0.0,
+        opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    # BASELINE.json configs[0] geometry (perturbed so that every term is active)
+    "film20_cpu": dict(
+        width=20.0, height=20.0, h=0.29, b=0.3, holes=(), terminals=False, current=0.0,
+        disorder=True, opts=dict(dt_init=1e-3, dt_max=1e-3, adaptive=False)),
+}
+
+
+def build_workload(name: str):
+    from tdgl_b200.synthetic import film_problem
+
+    w = WORKLOADS[name]
+    t0 = time.perf_counter()
+    mesh, A, eps, terms = film_problem(w["width"], w["height"], w["h"], b=w["b"],
+                                       holes=w["holes"], terminals=w["terminals"],
+                                       disorder=w.get("disorder", False))
+    currents = None
+    if w["terminals"]:
+        currents = {"source": w["current"], "drain": -w["current"]}
+    return dict(name=name, mesh=mesh, A=A, eps=eps, terms=terms, currents=currents,
+                opts=w["opts"], mesh_seconds=time.perf_counter() - t0)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        for key in ("hbm_gbs", "hbm_GBps", "hbm_gb_s"):
+            if key in d:
+                return float(d[key]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU path (oracle port)
+def cpu_path(work, steps: int, warmup: int, budget_s: float):
+    """The reference's scipy.sparse/SuperLU step (oracle port) on the host cores.  Steps
+    are capped by a time budget; returns steps/s over the steps actually timed."""
+    from oracle import tdgl_oracle as orc
+
+    o = work["opts"]
+    opts = orc.OracleOptions(solve_time=1e9, dt_init=o["dt_init"], dt_max=o["dt_max"],
+                             adaptive=o["adaptive"])
+    cf = (lambda t, _c=work["currents"]: _c) if work["currents"] else None
+    t0 = time.perf_counter()
+    solver = orc.OracleSolver(work["mesh"], opts, work["A"], work["eps"],
+                              terminal_info=[orc.TerminalInfo(*t) for t in work["terms"]],
+                              current_func=cf)
+    factor_s = time.perf_counter() - t0
+    psi, mu = solver.psi_init.copy(), solver.mu_init.copy()
+    t, i = 0.0, 0
+    for _ in range(warmup):
+        dt, psi, mu, _, _ = solver.update(i, t, psi, mu)
+        t += dt
+        i += 1
+    done = 0
+    t0 = time.perf_counter()
+    while done < steps:
+        dt, psi, mu, _, _ = solver.update(i, t, psi, mu)
+        t += dt
+        i += 1
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    return dict(steps=done, seconds=el, steps_per_s=done / el, factor_seconds=factor_s)
+
+
+def threads_used() -> int:
+    # scipy's CSR/CSC matvec, SuperLU's triangular solves and the NumPy elementwise code
+    # of this path are single-threaded whatever OMP_NUM_THREADS says
+    return 1
+
+
+# ------------------------------------------------------------------ main arms
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    work = build_workload(args.workload)
+    n = len(work["mesh"].sites)
+    res = cpu_path(work, args.steps, min(args.warmup, 3), budget_s=args.cpu_budget)
+    ncores = os.cpu_count()
+    sample = (f"{res['steps']} of the {args.steps} requested steps of the full {n}-site workload"
+              f" (time budget {args.cpu_budget:.0f} s; SuperLU factorisation"
+              f" {res['factor_seconds']:.1f} s and mesh build excluded)")
+    line = {
+        "impl": "reference", "metric": "tdgl_steps_per_sec", "value": res["steps_per_s"],
+        "unit": "steps/s", "n_gpus": args.gpus, "steps": res["steps"],
+        "steps_requested": args.steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": 1e3 / res["steps_per_s"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "sites": n,
+                   "edges": len(work["mesh"].edge_mesh.edges)},
+        "site_steps_per_sec": res["steps_per_s"] * n,
+        "cpu_baseline": {"value": res["steps_per_s"], "unit": "steps/s", "cores": threads_used(),
+                         "host_cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": res["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+
+    from tdgl_b200 import SolverOptions, TDGLSolver
+    from tdgl_b200.engine import pinned_empty
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    work = build_workload(args.workload)
+    mesh = work["mesh"]
+    n, n_edges = len(mesh.sites), len(mesh.edge_mesh.edges)
+    K, W = args.steps, args.warmup
+    opts = SolverOptions(solve_time=1e9, save_every=max(K, W, 1), cuda_device=local_rank,
+                         **work["opts"])
+    t0 = time.perf_counter()
+    solver = TDGLSolver.from_dimensionless(
+        mesh, opts, A_applied=work["A"], epsilon=work["eps"], terminal_info=work["terms"],
+        terminal_currents=work["currents"])
+    setup_s = time.perf_counter() - t0
+    eng = solver.engine
+    eng.set_state(solver.psi_init, solver.mu_init)
+    solver.update_mu_boundary(0.0)
+    info0 = eng.info()
+
+    # ---- device-resident throughput -----------------------------------------------------
+    barrier()
+    a = eng.advance(W, 1e300, 0, 0.0) if W > 0 else None
+    step, t = (a.step, a.time) if a is not None else (0, 0.0)
+    launches_before = eng.info()["launches"]
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        b = eng.advance(K, 1e300, step, t)
+        torch.cuda.synchronize()
+    barrier()
+    launches = eng.info()["launches"] - launches_before
+    ms = torch.tensor([b.device_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    steps_per_s = world * K / (ms_total / 1e3)
+    iters_per_step = b.mu_iterations / K
+
+    # ---- end to end through the reference's step seam --------------------------------------
+    psi_h = pinned_empty(n, np.complex128)
+    mu_h = pinned_empty(n, np.float64)
+    out = (pinned_empty(n, np.complex128), pinned_empty(n, np.float64),
+           pinned_empty(n_edges, np.float64), pinned_empty(n_edges, np.float64))
+    p0, m0 = eng.get_state()
+    psi_h[:] = p0
+    mu_h[:] = m0
+    state = {"step": b.step, "time": b.time, "dt": b.dt}
+    Ke = K
+    for phase in ("warm", "timed"):
+        nsteps = 2 if phase == "warm" else Ke
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            res = solver.update(state, None, state["dt"], psi=psi_h, mu=mu_h, out=out)
+            # the step's outputs are the next step's host inputs, as in Runner._run_stage
+            # (swap the pinned buffers instead of copying host -> host)
+            psi_h, mu_h, out = out[0], out[1], (psi_h, mu_h, out[2], out[3])
+            state = {"step": state["step"] + 1, "time": state["time"] + res.dt, "dt": res.dt}
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_steps_per_s = world * Ke / float(e2e_t.item())
+    h2d = 24 * n                     # psi (16 B) + mu (8 B) per site
+    d2h = 24 * n + 16 * n_edges      # psi', mu' + J_s, J_n per edge
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (rank 0, kernels timed alone after an L2 flush) ---------------
+    peak, peak_src = hbm_peak()
+    nnz = info0["nnz"]
+    levels = info0["amg_levels"]
+    kern = {
+        "kw_psi_step": (0, 20 * nnz + 52 * n, 1.0),
+        "kw_mu_rhs": (1, 28 * nnz + 60 * n, 1.0),
+        "kw_real<spmv_dot> fine level": (2, 12 * nnz + 20 * n, iters_per_step),
+    }
+    if levels > 1:
+        kern["kw_real<presmooth> fine level"] = (5, 12 * nnz + 36 * n, iters_per_step)
+        kern["kw_real<jacobi> fine level"] = (6, 12 * nnz + 44 * n, iters_per_step)
+    table = {}
+    for name, (which, nbytes, per_step) in kern.items():
+        kms = eng.time_kernel(which, 20, flush_l2=True)
+        table[name] = {"ms": kms, "bytes": nbytes, "GBps": nbytes / kms / 1e6,
+                       "frac": nbytes / kms / 1e6 / peak, "launches_per_step": per_step,
+                       "share_of_step": per_step * kms / (ms_total / K)}
+    vc_ms = eng.time_kernel(3, 10, flush_l2=True) if levels > 1 else None
+    dom = max(table, key=lambda k: table[k]["share_of_step"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBps"], "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": table[dom]["frac"],
+                "traffic": None, "kernels": table, "vcycle_ms": vc_ms}
+
+    line = {
+        "metric": "tdgl_steps_per_sec", "value": steps_per_s, "unit": "steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "sites": n, "edges": n_edges, "nnz": nnz,
+                   "parallelism": "single GPU" if world == 1 else f"{world} replicas",
+                   "l2": "operators (>= 230 MB at 1M sites) exceed the 126 MB L2; per-kernel"
+                         " roofline timings flush L2 before every launch",
+                   "mu_rtol": opts.mu_rtol, "amg_levels": levels},
+        "site_steps_per_sec": steps_per_s * n,
+        "mu_iterations_per_step": iters_per_step, "retries": b.retries,
+        "setup_seconds": {"mesh": work["mesh_seconds"], "engine": setup_s},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "api": "TDGLSolver.update (pinned host arrays)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu:
+        res = cpu_path(work, args.cpu_steps, 1, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = {
+            "value": res["steps_per_s"], "unit": "steps/s", "cores": threads_used(),
+            "host_cores": os.cpu_count(), "kind": "port",
+            "sample": (f"{res['steps']} steps of the same {n}-site workload from the same initial"
+                       f" state (SuperLU factorisation {res['factor_seconds']:.1f} s and mesh"
+                       " build excluded)")}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="film1m_holes_transport", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--cpu-budget", type=float, default=60.0,
+                    help="seconds of CPU stepping allowed for the cpu baseline / reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        import __graft_entry__ as ge
+
+        ge.build()  # no-op when the in-tree library is current; ranks serialise on a lock
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

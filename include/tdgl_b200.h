@@ -112,6 +112,7 @@ typedef struct tdgl_advance_info {
   int64_t retries;         /* total dt-shrinking retries in this call */
   int64_t mu_iterations;   /* total CG iterations in this call */
   double mu_rel_residual;  /* ||r||/||b|| of the last mu solve */
+  double device_ms;        /* CUDA-event time of the stepping on the engine's stream */
 } tdgl_advance_info;
 
 /* Runs the loop of Runner._run_stage (runner.py:379-433) on the device: up to
@@ -121,6 +122,20 @@ typedef struct tdgl_advance_info {
  * runner.py:294-318, while the solver's adaptive history persists). */
 int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, double time,
                  tdgl_advance_info* info);
+
+/* One call of TDGLSolver.update() exactly at the reference's step seam
+ * (runner.py:417-423, solver.py:580-714): host psi[N] (complex128) / mu[N] in, ONE time
+ * step on the device, host psi', mu', supercurrent[E], normal_current[E] out (any output
+ * pointer may be NULL).  `step` / `time` are Runner's state["step"] / state["time"]; the
+ * dt used is returned in info->dt.  All copies are asynchronous on the engine's stream
+ * when the host buffers are pinned (tdgl_host_alloc). */
+int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t step, double time,
+                double* psi_out, double* mu_out, double* supercurrent, double* normal_current,
+                tdgl_advance_info* info);
+
+/* Page-locked host memory for the arrays that cross the boundary every step. */
+void* tdgl_host_alloc(int64_t bytes);
+void tdgl_host_free(void* p);
 
 /* Current psi[N] (complex128) and mu[N]. */
 int tdgl_get_state(tdgl_handle* h, double* psi, double* mu);
@@ -152,10 +167,17 @@ int tdgl_op_mu_laplacian(tdgl_handle* h, const double* x, double* y);
 int tdgl_op_mu_solve(tdgl_handle* h, const double* rhs, double* mu, int32_t* iterations,
                      double* rel_residual);
 
-/* Time `reps` back-to-back launches of one kernel with CUDA events on the engine's
- * stream; which: 0 psi step (fused SpMV + update), 1 mu rhs, 2 mu SpMV (A p with dot),
- * 3 one V-cycle, 4 one full mu solve from a zero guess.  Returns mean milliseconds. */
-int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, double* mean_ms);
+/* Time one kernel (or kernel sequence) of the step with CUDA events on the engine's
+ * stream; returns the mean milliseconds per launch over `reps` launches after one warm-up.
+ *   which: 0 psi step (fused SpMV + update)        1 mu rhs (+ warm-start residual)
+ *          2 fine-level mu SpMV with dot (A p)     3 one whole V-cycle
+ *          4 one full mu solve from a zero guess   5 fine-level pre-smoothing + residual
+ *          6 fine-level Jacobi post-smoothing      7 fine-level restriction
+ *          8 fine-level prolongation
+ *   flush_l2 != 0: every launch is timed on its own after a kernel that reads a 256 MB
+ *   scratch buffer, so that nothing of the operator is left in the 126 MB L2. */
+int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_l2,
+                     double* mean_ms);
 
 /* Sizes and setup facts: [0] N, [1] E, [2] nnz of a site operator, [3] AMG levels,
  * [4] sum of level nnz, [5] coarsest size, [6] kernels launched so far (host count),

@@ -50,6 +50,7 @@ class tdgl_advance_info(C.Structure):
         ("retries", C.c_int64),
         ("mu_iterations", C.c_int64),
         ("mu_rel_residual", C.c_double),
+        ("device_ms", C.c_double),
     ]
 
 
@@ -71,6 +72,10 @@ SIGNATURES = {
     "tdgl_set_state": (C.c_int, [_P, _P, _P]),
     "tdgl_set_stepper": (C.c_int, [_P, _D, _D, _I32, _I32, _I32, _D]),
     "tdgl_advance": (C.c_int, [_P, _I64, _D, _I64, _D, C.POINTER(tdgl_advance_info)]),
+    "tdgl_update": (C.c_int, [_P, _P, _P, _I64, _D, _P, _P, _P, _P,
+                              C.POINTER(tdgl_advance_info)]),
+    "tdgl_host_alloc": (C.c_void_p, [_I64]),
+    "tdgl_host_free": (None, [_P]),
     "tdgl_get_state": (C.c_int, [_P, _P, _P]),
     "tdgl_get_currents": (C.c_int, [_P, _P, _P]),
     "tdgl_get_running": (C.c_int, [_P, _I64, _P, _P, _P]),
@@ -79,7 +84,7 @@ SIGNATURES = {
     "tdgl_op_mu_rhs": (C.c_int, [_P, _P, _P]),
     "tdgl_op_mu_laplacian": (C.c_int, [_P, _P, _P]),
     "tdgl_op_mu_solve": (C.c_int, [_P, _P, _P, C.POINTER(_I32), C.POINTER(_D)]),
-    "tdgl_time_kernel": (C.c_int, [_P, _I32, _I32, C.POINTER(_D)]),
+    "tdgl_time_kernel": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_D)]),
     "tdgl_get_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
     "tdgl_host_amg_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _D, _I32, C.POINTER(_I32),
                                       C.POINTER(_I64), C.POINTER(_I64), _P, _P, _I32, _D,

@@ -141,8 +141,11 @@ class Engine {
   struct AdvanceInfo {
     int64_t steps_done, step; double time, dt, tentative_dt; int finished, status;
     int64_t failed_step; double failed_dt; int64_t retries, mu_iterations; double mu_rel_residual;
+    double device_ms;
   };
   AdvanceInfo advance(int64_t max_steps, double t_end, int64_t step, double time);
+  AdvanceInfo update(const double* psi, const double* mu, int64_t step, double time,
+                     double* psi_out, double* mu_out, double* js, double* jn);
   void get_state(double* psi, double* mu);
   void get_currents(double* js, double* jn);
   void get_running(int64_t capacity, double* dt, double* mu_probe, double* theta_probe);
@@ -153,7 +156,7 @@ class Engine {
   void op_mu_rhs(const double* psi, double* rhs);
   void op_mu_laplacian(const double* x, double* y);
   void op_mu_solve(const double* rhs, double* mu, int* iterations, double* rel_res);
-  double time_kernel(int which, int reps);
+  double time_kernel(int which, int reps, int flush_l2);
   void get_info(int64_t* out, int n);
 
   std::string last_error;
@@ -202,6 +205,7 @@ class Engine {
   // ---- scratch for IO ------------------------------------------------------------------------
   DevBuf<double2> tmp_c_;
   DevBuf<double> tmp_d_, tmp_d2_, tmp_e_, tmp_e2_;
+  DevBuf<double> flush_;  // 256 MB scratch read between timed launches (time_kernel)
   // ---- control ------------------------------------------------------------------------------
   DevBuf<Ctl> ctl_;
   Ctl* h_ctl_ = nullptr;  // pinned mirror

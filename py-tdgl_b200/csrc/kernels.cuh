@@ -469,6 +469,16 @@ k_dot(const Ctl* __restrict__ ctl, int n, const double* __restrict__ a,
   }
 }
 
+// Reads a buffer larger than L2 so that the next kernel starts from a cold cache
+// (microbenchmarks only).
+__global__ void k_flush_l2(const double* __restrict__ buf, size_t n, double* sink) {
+  double s = 0.0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    s += buf[i];
+  if (s == 123.456) *sink = s;
+}
+
 // y = -y / areas   (A -> mu_laplacian)
 __global__ void k_neg_div(int n, const double* __restrict__ areas, double* __restrict__ y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

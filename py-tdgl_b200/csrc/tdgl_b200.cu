@@ -616,6 +616,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   h_ctl_->total_retries = 0;
   h_ctl_->total_cg_it = 0;
   TDGL_CUDA(cudaMemcpyAsync(ctl_.p, h_ctl_, sizeof(Ctl), cudaMemcpyHostToDevice, stream_));
+  TDGL_CUDA(cudaEventRecord(ev0_, stream_));
   if (graph_mode_ == 1) {
     TDGL_CUDA(cudaGraphLaunch(graph_exec_, stream_));
     ++launches_;
@@ -644,8 +645,13 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
       if (!h_ctl_->step_go) break;
     }
   }
+  TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+  TDGL_CUDA(cudaEventSynchronize(ev1_));
+  float dev_ms = 0.f;
+  TDGL_CUDA(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
   last_steps_done_ = h_ctl_->steps_done;
   AdvanceInfo info;
+  info.device_ms = dev_ms;
   info.steps_done = h_ctl_->steps_done;
   info.step = h_ctl_->step;
   info.time = h_ctl_->time;
@@ -658,6 +664,33 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   info.retries = h_ctl_->total_retries;
   info.mu_iterations = h_ctl_->total_cg_it;
   info.mu_rel_residual = h_ctl_->bb > 0 ? std::sqrt(h_ctl_->rr / h_ctl_->bb) : 0.0;
+  return info;
+}
+
+Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t step, double time,
+                                   double* psi_out, double* mu_out, double* js, double* jn) {
+  set_state(psi, mu);
+  AdvanceInfo info = advance(1, 1e300, step, time);
+  const int cur = h_ctl_->cur;
+  const int g = (N_ + kBlock - 1) / kBlock;
+  if (psi_out != nullptr) {
+    k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, psi_[cur].p, tmp_c_.p);
+    TDGL_LAUNCH_CHECK();
+    TDGL_CUDA(cudaMemcpyAsync(psi_out, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+  }
+  if (mu_out != nullptr) {
+    k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
+    TDGL_LAUNCH_CHECK();
+    tmp_d_.download(mu_out, N_, stream_);
+  }
+  if (js != nullptr || jn != nullptr) {
+    k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, tmp_e_.p, tmp_e2_.p);
+    TDGL_LAUNCH_CHECK();
+    if (js != nullptr) tmp_e_.download(js, E_, stream_);
+    if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
+  }
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
   return info;
 }
 
@@ -834,7 +867,7 @@ void Engine::op_mu_solve(const double* rhs, double* mu, int* iterations, double*
   if (status != 0) throw std::runtime_error("mu solver did not converge");
 }
 
-double Engine::time_kernel(int which, int reps) {
+double Engine::time_kernel(int which, int reps, int flush_l2) {
   if (reps < 1) reps = 1;
   sync_ctl_to_host();
   Ctl saved = *h_ctl_;
@@ -843,6 +876,12 @@ double Engine::time_kernel(int which, int reps) {
   TDGL_CUDA(cudaMemcpyAsync(mu_saved.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
   h_ctl_->status = 0;
   push_ctl();
+  const size_t flush_n = (256u << 20) / sizeof(double);
+  if (flush_l2 && flush_.n == 0) {
+    flush_.alloc(flush_n);
+    flush_.zero(stream_);
+  }
+  const bool multi = levels_.size() > 1;
   auto one = [&]() {
     switch (which) {
       case 0: enqueue_psi_step(nullptr, 1e-6); break;
@@ -856,17 +895,48 @@ double Engine::time_kernel(int which, int reps) {
         TDGL_LAUNCH_CHECK();
         host_solve_loop();
         break;
+      case 5:
+        if (!multi) throw std::invalid_argument("single-level hierarchy");
+        launch_presmooth(A0(), levels_[0].dinv.p, levels_[0].omega, cg_r_.p, levels_[0].x.p, levels_[0].r.p);
+        break;
+      case 6:
+        if (!multi) throw std::invalid_argument("single-level hierarchy");
+        launch_jacobi(A0(), levels_[0].dinv.p, levels_[0].omega, cg_r_.p, levels_[0].x.p, cg_z_.p, cg_r_.p, &ctl_.p->rz_new);
+        break;
+      case 7:
+        if (!multi) throw std::invalid_argument("single-level hierarchy");
+        launch_plain(levels_[0].R.view(), levels_[0].r.p, levels_[1].b.p, false);
+        break;
+      case 8:
+        if (!multi) throw std::invalid_argument("single-level hierarchy");
+        launch_plain(levels_[0].P.view(), levels_[1].y.p, levels_[0].x.p, true);
+        break;
       default: throw std::invalid_argument("unknown kernel id");
     }
   };
   one();  // warm-up
   TDGL_CUDA(cudaStreamSynchronize(stream_));
-  TDGL_CUDA(cudaEventRecord(ev0_, stream_));
-  for (int i = 0; i < reps; ++i) one();
-  TDGL_CUDA(cudaEventRecord(ev1_, stream_));
-  TDGL_CUDA(cudaEventSynchronize(ev1_));
-  float ms = 0.f;
-  TDGL_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  double total_ms = 0.0;
+  if (flush_l2) {
+    for (int i = 0; i < reps; ++i) {
+      k_flush_l2<<<1184, kBlock, 0, stream_>>>(flush_.p, flush_n, flush_.p);
+      TDGL_CUDA(cudaEventRecord(ev0_, stream_));
+      one();
+      TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+      TDGL_CUDA(cudaEventSynchronize(ev1_));
+      float ms = 0.f;
+      TDGL_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+      total_ms += ms;
+    }
+  } else {
+    TDGL_CUDA(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < reps; ++i) one();
+    TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+    TDGL_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0.f;
+    TDGL_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    total_ms = ms;
+  }
   // restore
   sync_ctl_to_host();
   const int cur = h_ctl_->cur;
@@ -875,7 +945,7 @@ double Engine::time_kernel(int which, int reps) {
   push_ctl();
   TDGL_CUDA(cudaMemcpyAsync(mu_.p, mu_saved.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
   TDGL_CUDA(cudaStreamSynchronize(stream_));
-  return static_cast<double>(ms) / reps;
+  return total_ms / reps;
 }
 
 void Engine::get_info(int64_t* out, int n) {
@@ -1006,6 +1076,7 @@ int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, 
       info->tentative_dt = r.tentative_dt; info->finished = r.finished; info->status = r.status;
       info->failed_step = r.failed_step; info->failed_dt = r.failed_dt; info->retries = r.retries;
       info->mu_iterations = r.mu_iterations; info->mu_rel_residual = r.mu_rel_residual;
+      info->device_ms = r.device_ms;
     }
     status = r.status;
   });
@@ -1014,6 +1085,38 @@ int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, 
   if (status == 2) { h->error = "mu solver did not reach tolerance within mu_max_iter iterations"; return TDGL_E_MU_SOLVER; }
   return TDGL_OK;
 }
+
+int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t step, double time,
+                double* psi_out, double* mu_out, double* supercurrent, double* normal_current,
+                tdgl_advance_info* info) {
+  int status = TDGL_OK;
+  const int rc = guarded(h, [&](tdgl::Engine& e) {
+    if (psi == nullptr || mu == nullptr) throw std::invalid_argument("null psi / mu");
+    const auto r = e.update(psi, mu, step, time, psi_out, mu_out, supercurrent, normal_current);
+    if (info != nullptr) {
+      info->steps_done = r.steps_done; info->step = r.step; info->time = r.time; info->dt = r.dt;
+      info->tentative_dt = r.tentative_dt; info->finished = r.finished; info->status = r.status;
+      info->failed_step = r.failed_step; info->failed_dt = r.failed_dt; info->retries = r.retries;
+      info->mu_iterations = r.mu_iterations; info->mu_rel_residual = r.mu_rel_residual;
+      info->device_ms = r.device_ms;
+    }
+    status = r.status;
+  });
+  if (rc != TDGL_OK) return rc;
+  if (status == 1) { h->error = "Solver failed to converge (|psi|^2 discriminant < 0 after max_solve_retries)"; return TDGL_E_STEP_FAILED; }
+  if (status == 2) { h->error = "mu solver did not reach tolerance within mu_max_iter iterations"; return TDGL_E_MU_SOLVER; }
+  return TDGL_OK;
+}
+
+void* tdgl_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, static_cast<size_t>(bytes)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void tdgl_host_free(void* p) { if (p != nullptr) cudaFreeHost(p); }
 
 int tdgl_get_state(tdgl_handle* h, double* psi, double* mu) {
   return guarded(h, [&](tdgl::Engine& e) { e.get_state(psi, mu); });
@@ -1053,9 +1156,10 @@ int tdgl_op_mu_solve(tdgl_handle* h, const double* rhs, double* mu, int32_t* ite
     if (rel_residual != nullptr) *rel_residual = rr;
   });
 }
-int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, double* mean_ms) {
+int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_l2,
+                     double* mean_ms) {
   return guarded(h, [&](tdgl::Engine& e) {
-    const double ms = e.time_kernel(which, reps);
+    const double ms = e.time_kernel(which, reps, flush_l2);
     if (mean_ms != nullptr) *mean_ms = ms;
   });
 }

@@ -34,6 +34,37 @@ class AdvanceInfo(NamedTuple):
     retries: int
     mu_iterations: int
     mu_rel_residual: float
+    device_ms: float = 0.0
+
+
+class _PinnedBlock:
+    """Owner of one page-locked allocation (freed when the last array view dies)."""
+
+    def __init__(self, nbytes: int):
+        self._lib = _lib.load()
+        self.ptr = self._lib.tdgl_host_alloc(int(nbytes))
+        if not self.ptr:
+            raise MemoryError(f"tdgl_host_alloc({nbytes}) failed")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.tdgl_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """NumPy array in page-locked host memory: the copies of ``DeviceEngine.update`` from /
+    to such arrays are true asynchronous DMA transfers."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    block = _PinnedBlock(max(n * dtype.itemsize, 16))
+    buf = (C.c_char * block.nbytes).from_address(block.ptr)
+    buf._tdgl_block = block  # the array's base keeps the allocation alive
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
 class DeviceEngine:
@@ -138,11 +169,32 @@ class DeviceEngine:
                                     float(time), C.byref(info))
         out = AdvanceInfo(info.steps_done, info.step, info.time, info.dt, info.tentative_dt,
                           bool(info.finished), info.status, info.failed_step, info.failed_dt,
-                          info.retries, info.mu_iterations, info.mu_rel_residual)
+                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms)
         if rc == _lib.TDGL_E_STEP_FAILED:
             raise StepFailed(f"step {out.failed_step} dt {out.failed_dt:.2e}", out)
         self._check(rc)
         return out
+
+    def update(self, psi, mu, step: int, time: float, out=None):
+        """One ``TDGLSolver.update`` at the reference's step seam: host arrays in, one step
+        on the device, host arrays out.  ``out`` = (psi, mu, supercurrent, normal_current)
+        arrays to write into (e.g. pinned); allocated if omitted."""
+        if out is None:
+            out = (np.empty(self.n_sites, np.complex128), np.empty(self.n_sites),
+                   np.empty(self.n_edges), np.empty(self.n_edges))
+        info = _lib.tdgl_advance_info()
+        psi = as_c128(psi, (self.n_sites,))
+        mu = as_f64(mu, (self.n_sites,))
+        rc = self._lib.tdgl_update(self._h, ptr(psi), ptr(mu), int(step), float(time),
+                                   ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
+                                   C.byref(info))
+        res = AdvanceInfo(info.steps_done, info.step, info.time, info.dt, info.tentative_dt,
+                          bool(info.finished), info.status, info.failed_step, info.failed_dt,
+                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms)
+        if rc == _lib.TDGL_E_STEP_FAILED:
+            raise StepFailed(f"step {res.failed_step} dt {res.failed_dt:.2e}", res)
+        self._check(rc)
+        return res, out
 
     # -- outputs --------------------------------------------------------------------------
     def get_state(self):
@@ -198,9 +250,10 @@ class DeviceEngine:
                                                C.byref(it), C.byref(rr)))
         return mu, it.value, rr.value
 
-    def time_kernel(self, which: int, reps: int = 20) -> float:
+    def time_kernel(self, which: int, reps: int = 20, flush_l2: bool = True) -> float:
         ms = C.c_double(0)
-        self._check(self._lib.tdgl_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
+        self._check(self._lib.tdgl_time_kernel(self._h, int(which), int(reps),
+                                               1 if flush_l2 else 0, C.byref(ms)))
         return ms.value
 
     def info(self) -> dict:

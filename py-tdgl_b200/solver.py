@@ -74,6 +74,9 @@ class _RunningState:
         self.values = {name: np.zeros((size, self.buffer_size))
                        for name, size in self.names_and_sizes.items()}
 
+    def append(self, name: str, value) -> None:
+        self.values[name][:, self.step] = value
+
 
 class TDGLSolver:
     """Drop-in for ``tdgl.TDGLSolver`` on the B200 engine.
@@ -255,6 +258,44 @@ class TDGLSolver:
                 changed = True
         if changed:
             self.engine.set_mu_boundary(self.mu_boundary)
+
+    def update(self, state: Dict[str, float], running_state, dt: float, *, psi, mu,
+               supercurrent=None, normal_current=None, induced_vector_potential=None,
+               applied_vector_potential=None, epsilon=None, out=None) -> SolverResult:
+        """One time step with the reference's signature (``TDGLSolver.update``,
+        solver.py:580-714), i.e. the function ``Runner._run_stage`` calls once per step
+        (runner.py:417-423): host ``psi`` / ``mu`` in, ``SolverResult`` of host arrays out.
+        ``supercurrent`` / ``normal_current`` inputs are ignored as in the reference; ``dt``
+        (the previous step's dt) only matters for time-dependent vector potentials, which
+        this path does not take.  ``solve()`` does not use this seam — it keeps the state
+        on the device between save steps."""
+        step, time = int(state["step"]), float(state["time"])
+        self.update_mu_boundary(time)
+        if self.dynamic_epsilon:
+            self.epsilon = self._eval_eps(time)
+            self.engine.set_epsilon(self.epsilon)
+        try:
+            info, (psi1, mu1, js, jn) = self.engine.update(psi, mu, step, time, out=out)
+        except StepFailed as exc:
+            fi = exc.args[1]
+            raise RuntimeError(
+                f"Solver failed to converge in {self.options.max_solve_retries}"
+                f" retries at step {fi.failed_step} with dt = {fi.failed_dt:.2e}."
+                f" Try using a smaller dt_init.") from None
+        if running_state is not None:
+            running_state.append("dt", info.dt)
+            if self.probe_points is not None:
+                running_state.append("mu", mu1[self.probe_points])
+                running_state.append("theta", np.angle(psi1[self.probe_points]))
+        self.stats["steps"] += 1
+        self.stats["retries"] += info.retries
+        self.stats["mu_iterations"] += info.mu_iterations
+        if induced_vector_potential is None:
+            induced_vector_potential = np.zeros((self.num_edges, 2))
+        results = [info.dt, psi1, mu1, js, jn, induced_vector_potential]
+        if self.dynamic_epsilon:
+            results.extend([None, self.epsilon])
+        return SolverResult(*results)
 
     # ------------------------------------------------------------------------------------
     def _values(self) -> Dict[str, np.ndarray]:

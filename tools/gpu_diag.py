@@ -37,16 +37,19 @@ print("timed", b, f"{steps/(te-ts):.1f} steps/s wall", flush=True)
 out.update(steps_per_s=steps / (te - ts), mu_iters_per_step=b.mu_iterations / steps,
            retries=b.retries, dt_last=b.dt)
 nnz = info["nnz"]
-alg = {0: 20 * nnz + 52 * n, 1: 32 * nnz + 60 * n, 2: 12 * nnz + 20 * n}
-names = {0: "psi_step", 1: "mu_rhs", 2: "mu_spmv_dot", 3: "vcycle", 4: "mu_solve_cold"}
-for k in range(5):
-    ms = eng.time_kernel(k, 20 if k < 4 else 3)
-    rec = dict(ms=ms)
-    if k in alg:
-        rec["GBps"] = alg[k] / ms / 1e6
-        rec["frac_of_6535"] = rec["GBps"] / 6535.1
-    out[names[k]] = rec
-    print(names[k], rec, flush=True)
+alg = {0: 20 * nnz + 52 * n, 1: 28 * nnz + 60 * n, 2: 12 * nnz + 20 * n, 5: 12 * nnz + 36 * n,
+       6: 12 * nnz + 44 * n}
+names = {0: "psi_step", 1: "mu_rhs", 2: "mu_spmv_dot", 3: "vcycle", 4: "mu_solve_cold",
+         5: "presmooth0", 6: "jacobi0", 7: "restrict0", 8: "prolong0"}
+for flush in (True, False):
+    for k in range(9):
+        ms = eng.time_kernel(k, 20 if k != 4 else 3, flush_l2=flush)
+        rec = dict(ms=ms)
+        if k in alg:
+            rec["GBps"] = alg[k] / ms / 1e6
+            rec["frac_of_6535"] = rec["GBps"] / 6535.1
+        out[names[k] + ("_flush" if flush else "_b2b")] = rec
+        print(names[k], "flush" if flush else "back-to-back", rec, flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", f"diag_{n}_g{use_graph}.json"), "w") as f:
     json.dump(out, f, indent=1)
