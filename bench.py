@@ -243,7 +243,7 @@ def run_b200(args, rank, world, local_rank):
     n, n_edges = len(mesh.sites), len(mesh.edge_mesh.edges)
     K, W = args.steps, args.warmup
     opts = SolverOptions(solve_time=1e9, save_every=max(K, W, 1), cuda_device=local_rank,
-                         **work["opts"])
+                         use_cuda_graph=not args.no_graph, **work["opts"])
     t0 = time.perf_counter()
     solver = TDGLSolver.from_dimensionless(
         mesh, opts, A_applied=work["A"], epsilon=work["eps"], terminal_info=work["terms"],
@@ -373,6 +373,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=60.0,
                     help="seconds of CPU stepping allowed for the cpu baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="host-driven launches instead of the device-side-loop CUDA graph"
+                         " (profiler runs: every kernel is an ordinary launch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
