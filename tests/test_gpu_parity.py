@@ -84,12 +84,11 @@ def _oracle(c):
                             current_func=cf, probe_points=c.probes)
 
 
-def _run_cuda(c, use_graph=True, mu_rtol=1e-10, snapshots=()):
+def _run_cuda(c, use_graph=True, mu_rtol=1e-10, snapshots=(), save_every=250):
     from tdgl_b200 import SolverOptions, TDGLSolver
 
     kw = dict(c.opts)
     solve_time = kw.pop("solve_time")
-    save_every = 250
     opts = SolverOptions(solve_time=solve_time if c.max_steps is None else 1e9,
                          save_every=save_every, use_cuda_graph=use_graph, mu_rtol=mu_rtol, **kw)
     solver = TDGLSolver.from_dimensionless(
@@ -169,19 +168,39 @@ def test_adaptive_vortex_trajectory():
 
 
 def test_transport_trajectory():
-    """Terminals + holes + transport current (phase slips / vortices => chaotic at long
-    times): 1e-6 parity on the early snapshot and the dt sequence up to it, physics-level
-    agreement at the end."""
+    """Terminals + holes + transport current.  The flow is smooth up to step ~170, then a
+    symmetry-breaking instability (phase slips / vortex entry at the holes) amplifies
+    roundoff-level differences by ~x100 per 10 steps (tools/parity_trace.py; the reference
+    shows the same sensitivity to a 1e-13 perturbation of its own initial state, checked
+    below).  Parity: 1e-8 on psi / mu at steps 50, 100, 150 and on the dt sequence up to
+    there (required 1e-6); physics-level agreement at the end."""
     c = load_case("strip_transport")
     g = c.g
-    out = _run_cuda(c)
+    out = _run_cuda(c, save_every=50)
     a = c.mesh.areas
+    for s in (50, 100, 150):
+        k = list(g["snap_steps"]).index(s)
+        psi_s, mu_s = out["snaps"][s]
+        d = orc.compare(dict(psi=psi_s, mu=mu_s),
+                        dict(psi=g["snap_psi"][k], mu=g["snap_mu"][k]), a)
+        print("strip_transport step", s, d)
+        assert d["psi"] < 1e-8 and d["mu"] < 1e-8, (s, d)
+    np.testing.assert_allclose(out["dt"][:150], g["dt"][:150], rtol=1e-8)
+    # the reference's own sensitivity: perturb its initial psi by 1e-13 and compare at
+    # step 250 -- the CUDA path may not be asked for more than the reference gives itself
+    o1, o2 = _oracle(c), _oracle(c)
+    rng = np.random.default_rng(1)
+    psi0 = o2.psi_init * (1 + 1e-13 * rng.normal(size=len(a)))
+    r1 = orc.run(o1, end_time=1e9, max_steps=250)
+    r2 = orc.run(o2, end_time=1e9, max_steps=250, psi0=psi0)
+    self_d = orc.compare(r2, r1, a)
     k = list(g["snap_steps"]).index(250)
     psi250, mu250 = out["snaps"][250]
-    d = orc.compare(dict(psi=psi250, mu=mu250), dict(psi=g["snap_psi"][k], mu=g["snap_mu"][k]), a)
-    print("strip_transport step 250", d)
-    assert d["psi"] < 1e-6 and d["mu"] < 1e-6, d
-    np.testing.assert_allclose(out["dt"][:250], g["dt"][:250], rtol=1e-6)
+    d250 = orc.compare(dict(psi=psi250, mu=mu250),
+                       dict(psi=g["snap_psi"][k], mu=g["snap_mu"][k]), a)
+    print("strip_transport step 250: cuda vs reference", d250, "reference vs itself(1e-13)",
+          self_d)
+    assert self_d["psi"] > 1e-4, "expected the reference to amplify a 1e-13 perturbation"
     ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
                normal_current=g["normal_current"])
     dd = orc.compare(out, ref, a)
@@ -192,7 +211,7 @@ def test_transport_trajectory():
     dyn = out["dynamics"]
     v_ref = g["running_mu"][0] - g["running_mu"][1]
     v = dyn.voltage(0, 1)
-    np.testing.assert_allclose(v[:250], v_ref[:250], atol=1e-6 * np.abs(v_ref).max())
+    np.testing.assert_allclose(v[:150], v_ref[:150], atol=1e-8 * np.abs(v_ref).max())
     # fixed terminal sites keep psi = 0
     fixed = np.concatenate([np.asarray(t.site_indices) for t in c.terminals])
     assert np.abs(out["psi"][fixed]).max() == 0.0
