@@ -54,6 +54,8 @@ typedef struct tdgl_config {
   int32_t reorder;          /* 1: renumber sites along a Z-order curve when coordinates
                                are given; 2: keep the caller's numbering [1] */
   int32_t running_capacity; /* steps of running state kept per advance() [4096] */
+  int32_t world;            /* number of shards the mesh is decomposed into, 1..8 [1] */
+  int32_t rank;             /* the shard this handle computes, 0..world-1 [0] */
 } tdgl_config;
 
 /* Mesh + material -> device-resident operators.  Replaces MeshOperators.__init__ +
@@ -184,6 +186,29 @@ int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_
  * [7] graph mode actually in use (1/2). */
 int tdgl_get_info(tdgl_handle* h, int64_t* out, int32_t n);
 
+/* ---- domain decomposition (no counterpart in the reference) ------
+ * A handle created with tdgl_config.world = P > 1 computes shard `rank` of the mesh: every
+ * rank passes the SAME whole-mesh arrays to tdgl_create (and to the tdgl_set_* calls); the
+ * engine keeps only its rows (a contiguous range of the Z-order numbering, on every AMG
+ * level) plus a halo.  Halo exchanges and scalar all-reduces are device code on the peers'
+ * memory (NVLink), so the shards must be wired once before the first tdgl_advance():
+ *   one process per GPU : tdgl_comm_export() -> all-gather the 64-byte handles with the
+ *                         host library of your choice (torch.distributed) ->
+ *                         tdgl_comm_connect_ipc()
+ *   one process, P handles (one or several GPUs): tdgl_comm_connect_local()
+ * All shards must then call tdgl_advance()/tdgl_update() with the same arguments, each from
+ * its own host thread or process.  Outputs (tdgl_get_state, tdgl_get_currents, tdgl_update,
+ * tdgl_get_running probes) are whole-mesh arrays holding this shard's sites / edges and
+ * zeros elsewhere: sum them over the shards. */
+int tdgl_comm_export(tdgl_handle* h, void* handle_out /* 64 bytes */);
+int tdgl_comm_connect_ipc(tdgl_handle* h, const void* handles /* world x 64 bytes */,
+                          int32_t world);
+int tdgl_comm_connect_local(tdgl_handle* h, tdgl_handle* const* peers, int32_t world);
+/* [0] world, [1] rank, [2] sites of the mesh, [3] sites owned, [4] level-0 halo sites,
+ * [5] halo entries over all levels, [6] level-0 neighbour shards, [7] level-0 entries sent
+ * per exchange. */
+int tdgl_shard_info(tdgl_handle* h, int64_t* out, int32_t n);
+
 /* ---- host-only helpers (no GPU needed): used by CPU tests ---------------------------- */
 
 /* Builds the AMG hierarchy on the host and reports per-level sizes; optionally applies
@@ -194,6 +219,27 @@ int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
                         double theta, int32_t max_coarse, int32_t* n_levels,
                         int64_t* level_rows, int64_t* level_nnz, const double* rhs,
                         double* x, int32_t max_iter, double rtol, int32_t* iterations);
+
+/* Builds the domain decomposition of a mesh for `world` shards exactly as the sharded engine
+ * does and validates it on the host: per-level ownership offsets (level_off[32][9]), halo
+ * sizes (halo_sizes[32][8]), the Z-order permutation (site_owner_perm[n_sites]: position
+ * in the ordering -> caller site), and, if rhs/x are given, the sharded AMG-PCG with all
+ * shards emulated in this process (same local operators, same exchange lists). */
+int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
+                          const double* edge_lengths, const double* dual_edge_lengths,
+                          const double* sites_xy, int32_t world, double theta,
+                          int32_t max_coarse, int32_t* n_levels, int64_t* level_off,
+                          int64_t* halo_sizes, int64_t* site_owner_perm, const double* rhs,
+                          double* x, int32_t max_iter, double rtol, int32_t* iterations);
+
+/* Level-0 exchange lists of one shard in the caller's site numbering: owned sites, halo
+ * sites, and per peer the owned sites sent to it (send_ptr[world+1] ranges into send_sites,
+ * ordered as the peer's halo).  counts[3] = {n_owned, n_halo, n_send}; call with null
+ * arrays first to size them. */
+int tdgl_host_shard_lists(int64_t n_sites, int64_t n_edges, const int64_t* edges,
+                          const double* edge_lengths, const double* dual_edge_lengths,
+                          const double* sites_xy, int32_t world, int32_t rank, int64_t* counts,
+                          int64_t* owned, int64_t* halo, int64_t* send_ptr, int64_t* send_sites);
 
 const char* tdgl_version(void);
 

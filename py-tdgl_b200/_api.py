@@ -4,6 +4,7 @@ from .engine import DeviceEngine, StepFailed
 from .mesh import EdgeMesh, Mesh, make_film_mesh
 from .options import SolverOptions, SolverOptionsError, SparseSolver
 from .solution import DynamicsData, Solution, TDGLData
+from .sharded import DistributedEngine, LocalShardGroup
 from .solver import SolverResult, TDGLSolver, solve
 from .synthetic import TerminalInfo
 
@@ -11,5 +12,5 @@ __all__ = [
     "Device", "Layer", "Polygon", "box", "circle", "DeviceEngine", "StepFailed", "EdgeMesh",
     "Mesh", "make_film_mesh", "SolverOptions", "SolverOptionsError", "SparseSolver",
     "DynamicsData", "Solution", "TDGLData", "SolverResult", "TDGLSolver", "solve",
-    "TerminalInfo",
+    "TerminalInfo", "DistributedEngine", "LocalShardGroup",
 ]

@@ -33,6 +33,8 @@ class tdgl_config(C.Structure):
         ("use_graph", C.c_int32),
         ("reorder", C.c_int32),
         ("running_capacity", C.c_int32),
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
     ]
 
 
@@ -86,6 +88,15 @@ SIGNATURES = {
     "tdgl_op_mu_solve": (C.c_int, [_P, _P, _P, C.POINTER(_I32), C.POINTER(_D)]),
     "tdgl_time_kernel": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_D)]),
     "tdgl_get_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
+    "tdgl_comm_export": (C.c_int, [_P, _P]),
+    "tdgl_comm_connect_ipc": (C.c_int, [_P, _P, _I32]),
+    "tdgl_comm_connect_local": (C.c_int, [_P, C.POINTER(_P), _I32]),
+    "tdgl_shard_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
+    "tdgl_host_shard_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _D, _I32,
+                                        C.POINTER(_I32), _P, _P, _P, _P, _P, _I32, _D,
+                                        C.POINTER(_I32)]),
+    "tdgl_host_shard_lists": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P,
+                                        _P]),
     "tdgl_host_amg_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _D, _I32, C.POINTER(_I32),
                                       C.POINTER(_I64), C.POINTER(_I64), _P, _P, _I32, _D,
                                       C.POINTER(_I32)]),

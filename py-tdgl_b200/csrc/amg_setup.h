@@ -25,7 +25,15 @@ struct AmgHierarchy {
   std::vector<AmgLevel> levels;
   std::vector<double> coarse_inv;  // dense (A_c + g B B^T)^-1, row-major nc x nc
   int64_t nc = 0;
+  // Domain decomposition: off[l][r] .. off[l][r+1] is the contiguous row range of level l
+  // owned by rank r (one entry {0, n} per level for a single rank).
+  std::vector<std::vector<int64_t>> off;
 };
+
+// Rank owning row i of a level partitioned into the contiguous ranges off[r]..off[r+1].
+inline int owner_of(const std::vector<int64_t>& off, int64_t i) {
+  return static_cast<int>(std::upper_bound(off.begin(), off.end(), i) - off.begin()) - 1;
+}
 
 // Greedy aggregation on the strength graph  a_ij^2 >= theta^2 a_ii a_jj:
 //  pass 1: a free node all of whose strong neighbours are free seeds an aggregate,
@@ -115,11 +123,20 @@ inline void dense_spd_inverse(std::vector<double>& M, int64_t n) {
     }
 }
 
+// `off0` (optional): world+1 offsets partitioning the rows of A into contiguous ranges, one
+// per rank.  Every coarse level is then partitioned too: an aggregate belongs to the rank
+// that owns its first (lowest-numbered) fine node, and aggregates are renumbered so that
+// each rank's aggregates are contiguous (H.off).  With one rank nothing is renumbered.
 inline AmgHierarchy build_amg(HostCsr<double> A, double theta, int64_t max_coarse,
-                              int max_levels) {
+                              int max_levels, const std::vector<int64_t>* off0 = nullptr) {
   AmgHierarchy H;
   std::vector<double> B(A.rows, 1.0);
+  std::vector<int64_t> cur_off = off0 != nullptr ? *off0 : std::vector<int64_t>{0, A.rows};
+  if (cur_off.size() < 2 || cur_off.front() != 0 || cur_off.back() != A.rows)
+    throw std::invalid_argument("bad partition offsets");
+  const int world = static_cast<int>(cur_off.size()) - 1;
   while (true) {
+    H.off.push_back(cur_off);
     AmgLevel lv;
     lv.A = std::move(A);
     const int64_t n = lv.A.rows;
@@ -136,6 +153,22 @@ inline AmgHierarchy build_amg(HostCsr<double> A, double theta, int64_t max_coars
     std::vector<int32_t> agg;
     const int64_t nagg = aggregate(lv.A, d, theta, agg);
     if (nagg >= n) { H.levels.push_back(std::move(lv)); break; }  // cannot coarsen
+    if (world > 1) {
+      // group the aggregates by owning rank (stable: keeps the creation order inside a rank)
+      std::vector<int> own(nagg, -1);
+      for (int64_t i = 0; i < n; ++i)
+        if (own[agg[i]] < 0) own[agg[i]] = owner_of(cur_off, i);  // i ascends: first node wins
+      std::vector<int64_t> next_off(world + 1, 0);
+      for (int64_t c = 0; c < nagg; ++c) next_off[own[c] + 1]++;
+      for (int r = 0; r < world; ++r) next_off[r + 1] += next_off[r];
+      std::vector<int64_t> fill(next_off.begin(), next_off.end() - 1);
+      std::vector<int32_t> relabel(nagg);
+      for (int64_t c = 0; c < nagg; ++c) relabel[c] = static_cast<int32_t>(fill[own[c]]++);
+      for (int64_t i = 0; i < n; ++i) agg[i] = relabel[agg[i]];
+      cur_off = next_off;
+    } else {
+      cur_off = {0, nagg};
+    }
     // tentative prolongator T (one entry per row), normalised so that T B_c = B
     std::vector<double> nrm(nagg, 0.0);
     for (int64_t i = 0; i < n; ++i) nrm[agg[i]] += B[i] * B[i];

@@ -178,8 +178,7 @@ struct RealArgs {
 //  kOpPlain     y = A x ;  kOpPlainAdd  y += A x  (restriction / prolongation)
 template <int OP>
 __global__ void __launch_bounds__(kWinRows)
-kw_real(const Ctl* __restrict__ ctl, WinCsr m, RealArgs a, double* partials,
-        unsigned int* counter) {
+kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned int* counter) {
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double red[32];
@@ -242,7 +241,10 @@ kw_real(const Ctl* __restrict__ ctl, WinCsr m, RealArgs a, double* partials,
     const double bs = block_sum(d, red);
     double total;
     if (grid_sum_last(bs, partials, counter, red, &total)) {
-      if (threadIdx.x == 0) *a.red_out = total;
+      if (threadIdx.x == 0) {
+        if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+        *a.red_out = total;
+      }
     }
   }
 }
@@ -322,7 +324,8 @@ kw_psi_step(Ctl* ctl, WinCsr m, const double2* __restrict__ lval,
 // (reference solve_for_observables, solver.py:507-510; identity: SURVEY.md appendix A).
 // The complex and the real matrix share one CSR structure and are staged together.
 __global__ void __launch_bounds__(kWinRows)
-kw_mu_rhs(Ctl* ctl, WinCsr m, const double2* __restrict__ lval, const double* __restrict__ aval,
+kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
+          const double* __restrict__ aval,
           const double2* psi_buf0, const double2* psi_buf1, const double* __restrict__ mu,
           const double* __restrict__ areas, const double* __restrict__ bterm,
           double* __restrict__ b, double* __restrict__ r,
@@ -383,6 +386,12 @@ kw_mu_rhs(Ctl* ctl, WinCsr m, const double2* __restrict__ lval, const double* __
     a0 = block_sum(a0, red);
     a1 = block_sum(a1, red);
     if (threadIdx.x == 0) {
+      if (comm != nullptr) {
+        double v[2] = {a0, a1};
+        comm_allreduce(ctl, comm, v, 2, false);
+        a0 = v[0];
+        a1 = v[1];
+      }
       ctl->bb = a0;
       ctl->rr = a1;
       *counter = 0u;

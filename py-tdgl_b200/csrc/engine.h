@@ -37,20 +37,27 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;  // false: a view into the arena (see shard.h)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
   void alloc(size_t count) {
     release();
     n = count;
     if (count) TDGL_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void view(void* base, size_t count) {  // non-owning window on memory someone else owns
+    release();
+    p = static_cast<T*>(base);
+    n = count;
+    owned = false;
   }
   void zero(cudaStream_t s) { if (n) TDGL_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t count, cudaStream_t s) {
@@ -79,11 +86,15 @@ struct DevCsr {
 };
 
 struct DevLevel {
-  int n = 0;
+  int n = 0;            // rows owned by this shard
+  int nx = 0;           // owned + halo entries of a vector on this level
   DevCsr A, P, R;       // P: n x n_coarse, R: n_coarse x n
-  DevBuf<double> dinv;
+  DevBuf<double> dinv;  // nx entries (the halo part is static, filled at setup)
   double omega = 0.0;   // Jacobi weight (4/3) / rho(D^-1 A)
-  DevBuf<double> b, x, y, r;  // work vectors (level 0 aliases CG vectors instead of b / y)
+  DevBuf<double> b, x, y, r;  // work vectors in the arena (level 0 uses the CG vectors for b / y)
+  // halo exchange of this level (sharded engine)
+  DevBuf<int> send_idx;
+  ExchArgs ex_x, ex_r, ex_b, ex_y;
 };
 
 // Largest aligned nnz extent of any window of `win` rows (shared-memory elements a CTA
@@ -121,6 +132,8 @@ struct Config {
   int use_graph = 1;
   int reorder = 1;
   int running_capacity = 4096;
+  int world = 1;   // number of shards (one GPU / process each, or several per process)
+  int rank = 0;    // this engine's shard
 };
 
 class Engine {
@@ -159,12 +172,32 @@ class Engine {
   double time_kernel(int which, int reps, int flush_l2);
   void get_info(int64_t* out, int n);
 
+  // ---- sharded engine: wiring of the peer arenas -------------------------------------------
+  void comm_export(void* handle_out /* 64 bytes: cudaIpcMemHandle_t */);
+  void comm_connect_ipc(const void* handles /* world x 64 bytes, rank order */);
+  void comm_connect_local(Engine* const* peers /* world engines of this process */);
+  void shard_info(int64_t* out, int n);
+  int world() const { return world_; }
+
   std::string last_error;
 
  private:
   // ---- sizes / host copies --------------------------------------------------------------
   Config cfg_;
-  int N_ = 0, E_ = 0, Eb_ = 0, nprobe_ = 0;
+  int Ng_ = 0;  // sites of the whole mesh
+  int N_ = 0;   // sites (rows) owned by this shard (= Ng_ for a single shard)
+  int Nx_ = 0;  // owned + halo sites: length of every level-0 vector that is gathered from
+  int E_ = 0, Eb_ = 0, nprobe_ = 0;
+  int world_ = 1, rank_ = 0;
+  bool comm_on_ = false;        // exchanges enabled in the launches being enqueued
+  bool connected_ = true;       // peer arenas mapped (always true for a single shard)
+  ShardPlan plan_;
+  std::vector<ArenaLayout> layouts_;  // arena layout of every rank
+  DevBuf<double> arena_;
+  DevBuf<Comm> comm_;
+  std::vector<void*> ipc_opened_;
+  ExchArgs ex_psi_[2], ex_mu_, ex_cg_r_, ex_cg_p_;
+  int nc_own_ = 0;              // coarsest-level rows owned by this shard
   int64_t nnz_ = 0;
   double gamma_, u_, total_area_ = 0.0;
   std::vector<int> perm_;      // internal index -> caller index
@@ -236,6 +269,11 @@ class Engine {
   void enqueue_cg_iteration(cudaGraphConditionalHandle cond);
   void enqueue_mu_finish();
   void host_solve_loop();   // host-driven CG loop on the current b/r
+  Comm* comm() const { return comm_on_ ? comm_.p : nullptr; }
+  ExchArgs make_exch(int level, int vec, int elem_doubles, const int* send_idx_dev) const;
+  void enqueue_exchange(const ExchArgs& a, const double* src);
+  void enqueue_exchange_psi();
+  void upload_comm(double* const* peers);
   void configure_kernels();
   void build_graph();
   void sync_ctl_to_host();

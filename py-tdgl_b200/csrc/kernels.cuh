@@ -52,6 +52,10 @@ struct Ctl {
   double mu_mean;
 };
 
+}  // namespace tdgl
+#include "comm.cuh"
+namespace tdgl {
+
 // ------------------------------------------------------------------------------------------
 // helpers
 
@@ -121,14 +125,15 @@ __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
 // ------------------------------------------------------------------------------------------
 // (the CSR kernels live in csr_window.cuh)
 
-// Coarsest level: x = Minv b with a dense row-major nc x nc matrix; one warp per row.
+// Coarsest level: x = Minv b with a dense row-major rows x nc matrix (rows = the rows this
+// shard owns, all nc for a single shard); one warp per row.
 __global__ void __launch_bounds__(kBlock)
-k_dense_matvec(const Ctl* __restrict__ ctl, int nc, const double* __restrict__ M,
+k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const double* __restrict__ M,
                const double* __restrict__ b, double* __restrict__ x) {
   if (ctl->status != 0) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= nc) return;
+  if (warp >= rows) return;
   const double* row = M + static_cast<size_t>(warp) * nc;
   double s = 0.0;
   for (int j = lane; j < nc; j += 32) s += row[j] * b[j];
@@ -152,9 +157,9 @@ k_cg_direction(const Ctl* __restrict__ ctl, int n, const double* __restrict__ z,
 // alpha = rz_new / pAp ; x += alpha p ; r -= alpha Ap ; rr = ||r||^2 ;
 // last block: bookkeeping + loop condition of the CG loop.
 __global__ void __launch_bounds__(kBlock)
-k_cg_update(Ctl* ctl, int n, const double* __restrict__ p, const double* __restrict__ Ap,
-            double* __restrict__ x, double* __restrict__ r, double* partials,
-            unsigned int* counter, cudaGraphConditionalHandle cond) {
+k_cg_update(Ctl* ctl, Comm* comm, int n, const double* __restrict__ p,
+            const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
+            double* partials, unsigned int* counter, cudaGraphConditionalHandle cond) {
   __shared__ double red[32];
   if (ctl->status != 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) set_cond(cond, 0);
@@ -172,6 +177,7 @@ k_cg_update(Ctl* ctl, int n, const double* __restrict__ p, const double* __restr
   double total;
   if (grid_sum_last(bs, partials, counter, red, &total)) {
     if (threadIdx.x == 0) {
+      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       ctl->rr = total;
       ctl->rz_prev = ctl->rz_new;
       const int it = ctl->cg_it + 1;
@@ -179,7 +185,9 @@ k_cg_update(Ctl* ctl, int n, const double* __restrict__ p, const double* __restr
       ctl->total_cg_it += 1;
       const double tol2 = ctl->mu_rtol * ctl->mu_rtol * ctl->bb;
       int go = (total > tol2) ? 1 : 0;
-      if (!(total == total)) {  // NaN: breakdown
+      if (ctl->status != 0) {  // exchange failure raised meanwhile
+        go = 0;
+      } else if (!(total == total)) {  // NaN: breakdown
         ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
       } else if (go && it >= ctl->cg_max_iter) {
         ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
@@ -263,9 +271,17 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
 }
 
 // adaptive_euler_step's retry logic (solver.py:475-485)
-__global__ void k_psi_control(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
+__global__ void k_psi_control(Ctl* ctl, Comm* comm, cudaGraphConditionalHandle cond_psi) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int go = 0;
+  if (ctl->status == 0 && comm != nullptr) {
+    // any(disc < 0) and max |d psi^2| over all shards
+    double v[2] = {ctl->disc_flag ? 1.0 : 0.0,
+                   __longlong_as_double(static_cast<long long>(ctl->max_dpsi_bits))};
+    comm_allreduce(ctl, comm, v, 2, true);
+    ctl->disc_flag = v[0] > 0.0 ? 1 : 0;
+    ctl->max_dpsi_bits = static_cast<unsigned long long>(__double_as_longlong(v[1]));
+  }
   if (ctl->status == 0) {
     if (ctl->disc_flag) {
       if (!ctl->adaptive || ctl->retries > ctl->max_retries) {
@@ -290,8 +306,9 @@ __global__ void k_psi_control(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
 
 // area-weighted mean of mu (deterministic), then mu -= mean
 __global__ void __launch_bounds__(kBlock)
-k_weighted_sum(Ctl* ctl, int n, const double* __restrict__ w, const double* __restrict__ x,
-               double* partials, unsigned int* counter, double inv_total_weight) {
+k_weighted_sum(Ctl* ctl, Comm* comm, int n, const double* __restrict__ w,
+               const double* __restrict__ x, double* partials, unsigned int* counter,
+               double inv_total_weight) {
   __shared__ double red[32];
   if (ctl->status != 0) return;
   double d = 0.0;
@@ -300,7 +317,10 @@ k_weighted_sum(Ctl* ctl, int n, const double* __restrict__ w, const double* __re
   const double bs = block_sum(d, red);
   double total;
   if (grid_sum_last(bs, partials, counter, red, &total)) {
-    if (threadIdx.x == 0) ctl->mu_mean = total * inv_total_weight;
+    if (threadIdx.x == 0) {
+      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+      ctl->mu_mean = total * inv_total_weight;
+    }
   }
 }
 
@@ -327,10 +347,10 @@ __global__ void k_step_end(Ctl* ctl, const double2* __restrict__ psi_buf0,
   const int cap = ctl->running_capacity;
   if (pos < cap && threadIdx.x < ctl->n_probe) {
     const double2* psi = ctl->cur ? psi_buf1 : psi_buf0;
-    const int s = probes[threadIdx.x];
-    run_mu[(size_t)threadIdx.x * cap + pos] = mu[s];
-    const double2 p = psi[s];
-    run_theta[(size_t)threadIdx.x * cap + pos] = atan2(p.y, p.x);
+    const int s = probes[threadIdx.x];  // < 0: the probe site belongs to another shard
+    run_mu[(size_t)threadIdx.x * cap + pos] = s >= 0 ? mu[s] : 0.0;
+    const double2 p = s >= 0 ? psi[s] : make_double2(1.0, 0.0);
+    run_theta[(size_t)threadIdx.x * cap + pos] = s >= 0 ? atan2(p.y, p.x) : 0.0;
   }
   if (threadIdx.x != 0) return;
   const double dt = ctl->dt;
@@ -379,9 +399,9 @@ __global__ void k_boundary_term(int nb, const int* __restrict__ be0, const int* 
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const double v = blen[b] * mub[b];
-  const int i = be0[b], j = be1[b];
-  atomicAdd(bterm + i, v / (2.0 * areas[i]));
-  atomicAdd(bterm + j, v / (2.0 * areas[j]));
+  const int i = be0[b], j = be1[b];  // < 0: the site belongs to another shard
+  if (i >= 0) atomicAdd(bterm + i, v / (2.0 * areas[i]));
+  if (j >= 0) atomicAdd(bterm + j, v / (2.0 * areas[j]));
 }
 
 // Values of the covariant Laplacian (all rows kept, see k_mu_rhs) from the link variables
@@ -422,6 +442,11 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
   const int i = e0[e], j = e1[e];
+  if (i < 0) {  // the edge belongs to another shard (owner = shard of edges[e,0])
+    js[e] = 0.0;
+    jn[e] = 0.0;
+    return;
+  }
   const double inv_l = 1.0 / elen[e];
   double s, c;
   sincos(-theta[e], &s, &c);
@@ -455,8 +480,8 @@ __global__ void k_scale_neg_area(int n, const double* __restrict__ areas,
 
 // *out = dot(a, b)   (deterministic)
 __global__ void __launch_bounds__(kBlock)
-k_dot(const Ctl* __restrict__ ctl, int n, const double* __restrict__ a,
-      const double* __restrict__ b, double* partials, unsigned int* counter, double* out) {
+k_dot(Ctl* ctl, Comm* comm, int n, const double* __restrict__ a, const double* __restrict__ b,
+      double* partials, unsigned int* counter, double* out) {
   __shared__ double red[32];
   if (ctl->status != 0) return;
   double d = 0.0;
@@ -465,7 +490,10 @@ k_dot(const Ctl* __restrict__ ctl, int n, const double* __restrict__ a,
   const double bs = block_sum(d, red);
   double total;
   if (grid_sum_last(bs, partials, counter, red, &total)) {
-    if (threadIdx.x == 0) *out = total;
+    if (threadIdx.x == 0) {
+      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+      *out = total;
+    }
   }
 }
 

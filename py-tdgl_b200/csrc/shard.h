@@ -1,0 +1,187 @@
+// Domain decomposition of the mesh operators and of the AMG hierarchy (host side, no CUDA).
+//
+// The reference has no multi-GPU path; this is the B200 build's own.  Sites
+// are numbered along a Z-order curve, rank r owns the contiguous range off[0][r]..off[0][r+1]
+// of that numbering (a coordinate partitioner: compact subdomains, no METIS needed), and
+// every coarse level is partitioned by build_amg() along with it.  A rank stores only its
+// rows; a local vector is laid out [owned | halo], the halo being the sorted list of
+// non-owned columns its rows reference.  Because ownership ranges are contiguous, a sorted
+// halo is automatically grouped by owning rank, and what rank p sends to rank q is simply
+// the part of q's halo that falls into p's range — both sides derive the same lists from
+// the same global plan, nothing has to be negotiated at run time.
+#pragma once
+
+#include "amg_setup.h"
+
+namespace tdgl {
+
+constexpr int kMaxWorld = 8;
+
+struct ShardPlan {
+  int world = 1;
+  int levels = 0;
+  std::vector<std::vector<int64_t>> off;                 // [level][world + 1]
+  std::vector<std::vector<std::vector<int32_t>>> halo;   // [level][rank] sorted global ids
+
+  int64_t owned(int l, int r) const { return off[l][r + 1] - off[l][r]; }
+  int64_t local_size(int l, int r) const { return owned(l, r) + static_cast<int64_t>(halo[l][r].size()); }
+  // position of global id g in rank r's local numbering of level l (-1: not present)
+  int64_t local_index(int l, int r, int64_t g) const {
+    if (g >= off[l][r] && g < off[l][r + 1]) return g - off[l][r];
+    const auto& h = halo[l][r];
+    auto it = std::lower_bound(h.begin(), h.end(), static_cast<int32_t>(g));
+    if (it == h.end() || *it != g) return -1;
+    return owned(l, r) + (it - h.begin());
+  }
+};
+
+// Equal split of n rows over `world` ranks.
+inline std::vector<int64_t> equal_offsets(int64_t n, int world) {
+  std::vector<int64_t> off(world + 1);
+  for (int r = 0; r <= world; ++r) off[r] = n * r / world;
+  return off;
+}
+
+// Adds to halo[r] the non-owned columns of the rows row_off[r]..row_off[r+1] of G, whose
+// columns live on a level partitioned by col_off.
+inline void collect_halo(const HostCsr<double>& G, const std::vector<int64_t>& row_off,
+                         const std::vector<int64_t>& col_off,
+                         std::vector<std::vector<int32_t>>& halo) {
+  const int world = static_cast<int>(row_off.size()) - 1;
+  for (int r = 0; r < world; ++r) {
+    const int64_t c0 = col_off[r], c1 = col_off[r + 1];
+    for (int64_t i = row_off[r]; i < row_off[r + 1]; ++i)
+      for (int32_t k = G.ptr[i]; k < G.ptr[i + 1]; ++k) {
+        const int32_t j = G.idx[k];
+        if (j < c0 || j >= c1) halo[r].push_back(j);
+      }
+  }
+}
+
+inline ShardPlan make_plan(const AmgHierarchy& H) {
+  ShardPlan p;
+  p.levels = static_cast<int>(H.levels.size());
+  p.off = H.off;
+  p.world = static_cast<int>(H.off[0].size()) - 1;
+  p.halo.assign(p.levels, std::vector<std::vector<int32_t>>(p.world));
+  if (p.world == 1) return p;
+  if (p.world > kMaxWorld) throw std::invalid_argument("at most 8 ranks");
+  if (p.levels < 2) throw std::invalid_argument("mesh too small to shard (single-level hierarchy)");
+  for (int l = 0; l < p.levels; ++l) {
+    const AmgLevel& lv = H.levels[l];
+    if (l == p.levels - 1) {
+      // coarsest level: solved redundantly from the gathered right-hand side
+      const int64_t n = lv.A.rows;
+      for (int r = 0; r < p.world; ++r)
+        for (int64_t g = 0; g < n; ++g)
+          if (g < p.off[l][r] || g >= p.off[l][r + 1]) p.halo[l][r].push_back(static_cast<int32_t>(g));
+      continue;
+    }
+    collect_halo(lv.A, p.off[l], p.off[l], p.halo[l]);       // smoothers, SpMV
+    collect_halo(lv.R, p.off[l + 1], p.off[l], p.halo[l]);   // restriction reads level-l residuals
+    if (l > 0) collect_halo(H.levels[l - 1].P, p.off[l - 1], p.off[l], p.halo[l]);  // prolongation
+    for (int r = 0; r < p.world; ++r) {
+      auto& h = p.halo[l][r];
+      std::sort(h.begin(), h.end());
+      h.erase(std::unique(h.begin(), h.end()), h.end());
+    }
+  }
+  // the coarsest level is also read by the prolongation of the level above: already "all"
+  return p;
+}
+
+// Rows r0..r1 of G with columns renumbered into rank `rank`'s local layout of the column
+// level `cl`.  Column order inside a row is kept (the kernels do not need sorted rows).
+inline HostCsr<double> extract_local(const HostCsr<double>& G, int64_t r0, int64_t r1,
+                                     const ShardPlan& plan, int cl, int rank) {
+  HostCsr<double> L;
+  L.rows = r1 - r0;
+  L.cols = plan.local_size(cl, rank);
+  L.ptr.resize(L.rows + 1);
+  const int32_t base = G.ptr[r0];
+  L.idx.resize(G.ptr[r1] - base);
+  L.val.assign(G.val.begin() + base, G.val.begin() + G.ptr[r1]);
+  for (int64_t i = r0; i <= r1; ++i) L.ptr[i - r0] = G.ptr[i] - base;
+  for (int32_t k = base; k < G.ptr[r1]; ++k) {
+    const int64_t li = plan.local_index(cl, rank, G.idx[k]);
+    if (li < 0) throw std::runtime_error("halo plan misses a column");
+    L.idx[k - base] = static_cast<int32_t>(li);
+  }
+  return L;
+}
+
+// What `rank` sends to `peer` on level l: local (owned) indices, in the order in which they
+// appear in the peer's halo, and the position of that block inside the peer's halo.
+struct SendBlock {
+  int peer = -1;
+  std::vector<int32_t> idx;   // local owned indices on `rank`
+  int64_t dst_pos = 0;        // first halo slot on the peer (relative to the start of its halo)
+};
+
+inline std::vector<SendBlock> send_blocks(const ShardPlan& plan, int l, int rank) {
+  std::vector<SendBlock> out;
+  const int64_t g0 = plan.off[l][rank], g1 = plan.off[l][rank + 1];
+  for (int q = 0; q < plan.world; ++q) {
+    if (q == rank) continue;
+    const auto& h = plan.halo[l][q];
+    auto b = std::lower_bound(h.begin(), h.end(), static_cast<int32_t>(g0));
+    auto e = std::lower_bound(h.begin(), h.end(), static_cast<int32_t>(g1));
+    if (b == e) continue;
+    SendBlock s;
+    s.peer = q;
+    s.dst_pos = b - h.begin();
+    s.idx.reserve(e - b);
+    for (auto it = b; it != e; ++it) s.idx.push_back(static_cast<int32_t>(*it - g0));
+    out.push_back(std::move(s));
+  }
+  return out;
+}
+
+// Ranks that send to `rank` on level l (the flags it waits for).
+inline std::vector<int> recv_peers(const ShardPlan& plan, int l, int rank) {
+  std::vector<int> out;
+  const auto& h = plan.halo[l][rank];
+  for (int q = 0; q < plan.world; ++q) {
+    if (q == rank) continue;
+    auto b = std::lower_bound(h.begin(), h.end(), static_cast<int32_t>(plan.off[l][q]));
+    auto e = std::lower_bound(h.begin(), h.end(), static_cast<int32_t>(plan.off[l][q + 1]));
+    if (b != e) out.push_back(q);
+  }
+  return out;
+}
+
+// ---- arena layout -------------------------------------------------------------------------
+// Every vector that carries a halo lives in ONE device allocation per rank (the arena), so
+// that one CUDA IPC handle per rank makes all of them addressable by the peers.  The layout
+// is a pure function of the plan, hence every rank can compute every peer's offsets.
+//   header (doubles): [0,8) halo flags  [8,16) reduction flags  [16,80) reduction slots
+//                     [2 parities][8 ranks][4 values]
+//   vectors: psi0, psi1 (complex: 2 doubles per entry), mu, cg_r, cg_p, then per level
+//            x, r, b, y; each start aligned to 32 doubles.
+constexpr int64_t kArenaHaloFlag = 0, kArenaRedFlag = 8, kArenaRedSlot = 16, kArenaHeader = 128;
+enum : int { kVecPsi0 = 0, kVecPsi1, kVecMu, kVecCgR, kVecCgP, kVecLevel0 };
+inline int vec_id(int level, int which /*0 x, 1 r, 2 b, 3 y*/) { return kVecLevel0 + 4 * level + which; }
+
+struct ArenaLayout {
+  std::vector<int64_t> off;  // per vector id, in doubles from the arena base
+  int64_t total = 0;         // doubles
+};
+
+inline ArenaLayout arena_layout(const ShardPlan& plan, int rank) {
+  ArenaLayout a;
+  int64_t pos = kArenaHeader;
+  auto add = [&](int64_t doubles) {
+    a.off.push_back(pos);
+    pos += (doubles + 31) / 32 * 32;
+  };
+  const int64_t nx0 = plan.local_size(0, rank);
+  add(2 * nx0); add(2 * nx0); add(nx0); add(nx0); add(nx0);
+  for (int l = 0; l < plan.levels; ++l) {
+    const int64_t nx = plan.local_size(l, rank);
+    for (int w = 0; w < 4; ++w) add(nx);
+  }
+  a.total = pos;
+  return a;
+}
+
+}  // namespace tdgl

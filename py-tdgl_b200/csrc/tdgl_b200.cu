@@ -59,6 +59,42 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
 // ============================================================================================
 // construction
 
+ExchArgs Engine::make_exch(int level, int vec, int elem_doubles, const int* send_idx_dev) const {
+  ExchArgs a;
+  if (world_ == 1) return a;
+  const std::vector<SendBlock> blocks = send_blocks(plan_, level, rank_);
+  const std::vector<int> recv = recv_peers(plan_, level, rank_);
+  std::vector<int> peers(recv);
+  for (const SendBlock& b : blocks) peers.push_back(b.peer);
+  std::sort(peers.begin(), peers.end());
+  peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+  // the relation must be symmetric (a rank that waits for me also signals me): make it so
+  for (int q = 0; q < world_; ++q) {
+    if (q == rank_ || std::binary_search(peers.begin(), peers.end(), q)) continue;
+    const std::vector<int> rq = recv_peers(plan_, level, q);
+    bool linked = std::find(rq.begin(), rq.end(), rank_) != rq.end();
+    for (const SendBlock& b : send_blocks(plan_, level, q)) linked = linked || b.peer == rank_;
+    if (linked) peers.push_back(q);
+  }
+  std::sort(peers.begin(), peers.end());
+  a.nnbr = static_cast<int>(peers.size());
+  a.send_idx = send_idx_dev;
+  int pos = 0;
+  for (int j = 0; j < a.nnbr; ++j) {
+    const int q = peers[j];
+    a.nbr[j] = q;
+    a.send_begin[j] = pos;
+    a.dst_off[j] = 0;
+    for (const SendBlock& b : blocks)
+      if (b.peer == q) {
+        pos += static_cast<int>(b.idx.size());
+        a.dst_off[j] = layouts_[q].off[vec] / elem_doubles + plan_.owned(level, q) + b.dst_pos;
+      }
+  }
+  a.send_begin[a.nnbr] = pos;
+  return a;
+}
+
 Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t* edges,
                const double* areas, const double* edge_len, const double* dual_len,
                const double* directions, const int64_t* bedge_idx, const int64_t* fixed_sites,
@@ -69,10 +105,14 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   if (n_sites > 0x7FFFFFF0ll / 32 || n_edges > 0x7FFFFFF0ll / 8)
     throw std::invalid_argument("mesh too large for 32-bit device indices");
   if (n_probe > kMaxProbes) throw std::invalid_argument("too many probe points");
-  N_ = static_cast<int>(n_sites);
+  if (cfg_.world < 1 || cfg_.world > kMaxWorld || cfg_.rank < 0 || cfg_.rank >= cfg_.world)
+    throw std::invalid_argument("bad shard rank / world (1..8 shards)");
+  Ng_ = static_cast<int>(n_sites);
   E_ = static_cast<int>(n_edges);
   Eb_ = static_cast<int>(n_bedges);
   nprobe_ = static_cast<int>(n_probe);
+  world_ = cfg_.world;
+  rank_ = cfg_.rank;
 
   int ndev = 0;
   TDGL_CUDA(cudaGetDeviceCount(&ndev));
@@ -84,47 +124,47 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   TDGL_CUDA(cudaMallocHost(&h_ctl_, sizeof(Ctl)));
   configure_kernels();
 
-  // ---- site numbering ---------------------------------------------------------------------
+  // ---- site numbering (global) --------------------------------------------------------------
   if (cfg_.reorder == 1 && sites_xy != nullptr) {
-    perm_ = morton_permutation(sites_xy, N_);
+    perm_ = morton_permutation(sites_xy, Ng_);
   } else {
-    perm_.resize(N_);
-    for (int i = 0; i < N_; ++i) perm_[i] = i;
+    if (world_ > 1 && sites_xy == nullptr)
+      throw std::invalid_argument("a sharded engine needs the site coordinates");
+    perm_.resize(Ng_);
+    for (int i = 0; i < Ng_; ++i) perm_[i] = i;
   }
-  inv_perm_.resize(N_);
-  for (int i = 0; i < N_; ++i) inv_perm_[perm_[i]] = i;
+  inv_perm_.resize(Ng_);
+  for (int i = 0; i < Ng_; ++i) inv_perm_[perm_[i]] = i;
 
   std::vector<int> e0(E_), e1(E_);
   std::vector<double> w(E_), len(E_);
   h_dirs_.assign(directions, directions + 2 * static_cast<size_t>(E_));
   for (int e = 0; e < E_; ++e) {
     const int64_t a = edges[2 * e], b = edges[2 * e + 1];
-    if (a < 0 || a >= N_ || b < 0 || b >= N_) throw std::invalid_argument("edge index out of range");
+    if (a < 0 || a >= Ng_ || b < 0 || b >= Ng_) throw std::invalid_argument("edge index out of range");
     e0[e] = inv_perm_[a];
     e1[e] = inv_perm_[b];
     if (!(edge_len[e] > 0)) throw std::invalid_argument("non-positive edge length");
     len[e] = edge_len[e];
     w[e] = dual_len[e] / edge_len[e];
   }
-  std::vector<double> a_int(N_);
+  std::vector<double> a_int(Ng_);
   total_area_ = 0.0;
-  for (int i = 0; i < N_; ++i) {
+  for (int i = 0; i < Ng_; ++i) {
     a_int[i] = areas[perm_[i]];
     if (!(a_int[i] > 0)) throw std::invalid_argument("non-positive site area");
   }
-  for (int i = 0; i < N_; ++i) total_area_ += a_int[i];
+  for (int i = 0; i < Ng_; ++i) total_area_ += a_int[i];
 
-  SiteGraph g = build_site_graph(N_, E_, e0.data(), e1.data());
-  nnz_ = g.ptr[N_];
-  win0_ = pick_window(g.ptr, N_, 28, 64 * 1024, &cap0_);
+  SiteGraph g = build_site_graph(Ng_, E_, e0.data(), e1.data());
 
-  // ---- mu operator (symmetrised) + AMG hierarchy on the host ----------------------------
+  // ---- mu operator (symmetrised) + AMG hierarchy on the host (global) ------------------------
   HostCsr<double> A0;
-  A0.rows = A0.cols = N_;
+  A0.rows = A0.cols = Ng_;
   A0.ptr = g.ptr;
   A0.idx = g.nbr;
-  A0.val.assign(nnz_, 0.0);
-  for (int i = 0; i < N_; ++i) {
+  A0.val.assign(g.ptr[Ng_], 0.0);
+  for (int i = 0; i < Ng_; ++i) {
     double diag = 0.0;
     int kd = -1;
     for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
@@ -134,45 +174,95 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     }
     A0.val[kd] = diag;
   }
-  std::vector<double> aval_host = A0.val;
-  AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24);
+  const std::vector<int64_t> off0 = equal_offsets(Ng_, world_);
+  AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24, &off0);
   if (H.nc > 4096) throw std::runtime_error("AMG coarsening stalled (coarsest level too large)");
+  plan_ = make_plan(H);
+  layouts_.resize(world_);
+  for (int q = 0; q < world_; ++q) layouts_[q] = arena_layout(plan_, q);
+  const size_t L = H.levels.size();
+
+  // ---- this shard's part of level 0 ------------------------------------------------------------
+  const int64_t o0 = plan_.off[0][rank_], o1 = plan_.off[0][rank_ + 1];
+  N_ = static_cast<int>(o1 - o0);
+  Nx_ = static_cast<int>(plan_.local_size(0, rank_));
+  if (N_ < 1) throw std::invalid_argument("a shard owns no sites");
+  std::vector<int> l2g(Nx_);  // local -> internal (Z-order) global index
+  for (int k = 0; k < N_; ++k) l2g[k] = static_cast<int>(o0 + k);
+  for (int k = N_; k < Nx_; ++k) l2g[k] = plan_.halo[0][rank_][k - N_];
+  auto to_local = [&](int64_t gidx) { return static_cast<int>(plan_.local_index(0, rank_, gidx)); };
+
+  std::vector<int32_t> lptr(N_ + 1), lnbr, ledge;
+  std::vector<signed char> lhead;
+  std::vector<double> aval_host;
+  {
+    const HostCsr<double>& G0 = H.levels[0].A;  // same structure as g
+    const int32_t base = g.ptr[o0];
+    nnz_ = g.ptr[o1] - base;
+    lnbr.resize(nnz_ + 4, 0);
+    ledge.assign(g.edge.begin() + base, g.edge.begin() + g.ptr[o1]);
+    lhead.assign(g.head.begin() + base, g.head.begin() + g.ptr[o1]);
+    aval_host.assign(G0.val.begin() + base, G0.val.begin() + g.ptr[o1]);
+    aval_host.resize(nnz_ + 4, 0.0);
+    for (int64_t i = o0; i <= o1; ++i) lptr[i - o0] = g.ptr[i] - base;
+    for (int64_t k = base; k < g.ptr[o1]; ++k) {
+      const int li = to_local(g.nbr[k]);
+      if (li < 0) throw std::runtime_error("halo plan misses a neighbour");
+      lnbr[k - base] = li;
+    }
+  }
+  win0_ = pick_window(lptr, N_, 28, 64 * 1024, &cap0_);
+
+  // ---- arena: every vector with a halo, plus flags and reduction slots ----------------------
+  const ArenaLayout& lay = layouts_[rank_];
+  arena_.alloc(lay.total);
+  arena_.zero(stream_);
+  psi_[0].view(arena_.p + lay.off[kVecPsi0], Nx_);
+  psi_[1].view(arena_.p + lay.off[kVecPsi1], Nx_);
+  mu_.view(arena_.p + lay.off[kVecMu], Nx_);
+  cg_r_.view(arena_.p + lay.off[kVecCgR], Nx_);
+  cg_p_.view(arena_.p + lay.off[kVecCgP], Nx_);
+  comm_.alloc(1);
 
   // ---- uploads --------------------------------------------------------------------------
-  ptr_.upload(g.ptr, stream_);
-  {
-    std::vector<int32_t> nbr(g.nbr);
-    nbr.resize(nbr.size() + 4, 0);
-    idx_.upload(nbr, stream_);
-    aval_host.resize(aval_host.size() + 4, 0.0);
-    TDGL_CUDA(cudaStreamSynchronize(stream_));
-  }
-  eidx_.upload(g.edge, stream_);
-  {
-    std::vector<signed char> hd(g.head.begin(), g.head.end());
-    head_.upload(hd, stream_);
-  }
+  ptr_.upload(lptr, stream_);
+  idx_.upload(lnbr, stream_);
+  eidx_.upload(ledge, stream_);
+  head_.upload(lhead, stream_);
   aval_.upload(aval_host, stream_);
   lval_.alloc(nnz_ + 4);
   lval_.zero(stream_);
-  areas_.upload(a_int, stream_);
   {
-    std::vector<unsigned char> fx(N_, 0);
+    std::vector<double> al(Nx_);
+    for (int k = 0; k < Nx_; ++k) al[k] = a_int[l2g[k]];
+    areas_.upload(al, stream_);
+    std::vector<unsigned char> fx(Nx_, 0);
     if (fix_psi)
       for (int64_t k = 0; k < n_fixed; ++k) {
-        if (fixed_sites[k] < 0 || fixed_sites[k] >= N_) throw std::invalid_argument("fixed site out of range");
-        fx[inv_perm_[fixed_sites[k]]] = 1;
+        if (fixed_sites[k] < 0 || fixed_sites[k] >= Ng_) throw std::invalid_argument("fixed site out of range");
+        const int li = to_local(inv_perm_[fixed_sites[k]]);
+        if (li >= 0) fx[li] = 1;
       }
     fixed_.upload(fx, stream_);
-  }
-  {
-    std::vector<double> ones(N_, 1.0);
+    std::vector<double> ones(Nx_, 1.0);
     eps_.upload(ones, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
-  bterm_.alloc(N_);
+  bterm_.alloc(Nx_);
   bterm_.zero(stream_);
-  e0_.upload(e0, stream_);
-  e1_.upload(e1, stream_);
+  {
+    // edges keep the caller's (global) order; site indices are local, -1 = not on this shard.
+    // An edge is owned by the shard that owns edges[e,0] (its e1 is then owned or in the halo).
+    std::vector<int> e0l(E_), e1l(E_);
+    for (int e = 0; e < E_; ++e) {
+      const bool mine = e0[e] >= o0 && e0[e] < o1;
+      e0l[e] = mine ? static_cast<int>(e0[e] - o0) : -1;
+      e1l[e] = mine ? to_local(e1[e]) : -1;
+    }
+    e0_.upload(e0l, stream_);
+    e1_.upload(e1l, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
   elen_.upload(len, stream_);
   weight_.upload(w, stream_);
   theta_.alloc(E_);
@@ -183,78 +273,120 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     for (int b = 0; b < Eb_; ++b) {
       const int64_t e = bedge_idx[b];
       if (e < 0 || e >= E_) throw std::invalid_argument("boundary edge index out of range");
-      b0[b] = e0[e]; b1[b] = e1[e]; bl[b] = len[e];
+      b0[b] = (e0[e] >= o0 && e0[e] < o1) ? static_cast<int>(e0[e] - o0) : -1;
+      b1[b] = (e1[e] >= o0 && e1[e] < o1) ? static_cast<int>(e1[e] - o0) : -1;
+      bl[b] = len[e];
     }
     be0_.upload(b0, stream_);
     be1_.upload(b1, stream_);
     blen_.upload(bl, stream_);
     mub_.alloc(Eb_ > 0 ? Eb_ : 1);
     mub_.zero(stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
-  dperm_.upload(perm_, stream_);
   {
-    std::vector<int> pr(std::max(nprobe_, 1), 0);
+    std::vector<int> dp(Nx_);
+    for (int k = 0; k < Nx_; ++k) dp[k] = perm_[l2g[k]];
+    dperm_.upload(dp, stream_);
+    std::vector<int> pr(std::max(nprobe_, 1), -1);
     for (int k = 0; k < nprobe_; ++k) {
-      if (probe_sites[k] < 0 || probe_sites[k] >= N_) throw std::invalid_argument("probe site out of range");
-      pr[k] = inv_perm_[probe_sites[k]];
+      if (probe_sites[k] < 0 || probe_sites[k] >= Ng_) throw std::invalid_argument("probe site out of range");
+      const int gi = inv_perm_[probe_sites[k]];
+      pr[k] = (gi >= o0 && gi < o1) ? static_cast<int>(gi - o0) : -1;
     }
     probes_.upload(pr, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
   const size_t cap = static_cast<size_t>(cfg_.running_capacity);
   run_dt_.alloc(cap);
   run_mu_.alloc(cap * std::max(nprobe_, 1));
   run_theta_.alloc(cap * std::max(nprobe_, 1));
-
-  psi_[0].alloc(N_);
-  psi_[1].alloc(N_);
-  mu_.alloc(N_);
-  mu_.zero(stream_);
   {
-    std::vector<double2> one(N_, make_double2(1.0, 0.0));
+    std::vector<double2> one(Nx_, make_double2(1.0, 0.0));
     psi_[0].upload(one, stream_);
     psi_[1].upload(one, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
 
-  // hierarchy
-  levels_.resize(H.levels.size());
+  // ---- hierarchy: this shard's rows of every level ---------------------------------------------
+  levels_.resize(L);
   amg_nnz_ = 0;
   int max_grid_rows = grid_win(N_, win0_);
-  for (size_t l = 0; l < H.levels.size(); ++l) {
+  for (size_t l = 0; l < L; ++l) {
     AmgLevel& hl = H.levels[l];
     DevLevel& dl = levels_[l];
-    dl.n = static_cast<int>(hl.A.rows);
-    amg_nnz_ += hl.A.nnz();
+    const int li = static_cast<int>(l);
+    const int64_t r0 = plan_.off[l][rank_], r1 = plan_.off[l][rank_ + 1];
+    dl.n = static_cast<int>(r1 - r0);
+    dl.nx = static_cast<int>(plan_.local_size(li, rank_));
+    amg_nnz_ += hl.A.ptr[r1] - hl.A.ptr[r0];
     if (l > 0) {
-      upload_csr(hl.A, dl.A);
+      upload_csr(extract_local(hl.A, r0, r1, plan_, li, rank_), dl.A);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.A.rows, dl.A.win));
     }
-    dl.dinv.upload(hl.dinv, stream_);
+    {
+      std::vector<double> dloc(dl.nx);
+      for (int k = 0; k < dl.n; ++k) dloc[k] = hl.dinv[r0 + k];
+      for (int k = dl.n; k < dl.nx; ++k) dloc[k] = hl.dinv[plan_.halo[l][rank_][k - dl.n]];
+      dl.dinv.upload(dloc, stream_);
+      TDGL_CUDA(cudaStreamSynchronize(stream_));
+    }
     dl.omega = (4.0 / 3.0) / hl.rho;
-    if (l + 1 < H.levels.size()) {
-      upload_csr(hl.P, dl.P);
-      upload_csr(hl.R, dl.R);
+    if (l + 1 < L) {
+      const int64_t c0 = plan_.off[l + 1][rank_], c1 = plan_.off[l + 1][rank_ + 1];
+      upload_csr(extract_local(hl.P, r0, r1, plan_, li + 1, rank_), dl.P);
+      upload_csr(extract_local(hl.R, c0, c1, plan_, li, rank_), dl.R);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.P.rows, dl.P.win));
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.R.rows, dl.R.win));
     }
-    dl.x.alloc(dl.n);
-    dl.r.alloc(dl.n);
-    if (l > 0) { dl.b.alloc(dl.n); dl.y.alloc(dl.n); }
-    TDGL_CUDA(cudaStreamSynchronize(stream_));  // host vectors die with H
+    dl.x.view(arena_.p + lay.off[vec_id(li, 0)], dl.nx);
+    dl.r.view(arena_.p + lay.off[vec_id(li, 1)], dl.nx);
+    dl.b.view(arena_.p + lay.off[vec_id(li, 2)], dl.nx);
+    dl.y.view(arena_.p + lay.off[vec_id(li, 3)], dl.nx);
+    if (world_ > 1) {
+      std::vector<int> sidx;
+      for (const SendBlock& b : send_blocks(plan_, li, rank_)) sidx.insert(sidx.end(), b.idx.begin(), b.idx.end());
+      if (sidx.empty()) sidx.push_back(0);
+      dl.send_idx.upload(sidx, stream_);
+      TDGL_CUDA(cudaStreamSynchronize(stream_));
+      dl.ex_x = make_exch(li, vec_id(li, 0), 1, dl.send_idx.p);
+      dl.ex_r = make_exch(li, vec_id(li, 1), 1, dl.send_idx.p);
+      dl.ex_b = make_exch(li, vec_id(li, 2), 1, dl.send_idx.p);
+      dl.ex_y = make_exch(li, vec_id(li, 3), 1, dl.send_idx.p);
+    }
   }
-  nc_ = static_cast<int>(H.nc);
-  coarse_inv_.upload(H.coarse_inv, stream_);
-  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  if (world_ > 1) {
+    const int* s0 = levels_[0].send_idx.p;
+    ex_psi_[0] = make_exch(0, kVecPsi0, 2, s0);
+    ex_psi_[1] = make_exch(0, kVecPsi1, 2, s0);
+    ex_mu_ = make_exch(0, kVecMu, 1, s0);
+    ex_cg_r_ = make_exch(0, kVecCgR, 1, s0);
+    ex_cg_p_ = make_exch(0, kVecCgP, 1, s0);
+  }
+  {
+    // coarsest level: this shard's rows of the dense inverse, columns in local order
+    const int lc = static_cast<int>(L) - 1;
+    nc_ = static_cast<int>(H.nc);
+    const int64_t r0 = plan_.off[lc][rank_], r1 = plan_.off[lc][rank_ + 1];
+    nc_own_ = static_cast<int>(r1 - r0);
+    std::vector<double> loc(static_cast<size_t>(std::max(nc_own_, 1)) * nc_, 0.0);
+    for (int i = 0; i < nc_own_; ++i)
+      for (int64_t gcol = 0; gcol < nc_; ++gcol) {
+        const int64_t lcidx = plan_.local_index(lc, rank_, gcol);
+        loc[static_cast<size_t>(i) * nc_ + lcidx] = H.coarse_inv[(r0 + i) * nc_ + gcol];
+      }
+    coarse_inv_.upload(loc, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
 
-  cg_b_.alloc(N_); cg_r_.alloc(N_); cg_p_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_);
-  cg_p_.zero(stream_);
+  cg_b_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_);
   const size_t max_grid = static_cast<size_t>(max_grid_rows) + 2;
   partials_.alloc(2 * std::max<size_t>(max_grid, 4096));
   counter_.alloc(4);
   counter_.zero(stream_);
-  tmp_c_.alloc(N_);
-  tmp_d_.alloc(N_);
-  tmp_d2_.alloc(N_);
+  tmp_c_.alloc(Ng_);
+  tmp_d_.alloc(Ng_);
+  tmp_d2_.alloc(Ng_);
   tmp_e_.alloc(E_);
   tmp_e2_.alloc(E_);
 
@@ -268,6 +400,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   h_ctl_->tentative_dt = 1e-6; h_ctl_->dt = 1e-6;
   ctl_.alloc(1);
   push_ctl();
+  {
+    double* none[kMaxWorld] = {};
+    none[rank_] = arena_.p;
+    upload_comm(none);
+  }
 
   // link variables for A = 0
   {
@@ -275,6 +412,9 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     set_link_exponents(zeroA.data());
   }
 
+  // A sharded engine records its graph with the exchange kernels in place; they are only
+  // ever executed after comm_connect_*().
+  comm_on_ = world_ > 1;
   graph_mode_ = 2;
   if (cfg_.use_graph == 1) {
     try {
@@ -290,9 +430,73 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       if (std::getenv("TDGL_B200_VERBOSE")) fprintf(stderr, "[tdgl_b200] %s\n", last_error.c_str());
     }
   }
+  comm_on_ = false;  // until the peers are connected
+  connected_ = world_ == 1;
+}
+
+void Engine::upload_comm(double* const* peers) {
+  Comm c;
+  c.rank = rank_;
+  c.world = world_;
+  for (int q = 0; q < world_; ++q) c.peer[q] = peers[q];
+  TDGL_CUDA(cudaMemcpyAsync(comm_.p, &c, sizeof(Comm), cudaMemcpyHostToDevice, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::comm_export(void* handle_out) {
+  cudaIpcMemHandle_t h;
+  TDGL_CUDA(cudaIpcGetMemHandle(&h, arena_.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::memcpy(handle_out, &h, sizeof h);
+}
+
+void Engine::comm_connect_ipc(const void* handles) {
+  if (world_ == 1) return;
+  TDGL_CUDA(cudaSetDevice(cfg_.device));
+  double* peers[kMaxWorld] = {};
+  for (int q = 0; q < world_; ++q) {
+    if (q == rank_) { peers[q] = arena_.p; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + 64 * q, sizeof h);
+    void* p = nullptr;
+    TDGL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ipc_opened_.push_back(p);
+    peers[q] = static_cast<double*>(p);
+  }
+  upload_comm(peers);
+  comm_on_ = connected_ = true;
+}
+
+void Engine::comm_connect_local(Engine* const* engines) {
+  if (world_ == 1) return;
+  TDGL_CUDA(cudaSetDevice(cfg_.device));
+  double* peers[kMaxWorld] = {};
+  for (int q = 0; q < world_; ++q) {
+    Engine* e = engines[q];
+    if (e == nullptr || e->world_ != world_ || e->rank_ != q || e->Ng_ != Ng_)
+      throw std::invalid_argument("comm_connect_local: engine list does not match the shards");
+    if (e->cfg_.device != cfg_.device) {
+      const cudaError_t err = cudaDeviceEnablePeerAccess(e->cfg_.device, 0);
+      if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) TDGL_CUDA(err);
+      cudaGetLastError();
+    }
+    peers[q] = e->arena_.p;
+  }
+  upload_comm(peers);
+  comm_on_ = connected_ = true;
+}
+
+void Engine::shard_info(int64_t* out, int n) {
+  int64_t halo_total = 0, nbr0 = 0;
+  for (int l = 0; l < plan_.levels; ++l) halo_total += static_cast<int64_t>(plan_.halo[l][rank_].size());
+  nbr0 = ex_mu_.nnbr;
+  const int64_t vals[8] = {world_, rank_, Ng_, N_, Nx_ - N_, halo_total, nbr0,
+                           static_cast<int64_t>(ex_mu_.send_begin[ex_mu_.nnbr])};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = vals[i];
 }
 
 Engine::~Engine() {
+  for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
   if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   if (graph_) cudaGraphDestroy(graph_);
   if (h_ctl_) cudaFreeHost(h_ctl_);
@@ -338,8 +542,9 @@ void Engine::configure_kernels() {
 template <int OP>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
   const size_t smem = static_cast<size_t>(A.m.cap) * 12;
-  kw_real<OP><<<grid_win(A.m.rows, A.win), A.win, smem, stream_>>>(ctl_.p, A.m, a, partials_.p,
-                                                                   counter_.p);
+  if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
+  kw_real<OP><<<grid_win(A.m.rows, A.win), A.win, smem, stream_>>>(ctl_.p, comm(), A.m, a,
+                                                                   partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -379,33 +584,55 @@ void Engine::launch_residual(const CsrView& A, const double* x, const double* b,
 
 // z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
 // smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
+void Engine::enqueue_exchange(const ExchArgs& a, const double* src) {
+  if (!comm_on_) return;
+  k_halo_exchange<double><<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, a, src);
+  TDGL_LAUNCH_CHECK();
+}
+
+void Engine::enqueue_exchange_psi() {
+  if (!comm_on_) return;
+  k_halo_exchange_psi<<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, ex_psi_[0], ex_psi_[1], psi_[0].p,
+                                              psi_[1].p);
+  TDGL_LAUNCH_CHECK();
+}
+
 void Engine::enqueue_vcycle(const double* r_in, double* z_out, double* rz_out) {
   const size_t L = levels_.size();
   if (L == 1) {
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, coarse_inv_.p, r_in, z_out);
+    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, nc_, coarse_inv_.p, r_in, z_out);
     TDGL_LAUNCH_CHECK();
-    k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, r_in, z_out, partials_.p, counter_.p, rz_out);
+    k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
     TDGL_LAUNCH_CHECK();
     return;
   }
+  // Sharded: a vector is exchanged right before the kernel that gathers from it (r_in is
+  // the CG residual, whose halo slots live in the arena like every level vector's).
   for (size_t l = 0; l + 1 < L; ++l) {
     DevLevel& lv = levels_[l];
     const double* b = (l == 0) ? r_in : lv.b.p;
+    enqueue_exchange(l == 0 ? ex_cg_r_ : lv.ex_b, b);
     launch_presmooth(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, lv.r.p);
+    enqueue_exchange(lv.ex_r, lv.r.p);
     launch_plain(lv.R.view(), lv.r.p, levels_[l + 1].b.p, false);
   }
   {
     DevLevel& c = levels_[L - 1];
-    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, coarse_inv_.p, c.b.p, c.y.p);
-    TDGL_LAUNCH_CHECK();
+    enqueue_exchange(c.ex_b, c.b.p);  // all-gather of the coarsest right-hand side
+    if (nc_own_ > 0) {
+      const int grid = (nc_own_ * 32 + kBlock - 1) / kBlock;
+      k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_own_, nc_, coarse_inv_.p, c.b.p, c.y.p);
+      TDGL_LAUNCH_CHECK();
+    }
   }
   for (size_t l = L - 1; l-- > 0;) {
     DevLevel& lv = levels_[l];
     const double* b = (l == 0) ? r_in : lv.b.p;
     double* y = (l == 0) ? z_out : lv.y.p;
+    enqueue_exchange(levels_[l + 1].ex_y, levels_[l + 1].y.p);
     launch_plain(lv.P.view(), levels_[l + 1].y.p, lv.x.p, true);
+    enqueue_exchange(lv.ex_x, lv.x.p);
     launch_jacobi(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, y, (l == 0) ? r_in : nullptr,
                   (l == 0) ? rz_out : nullptr);
   }
@@ -420,8 +647,8 @@ void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
 
 void Engine::enqueue_mu_rhs(double* rhs_raw) {
   kw_mu_rhs<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, stream_>>>(
-      ctl_.p, site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p,
-      cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
+      ctl_.p, comm(), site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p,
+      bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -429,20 +656,22 @@ void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new);
   k_cg_direction<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, cg_z_.p, cg_p_.p);
   TDGL_LAUNCH_CHECK();
+  enqueue_exchange(ex_cg_p_, cg_p_.p);
   launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp);
-  k_cg_update<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_p_.p, cg_Ap_.p, mu_.p, cg_r_.p,
-                                                   partials_.p, counter_.p, cond);
+  k_cg_update<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_p_.p, cg_Ap_.p, mu_.p,
+                                                   cg_r_.p, partials_.p, counter_.p, cond);
   TDGL_LAUNCH_CHECK();
 }
 
 // project mu to area-weighted mean zero (fixes the gauge the reference leaves to SuperLU
 // roundoff)
 void Engine::enqueue_mu_finish() {
-  k_weighted_sum<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, areas_.p, mu_.p, partials_.p,
-                                                      counter_.p, 1.0 / total_area_);
+  k_weighted_sum<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, areas_.p, mu_.p,
+                                                      partials_.p, counter_.p, 1.0 / total_area_);
   TDGL_LAUNCH_CHECK();
   k_shift<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, mu_.p);
   TDGL_LAUNCH_CHECK();
+  enqueue_exchange(ex_mu_, mu_.p);  // the next step's rhs / the edge currents read mu's halo
 }
 
 void Engine::host_solve_loop() {
@@ -518,11 +747,12 @@ void Engine::build_graph() {
     GraphBuilder pb{psi_body, stream_, {}};
     pb.capture([&] {
       enqueue_psi_step(nullptr, -1.0);
-      k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, h_psi_);
+      k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, comm(), h_psi_);
       TDGL_LAUNCH_CHECK();
     });
   }
   sb.capture([&] {
+    enqueue_exchange_psi();
     enqueue_mu_rhs(nullptr);
     k_cg_begin<<<1, 32, 0, stream_>>>(ctl_.p, h_cg_);
     TDGL_LAUNCH_CHECK();
@@ -557,8 +787,8 @@ void Engine::set_link_exponents(const double* A) {
 }
 
 void Engine::set_epsilon(const double* eps) {
-  tmp_d_.upload(eps, N_, stream_);
-  k_gather<double><<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, eps_.p);
+  tmp_d_.upload(eps, Ng_, stream_);
+  k_gather<double><<<(Nx_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(Nx_, dperm_.p, tmp_d_.p, eps_.p);
   TDGL_LAUNCH_CHECK();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -576,11 +806,12 @@ void Engine::set_mu_boundary(const double* mub) {
 void Engine::set_state(const double* psi, const double* mu) {
   sync_ctl_to_host();
   const int cur = h_ctl_->cur;
-  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
-  k_gather<double2><<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_c_.p, psi_[cur].p);
+  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi, sizeof(double2) * Ng_, cudaMemcpyHostToDevice, stream_));
+  // owned and halo entries are both filled from the caller's (whole-mesh) arrays
+  k_gather<double2><<<(Nx_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(Nx_, dperm_.p, tmp_c_.p, psi_[cur].p);
   TDGL_LAUNCH_CHECK();
-  tmp_d_.upload(mu, N_, stream_);
-  k_gather<double><<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, dperm_.p, tmp_d_.p, mu_.p);
+  tmp_d_.upload(mu, Ng_, stream_);
+  k_gather<double><<<(Nx_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(Nx_, dperm_.p, tmp_d_.p, mu_.p);
   TDGL_LAUNCH_CHECK();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -603,6 +834,8 @@ void Engine::set_stepper(double dt_init, double dt_max, int adaptive, int window
 
 Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t step, double time) {
   if (max_steps < 1) throw std::invalid_argument("max_steps must be >= 1");
+  if (!connected_) throw std::invalid_argument("sharded engine: connect the peers first (tdgl_comm_connect_*)");
+  comm_on_ = world_ > 1;
   sync_ctl_to_host();
   h_ctl_->steps_left = max_steps;
   h_ctl_->steps_done = 0;
@@ -622,19 +855,22 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     ++launches_;
     sync_ctl_to_host();
     // the graph's kernels were launched by the device-side loops; account for them
-    launches_ += h_ctl_->steps_done * 6 + h_ctl_->total_retries * 2 +
-                 h_ctl_->total_cg_it * (3 + 4 * (static_cast<int64_t>(levels_.size()) - 1) + 1);
+    const int64_t L = static_cast<int64_t>(levels_.size());
+    const int64_t ex_step = world_ > 1 ? 2 : 0, ex_it = world_ > 1 ? (4 * L - 3) + 1 : 0;
+    launches_ += h_ctl_->steps_done * (6 + ex_step) + h_ctl_->total_retries * 2 +
+                 h_ctl_->total_cg_it * (3 + 4 * (L - 1) + 1 + ex_it);
   } else {
     while (true) {
       k_step_begin<<<1, 32, 0, stream_>>>(ctl_.p, 0);
       TDGL_LAUNCH_CHECK();
       do {
         enqueue_psi_step(nullptr, -1.0);
-        k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, 0);
+        k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, comm(), 0);
         TDGL_LAUNCH_CHECK();
         sync_ctl_to_host();
       } while (h_ctl_->psi_go);
       if (h_ctl_->status != 0) break;
+      enqueue_exchange_psi();
       enqueue_mu_rhs(nullptr);
       host_solve_loop();
       enqueue_mu_finish();
@@ -673,15 +909,18 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
   AdvanceInfo info = advance(1, 1e300, step, time);
   const int cur = h_ctl_->cur;
   const int g = (N_ + kBlock - 1) / kBlock;
+  // a shard fills its own sites (edges) and leaves zeros elsewhere: the caller sums shards
   if (psi_out != nullptr) {
+    if (world_ > 1) tmp_c_.zero(stream_);
     k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, psi_[cur].p, tmp_c_.p);
     TDGL_LAUNCH_CHECK();
-    TDGL_CUDA(cudaMemcpyAsync(psi_out, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+    TDGL_CUDA(cudaMemcpyAsync(psi_out, tmp_c_.p, sizeof(double2) * Ng_, cudaMemcpyDeviceToHost, stream_));
   }
   if (mu_out != nullptr) {
+    if (world_ > 1) tmp_d_.zero(stream_);
     k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
     TDGL_LAUNCH_CHECK();
-    tmp_d_.download(mu_out, N_, stream_);
+    tmp_d_.download(mu_out, Ng_, stream_);
   }
   if (js != nullptr || jn != nullptr) {
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
@@ -699,14 +938,16 @@ void Engine::get_state(double* psi, double* mu) {
   const int cur = h_ctl_->cur;
   const int g = (N_ + kBlock - 1) / kBlock;
   if (psi != nullptr) {
+    if (world_ > 1) tmp_c_.zero(stream_);
     k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, psi_[cur].p, tmp_c_.p);
     TDGL_LAUNCH_CHECK();
-    TDGL_CUDA(cudaMemcpyAsync(psi, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+    TDGL_CUDA(cudaMemcpyAsync(psi, tmp_c_.p, sizeof(double2) * Ng_, cudaMemcpyDeviceToHost, stream_));
   }
   if (mu != nullptr) {
+    if (world_ > 1) tmp_d_.zero(stream_);
     k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
     TDGL_LAUNCH_CHECK();
-    tmp_d_.download(mu, N_, stream_);
+    tmp_d_.download(mu, Ng_, stream_);
   }
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -740,6 +981,7 @@ void Engine::get_running(int64_t capacity, double* dt, double* mu_probe, double*
 // ---- single operators ------------------------------------------------------------------------
 
 void Engine::op_psi_laplacian(const double* x, double* y) {
+  if (world_ > 1) throw std::invalid_argument("single-operator calls are not available on a sharded engine");
   // complex SpMV through the psi-step kernel's gather path is not exposed separately; use
   // the rhs kernel's building block: run k_psi_lap (fixed rows -> identity)
   const int g = (N_ + kBlock - 1) / kBlock;
@@ -759,6 +1001,7 @@ void Engine::op_psi_laplacian(const double* x, double* y) {
 
 void Engine::op_psi_step(const double* psi, const double* mu, double dt, double* psi_out,
                          double* sq_out, int* failed) {
+  if (world_ > 1) throw std::invalid_argument("single-operator calls are not available on a sharded engine");
   const int g = (N_ + kBlock - 1) / kBlock;
   DevBuf<double2> pin, pout;
   DevBuf<double> muin, sq;
@@ -793,6 +1036,7 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
 }
 
 void Engine::op_mu_rhs(const double* psi, double* rhs) {
+  if (world_ > 1) throw std::invalid_argument("single-operator calls are not available on a sharded engine");
   const int g = (N_ + kBlock - 1) / kBlock;
   DevBuf<double2> pin;
   DevBuf<double> raw, b, r;
@@ -803,7 +1047,7 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   sync_ctl_to_host();
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
   kw_mu_rhs<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, stream_>>>(
-      ctl_.p, site_csr(), lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p,
+      ctl_.p, comm(), site_csr(), lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p,
       raw.p, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
@@ -815,6 +1059,7 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
 }
 
 void Engine::op_mu_laplacian(const double* x, double* y) {
+  if (world_ > 1) throw std::invalid_argument("single-operator calls are not available on a sharded engine");
   // mu_laplacian = -diag(1/areas) A
   const int g = (N_ + kBlock - 1) / kBlock;
   DevBuf<double> xin, yout;
@@ -832,6 +1077,7 @@ void Engine::op_mu_laplacian(const double* x, double* y) {
 }
 
 void Engine::op_mu_solve(const double* rhs, double* mu, int* iterations, double* rel_res) {
+  if (world_ > 1) throw std::invalid_argument("single-operator calls are not available on a sharded engine");
   const int g = (N_ + kBlock - 1) / kBlock;
   DevBuf<double> saved;
   saved.alloc(N_);
@@ -847,9 +1093,9 @@ void Engine::op_mu_solve(const double* rhs, double* mu, int* iterations, double*
   h_ctl_->status = 0;
   h_ctl_->total_cg_it = 0;
   push_ctl();
-  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_b_.p, cg_b_.p, partials_.p, counter_.p, &ctl_.p->bb);
+  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_b_.p, cg_b_.p, partials_.p, counter_.p, &ctl_.p->bb);
   TDGL_LAUNCH_CHECK();
-  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
+  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
   TDGL_LAUNCH_CHECK();
   host_solve_loop();
   enqueue_mu_finish();
@@ -869,6 +1115,7 @@ void Engine::op_mu_solve(const double* rhs, double* mu, int* iterations, double*
 
 double Engine::time_kernel(int which, int reps, int flush_l2) {
   if (reps < 1) reps = 1;
+  comm_on_ = false;  // one shard is timed on its own: no exchange steps in these launches
   sync_ctl_to_host();
   Ctl saved = *h_ctl_;
   DevBuf<double> mu_saved;
@@ -891,7 +1138,7 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
       case 4:
         mu_.zero(stream_);
         TDGL_CUDA(cudaMemcpyAsync(cg_r_.p, cg_b_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
-        k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
+        k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
         TDGL_LAUNCH_CHECK();
         host_solve_loop();
         break;
@@ -949,7 +1196,7 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
 }
 
 void Engine::get_info(int64_t* out, int n) {
-  const int64_t vals[8] = {N_, E_, nnz_, static_cast<int64_t>(levels_.size()), amg_nnz_, nc_,
+  const int64_t vals[8] = {Ng_, E_, nnz_, static_cast<int64_t>(levels_.size()), amg_nnz_, nc_,
                            launches_, graph_mode_};
   for (int i = 0; i < n && i < 8; ++i) out[i] = vals[i];
 }
@@ -1013,6 +1260,7 @@ int tdgl_create(tdgl_handle** out, int64_t n_sites, int64_t n_edges, int64_t n_b
     if (config->use_graph > 0) cfg.use_graph = config->use_graph;
     if (config->reorder > 0) cfg.reorder = config->reorder;
     if (config->running_capacity > 0) cfg.running_capacity = config->running_capacity;
+    if (config->world > 0) { cfg.world = config->world; cfg.rank = config->rank; }
   }
   auto h = std::make_unique<tdgl_handle>();
   try {
@@ -1083,6 +1331,7 @@ int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, 
   if (rc != TDGL_OK) return rc;
   if (status == 1) { h->error = "Solver failed to converge (|psi|^2 discriminant < 0 after max_solve_retries)"; return TDGL_E_STEP_FAILED; }
   if (status == 2) { h->error = "mu solver did not reach tolerance within mu_max_iter iterations"; return TDGL_E_MU_SOLVER; }
+  if (status == 3) { h->error = "shard exchange timed out (a peer shard stopped or was never connected)"; return TDGL_E_CUDA; }
   return TDGL_OK;
 }
 
@@ -1167,6 +1416,33 @@ int tdgl_get_info(tdgl_handle* h, int64_t* out, int32_t n) {
   return guarded(h, [&](tdgl::Engine& e) { e.get_info(out, n); });
 }
 
+int tdgl_comm_export(tdgl_handle* h, void* handle_out) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (handle_out == nullptr) throw std::invalid_argument("null handle buffer");
+    e.comm_export(handle_out);
+  });
+}
+int tdgl_comm_connect_ipc(tdgl_handle* h, const void* handles, int32_t world) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (handles == nullptr || world != e.world()) throw std::invalid_argument("handle list does not match the number of shards");
+    e.comm_connect_ipc(handles);
+  });
+}
+int tdgl_comm_connect_local(tdgl_handle* h, tdgl_handle* const* peers, int32_t world) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (peers == nullptr || world != e.world()) throw std::invalid_argument("peer list does not match the number of shards");
+    tdgl::Engine* list[tdgl::kMaxWorld] = {};
+    for (int q = 0; q < world; ++q) {
+      if (peers[q] == nullptr || !peers[q]->engine) throw std::invalid_argument("null peer");
+      list[q] = peers[q]->engine.get();
+    }
+    e.comm_connect_local(list);
+  });
+}
+int tdgl_shard_info(tdgl_handle* h, int64_t* out, int32_t n) {
+  return guarded(h, [&](tdgl::Engine& e) { e.shard_info(out, n); });
+}
+
 int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
                         const double* edge_lengths, const double* dual_edge_lengths,
                         double theta, int32_t max_coarse, int32_t* n_levels,
@@ -1240,6 +1516,234 @@ int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
     }
     for (int64_t i = 0; i < n; ++i) x[i] = sol[i];
     if (iterations) *iterations = it;
+    return TDGL_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return TDGL_E_INVALID;
+  }
+}
+
+
+// Host-only validation of the domain decomposition: builds the same plan the sharded engine
+// builds, extracts every shard's local operators, and runs the sharded AMG-PCG with all
+// shards emulated in this process (halo exchange = the copies the exchange kernel does,
+// all-reduce = sums in rank order).  Also reports the plan (CPU tests, gloo tests).
+int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
+                          const double* edge_lengths, const double* dual_edge_lengths,
+                          const double* sites_xy, int32_t world, double theta,
+                          int32_t max_coarse, int32_t* n_levels, int64_t* level_off,
+                          int64_t* halo_sizes, int64_t* site_owner_perm, const double* rhs,
+                          double* x, int32_t max_iter, double rtol, int32_t* iterations) {
+  using namespace tdgl;
+  try {
+    if (sites_xy == nullptr) throw std::invalid_argument("site coordinates required");
+    std::vector<int> perm = morton_permutation(sites_xy, n_sites), inv(n_sites);
+    for (int64_t i = 0; i < n_sites; ++i) inv[perm[i]] = static_cast<int>(i);
+    std::vector<int32_t> e0(n_edges), e1(n_edges);
+    for (int64_t e = 0; e < n_edges; ++e) { e0[e] = inv[edges[2 * e]]; e1[e] = inv[edges[2 * e + 1]]; }
+    SiteGraph g = build_site_graph(n_sites, n_edges, e0.data(), e1.data());
+    HostCsr<double> A;
+    A.rows = A.cols = n_sites;
+    A.ptr = g.ptr; A.idx = g.nbr; A.val.assign(g.nbr.size(), 0.0);
+    for (int64_t i = 0; i < n_sites; ++i) {
+      double diag = 0; int kd = -1;
+      for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
+        if (g.edge[k] < 0) { kd = k; continue; }
+        const double w = dual_edge_lengths[g.edge[k]] / edge_lengths[g.edge[k]];
+        A.val[k] = -w; diag += w;
+      }
+      A.val[kd] = diag;
+    }
+    const std::vector<int64_t> off0 = equal_offsets(n_sites, world);
+    AmgHierarchy H = build_amg(std::move(A), theta > 0 ? theta : 0.08, max_coarse > 0 ? max_coarse : 200, 24, &off0);
+    ShardPlan plan = make_plan(H);
+    const int L = plan.levels, W = plan.world;
+    if (n_levels) *n_levels = L;
+    for (int l = 0; l < L && l < 32; ++l)
+      for (int r = 0; r <= W; ++r) {
+        if (level_off) level_off[l * 9 + r] = plan.off[l][r];
+        if (halo_sizes && r < W) halo_sizes[l * 8 + r] = static_cast<int64_t>(plan.halo[l][r].size());
+      }
+    if (site_owner_perm) for (int64_t i = 0; i < n_sites; ++i) site_owner_perm[i] = perm[i];
+    if (rhs == nullptr || x == nullptr) return TDGL_OK;
+
+    // ---- local operators of every shard ---------------------------------------------------
+    struct Shard { std::vector<HostCsr<double>> A, P, R; std::vector<std::vector<double>> dinv, b, x, r, y; };
+    std::vector<Shard> S(W);
+    for (int p = 0; p < W; ++p) {
+      Shard& s = S[p];
+      s.A.resize(L); s.P.resize(L); s.R.resize(L); s.dinv.resize(L); s.b.resize(L); s.x.resize(L); s.r.resize(L); s.y.resize(L);
+      for (int l = 0; l < L; ++l) {
+        const int64_t r0 = plan.off[l][p], r1 = plan.off[l][p + 1];
+        const int64_t nx = plan.local_size(l, p);
+        s.A[l] = extract_local(H.levels[l].A, r0, r1, plan, l, p);
+        if (l + 1 < L) {
+          s.P[l] = extract_local(H.levels[l].P, r0, r1, plan, l + 1, p);
+          s.R[l] = extract_local(H.levels[l].R, plan.off[l + 1][p], plan.off[l + 1][p + 1], plan, l, p);
+        }
+        s.dinv[l].resize(nx);
+        for (int64_t k = 0; k < nx; ++k) {
+          const int64_t gi = k < r1 - r0 ? r0 + k : plan.halo[l][p][k - (r1 - r0)];
+          s.dinv[l][k] = H.levels[l].dinv[gi];
+        }
+        s.b[l].assign(nx, 0.0); s.x[l].assign(nx, 0.0); s.r[l].assign(nx, 0.0); s.y[l].assign(nx, 0.0);
+      }
+    }
+    // exchange of one vector family on one level: exactly the copies k_halo_exchange makes
+    auto exchange = [&](int l, std::vector<double> Shard::*dummy, int which) {
+      (void)dummy;
+      for (int p = 0; p < W; ++p)
+        for (const SendBlock& blk : send_blocks(plan, l, p)) {
+          auto pick = [&](Shard& s) -> std::vector<double>& { return which == 0 ? s.x[l] : which == 1 ? s.r[l] : which == 2 ? s.b[l] : s.y[l]; };
+          std::vector<double>& src = pick(S[p]);
+          std::vector<double>& dst = pick(S[blk.peer]);
+          const int64_t base = plan.owned(l, blk.peer) + blk.dst_pos;
+          for (size_t k = 0; k < blk.idx.size(); ++k) dst[base + k] = src[blk.idx[k]];
+        }
+    };
+    auto local_spmv = [&](const HostCsr<double>& M, const std::vector<double>& xin, std::vector<double>& yout, bool add) {
+      for (int64_t i = 0; i < M.rows; ++i) {
+        double sum = 0;
+        for (int32_t k = M.ptr[i]; k < M.ptr[i + 1]; ++k) sum += M.val[k] * xin[M.idx[k]];
+        yout[i] = add ? yout[i] + sum : sum;
+      }
+    };
+    std::vector<double> tmp;
+    std::function<void(int)> cycle = [&](int l) {
+      if (l == L - 1) {
+        exchange(l, nullptr, 2);
+        const int64_t nc = H.nc;
+        for (int p = 0; p < W; ++p)
+          for (int64_t i = 0; i < plan.owned(l, p); ++i) {
+            double sum = 0;
+            for (int64_t gc = 0; gc < nc; ++gc)
+              sum += H.coarse_inv[(plan.off[l][p] + i) * nc + gc] * S[p].b[l][plan.local_index(l, p, gc)];
+            S[p].y[l][i] = sum;
+          }
+        return;
+      }
+      const double om = (4.0 / 3.0) / H.levels[l].rho;
+      exchange(l, nullptr, 2);
+      for (int p = 0; p < W; ++p) {
+        Shard& s = S[p];
+        const int64_t nx = plan.local_size(l, p), n = plan.owned(l, p);
+        tmp.assign(nx, 0.0);
+        for (int64_t k = 0; k < nx; ++k) tmp[k] = om * s.dinv[l][k] * s.b[l][k];  // x incl. halo, as presmooth forms it
+        for (int64_t i = 0; i < n; ++i) s.x[l][i] = tmp[i];
+        std::vector<double> ax(n);
+        local_spmv(s.A[l], tmp, ax, false);
+        for (int64_t i = 0; i < n; ++i) s.r[l][i] = s.b[l][i] - ax[i];
+      }
+      exchange(l, nullptr, 1);
+      for (int p = 0; p < W; ++p) local_spmv(S[p].R[l], S[p].r[l], S[p].b[l + 1], false);
+      cycle(l + 1);
+      exchange(l + 1, nullptr, 3);
+      for (int p = 0; p < W; ++p) local_spmv(S[p].P[l], S[p].y[l + 1], S[p].x[l], true);
+      exchange(l, nullptr, 0);
+      for (int p = 0; p < W; ++p) {
+        Shard& s = S[p];
+        const int64_t n = plan.owned(l, p);
+        std::vector<double> ax(n);
+        local_spmv(s.A[l], s.x[l], ax, false);
+        for (int64_t i = 0; i < n; ++i) s.y[l][i] = s.x[l][i] + om * s.dinv[l][i] * (s.b[l][i] - ax[i]);
+      }
+    };
+    // ---- sharded PCG (b, r live in level-0 `b`; p in level-0 `r` slot of a scratch) ---------
+    std::vector<std::vector<double>> r(W), pv(W), sol(W), Ap(W);
+    double bb = 0;
+    for (int p = 0; p < W; ++p) {
+      const int64_t n = plan.owned(0, p), nx = plan.local_size(0, p);
+      r[p].resize(n); pv[p].assign(nx, 0.0); sol[p].assign(n, 0.0); Ap[p].resize(n);
+      double part = 0;
+      for (int64_t i = 0; i < n; ++i) { r[p][i] = rhs[perm[plan.off[0][p] + i]]; part += r[p][i] * r[p][i]; }
+      bb += part;
+    }
+    double rz_prev = 1.0, rnorm2 = bb;
+    int it = 0;
+    while (rnorm2 > rtol * rtol * bb && it < max_iter) {
+      for (int p = 0; p < W; ++p) std::copy(r[p].begin(), r[p].end(), S[p].b[0].begin());
+      cycle(0);
+      double rz = 0;
+      for (int p = 0; p < W; ++p) { double part = 0; for (size_t i = 0; i < r[p].size(); ++i) part += r[p][i] * S[p].y[0][i]; rz += part; }
+      const double beta = it == 0 ? 0.0 : rz / rz_prev;
+      for (int p = 0; p < W; ++p) {
+        for (size_t i = 0; i < r[p].size(); ++i) pv[p][i] = S[p].y[0][i] + beta * pv[p][i];
+        std::copy(pv[p].begin(), pv[p].begin() + r[p].size(), S[p].x[0].begin());
+      }
+      exchange(0, nullptr, 0);  // p's halo (through the x slot)
+      double pAp = 0;
+      for (int p = 0; p < W; ++p) {
+        local_spmv(S[p].A[0], S[p].x[0], Ap[p], false);
+        double part = 0; for (size_t i = 0; i < r[p].size(); ++i) part += pv[p][i] * Ap[p][i];
+        pAp += part;
+      }
+      const double alpha = rz / pAp;
+      rnorm2 = 0;
+      for (int p = 0; p < W; ++p) {
+        double part = 0;
+        for (size_t i = 0; i < r[p].size(); ++i) { sol[p][i] += alpha * pv[p][i]; r[p][i] -= alpha * Ap[p][i]; part += r[p][i] * r[p][i]; }
+        rnorm2 += part;
+      }
+      rz_prev = rz; ++it;
+    }
+    for (int p = 0; p < W; ++p)
+      for (size_t i = 0; i < sol[p].size(); ++i) x[perm[plan.off[0][p] + i]] = sol[p][i];
+    if (iterations) *iterations = it;
+    return TDGL_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return TDGL_E_INVALID;
+  }
+}
+
+// Level-0 exchange lists of one shard, in the caller's site numbering (CPU / gloo tests):
+// owned[n_owned], halo[n_halo] site ids, and for every peer the owned sites sent to it
+// (send_ptr[world + 1] ranges into send_sites, in the order of the peer's halo).
+// Call once with null arrays to get the sizes in counts[3] = {n_owned, n_halo, n_send}.
+int tdgl_host_shard_lists(int64_t n_sites, int64_t n_edges, const int64_t* edges,
+                          const double* edge_lengths, const double* dual_edge_lengths,
+                          const double* sites_xy, int32_t world, int32_t rank, int64_t* counts,
+                          int64_t* owned, int64_t* halo, int64_t* send_ptr, int64_t* send_sites) {
+  using namespace tdgl;
+  try {
+    if (sites_xy == nullptr || rank < 0 || rank >= world) throw std::invalid_argument("bad arguments");
+    std::vector<int> perm = morton_permutation(sites_xy, n_sites), inv(n_sites);
+    for (int64_t i = 0; i < n_sites; ++i) inv[perm[i]] = static_cast<int>(i);
+    std::vector<int32_t> e0(n_edges), e1(n_edges);
+    for (int64_t e = 0; e < n_edges; ++e) { e0[e] = inv[edges[2 * e]]; e1[e] = inv[edges[2 * e + 1]]; }
+    SiteGraph g = build_site_graph(n_sites, n_edges, e0.data(), e1.data());
+    HostCsr<double> A;
+    A.rows = A.cols = n_sites;
+    A.ptr = g.ptr; A.idx = g.nbr; A.val.assign(g.nbr.size(), 0.0);
+    for (int64_t i = 0; i < n_sites; ++i) {
+      double diag = 0; int kd = -1;
+      for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
+        if (g.edge[k] < 0) { kd = k; continue; }
+        const double w = dual_edge_lengths[g.edge[k]] / edge_lengths[g.edge[k]];
+        A.val[k] = -w; diag += w;
+      }
+      A.val[kd] = diag;
+    }
+    const std::vector<int64_t> off0 = equal_offsets(n_sites, world);
+    AmgHierarchy H = build_amg(std::move(A), 0.08, 200, 24, &off0);
+    ShardPlan plan = make_plan(H);
+    const std::vector<SendBlock> blocks = send_blocks(plan, 0, rank);
+    int64_t n_send = 0;
+    for (const SendBlock& b : blocks) n_send += static_cast<int64_t>(b.idx.size());
+    const int64_t n_owned = plan.owned(0, rank), n_halo = static_cast<int64_t>(plan.halo[0][rank].size());
+    if (counts) { counts[0] = n_owned; counts[1] = n_halo; counts[2] = n_send; }
+    if (owned) for (int64_t k = 0; k < n_owned; ++k) owned[k] = perm[plan.off[0][rank] + k];
+    if (halo) for (int64_t k = 0; k < n_halo; ++k) halo[k] = perm[plan.halo[0][rank][k]];
+    if (send_ptr && send_sites) {
+      int64_t pos = 0;
+      for (int q = 0; q < world; ++q) {
+        send_ptr[q] = pos;
+        for (const SendBlock& b : blocks)
+          if (b.peer == q)
+            for (int32_t li : b.idx) send_sites[pos++] = perm[plan.off[0][rank] + li];
+      }
+      send_ptr[world] = pos;
+    }
     return TDGL_OK;
   } catch (const std::exception& e) {
     g_create_error = e.what();

@@ -73,7 +73,7 @@ class DeviceEngine:
                  probe_sites: Optional[Sequence[int]] = None, device: int = 0,
                  mu_rtol: float = 0.0, mu_max_iter: int = 0, amg_theta: float = 0.0,
                  amg_max_coarse: int = 0, use_graph: int = 0, reorder: int = 0,
-                 running_capacity: int = 0):
+                 running_capacity: int = 0, world: int = 1, rank: int = 0):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         em = mesh.edge_mesh
@@ -100,6 +100,9 @@ class DeviceEngine:
         cfg.use_graph = use_graph
         cfg.reorder = reorder
         cfg.running_capacity = running_capacity
+        cfg.world = world
+        cfg.rank = rank
+        self.world, self.rank = int(world), int(rank)
         self.running_capacity = running_capacity or 4096
         rc = self._lib.tdgl_create(
             C.byref(self._h), self.n_sites, self.n_edges, self.n_boundary_edges, ptr(edges),
@@ -140,6 +143,32 @@ class DeviceEngine:
     @property
     def message(self) -> str:
         return self._lib.tdgl_last_error(self._h).decode()
+
+    # -- sharding: wiring of the peer arenas (include/tdgl_b200.h, "domain decomposition") ---
+    def comm_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this shard's arena (to be all-gathered)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.tdgl_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_connect_ipc(self, handles: Sequence[bytes]) -> None:
+        """``handles``: the exported handles of all shards in rank order (other processes)."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * self.world:
+            raise ValueError("need one 64-byte handle per shard")
+        self._check(self._lib.tdgl_comm_connect_ipc(self._h, blob, self.world))
+
+    def comm_connect_local(self, engines: Sequence["DeviceEngine"]) -> None:
+        """``engines``: all shards in rank order, living in this process."""
+        arr = (C.c_void_p * len(engines))(*[e._h.value for e in engines])
+        self._check(self._lib.tdgl_comm_connect_local(self._h, arr, len(engines)))
+
+    def shard_info(self) -> dict:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.tdgl_shard_info(self._h, out, 8))
+        keys = ["world", "rank", "n_sites", "n_owned", "n_halo0", "n_halo_all_levels",
+                "neighbours0", "n_send0"]
+        return dict(zip(keys, [int(v) for v in out]))
 
     # -- inputs ---------------------------------------------------------------------------
     def set_link_exponents(self, A) -> None:
@@ -262,6 +291,58 @@ class DeviceEngine:
         keys = ["n_sites", "n_edges", "nnz", "amg_levels", "amg_nnz", "amg_coarsest",
                 "launches", "graph_mode"]
         return dict(zip(keys, [int(v) for v in out]))
+
+
+def host_shard_probe(mesh, world: int, rhs=None, theta=0.0, max_coarse=0, max_iter=200,
+                     rtol=1e-10):
+    """Host-only: the domain decomposition the sharded engine builds for ``world`` shards,
+    and (optionally) the sharded AMG-PCG emulated in this process."""
+    lib = _lib.load()
+    em = mesh.edge_mesh
+    n, E = len(mesh.sites), len(em.edges)
+    nl = C.c_int32(0)
+    off = np.zeros((32, 9), dtype=np.int64)
+    halo = np.zeros((32, 8), dtype=np.int64)
+    perm = np.zeros(n, dtype=np.int64)
+    it = C.c_int32(0)
+    x = None
+    if rhs is not None:
+        rhs = as_f64(rhs, (n,))
+        x = np.zeros(n)
+    rc = lib.tdgl_host_shard_probe(n, E, ptr(as_i64(em.edges)), ptr(as_f64(em.edge_lengths)),
+                                   ptr(as_f64(em.dual_edge_lengths)),
+                                   ptr(as_f64(mesh.sites, (n, 2))), world, theta, max_coarse,
+                                   C.byref(nl), ptr(off), ptr(halo), ptr(perm), ptr(rhs), ptr(x),
+                                   max_iter, rtol, C.byref(it))
+    if rc != 0:
+        raise _lib.TDGLLibraryError(lib.tdgl_last_error(None).decode())
+    L = nl.value
+    return dict(levels=L, offsets=off[:L, :world + 1].copy(), halo_sizes=halo[:L, :world].copy(),
+                perm=perm, x=x, iterations=it.value)
+
+
+def host_shard_lists(mesh, world: int, rank: int):
+    """Host-only: level-0 exchange lists of one shard (caller site ids): owned, halo, and
+    ``send[q]`` = the owned sites sent to shard q, ordered as q's halo."""
+    lib = _lib.load()
+    em = mesh.edge_mesh
+    n, E = len(mesh.sites), len(em.edges)
+    args = (n, E, ptr(as_i64(em.edges)), ptr(as_f64(em.edge_lengths)),
+            ptr(as_f64(em.dual_edge_lengths)), ptr(as_f64(mesh.sites, (n, 2))), world, rank)
+    counts = np.zeros(3, dtype=np.int64)
+    rc = lib.tdgl_host_shard_lists(*args, ptr(counts), None, None, None, None)
+    if rc != 0:
+        raise _lib.TDGLLibraryError(lib.tdgl_last_error(None).decode())
+    owned = np.zeros(counts[0], dtype=np.int64)
+    halo = np.zeros(max(counts[1], 1), dtype=np.int64)
+    send_ptr = np.zeros(world + 1, dtype=np.int64)
+    send = np.zeros(max(counts[2], 1), dtype=np.int64)
+    rc = lib.tdgl_host_shard_lists(*args, ptr(counts), ptr(owned), ptr(halo), ptr(send_ptr),
+                                   ptr(send))
+    if rc != 0:
+        raise _lib.TDGLLibraryError(lib.tdgl_last_error(None).decode())
+    return dict(owned=owned, halo=halo[:counts[1]],
+                send=[send[send_ptr[q]:send_ptr[q + 1]] for q in range(world)])
 
 
 def host_amg_probe(mesh, theta=0.08, max_coarse=200, rhs=None, max_iter=200, rtol=1e-10):

@@ -58,6 +58,8 @@ class SolverOptions:
     mu_max_iterations: int = 500
     cuda_device: int = 0
     use_cuda_graph: bool = True   # device-side step / retry / CG loops in one CUDA graph
+    distributed: bool = False     # True: this process is one shard of a torchrun job (the
+    #                               mesh is domain-decomposed over torch.distributed's ranks)
 
     def validate(self) -> None:
         """Same checks and messages as the reference (options.py:91-166)."""

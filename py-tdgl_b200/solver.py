@@ -230,7 +230,10 @@ class TDGLSolver:
             self.psi_init[fixed] = terminal_psi
         self.mu_init = np.zeros(n)
         self.mu_boundary = np.zeros(len(mesh.edge_mesh.boundary_edge_indices))
-        self.engine = DeviceEngine(
+        engine_cls = DeviceEngine
+        if options.distributed:
+            from .sharded import DistributedEngine as engine_cls
+        self.engine = engine_cls(
             mesh, fixed_sites=fixed, fix_psi=(terminal_psi is not None), gamma=gamma, u=u,
             probe_sites=self.probe_points, device=options.cuda_device, mu_rtol=options.mu_rtol,
             mu_max_iter=options.mu_max_iterations,

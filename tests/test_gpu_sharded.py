@@ -1,0 +1,150 @@
+"""The domain-decomposed engine on the GPU.  Several shards of one mesh run
+in this process, one host thread each, on the same device: the halo-exchange and all-reduce
+kernels execute exactly as across GPUs (stores / flag spins on the peers' arenas), so a
+1-GPU box covers the sharded code path; with >= 2 GPUs the same tests also run one shard per
+device, and a torchrun job exercises the one-process-per-GPU wiring (CUDA IPC)."""
+import os
+import subprocess
+import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per shard stream
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+
+from helpers import load_case  # noqa: E402
+from oracle import tdgl_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _devices(world):
+    import torch
+
+    n = torch.cuda.device_count()
+    return [r % n for r in range(world)] if n >= world else [0] * world
+
+
+def _group(c, world, devices=None, **kw):
+    from tdgl_b200.sharded import LocalShardGroup
+
+    fixed = (np.concatenate([np.asarray(t.site_indices) for t in c.terminals])
+             if c.terminals else None)
+    g = LocalShardGroup(c.mesh, world, devices=devices, fixed_sites=fixed, fix_psi=True,
+                        gamma=c.gamma, u=c.u, probe_sites=c.probes, **kw)
+    g.set_link_exponents(c.A)
+    g.set_epsilon(c.eps)
+    return g
+
+
+def _stepper(c):
+    o = c.opts
+    return dict(dt_init=o["dt_init"], dt_max=o["dt_max"], adaptive=o.get("adaptive", True))
+
+
+@pytest.mark.parametrize("world,use_graph", [(2, 1), (4, 1), (3, 2)])
+def test_sharded_smooth_trajectory_matches_reference(world, use_graph):
+    """film20_fixed, 1000 fixed-dt steps on `world` shards: same 1e-8 gauge-fixed parity with
+    the reference as the single-GPU engine."""
+    c = load_case("film20_fixed")
+    g = c.g
+    with _group(c, world, use_graph=use_graph, running_capacity=1000) as grp:
+        grp.set_stepper(**_stepper(c))
+        grp.set_state(np.ones(len(c.mesh.sites), complex), np.zeros(len(c.mesh.sites)))
+        info = grp.advance(1000, 1e300, 0, 0.0)
+        assert info.steps_done == 1000
+        psi, mu = grp.get_state()
+        js, jn = grp.get_currents()
+        dt, mu_p, th_p = grp.get_running(1000)
+        print("shards", grp.shard_info(), "info", grp.info(), info)
+        assert grp.info()["graph_mode"] == use_graph
+    ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
+               normal_current=g["normal_current"])
+    d = orc.compare(dict(psi=psi, mu=mu, supercurrent=js, normal_current=jn), ref, c.mesh.areas)
+    print("film20_fixed on", world, "shards:", d)
+    for k, v in d.items():
+        assert v < 1e-8, (k, d)
+    np.testing.assert_allclose(dt, g["dt"], rtol=1e-12)
+    # probe traces: gauge-invariant combination (voltage between the two probes)
+    v_ref = g["running_mu"][0] - g["running_mu"][1]
+    np.testing.assert_allclose(mu_p[0] - mu_p[1], v_ref, atol=1e-8 * np.abs(v_ref).max())
+
+
+def test_sharded_transport_matches_reference():
+    """Terminals (fixed sites, boundary currents), holes, adaptive dt with retries, probes —
+    on 3 shards; parity on the smooth window (see test_gpu_parity.test_transport_trajectory)."""
+    c = load_case("strip_transport")
+    g = c.g
+    n = len(c.mesh.sites)
+    with _group(c, 3, running_capacity=150) as grp:
+        grp.set_stepper(**_stepper(c))
+        psi0 = np.ones(n, complex)
+        fixed = np.concatenate([np.asarray(t.site_indices) for t in c.terminals])
+        psi0[fixed] = 0.0
+        grp.set_state(psi0, np.zeros(n))
+        mub = np.zeros(len(c.mesh.edge_mesh.boundary_edge_indices))
+        names = [t.name for t in c.terminals]
+        for t in c.terminals:
+            dens = (-1 / t.length) * sum(c.currents[m] for m in names if m != t.name)
+            mub[np.asarray(t.boundary_edge_indices)] = dens
+        grp.set_mu_boundary(mub)
+        info = grp.advance(150, 1e300, 0, 0.0)
+        psi, mu = grp.get_state()
+        dt = grp.get_running(150)[0]
+    k = list(g["snap_steps"]).index(150)
+    d = orc.compare(dict(psi=psi, mu=mu), dict(psi=g["snap_psi"][k], mu=g["snap_mu"][k]),
+                    c.mesh.areas)
+    print("strip_transport on 3 shards, step 150:", d, info)
+    assert d["psi"] < 1e-8 and d["mu"] < 1e-8, d
+    np.testing.assert_allclose(dt, g["dt"][:150], rtol=1e-8)
+    assert np.abs(psi[fixed]).max() == 0.0
+
+
+def test_sharded_large_mesh_against_single_engine():
+    """250k sites on 4 shards against the single-shard engine: identical step bookkeeping,
+    psi / mu within 1e-9 after 30 adaptive steps (summation orders differ)."""
+    from tdgl_b200.engine import DeviceEngine
+    from tdgl_b200.sharded import LocalShardGroup
+    from tdgl_b200.synthetic import film_problem
+
+    mesh, A, eps, _ = film_problem(200, 200, 0.43, b=0.1)
+    n = len(mesh.sites)
+    st = dict(dt_init=1e-4, dt_max=1e-1)
+
+    def run(e):
+        e.set_link_exponents(A)
+        e.set_epsilon(eps)
+        e.set_stepper(**st)
+        e.set_state(np.ones(n, complex), np.zeros(n))
+        info = e.advance(30, 1e300, 0, 0.0)
+        return info, e.get_state(), e.get_currents(), e.get_running(30)[0]
+
+    with DeviceEngine(mesh, running_capacity=64) as e1:
+        i1, (p1, m1), (js1, jn1), dt1 = run(e1)
+    with LocalShardGroup(mesh, 4, devices=_devices(4), running_capacity=64) as grp:
+        i4, (p4, m4), (js4, jn4), dt4 = run(grp)
+        print("250k on 4 shards:", grp.shard_info())
+    assert (i1.step, i1.retries) == (i4.step, i4.retries)
+    np.testing.assert_allclose(dt4, dt1, rtol=1e-10)
+    d = orc.compare(dict(psi=p4, mu=m4, supercurrent=js4, normal_current=jn4),
+                    dict(psi=p1, mu=m1, supercurrent=js1, normal_current=jn1), mesh.areas)
+    print("250k, 4 shards vs 1:", d, "iterations", i1.mu_iterations, i4.mu_iterations)
+    for k, v in d.items():
+        assert v < 1e-8, (k, d)
+    assert abs(i4.mu_iterations - i1.mu_iterations) <= 0.1 * i1.mu_iterations + 5
+
+
+def test_one_process_per_gpu_torchrun():
+    """torchrun, NCCL for the plumbing, CUDA IPC for the peer arenas (needs >= 2 GPUs)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tools", "dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "DIST_OK" in res.stdout
