@@ -23,9 +23,10 @@ b200 arm
           box's host cores (N=1 only; bounded number of steps of the same workload).
 reference arm (--impl reference): that CPU path alone, same workload/metric.
 
-With N > 1 ranks (torchrun) every rank steps a full replica of the workload on its own GPU
-(no data-path collective; "scaling": "weak") — domain decomposition across GPUs is the
-next row of the scope table.
+With N > 1 ranks (torchrun) the workload's mesh is domain-decomposed over the N GPUs
+(--mode shard, default: one shard per rank, halo exchange + all-reduces as device code over
+NVLink peer memory, "scaling": "strong": the same mesh, N times the hardware), or every rank
+steps a full replica (--mode replicas, "scaling": "weak", no data-path exchange).
 """
 from __future__ import annotations
 
@@ -56,6 +57,17 @@ WORKLOADS = {
     "film250k_field": dict(
         width=200.0, height=200.0, h=0.43, b=0.1, holes=(), terminals=False, current=0.0,
         opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    # BASELINE.json configs[3]: long strip with transport current (4 GPUs)
+    "strip4m_transport": dict(
+        width=3200.0, height=200.0, h=0.4225, b=0.0, holes=(), terminals=True, current=40.0,
+        opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    # BASELINE.json configs[4]: 10M-site film in a field (strong scaling at 1/2/4/8 GPUs)
+    "film10m_field": dict(
+        width=1265.0, height=1265.0, h=0.4225, b=0.1, holes=(), terminals=False, current=0.0,
+        opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    "film4m_field": dict(
+        width=800.0, height=800.0, h=0.4225, b=0.1, holes=(), terminals=False, current=0.0,
+        opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
     # BASELINE.json configs[0] geometry (perturbed so that every term is active)
     "film20_cpu": dict(
         width=20.0, height=20.0, h=0.29, b=0.3, holes=(), terminals=False, current=0.0,
@@ -63,14 +75,60 @@ WORKLOADS = {
 }
 
 
-def build_workload(name: str):
-    from tdgl_b200.synthetic import film_problem
+def _mesh_to_arrays(mesh):
+    em = mesh.edge_mesh
+    return dict(sites=mesh.sites, elements=mesh.elements, boundary_indices=mesh.boundary_indices,
+                areas=mesh.areas, centers=em.centers, edges=em.edges,
+                boundary_edge_indices=em.boundary_edge_indices, directions=em.directions,
+                edge_lengths=em.edge_lengths, dual_edge_lengths=em.dual_edge_lengths)
+
+
+def _mesh_from_arrays(g):
+    from tdgl_b200.mesh import EdgeMesh, Mesh
+
+    em = EdgeMesh(g["centers"], g["edges"], g["boundary_edge_indices"], g["directions"],
+                  g["edge_lengths"], g["dual_edge_lengths"])
+    return Mesh(g["sites"], g["elements"], g["boundary_indices"], areas=g["areas"], edge_mesh=em)
+
+
+def build_workload(name: str, rank: int = 0, barrier=None):
+    """Synthetic mesh + inputs.  With several ranks, rank 0 builds the mesh once and the
+    others read it from /dev/shm (the Delaunay triangulation is the slow, single-threaded
+    part of the setup and is not what is measured)."""
+    from tdgl_b200.synthetic import box_terminal, gaussian_disorder, film_problem, \
+        uniform_field_vector_potential
 
     w = WORKLOADS[name]
     t0 = time.perf_counter()
-    mesh, A, eps, terms = film_problem(w["width"], w["height"], w["h"], b=w["b"],
-                                       holes=w["holes"], terminals=w["terminals"],
-                                       disorder=w.get("disorder", False))
+    if barrier is None:
+        mesh, A, eps, terms = film_problem(w["width"], w["height"], w["h"], b=w["b"],
+                                           holes=w["holes"], terminals=w["terminals"],
+                                           disorder=w.get("disorder", False))
+    else:
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        path = os.path.join(shm, f"tdgl_b200_{name}_{os.environ.get('MASTER_PORT', '0')}.npz")
+        if rank == 0:
+            mesh = film_problem(w["width"], w["height"], w["h"], b=w["b"], holes=w["holes"],
+                                terminals=False)[0]
+            np.savez(path + ".tmp.npz", **_mesh_to_arrays(mesh))
+            os.replace(path + ".tmp.npz", path)
+        barrier()
+        if rank != 0:
+            with np.load(path) as g:
+                mesh = _mesh_from_arrays({k: g[k] for k in g.files})
+        barrier()
+        if rank == 0:
+            os.remove(path)
+        A = uniform_field_vector_potential(mesh.edge_mesh.centers, w["b"])
+        eps = (gaussian_disorder(mesh.sites) if w.get("disorder", False)
+               else np.ones(len(mesh.sites)))
+        terms = ()
+        if w["terminals"]:
+            tol = 1e-9 * max(w["width"], w["height"])
+            x0, x1, big = -w["width"] / 2, w["width"] / 2, 10 * max(w["width"], w["height"])
+            terms = tuple(sorted((box_terminal(mesh, "source", x0 - tol, x0 + tol, -big, big),
+                                  box_terminal(mesh, "drain", x1 - tol, x1 + tol, -big, big)),
+                                 key=lambda t: t.length))
     currents = None
     if w["terminals"]:
         currents = {"source": w["current"], "drain": -w["current"]}
@@ -238,12 +296,13 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    work = build_workload(args.workload)
+    shard = world > 1 and args.mode == "shard"
+    work = build_workload(args.workload, rank, barrier if world > 1 else None)
     mesh = work["mesh"]
     n, n_edges = len(mesh.sites), len(mesh.edge_mesh.edges)
     K, W = args.steps, args.warmup
     opts = SolverOptions(solve_time=1e9, save_every=max(K, W, 1), cuda_device=local_rank,
-                         use_cuda_graph=not args.no_graph, **work["opts"])
+                         use_cuda_graph=not args.no_graph, distributed=shard, **work["opts"])
     t0 = time.perf_counter()
     solver = TDGLSolver.from_dimensionless(
         mesh, opts, A_applied=work["A"], epsilon=work["eps"], terminal_info=work["terms"],
@@ -269,8 +328,10 @@ def run_b200(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    steps_per_s = world * K / (ms_total / 1e3)
+    jobs = 1 if shard else world          # a sharded job advances ONE mesh, replicas advance N
+    steps_per_s = jobs * K / (ms_total / 1e3)
     iters_per_step = b.mu_iterations / K
+    sh = eng.shard_info() if shard else None
 
     # ---- end to end through the reference's step seam --------------------------------------
     psi_h = pinned_empty(n, np.complex128)
@@ -297,9 +358,9 @@ def run_b200(args, rank, world, local_rank):
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_steps_per_s = world * Ke / float(e2e_t.item())
-    h2d = 24 * n                     # psi (16 B) + mu (8 B) per site
-    d2h = 24 * n + 16 * n_edges      # psi', mu' + J_s, J_n per edge
+    e2e_steps_per_s = jobs * Ke / float(e2e_t.item())
+    h2d = 24 * n                     # psi (16 B) + mu (8 B) per site (per rank)
+    d2h = 24 * n + 16 * n_edges      # psi', mu' + J_s, J_n per edge (per rank)
 
     if rank != 0:
         if dist is not None:
@@ -308,16 +369,17 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- per-kernel roofline (rank 0, kernels timed alone after an L2 flush) ---------------
     peak, peak_src = hbm_peak()
-    nnz = info0["nnz"]
+    nnz = info0["nnz"]                      # of this rank's rows
+    nl = sh["n_owned"] if shard else n      # rows this rank's kernels process
     levels = info0["amg_levels"]
     kern = {
-        "kw_psi_step": (0, 20 * nnz + 52 * n, 1.0),
-        "kw_mu_rhs": (1, 28 * nnz + 60 * n, 1.0),
-        "kw_real<spmv_dot> fine level": (2, 12 * nnz + 20 * n, iters_per_step),
+        "kw_psi_step": (0, 20 * nnz + 52 * nl, 1.0),
+        "kw_mu_rhs": (1, 28 * nnz + 60 * nl, 1.0),
+        "kw_real<spmv_dot> fine level": (2, 12 * nnz + 20 * nl, iters_per_step),
     }
     if levels > 1:
-        kern["kw_real<presmooth> fine level"] = (5, 12 * nnz + 36 * n, iters_per_step)
-        kern["kw_real<jacobi> fine level"] = (6, 12 * nnz + 44 * n, iters_per_step)
+        kern["kw_real<presmooth> fine level"] = (5, 12 * nnz + 36 * nl, iters_per_step)
+        kern["kw_real<jacobi> fine level"] = (6, 12 * nnz + 44 * nl, iters_per_step)
     table = {}
     for name, (which, nbytes, per_step) in kern.items():
         kms = eng.time_kernel(which, 20, flush_l2=True)
@@ -333,10 +395,15 @@ def run_b200(args, rank, world, local_rank):
     line = {
         "metric": "tdgl_steps_per_sec", "value": steps_per_s, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "sites": n, "edges": n_edges, "nnz": nnz,
-                   "parallelism": "single GPU" if world == 1 else f"{world} replicas",
+        "higher_is_better": True, "scaling": "strong" if shard else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "sites": n, "edges": n_edges,
+                   "nnz_rank0": nnz,
+                   "parallelism": ("single GPU" if world == 1 else
+                                   f"domain decomposition over {world} GPUs (Z-order ranges,"
+                                   " halo exchange + all-reduce kernels on NVLink peer memory)"
+                                   if shard else f"{world} replicas"),
+                   "shard_rank0": sh,
                    "l2": "operators (>= 230 MB at 1M sites) exceed the 126 MB L2; per-kernel"
                          " roofline timings flush L2 before every launch",
                    "mu_rtol": opts.mu_rtol, "amg_levels": levels},
@@ -373,6 +440,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=60.0,
                     help="seconds of CPU stepping allowed for the cpu baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+                    help="N > 1: domain-decompose the mesh over the ranks (default) or run one"
+                         " replica of the workload per rank")
     ap.add_argument("--no-graph", action="store_true",
                     help="host-driven launches instead of the device-side-loop CUDA graph"
                          " (profiler runs: every kernel is an ordinary launch)")
