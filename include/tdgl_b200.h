@@ -56,6 +56,9 @@ typedef struct tdgl_config {
   int32_t running_capacity; /* steps of running state kept per advance() [4096] */
   int32_t world;            /* number of shards the mesh is decomposed into, 1..8 [1] */
   int32_t rank;             /* the shard this handle computes, 0..world-1 [0] */
+  int32_t replicate_below;  /* sharded: AMG levels with at most this many rows are computed
+                               redundantly by every shard instead of exchanged [32768] */
+  int32_t reserved;
 } tdgl_config;
 
 /* Mesh + material -> device-resident operators.  Replaces MeshOperators.__init__ +
@@ -222,15 +225,16 @@ int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
 
 /* Builds the domain decomposition of a mesh for `world` shards exactly as the sharded engine
  * does and validates it on the host: per-level ownership offsets (level_off[32][9]), halo
- * sizes (halo_sizes[32][8]), the Z-order permutation (site_owner_perm[n_sites]: position
+ * sizes (halo_sizes[32][8]; level_off[31][0] holds the first replicated level), the Z-order permutation (site_owner_perm[n_sites]: position
  * in the ordering -> caller site), and, if rhs/x are given, the sharded AMG-PCG with all
  * shards emulated in this process (same local operators, same exchange lists). */
 int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
                           const double* edge_lengths, const double* dual_edge_lengths,
                           const double* sites_xy, int32_t world, double theta,
-                          int32_t max_coarse, int32_t* n_levels, int64_t* level_off,
-                          int64_t* halo_sizes, int64_t* site_owner_perm, const double* rhs,
-                          double* x, int32_t max_iter, double rtol, int32_t* iterations);
+                          int32_t max_coarse, int64_t replicate_below, int32_t* n_levels,
+                          int64_t* level_off, int64_t* halo_sizes, int64_t* site_owner_perm,
+                          const double* rhs, double* x, int32_t max_iter, double rtol,
+                          int32_t* iterations);
 
 /* Level-0 exchange lists of one shard in the caller's site numbering: owned sites, halo
  * sites, and per peer the owned sites sent to it (send_ptr[world+1] ranges into send_sites,

@@ -35,6 +35,8 @@ class tdgl_config(C.Structure):
         ("running_capacity", C.c_int32),
         ("world", C.c_int32),
         ("rank", C.c_int32),
+        ("replicate_below", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -92,7 +94,7 @@ SIGNATURES = {
     "tdgl_comm_connect_ipc": (C.c_int, [_P, _P, _I32]),
     "tdgl_comm_connect_local": (C.c_int, [_P, C.POINTER(_P), _I32]),
     "tdgl_shard_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
-    "tdgl_host_shard_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _D, _I32,
+    "tdgl_host_shard_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _D, _I32, _I64,
                                         C.POINTER(_I32), _P, _P, _P, _P, _P, _I32, _D,
                                         C.POINTER(_I32)]),
     "tdgl_host_shard_lists": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P,

@@ -240,11 +240,10 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
     const double bs = block_sum(d, red);
     double total;
-    if (grid_sum_last(bs, partials, counter, red, &total)) {
-      if (threadIdx.x == 0) {
-        if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
-        *a.red_out = total;
-      }
+    if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
+      total = __shfl_sync(0xffffffffu, total, 0);
+      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+      if (threadIdx.x == 0) *a.red_out = total;
     }
   }
 }
@@ -385,16 +384,18 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
     }
     a0 = block_sum(a0, red);
     a1 = block_sum(a1, red);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0
       if (comm != nullptr) {
         double v[2] = {a0, a1};
         comm_allreduce(ctl, comm, v, 2, false);
         a0 = v[0];
         a1 = v[1];
       }
-      ctl->bb = a0;
-      ctl->rr = a1;
-      *counter = 0u;
+      if (threadIdx.x == 0) {
+        ctl->bb = a0;
+        ctl->rr = a1;
+        *counter = 0u;
+      }
     }
   }
 }

@@ -92,9 +92,9 @@ struct DevLevel {
   DevBuf<double> dinv;  // nx entries (the halo part is static, filled at setup)
   double omega = 0.0;   // Jacobi weight (4/3) / rho(D^-1 A)
   DevBuf<double> b, x, y, r;  // work vectors in the arena (level 0 uses the CG vectors for b / y)
-  // halo exchange of this level (sharded engine)
+  // halo exchange of this level (sharded engine, partitioned / gathered levels only)
   DevBuf<int> send_idx;
-  ExchArgs ex_x, ex_r, ex_b, ex_y;
+  ExchArgs ex;
 };
 
 // Largest aligned nnz extent of any window of `win` rows (shared-memory elements a CTA
@@ -134,6 +134,7 @@ struct Config {
   int running_capacity = 4096;
   int world = 1;   // number of shards (one GPU / process each, or several per process)
   int rank = 0;    // this engine's shard
+  int replicate_below = 0;  // AMG levels with at most this many rows are replicated (0: 32768)
 };
 
 class Engine {
@@ -196,8 +197,7 @@ class Engine {
   DevBuf<double> arena_;
   DevBuf<Comm> comm_;
   std::vector<void*> ipc_opened_;
-  ExchArgs ex_psi_[2], ex_mu_, ex_cg_r_, ex_cg_p_;
-  int nc_own_ = 0;              // coarsest-level rows owned by this shard
+
   int64_t nnz_ = 0;
   double gamma_, u_, total_area_ = 0.0;
   std::vector<int> perm_;      // internal index -> caller index
@@ -263,15 +263,15 @@ class Engine {
   void launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
                      const double* x, double* y, const double* w, double* dot_out);
   void launch_residual(const CsrView& A, const double* x, const double* b, double* r, double* rr);
-  void enqueue_vcycle(const double* r_in, double* z_out, double* rz_out);
+  void enqueue_vcycle(double* r_in, double* z_out, double* rz_out);
   void enqueue_psi_step(double* sq_out, double dt_override);
   void enqueue_mu_rhs(double* rhs_raw);
   void enqueue_cg_iteration(cudaGraphConditionalHandle cond);
   void enqueue_mu_finish();
   void host_solve_loop();   // host-driven CG loop on the current b/r
   Comm* comm() const { return comm_on_ ? comm_.p : nullptr; }
-  ExchArgs make_exch(int level, int vec, int elem_doubles, const int* send_idx_dev) const;
-  void enqueue_exchange(const ExchArgs& a, const double* src);
+  ExchArgs make_exch(int level, const int* send_idx_dev) const;
+  void enqueue_exchange(int level, double* vec);
   void enqueue_exchange_psi();
   void upload_comm(double* const* peers);
   void configure_kernels();

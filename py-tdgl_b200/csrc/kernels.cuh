@@ -175,9 +175,10 @@ k_cg_update(Ctl* ctl, Comm* comm, int n, const double* __restrict__ p,
   }
   const double bs = block_sum(d, red);
   double total;
-  if (grid_sum_last(bs, partials, counter, red, &total)) {
+  if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
+    total = __shfl_sync(0xffffffffu, total, 0);
+    if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
     if (threadIdx.x == 0) {
-      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       ctl->rr = total;
       ctl->rz_prev = ctl->rz_new;
       const int it = ctl->cg_it + 1;
@@ -272,16 +273,19 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
 
 // adaptive_euler_step's retry logic (solver.py:475-485)
 __global__ void k_psi_control(Ctl* ctl, Comm* comm, cudaGraphConditionalHandle cond_psi) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   int go = 0;
-  if (ctl->status == 0 && comm != nullptr) {
+  if (comm != nullptr && ctl->status == 0) {  // one full warp (launched with 32 threads)
     // any(disc < 0) and max |d psi^2| over all shards
     double v[2] = {ctl->disc_flag ? 1.0 : 0.0,
                    __longlong_as_double(static_cast<long long>(ctl->max_dpsi_bits))};
     comm_allreduce(ctl, comm, v, 2, true);
-    ctl->disc_flag = v[0] > 0.0 ? 1 : 0;
-    ctl->max_dpsi_bits = static_cast<unsigned long long>(__double_as_longlong(v[1]));
+    if (threadIdx.x == 0) {
+      ctl->disc_flag = v[0] > 0.0 ? 1 : 0;
+      ctl->max_dpsi_bits = static_cast<unsigned long long>(__double_as_longlong(v[1]));
+    }
   }
+  if (threadIdx.x != 0) return;
   if (ctl->status == 0) {
     if (ctl->disc_flag) {
       if (!ctl->adaptive || ctl->retries > ctl->max_retries) {
@@ -316,11 +320,10 @@ k_weighted_sum(Ctl* ctl, Comm* comm, int n, const double* __restrict__ w,
     d += w[i] * x[i];
   const double bs = block_sum(d, red);
   double total;
-  if (grid_sum_last(bs, partials, counter, red, &total)) {
-    if (threadIdx.x == 0) {
-      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
-      ctl->mu_mean = total * inv_total_weight;
-    }
+  if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
+    total = __shfl_sync(0xffffffffu, total, 0);
+    if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+    if (threadIdx.x == 0) ctl->mu_mean = total * inv_total_weight;
   }
 }
 
@@ -489,11 +492,10 @@ k_dot(Ctl* ctl, Comm* comm, int n, const double* __restrict__ a, const double* _
     d += a[i] * b[i];
   const double bs = block_sum(d, red);
   double total;
-  if (grid_sum_last(bs, partials, counter, red, &total)) {
-    if (threadIdx.x == 0) {
-      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
-      *out = total;
-    }
+  if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
+    total = __shfl_sync(0xffffffffu, total, 0);
+    if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+    if (threadIdx.x == 0) *out = total;
   }
 }
 

@@ -20,20 +20,40 @@ constexpr int kMaxWorld = 8;
 struct ShardPlan {
   int world = 1;
   int levels = 0;
+  // First replicated level.  Levels l < rep are partitioned (a rank computes its owned rows,
+  // vectors are [owned | halo]); on level rep every rank holds the whole vector, laid out
+  // [owned | all others], computes ALL rows redundantly and only the restriction into it is
+  // partitioned (followed by an all-gather); levels l > rep are plain replicas in the global
+  // numbering.  The coarse levels are tiny (<= kReplicateBelow rows): recomputing them on
+  // every GPU costs nothing and removes four exchanges per level from every V-cycle.
+  int rep = 0;
   std::vector<std::vector<int64_t>> off;                 // [level][world + 1]
   std::vector<std::vector<std::vector<int32_t>>> halo;   // [level][rank] sorted global ids
 
-  int64_t owned(int l, int r) const { return off[l][r + 1] - off[l][r]; }
-  int64_t local_size(int l, int r) const { return owned(l, r) + static_cast<int64_t>(halo[l][r].size()); }
+  int64_t rows(int l) const { return off[l][world]; }
+  int64_t owned(int l, int r) const { return l > rep ? rows(l) : off[l][r + 1] - off[l][r]; }
+  int64_t local_size(int l, int r) const {
+    return l > rep ? rows(l) : off[l][r + 1] - off[l][r] + static_cast<int64_t>(halo[l][r].size());
+  }
+  // rows rank r computes on level l
+  int64_t compute_rows(int l, int r) const { return l < rep ? owned(l, r) : local_size(l, r); }
   // position of global id g in rank r's local numbering of level l (-1: not present)
   int64_t local_index(int l, int r, int64_t g) const {
+    if (l > rep) return g;
     if (g >= off[l][r] && g < off[l][r + 1]) return g - off[l][r];
     const auto& h = halo[l][r];
     auto it = std::lower_bound(h.begin(), h.end(), static_cast<int32_t>(g));
     if (it == h.end() || *it != g) return -1;
-    return owned(l, r) + (it - h.begin());
+    return (off[l][r + 1] - off[l][r]) + (it - h.begin());
+  }
+  int64_t global_index(int l, int r, int64_t k) const {
+    if (l > rep) return k;
+    const int64_t n = off[l][r + 1] - off[l][r];
+    return k < n ? off[l][r] + k : halo[l][r][k - n];
   }
 };
+
+constexpr int64_t kReplicateBelow = 32768;
 
 // Equal split of n rows over `world` ranks.
 inline std::vector<int64_t> equal_offsets(int64_t n, int world) {
@@ -58,19 +78,23 @@ inline void collect_halo(const HostCsr<double>& G, const std::vector<int64_t>& r
   }
 }
 
-inline ShardPlan make_plan(const AmgHierarchy& H) {
+inline ShardPlan make_plan(const AmgHierarchy& H, int64_t replicate_below = kReplicateBelow) {
   ShardPlan p;
   p.levels = static_cast<int>(H.levels.size());
   p.off = H.off;
   p.world = static_cast<int>(H.off[0].size()) - 1;
   p.halo.assign(p.levels, std::vector<std::vector<int32_t>>(p.world));
+  p.rep = 0;
   if (p.world == 1) return p;
   if (p.world > kMaxWorld) throw std::invalid_argument("at most 8 ranks");
   if (p.levels < 2) throw std::invalid_argument("mesh too small to shard (single-level hierarchy)");
-  for (int l = 0; l < p.levels; ++l) {
+  p.rep = p.levels - 1;
+  for (int l = 1; l < p.levels; ++l)
+    if (H.levels[l].A.rows <= replicate_below) { p.rep = l; break; }
+  for (int l = 0; l <= p.rep; ++l) {
     const AmgLevel& lv = H.levels[l];
-    if (l == p.levels - 1) {
-      // coarsest level: solved redundantly from the gathered right-hand side
+    if (l == p.rep) {
+      // gathered level: every other rank's rows are "halo"
       const int64_t n = lv.A.rows;
       for (int r = 0; r < p.world; ++r)
         for (int64_t g = 0; g < n; ++g)
@@ -86,28 +110,46 @@ inline ShardPlan make_plan(const AmgHierarchy& H) {
       h.erase(std::unique(h.begin(), h.end()), h.end());
     }
   }
-  // the coarsest level is also read by the prolongation of the level above: already "all"
   return p;
+}
+
+// The global rows rank `rank` computes on level l, in its local order.
+inline std::vector<int64_t> compute_row_list(const ShardPlan& plan, int l, int rank) {
+  std::vector<int64_t> rows(plan.compute_rows(l, rank));
+  for (size_t k = 0; k < rows.size(); ++k) rows[k] = plan.global_index(l, rank, static_cast<int64_t>(k));
+  return rows;
+}
+
+// The given global rows of G (in that order), columns renumbered into rank `rank`'s local
+// layout of the column level `cl`.
+inline HostCsr<double> extract_rows(const HostCsr<double>& G, const std::vector<int64_t>& rows,
+                                    const ShardPlan& plan, int cl, int rank) {
+  HostCsr<double> L;
+  L.rows = static_cast<int64_t>(rows.size());
+  L.cols = plan.local_size(cl, rank);
+  L.ptr.assign(L.rows + 1, 0);
+  for (int64_t i = 0; i < L.rows; ++i) L.ptr[i + 1] = L.ptr[i] + (G.ptr[rows[i] + 1] - G.ptr[rows[i]]);
+  L.idx.resize(L.ptr[L.rows]);
+  L.val.resize(L.ptr[L.rows]);
+  for (int64_t i = 0; i < L.rows; ++i) {
+    int32_t d = L.ptr[i];
+    for (int32_t k = G.ptr[rows[i]]; k < G.ptr[rows[i] + 1]; ++k, ++d) {
+      const int64_t li = plan.local_index(cl, rank, G.idx[k]);
+      if (li < 0) throw std::runtime_error("halo plan misses a column");
+      L.idx[d] = static_cast<int32_t>(li);
+      L.val[d] = G.val[k];
+    }
+  }
+  return L;
 }
 
 // Rows r0..r1 of G with columns renumbered into rank `rank`'s local layout of the column
 // level `cl`.  Column order inside a row is kept (the kernels do not need sorted rows).
 inline HostCsr<double> extract_local(const HostCsr<double>& G, int64_t r0, int64_t r1,
                                      const ShardPlan& plan, int cl, int rank) {
-  HostCsr<double> L;
-  L.rows = r1 - r0;
-  L.cols = plan.local_size(cl, rank);
-  L.ptr.resize(L.rows + 1);
-  const int32_t base = G.ptr[r0];
-  L.idx.resize(G.ptr[r1] - base);
-  L.val.assign(G.val.begin() + base, G.val.begin() + G.ptr[r1]);
-  for (int64_t i = r0; i <= r1; ++i) L.ptr[i - r0] = G.ptr[i] - base;
-  for (int32_t k = base; k < G.ptr[r1]; ++k) {
-    const int64_t li = plan.local_index(cl, rank, G.idx[k]);
-    if (li < 0) throw std::runtime_error("halo plan misses a column");
-    L.idx[k - base] = static_cast<int32_t>(li);
-  }
-  return L;
+  std::vector<int64_t> rows(r1 - r0);
+  for (int64_t i = r0; i < r1; ++i) rows[i - r0] = i;
+  return extract_rows(G, rows, plan, cl, rank);
 }
 
 // What `rank` sends to `peer` on level l: local (owned) indices, in the order in which they
@@ -120,6 +162,7 @@ struct SendBlock {
 
 inline std::vector<SendBlock> send_blocks(const ShardPlan& plan, int l, int rank) {
   std::vector<SendBlock> out;
+  if (l > plan.rep) return out;
   const int64_t g0 = plan.off[l][rank], g1 = plan.off[l][rank + 1];
   for (int q = 0; q < plan.world; ++q) {
     if (q == rank) continue;
@@ -140,6 +183,7 @@ inline std::vector<SendBlock> send_blocks(const ShardPlan& plan, int l, int rank
 // Ranks that send to `rank` on level l (the flags it waits for).
 inline std::vector<int> recv_peers(const ShardPlan& plan, int l, int rank) {
   std::vector<int> out;
+  if (l > plan.rep) return out;
   const auto& h = plan.halo[l][rank];
   for (int q = 0; q < plan.world; ++q) {
     if (q == rank) continue;
@@ -151,34 +195,50 @@ inline std::vector<int> recv_peers(const ShardPlan& plan, int l, int rank) {
 }
 
 // ---- arena layout -------------------------------------------------------------------------
-// Every vector that carries a halo lives in ONE device allocation per rank (the arena), so
-// that one CUDA IPC handle per rank makes all of them addressable by the peers.  The layout
-// is a pure function of the plan, hence every rank can compute every peer's offsets.
-//   header (doubles): [0,8) halo flags  [8,16) reduction flags  [16,80) reduction slots
-//                     [2 parities][8 ranks][4 values]
-//   vectors: psi0, psi1 (complex: 2 doubles per entry), mu, cg_r, cg_p, then per level
-//            x, r, b, y; each start aligned to 32 doubles.
-constexpr int64_t kArenaHaloFlag = 0, kArenaRedFlag = 8, kArenaRedSlot = 16, kArenaHeader = 128;
+// Everything a peer writes into lives in ONE device allocation per rank (the arena), so that
+// one CUDA IPC handle per rank makes it addressable.  The layout is a pure function of the
+// plan, hence every rank can compute every peer's offsets.  Units: 8-byte words.
+//   [0, kArenaHeader)   all-reduce mailbox: [2 parities][8 ranks][4 values][2 words]
+//   vectors             psi0, psi1 (complex: 2 words per entry), mu, cg_r, cg_p, then per
+//                       level x, r, b, y; each start aligned to 32 words
+//   halo mailboxes      per partitioned level: [2 parities][halo entries][kLLWords(level)]
+// Mailbox words use the "low latency" format of comm.cuh: 32 bits of payload + a 32-bit
+// sequence tag in one 8-byte store, so that a value and its arrival flag are one atomic
+// write and no fence / separate flag round trip is needed.
+constexpr int64_t kArenaRedBox = 0, kArenaHeader = 256;
 enum : int { kVecPsi0 = 0, kVecPsi1, kVecMu, kVecCgR, kVecCgP, kVecLevel0 };
 inline int vec_id(int level, int which /*0 x, 1 r, 2 b, 3 y*/) { return kVecLevel0 + 4 * level + which; }
+// mailbox words per halo entry: a double is 2 words; level 0 also carries psi (complex: 4)
+inline int ll_words(int level) { return level == 0 ? 4 : 2; }
 
 struct ArenaLayout {
-  std::vector<int64_t> off;  // per vector id, in doubles from the arena base
-  int64_t total = 0;         // doubles
+  std::vector<int64_t> off;     // per vector id, in words from the arena base
+  std::vector<int64_t> ll_off;  // per level: start of the halo mailbox (parity 0)
+  std::vector<int64_t> ll_cap;  // per level: words per parity
+  int64_t total = 0;            // words
 };
 
 inline ArenaLayout arena_layout(const ShardPlan& plan, int rank) {
   ArenaLayout a;
   int64_t pos = kArenaHeader;
-  auto add = [&](int64_t doubles) {
-    a.off.push_back(pos);
-    pos += (doubles + 31) / 32 * 32;
+  auto add = [&](int64_t words) {
+    const int64_t at = pos;
+    pos += (words + 31) / 32 * 32;
+    return at;
   };
   const int64_t nx0 = plan.local_size(0, rank);
-  add(2 * nx0); add(2 * nx0); add(nx0); add(nx0); add(nx0);
+  a.off.push_back(add(2 * nx0)); a.off.push_back(add(2 * nx0));
+  a.off.push_back(add(nx0)); a.off.push_back(add(nx0)); a.off.push_back(add(nx0));
   for (int l = 0; l < plan.levels; ++l) {
     const int64_t nx = plan.local_size(l, rank);
-    for (int w = 0; w < 4; ++w) add(nx);
+    for (int w = 0; w < 4; ++w) a.off.push_back(add(nx));
+  }
+  a.ll_off.assign(plan.levels, 0);
+  a.ll_cap.assign(plan.levels, 0);
+  for (int l = 0; l < plan.levels && l <= plan.rep && plan.world > 1; ++l) {
+    // payload words + one "present" word per rank (see ExchArgs in comm.cuh)
+    a.ll_cap[l] = static_cast<int64_t>(plan.halo[l][rank].size()) * ll_words(l) + kMaxWorld;
+    a.ll_off[l] = add(2 * a.ll_cap[l]);
   }
   a.total = pos;
   return a;

@@ -59,36 +59,49 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
 // ============================================================================================
 // construction
 
-ExchArgs Engine::make_exch(int level, int vec, int elem_doubles, const int* send_idx_dev) const {
+ExchArgs Engine::make_exch(int level, const int* send_idx_dev) const {
   ExchArgs a;
-  if (world_ == 1) return a;
+  if (world_ == 1 || level > plan_.rep) return a;
   const std::vector<SendBlock> blocks = send_blocks(plan_, level, rank_);
-  const std::vector<int> recv = recv_peers(plan_, level, rank_);
-  std::vector<int> peers(recv);
+  std::vector<int> peers = recv_peers(plan_, level, rank_);
   for (const SendBlock& b : blocks) peers.push_back(b.peer);
-  std::sort(peers.begin(), peers.end());
-  peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
-  // the relation must be symmetric (a rank that waits for me also signals me): make it so
+  // (send or receive) must be a symmetric relation: also list the ranks that list this one
   for (int q = 0; q < world_; ++q) {
-    if (q == rank_ || std::binary_search(peers.begin(), peers.end(), q)) continue;
+    if (q == rank_) continue;
     const std::vector<int> rq = recv_peers(plan_, level, q);
-    bool linked = std::find(rq.begin(), rq.end(), rank_) != rq.end();
-    for (const SendBlock& b : send_blocks(plan_, level, q)) linked = linked || b.peer == rank_;
-    if (linked) peers.push_back(q);
+    if (std::find(rq.begin(), rq.end(), rank_) != rq.end()) peers.push_back(q);
+    for (const SendBlock& b : send_blocks(plan_, level, q))
+      if (b.peer == rank_) peers.push_back(q);
   }
   std::sort(peers.begin(), peers.end());
+  peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+  a.level = level;
   a.nnbr = static_cast<int>(peers.size());
+  a.n_owned = static_cast<int>(plan_.off[level][rank_ + 1] - plan_.off[level][rank_]);
+  a.n_halo = static_cast<int>(plan_.halo[level][rank_].size());
   a.send_idx = send_idx_dev;
+  const int W = ll_words(level);
+  const ArenaLayout& mine = layouts_[rank_];
+  for (int par = 0; par < 2; ++par) {
+    a.box_word[par] = mine.ll_off[level] + par * mine.ll_cap[level];
+    a.box_ack[par] = a.box_word[par] + static_cast<long long>(a.n_halo) * W;
+  }
   int pos = 0;
   for (int j = 0; j < a.nnbr; ++j) {
     const int q = peers[j];
+    const ArenaLayout& lq = layouts_[q];
+    const long long q_halo = static_cast<long long>(plan_.halo[level][q].size());
     a.nbr[j] = q;
     a.send_begin[j] = pos;
-    a.dst_off[j] = 0;
+    for (int par = 0; par < 2; ++par) {
+      const long long base = lq.ll_off[level] + par * lq.ll_cap[level];
+      a.dst_word[par][j] = base;
+      a.ack_word[par][j] = base + q_halo * W + rank_;
+    }
     for (const SendBlock& b : blocks)
       if (b.peer == q) {
         pos += static_cast<int>(b.idx.size());
-        a.dst_off[j] = layouts_[q].off[vec] / elem_doubles + plan_.owned(level, q) + b.dst_pos;
+        for (int par = 0; par < 2; ++par) a.dst_word[par][j] += b.dst_pos * W;
       }
   }
   a.send_begin[a.nnbr] = pos;
@@ -177,7 +190,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   const std::vector<int64_t> off0 = equal_offsets(Ng_, world_);
   AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24, &off0);
   if (H.nc > 4096) throw std::runtime_error("AMG coarsening stalled (coarsest level too large)");
-  plan_ = make_plan(H);
+  plan_ = make_plan(H, cfg_.replicate_below > 0 ? cfg_.replicate_below : kReplicateBelow);
   layouts_.resize(world_);
   for (int q = 0; q < world_; ++q) layouts_[q] = arena_layout(plan_, q);
   const size_t L = H.levels.size();
@@ -309,33 +322,42 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   }
 
   // ---- hierarchy: this shard's rows of every level ---------------------------------------------
+  // Levels below plan_.rep are partitioned, level rep and coarser are computed redundantly by
+  // every shard (shard.h); for a single shard everything is "replicated" = the whole matrix.
   levels_.resize(L);
   amg_nnz_ = 0;
   int max_grid_rows = grid_win(N_, win0_);
+  const int rep_level = plan_.rep;
   for (size_t l = 0; l < L; ++l) {
     AmgLevel& hl = H.levels[l];
     DevLevel& dl = levels_[l];
     const int li = static_cast<int>(l);
-    const int64_t r0 = plan_.off[l][rank_], r1 = plan_.off[l][rank_ + 1];
-    dl.n = static_cast<int>(r1 - r0);
+    const std::vector<int64_t> rows = compute_row_list(plan_, li, rank_);
+    dl.n = static_cast<int>(rows.size());
     dl.nx = static_cast<int>(plan_.local_size(li, rank_));
-    amg_nnz_ += hl.A.ptr[r1] - hl.A.ptr[r0];
+    for (int64_t gr : rows) amg_nnz_ += hl.A.ptr[gr + 1] - hl.A.ptr[gr];
     if (l > 0) {
-      upload_csr(extract_local(hl.A, r0, r1, plan_, li, rank_), dl.A);
+      upload_csr(extract_rows(hl.A, rows, plan_, li, rank_), dl.A);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.A.rows, dl.A.win));
     }
     {
       std::vector<double> dloc(dl.nx);
-      for (int k = 0; k < dl.n; ++k) dloc[k] = hl.dinv[r0 + k];
-      for (int k = dl.n; k < dl.nx; ++k) dloc[k] = hl.dinv[plan_.halo[l][rank_][k - dl.n]];
+      for (int k = 0; k < dl.nx; ++k) dloc[k] = hl.dinv[plan_.global_index(li, rank_, k)];
       dl.dinv.upload(dloc, stream_);
       TDGL_CUDA(cudaStreamSynchronize(stream_));
     }
     dl.omega = (4.0 / 3.0) / hl.rho;
     if (l + 1 < L) {
-      const int64_t c0 = plan_.off[l + 1][rank_], c1 = plan_.off[l + 1][rank_ + 1];
-      upload_csr(extract_local(hl.P, r0, r1, plan_, li + 1, rank_), dl.P);
-      upload_csr(extract_local(hl.R, c0, c1, plan_, li, rank_), dl.R);
+      // restriction INTO level l+1: only the owned rows while that level is partitioned or
+      // gathered (l+1 <= rep), all rows below
+      std::vector<int64_t> rrows;
+      if (li + 1 <= rep_level && world_ > 1) {
+        for (int64_t gr = plan_.off[l + 1][rank_]; gr < plan_.off[l + 1][rank_ + 1]; ++gr) rrows.push_back(gr);
+      } else {
+        rrows = compute_row_list(plan_, li + 1, rank_);
+      }
+      upload_csr(extract_rows(hl.P, rows, plan_, li + 1, rank_), dl.P);
+      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.P.rows, dl.P.win));
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.R.rows, dl.R.win));
     }
@@ -343,38 +365,25 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     dl.r.view(arena_.p + lay.off[vec_id(li, 1)], dl.nx);
     dl.b.view(arena_.p + lay.off[vec_id(li, 2)], dl.nx);
     dl.y.view(arena_.p + lay.off[vec_id(li, 3)], dl.nx);
-    if (world_ > 1) {
+    if (world_ > 1 && li <= rep_level) {
       std::vector<int> sidx;
       for (const SendBlock& b : send_blocks(plan_, li, rank_)) sidx.insert(sidx.end(), b.idx.begin(), b.idx.end());
       if (sidx.empty()) sidx.push_back(0);
       dl.send_idx.upload(sidx, stream_);
       TDGL_CUDA(cudaStreamSynchronize(stream_));
-      dl.ex_x = make_exch(li, vec_id(li, 0), 1, dl.send_idx.p);
-      dl.ex_r = make_exch(li, vec_id(li, 1), 1, dl.send_idx.p);
-      dl.ex_b = make_exch(li, vec_id(li, 2), 1, dl.send_idx.p);
-      dl.ex_y = make_exch(li, vec_id(li, 3), 1, dl.send_idx.p);
+      dl.ex = make_exch(li, dl.send_idx.p);
     }
   }
-  if (world_ > 1) {
-    const int* s0 = levels_[0].send_idx.p;
-    ex_psi_[0] = make_exch(0, kVecPsi0, 2, s0);
-    ex_psi_[1] = make_exch(0, kVecPsi1, 2, s0);
-    ex_mu_ = make_exch(0, kVecMu, 1, s0);
-    ex_cg_r_ = make_exch(0, kVecCgR, 1, s0);
-    ex_cg_p_ = make_exch(0, kVecCgP, 1, s0);
-  }
   {
-    // coarsest level: this shard's rows of the dense inverse, columns in local order
+    // coarsest level: dense inverse with rows and columns in this shard's local order
     const int lc = static_cast<int>(L) - 1;
     nc_ = static_cast<int>(H.nc);
-    const int64_t r0 = plan_.off[lc][rank_], r1 = plan_.off[lc][rank_ + 1];
-    nc_own_ = static_cast<int>(r1 - r0);
-    std::vector<double> loc(static_cast<size_t>(std::max(nc_own_, 1)) * nc_, 0.0);
-    for (int i = 0; i < nc_own_; ++i)
-      for (int64_t gcol = 0; gcol < nc_; ++gcol) {
-        const int64_t lcidx = plan_.local_index(lc, rank_, gcol);
-        loc[static_cast<size_t>(i) * nc_ + lcidx] = H.coarse_inv[(r0 + i) * nc_ + gcol];
-      }
+    std::vector<double> loc(static_cast<size_t>(nc_) * nc_, 0.0);
+    for (int i = 0; i < nc_; ++i) {
+      const int64_t gi = plan_.global_index(lc, rank_, i);
+      for (int j = 0; j < nc_; ++j)
+        loc[static_cast<size_t>(i) * nc_ + j] = H.coarse_inv[gi * nc_ + plan_.global_index(lc, rank_, j)];
+    }
     coarse_inv_.upload(loc, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
@@ -438,7 +447,7 @@ void Engine::upload_comm(double* const* peers) {
   Comm c;
   c.rank = rank_;
   c.world = world_;
-  for (int q = 0; q < world_; ++q) c.peer[q] = peers[q];
+  for (int q = 0; q < world_; ++q) c.peer[q] = reinterpret_cast<unsigned long long*>(peers[q]);
   TDGL_CUDA(cudaMemcpyAsync(comm_.p, &c, sizeof(Comm), cudaMemcpyHostToDevice, stream_));
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -489,9 +498,10 @@ void Engine::comm_connect_local(Engine* const* engines) {
 void Engine::shard_info(int64_t* out, int n) {
   int64_t halo_total = 0, nbr0 = 0;
   for (int l = 0; l < plan_.levels; ++l) halo_total += static_cast<int64_t>(plan_.halo[l][rank_].size());
-  nbr0 = ex_mu_.nnbr;
+  const ExchArgs& e0 = levels_[0].ex;
+  nbr0 = e0.nnbr;
   const int64_t vals[8] = {world_, rank_, Ng_, N_, Nx_ - N_, halo_total, nbr0,
-                           static_cast<int64_t>(ex_mu_.send_begin[ex_mu_.nnbr])};
+                           static_cast<int64_t>(e0.send_begin[e0.nnbr])};
   for (int i = 0; i < n && i < 8; ++i) out[i] = vals[i];
 }
 
@@ -584,20 +594,19 @@ void Engine::launch_residual(const CsrView& A, const double* x, const double* b,
 
 // z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
 // smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
-void Engine::enqueue_exchange(const ExchArgs& a, const double* src) {
-  if (!comm_on_) return;
-  k_halo_exchange<double><<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, a, src);
+void Engine::enqueue_exchange(int level, double* vec) {
+  if (!comm_on_ || level > plan_.rep) return;
+  k_halo_exchange<double><<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, levels_[level].ex, vec);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_exchange_psi() {
   if (!comm_on_) return;
-  k_halo_exchange_psi<<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, ex_psi_[0], ex_psi_[1], psi_[0].p,
-                                              psi_[1].p);
+  k_halo_exchange_psi<<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, levels_[0].ex, psi_[0].p, psi_[1].p);
   TDGL_LAUNCH_CHECK();
 }
 
-void Engine::enqueue_vcycle(const double* r_in, double* z_out, double* rz_out) {
+void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   const size_t L = levels_.size();
   if (L == 1) {
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
@@ -607,32 +616,34 @@ void Engine::enqueue_vcycle(const double* r_in, double* z_out, double* rz_out) {
     TDGL_LAUNCH_CHECK();
     return;
   }
-  // Sharded: a vector is exchanged right before the kernel that gathers from it (r_in is
-  // the CG residual, whose halo slots live in the arena like every level vector's).
+  // Sharded: on a partitioned level (l < rep) a vector is exchanged right before the kernel
+  // that gathers from it; the right-hand side of level rep is all-gathered and everything
+  // from there down is computed redundantly by every shard (no exchange).
+  const int rep = comm_on_ ? plan_.rep : -1;
   for (size_t l = 0; l + 1 < L; ++l) {
     DevLevel& lv = levels_[l];
-    const double* b = (l == 0) ? r_in : lv.b.p;
-    enqueue_exchange(l == 0 ? ex_cg_r_ : lv.ex_b, b);
+    const int li = static_cast<int>(l);
+    double* b = (l == 0) ? r_in : lv.b.p;
+    if (li <= rep) enqueue_exchange(li, b);
     launch_presmooth(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, lv.r.p);
-    enqueue_exchange(lv.ex_r, lv.r.p);
+    if (li < rep) enqueue_exchange(li, lv.r.p);
     launch_plain(lv.R.view(), lv.r.p, levels_[l + 1].b.p, false);
   }
   {
     DevLevel& c = levels_[L - 1];
-    enqueue_exchange(c.ex_b, c.b.p);  // all-gather of the coarsest right-hand side
-    if (nc_own_ > 0) {
-      const int grid = (nc_own_ * 32 + kBlock - 1) / kBlock;
-      k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_own_, nc_, coarse_inv_.p, c.b.p, c.y.p);
-      TDGL_LAUNCH_CHECK();
-    }
+    if (static_cast<int>(L) - 1 <= rep) enqueue_exchange(static_cast<int>(L) - 1, c.b.p);
+    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
+    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, nc_, coarse_inv_.p, c.b.p, c.y.p);
+    TDGL_LAUNCH_CHECK();
   }
   for (size_t l = L - 1; l-- > 0;) {
     DevLevel& lv = levels_[l];
+    const int li = static_cast<int>(l);
     const double* b = (l == 0) ? r_in : lv.b.p;
     double* y = (l == 0) ? z_out : lv.y.p;
-    enqueue_exchange(levels_[l + 1].ex_y, levels_[l + 1].y.p);
+    if (li + 1 < rep) enqueue_exchange(li + 1, levels_[l + 1].y.p);
     launch_plain(lv.P.view(), levels_[l + 1].y.p, lv.x.p, true);
-    enqueue_exchange(lv.ex_x, lv.x.p);
+    if (li < rep) enqueue_exchange(li, lv.x.p);
     launch_jacobi(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, y, (l == 0) ? r_in : nullptr,
                   (l == 0) ? rz_out : nullptr);
   }
@@ -656,7 +667,7 @@ void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new);
   k_cg_direction<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, cg_z_.p, cg_p_.p);
   TDGL_LAUNCH_CHECK();
-  enqueue_exchange(ex_cg_p_, cg_p_.p);
+  enqueue_exchange(0, cg_p_.p);
   launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp);
   k_cg_update<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_p_.p, cg_Ap_.p, mu_.p,
                                                    cg_r_.p, partials_.p, counter_.p, cond);
@@ -671,7 +682,7 @@ void Engine::enqueue_mu_finish() {
   TDGL_LAUNCH_CHECK();
   k_shift<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, mu_.p);
   TDGL_LAUNCH_CHECK();
-  enqueue_exchange(ex_mu_, mu_.p);  // the next step's rhs / the edge currents read mu's halo
+  enqueue_exchange(0, mu_.p);  // the next step's rhs / the edge currents read mu's halo
 }
 
 void Engine::host_solve_loop() {
@@ -856,7 +867,8 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     sync_ctl_to_host();
     // the graph's kernels were launched by the device-side loops; account for them
     const int64_t L = static_cast<int64_t>(levels_.size());
-    const int64_t ex_step = world_ > 1 ? 2 : 0, ex_it = world_ > 1 ? (4 * L - 3) + 1 : 0;
+    const int64_t R = std::min<int64_t>(plan_.rep, L - 1);
+    const int64_t ex_step = world_ > 1 ? 2 : 0, ex_it = world_ > 1 ? 4 * R + 1 + 1 : 0;
     launches_ += h_ctl_->steps_done * (6 + ex_step) + h_ctl_->total_retries * 2 +
                  h_ctl_->total_cg_it * (3 + 4 * (L - 1) + 1 + ex_it);
   } else {
@@ -1261,6 +1273,7 @@ int tdgl_create(tdgl_handle** out, int64_t n_sites, int64_t n_edges, int64_t n_b
     if (config->reorder > 0) cfg.reorder = config->reorder;
     if (config->running_capacity > 0) cfg.running_capacity = config->running_capacity;
     if (config->world > 0) { cfg.world = config->world; cfg.rank = config->rank; }
+    if (config->replicate_below > 0) cfg.replicate_below = config->replicate_below;
   }
   auto h = std::make_unique<tdgl_handle>();
   try {
@@ -1531,9 +1544,10 @@ int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
 int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
                           const double* edge_lengths, const double* dual_edge_lengths,
                           const double* sites_xy, int32_t world, double theta,
-                          int32_t max_coarse, int32_t* n_levels, int64_t* level_off,
-                          int64_t* halo_sizes, int64_t* site_owner_perm, const double* rhs,
-                          double* x, int32_t max_iter, double rtol, int32_t* iterations) {
+                          int32_t max_coarse, int64_t replicate_below, int32_t* n_levels,
+                          int64_t* level_off, int64_t* halo_sizes, int64_t* site_owner_perm,
+                          const double* rhs, double* x, int32_t max_iter, double rtol,
+                          int32_t* iterations) {
   using namespace tdgl;
   try {
     if (sites_xy == nullptr) throw std::invalid_argument("site coordinates required");
@@ -1556,10 +1570,11 @@ int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges
     }
     const std::vector<int64_t> off0 = equal_offsets(n_sites, world);
     AmgHierarchy H = build_amg(std::move(A), theta > 0 ? theta : 0.08, max_coarse > 0 ? max_coarse : 200, 24, &off0);
-    ShardPlan plan = make_plan(H);
+    ShardPlan plan = make_plan(H, replicate_below > 0 ? replicate_below : kReplicateBelow);
     const int L = plan.levels, W = plan.world;
     if (n_levels) *n_levels = L;
-    for (int l = 0; l < L && l < 32; ++l)
+    if (level_off) level_off[31 * 9] = plan.rep;  // (last row of the table: first replicated level)
+    for (int l = 0; l < L && l < 31; ++l)
       for (int r = 0; r <= W; ++r) {
         if (level_off) level_off[l * 9 + r] = plan.off[l][r];
         if (halo_sizes && r < W) halo_sizes[l * 8 + r] = static_cast<int64_t>(plan.halo[l][r].size());
@@ -1567,37 +1582,42 @@ int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges
     if (site_owner_perm) for (int64_t i = 0; i < n_sites; ++i) site_owner_perm[i] = perm[i];
     if (rhs == nullptr || x == nullptr) return TDGL_OK;
 
-    // ---- local operators of every shard ---------------------------------------------------
+    // ---- local operators of every shard (the same extraction the device engine does) -------
     struct Shard { std::vector<HostCsr<double>> A, P, R; std::vector<std::vector<double>> dinv, b, x, r, y; };
     std::vector<Shard> S(W);
+    const int rep = plan.rep;
     for (int p = 0; p < W; ++p) {
       Shard& s = S[p];
       s.A.resize(L); s.P.resize(L); s.R.resize(L); s.dinv.resize(L); s.b.resize(L); s.x.resize(L); s.r.resize(L); s.y.resize(L);
       for (int l = 0; l < L; ++l) {
-        const int64_t r0 = plan.off[l][p], r1 = plan.off[l][p + 1];
+        const std::vector<int64_t> rows = compute_row_list(plan, l, p);
         const int64_t nx = plan.local_size(l, p);
-        s.A[l] = extract_local(H.levels[l].A, r0, r1, plan, l, p);
+        s.A[l] = extract_rows(H.levels[l].A, rows, plan, l, p);
         if (l + 1 < L) {
-          s.P[l] = extract_local(H.levels[l].P, r0, r1, plan, l + 1, p);
-          s.R[l] = extract_local(H.levels[l].R, plan.off[l + 1][p], plan.off[l + 1][p + 1], plan, l, p);
+          std::vector<int64_t> rrows;
+          if (l + 1 <= rep && W > 1) {
+            for (int64_t gr = plan.off[l + 1][p]; gr < plan.off[l + 1][p + 1]; ++gr) rrows.push_back(gr);
+          } else {
+            rrows = compute_row_list(plan, l + 1, p);
+          }
+          s.P[l] = extract_rows(H.levels[l].P, rows, plan, l + 1, p);
+          s.R[l] = extract_rows(H.levels[l].R, rrows, plan, l, p);
         }
         s.dinv[l].resize(nx);
-        for (int64_t k = 0; k < nx; ++k) {
-          const int64_t gi = k < r1 - r0 ? r0 + k : plan.halo[l][p][k - (r1 - r0)];
-          s.dinv[l][k] = H.levels[l].dinv[gi];
-        }
+        for (int64_t k = 0; k < nx; ++k) s.dinv[l][k] = H.levels[l].dinv[plan.global_index(l, p, k)];
         s.b[l].assign(nx, 0.0); s.x[l].assign(nx, 0.0); s.r[l].assign(nx, 0.0); s.y[l].assign(nx, 0.0);
       }
     }
     // exchange of one vector family on one level: exactly the copies k_halo_exchange makes
     auto exchange = [&](int l, std::vector<double> Shard::*dummy, int which) {
       (void)dummy;
+      if (l > rep) return;
       for (int p = 0; p < W; ++p)
         for (const SendBlock& blk : send_blocks(plan, l, p)) {
           auto pick = [&](Shard& s) -> std::vector<double>& { return which == 0 ? s.x[l] : which == 1 ? s.r[l] : which == 2 ? s.b[l] : s.y[l]; };
           std::vector<double>& src = pick(S[p]);
           std::vector<double>& dst = pick(S[blk.peer]);
-          const int64_t base = plan.owned(l, blk.peer) + blk.dst_pos;
+          const int64_t base = (plan.off[l][blk.peer + 1] - plan.off[l][blk.peer]) + blk.dst_pos;
           for (size_t k = 0; k < blk.idx.size(); ++k) dst[base + k] = src[blk.idx[k]];
         }
     };
@@ -1611,22 +1631,23 @@ int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges
     std::vector<double> tmp;
     std::function<void(int)> cycle = [&](int l) {
       if (l == L - 1) {
-        exchange(l, nullptr, 2);
+        if (l <= rep) exchange(l, nullptr, 2);
         const int64_t nc = H.nc;
         for (int p = 0; p < W; ++p)
-          for (int64_t i = 0; i < plan.owned(l, p); ++i) {
+          for (int64_t i = 0; i < nc; ++i) {   // every shard solves the whole coarsest system
             double sum = 0;
-            for (int64_t gc = 0; gc < nc; ++gc)
-              sum += H.coarse_inv[(plan.off[l][p] + i) * nc + gc] * S[p].b[l][plan.local_index(l, p, gc)];
+            const int64_t gi = plan.global_index(l, p, i);
+            for (int64_t j = 0; j < nc; ++j)
+              sum += H.coarse_inv[gi * nc + plan.global_index(l, p, j)] * S[p].b[l][j];
             S[p].y[l][i] = sum;
           }
         return;
       }
       const double om = (4.0 / 3.0) / H.levels[l].rho;
-      exchange(l, nullptr, 2);
+      if (l <= rep) exchange(l, nullptr, 2);
       for (int p = 0; p < W; ++p) {
         Shard& s = S[p];
-        const int64_t nx = plan.local_size(l, p), n = plan.owned(l, p);
+        const int64_t nx = plan.local_size(l, p), n = plan.compute_rows(l, p);
         tmp.assign(nx, 0.0);
         for (int64_t k = 0; k < nx; ++k) tmp[k] = om * s.dinv[l][k] * s.b[l][k];  // x incl. halo, as presmooth forms it
         for (int64_t i = 0; i < n; ++i) s.x[l][i] = tmp[i];
@@ -1634,15 +1655,15 @@ int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges
         local_spmv(s.A[l], tmp, ax, false);
         for (int64_t i = 0; i < n; ++i) s.r[l][i] = s.b[l][i] - ax[i];
       }
-      exchange(l, nullptr, 1);
+      if (l < rep) exchange(l, nullptr, 1);
       for (int p = 0; p < W; ++p) local_spmv(S[p].R[l], S[p].r[l], S[p].b[l + 1], false);
       cycle(l + 1);
-      exchange(l + 1, nullptr, 3);
+      if (l + 1 < rep) exchange(l + 1, nullptr, 3);
       for (int p = 0; p < W; ++p) local_spmv(S[p].P[l], S[p].y[l + 1], S[p].x[l], true);
-      exchange(l, nullptr, 0);
+      if (l < rep) exchange(l, nullptr, 0);
       for (int p = 0; p < W; ++p) {
         Shard& s = S[p];
-        const int64_t n = plan.owned(l, p);
+        const int64_t n = plan.compute_rows(l, p);
         std::vector<double> ax(n);
         local_spmv(s.A[l], s.x[l], ax, false);
         for (int64_t i = 0; i < n; ++i) s.y[l][i] = s.x[l][i] + om * s.dinv[l][i] * (s.b[l][i] - ax[i]);
@@ -1652,7 +1673,7 @@ int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges
     std::vector<std::vector<double>> r(W), pv(W), sol(W), Ap(W);
     double bb = 0;
     for (int p = 0; p < W; ++p) {
-      const int64_t n = plan.owned(0, p), nx = plan.local_size(0, p);
+      const int64_t n = plan.off[0][p + 1] - plan.off[0][p], nx = plan.local_size(0, p);
       r[p].resize(n); pv[p].assign(nx, 0.0); sol[p].assign(n, 0.0); Ap[p].resize(n);
       double part = 0;
       for (int64_t i = 0; i < n; ++i) { r[p][i] = rhs[perm[plan.off[0][p] + i]]; part += r[p][i] * r[p][i]; }
@@ -1730,7 +1751,7 @@ int tdgl_host_shard_lists(int64_t n_sites, int64_t n_edges, const int64_t* edges
     const std::vector<SendBlock> blocks = send_blocks(plan, 0, rank);
     int64_t n_send = 0;
     for (const SendBlock& b : blocks) n_send += static_cast<int64_t>(b.idx.size());
-    const int64_t n_owned = plan.owned(0, rank), n_halo = static_cast<int64_t>(plan.halo[0][rank].size());
+    const int64_t n_owned = plan.off[0][rank + 1] - plan.off[0][rank], n_halo = static_cast<int64_t>(plan.halo[0][rank].size());
     if (counts) { counts[0] = n_owned; counts[1] = n_halo; counts[2] = n_send; }
     if (owned) for (int64_t k = 0; k < n_owned; ++k) owned[k] = perm[plan.off[0][rank] + k];
     if (halo) for (int64_t k = 0; k < n_halo; ++k) halo[k] = perm[plan.halo[0][rank][k]];

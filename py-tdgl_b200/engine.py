@@ -73,7 +73,8 @@ class DeviceEngine:
                  probe_sites: Optional[Sequence[int]] = None, device: int = 0,
                  mu_rtol: float = 0.0, mu_max_iter: int = 0, amg_theta: float = 0.0,
                  amg_max_coarse: int = 0, use_graph: int = 0, reorder: int = 0,
-                 running_capacity: int = 0, world: int = 1, rank: int = 0):
+                 running_capacity: int = 0, world: int = 1, rank: int = 0,
+                 replicate_below: int = 0):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         em = mesh.edge_mesh
@@ -102,6 +103,7 @@ class DeviceEngine:
         cfg.running_capacity = running_capacity
         cfg.world = world
         cfg.rank = rank
+        cfg.replicate_below = replicate_below
         self.world, self.rank = int(world), int(rank)
         self.running_capacity = running_capacity or 4096
         rc = self._lib.tdgl_create(
@@ -294,7 +296,7 @@ class DeviceEngine:
 
 
 def host_shard_probe(mesh, world: int, rhs=None, theta=0.0, max_coarse=0, max_iter=200,
-                     rtol=1e-10):
+                     rtol=1e-10, replicate_below=0):
     """Host-only: the domain decomposition the sharded engine builds for ``world`` shards,
     and (optionally) the sharded AMG-PCG emulated in this process."""
     lib = _lib.load()
@@ -312,12 +314,13 @@ def host_shard_probe(mesh, world: int, rhs=None, theta=0.0, max_coarse=0, max_it
     rc = lib.tdgl_host_shard_probe(n, E, ptr(as_i64(em.edges)), ptr(as_f64(em.edge_lengths)),
                                    ptr(as_f64(em.dual_edge_lengths)),
                                    ptr(as_f64(mesh.sites, (n, 2))), world, theta, max_coarse,
-                                   C.byref(nl), ptr(off), ptr(halo), ptr(perm), ptr(rhs), ptr(x),
+                                   replicate_below, C.byref(nl), ptr(off), ptr(halo), ptr(perm), ptr(rhs), ptr(x),
                                    max_iter, rtol, C.byref(it))
     if rc != 0:
         raise _lib.TDGLLibraryError(lib.tdgl_last_error(None).decode())
     L = nl.value
-    return dict(levels=L, offsets=off[:L, :world + 1].copy(), halo_sizes=halo[:L, :world].copy(),
+    return dict(levels=L, rep=int(off[31, 0]), offsets=off[:L, :world + 1].copy(),
+                halo_sizes=halo[:L, :world].copy(),
                 perm=perm, x=x, iterations=it.value)
 
 

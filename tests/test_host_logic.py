@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert b"sm_100a" in lib.tdgl_version()
-    assert ctypes.sizeof(_lib.tdgl_config) == 56
+    assert ctypes.sizeof(_lib.tdgl_config) == 64
     assert ctypes.sizeof(_lib.tdgl_advance_info) == 96
 
 

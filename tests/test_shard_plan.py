@@ -33,11 +33,16 @@ def problem():
     return mesh, _sym_mu_matrix(mesh) @ x0
 
 
-@pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_sharded_pcg_matches_single(problem, world):
+@pytest.mark.parametrize("world,replicate_below", [(2, 0), (3, 0), (4, 0), (8, 0), (2, 100),
+                                                   (4, 500), (8, 1)])
+def test_sharded_pcg_matches_single(problem, world, replicate_below):
+    """replicate_below: AMG levels with at most that many rows are computed redundantly by
+    every shard (default 32768: only the fine level of this small mesh is partitioned;
+    100 / 500 / 1 partition two, one-or-two and all levels)."""
     mesh, rhs = problem
     g = host_amg_probe(mesh, rhs=rhs)
-    p = host_shard_probe(mesh, world, rhs=rhs)
+    p = host_shard_probe(mesh, world, rhs=rhs, replicate_below=replicate_below)
+    assert 1 <= p["rep"] <= p["levels"] - 1
     n = len(mesh.sites)
     off = p["offsets"]
     assert off[0, 0] == 0 and off[0, -1] == n
