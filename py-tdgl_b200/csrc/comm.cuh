@@ -84,11 +84,39 @@ __device__ __forceinline__ unsigned int poll_word(Ctl* ctl, const unsigned long 
     }
   }
 }
+// A double travels as two tagged words (low half, high half) in one aligned 16-byte pair:
+// fetch both with one vector load (each word is validated by its own tag, so the pair needs
+// no atomicity of its own) and re-poll until both tags match.
+__device__ __forceinline__ void ld_pair(const unsigned long long* p, unsigned long long* lo,
+                                        unsigned long long* hi) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(*lo), "=l"(*hi) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool pair_ready(unsigned long long lo, unsigned long long hi,
+                                           unsigned int tag) {
+  return static_cast<unsigned int>(lo >> 32) == tag && static_cast<unsigned int>(hi >> 32) == tag;
+}
+__device__ __forceinline__ double pair_value(unsigned long long lo, unsigned long long hi) {
+  return __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffull)));
+}
 __device__ __forceinline__ double poll_f64(Ctl* ctl, const unsigned long long* p,
                                            unsigned int tag, bool* ok) {
-  const unsigned long long lo = poll_word(ctl, p, tag, ok);
-  const unsigned long long hi = poll_word(ctl, p + 1, tag, ok);
-  return __longlong_as_double(static_cast<long long>((hi << 32) | lo));
+  unsigned long long lo, hi;
+  ld_pair(p, &lo, &hi);
+  if (pair_ready(lo, hi, tag)) return pair_value(lo, hi);
+  const unsigned long long t0 = global_ns();
+  unsigned int n = 0;
+  while (true) {
+    ld_pair(p, &lo, &hi);
+    if (pair_ready(lo, hi, tag)) return pair_value(lo, hi);
+    if ((++n & 255u) == 0) {
+      if (global_ns() - t0 > kSpinTimeoutNs ||
+          *reinterpret_cast<volatile int*>(&ctl->status) != 0) {
+        atomicCAS(&ctl->status, 0, 3);
+        *ok = false;
+        return 0.0;
+      }
+    }
+  }
 }
 
 // v[0..n) <- reduction over all ranks (sum in rank order, or max), n <= 4.  Must be called by
@@ -132,7 +160,8 @@ struct ExchArgs {
                                         // swaps one "present" word per exchange, so that neither
                                         // side can run more than one exchange of the level ahead
   int send_begin[kMaxWorld] = {};       // ranges of send_idx per neighbour
-  long long dst_word[2][kMaxWorld - 1] = {};  // first mailbox word on the neighbour, per parity
+  long long dst_word[2][kMaxWorld - 1] = {};  // the neighbour's mailbox of the level, per parity
+  int dst_entry[kMaxWorld - 1] = {};    // first halo entry there that this rank fills
   long long ack_word[2][kMaxWorld - 1] = {};  // this rank's "present" word on the neighbour
   long long box_word[2] = {};           // this rank's mailbox of the level, per parity
   long long box_ack[2] = {};            // the neighbours' "present" words in it (indexed by rank)
@@ -149,7 +178,8 @@ __device__ __forceinline__ void halo_exchange_body(Ctl* ctl, Comm* c, const Exch
   if (s == 0u) s = 1u;
   const int par = static_cast<int>(s & 1u);
   for (int j = 0; j < a.nnbr; ++j) {
-    unsigned long long* dst = c->peer[a.nbr[j]] + a.dst_word[par][j];
+    unsigned long long* dst = c->peer[a.nbr[j]] + a.dst_word[par][j] +
+                              static_cast<long long>(a.dst_entry[j]) * W;
     const int b = a.send_begin[j], e = a.send_begin[j + 1];
     for (int k = b + threadIdx.x; k < e; k += blockDim.x) {
       const T v = vec[a.send_idx[k]];
@@ -164,12 +194,33 @@ __device__ __forceinline__ void halo_exchange_body(Ctl* ctl, Comm* c, const Exch
   bool ok = true;
   if (threadIdx.x < a.nnbr)
     poll_word(ctl, c->peer[c->rank] + a.box_ack[par] + a.nbr[threadIdx.x], s, &ok);
-  for (int h = threadIdx.x; h < a.n_halo && ok; h += blockDim.x) {
-    T v;
-    double* d = reinterpret_cast<double*>(&v);
+  // receive: four entries per thread in flight (first-try loads issued back to back), then
+  // only the entries whose words have not landed yet are polled again
+  constexpr int P = W / 2;  // 16-byte pairs per entry
+  for (int h0 = threadIdx.x; h0 < a.n_halo && ok; h0 += 4 * blockDim.x) {
+    unsigned long long lo[4][P], hi[4][P];
 #pragma unroll
-    for (int w = 0; w < W / 2; ++w) d[w] = poll_f64(ctl, box + static_cast<long long>(h) * W + 2 * w, s, &ok);
-    if (ok) vec[a.n_owned + h] = v;
+    for (int u = 0; u < 4; ++u) {
+      const int h = h0 + u * blockDim.x;
+      if (h < a.n_halo) {
+#pragma unroll
+        for (int w = 0; w < P; ++w) ld_pair(box + static_cast<long long>(h) * W + 2 * w, &lo[u][w], &hi[u][w]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int h = h0 + u * blockDim.x;
+      if (h < a.n_halo) {
+        T v;
+        double* d = reinterpret_cast<double*>(&v);
+#pragma unroll
+        for (int w = 0; w < P; ++w)
+          d[w] = pair_ready(lo[u][w], hi[u][w], s)
+                     ? pair_value(lo[u][w], hi[u][w])
+                     : poll_f64(ctl, box + static_cast<long long>(h) * W + 2 * w, s, &ok);
+        if (ok) vec[a.n_owned + h] = v;
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) c->lseq[a.level] = s;

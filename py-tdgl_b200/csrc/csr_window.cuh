@@ -419,3 +419,111 @@ kw_psi_laplacian(WinCsr m, const double2* __restrict__ lval,
 }
 
 }  // namespace tdgl
+
+namespace tdgl {
+
+// ---- fused coarse levels -------------------------------------------------------------------------
+// The coarse part of the V-cycle — every level with at most kFuseBelow rows, down to the dense
+// coarsest solve and back up — as ONE kernel: a single thread-block cluster of 8 CTAs walks
+// through the phases with hardware cluster barriers between them instead of one kernel launch
+// per operator per level.  These levels hold < 1 % of the unknowns but, launched one by one,
+// cost more than half of the V-cycle's launches; their matrices and vectors stay L2-resident,
+// so no shared-memory staging is needed — a phase is a few dependent L2 round trips.
+//   down:  x = w D^-1 b ; r = b - A x ; b' = R r          (per level)
+//   coarsest: y = Minv b (dense)
+//   up:    x += P y' ; y = x + w D^-1 (b - A x)            (per level)
+// Input: b of level `first`; output: y of level `first`.  In the sharded engine these levels
+// are replicated on every shard (shard.h), so the kernel contains no exchange.
+
+constexpr int kFuseBelow = 32768;   // rows (the same threshold below which shards replicate)
+constexpr int kFuseCtas = 8;        // portable cluster size
+constexpr int kFuseThreads = 1024;
+
+struct FusedCsr {
+  int rows = 0;
+  const int* ptr = nullptr;
+  const int* idx = nullptr;
+  const double* val = nullptr;
+};
+struct FusedLevel {
+  int n = 0;
+  FusedCsr A, P, R;   // P: n x n_coarse, R: n_coarse x n
+  const double* dinv = nullptr;
+  double omega = 0.0;
+  double *b = nullptr, *x = nullptr, *r = nullptr, *y = nullptr;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// row dot with vector reads that bypass L1 (the vectors are rewritten between phases by other
+// CTAs of the cluster)
+__device__ __forceinline__ double fused_row_dot(const FusedCsr& m, int row, const double* x) {
+  const int kb = __ldg(m.ptr + row), ke = __ldg(m.ptr + row + 1);
+  double s = 0.0;
+  int k = kb;
+  for (; k + 4 <= ke; k += 4) {
+    const int j0 = __ldg(m.idx + k), j1 = __ldg(m.idx + k + 1), j2 = __ldg(m.idx + k + 2),
+              j3 = __ldg(m.idx + k + 3);
+    const double v0 = __ldg(m.val + k), v1 = __ldg(m.val + k + 1), v2 = __ldg(m.val + k + 2),
+                 v3 = __ldg(m.val + k + 3);
+    const double x0 = __ldcg(x + j0), x1 = __ldcg(x + j1), x2 = __ldcg(x + j2), x3 = __ldcg(x + j3);
+    s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
+  }
+  for (; k < ke; ++k) s = fma(__ldg(m.val + k), __ldcg(x + __ldg(m.idx + k)), s);
+  return s;
+}
+
+__global__ void __cluster_dims__(kFuseCtas, 1, 1) __launch_bounds__(kFuseThreads)
+k_coarse_cycle(const Ctl* __restrict__ ctl, const FusedLevel* __restrict__ lv, int first,
+               int n_levels, const double* __restrict__ coarse_inv, int nc) {
+  if (ctl->status != 0) return;  // uniform over the cluster
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  for (int l = first; l + 1 < n_levels; ++l) {
+    const FusedLevel L = lv[l];
+    // x = w D^-1 b ; r = b - A x  (x_j formed on the fly from b_j, as kw_real<presmooth>)
+    for (int i = tid; i < L.n; i += nth) {
+      const int kb = __ldg(L.A.ptr + i), ke = __ldg(L.A.ptr + i + 1);
+      double s = 0.0;
+      for (int k = kb; k < ke; ++k) {
+        const int j = __ldg(L.A.idx + k);
+        s = fma(__ldg(L.A.val + k), L.omega * (__ldg(L.dinv + j) * __ldcg(L.b + j)), s);
+      }
+      const double bi = __ldcg(L.b + i);
+      __stcg(L.x + i, L.omega * __ldg(L.dinv + i) * bi);
+      __stcg(L.r + i, bi - s);
+    }
+    cluster_sync_all();
+    const FusedLevel C = lv[l + 1];
+    for (int i = tid; i < L.R.rows; i += nth) __stcg(C.b + i, fused_row_dot(L.R, i, L.r));
+    cluster_sync_all();
+  }
+  {
+    const FusedLevel C = lv[n_levels - 1];
+    const int warp = tid >> 5, lane = threadIdx.x & 31, nwarp = nth >> 5;
+    for (int i = warp; i < nc; i += nwarp) {
+      const double* row = coarse_inv + static_cast<size_t>(i) * nc;
+      double s = 0.0;
+      for (int j = lane; j < nc; j += 32) s += __ldg(row + j) * __ldcg(C.b + j);
+      s = warp_sum(s);
+      if (lane == 0) __stcg(C.y + i, s);
+    }
+    cluster_sync_all();
+  }
+  for (int l = n_levels - 2; l >= first; --l) {
+    const FusedLevel L = lv[l];
+    const FusedLevel C = lv[l + 1];
+    for (int i = tid; i < L.n; i += nth) __stcg(L.x + i, __ldcg(L.x + i) + fused_row_dot(L.P, i, C.y));
+    cluster_sync_all();
+    for (int i = tid; i < L.n; i += nth) {
+      const double s = fused_row_dot(L.A, i, L.x);
+      __stcg(L.y + i, __ldcg(L.x + i) + L.omega * __ldg(L.dinv + i) * (__ldcg(L.b + i) - s));
+    }
+    if (l > first) cluster_sync_all();
+  }
+}
+
+}  // namespace tdgl

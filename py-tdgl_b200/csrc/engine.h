@@ -230,6 +230,8 @@ class Engine {
   // ---- mu solver ----------------------------------------------------------------------------
   std::vector<DevLevel> levels_;
   DevBuf<double> coarse_inv_;
+  DevBuf<FusedLevel> fused_;   // per-level operator table of the fused coarse-level kernel
+  int fuse_from_ = -1;         // first level the cluster kernel handles (-1: none)
   int nc_ = 0;
   int64_t amg_nnz_ = 0;
   DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_;

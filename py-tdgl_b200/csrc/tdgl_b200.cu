@@ -101,7 +101,7 @@ ExchArgs Engine::make_exch(int level, const int* send_idx_dev) const {
     for (const SendBlock& b : blocks)
       if (b.peer == q) {
         pos += static_cast<int>(b.idx.size());
-        for (int par = 0; par < 2; ++par) a.dst_word[par][j] += b.dst_pos * W;
+        a.dst_entry[j] = static_cast<int>(b.dst_pos);
       }
   }
   a.send_begin[a.nnbr] = pos;
@@ -375,6 +375,30 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     }
   }
   {
+    // levels small enough to run fused in one cluster kernel (replicated levels only)
+    fuse_from_ = -1;
+    if (std::getenv("TDGL_B200_NO_FUSE") == nullptr)
+      for (size_t l = 1; l + 1 < L; ++l)
+        if (H.levels[l].A.rows <= kFuseBelow && (world_ == 1 || static_cast<int>(l) >= rep_level)) {
+          fuse_from_ = static_cast<int>(l);
+          break;
+        }
+    std::vector<FusedLevel> fl(L);
+    for (size_t l = 1; l < L; ++l) {
+      DevLevel& dl = levels_[l];
+      FusedLevel& f = fl[l];
+      f.n = dl.n;
+      f.A = FusedCsr{dl.A.rows, dl.A.ptr.p, dl.A.idx.p, dl.A.val.p};
+      f.P = FusedCsr{dl.P.rows, dl.P.ptr.p, dl.P.idx.p, dl.P.val.p};
+      f.R = FusedCsr{dl.R.rows, dl.R.ptr.p, dl.R.idx.p, dl.R.val.p};
+      f.dinv = dl.dinv.p;
+      f.omega = dl.omega;
+      f.b = dl.b.p; f.x = dl.x.p; f.r = dl.r.p; f.y = dl.y.p;
+    }
+    fused_.upload(fl, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
+  {
     // coarsest level: dense inverse with rows and columns in this shard's local order
     const int lc = static_cast<int>(L) - 1;
     nc_ = static_cast<int>(H.nc);
@@ -619,33 +643,39 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   // Sharded: on a partitioned level (l < rep) a vector is exchanged right before the kernel
   // that gathers from it; the right-hand side of level rep is all-gathered and everything
   // from there down is computed redundantly by every shard (no exchange).
+  // Levels fuse_from_ .. L-1 (the small ones) run as ONE cluster kernel.
   const int rep = comm_on_ ? plan_.rep : -1;
-  for (size_t l = 0; l + 1 < L; ++l) {
-    DevLevel& lv = levels_[l];
-    const int li = static_cast<int>(l);
-    double* b = (l == 0) ? r_in : lv.b.p;
+  const int Li = static_cast<int>(L);
+  const int split = (fuse_from_ >= 1 && fuse_from_ <= Li - 2) ? fuse_from_ : Li - 1;
+  for (int li = 0; li < split; ++li) {
+    DevLevel& lv = levels_[li];
+    double* b = (li == 0) ? r_in : lv.b.p;
     if (li <= rep) enqueue_exchange(li, b);
-    launch_presmooth(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, lv.r.p);
+    launch_presmooth(levelA(li), lv.dinv.p, lv.omega, b, lv.x.p, lv.r.p);
     if (li < rep) enqueue_exchange(li, lv.r.p);
-    launch_plain(lv.R.view(), lv.r.p, levels_[l + 1].b.p, false);
+    launch_plain(lv.R.view(), lv.r.p, levels_[li + 1].b.p, false);
   }
   {
-    DevLevel& c = levels_[L - 1];
-    if (static_cast<int>(L) - 1 <= rep) enqueue_exchange(static_cast<int>(L) - 1, c.b.p);
-    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, nc_, coarse_inv_.p, c.b.p, c.y.p);
+    DevLevel& c = levels_[split];
+    if (split <= rep) enqueue_exchange(split, c.b.p);
+    if (split < Li - 1) {
+      k_coarse_cycle<<<kFuseCtas, kFuseThreads, 0, stream_>>>(ctl_.p, fused_.p, split, Li,
+                                                             coarse_inv_.p, nc_);
+    } else {
+      const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
+      k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, nc_, coarse_inv_.p, c.b.p, c.y.p);
+    }
     TDGL_LAUNCH_CHECK();
   }
-  for (size_t l = L - 1; l-- > 0;) {
-    DevLevel& lv = levels_[l];
-    const int li = static_cast<int>(l);
-    const double* b = (l == 0) ? r_in : lv.b.p;
-    double* y = (l == 0) ? z_out : lv.y.p;
-    if (li + 1 < rep) enqueue_exchange(li + 1, levels_[l + 1].y.p);
-    launch_plain(lv.P.view(), levels_[l + 1].y.p, lv.x.p, true);
+  for (int li = split - 1; li >= 0; --li) {
+    DevLevel& lv = levels_[li];
+    const double* b = (li == 0) ? r_in : lv.b.p;
+    double* y = (li == 0) ? z_out : lv.y.p;
+    if (li + 1 < rep) enqueue_exchange(li + 1, levels_[li + 1].y.p);
+    launch_plain(lv.P.view(), levels_[li + 1].y.p, lv.x.p, true);
     if (li < rep) enqueue_exchange(li, lv.x.p);
-    launch_jacobi(levelA(l), lv.dinv.p, lv.omega, b, lv.x.p, y, (l == 0) ? r_in : nullptr,
-                  (l == 0) ? rz_out : nullptr);
+    launch_jacobi(levelA(li), lv.dinv.p, lv.omega, b, lv.x.p, y, (li == 0) ? r_in : nullptr,
+                  (li == 0) ? rz_out : nullptr);
   }
 }
 
@@ -868,9 +898,10 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     // the graph's kernels were launched by the device-side loops; account for them
     const int64_t L = static_cast<int64_t>(levels_.size());
     const int64_t R = std::min<int64_t>(plan_.rep, L - 1);
-    const int64_t ex_step = world_ > 1 ? 2 : 0, ex_it = world_ > 1 ? 4 * R + 1 + 1 : 0;
+    const int64_t ex_step = world_ > 1 ? 2 : 0, ex_it = world_ > 1 ? 4 * R + 1 : 0;
+    const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
     launches_ += h_ctl_->steps_done * (6 + ex_step) + h_ctl_->total_retries * 2 +
-                 h_ctl_->total_cg_it * (3 + 4 * (L - 1) + 1 + ex_it);
+                 h_ctl_->total_cg_it * (3 + 4 * split + 1 + ex_it);
   } else {
     while (true) {
       k_step_begin<<<1, 32, 0, stream_>>>(ctl_.p, 0);
