@@ -229,6 +229,7 @@ __device__ __forceinline__ void halo_exchange_body(Ctl* ctl, Comm* c, const Exch
 template <typename T>
 __global__ void __launch_bounds__(1024)
 k_halo_exchange(Ctl* ctl, Comm* c, ExchArgs a, T* __restrict__ vec) {
+  griddep_enter();
   if (ctl->status != 0) return;
   halo_exchange_body<T>(ctl, c, a, vec);
 }
@@ -236,6 +237,7 @@ k_halo_exchange(Ctl* ctl, Comm* c, ExchArgs a, T* __restrict__ vec) {
 // psi is double-buffered: exchange the buffer that holds the current psi.
 __global__ void __launch_bounds__(1024)
 k_halo_exchange_psi(Ctl* ctl, Comm* c, ExchArgs a, double2* psi0, double2* psi1) {
+  griddep_enter();
   if (ctl->status != 0) return;
   halo_exchange_body<double2>(ctl, c, a, ctl->cur ? psi1 : psi0);
 }

@@ -62,13 +62,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// Programmatic dependent launch: block until the kernels this launch depends on have
-// completed and flushed (a no-op for an ordinary launch).
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
 // ---- staging ---------------------------------------------------------------------------------
 
 struct WinRow {
@@ -83,6 +76,7 @@ template <int SA, int SB>
 __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA,
                                                const void* valB, unsigned char* smem,
                                                uint64_t* bar) {
+  griddep_launch_dependents();
   const int r0 = blockIdx.x * blockDim.x;
   const int r1 = min(r0 + static_cast<int>(blockDim.x), m.rows);
   const int k0a = __ldg(m.ptr + r0) & ~3;
@@ -426,8 +420,8 @@ namespace tdgl {
 // The coarse part of the V-cycle — every level with at most kFuseBelow rows, down to the dense
 // coarsest solve and back up — as ONE kernel: a single thread-block cluster of 8 CTAs walks
 // through the phases with hardware cluster barriers between them instead of one kernel launch
-// per operator per level.  These levels hold < 1 % of the unknowns but, launched one by one,
-// cost more than half of the V-cycle's launches; their matrices and vectors stay L2-resident,
+// per operator per level.  These levels hold ~0.2 % of the unknowns but, launched one by one,
+// cost a third of the V-cycle's launches; their matrices and vectors stay L2-resident,
 // so no shared-memory staging is needed — a phase is a few dependent L2 round trips.
 //   down:  x = w D^-1 b ; r = b - A x ; b' = R r          (per level)
 //   coarsest: y = Minv b (dense)
@@ -435,7 +429,7 @@ namespace tdgl {
 // Input: b of level `first`; output: y of level `first`.  In the sharded engine these levels
 // are replicated on every shard (shard.h), so the kernel contains no exchange.
 
-constexpr int kFuseBelow = 32768;   // rows (the same threshold below which shards replicate)
+constexpr int kFuseBelow = 4096;    // rows: what one 8-CTA cluster turns around in a few microseconds
 constexpr int kFuseCtas = 8;        // portable cluster size
 constexpr int kFuseThreads = 1024;
 
@@ -458,47 +452,54 @@ __device__ __forceinline__ void cluster_sync_all() {
                "barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// row dot with vector reads that bypass L1 (the vectors are rewritten between phases by other
-// CTAs of the cluster)
-__device__ __forceinline__ double fused_row_dot(const FusedCsr& m, int row, const double* x) {
-  const int kb = __ldg(m.ptr + row), ke = __ldg(m.ptr + row + 1);
+// One row = one group of 8 lanes (the rows of these levels are long, 15-30 entries, and there
+// are few of them: spreading a row over lanes keeps the dependent-load chains short).
+// `term(k)` returns the k-th product of the row.  All 32 lanes of a warp must call this.
+template <typename F>
+__device__ __forceinline__ double fused_row_sum(const FusedCsr& m, int row, bool live, int sub,
+                                                F term) {
   double s = 0.0;
-  int k = kb;
-  for (; k + 4 <= ke; k += 4) {
-    const int j0 = __ldg(m.idx + k), j1 = __ldg(m.idx + k + 1), j2 = __ldg(m.idx + k + 2),
-              j3 = __ldg(m.idx + k + 3);
-    const double v0 = __ldg(m.val + k), v1 = __ldg(m.val + k + 1), v2 = __ldg(m.val + k + 2),
-                 v3 = __ldg(m.val + k + 3);
-    const double x0 = __ldcg(x + j0), x1 = __ldcg(x + j1), x2 = __ldcg(x + j2), x3 = __ldcg(x + j3);
-    s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
+  if (live) {
+    const int kb = __ldg(m.ptr + row), ke = __ldg(m.ptr + row + 1);
+    for (int k = kb + sub; k < ke; k += 8) s += term(k);
   }
-  for (; k < ke; ++k) s = fma(__ldg(m.val + k), __ldcg(x + __ldg(m.idx + k)), s);
-  return s;
+  return group_sum<8>(s);
 }
 
 __global__ void __cluster_dims__(kFuseCtas, 1, 1) __launch_bounds__(kFuseThreads)
 k_coarse_cycle(const Ctl* __restrict__ ctl, const FusedLevel* __restrict__ lv, int first,
                int n_levels, const double* __restrict__ coarse_inv, int nc) {
+  griddep_enter();
   if (ctl->status != 0) return;  // uniform over the cluster
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
+  const int grp = tid >> 3, sub = tid & 7, ngrp = nth >> 3;
   for (int l = first; l + 1 < n_levels; ++l) {
     const FusedLevel L = lv[l];
     // x = w D^-1 b ; r = b - A x  (x_j formed on the fly from b_j, as kw_real<presmooth>)
-    for (int i = tid; i < L.n; i += nth) {
-      const int kb = __ldg(L.A.ptr + i), ke = __ldg(L.A.ptr + i + 1);
-      double s = 0.0;
-      for (int k = kb; k < ke; ++k) {
+    for (int base = 0; base < L.n; base += ngrp) {
+      const int i = base + grp;
+      const bool live = i < L.n;
+      const double s = fused_row_sum(L.A, i, live, sub, [&](int k) {
         const int j = __ldg(L.A.idx + k);
-        s = fma(__ldg(L.A.val + k), L.omega * (__ldg(L.dinv + j) * __ldcg(L.b + j)), s);
+        return __ldg(L.A.val + k) * (L.omega * (__ldg(L.dinv + j) * __ldcg(L.b + j)));
+      });
+      if (live && sub == 0) {
+        const double bi = __ldcg(L.b + i);
+        __stcg(L.x + i, L.omega * __ldg(L.dinv + i) * bi);
+        __stcg(L.r + i, bi - s);
       }
-      const double bi = __ldcg(L.b + i);
-      __stcg(L.x + i, L.omega * __ldg(L.dinv + i) * bi);
-      __stcg(L.r + i, bi - s);
     }
     cluster_sync_all();
     const FusedLevel C = lv[l + 1];
-    for (int i = tid; i < L.R.rows; i += nth) __stcg(C.b + i, fused_row_dot(L.R, i, L.r));
+    for (int base = 0; base < L.R.rows; base += ngrp) {
+      const int i = base + grp;
+      const bool live = i < L.R.rows;
+      const double s = fused_row_sum(L.R, i, live, sub, [&](int k) {
+        return __ldg(L.R.val + k) * __ldcg(L.r + __ldg(L.R.idx + k));
+      });
+      if (live && sub == 0) __stcg(C.b + i, s);
+    }
     cluster_sync_all();
   }
   {
@@ -516,11 +517,23 @@ k_coarse_cycle(const Ctl* __restrict__ ctl, const FusedLevel* __restrict__ lv, i
   for (int l = n_levels - 2; l >= first; --l) {
     const FusedLevel L = lv[l];
     const FusedLevel C = lv[l + 1];
-    for (int i = tid; i < L.n; i += nth) __stcg(L.x + i, __ldcg(L.x + i) + fused_row_dot(L.P, i, C.y));
+    for (int base = 0; base < L.n; base += ngrp) {
+      const int i = base + grp;
+      const bool live = i < L.n;
+      const double s = fused_row_sum(L.P, i, live, sub, [&](int k) {
+        return __ldg(L.P.val + k) * __ldcg(C.y + __ldg(L.P.idx + k));
+      });
+      if (live && sub == 0) __stcg(L.x + i, __ldcg(L.x + i) + s);
+    }
     cluster_sync_all();
-    for (int i = tid; i < L.n; i += nth) {
-      const double s = fused_row_dot(L.A, i, L.x);
-      __stcg(L.y + i, __ldcg(L.x + i) + L.omega * __ldg(L.dinv + i) * (__ldcg(L.b + i) - s));
+    for (int base = 0; base < L.n; base += ngrp) {
+      const int i = base + grp;
+      const bool live = i < L.n;
+      const double s = fused_row_sum(L.A, i, live, sub, [&](int k) {
+        return __ldg(L.A.val + k) * __ldcg(L.x + __ldg(L.A.idx + k));
+      });
+      if (live && sub == 0)
+        __stcg(L.y + i, __ldcg(L.x + i) + L.omega * __ldg(L.dinv + i) * (__ldcg(L.b + i) - s));
     }
     if (l > first) cluster_sync_all();
   }

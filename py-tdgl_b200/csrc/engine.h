@@ -249,6 +249,25 @@ class Engine {
   cudaGraphConditionalHandle h_step_ = 0, h_psi_ = 0, h_cg_ = 0;
 
   // ---- launch sequences ------------------------------------------------------------------
+  // Every kernel of the stepping sequence is launched with programmatic stream
+  // serialisation (PDL): it may become resident while its predecessor drains, issues the
+  // bulk copies of its (static) CSR window, and blocks in griddepcontrol.wait until the
+  // predecessor's results are visible.  TDGL_B200_PDL=0 turns the attribute off.
+  bool pdl_ = true;
+  template <typename... KArgs, typename... Args>
+  void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream_;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_ ? 1 : 0;
+    TDGL_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  }
   static int grid_win(int rows, int win) { return (rows + win - 1) / win; }
   WinCsr site_csr() const { return WinCsr{N_, cap0_, ptr_.p, idx_.p}; }
   template <int OP>

@@ -52,6 +52,19 @@ struct Ctl {
   double mu_mean;
 };
 
+// Programmatic dependent launch: `griddep_wait` blocks until the kernels this launch depends
+// on have completed and flushed their results (a no-op for an ordinary launch);
+// `griddep_launch_dependents` lets the next kernel of the stream become resident early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// kernels without a static prologue: let the successor in, then wait for the predecessor
+__device__ __forceinline__ void griddep_enter() {
+  griddep_launch_dependents();
+  griddep_wait();
+}
+
 }  // namespace tdgl
 #include "comm.cuh"
 namespace tdgl {
@@ -130,6 +143,7 @@ __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
 __global__ void __launch_bounds__(kBlock)
 k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const double* __restrict__ M,
                const double* __restrict__ b, double* __restrict__ x) {
+  griddep_enter();
   if (ctl->status != 0) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,6 +162,7 @@ k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const double* __re
 __global__ void __launch_bounds__(kBlock)
 k_cg_direction(const Ctl* __restrict__ ctl, int n, const double* __restrict__ z,
                double* __restrict__ p) {
+  griddep_enter();
   if (ctl->status != 0) return;
   const double beta = (ctl->cg_it == 0) ? 0.0 : ctl->rz_new / ctl->rz_prev;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,6 +175,7 @@ __global__ void __launch_bounds__(kBlock)
 k_cg_update(Ctl* ctl, Comm* comm, int n, const double* __restrict__ p,
             const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
             double* partials, unsigned int* counter, cudaGraphConditionalHandle cond) {
+  griddep_enter();
   __shared__ double red[32];
   if (ctl->status != 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) set_cond(cond, 0);
@@ -202,6 +218,7 @@ k_cg_update(Ctl* ctl, Comm* comm, int n, const double* __restrict__ p,
 // Decide whether the CG loop has to run at all (warm start may already satisfy the
 // tolerance) and arm its counters.
 __global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond) {
+  griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int go = 0;
   if (ctl->status == 0) {
@@ -261,6 +278,7 @@ __device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu
 
 // Start of TDGLSolver.update (solver.py:649-668): dt <- tentative_dt, retries <- 0.
 __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
+  griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->dt = ctl->tentative_dt;
   ctl->retries = 0;
@@ -273,6 +291,7 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
 
 // adaptive_euler_step's retry logic (solver.py:475-485)
 __global__ void k_psi_control(Ctl* ctl, Comm* comm, cudaGraphConditionalHandle cond_psi) {
+  griddep_enter();
   if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   int go = 0;
   if (comm != nullptr && ctl->status == 0) {  // one full warp (launched with 32 threads)
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(kBlock)
 k_weighted_sum(Ctl* ctl, Comm* comm, int n, const double* __restrict__ w,
                const double* __restrict__ x, double* partials, unsigned int* counter,
                double inv_total_weight) {
+  griddep_enter();
   __shared__ double red[32];
   if (ctl->status != 0) return;
   double d = 0.0;
@@ -329,6 +349,7 @@ k_weighted_sum(Ctl* ctl, Comm* comm, int n, const double* __restrict__ w,
 
 __global__ void __launch_bounds__(kBlock)
 k_shift(const Ctl* __restrict__ ctl, int n, double* __restrict__ x) {
+  griddep_enter();
   if (ctl->status != 0) return;
   const double m = ctl->mu_mean;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,6 +362,7 @@ __global__ void k_step_end(Ctl* ctl, const double2* __restrict__ psi_buf0,
                            const double2* __restrict__ psi_buf1, const double* __restrict__ mu,
                            const int* __restrict__ probes, double* run_dt, double* run_mu,
                            double* run_theta, cudaGraphConditionalHandle cond_step) {
+  griddep_enter();
   if (blockIdx.x != 0) return;
   if (ctl->status != 0) {
     if (threadIdx.x == 0) { ctl->step_go = 0; set_cond(cond_step, 0); }
@@ -485,6 +507,7 @@ __global__ void k_scale_neg_area(int n, const double* __restrict__ areas,
 __global__ void __launch_bounds__(kBlock)
 k_dot(Ctl* ctl, Comm* comm, int n, const double* __restrict__ a, const double* __restrict__ b,
       double* partials, unsigned int* counter, double* out) {
+  griddep_enter();
   __shared__ double red[32];
   if (ctl->status != 0) return;
   double d = 0.0;

@@ -126,6 +126,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   nprobe_ = static_cast<int>(n_probe);
   world_ = cfg_.world;
   rank_ = cfg_.rank;
+  if (const char* e = std::getenv("TDGL_B200_PDL")) pdl_ = e[0] != '0';
 
   int ndev = 0;
   TDGL_CUDA(cudaGetDeviceCount(&ndev));
@@ -577,7 +578,7 @@ template <int OP>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
   const size_t smem = static_cast<size_t>(A.m.cap) * 12;
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
-  kw_real<OP><<<grid_win(A.m.rows, A.win), A.win, smem, stream_>>>(ctl_.p, comm(), A.m, a,
+  launch_k(kw_real<OP>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
                                                                    partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
@@ -620,13 +621,13 @@ void Engine::launch_residual(const CsrView& A, const double* x, const double* b,
 // smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
 void Engine::enqueue_exchange(int level, double* vec) {
   if (!comm_on_ || level > plan_.rep) return;
-  k_halo_exchange<double><<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, levels_[level].ex, vec);
+  launch_k(k_halo_exchange<double>, 1, 1024, 0, ctl_.p, comm_.p, levels_[level].ex, vec);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_exchange_psi() {
   if (!comm_on_) return;
-  k_halo_exchange_psi<<<1, 1024, 0, stream_>>>(ctl_.p, comm_.p, levels_[0].ex, psi_[0].p, psi_[1].p);
+  launch_k(k_halo_exchange_psi, 1, 1024, 0, ctl_.p, comm_.p, levels_[0].ex, psi_[0].p, psi_[1].p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -634,9 +635,9 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   const size_t L = levels_.size();
   if (L == 1) {
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, nc_, coarse_inv_.p, r_in, z_out);
+    launch_k(k_dense_matvec, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p, r_in, z_out);
     TDGL_LAUNCH_CHECK();
-    k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
+    launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
     TDGL_LAUNCH_CHECK();
     return;
   }
@@ -659,11 +660,11 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     DevLevel& c = levels_[split];
     if (split <= rep) enqueue_exchange(split, c.b.p);
     if (split < Li - 1) {
-      k_coarse_cycle<<<kFuseCtas, kFuseThreads, 0, stream_>>>(ctl_.p, fused_.p, split, Li,
+      launch_k(k_coarse_cycle, kFuseCtas, kFuseThreads, 0, ctl_.p, fused_.p, split, Li,
                                                              coarse_inv_.p, nc_);
     } else {
       const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-      k_dense_matvec<<<grid, kBlock, 0, stream_>>>(ctl_.p, nc_, nc_, coarse_inv_.p, c.b.p, c.y.p);
+      launch_k(k_dense_matvec, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p, c.b.p, c.y.p);
     }
     TDGL_LAUNCH_CHECK();
   }
@@ -680,14 +681,14 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
 }
 
 void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
-  kw_psi_step<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, stream_>>>(
+  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, 
       ctl_.p, site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p, mu_.p,
       eps_.p, sq_out, dt_override);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_mu_rhs(double* rhs_raw) {
-  kw_mu_rhs<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, stream_>>>(
+  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, 
       ctl_.p, comm(), site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p,
       bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
@@ -695,11 +696,11 @@ void Engine::enqueue_mu_rhs(double* rhs_raw) {
 
 void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new);
-  k_cg_direction<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, cg_z_.p, cg_p_.p);
+  launch_k(k_cg_direction, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, cg_z_.p, cg_p_.p);
   TDGL_LAUNCH_CHECK();
   enqueue_exchange(0, cg_p_.p);
   launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp);
-  k_cg_update<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_p_.p, cg_Ap_.p, mu_.p,
+  launch_k(k_cg_update, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, cg_p_.p, cg_Ap_.p, mu_.p,
                                                    cg_r_.p, partials_.p, counter_.p, cond);
   TDGL_LAUNCH_CHECK();
 }
@@ -707,16 +708,16 @@ void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
 // project mu to area-weighted mean zero (fixes the gauge the reference leaves to SuperLU
 // roundoff)
 void Engine::enqueue_mu_finish() {
-  k_weighted_sum<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, areas_.p, mu_.p,
+  launch_k(k_weighted_sum, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, areas_.p, mu_.p,
                                                       partials_.p, counter_.p, 1.0 / total_area_);
   TDGL_LAUNCH_CHECK();
-  k_shift<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(ctl_.p, N_, mu_.p);
+  launch_k(k_shift, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, mu_.p);
   TDGL_LAUNCH_CHECK();
   enqueue_exchange(0, mu_.p);  // the next step's rhs / the edge currents read mu's halo
 }
 
 void Engine::host_solve_loop() {
-  k_cg_begin<<<1, 32, 0, stream_>>>(ctl_.p, 0);
+  launch_k(k_cg_begin, 1, 32, 0, ctl_.p, 0);
   TDGL_LAUNCH_CHECK();
   sync_ctl_to_host();
   while (h_ctl_->cg_go) {
@@ -780,7 +781,7 @@ void Engine::build_graph() {
 
   GraphBuilder sb{step_body, stream_, {}};
   sb.capture([&] {
-    k_step_begin<<<1, 32, 0, stream_>>>(ctl_.p, h_psi_);
+    launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_);
     TDGL_LAUNCH_CHECK();
   });
   cudaGraph_t psi_body = sb.add_while(h_psi_);
@@ -788,14 +789,14 @@ void Engine::build_graph() {
     GraphBuilder pb{psi_body, stream_, {}};
     pb.capture([&] {
       enqueue_psi_step(nullptr, -1.0);
-      k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, comm(), h_psi_);
+      launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), h_psi_);
       TDGL_LAUNCH_CHECK();
     });
   }
   sb.capture([&] {
     enqueue_exchange_psi();
     enqueue_mu_rhs(nullptr);
-    k_cg_begin<<<1, 32, 0, stream_>>>(ctl_.p, h_cg_);
+    launch_k(k_cg_begin, 1, 32, 0, ctl_.p, h_cg_);
     TDGL_LAUNCH_CHECK();
   });
   cudaGraph_t cg_body = sb.add_while(h_cg_);
@@ -805,7 +806,7 @@ void Engine::build_graph() {
   }
   sb.capture([&] {
     enqueue_mu_finish();
-    k_step_end<<<1, kMaxProbes, 0, stream_>>>(ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
+    launch_k(k_step_end, 1, kMaxProbes, 0, ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
                                             run_dt_.p, run_mu_.p, run_theta_.p, h_step_);
     TDGL_LAUNCH_CHECK();
   });
@@ -904,11 +905,11 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
                  h_ctl_->total_cg_it * (3 + 4 * split + 1 + ex_it);
   } else {
     while (true) {
-      k_step_begin<<<1, 32, 0, stream_>>>(ctl_.p, 0);
+      launch_k(k_step_begin, 1, 32, 0, ctl_.p, 0);
       TDGL_LAUNCH_CHECK();
       do {
         enqueue_psi_step(nullptr, -1.0);
-        k_psi_control<<<1, 32, 0, stream_>>>(ctl_.p, comm(), 0);
+        launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), 0);
         TDGL_LAUNCH_CHECK();
         sync_ctl_to_host();
       } while (h_ctl_->psi_go);
@@ -917,7 +918,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
       enqueue_mu_rhs(nullptr);
       host_solve_loop();
       enqueue_mu_finish();
-      k_step_end<<<1, kMaxProbes, 0, stream_>>>(ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
+      launch_k(k_step_end, 1, kMaxProbes, 0, ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
                                               run_dt_.p, run_mu_.p, run_theta_.p, 0);
       TDGL_LAUNCH_CHECK();
       sync_ctl_to_host();
@@ -1061,7 +1062,7 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
   h_ctl_->disc_flag = 0;
   h_ctl_->status = 0;
   push_ctl();
-  kw_psi_step<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, stream_>>>(
+  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, 
       ctl_.p, site_csr(), lval_.p, fixed_.p, pin.p, pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p,
       dt);
   TDGL_LAUNCH_CHECK();
@@ -1089,7 +1090,7 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   TDGL_LAUNCH_CHECK();
   sync_ctl_to_host();
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
-  kw_mu_rhs<<<grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, stream_>>>(
+  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, 
       ctl_.p, comm(), site_csr(), lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p,
       raw.p, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
@@ -1136,9 +1137,9 @@ void Engine::op_mu_solve(const double* rhs, double* mu, int* iterations, double*
   h_ctl_->status = 0;
   h_ctl_->total_cg_it = 0;
   push_ctl();
-  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_b_.p, cg_b_.p, partials_.p, counter_.p, &ctl_.p->bb);
+  launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, cg_b_.p, cg_b_.p, partials_.p, counter_.p, &ctl_.p->bb);
   TDGL_LAUNCH_CHECK();
-  k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
+  launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
   TDGL_LAUNCH_CHECK();
   host_solve_loop();
   enqueue_mu_finish();
@@ -1181,7 +1182,7 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
       case 4:
         mu_.zero(stream_);
         TDGL_CUDA(cudaMemcpyAsync(cg_r_.p, cg_b_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
-        k_dot<<<grid_flat(N_), kBlock, 0, stream_>>>(ctl_.p, comm(), N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
+        launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, cg_r_.p, cg_r_.p, partials_.p, counter_.p, &ctl_.p->rr);
         TDGL_LAUNCH_CHECK();
         host_solve_loop();
         break;
