@@ -58,7 +58,9 @@ typedef struct tdgl_config {
   int32_t rank;             /* the shard this handle computes, 0..world-1 [0] */
   int32_t replicate_below;  /* sharded: AMG levels with at most this many rows are computed
                                redundantly by every shard instead of exchanged [32768] */
-  int32_t reserved;
+  int32_t fuse_coarse;      /* 1: AMG levels with <= 4096 rows run as ONE thread-block-cluster
+                               kernel; 2: one kernel per operator per level.  Measured at 1M
+                               sites the fused form is not faster, hence [2] */
 } tdgl_config;
 
 /* Mesh + material -> device-resident operators.  Replaces MeshOperators.__init__ +

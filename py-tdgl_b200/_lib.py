@@ -36,7 +36,7 @@ class tdgl_config(C.Structure):
         ("world", C.c_int32),
         ("rank", C.c_int32),
         ("replicate_below", C.c_int32),
-        ("reserved", C.c_int32),
+        ("fuse_coarse", C.c_int32),
     ]
 
 

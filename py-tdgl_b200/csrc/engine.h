@@ -82,7 +82,7 @@ struct DevCsr {
   int64_t nnz = 0;
   DevBuf<int> ptr, idx;   // idx / val carry 4 padding elements (see csr_window.cuh)
   DevBuf<double> val;
-  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p}, val.p, win}; }
+  CsrView view() const { return CsrView{WinCsr{rows, 1, cap, ptr.p, idx.p}, val.p, win}; }
 };
 
 struct DevLevel {
@@ -135,6 +135,7 @@ struct Config {
   int world = 1;   // number of shards (one GPU / process each, or several per process)
   int rank = 0;    // this engine's shard
   int replicate_below = 0;  // AMG levels with at most this many rows are replicated (0: 32768)
+  int fuse_coarse = 0;      // 1: levels <= 4096 rows run as one cluster kernel (k_coarse_cycle)
 };
 
 class Engine {
@@ -269,7 +270,10 @@ class Engine {
     TDGL_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
   }
   static int grid_win(int rows, int win) { return (rows + win - 1) / win; }
-  WinCsr site_csr() const { return WinCsr{N_, cap0_, ptr_.p, idx_.p}; }
+  WinCsr site_csr() const { return WinCsr{N_, 1, cap0_, ptr_.p, idx_.p}; }
+  struct PersistPlan { int grid = 1, stages = 1; size_t smem = 0; };
+  PersistPlan persist_plan(const void* kernel, int rows, int win, int cap, int bytes_per_nnz);
+  int sm_count_ = 148;
   template <int OP>
   void launch_real(const CsrView& A, const RealArgs& a);
   int grid_flat(int n) const {

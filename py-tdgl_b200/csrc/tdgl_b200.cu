@@ -132,6 +132,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   TDGL_CUDA(cudaGetDeviceCount(&ndev));
   if (cfg_.device < 0 || cfg_.device >= ndev) throw std::invalid_argument("bad CUDA device ordinal");
   TDGL_CUDA(cudaSetDevice(cfg_.device));
+  TDGL_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, cfg_.device));
   TDGL_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   TDGL_CUDA(cudaEventCreate(&ev0_));
   TDGL_CUDA(cudaEventCreate(&ev1_));
@@ -378,7 +379,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   {
     // levels small enough to run fused in one cluster kernel (replicated levels only)
     fuse_from_ = -1;
-    if (std::getenv("TDGL_B200_NO_FUSE") == nullptr)
+    if (cfg_.fuse_coarse == 1 || std::getenv("TDGL_B200_FUSE") != nullptr)
       for (size_t l = 1; l + 1 < L; ++l)
         if (H.levels[l].A.rows <= kFuseBelow && (world_ == 1 || static_cast<int>(l) >= rep_level)) {
           fuse_from_ = static_cast<int>(l);
@@ -574,12 +575,41 @@ void Engine::configure_kernels() {
 #define TDGL_LAUNCH_CHECK()                                                                \
   do { ++launches_; TDGL_CUDA(cudaGetLastError()); } while (0)
 
+// Grid and ring depth of a persistent window kernel: one wave of one-shot CTAs if the matrix
+// is that small, otherwise as many CTAs as are resident at once, each walking
+// ceil(nwin / resident) windows through a 3-stage ring.
+Engine::PersistPlan Engine::persist_plan(const void* kernel, int rows, int win, int cap,
+                                         int bytes_per_nnz) {
+  PersistPlan p;
+  const int nwin = (rows + win - 1) / win;
+  auto resident = [&](int stages) {
+    int nb = 0;
+    TDGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &nb, kernel, win, static_cast<size_t>(stages) * cap * bytes_per_nnz));
+    return std::max(nb, 1) * sm_count_;
+  };
+  if (nwin <= resident(1)) {
+    p.stages = 1;
+    p.grid = nwin;
+  } else {
+    p.stages = 3;
+    while (p.stages > 2 && static_cast<size_t>(p.stages) * cap * bytes_per_nnz > 200u * 1024u) --p.stages;
+    const int res = resident(p.stages);
+    const int per_cta = (nwin + res - 1) / res;
+    p.grid = (nwin + per_cta - 1) / per_cta;
+  }
+  p.smem = static_cast<size_t>(p.stages) * cap * bytes_per_nnz;
+  return p;
+}
+
 template <int OP>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
-  const size_t smem = static_cast<size_t>(A.m.cap) * 12;
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
-  launch_k(kw_real<OP>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
-                                                                   partials_.p, counter_.p);
+  const PersistPlan p = persist_plan(reinterpret_cast<const void*>(&kw_real<OP>), A.m.rows, A.win,
+                                     A.m.cap, 12);
+  WinCsr m = A.m;
+  m.stages = p.stages;
+  launch_k(kw_real<OP>, p.grid, A.win, p.smem, ctl_.p, comm(), m, a, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -1306,6 +1336,7 @@ int tdgl_create(tdgl_handle** out, int64_t n_sites, int64_t n_edges, int64_t n_b
     if (config->running_capacity > 0) cfg.running_capacity = config->running_capacity;
     if (config->world > 0) { cfg.world = config->world; cfg.rank = config->rank; }
     if (config->replicate_below > 0) cfg.replicate_below = config->replicate_below;
+    if (config->fuse_coarse > 0) cfg.fuse_coarse = config->fuse_coarse;
   }
   auto h = std::make_unique<tdgl_handle>();
   try {

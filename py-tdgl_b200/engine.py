@@ -74,7 +74,7 @@ class DeviceEngine:
                  mu_rtol: float = 0.0, mu_max_iter: int = 0, amg_theta: float = 0.0,
                  amg_max_coarse: int = 0, use_graph: int = 0, reorder: int = 0,
                  running_capacity: int = 0, world: int = 1, rank: int = 0,
-                 replicate_below: int = 0):
+                 replicate_below: int = 0, fuse_coarse: int = 0):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         em = mesh.edge_mesh
@@ -104,6 +104,7 @@ class DeviceEngine:
         cfg.world = world
         cfg.rank = rank
         cfg.replicate_below = replicate_below
+        cfg.fuse_coarse = fuse_coarse
         self.world, self.rank = int(world), int(rank)
         self.running_capacity = running_capacity or 4096
         rc = self._lib.tdgl_create(

