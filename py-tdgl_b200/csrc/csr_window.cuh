@@ -29,10 +29,13 @@ constexpr int kWinRows = 256;  // default rows per window (= threads per CTA)
 
 struct WinCsr {
   int rows = 0;
-  int stages = 1;            // shared-memory ring depth of the persistent kernels
   int cap = 0;               // max over windows of the aligned nnz extent (elements)
   const int* ptr = nullptr;  // rows + 1
   const int* idx = nullptr;  // nnz (+4 padding)
+  // per window {first staged nnz (multiple of 4), staged nnz count}: 8 bytes per CTA that stay
+  // L2-resident across launches, so that the bulk copies of a window are issued after one
+  // L2 hit instead of after a DRAM round trip for the two row pointers bounding it
+  const int2* win = nullptr;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -79,11 +82,10 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
                                                uint64_t* bar) {
   griddep_launch_dependents();
   const int r0 = blockIdx.x * blockDim.x;
-  const int r1 = min(r0 + static_cast<int>(blockDim.x), m.rows);
-  const int k0a = __ldg(m.ptr + r0) & ~3;
+  const int2 wd = __ldg(m.win + blockIdx.x);
+  const int k0a = wd.x;
   if (threadIdx.x == 0) {
-    const int k1a = (__ldg(m.ptr + r1) + 3) & ~3;
-    const uint32_t n = static_cast<uint32_t>(k1a - k0a);
+    const uint32_t n = static_cast<uint32_t>(wd.y);
     mbar_init(bar, 1);
     mbar_arrive_expect_tx(bar, n * (SA + SB + 4));
     if (n > 0) {
@@ -171,141 +173,71 @@ struct RealArgs {
 //  kOpPresmooth y = omega D^-1 b ; r = b - A y    (smoothing from a zero guess + residual)
 //  kOpJacobi    y = x + omega D^-1 (b - A x) ;    red = dot(w, y)
 //  kOpPlain     y = A x ;  kOpPlainAdd  y += A x  (restriction / prolongation)
-//
-// Persistent, software-pipelined form: the grid is sized to what is resident at once
-// (SMs x CTAs/SM, see Engine::persist_grid); CTA c walks the windows c, c + grid, c + 2 grid ...
-// through a ring of `m.stages` shared-memory stages.  Thread 0 keeps stages - 1 windows of
-// bulk copies in flight ahead of the one being computed, so the DRAM latency of the matrix
-// stream, the row-pointer round trip that precedes every copy and the fence + atomic of the
-// grid reduction (now once per CTA instead of once per window) are off the critical path.
-template <int SA, int SB>
-__device__ __forceinline__ void pipe_issue(const WinCsr& m, const void* valA, const void* valB,
-                                           unsigned char* stage, uint64_t* bar, int w) {
-  const int r0 = w * static_cast<int>(blockDim.x);
-  const int r1 = min(r0 + static_cast<int>(blockDim.x), m.rows);
-  const int k0a = __ldg(m.ptr + r0) & ~3;
-  const int k1a = (__ldg(m.ptr + r1) + 3) & ~3;
-  const uint32_t n = static_cast<uint32_t>(k1a - k0a);
-  mbar_arrive_expect_tx(bar, n * (SA + SB + 4));
-  if (n > 0) {
-    bulk_g2s(stage, static_cast<const unsigned char*>(valA) + static_cast<size_t>(k0a) * SA,
-             n * SA, bar);
-    if (SB > 0)
-      bulk_g2s(stage + static_cast<size_t>(m.cap) * SA,
-               static_cast<const unsigned char*>(valB) + static_cast<size_t>(k0a) * SB, n * SB, bar);
-    bulk_g2s(stage + static_cast<size_t>(m.cap) * (SA + SB), m.idx + k0a, n * 4, bar);
-  }
-}
-
-constexpr int kMaxStages = 4;
-
-// Ring set-up: initialises the stage barriers and puts the first stages - 1 windows of this
-// CTA in flight.  Ends with __syncthreads().
-template <int SA, int SB>
-__device__ __forceinline__ void pipe_begin(const WinCsr& m, const void* valA, const void* valB,
-                                           unsigned char* smem, uint64_t* bars, int nwin) {
-  griddep_launch_dependents();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < m.stages; ++s) mbar_init(bars + s, 1);
-    const size_t stage_bytes = static_cast<size_t>(m.cap) * (SA + SB + 4);
-    for (int p = 0; p < m.stages - 1; ++p) {
-      const int w = blockIdx.x + p * gridDim.x;
-      if (w < nwin) pipe_issue<SA, SB>(m, valA, valB, smem + p * stage_bytes, bars + p, w);
-    }
-  }
-  __syncthreads();
-}
-
 template <int OP>
 __global__ void __launch_bounds__(kWinRows)
 kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned int* counter) {
   extern __shared__ __align__(128) unsigned char win_smem[];
-  __shared__ uint64_t bars[kMaxStages];
+  __shared__ uint64_t bar;
   __shared__ double red[32];
-  const int W = blockDim.x;
-  const int nwin = (m.rows + W - 1) / W;
-  const int S = m.stages;
-  const size_t stage_bytes = static_cast<size_t>(m.cap) * 12;
-  pipe_begin<8, 0>(m, a.val, nullptr, win_smem, bars, nwin);
+  const WinRow w = window_stage<8, 0>(m, a.val, nullptr, win_smem, &bar);
+  const double* sv = reinterpret_cast<const double*>(win_smem);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 8);
   griddep_wait();
   const bool live = (ctl->status == 0);
-  double d = 0.0;
-  int it = 0;
-  for (int w = blockIdx.x; w < nwin; w += gridDim.x, ++it) {
-    const int s = it % S;
-    if (threadIdx.x == 0) {
-      // refill the stage the previous iteration consumed
-      const int wn = w + (S - 1) * gridDim.x;
-      if (S > 1 && wn < nwin) {
-        const int sn = (it + S - 1) % S;
-        pipe_issue<8, 0>(m, a.val, nullptr, win_smem + sn * stage_bytes, bars + sn, wn);
-      } else if (S == 1) {
-        pipe_issue<8, 0>(m, a.val, nullptr, win_smem, bars, w);
-      }
-    }
-    const int row = w * W + threadIdx.x;
-    const bool in = live && row < m.rows;
-    const int k0a = __ldg(m.ptr + w * W) & ~3;
-    int kb = 0, ke = 0;
-    // row-local operands travel while the window lands
-    double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
-    if (in) {
-      kb = __ldg(m.ptr + row) - k0a;
-      ke = __ldg(m.ptr + row + 1) - k0a;
-      if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi) bi = a.b[row];
-      if (OP == kOpPresmooth || OP == kOpJacobi) di = a.dinv[row];
-      if (OP == kOpSpmvDot || OP == kOpJacobi) xi = a.x[row];
-      if (OP == kOpPlainAdd) xi = a.y[row];
-      if (OP == kOpJacobi && a.w != nullptr) wi = a.w[row];
-    }
-    const double* sv = reinterpret_cast<const double*>(win_smem + s * stage_bytes);
-    const int* si = reinterpret_cast<const int*>(win_smem + s * stage_bytes + static_cast<size_t>(m.cap) * 8);
-    mbar_wait(bars + s, static_cast<uint32_t>((it / S) & 1));
-    if (in) {
-      double sum;
-      if (OP == kOpPresmooth) {
-        // x_j = omega dinv_j b_j on the fly
-        sum = 0.0;
-        const int last = ke - 1;
-        for (int k = kb; k < ke; k += 2) {
-          const int k1 = min(k + 1, last);
-          const int j0 = si[k], j1 = si[k1];
-          const double t0 = __ldg(a.dinv + j0) * __ldg(a.b + j0);
-          const double t1 = __ldg(a.dinv + j1) * __ldg(a.b + j1);
-          sum = fma(sv[k], a.omega * t0, sum);
-          sum = fma((k + 1 < ke) ? sv[k1] : 0.0, a.omega * t1, sum);
-        }
-      } else {
-        sum = row_dot(sv, si, kb, ke, a.x);
-      }
-      if (OP == kOpSpmvDot) {
-        a.y[row] = sum;
-        d += sum * xi;
-      } else if (OP == kOpResidual) {
-        const double ri = bi - sum;
-        a.y[row] = ri;
-        d += ri * ri;
-      } else if (OP == kOpPresmooth) {
-        a.y[row] = a.omega * di * bi;
-        a.r[row] = bi - sum;
-      } else if (OP == kOpJacobi) {
-        const double yi = xi + a.omega * di * (bi - sum);
-        a.y[row] = yi;
-        d += wi * yi;
-      } else if (OP == kOpPlain) {
-        a.y[row] = sum;
-      } else {
-        a.y[row] = xi + sum;
-      }
-    }
-    __syncthreads();  // every thread is done with stage s before it is refilled
+  const bool in = live && w.row < m.rows;
+  // row-local operands travel while the window lands
+  double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
+  if (in) {
+    if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi) bi = a.b[w.row];
+    if (OP == kOpPresmooth || OP == kOpJacobi) di = a.dinv[w.row];
+    if (OP == kOpSpmvDot || OP == kOpJacobi) xi = a.x[w.row];
+    if (OP == kOpPlainAdd) xi = a.y[w.row];
+    if (OP == kOpJacobi && a.w != nullptr) wi = a.w[w.row];
   }
+  mbar_wait(&bar, 0);
   if (!live) return;
+  double d = 0.0;
+  if (in) {
+    double s;
+    if (OP == kOpPresmooth) {
+      // x_j = omega dinv_j b_j on the fly
+      s = 0.0;
+      const int last = w.ke - 1;
+      for (int k = w.kb; k < w.ke; k += 2) {
+        const int k1 = min(k + 1, last);
+        const int j0 = si[k], j1 = si[k1];
+        const double t0 = __ldg(a.dinv + j0) * __ldg(a.b + j0);
+        const double t1 = __ldg(a.dinv + j1) * __ldg(a.b + j1);
+        s = fma(sv[k], a.omega * t0, s);
+        s = fma((k + 1 < w.ke) ? sv[k1] : 0.0, a.omega * t1, s);
+      }
+    } else {
+      s = row_dot(sv, si, w.kb, w.ke, a.x);
+    }
+    if (OP == kOpSpmvDot) {
+      a.y[w.row] = s;
+      d = s * xi;
+    } else if (OP == kOpResidual) {
+      const double ri = bi - s;
+      a.y[w.row] = ri;
+      d = ri * ri;
+    } else if (OP == kOpPresmooth) {
+      a.y[w.row] = a.omega * di * bi;
+      a.r[w.row] = bi - s;
+    } else if (OP == kOpJacobi) {
+      const double yi = xi + a.omega * di * (bi - s);
+      a.y[w.row] = yi;
+      d = wi * yi;
+    } else if (OP == kOpPlain) {
+      a.y[w.row] = s;
+    } else {
+      a.y[w.row] = xi + s;
+    }
+  }
   if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
-    const double bs = block_sum(d, red);
-    double total;
-    if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
-      total = __shfl_sync(0xffffffffu, total, 0);
+    double total = block_sum(d, red);
+    if (threadIdx.x >= 32) return;  // the tail is warp 0's business: free the other warps' slots
+    if (grid_sum_last_warp(&total, 1, partials, counter)) {
       if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       if (threadIdx.x == 0) *a.red_out = total;
     }
@@ -397,7 +329,6 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double red[32];
-  __shared__ int s_last;
   const WinRow w = window_stage<16, 8>(m, lval, aval, win_smem, &bar);
   const double2* sl = reinterpret_cast<const double2*>(win_smem);
   const double* sa = reinterpret_cast<const double*>(win_smem + static_cast<size_t>(m.cap) * 16);
@@ -429,37 +360,15 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
     drr = ri * ri;
   }
   // two sums through one deterministic reduction
-  const double sb = block_sum(dbb, red);
-  const double sr = block_sum(drr, red);
-  if (threadIdx.x == 0) {
-    partials[2 * blockIdx.x] = sb;
-    partials[2 * blockIdx.x + 1] = sr;
-    __threadfence();
-    const unsigned int t = atomicAdd(counter, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    double a0 = 0.0, a1 = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-      a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
-      a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
-    }
-    a0 = block_sum(a0, red);
-    a1 = block_sum(a1, red);
-    if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0
-      if (comm != nullptr) {
-        double v[2] = {a0, a1};
-        comm_allreduce(ctl, comm, v, 2, false);
-        a0 = v[0];
-        a1 = v[1];
-      }
-      if (threadIdx.x == 0) {
-        ctl->bb = a0;
-        ctl->rr = a1;
-        *counter = 0u;
-      }
+  double v[2];
+  v[0] = block_sum(dbb, red);
+  v[1] = block_sum(drr, red);
+  if (threadIdx.x >= 32) return;
+  if (grid_sum_last_warp(v, 2, partials, counter)) {
+    if (comm != nullptr) comm_allreduce(ctl, comm, v, 2, false);
+    if (threadIdx.x == 0) {
+      ctl->bb = v[0];
+      ctl->rr = v[1];
     }
   }
 }

@@ -81,8 +81,9 @@ struct DevCsr {
   int rows = 0, cols = 0, win = kWinRows, cap = 0;
   int64_t nnz = 0;
   DevBuf<int> ptr, idx;   // idx / val carry 4 padding elements (see csr_window.cuh)
+  DevBuf<int2> wdesc;     // per window {first staged nnz, staged nnz count}
   DevBuf<double> val;
-  CsrView view() const { return CsrView{WinCsr{rows, 1, cap, ptr.p, idx.p}, val.p, win}; }
+  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p, wdesc.p}, val.p, win}; }
 };
 
 struct DevLevel {
@@ -106,6 +107,18 @@ inline int window_cap(const std::vector<int32_t>& ptr, int64_t rows, int win) {
     cap = std::max(cap, ((ptr[r1] + 3) & ~3) - (ptr[r0] & ~3));
   }
   return cap;
+}
+
+// {first staged nnz, staged nnz count} of every window of `win` rows.
+inline std::vector<int2> window_descriptors(const std::vector<int32_t>& ptr, int64_t rows, int win) {
+  std::vector<int2> d;
+  for (int64_t r0 = 0; r0 < rows; r0 += win) {
+    const int64_t r1 = std::min<int64_t>(r0 + win, rows);
+    const int k0a = ptr[r0] & ~3, k1a = (ptr[r1] + 3) & ~3;
+    d.push_back(make_int2(k0a, k1a - k0a));
+  }
+  if (d.empty()) d.push_back(make_int2(0, 0));
+  return d;
 }
 
 // Rows per window: as many as fit `budget` bytes of shared memory at `bytes_per_nnz`.
@@ -213,6 +226,7 @@ class Engine {
 
   // ---- site operators (shared structure) --------------------------------------------------
   DevBuf<int> ptr_, idx_, eidx_;
+  DevBuf<int2> wdesc0_;
   DevBuf<signed char> head_;
   DevBuf<double2> lval_;           // covariant Laplacian values (all rows kept)
   DevBuf<unsigned char> fixed_;    // rows the reference replaces by identity
@@ -270,9 +284,7 @@ class Engine {
     TDGL_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
   }
   static int grid_win(int rows, int win) { return (rows + win - 1) / win; }
-  WinCsr site_csr() const { return WinCsr{N_, 1, cap0_, ptr_.p, idx_.p}; }
-  struct PersistPlan { int grid = 1, stages = 1; size_t smem = 0; };
-  PersistPlan persist_plan(const void* kernel, int rows, int win, int cap, int bytes_per_nnz);
+  WinCsr site_csr() const { return WinCsr{N_, cap0_, ptr_.p, idx_.p, wdesc0_.p}; }
   int sm_count_ = 148;
   template <int OP>
   void launch_real(const CsrView& A, const RealArgs& a);

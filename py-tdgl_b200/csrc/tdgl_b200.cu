@@ -53,6 +53,8 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
   d.ptr.upload(h.ptr, stream_);
   d.idx.upload(idx, stream_);
   d.val.upload(val, stream_);
+  const std::vector<int2> wd = window_descriptors(h.ptr, h.rows, d.win);
+  d.wdesc.upload(wd, stream_);
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -241,6 +243,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
 
   // ---- uploads --------------------------------------------------------------------------
   ptr_.upload(lptr, stream_);
+  {
+    const std::vector<int2> wd = window_descriptors(lptr, N_, win0_);
+    wdesc0_.upload(wd, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
   idx_.upload(lnbr, stream_);
   eidx_.upload(ledge, stream_);
   head_.upload(lhead, stream_);
@@ -506,6 +513,7 @@ void Engine::comm_connect_local(Engine* const* engines) {
   if (world_ == 1) return;
   TDGL_CUDA(cudaSetDevice(cfg_.device));
   double* peers[kMaxWorld] = {};
+  bool same_device = false;
   for (int q = 0; q < world_; ++q) {
     Engine* e = engines[q];
     if (e == nullptr || e->world_ != world_ || e->rank_ != q || e->Ng_ != Ng_)
@@ -516,9 +524,24 @@ void Engine::comm_connect_local(Engine* const* engines) {
       cudaGetLastError();
     }
     peers[q] = e->arena_.p;
+    if (q != rank_ && e->cfg_.device == cfg_.device) same_device = true;
   }
   upload_comm(peers);
-  comm_on_ = connected_ = true;
+  connected_ = true;
+  if (same_device && pdl_) {
+    // Shards that share one GPU wait for each other inside kernels; an early-launched
+    // (PDL) successor would hold the SM resources its peer's kernel needs.  Re-record the
+    // graph with ordinary launches.
+    pdl_ = false;
+    if (graph_mode_ == 1) {
+      cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
+      cudaGraphDestroy(graph_); graph_ = nullptr;
+      h_step_ = h_psi_ = h_cg_ = 0;
+      comm_on_ = true;
+      build_graph();
+    }
+  }
+  comm_on_ = true;
 }
 
 void Engine::shard_info(int64_t* out, int n) {
@@ -575,41 +598,12 @@ void Engine::configure_kernels() {
 #define TDGL_LAUNCH_CHECK()                                                                \
   do { ++launches_; TDGL_CUDA(cudaGetLastError()); } while (0)
 
-// Grid and ring depth of a persistent window kernel: one wave of one-shot CTAs if the matrix
-// is that small, otherwise as many CTAs as are resident at once, each walking
-// ceil(nwin / resident) windows through a 3-stage ring.
-Engine::PersistPlan Engine::persist_plan(const void* kernel, int rows, int win, int cap,
-                                         int bytes_per_nnz) {
-  PersistPlan p;
-  const int nwin = (rows + win - 1) / win;
-  auto resident = [&](int stages) {
-    int nb = 0;
-    TDGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &nb, kernel, win, static_cast<size_t>(stages) * cap * bytes_per_nnz));
-    return std::max(nb, 1) * sm_count_;
-  };
-  if (nwin <= resident(1)) {
-    p.stages = 1;
-    p.grid = nwin;
-  } else {
-    p.stages = 3;
-    while (p.stages > 2 && static_cast<size_t>(p.stages) * cap * bytes_per_nnz > 200u * 1024u) --p.stages;
-    const int res = resident(p.stages);
-    const int per_cta = (nwin + res - 1) / res;
-    p.grid = (nwin + per_cta - 1) / per_cta;
-  }
-  p.smem = static_cast<size_t>(p.stages) * cap * bytes_per_nnz;
-  return p;
-}
-
 template <int OP>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
+  const size_t smem = static_cast<size_t>(A.m.cap) * 12;
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
-  const PersistPlan p = persist_plan(reinterpret_cast<const void*>(&kw_real<OP>), A.m.rows, A.win,
-                                     A.m.cap, 12);
-  WinCsr m = A.m;
-  m.stages = p.stages;
-  launch_k(kw_real<OP>, p.grid, A.win, p.smem, ctl_.p, comm(), m, a, partials_.p, counter_.p);
+  launch_k(kw_real<OP>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
+           partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
