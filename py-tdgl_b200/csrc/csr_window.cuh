@@ -235,9 +235,10 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
     }
   }
   if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
-    double total = block_sum(d, red);
-    if (threadIdx.x >= 32) return;  // the tail is warp 0's business: free the other warps' slots
-    if (grid_sum_last_warp(&total, 1, partials, counter)) {
+    const double bs = block_sum(d, red);
+    double total;
+    if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
+      total = __shfl_sync(0xffffffffu, total, 0);
       if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       if (threadIdx.x == 0) *a.red_out = total;
     }
@@ -329,6 +330,7 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double red[32];
+  __shared__ int s_last;
   const WinRow w = window_stage<16, 8>(m, lval, aval, win_smem, &bar);
   const double2* sl = reinterpret_cast<const double2*>(win_smem);
   const double* sa = reinterpret_cast<const double*>(win_smem + static_cast<size_t>(m.cap) * 16);
@@ -360,15 +362,37 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
     drr = ri * ri;
   }
   // two sums through one deterministic reduction
-  double v[2];
-  v[0] = block_sum(dbb, red);
-  v[1] = block_sum(drr, red);
-  if (threadIdx.x >= 32) return;
-  if (grid_sum_last_warp(v, 2, partials, counter)) {
-    if (comm != nullptr) comm_allreduce(ctl, comm, v, 2, false);
-    if (threadIdx.x == 0) {
-      ctl->bb = v[0];
-      ctl->rr = v[1];
+  const double sb = block_sum(dbb, red);
+  const double sr = block_sum(drr, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = sb;
+    partials[2 * blockIdx.x + 1] = sr;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
+      a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
+    }
+    a0 = block_sum(a0, red);
+    a1 = block_sum(a1, red);
+    if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0
+      if (comm != nullptr) {
+        double v[2] = {a0, a1};
+        comm_allreduce(ctl, comm, v, 2, false);
+        a0 = v[0];
+        a1 = v[1];
+      }
+      if (threadIdx.x == 0) {
+        ctl->bb = a0;
+        ctl->rr = a1;
+        *counter = 0u;
+      }
     }
   }
 }

@@ -129,33 +129,6 @@ __device__ __forceinline__ bool grid_sum_last(double partial, double* partials,
   return true;
 }
 
-// The same reduction run by warp 0 alone (call with all 32 lanes of warp 0, after block_sum,
-// which leaves the block's partial in every lane of warp 0): the other warps of the CTA can
-// exit right away, so their thread slots are free for the next CTA while this one pays the
-// fence + atomic round trip.  v[0..n) in: the block's partials; out (last block only, return
-// value true): the grid totals, added in block order.  n <= 2.
-__device__ __forceinline__ bool grid_sum_last_warp(double* v, int n, double* partials,
-                                                   unsigned int* counter) {
-  const int lane = threadIdx.x & 31;
-  int last = 0;
-  if (lane == 0) {
-    for (int k = 0; k < n; ++k) partials[n * blockIdx.x + k] = v[k];
-    __threadfence();
-    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return false;
-  __threadfence();
-  for (int k = 0; k < n; ++k) {
-    double acc = 0.0;
-    for (unsigned int i = lane; i < gridDim.x; i += 32)
-      acc += reinterpret_cast<volatile double*>(partials)[n * i + k];
-    v[k] = warp_sum(acc);
-  }
-  if (lane == 0) *counter = 0u;
-  return true;
-}
-
 #define TDGL_COND_ARG cudaGraphConditionalHandle
 
 __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
