@@ -23,10 +23,17 @@ b200 arm
           box's host cores (N=1 only; bounded number of steps of the same workload).
 reference arm (--impl reference): that CPU path alone, same workload/metric.
 
-With N > 1 ranks (torchrun) the workload's mesh is domain-decomposed over the N GPUs
-(--mode shard, default: one shard per rank, halo exchange + all-reduces as device code over
-NVLink peer memory, "scaling": "strong": the same mesh, N times the hardware), or every rank
-steps a full replica (--mode replicas, "scaling": "weak", no data-path exchange).
+The metric is BASELINE.json's "TDGL time-steps/sec (and mesh-sites x steps/sec)": `value` is
+site-steps/s (sites of the mesh x steps/s), which is comparable across mesh sizes; steps/s is
+reported next to it (`steps_per_sec`).
+
+With N > 1 ranks (torchrun) the mesh is domain-decomposed over the N GPUs (one shard per
+rank; halo exchange + all-reduces are device code on NVLink peer memory):
+  --mode weak (default)  the workload is BASELINE.json's configuration for N GPUs — ~1M sites
+                         per GPU: 2M film + holes + transport at N=2, 4M transport strip at
+                         N=4, 10M film in a field at N=8 — "scaling": "weak";
+  --mode strong          the N=1 workload (or --workload) on N GPUs, "scaling": "strong";
+  --mode replicas        every rank steps its own replica of the N=1 workload (no exchange).
 """
 from __future__ import annotations
 
@@ -57,6 +64,12 @@ WORKLOADS = {
     "film250k_field": dict(
         width=200.0, height=200.0, h=0.43, b=0.1, holes=(), terminals=False, current=0.0,
         opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    # the configs[2] film at twice the area (2 GPUs)
+    "film2m_holes_transport": dict(
+        width=566.0, height=566.0, h=0.4225, b=0.0,
+        holes=((141.5, 141.5, 28.3), (-141.5, 141.5, 28.3), (141.5, -141.5, 28.3),
+               (-141.5, -141.5, 28.3)),
+        terminals=True, current=113.2, opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
     # BASELINE.json configs[3]: long strip with transport current (4 GPUs)
     "strip4m_transport": dict(
         width=3200.0, height=200.0, h=0.4225, b=0.0, holes=(), terminals=True, current=40.0,
@@ -89,6 +102,14 @@ def _mesh_from_arrays(g):
     em = EdgeMesh(g["centers"], g["edges"], g["boundary_edge_indices"], g["directions"],
                   g["edge_lengths"], g["dual_edge_lengths"])
     return Mesh(g["sites"], g["elements"], g["boundary_indices"], areas=g["areas"], edge_mesh=em)
+
+
+def auto_workload(n_gpus: int, mode: str) -> str:
+    """BASELINE.json's configuration for this GPU count (weak mode) or the 1-GPU one."""
+    if mode != "weak" or n_gpus == 1:
+        return "film1m_holes_transport"
+    return {2: "film2m_holes_transport", 4: "strip4m_transport", 8: "film10m_field"}.get(
+        n_gpus, "film4m_field")
 
 
 def build_workload(name: str, rank: int = 0, barrier=None):
@@ -251,25 +272,34 @@ def threads_used() -> int:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    work = build_workload(args.workload)
+    # The SuperLU factorisation of the reference's path needs ~10 GB and 25-40 s per million
+    # sites (fill grows faster than linearly): the multi-GPU configurations are sampled by
+    # their 1-GPU sibling (~1M sites); site-steps/s is what carries over.
+    sampled = args.workload not in ("film1m_holes_transport", "film250k_field", "film20_cpu")
+    name = "film1m_holes_transport" if sampled else args.workload
+    work = build_workload(name)
     n = len(work["mesh"].sites)
     res = cpu_path(work, args.steps, min(args.warmup, 3), budget_s=args.cpu_budget)
     ncores = os.cpu_count()
-    sample = (f"{res['steps']} of the {args.steps} requested steps of the full {n}-site workload"
-              f" (time budget {args.cpu_budget:.0f} s; SuperLU factorisation"
+    sample = (f"{res['steps']} of the {args.steps} requested steps of the {n}-site workload {name}"
+              + (f" standing in for {args.workload}" if sampled else "")
+              + f" (time budget {args.cpu_budget:.0f} s; SuperLU factorisation"
               f" {res['factor_seconds']:.1f} s and mesh build excluded)")
+    value = res["steps_per_s"] * n
     line = {
-        "impl": "reference", "metric": "tdgl_steps_per_sec", "value": res["steps_per_s"],
-        "unit": "steps/s", "n_gpus": args.gpus, "steps": res["steps"],
+        "impl": "reference", "metric": "tdgl_site_steps_per_sec", "value": value,
+        "unit": "site-steps/s", "n_gpus": args.gpus, "steps": res["steps"],
         "steps_requested": args.steps, "warmup": min(args.warmup, 3),
-        "ms_per_step": 1e3 / res["steps_per_s"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 / res["steps_per_s"], "higher_is_better": True,
+        "scaling": "strong" if args.mode == "strong" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sites": n,
-                   "edges": len(work["mesh"].edge_mesh.edges)},
-        "site_steps_per_sec": res["steps_per_s"] * n,
-        "cpu_baseline": {"value": res["steps_per_s"], "unit": "steps/s", "cores": threads_used(),
+        "config": {"workload": args.workload, "sampled_by": name if sampled else None,
+                   "sites": n, "edges": len(work["mesh"].edge_mesh.edges)},
+        "steps_per_sec": res["steps_per_s"],
+        "cpu_baseline": {"value": value, "unit": "site-steps/s",
+                         "steps_per_sec": res["steps_per_s"], "cores": threads_used(),
                          "host_cores": ncores, "kind": "port", "sample": sample},
-        "e2e": {"value": res["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0,
+        "e2e": {"value": value, "unit": "site-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -296,7 +326,7 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    shard = world > 1 and args.mode == "shard"
+    shard = world > 1 and args.mode != "replicas"
     work = build_workload(args.workload, rank, barrier if world > 1 else None)
     mesh = work["mesh"]
     n, n_edges = len(mesh.sites), len(mesh.edge_mesh.edges)
@@ -342,7 +372,7 @@ def run_b200(args, rank, world, local_rank):
     psi_h[:] = p0
     mu_h[:] = m0
     state = {"step": b.step, "time": b.time, "dt": b.dt}
-    Ke = K
+    Ke = K if n <= 2_500_000 else min(K, 40)   # (whole-mesh host copies every step)
     for phase in ("warm", "timed"):
         nsteps = 2 if phase == "warm" else Ke
         barrier()
@@ -393,9 +423,10 @@ def run_b200(args, rank, world, local_rank):
                 "traffic": None, "kernels": table, "vcycle_ms": vc_ms}
 
     line = {
-        "metric": "tdgl_steps_per_sec", "value": steps_per_s, "unit": "steps/s",
+        "metric": "tdgl_site_steps_per_sec", "value": steps_per_s * n, "unit": "site-steps/s",
+        "steps_per_sec": steps_per_s,
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "strong" if shard else "weak",
+        "higher_is_better": True, "scaling": "strong" if args.mode == "strong" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "sites": n, "edges": n_edges,
                    "nnz_rank0": nnz,
@@ -407,11 +438,11 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "operators (>= 230 MB at 1M sites) exceed the 126 MB L2; per-kernel"
                          " roofline timings flush L2 before every launch",
                    "mu_rtol": opts.mu_rtol, "amg_levels": levels},
-        "site_steps_per_sec": steps_per_s * n,
         "mu_iterations_per_step": iters_per_step, "retries": b.retries,
         "setup_seconds": {"mesh": work["mesh_seconds"], "engine": setup_s},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": e2e_steps_per_s * n, "unit": "site-steps/s",
+                "steps_per_sec": e2e_steps_per_s, "steps": Ke, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "TDGLSolver.update (pinned host arrays)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -419,7 +450,8 @@ def run_b200(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         res = cpu_path(work, args.cpu_steps, 1, budget_s=args.cpu_budget)
         line["cpu_baseline"] = {
-            "value": res["steps_per_s"], "unit": "steps/s", "cores": threads_used(),
+            "value": res["steps_per_s"] * n, "unit": "site-steps/s",
+            "steps_per_sec": res["steps_per_s"], "cores": threads_used(),
             "host_cores": os.cpu_count(), "kind": "port",
             "sample": (f"{res['steps']} steps of the same {n}-site workload from the same initial"
                        f" state (SuperLU factorisation {res['factor_seconds']:.1f} s and mesh"
@@ -435,14 +467,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="film1m_holes_transport", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--cpu-budget", type=float, default=60.0,
                     help="seconds of CPU stepping allowed for the cpu baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
-                    help="N > 1: domain-decompose the mesh over the ranks (default) or run one"
-                         " replica of the workload per rank")
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong", "replicas"],
+                    help="N > 1: domain decomposition of BASELINE.json's config for N GPUs"
+                         " (weak, default), of the 1-GPU workload (strong), or replicas")
     ap.add_argument("--no-graph", action="store_true",
                     help="host-driven launches instead of the device-side-loop CUDA graph"
                          " (profiler runs: every kernel is an ordinary launch)")
@@ -452,6 +484,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")
+    if args.workload == "auto":
+        args.workload = auto_workload(max(world, args.gpus), args.mode)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -32,9 +32,13 @@ def run(e):
 with DeviceEngine(c.mesh, gamma=c.gamma, u=c.u, use_graph=graph, running_capacity=steps) as e1:
     i1, (p1, m1) = run(e1)
 print("single", i1, flush=True)
-with LocalShardGroup(c.mesh, world, gamma=c.gamma, u=c.u, use_graph=graph,
+devs = os.environ.get("SHARD_DEVICES")
+devs = [int(d) for d in devs.split(",")] if devs else None
+with LocalShardGroup(c.mesh, world, devices=devs, gamma=c.gamma, u=c.u, use_graph=graph,
                      running_capacity=steps) as grp:
     print("shards", grp.shard_info(), flush=True)
     iw, (pw, mw) = run(grp)
 print("sharded", iw, flush=True)
+print(f"per step: single {i1.device_ms / steps * 1e3:.0f} us, sharded {iw.device_ms / steps * 1e3:.0f} us;"
+      f" {iw.mu_iterations / steps:.1f} CG iterations/step", flush=True)
 print("diff", orc.compare(dict(psi=pw, mu=mw), dict(psi=p1, mu=m1), c.mesh.areas))
