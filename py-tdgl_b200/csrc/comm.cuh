@@ -11,11 +11,12 @@
 // number it expects: data and arrival flag are the same write, so there is no
 // fence + flag round trip — the cost of an exchange is one NVLink traversal.
 //
-//   halo exchange  k_halo_exchange (one CTA): scatters the rank's boundary entries into the
-//                  neighbours' mailboxes, then polls its own mailbox and unpacks it into the
-//                  halo slots of the vector.  Mailboxes are per level and double-buffered by
-//                  the parity of the per-level sequence number: a neighbour can be at most
-//                  one exchange of that level ahead (it needs this rank's data to go on).
+//   halo exchange  there is no exchange kernel.  A kernel that produces a vector stores
+//                  its boundary rows into the neighbours' mailboxes as it computes them
+//                  (push_row); a kernel that gathers from a vector reads halo columns out of
+//                  its own mailbox (halo_get), polling only for the entries it needs — CTAs
+//                  that touch no halo column never wait, so the NVLink latency overlaps
+//                  the interior of the subdomain.
 //   all-reduce     comm_allreduce, called by ONE warp (in the last block of a reducing kernel
 //                  or in a controller kernel): lane q stores the partial into rank q's
 //                  mailbox and polls this rank's mailbox for rank q's partial; the partials
@@ -36,7 +37,6 @@ constexpr int kMaxLevels = 24;
 struct Comm {
   int rank = 0, world = 1;
   unsigned int rseq = 0;               // all-reduce sequence number (device mutated)
-  unsigned int lseq[kMaxLevels] = {};  // halo-exchange sequence number per level
   unsigned long long* peer[kMaxWorld] = {};  // arena base of every rank as mapped here
 };
 
@@ -149,97 +149,127 @@ __device__ __forceinline__ void comm_allreduce(Ctl* ctl, Comm* c, double* v, int
   if (lane == 0) c->rseq = s;
 }
 
-// One exchange of one vector on one level, as seen by one rank.
-struct ExchArgs {
-  int level = 0;
-  int nnbr = 0;
-  int n_owned = 0;                      // halo slots of the vector start here
-  int n_halo = 0;                       // entries to receive
-  int nbr[kMaxWorld - 1] = {};          // ranks exchanged with: everyone this rank sends to or
-                                        // receives from (a symmetric relation); each pair also
-                                        // swaps one "present" word per exchange, so that neither
-                                        // side can run more than one exchange of the level ahead
-  int send_begin[kMaxWorld] = {};       // ranges of send_idx per neighbour
-  long long dst_word[2][kMaxWorld - 1] = {};  // the neighbour's mailbox of the level, per parity
-  int dst_entry[kMaxWorld - 1] = {};    // first halo entry there that this rank fills
-  long long ack_word[2][kMaxWorld - 1] = {};  // this rank's "present" word on the neighbour
-  long long box_word[2] = {};           // this rank's mailbox of the level, per parity
-  long long box_ack[2] = {};            // the neighbours' "present" words in it (indexed by rank)
-  const int* send_idx = nullptr;        // local owned indices
+// ---- tags ------------------------------------------------------------------------------------
+// A mailbox word is valid for a consumer when its tag equals the tag the consumer expects.
+// Tags are derived from counters of the control block that are identical on all ranks and
+// constant while the kernels that use them run, so nothing has to be signalled:
+//   kTagIter      (solve_epoch, cg_it)      vectors of the V-cycle / CG of iteration cg_it
+//   kTagIterNext  (solve_epoch, cg_it + 1)  the residual k_cg_update leaves for the next one
+//   kTagIter0     (solve_epoch, 0)          the residual the rhs kernel leaves for iteration 0
+//   kTagPsiNew    psi_epoch + 1             psi written by the current attempt of the psi step
+//   kTagPsiCur    psi_tag[cur]              the accepted psi
+//   kTagMu        solve_epoch               mu of this step's solve (after the gauge shift)
+//   kTagMuPrev    solve_epoch - 1           mu of the previous step (read by the rhs kernel)
+// Each channel's mailbox is double-buffered by tag parity; between two stores into the same
+// buffer lies at least one all-reduce that every rank has passed, so its readers are done.
+enum : int { kTagIter = 0, kTagIterNext, kTagIter0, kTagPsiNew, kTagPsiCur, kTagMu, kTagMuPrev };
+
+__device__ __forceinline__ unsigned int comm_tag(const Ctl* ctl, int mode) {
+  const unsigned int s = static_cast<unsigned int>(ctl->solve_epoch) << 10;
+  switch (mode) {
+    case kTagIter: return s | (static_cast<unsigned int>(ctl->cg_it) & 1023u);
+    case kTagIterNext: return s | ((static_cast<unsigned int>(ctl->cg_it) + 1u) & 1023u);
+    case kTagIter0: return s;
+    case kTagPsiNew: return static_cast<unsigned int>(ctl->psi_epoch) + 1u;
+    case kTagPsiCur: return static_cast<unsigned int>(ctl->psi_tag[ctl->cur]);
+    case kTagMu: return static_cast<unsigned int>(ctl->solve_epoch);
+    default: return static_cast<unsigned int>(ctl->solve_epoch) - 1u;
+  }
+}
+
+// ---- producer side: boundary rows go straight into the peers' mailboxes ------------------------
+struct PushArgs {
+  const unsigned char* bnd = nullptr;  // per 32 rows: any of them is sent somewhere (null: off)
+  const int* rptr = nullptr;           // per row: range of `ent`
+  const int2* ent = nullptr;           // {peer rank, halo entry on that peer}
+  long long box[2][kMaxWorld] = {};    // the channel's mailbox on every peer, per parity (words)
+  int tag_mode = 0;
 };
 
-// T = double (W = 2 mailbox words per entry) or double2 (W = 4); the level-0 mailbox is laid
-// out with 4 words per entry, coarser ones with 2 (shard.h: ll_words).
 template <typename T>
-__device__ __forceinline__ void halo_exchange_body(Ctl* ctl, Comm* c, const ExchArgs& a,
-                                                   T* __restrict__ vec) {
+__device__ __forceinline__ void push_row(const Comm* c, const PushArgs& p, unsigned int tag,
+                                         int row, T v) {
+  if (p.bnd == nullptr || !p.bnd[row >> 5]) return;   // uniform per warp
   constexpr int W = sizeof(T) / 4;
-  unsigned int s = c->lseq[a.level] + 1u;
-  if (s == 0u) s = 1u;
-  const int par = static_cast<int>(s & 1u);
-  for (int j = 0; j < a.nnbr; ++j) {
-    unsigned long long* dst = c->peer[a.nbr[j]] + a.dst_word[par][j] +
-                              static_cast<long long>(a.dst_entry[j]) * W;
-    const int b = a.send_begin[j], e = a.send_begin[j + 1];
-    for (int k = b + threadIdx.x; k < e; k += blockDim.x) {
-      const T v = vec[a.send_idx[k]];
-      const double* d = reinterpret_cast<const double*>(&v);
+  const double* d = reinterpret_cast<const double*>(&v);
+  const int par = static_cast<int>(tag & 1u);
+  for (int k = __ldg(p.rptr + row), ke = __ldg(p.rptr + row + 1); k < ke; ++k) {
+    const int2 e = __ldg(p.ent + k);
+    unsigned long long* dst = c->peer[e.x] + p.box[par][e.x] + static_cast<long long>(e.y) * W;
 #pragma unroll
-      for (int w = 0; w < W / 2; ++w) st_f64(dst + static_cast<long long>(k - b) * W + 2 * w, d[w], s);
-    }
+    for (int w = 0; w < W / 2; ++w) st_f64(dst + 2 * w, d[w], tag);
   }
-  if (threadIdx.x < a.nnbr)
-    st_word(c->peer[a.nbr[threadIdx.x]] + a.ack_word[par][threadIdx.x], 0u, s);
-  const unsigned long long* box = c->peer[c->rank] + a.box_word[par];
-  bool ok = true;
-  if (threadIdx.x < a.nnbr)
-    poll_word(ctl, c->peer[c->rank] + a.box_ack[par] + a.nbr[threadIdx.x], s, &ok);
-  // receive: four entries per thread in flight (first-try loads issued back to back), then
-  // only the entries whose words have not landed yet are polled again
-  constexpr int P = W / 2;  // 16-byte pairs per entry
-  for (int h0 = threadIdx.x; h0 < a.n_halo && ok; h0 += 4 * blockDim.x) {
-    unsigned long long lo[4][P], hi[4][P];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int h = h0 + u * blockDim.x;
-      if (h < a.n_halo) {
-#pragma unroll
-        for (int w = 0; w < P; ++w) ld_pair(box + static_cast<long long>(h) * W + 2 * w, &lo[u][w], &hi[u][w]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int h = h0 + u * blockDim.x;
-      if (h < a.n_halo) {
-        T v;
-        double* d = reinterpret_cast<double*>(&v);
-#pragma unroll
-        for (int w = 0; w < P; ++w)
-          d[w] = pair_ready(lo[u][w], hi[u][w], s)
-                     ? pair_value(lo[u][w], hi[u][w])
-                     : poll_f64(ctl, box + static_cast<long long>(h) * W + 2 * w, s, &ok);
-        if (ok) vec[a.n_owned + h] = v;
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) c->lseq[a.level] = s;
 }
 
+// ---- consumer side: halo columns are read out of this rank's mailbox ---------------------------
+struct HaloArgs {
+  int n_owned = 0x7fffffff;   // columns >= n_owned are halo entries (default: there are none)
+  long long box[2] = {};      // this rank's mailbox of the channel, per parity (words)
+  int tag_mode = 0;
+};
+
+struct HaloView {             // HaloArgs resolved for one kernel invocation
+  int n_owned;
+  const unsigned long long* box;
+  unsigned int tag;
+};
+__device__ __forceinline__ HaloView halo_view(const Ctl* ctl, const Comm* c, const HaloArgs& h) {
+  HaloView v;
+  v.n_owned = h.n_owned;
+  v.box = nullptr;
+  v.tag = 0;
+  if (c != nullptr && h.n_owned != 0x7fffffff) {
+    v.tag = comm_tag(ctl, h.tag_mode);
+    v.box = c->peer[c->rank] + h.box[v.tag & 1u];
+  } else {
+    v.n_owned = 0x7fffffff;
+  }
+  return v;
+}
+__device__ __forceinline__ double halo_get(Ctl* ctl, const HaloView& h, const double* __restrict__ x,
+                                           int j) {
+  if (j < h.n_owned) return __ldg(x + j);
+  bool ok = true;
+  return poll_f64(ctl, h.box + static_cast<long long>(j - h.n_owned) * 2, h.tag, &ok);
+}
+__device__ __forceinline__ double2 halo_get(Ctl* ctl, const HaloView& h,
+                                            const double2* __restrict__ x, int j) {
+  if (j < h.n_owned) return __ldg(x + j);
+  bool ok = true;
+  const unsigned long long* p = h.box + static_cast<long long>(j - h.n_owned) * 4;
+  double2 v;
+  v.x = poll_f64(ctl, p, h.tag, &ok);
+  v.y = poll_f64(ctl, p + 2, h.tag, &ok);
+  return v;
+}
+
+// Copies a channel's mailbox into the halo slots of its vector (waiting for the entries):
+// for the consumers that read plain arrays — the replicated AMG levels, whose right-hand side
+// is all-gathered this way once per V-cycle, and the edge-current kernel at save steps.
 template <typename T>
 __global__ void __launch_bounds__(1024)
-k_halo_exchange(Ctl* ctl, Comm* c, ExchArgs a, T* __restrict__ vec) {
+k_unpack(Ctl* ctl, Comm* c, HaloArgs h, int n_halo, T* __restrict__ vec) {
   griddep_enter();
   if (ctl->status != 0) return;
-  halo_exchange_body<T>(ctl, c, a, vec);
+  const HaloView v = halo_view(ctl, c, h);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_halo; e += gridDim.x * blockDim.x)
+    vec[h.n_owned + e] = halo_get(ctl, v, vec, h.n_owned + e);
 }
 
-// psi is double-buffered: exchange the buffer that holds the current psi.
-__global__ void __launch_bounds__(1024)
-k_halo_exchange_psi(Ctl* ctl, Comm* c, ExchArgs a, double2* psi0, double2* psi1) {
-  griddep_enter();
-  if (ctl->status != 0) return;
-  halo_exchange_body<double2>(ctl, c, a, ctl->cur ? psi1 : psi0);
+// Fills a channel of this rank's OWN mailbox from a whole-mesh array (tdgl_set_state: every
+// rank is handed the whole psi / mu, nothing has to travel).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fill_box(Comm* c, long long box0, long long box1, unsigned int tag, int n_owned, int n_halo,
+           const T* __restrict__ vec) {
+  constexpr int W = sizeof(T) / 4;
+  unsigned long long* box = c->peer[c->rank] + ((tag & 1u) ? box1 : box0);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_halo; e += gridDim.x * blockDim.x) {
+    const T v = vec[n_owned + e];
+    const double* d = reinterpret_cast<const double*>(&v);
+#pragma unroll
+    for (int w = 0; w < W / 2; ++w) st_f64(box + static_cast<long long>(e) * W + 2 * w, d[w], tag);
+  }
 }
 
 }  // namespace tdgl

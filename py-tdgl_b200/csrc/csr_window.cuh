@@ -111,16 +111,18 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
 
 // sum_k val[k] * x[idx[k]] over the staged row, four gathers in flight per thread, added in
 // column order.
+// (halo columns — sharded engine only — come out of the mailbox, see comm.cuh)
 __device__ __forceinline__ double row_dot(const double* __restrict__ sv,
                                           const int* __restrict__ si, int kb, int ke,
-                                          const double* __restrict__ x) {
+                                          const double* __restrict__ x, Ctl* ctl,
+                                          const HaloView& h) {
   double s = 0.0;
   const int last = ke - 1;
 #pragma unroll 2
   for (int k = kb; k < ke; k += 4) {
     const int k1 = min(k + 1, last), k2 = min(k + 2, last), k3 = min(k + 3, last);
-    const double x0 = __ldg(x + si[k]), x1 = __ldg(x + si[k1]), x2 = __ldg(x + si[k2]),
-                 x3 = __ldg(x + si[k3]);
+    const double x0 = halo_get(ctl, h, x, si[k]), x1 = halo_get(ctl, h, x, si[k1]),
+                 x2 = halo_get(ctl, h, x, si[k2]), x3 = halo_get(ctl, h, x, si[k3]);
     const double v0 = sv[k], v1 = (k + 1 < ke) ? sv[k1] : 0.0, v2 = (k + 2 < ke) ? sv[k2] : 0.0,
                  v3 = (k + 3 < ke) ? sv[k3] : 0.0;
     s = fma(v0, x0, s);
@@ -134,13 +136,14 @@ __device__ __forceinline__ double row_dot(const double* __restrict__ sv,
 // complex: sum_k val[k] * x[idx[k]]
 __device__ __forceinline__ double2 row_dot_c(const double2* __restrict__ sv,
                                              const int* __restrict__ si, int kb, int ke,
-                                             const double2* __restrict__ x) {
+                                             const double2* __restrict__ x, Ctl* ctl,
+                                             const HaloView& h) {
   double sx = 0.0, sy = 0.0;
   const int last = ke - 1;
 #pragma unroll 2
   for (int k = kb; k < ke; k += 2) {
     const int k1 = min(k + 1, last);
-    const double2 x0 = __ldg(x + si[k]), x1 = __ldg(x + si[k1]);
+    const double2 x0 = halo_get(ctl, h, x, si[k]), x1 = halo_get(ctl, h, x, si[k1]);
     const double2 v0 = sv[k];
     double2 v1 = sv[k1];
     if (k + 1 >= ke) v1 = make_double2(0.0, 0.0);
@@ -166,6 +169,17 @@ struct RealArgs {
   double* r = nullptr;           // kOpPresmooth: residual output
   double omega = 0.0;
   double* red_out = nullptr;     // reduction result (deterministic), may be null
+  // sharded engine: where the halo columns of the gathered vector (x; b for kOpPresmooth)
+  // are found, and where the boundary rows of the output (r for kOpPresmooth, y otherwise)
+  // go.  Defaults: no halo, nothing to send.
+  HaloArgs halo;
+  PushArgs push;
+};
+
+// psi is double-buffered, and so are its mailboxes: [b] belongs to buffer b
+struct PsiComm {
+  HaloArgs halo[2];
+  PushArgs push[2];
 };
 
 //  kOpSpmvDot   y = A x ;                         red = dot(x, y)
@@ -185,6 +199,8 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   griddep_wait();
   const bool live = (ctl->status == 0);
   const bool in = live && w.row < m.rows;
+  const HaloView hv = halo_view(ctl, comm, a.halo);
+  const unsigned int tag_out = (comm != nullptr && a.push.bnd != nullptr) ? comm_tag(ctl, a.push.tag_mode) : 0u;
   // row-local operands travel while the window lands
   double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
   if (in) {
@@ -206,33 +222,35 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
       for (int k = w.kb; k < w.ke; k += 2) {
         const int k1 = min(k + 1, last);
         const int j0 = si[k], j1 = si[k1];
-        const double t0 = __ldg(a.dinv + j0) * __ldg(a.b + j0);
-        const double t1 = __ldg(a.dinv + j1) * __ldg(a.b + j1);
+        const double t0 = __ldg(a.dinv + j0) * halo_get(ctl, hv, a.b, j0);
+        const double t1 = __ldg(a.dinv + j1) * halo_get(ctl, hv, a.b, j1);
         s = fma(sv[k], a.omega * t0, s);
         s = fma((k + 1 < w.ke) ? sv[k1] : 0.0, a.omega * t1, s);
       }
     } else {
-      s = row_dot(sv, si, w.kb, w.ke, a.x);
+      s = row_dot(sv, si, w.kb, w.ke, a.x, ctl, hv);
     }
+    double out;  // the value other shards may need
     if (OP == kOpSpmvDot) {
-      a.y[w.row] = s;
+      a.y[w.row] = out = s;
       d = s * xi;
     } else if (OP == kOpResidual) {
       const double ri = bi - s;
-      a.y[w.row] = ri;
+      a.y[w.row] = out = ri;
       d = ri * ri;
     } else if (OP == kOpPresmooth) {
       a.y[w.row] = a.omega * di * bi;
-      a.r[w.row] = bi - s;
+      a.r[w.row] = out = bi - s;
     } else if (OP == kOpJacobi) {
       const double yi = xi + a.omega * di * (bi - s);
-      a.y[w.row] = yi;
+      a.y[w.row] = out = yi;
       d = wi * yi;
     } else if (OP == kOpPlain) {
-      a.y[w.row] = s;
+      a.y[w.row] = out = s;
     } else {
-      a.y[w.row] = xi + s;
+      a.y[w.row] = out = xi + s;
     }
+    if (tag_out != 0u) push_row(comm, a.push, tag_out, w.row, out);
   }
   if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
     const double bs = block_sum(d, red);
@@ -250,7 +268,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
 // TDGLSolver.solve_for_psi_squared, tdgl/solver/solver.py:418-438); fixed[i] != 0 marks rows
 // the reference replaces by the identity (operators.py:170-184): there (L psi)_i = psi_i.
 __global__ void __launch_bounds__(kWinRows)
-kw_psi_step(Ctl* ctl, WinCsr m, const double2* __restrict__ lval,
+kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __restrict__ lval,
             const unsigned char* __restrict__ fixed, const double2* psi_buf0,
             const double2* psi_buf1, double2* out_buf0, double2* out_buf1,
             const double* __restrict__ mu, const double* __restrict__ eps,
@@ -270,6 +288,10 @@ kw_psi_step(Ctl* ctl, WinCsr m, const double2* __restrict__ lval,
   double2* __restrict__ out = cur ? out_buf0 : out_buf1;
   const double dt = dt_override >= 0.0 ? dt_override : ctl->dt;
   const bool in = live && w.row < m.rows;
+  // sharded: halo columns of the current psi come out of its buffer's mailbox, the boundary
+  // rows of the new psi go into the other buffer's mailbox on the neighbours
+  const HaloView hv = halo_view(ctl, comm, pc.halo[cur]);
+  const unsigned int tag_out = comm != nullptr ? comm_tag(ctl, kTagPsiNew) : 0u;
   double2 p = make_double2(0.0, 0.0);
   double mui = 0.0, epsi = 0.0;
   bool fx = false;
@@ -284,10 +306,11 @@ kw_psi_step(Ctl* ctl, WinCsr m, const double2* __restrict__ lval,
   double dmax = 0.0;
   int failed = 0;
   if (in) {
-    double2 lap = row_dot_c(sv, si, w.kb, w.ke, psi);
+    double2 lap = row_dot_c(sv, si, w.kb, w.ke, psi, ctl, hv);
     if (fx) lap = p;
     const PsiOut o = psi_update(p, lap, mui, epsi, ctl->gamma, ctl->u, dt);
     out[w.row] = o.psi;
+    if (comm != nullptr) push_row(comm, pc.push[cur ^ 1], tag_out, w.row, o.psi);
     if (sq_out != nullptr) sq_out[w.row] = o.sq;
     failed = o.failed;
     const double d = fabs(o.sq - (p.x * p.x + p.y * p.y));
@@ -320,8 +343,8 @@ kw_psi_step(Ctl* ctl, WinCsr m, const double2* __restrict__ lval,
 // (reference solve_for_observables, solver.py:507-510; identity: SURVEY.md appendix A).
 // The complex and the real matrix share one CSR structure and are staged together.
 __global__ void __launch_bounds__(kWinRows)
-kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
-          const double* __restrict__ aval,
+kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, WinCsr m,
+          const double2* __restrict__ lval, const double* __restrict__ aval,
           const double2* psi_buf0, const double2* psi_buf1, const double* __restrict__ mu,
           const double* __restrict__ areas, const double* __restrict__ bterm,
           double* __restrict__ b, double* __restrict__ r,
@@ -339,6 +362,9 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
   const bool live = (ctl->status == 0);
   const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
   const bool in = live && w.row < m.rows;
+  const HaloView hpsi = halo_view(ctl, comm, pc.halo[ctl->cur]);
+  const HaloView hmu = halo_view(ctl, comm, mu_halo);
+  const unsigned int tag_out = comm != nullptr ? comm_tag(ctl, r_push.tag_mode) : 0u;
   double2 p = make_double2(0.0, 0.0);
   double ai = 0.0, bt = 0.0;
   if (in) {
@@ -350,14 +376,15 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, WinCsr m, const double2* __restrict__ lval,
   if (!live) return;
   double dbb = 0.0, drr = 0.0;
   if (in) {
-    const double2 lap = row_dot_c(sl, si, w.kb, w.ke, psi);
-    const double am = row_dot(sa, si, w.kb, w.ke, mu);
+    const double2 lap = row_dot_c(sl, si, w.kb, w.ke, psi, ctl, hpsi);
+    const double am = row_dot(sa, si, w.kb, w.ke, mu, ctl, hmu);
     const double rhs = (p.x * lap.y - p.y * lap.x) - bt;
     if (rhs_raw != nullptr) rhs_raw[w.row] = rhs;
     const double bi = -ai * rhs;
     const double ri = bi - am;
     b[w.row] = bi;
     r[w.row] = ri;
+    if (comm != nullptr) push_row(comm, r_push, tag_out, w.row, ri);  // iteration 0's V-cycle input
     dbb = bi * bi;
     drr = ri * ri;
   }
@@ -410,7 +437,9 @@ kw_psi_laplacian(WinCsr m, const double2* __restrict__ lval,
   griddep_wait();
   mbar_wait(&bar, 0);
   if (w.row < m.rows) {
-    const double2 lap = row_dot_c(sv, si, w.kb, w.ke, x);
+    HaloView none;
+    none.n_owned = 0x7fffffff; none.box = nullptr; none.tag = 0;
+    const double2 lap = row_dot_c(sv, si, w.kb, w.ke, x, nullptr, none);
     y[w.row] = fixed[w.row] ? x[w.row] : lap;
   }
 }

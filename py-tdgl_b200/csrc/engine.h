@@ -93,9 +93,11 @@ struct DevLevel {
   DevBuf<double> dinv;  // nx entries (the halo part is static, filled at setup)
   double omega = 0.0;   // Jacobi weight (4/3) / rho(D^-1 A)
   DevBuf<double> b, x, y, r;  // work vectors in the arena (level 0 uses the CG vectors for b / y)
-  // halo exchange of this level (sharded engine, partitioned / gathered levels only)
-  DevBuf<int> send_idx;
-  ExchArgs ex;
+  // sharded engine, partitioned / gathered levels: per owned row the (peer, halo entry)
+  // pairs its value is stored to, and a per-32-rows "anything to send" byte
+  DevBuf<int> push_rptr;
+  DevBuf<int2> push_ent;
+  DevBuf<unsigned char> push_bnd;
 };
 
 // Largest aligned nnz extent of any window of `win` rows (shared-memory elements a CTA
@@ -307,9 +309,12 @@ class Engine {
   void enqueue_mu_finish();
   void host_solve_loop();   // host-driven CG loop on the current b/r
   Comm* comm() const { return comm_on_ ? comm_.p : nullptr; }
-  ExchArgs make_exch(int level, const int* send_idx_dev) const;
-  void enqueue_exchange(int level, double* vec);
-  void enqueue_exchange_psi();
+  PushArgs make_push(int level, int channel, int tag_mode) const;
+  HaloArgs make_halo(int level, int channel, int tag_mode) const;
+  PsiComm make_psi_comm() const;
+  void enqueue_unpack(int level, int channel, int tag_mode, double* vec);
+  void fill_state_boxes();
+  void unpack_state_halos(int cur);
   void upload_comm(double* const* peers);
   void configure_kernels();
   void build_graph();

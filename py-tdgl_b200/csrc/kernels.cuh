@@ -50,6 +50,10 @@ struct Ctl {
   int step_go;
   // --- scratch for means ------------------------------------------------------------------
   double mu_mean;
+  // --- epochs the sharded engine derives its mailbox tags from (comm.cuh) -------------------
+  int solve_epoch;    // mu solves started so far (+1): bumped at the start of every step
+  int psi_epoch;      // attempts of the psi step so far (+1)
+  int psi_tag[2];     // psi_epoch of the attempt that produced each psi buffer
 };
 
 // Programmatic dependent launch: `griddep_wait` blocks until the kernels this launch depends
@@ -160,19 +164,23 @@ k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const double* __re
 
 // p = z + beta p   (beta = rz_new / rz_prev, 0 on the first iteration)
 __global__ void __launch_bounds__(kBlock)
-k_cg_direction(const Ctl* __restrict__ ctl, int n, const double* __restrict__ z,
-               double* __restrict__ p) {
+k_cg_direction(const Ctl* __restrict__ ctl, const Comm* comm, PushArgs push, int n,
+               const double* __restrict__ z, double* __restrict__ p) {
   griddep_enter();
   if (ctl->status != 0) return;
   const double beta = (ctl->cg_it == 0) ? 0.0 : ctl->rz_new / ctl->rz_prev;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = z[i] + beta * p[i];
+  if (i < n) {
+    const double pi = z[i] + beta * p[i];
+    p[i] = pi;
+    if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, pi);
+  }
 }
 
 // alpha = rz_new / pAp ; x += alpha p ; r -= alpha Ap ; rr = ||r||^2 ;
 // last block: bookkeeping + loop condition of the CG loop.
 __global__ void __launch_bounds__(kBlock)
-k_cg_update(Ctl* ctl, Comm* comm, int n, const double* __restrict__ p,
+k_cg_update(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict__ p,
             const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
             double* partials, unsigned int* counter, cudaGraphConditionalHandle cond) {
   griddep_enter();
@@ -182,11 +190,13 @@ k_cg_update(Ctl* ctl, Comm* comm, int n, const double* __restrict__ p,
     return;
   }
   const double alpha = ctl->rz_new / ctl->pAp;
+  const unsigned int tag = comm != nullptr ? comm_tag(ctl, push.tag_mode) : 0u;
   double d = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * Ap[i];
     r[i] = ri;
+    if (comm != nullptr) push_row(comm, push, tag, i, ri);  // next iteration's V-cycle input
     d += ri * ri;
   }
   const double bs = block_sum(d, red);
@@ -281,6 +291,7 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
   griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->dt = ctl->tentative_dt;
+  ctl->solve_epoch += 1;
   ctl->retries = 0;
   ctl->disc_flag = 0;
   ctl->max_dpsi_bits = 0ull;
@@ -305,6 +316,7 @@ __global__ void k_psi_control(Ctl* ctl, Comm* comm, cudaGraphConditionalHandle c
     }
   }
   if (threadIdx.x != 0) return;
+  ctl->psi_epoch += 1;  // = the tag the attempt just made stored its boundary rows with
   if (ctl->status == 0) {
     if (ctl->disc_flag) {
       if (!ctl->adaptive || ctl->retries > ctl->max_retries) {
@@ -321,6 +333,7 @@ __global__ void k_psi_control(Ctl* ctl, Comm* comm, cudaGraphConditionalHandle c
       }
     } else {
       ctl->cur ^= 1;  // accept: the freshly written buffer becomes the current psi
+      ctl->psi_tag[ctl->cur] = ctl->psi_epoch;
     }
   }
   ctl->psi_go = go;
@@ -348,12 +361,17 @@ k_weighted_sum(Ctl* ctl, Comm* comm, int n, const double* __restrict__ w,
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_shift(const Ctl* __restrict__ ctl, int n, double* __restrict__ x) {
+k_shift(const Ctl* __restrict__ ctl, const Comm* comm, PushArgs push, int n,
+        double* __restrict__ x) {
   griddep_enter();
   if (ctl->status != 0) return;
   const double m = ctl->mu_mean;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) x[i] -= m;
+  if (i < n) {
+    const double v = x[i] - m;
+    x[i] = v;
+    if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, v);
+  }
 }
 
 // End of update() + the Runner bookkeeping (solver.py:690-707, runner.py:429-433).

@@ -201,21 +201,25 @@ inline std::vector<int> recv_peers(const ShardPlan& plan, int l, int rank) {
 //   [0, kArenaHeader)   all-reduce mailbox: [2 parities][8 ranks][4 values][2 words]
 //   vectors             psi0, psi1 (complex: 2 words per entry), mu, cg_r, cg_p, then per
 //                       level x, r, b, y; each start aligned to 32 words
-//   halo mailboxes      per partitioned level: [2 parities][halo entries][kLLWords(level)]
-// Mailbox words use the "low latency" format of comm.cuh: 32 bits of payload + a 32-bit
-// sequence tag in one 8-byte store, so that a value and its arrival flag are one atomic
-// write and no fence / separate flag round trip is needed.
+//   halo mailboxes      one per CHANNEL (= exchanged vector): [2 parities][halo entries of
+//                       the vector's level][2 words per double]
+// Mailbox words use the "low latency" format of comm.cuh: 32 bits of payload + a 32-bit tag
+// in one 8-byte store, so that a value and its arrival flag are one atomic write.  A
+// consumer kernel reads halo entries straight out of the mailbox (polling the tag), so there
+// is no separate exchange step: the producer kernel stores its boundary rows into the
+// peers' mailboxes as it computes them.
 constexpr int64_t kArenaRedBox = 0, kArenaHeader = 256;
 enum : int { kVecPsi0 = 0, kVecPsi1, kVecMu, kVecCgR, kVecCgP, kVecLevel0 };
 inline int vec_id(int level, int which /*0 x, 1 r, 2 b, 3 y*/) { return kVecLevel0 + 4 * level + which; }
-// mailbox words per halo entry: a double is 2 words; level 0 also carries psi (complex: 4)
-inline int ll_words(int level) { return level == 0 ? 4 : 2; }
+// channels are numbered like the vectors they carry
+inline int ch_words(int ch) { return ch <= kVecPsi1 ? 4 : 2; }
+inline int ch_level(int ch) { return ch < kVecLevel0 ? 0 : (ch - kVecLevel0) / 4; }
 
 struct ArenaLayout {
-  std::vector<int64_t> off;     // per vector id, in words from the arena base
-  std::vector<int64_t> ll_off;  // per level: start of the halo mailbox (parity 0)
-  std::vector<int64_t> ll_cap;  // per level: words per parity
-  int64_t total = 0;            // words
+  std::vector<int64_t> off;      // per vector id, in words from the arena base
+  std::vector<int64_t> box_off;  // per channel: start of the mailbox (parity 0); 0: none
+  std::vector<int64_t> box_cap;  // per channel: words per parity
+  int64_t total = 0;             // words
 };
 
 inline ArenaLayout arena_layout(const ShardPlan& plan, int rank) {
@@ -233,13 +237,16 @@ inline ArenaLayout arena_layout(const ShardPlan& plan, int rank) {
     const int64_t nx = plan.local_size(l, rank);
     for (int w = 0; w < 4; ++w) a.off.push_back(add(nx));
   }
-  a.ll_off.assign(plan.levels, 0);
-  a.ll_cap.assign(plan.levels, 0);
-  for (int l = 0; l < plan.levels && l <= plan.rep && plan.world > 1; ++l) {
-    // payload words + one "present" word per rank (see ExchArgs in comm.cuh)
-    a.ll_cap[l] = static_cast<int64_t>(plan.halo[l][rank].size()) * ll_words(l) + kMaxWorld;
-    a.ll_off[l] = add(2 * a.ll_cap[l]);
-  }
+  const int nch = kVecLevel0 + 4 * plan.levels;
+  a.box_off.assign(nch, 0);
+  a.box_cap.assign(nch, 0);
+  if (plan.world > 1)
+    for (int ch = 0; ch < nch; ++ch) {
+      const int l = ch_level(ch);
+      if (l > plan.rep) continue;
+      a.box_cap[ch] = std::max<int64_t>(static_cast<int64_t>(plan.halo[l][rank].size()) * ch_words(ch), 2);
+      a.box_off[ch] = add(2 * a.box_cap[ch]);
+    }
   a.total = pos;
   return a;
 }

@@ -61,53 +61,37 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
 // ============================================================================================
 // construction
 
-ExchArgs Engine::make_exch(int level, const int* send_idx_dev) const {
-  ExchArgs a;
-  if (world_ == 1 || level > plan_.rep) return a;
-  const std::vector<SendBlock> blocks = send_blocks(plan_, level, rank_);
-  std::vector<int> peers = recv_peers(plan_, level, rank_);
-  for (const SendBlock& b : blocks) peers.push_back(b.peer);
-  // (send or receive) must be a symmetric relation: also list the ranks that list this one
-  for (int q = 0; q < world_; ++q) {
-    if (q == rank_) continue;
-    const std::vector<int> rq = recv_peers(plan_, level, q);
-    if (std::find(rq.begin(), rq.end(), rank_) != rq.end()) peers.push_back(q);
-    for (const SendBlock& b : send_blocks(plan_, level, q))
-      if (b.peer == rank_) peers.push_back(q);
-  }
-  std::sort(peers.begin(), peers.end());
-  peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
-  a.level = level;
-  a.nnbr = static_cast<int>(peers.size());
-  a.n_owned = static_cast<int>(plan_.off[level][rank_ + 1] - plan_.off[level][rank_]);
-  a.n_halo = static_cast<int>(plan_.halo[level][rank_].size());
-  a.send_idx = send_idx_dev;
-  const int W = ll_words(level);
+PushArgs Engine::make_push(int level, int channel, int tag_mode) const {
+  PushArgs p;
+  if (world_ == 1 || level > plan_.rep) return p;   // bnd == nullptr: nothing is sent
+  const DevLevel& dl = levels_[level];
+  p.bnd = dl.push_bnd.p;
+  p.rptr = dl.push_rptr.p;
+  p.ent = dl.push_ent.p;
+  p.tag_mode = tag_mode;
+  for (int q = 0; q < world_; ++q)
+    for (int par = 0; par < 2; ++par)
+      p.box[par][q] = layouts_[q].box_off[channel] + par * layouts_[q].box_cap[channel];
+  return p;
+}
+
+HaloArgs Engine::make_halo(int level, int channel, int tag_mode) const {
+  HaloArgs h;
+  if (world_ == 1 || level > plan_.rep) return h;   // no halo columns
+  h.n_owned = static_cast<int>(plan_.off[level][rank_ + 1] - plan_.off[level][rank_]);
+  h.tag_mode = tag_mode;
   const ArenaLayout& mine = layouts_[rank_];
-  for (int par = 0; par < 2; ++par) {
-    a.box_word[par] = mine.ll_off[level] + par * mine.ll_cap[level];
-    a.box_ack[par] = a.box_word[par] + static_cast<long long>(a.n_halo) * W;
+  for (int par = 0; par < 2; ++par) h.box[par] = mine.box_off[channel] + par * mine.box_cap[channel];
+  return h;
+}
+
+PsiComm Engine::make_psi_comm() const {
+  PsiComm pc;
+  for (int b = 0; b < 2; ++b) {
+    pc.halo[b] = make_halo(0, kVecPsi0 + b, kTagPsiCur);
+    pc.push[b] = make_push(0, kVecPsi0 + b, kTagPsiNew);
   }
-  int pos = 0;
-  for (int j = 0; j < a.nnbr; ++j) {
-    const int q = peers[j];
-    const ArenaLayout& lq = layouts_[q];
-    const long long q_halo = static_cast<long long>(plan_.halo[level][q].size());
-    a.nbr[j] = q;
-    a.send_begin[j] = pos;
-    for (int par = 0; par < 2; ++par) {
-      const long long base = lq.ll_off[level] + par * lq.ll_cap[level];
-      a.dst_word[par][j] = base;
-      a.ack_word[par][j] = base + q_halo * W + rank_;
-    }
-    for (const SendBlock& b : blocks)
-      if (b.peer == q) {
-        pos += static_cast<int>(b.idx.size());
-        a.dst_entry[j] = static_cast<int>(b.dst_pos);
-      }
-  }
-  a.send_begin[a.nnbr] = pos;
-  return a;
+  return pc;
 }
 
 Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t* edges,
@@ -375,12 +359,25 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     dl.b.view(arena_.p + lay.off[vec_id(li, 2)], dl.nx);
     dl.y.view(arena_.p + lay.off[vec_id(li, 3)], dl.nx);
     if (world_ > 1 && li <= rep_level) {
-      std::vector<int> sidx;
-      for (const SendBlock& b : send_blocks(plan_, li, rank_)) sidx.insert(sidx.end(), b.idx.begin(), b.idx.end());
-      if (sidx.empty()) sidx.push_back(0);
-      dl.send_idx.upload(sidx, stream_);
+      // per owned row: the (peer, halo entry) pairs its value is stored to (comm.cuh push_row)
+      const int n_own = static_cast<int>(plan_.off[l][rank_ + 1] - plan_.off[l][rank_]);
+      std::vector<int> rptr(n_own + 1, 0);
+      const std::vector<SendBlock> blocks = send_blocks(plan_, li, rank_);
+      for (const SendBlock& b : blocks)
+        for (int32_t row : b.idx) rptr[row + 1]++;
+      for (int i = 0; i < n_own; ++i) rptr[i + 1] += rptr[i];
+      std::vector<int2> ent(std::max(rptr[n_own], 1));
+      std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+      for (const SendBlock& b : blocks)
+        for (size_t k = 0; k < b.idx.size(); ++k)
+          ent[fill[b.idx[k]]++] = make_int2(b.peer, static_cast<int>(b.dst_pos + k));
+      std::vector<unsigned char> bnd((n_own + 31) / 32 + 1, 0);
+      for (int i = 0; i < n_own; ++i)
+        if (rptr[i + 1] > rptr[i]) bnd[i >> 5] = 1;
+      dl.push_rptr.upload(rptr, stream_);
+      dl.push_ent.upload(ent, stream_);
+      dl.push_bnd.upload(bnd, stream_);
       TDGL_CUDA(cudaStreamSynchronize(stream_));
-      dl.ex = make_exch(li, dl.send_idx.p);
     }
   }
   {
@@ -440,12 +437,15 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   h_ctl_->cg_max_iter = cfg_.mu_max_iter;
   h_ctl_->n_probe = nprobe_; h_ctl_->running_capacity = cfg_.running_capacity;
   h_ctl_->tentative_dt = 1e-6; h_ctl_->dt = 1e-6;
+  h_ctl_->solve_epoch = 1; h_ctl_->psi_epoch = 1; h_ctl_->psi_tag[0] = h_ctl_->psi_tag[1] = 1;
   ctl_.alloc(1);
   push_ctl();
   {
     double* none[kMaxWorld] = {};
     none[rank_] = arena_.p;
     upload_comm(none);
+    fill_state_boxes();
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
 
   // link variables for A = 0
@@ -547,10 +547,13 @@ void Engine::comm_connect_local(Engine* const* engines) {
 void Engine::shard_info(int64_t* out, int n) {
   int64_t halo_total = 0, nbr0 = 0;
   for (int l = 0; l < plan_.levels; ++l) halo_total += static_cast<int64_t>(plan_.halo[l][rank_].size());
-  const ExchArgs& e0 = levels_[0].ex;
-  nbr0 = e0.nnbr;
-  const int64_t vals[8] = {world_, rank_, Ng_, N_, Nx_ - N_, halo_total, nbr0,
-                           static_cast<int64_t>(e0.send_begin[e0.nnbr])};
+  int64_t n_send0 = 0;
+  if (world_ > 1) {
+    const std::vector<SendBlock> blocks = send_blocks(plan_, 0, rank_);
+    nbr0 = static_cast<int64_t>(blocks.size());
+    for (const SendBlock& b : blocks) n_send0 += static_cast<int64_t>(b.idx.size());
+  }
+  const int64_t vals[8] = {world_, rank_, Ng_, N_, Nx_ - N_, halo_total, nbr0, n_send0};
   for (int i = 0; i < n && i < 8; ++i) out[i] = vals[i];
 }
 
@@ -643,15 +646,13 @@ void Engine::launch_residual(const CsrView& A, const double* x, const double* b,
 
 // z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
 // smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
-void Engine::enqueue_exchange(int level, double* vec) {
+// Mailbox -> halo slots of a plain array (the consumers that do not read mailboxes).
+void Engine::enqueue_unpack(int level, int channel, int tag_mode, double* vec) {
   if (!comm_on_ || level > plan_.rep) return;
-  launch_k(k_halo_exchange<double>, 1, 1024, 0, ctl_.p, comm_.p, levels_[level].ex, vec);
-  TDGL_LAUNCH_CHECK();
-}
-
-void Engine::enqueue_exchange_psi() {
-  if (!comm_on_) return;
-  launch_k(k_halo_exchange_psi, 1, 1024, 0, ctl_.p, comm_.p, levels_[0].ex, psi_[0].p, psi_[1].p);
+  const int n_halo = static_cast<int>(plan_.halo[level][rank_].size());
+  if (n_halo == 0) return;
+  launch_k(k_unpack<double>, std::min((n_halo + 1023) / 1024, 64), 1024, 0, ctl_.p, comm_.p,
+           make_halo(level, channel, tag_mode), n_halo, vec);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -665,24 +666,39 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     TDGL_LAUNCH_CHECK();
     return;
   }
-  // Sharded: on a partitioned level (l < rep) a vector is exchanged right before the kernel
-  // that gathers from it; the right-hand side of level rep is all-gathered and everything
-  // from there down is computed redundantly by every shard (no exchange).
-  // Levels fuse_from_ .. L-1 (the small ones) run as ONE cluster kernel.
+  // Sharded: on a partitioned level (l < rep) every kernel stores the boundary rows of its
+  // output into the neighbours' mailboxes and reads the halo columns of its input out of its
+  // own (comm.cuh) — there is no exchange step.  The right-hand side of level rep is
+  // all-gathered the same way and unpacked into a plain array, and everything from there
+  // down is computed redundantly by every shard.
+  // Levels fuse_from_ .. L-1 (the small ones) can run as ONE cluster kernel.
   const int rep = comm_on_ ? plan_.rep : -1;
   const int Li = static_cast<int>(L);
   const int split = (fuse_from_ >= 1 && fuse_from_ <= Li - 2) ? fuse_from_ : Li - 1;
+  auto chan = [](int l, int which) { return vec_id(l, which); };
   for (int li = 0; li < split; ++li) {
     DevLevel& lv = levels_[li];
     double* b = (li == 0) ? r_in : lv.b.p;
-    if (li <= rep) enqueue_exchange(li, b);
-    launch_presmooth(levelA(li), lv.dinv.p, lv.omega, b, lv.x.p, lv.r.p);
-    if (li < rep) enqueue_exchange(li, lv.r.p);
-    launch_plain(lv.R.view(), lv.r.p, levels_[li + 1].b.p, false);
+    {
+      RealArgs a;
+      a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.b = b; a.y = lv.x.p; a.r = lv.r.p;
+      if (li < rep) {
+        a.halo = make_halo(li, li == 0 ? kVecCgR : chan(li, 2), kTagIter);
+        a.push = make_push(li, chan(li, 1), kTagIter);
+      }
+      launch_real<kOpPresmooth>(levelA(li), a);
+    }
+    {
+      RealArgs a;
+      a.val = lv.R.view().val; a.x = lv.r.p; a.y = levels_[li + 1].b.p;
+      if (li < rep) a.halo = make_halo(li, chan(li, 1), kTagIter);
+      if (li + 1 <= rep) a.push = make_push(li + 1, chan(li + 1, 2), kTagIter);
+      launch_real<kOpPlain>(lv.R.view(), a);
+    }
+    if (li + 1 == rep) enqueue_unpack(rep, chan(rep, 2), kTagIter, levels_[rep].b.p);
   }
   {
     DevLevel& c = levels_[split];
-    if (split <= rep) enqueue_exchange(split, c.b.p);
     if (split < Li - 1) {
       launch_k(k_coarse_cycle, kFuseCtas, kFuseThreads, 0, ctl_.p, fused_.p, split, Li,
                                                              coarse_inv_.p, nc_);
@@ -696,36 +712,58 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     DevLevel& lv = levels_[li];
     const double* b = (li == 0) ? r_in : lv.b.p;
     double* y = (li == 0) ? z_out : lv.y.p;
-    if (li + 1 < rep) enqueue_exchange(li + 1, levels_[li + 1].y.p);
-    launch_plain(lv.P.view(), levels_[li + 1].y.p, lv.x.p, true);
-    if (li < rep) enqueue_exchange(li, lv.x.p);
-    launch_jacobi(levelA(li), lv.dinv.p, lv.omega, b, lv.x.p, y, (li == 0) ? r_in : nullptr,
-                  (li == 0) ? rz_out : nullptr);
+    {
+      RealArgs a;
+      a.val = lv.P.view().val; a.x = levels_[li + 1].y.p; a.y = lv.x.p;
+      if (li + 1 < rep) a.halo = make_halo(li + 1, chan(li + 1, 3), kTagIter);
+      if (li < rep) a.push = make_push(li, chan(li, 0), kTagIter);
+      launch_real<kOpPlainAdd>(lv.P.view(), a);
+    }
+    {
+      RealArgs a;
+      a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.b = b; a.x = lv.x.p; a.y = y;
+      a.w = (li == 0) ? r_in : nullptr;
+      a.red_out = (li == 0) ? rz_out : nullptr;
+      if (li < rep) {
+        a.halo = make_halo(li, chan(li, 0), kTagIter);
+        if (li > 0) a.push = make_push(li, chan(li, 3), kTagIter);
+      }
+      launch_real<kOpJacobi>(levelA(li), a);
+    }
   }
 }
 
 void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
-  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, 
-      ctl_.p, site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p, mu_.p,
-      eps_.p, sq_out, dt_override);
+  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
+           ctl_.p, comm(), comm_on_ ? make_psi_comm() : PsiComm(), site_csr(), lval_.p, fixed_.p,
+           psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_mu_rhs(double* rhs_raw) {
-  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, 
-      ctl_.p, comm(), site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p, mu_.p, areas_.p,
-      bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
+  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
+           ctl_.p, comm(), comm_on_ ? make_psi_comm() : PsiComm(),
+           comm_on_ ? make_halo(0, kVecMu, kTagMuPrev) : HaloArgs(),
+           comm_on_ ? make_push(0, kVecCgR, kTagIter0) : PushArgs(), site_csr(), lval_.p, aval_.p,
+           psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p,
+           counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new);
-  launch_k(k_cg_direction, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, cg_z_.p, cg_p_.p);
+  launch_k(k_cg_direction, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
+           comm_on_ ? make_push(0, kVecCgP, kTagIter) : PushArgs(), N_, cg_z_.p, cg_p_.p);
   TDGL_LAUNCH_CHECK();
-  enqueue_exchange(0, cg_p_.p);
-  launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp);
-  launch_k(k_cg_update, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, cg_p_.p, cg_Ap_.p, mu_.p,
-                                                   cg_r_.p, partials_.p, counter_.p, cond);
+  {
+    RealArgs a;
+    a.val = A0().val; a.x = cg_p_.p; a.y = cg_Ap_.p; a.red_out = &ctl_.p->pAp;
+    if (comm_on_) a.halo = make_halo(0, kVecCgP, kTagIter);
+    launch_real<kOpSpmvDot>(A0(), a);
+  }
+  launch_k(k_cg_update, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
+           comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_p_.p, cg_Ap_.p,
+           mu_.p, cg_r_.p, partials_.p, counter_.p, cond);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -735,9 +773,11 @@ void Engine::enqueue_mu_finish() {
   launch_k(k_weighted_sum, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, areas_.p, mu_.p,
                                                       partials_.p, counter_.p, 1.0 / total_area_);
   TDGL_LAUNCH_CHECK();
-  launch_k(k_shift, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, mu_.p);
+  // (sharded: the shifted boundary values go to the neighbours — the next step's rhs kernel
+  // and the edge currents read mu's halo)
+  launch_k(k_shift, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
+           comm_on_ ? make_push(0, kVecMu, kTagMu) : PushArgs(), N_, mu_.p);
   TDGL_LAUNCH_CHECK();
-  enqueue_exchange(0, mu_.p);  // the next step's rhs / the edge currents read mu's halo
 }
 
 void Engine::host_solve_loop() {
@@ -818,7 +858,6 @@ void Engine::build_graph() {
     });
   }
   sb.capture([&] {
-    enqueue_exchange_psi();
     enqueue_mu_rhs(nullptr);
     launch_k(k_cg_begin, 1, 32, 0, ctl_.p, h_cg_);
     TDGL_LAUNCH_CHECK();
@@ -879,7 +918,29 @@ void Engine::set_state(const double* psi, const double* mu) {
   tmp_d_.upload(mu, Ng_, stream_);
   k_gather<double><<<(Nx_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(Nx_, dperm_.p, tmp_d_.p, mu_.p);
   TDGL_LAUNCH_CHECK();
+  fill_state_boxes();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// Sharded: the halo columns of psi / mu are read out of this shard's mailboxes; after the
+// state was set from whole-mesh arrays (which every shard holds) each shard fills its own.
+void Engine::fill_state_boxes() {
+  if (world_ == 1) return;
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  const int n_halo = Nx_ - N_;
+  h_ctl_->psi_tag[cur] = h_ctl_->psi_epoch;
+  push_ctl();
+  if (n_halo == 0) return;
+  const ArenaLayout& lay = layouts_[rank_];
+  const int g = (n_halo + 255) / 256;
+  const int chp = kVecPsi0 + cur;
+  k_fill_box<double2><<<g, 256, 0, stream_>>>(comm_.p, lay.box_off[chp], lay.box_off[chp] + lay.box_cap[chp],
+                                             static_cast<unsigned int>(h_ctl_->psi_epoch), N_, n_halo, psi_[cur].p);
+  TDGL_LAUNCH_CHECK();
+  k_fill_box<double><<<g, 256, 0, stream_>>>(comm_.p, lay.box_off[kVecMu], lay.box_off[kVecMu] + lay.box_cap[kVecMu],
+                                            static_cast<unsigned int>(h_ctl_->solve_epoch), N_, n_halo, mu_.p);
+  TDGL_LAUNCH_CHECK();
 }
 
 void Engine::set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
@@ -922,8 +983,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     sync_ctl_to_host();
     // the graph's kernels were launched by the device-side loops; account for them
     const int64_t L = static_cast<int64_t>(levels_.size());
-    const int64_t R = std::min<int64_t>(plan_.rep, L - 1);
-    const int64_t ex_step = world_ > 1 ? 2 : 0, ex_it = world_ > 1 ? 4 * R + 1 : 0;
+    const int64_t ex_step = 0, ex_it = world_ > 1 ? 1 : 0;  // (the all-gather unpack of level rep)
     const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
     launches_ += h_ctl_->steps_done * (6 + ex_step) + h_ctl_->total_retries * 2 +
                  h_ctl_->total_cg_it * (3 + 4 * split + 1 + ex_it);
@@ -938,7 +998,6 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
         sync_ctl_to_host();
       } while (h_ctl_->psi_go);
       if (h_ctl_->status != 0) break;
-      enqueue_exchange_psi();
       enqueue_mu_rhs(nullptr);
       host_solve_loop();
       enqueue_mu_finish();
@@ -991,6 +1050,7 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     tmp_d_.download(mu_out, Ng_, stream_);
   }
   if (js != nullptr || jn != nullptr) {
+    unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
@@ -1023,12 +1083,26 @@ void Engine::get_state(double* psi, double* mu) {
 void Engine::get_currents(double* js, double* jn) {
   sync_ctl_to_host();
   const int cur = h_ctl_->cur;
+  unpack_state_halos(cur);
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
       E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, tmp_e_.p, tmp_e2_.p);
   TDGL_LAUNCH_CHECK();
   if (js != nullptr) tmp_e_.download(js, E_, stream_);
   if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
   TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// Sharded: k_currents reads plain arrays; bring the halo slots of psi and mu up to date.
+void Engine::unpack_state_halos(int cur) {
+  if (world_ == 1 || !connected_) return;
+  const int n_halo = Nx_ - N_;
+  if (n_halo == 0) return;
+  const int g = std::min((n_halo + 1023) / 1024, 64);
+  k_unpack<double2><<<g, 1024, 0, stream_>>>(ctl_.p, comm_.p, make_halo(0, kVecPsi0 + cur, kTagPsiCur),
+                                            n_halo, psi_[cur].p);
+  TDGL_LAUNCH_CHECK();
+  k_unpack<double><<<g, 1024, 0, stream_>>>(ctl_.p, comm_.p, make_halo(0, kVecMu, kTagMu), n_halo, mu_.p);
+  TDGL_LAUNCH_CHECK();
 }
 
 void Engine::get_running(int64_t capacity, double* dt, double* mu_probe, double* theta_probe) {
@@ -1086,9 +1160,9 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
   h_ctl_->disc_flag = 0;
   h_ctl_->status = 0;
   push_ctl();
-  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20, 
-      ctl_.p, site_csr(), lval_.p, fixed_.p, pin.p, pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p,
-      dt);
+  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
+           ctl_.p, static_cast<const Comm*>(nullptr), PsiComm(), site_csr(), lval_.p, fixed_.p, pin.p,
+           pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p, dt);
   TDGL_LAUNCH_CHECK();
   k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, pout.p, tmp_c_.p);
   TDGL_LAUNCH_CHECK();
@@ -1114,9 +1188,10 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   TDGL_LAUNCH_CHECK();
   sync_ctl_to_host();
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
-  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28, 
-      ctl_.p, comm(), site_csr(), lval_.p, aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p,
-      raw.p, partials_.p, counter_.p);
+  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
+           ctl_.p, static_cast<Comm*>(nullptr), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p,
+           aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p, raw.p, partials_.p,
+           counter_.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
   TDGL_LAUNCH_CHECK();

@@ -58,6 +58,15 @@ class DistributedEngine(DeviceEngine):
             flat[:] = t.cpu().numpy()
         return arrays
 
+    def set_state(self, psi, mu) -> None:
+        # every shard fills its own halo mailboxes from the whole-mesh arrays; no shard may
+        # still be stepping (and storing into a peer's mailbox) while that happens
+        if self.world > 1:
+            self._dist.barrier(group=self._group)
+        super().set_state(psi, mu)
+        if self.world > 1:
+            self._dist.barrier(group=self._group)
+
     def get_state(self):
         return self._sum(*super().get_state())
 
