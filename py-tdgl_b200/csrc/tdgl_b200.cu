@@ -1361,6 +1361,7 @@ template <typename F>
 int guarded(tdgl_handle* h, F&& f) {
   if (h == nullptr || !h->engine) return TDGL_E_INVALID;
   try {
+    h->engine->make_current();  // calls may come from any host thread
     f(*h->engine);
     return TDGL_OK;
   } catch (const tdgl::CudaError& e) {
