@@ -111,18 +111,28 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
 
 // sum_k val[k] * x[idx[k]] over the staged row, four gathers in flight per thread, added in
 // column order.
-// (halo columns — sharded engine only — come out of the mailbox, see comm.cuh)
+// Halo columns — sharded engine only — come out of the mailbox (comm.cuh).  The gathers are
+// issued unconditionally from the array (index clamped), so that they stay independent and
+// in flight together; the rare halo entries are patched afterwards.
 __device__ __forceinline__ double row_dot(const double* __restrict__ sv,
                                           const int* __restrict__ si, int kb, int ke,
                                           const double* __restrict__ x, Ctl* ctl,
                                           const HaloView& h) {
   double s = 0.0;
   const int last = ke - 1;
+  const int top = h.n_owned - 1;
 #pragma unroll 2
   for (int k = kb; k < ke; k += 4) {
     const int k1 = min(k + 1, last), k2 = min(k + 2, last), k3 = min(k + 3, last);
-    const double x0 = halo_get(ctl, h, x, si[k]), x1 = halo_get(ctl, h, x, si[k1]),
-                 x2 = halo_get(ctl, h, x, si[k2]), x3 = halo_get(ctl, h, x, si[k3]);
+    const int j0 = si[k], j1 = si[k1], j2 = si[k2], j3 = si[k3];
+    double x0 = __ldg(x + min(j0, top)), x1 = __ldg(x + min(j1, top)), x2 = __ldg(x + min(j2, top)),
+           x3 = __ldg(x + min(j3, top));
+    if (max(max(j0, j1), max(j2, j3)) > top) {
+      if (j0 > top) x0 = halo_get(ctl, h, x, j0);
+      if (j1 > top) x1 = halo_get(ctl, h, x, j1);
+      if (j2 > top) x2 = halo_get(ctl, h, x, j2);
+      if (j3 > top) x3 = halo_get(ctl, h, x, j3);
+    }
     const double v0 = sv[k], v1 = (k + 1 < ke) ? sv[k1] : 0.0, v2 = (k + 2 < ke) ? sv[k2] : 0.0,
                  v3 = (k + 3 < ke) ? sv[k3] : 0.0;
     s = fma(v0, x0, s);
@@ -140,10 +150,16 @@ __device__ __forceinline__ double2 row_dot_c(const double2* __restrict__ sv,
                                              const HaloView& h) {
   double sx = 0.0, sy = 0.0;
   const int last = ke - 1;
+  const int top = h.n_owned - 1;
 #pragma unroll 2
   for (int k = kb; k < ke; k += 2) {
     const int k1 = min(k + 1, last);
-    const double2 x0 = halo_get(ctl, h, x, si[k]), x1 = halo_get(ctl, h, x, si[k1]);
+    const int j0 = si[k], j1 = si[k1];
+    double2 x0 = __ldg(x + min(j0, top)), x1 = __ldg(x + min(j1, top));
+    if (max(j0, j1) > top) {
+      if (j0 > top) x0 = halo_get(ctl, h, x, j0);
+      if (j1 > top) x1 = halo_get(ctl, h, x, j1);
+    }
     const double2 v0 = sv[k];
     double2 v1 = sv[k1];
     if (k + 1 >= ke) v1 = make_double2(0.0, 0.0);
@@ -222,8 +238,13 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
       for (int k = w.kb; k < w.ke; k += 2) {
         const int k1 = min(k + 1, last);
         const int j0 = si[k], j1 = si[k1];
-        const double t0 = __ldg(a.dinv + j0) * halo_get(ctl, hv, a.b, j0);
-        const double t1 = __ldg(a.dinv + j1) * halo_get(ctl, hv, a.b, j1);
+        double b0 = __ldg(a.b + min(j0, hv.n_owned - 1)), b1 = __ldg(a.b + min(j1, hv.n_owned - 1));
+        if (max(j0, j1) >= hv.n_owned) {
+          if (j0 >= hv.n_owned) b0 = halo_get(ctl, hv, a.b, j0);
+          if (j1 >= hv.n_owned) b1 = halo_get(ctl, hv, a.b, j1);
+        }
+        const double t0 = __ldg(a.dinv + j0) * b0;
+        const double t1 = __ldg(a.dinv + j1) * b1;
         s = fma(sv[k], a.omega * t0, s);
         s = fma((k + 1 < w.ke) ? sv[k1] : 0.0, a.omega * t1, s);
       }
