@@ -114,20 +114,21 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
 // Halo columns — sharded engine only — come out of the mailbox (comm.cuh).  The gathers are
 // issued unconditionally from the array (index clamped), so that they stay independent and
 // in flight together; the rare halo entries are patched afterwards.
+template <bool SH>
 __device__ __forceinline__ double row_dot(const double* __restrict__ sv,
                                           const int* __restrict__ si, int kb, int ke,
                                           const double* __restrict__ x, Ctl* ctl,
                                           const HaloView& h) {
   double s = 0.0;
   const int last = ke - 1;
-  const int top = h.n_owned - 1;
+  const int top = SH ? h.n_owned - 1 : 0x7fffffff;
 #pragma unroll 2
   for (int k = kb; k < ke; k += 4) {
     const int k1 = min(k + 1, last), k2 = min(k + 2, last), k3 = min(k + 3, last);
     const int j0 = si[k], j1 = si[k1], j2 = si[k2], j3 = si[k3];
     double x0 = __ldg(x + min(j0, top)), x1 = __ldg(x + min(j1, top)), x2 = __ldg(x + min(j2, top)),
            x3 = __ldg(x + min(j3, top));
-    if (max(max(j0, j1), max(j2, j3)) > top) {
+    if (SH && max(max(j0, j1), max(j2, j3)) > top) {
       if (j0 > top) x0 = halo_get(ctl, h, x, j0);
       if (j1 > top) x1 = halo_get(ctl, h, x, j1);
       if (j2 > top) x2 = halo_get(ctl, h, x, j2);
@@ -144,19 +145,20 @@ __device__ __forceinline__ double row_dot(const double* __restrict__ sv,
 }
 
 // complex: sum_k val[k] * x[idx[k]]
+template <bool SH>
 __device__ __forceinline__ double2 row_dot_c(const double2* __restrict__ sv,
                                              const int* __restrict__ si, int kb, int ke,
                                              const double2* __restrict__ x, Ctl* ctl,
                                              const HaloView& h) {
   double sx = 0.0, sy = 0.0;
   const int last = ke - 1;
-  const int top = h.n_owned - 1;
+  const int top = SH ? h.n_owned - 1 : 0x7fffffff;
 #pragma unroll 2
   for (int k = kb; k < ke; k += 2) {
     const int k1 = min(k + 1, last);
     const int j0 = si[k], j1 = si[k1];
     double2 x0 = __ldg(x + min(j0, top)), x1 = __ldg(x + min(j1, top));
-    if (max(j0, j1) > top) {
+    if (SH && max(j0, j1) > top) {
       if (j0 > top) x0 = halo_get(ctl, h, x, j0);
       if (j1 > top) x1 = halo_get(ctl, h, x, j1);
     }
@@ -203,7 +205,9 @@ struct PsiComm {
 //  kOpPresmooth y = omega D^-1 b ; r = b - A y    (smoothing from a zero guess + residual)
 //  kOpJacobi    y = x + omega D^-1 (b - A x) ;    red = dot(w, y)
 //  kOpPlain     y = A x ;  kOpPlainAdd  y += A x  (restriction / prolongation)
-template <int OP>
+// SH: instantiated for the sharded engine (halo columns out of the mailbox, boundary rows
+// pushed to the peers); the single-GPU instantiation carries none of that code.
+template <int OP, bool SH>
 __global__ void __launch_bounds__(kWinRows)
 kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned int* counter) {
   extern __shared__ __align__(128) unsigned char win_smem[];
@@ -215,8 +219,13 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   griddep_wait();
   const bool live = (ctl->status == 0);
   const bool in = live && w.row < m.rows;
-  const HaloView hv = halo_view(ctl, comm, a.halo);
-  const unsigned int tag_out = (comm != nullptr && a.push.bnd != nullptr) ? comm_tag(ctl, a.push.tag_mode) : 0u;
+  HaloView hv;
+  hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
+  unsigned int tag_out = 0u;
+  if (SH) {
+    hv = halo_view(ctl, comm, a.halo);
+    if (comm != nullptr && a.push.bnd != nullptr) tag_out = comm_tag(ctl, a.push.tag_mode);
+  }
   // row-local operands travel while the window lands
   double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
   if (in) {
@@ -238,8 +247,9 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
       for (int k = w.kb; k < w.ke; k += 2) {
         const int k1 = min(k + 1, last);
         const int j0 = si[k], j1 = si[k1];
-        double b0 = __ldg(a.b + min(j0, hv.n_owned - 1)), b1 = __ldg(a.b + min(j1, hv.n_owned - 1));
-        if (max(j0, j1) >= hv.n_owned) {
+        double b0 = __ldg(a.b + (SH ? min(j0, hv.n_owned - 1) : j0)),
+               b1 = __ldg(a.b + (SH ? min(j1, hv.n_owned - 1) : j1));
+        if (SH && max(j0, j1) >= hv.n_owned) {
           if (j0 >= hv.n_owned) b0 = halo_get(ctl, hv, a.b, j0);
           if (j1 >= hv.n_owned) b1 = halo_get(ctl, hv, a.b, j1);
         }
@@ -249,7 +259,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
         s = fma((k + 1 < w.ke) ? sv[k1] : 0.0, a.omega * t1, s);
       }
     } else {
-      s = row_dot(sv, si, w.kb, w.ke, a.x, ctl, hv);
+      s = row_dot<SH>(sv, si, w.kb, w.ke, a.x, ctl, hv);
     }
     double out;  // the value other shards may need
     if (OP == kOpSpmvDot) {
@@ -271,14 +281,15 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
     } else {
       a.y[w.row] = out = xi + s;
     }
-    if (tag_out != 0u) push_row(comm, a.push, tag_out, w.row, out);
+    if (SH && tag_out != 0u) push_row(comm, a.push, tag_out, w.row, out);
+    (void)out;
   }
   if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
     const double bs = block_sum(d, red);
     double total;
     if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
       total = __shfl_sync(0xffffffffu, total, 0);
-      if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+      if (SH && comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       if (threadIdx.x == 0) *a.red_out = total;
     }
   }
@@ -288,6 +299,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
 // Fused covariant-Laplacian SpMV + closed-form |psi|^2 update (reference
 // TDGLSolver.solve_for_psi_squared, tdgl/solver/solver.py:418-438); fixed[i] != 0 marks rows
 // the reference replaces by the identity (operators.py:170-184): there (L psi)_i = psi_i.
+template <bool SH>
 __global__ void __launch_bounds__(kWinRows)
 kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __restrict__ lval,
             const unsigned char* __restrict__ fixed, const double2* psi_buf0,
@@ -311,8 +323,13 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
   const bool in = live && w.row < m.rows;
   // sharded: halo columns of the current psi come out of its buffer's mailbox, the boundary
   // rows of the new psi go into the other buffer's mailbox on the neighbours
-  const HaloView hv = halo_view(ctl, comm, pc.halo[cur]);
-  const unsigned int tag_out = comm != nullptr ? comm_tag(ctl, kTagPsiNew) : 0u;
+  HaloView hv;
+  hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
+  unsigned int tag_out = 0u;
+  if (SH && comm != nullptr) {
+    hv = halo_view(ctl, comm, pc.halo[cur]);
+    tag_out = comm_tag(ctl, kTagPsiNew);
+  }
   double2 p = make_double2(0.0, 0.0);
   double mui = 0.0, epsi = 0.0;
   bool fx = false;
@@ -327,11 +344,11 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
   double dmax = 0.0;
   int failed = 0;
   if (in) {
-    double2 lap = row_dot_c(sv, si, w.kb, w.ke, psi, ctl, hv);
+    double2 lap = row_dot_c<SH>(sv, si, w.kb, w.ke, psi, ctl, hv);
     if (fx) lap = p;
     const PsiOut o = psi_update(p, lap, mui, epsi, ctl->gamma, ctl->u, dt);
     out[w.row] = o.psi;
-    if (comm != nullptr) push_row(comm, pc.push[cur ^ 1], tag_out, w.row, o.psi);
+    if (SH && comm != nullptr) push_row(comm, pc.push[cur ^ 1], tag_out, w.row, o.psi);
     if (sq_out != nullptr) sq_out[w.row] = o.sq;
     failed = o.failed;
     const double d = fabs(o.sq - (p.x * p.x + p.y * p.y));
@@ -363,6 +380,7 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
 //   b_i   = -areas_i * rhs_i ;   r_i = b_i - (A mu)_i ;  bb = ||b||^2, rr = ||r||^2
 // (reference solve_for_observables, solver.py:507-510; identity: SURVEY.md appendix A).
 // The complex and the real matrix share one CSR structure and are staged together.
+template <bool SH>
 __global__ void __launch_bounds__(kWinRows)
 kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, WinCsr m,
           const double2* __restrict__ lval, const double* __restrict__ aval,
@@ -383,9 +401,14 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
   const bool live = (ctl->status == 0);
   const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
   const bool in = live && w.row < m.rows;
-  const HaloView hpsi = halo_view(ctl, comm, pc.halo[ctl->cur]);
-  const HaloView hmu = halo_view(ctl, comm, mu_halo);
-  const unsigned int tag_out = comm != nullptr ? comm_tag(ctl, r_push.tag_mode) : 0u;
+  HaloView hpsi, hmu;
+  hpsi.n_owned = hmu.n_owned = 0x7fffffff; hpsi.box = hmu.box = nullptr; hpsi.tag = hmu.tag = 0u;
+  unsigned int tag_out = 0u;
+  if (SH && comm != nullptr) {
+    hpsi = halo_view(ctl, comm, pc.halo[ctl->cur]);
+    hmu = halo_view(ctl, comm, mu_halo);
+    tag_out = comm_tag(ctl, r_push.tag_mode);
+  }
   double2 p = make_double2(0.0, 0.0);
   double ai = 0.0, bt = 0.0;
   if (in) {
@@ -397,15 +420,15 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
   if (!live) return;
   double dbb = 0.0, drr = 0.0;
   if (in) {
-    const double2 lap = row_dot_c(sl, si, w.kb, w.ke, psi, ctl, hpsi);
-    const double am = row_dot(sa, si, w.kb, w.ke, mu, ctl, hmu);
+    const double2 lap = row_dot_c<SH>(sl, si, w.kb, w.ke, psi, ctl, hpsi);
+    const double am = row_dot<SH>(sa, si, w.kb, w.ke, mu, ctl, hmu);
     const double rhs = (p.x * lap.y - p.y * lap.x) - bt;
     if (rhs_raw != nullptr) rhs_raw[w.row] = rhs;
     const double bi = -ai * rhs;
     const double ri = bi - am;
     b[w.row] = bi;
     r[w.row] = ri;
-    if (comm != nullptr) push_row(comm, r_push, tag_out, w.row, ri);  // iteration 0's V-cycle input
+    if (SH && comm != nullptr) push_row(comm, r_push, tag_out, w.row, ri);  // iteration 0's V-cycle input
     dbb = bi * bi;
     drr = ri * ri;
   }
@@ -430,7 +453,7 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
     a0 = block_sum(a0, red);
     a1 = block_sum(a1, red);
     if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0
-      if (comm != nullptr) {
+      if (SH && comm != nullptr) {
         double v[2] = {a0, a1};
         comm_allreduce(ctl, comm, v, 2, false);
         a0 = v[0];
@@ -460,7 +483,7 @@ kw_psi_laplacian(WinCsr m, const double2* __restrict__ lval,
   if (w.row < m.rows) {
     HaloView none;
     none.n_owned = 0x7fffffff; none.box = nullptr; none.tag = 0;
-    const double2 lap = row_dot_c(sv, si, w.kb, w.ke, x, nullptr, none);
+    const double2 lap = row_dot_c<false>(sv, si, w.kb, w.ke, x, nullptr, none);
     y[w.row] = fixed[w.row] ? x[w.row] : lap;
   }
 }

@@ -587,14 +587,20 @@ void Engine::configure_kernels() {
   auto allow = [&](const void* f) {
     TDGL_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   };
-  allow(reinterpret_cast<const void*>(&kw_real<kOpSpmvDot>));
-  allow(reinterpret_cast<const void*>(&kw_real<kOpResidual>));
-  allow(reinterpret_cast<const void*>(&kw_real<kOpPresmooth>));
-  allow(reinterpret_cast<const void*>(&kw_real<kOpJacobi>));
-  allow(reinterpret_cast<const void*>(&kw_real<kOpPlain>));
-  allow(reinterpret_cast<const void*>(&kw_real<kOpPlainAdd>));
-  allow(reinterpret_cast<const void*>(&kw_psi_step));
-  allow(reinterpret_cast<const void*>(&kw_mu_rhs));
+#define TDGL_ALLOW_REAL(OP)                                            \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, false>));           \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, true>));
+  TDGL_ALLOW_REAL(kOpSpmvDot)
+  TDGL_ALLOW_REAL(kOpResidual)
+  TDGL_ALLOW_REAL(kOpPresmooth)
+  TDGL_ALLOW_REAL(kOpJacobi)
+  TDGL_ALLOW_REAL(kOpPlain)
+  TDGL_ALLOW_REAL(kOpPlainAdd)
+#undef TDGL_ALLOW_REAL
+  allow(reinterpret_cast<const void*>(&kw_psi_step<false>));
+  allow(reinterpret_cast<const void*>(&kw_psi_step<true>));
+  allow(reinterpret_cast<const void*>(&kw_mu_rhs<false>));
+  allow(reinterpret_cast<const void*>(&kw_mu_rhs<true>));
   allow(reinterpret_cast<const void*>(&kw_psi_laplacian));
 }
 
@@ -605,8 +611,12 @@ template <int OP>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
   const size_t smem = static_cast<size_t>(A.m.cap) * 12;
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
-  launch_k(kw_real<OP>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
-           partials_.p, counter_.p);
+  if (comm_on_)
+    launch_k(kw_real<OP, true>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
+             partials_.p, counter_.p);
+  else
+    launch_k(kw_real<OP, false>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
+             partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -734,19 +744,28 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
 }
 
 void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
-  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
-           ctl_.p, comm(), comm_on_ ? make_psi_comm() : PsiComm(), site_csr(), lval_.p, fixed_.p,
-           psi_[0].p, psi_[1].p, psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override);
+  if (comm_on_)
+    launch_k(kw_psi_step<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
+             ctl_.p, comm(), make_psi_comm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
+             psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override);
+  else
+    launch_k(kw_psi_step<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
+             ctl_.p, comm(), PsiComm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
+             psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_mu_rhs(double* rhs_raw) {
-  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
-           ctl_.p, comm(), comm_on_ ? make_psi_comm() : PsiComm(),
-           comm_on_ ? make_halo(0, kVecMu, kTagMuPrev) : HaloArgs(),
-           comm_on_ ? make_push(0, kVecCgR, kTagIter0) : PushArgs(), site_csr(), lval_.p, aval_.p,
-           psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p,
-           counter_.p);
+  if (comm_on_)
+    launch_k(kw_mu_rhs<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
+             ctl_.p, comm(), make_psi_comm(), make_halo(0, kVecMu, kTagMuPrev),
+             make_push(0, kVecCgR, kTagIter0), site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p,
+             mu_.p, areas_.p, bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
+  else
+    launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
+             ctl_.p, comm(), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p, aval_.p,
+             psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p, cg_b_.p, cg_r_.p, rhs_raw,
+             partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -1160,7 +1179,7 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
   h_ctl_->disc_flag = 0;
   h_ctl_->status = 0;
   push_ctl();
-  launch_k(kw_psi_step, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
+  launch_k(kw_psi_step<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
            ctl_.p, static_cast<const Comm*>(nullptr), PsiComm(), site_csr(), lval_.p, fixed_.p, pin.p,
            pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p, dt);
   TDGL_LAUNCH_CHECK();
@@ -1188,7 +1207,7 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   TDGL_LAUNCH_CHECK();
   sync_ctl_to_host();
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
-  launch_k(kw_mu_rhs, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
+  launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
            ctl_.p, static_cast<Comm*>(nullptr), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p,
            aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p, raw.p, partials_.p,
            counter_.p);
