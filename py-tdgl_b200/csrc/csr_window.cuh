@@ -76,12 +76,14 @@ struct WinRow {
 // Issues the window's bulk copies and returns this thread's row extent.  SA / SB are the
 // element sizes of up to two value arrays that share the matrix structure (SB = 0: one).
 // Shared layout: [valA: cap*SA][valB: cap*SB][idx: cap*4].  Ends with __syncthreads().
-template <int SA, int SB>
+// LPR = lanes per row: 1 (a thread per row) or, for matrices with long rows, 4 (blockDim / 4
+// rows per window; the lanes of a row split its entries).
+template <int SA, int SB, int LPR = 1>
 __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA,
                                                const void* valB, unsigned char* smem,
                                                uint64_t* bar) {
   griddep_launch_dependents();
-  const int r0 = blockIdx.x * blockDim.x;
+  const int r0 = blockIdx.x * (blockDim.x / LPR);
   const int2 wd = __ldg(m.win + blockIdx.x);
   const int k0a = wd.x;
   if (threadIdx.x == 0) {
@@ -99,7 +101,7 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
     }
   }
   WinRow w;
-  w.row = r0 + threadIdx.x;
+  w.row = r0 + threadIdx.x / LPR;
   w.kb = w.ke = 0;
   if (w.row < m.rows) {
     w.kb = __ldg(m.ptr + w.row) - k0a;
@@ -292,6 +294,54 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
       if (SH && comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       if (threadIdx.x == 0) *a.red_out = total;
     }
+  }
+}
+
+// Restriction b' = R r.  The rows of R = P^T are long (~27 entries on the fine level) and
+// there are few of them: four lanes share a row (entries k, k + 4, ... each), so the chain of
+// dependent gathers per thread is a quarter as long and four times as many are in flight.
+template <bool SH>
+__global__ void __launch_bounds__(kWinRows)
+kw_restrict(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a) {
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  __shared__ uint64_t bar;
+  const WinRow w = window_stage<8, 0, 4>(m, a.val, nullptr, win_smem, &bar);
+  const double* sv = reinterpret_cast<const double*>(win_smem);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 8);
+  griddep_wait();
+  const bool live = (ctl->status == 0);
+  const bool in = live && w.row < m.rows;
+  const int sub = threadIdx.x & 3;
+  HaloView hv;
+  hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
+  unsigned int tag_out = 0u;
+  if (SH) {
+    hv = halo_view(ctl, comm, a.halo);
+    if (comm != nullptr && a.push.bnd != nullptr) tag_out = comm_tag(ctl, a.push.tag_mode);
+  }
+  mbar_wait(&bar, 0);
+  if (!live) return;
+  double s = 0.0;
+  if (in) {
+    const int top = SH ? hv.n_owned - 1 : 0x7fffffff;
+#pragma unroll 2
+    for (int k = w.kb + sub; k < w.ke; k += 8) {
+      const int k1 = k + 4;
+      const bool two = k1 < w.ke;
+      const int j0 = si[k], j1 = two ? si[k1] : j0;
+      double x0 = __ldg(a.x + min(j0, top)), x1 = __ldg(a.x + min(j1, top));
+      if (SH && max(j0, j1) > top) {
+        if (j0 > top) x0 = halo_get(ctl, hv, a.x, j0);
+        if (j1 > top) x1 = halo_get(ctl, hv, a.x, j1);
+      }
+      s = fma(sv[k], x0, s);
+      s = fma(two ? sv[k1] : 0.0, x1, s);
+    }
+  }
+  s = group_sum<4>(s);
+  if (in && sub == 0) {
+    a.y[w.row] = s;
+    if (SH && tag_out != 0u) push_row(comm, a.push, tag_out, w.row, s);
   }
 }
 

@@ -79,6 +79,7 @@ struct CsrView {
 
 struct DevCsr {
   int rows = 0, cols = 0, win = kWinRows, cap = 0;
+  int lpr = 1;            // lanes per row of the kernel that applies it (4: restriction)
   int64_t nnz = 0;
   DevBuf<int> ptr, idx;   // idx / val carry 4 padding elements (see csr_window.cuh)
   DevBuf<int2> wdesc;     // per window {first staged nnz, staged nnz count}
@@ -125,8 +126,8 @@ inline std::vector<int2> window_descriptors(const std::vector<int32_t>& ptr, int
 
 // Rows per window: as many as fit `budget` bytes of shared memory at `bytes_per_nnz`.
 inline int pick_window(const std::vector<int32_t>& ptr, int64_t rows, int bytes_per_nnz,
-                       int budget, int* cap_out) {
-  for (int win = kWinRows; win >= 32; win /= 2) {
+                       int budget, int* cap_out, int max_rows = kWinRows) {
+  for (int win = max_rows; win >= 32; win /= 2) {
     const int cap = window_cap(ptr, rows, win);
     if (static_cast<int64_t>(cap) * bytes_per_nnz <= budget || win == 32) {
       if (static_cast<int64_t>(cap) * bytes_per_nnz > 200 * 1024)
@@ -295,7 +296,8 @@ class Engine {
     int g = (n + kBlock - 1) / kBlock;
     return g < 1 ? 1 : (g > 1184 ? 1184 : g);  // 148 SMs x 8 resident blocks
   }
-  void upload_csr(const HostCsr<double>& h, DevCsr& d);
+  void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 1);
+  void launch_restrict(const CsrView& A, const RealArgs& a);
   void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);
   void launch_plain(const CsrView& A, const double* x, double* y, bool add);
   void launch_presmooth(const CsrView& A, const double* dinv, double omega, const double* b,

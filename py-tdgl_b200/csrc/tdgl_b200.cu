@@ -41,11 +41,14 @@ static std::vector<int> morton_permutation(const double* xy, int64_t n) {
   return perm;
 }
 
-void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d) {
+void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row) {
   d.rows = static_cast<int>(h.rows);
   d.cols = static_cast<int>(h.cols);
   d.nnz = h.nnz();
-  d.win = pick_window(h.ptr, h.rows, 12, 64 * 1024, &d.cap);
+  d.lpr = lanes_per_row;
+  // (a CTA has at most kWinRows threads: windows of a matrix with several lanes per row
+  // hold correspondingly fewer rows)
+  d.win = pick_window(h.ptr, h.rows, 12, 64 * 1024, &d.cap, kWinRows / lanes_per_row);
   std::vector<int32_t> idx(h.idx);
   std::vector<double> val(h.val);
   idx.resize(idx.size() + 4, 0);   // bulk copies round the window up to 4 entries
@@ -350,7 +353,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
         rrows = compute_row_list(plan_, li + 1, rank_);
       }
       upload_csr(extract_rows(hl.P, rows, plan_, li + 1, rank_), dl.P);
-      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R);
+      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R, 4);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.P.rows, dl.P.win));
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.R.rows, dl.R.win));
     }
@@ -602,6 +605,8 @@ void Engine::configure_kernels() {
   allow(reinterpret_cast<const void*>(&kw_mu_rhs<false>));
   allow(reinterpret_cast<const void*>(&kw_mu_rhs<true>));
   allow(reinterpret_cast<const void*>(&kw_psi_laplacian));
+  allow(reinterpret_cast<const void*>(&kw_restrict<false>));
+  allow(reinterpret_cast<const void*>(&kw_restrict<true>));
 }
 
 #define TDGL_LAUNCH_CHECK()                                                                \
@@ -626,10 +631,20 @@ void Engine::launch_spmv(const CsrView& A, const double* x, double* y, double* d
   launch_real<kOpSpmvDot>(A, a);
 }
 
+void Engine::launch_restrict(const CsrView& A, const RealArgs& a) {
+  if (A.m.rows < 1) return;
+  const size_t smem = static_cast<size_t>(A.m.cap) * 12;
+  if (comm_on_)
+    launch_k(kw_restrict<true>, grid_win(A.m.rows, A.win), A.win * 4, smem, ctl_.p, comm(), A.m, a);
+  else
+    launch_k(kw_restrict<false>, grid_win(A.m.rows, A.win), A.win * 4, smem, ctl_.p, comm(), A.m, a);
+  TDGL_LAUNCH_CHECK();
+}
+
 void Engine::launch_plain(const CsrView& A, const double* x, double* y, bool add) {
   RealArgs a;
   a.val = A.val; a.x = x; a.y = y;
-  if (add) launch_real<kOpPlainAdd>(A, a); else launch_real<kOpPlain>(A, a);
+  if (add) launch_real<kOpPlainAdd>(A, a); else launch_restrict(A, a);
 }
 
 void Engine::launch_presmooth(const CsrView& A, const double* dinv, double omega,
@@ -703,7 +718,7 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
       a.val = lv.R.view().val; a.x = lv.r.p; a.y = levels_[li + 1].b.p;
       if (li < rep) a.halo = make_halo(li, chan(li, 1), kTagIter);
       if (li + 1 <= rep) a.push = make_push(li + 1, chan(li + 1, 2), kTagIter);
-      launch_real<kOpPlain>(lv.R.view(), a);
+      launch_restrict(lv.R.view(), a);
     }
     if (li + 1 == rep) enqueue_unpack(rep, chan(rep, 2), kTagIter, levels_[rep].b.p);
   }
