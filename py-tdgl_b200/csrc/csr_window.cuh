@@ -209,18 +209,24 @@ struct PsiComm {
 //  kOpPlain     y = A x ;  kOpPlainAdd  y += A x  (restriction / prolongation)
 // SH: instantiated for the sharded engine (halo columns out of the mailbox, boundary rows
 // pushed to the peers); the single-GPU instantiation carries none of that code.
-template <int OP, bool SH>
+// LPR: lanes per row.  1 = a thread per row (the mesh operators, ~7 entries per row); 4 = four
+// lanes share a row, entries k, k + 4, ... each (the AMG operators: rows of 15-30 entries and
+// few of them — a quarter of the dependent-gather chain per thread, four times the gathers in
+// flight; measured 25.8 -> ~12 us for the fine-level restriction).
+template <int OP, bool SH, int LPR>
 __global__ void __launch_bounds__(kWinRows)
 kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned int* counter) {
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double red[32];
-  const WinRow w = window_stage<8, 0>(m, a.val, nullptr, win_smem, &bar);
+  const WinRow w = window_stage<8, 0, LPR>(m, a.val, nullptr, win_smem, &bar);
   const double* sv = reinterpret_cast<const double*>(win_smem);
   const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 8);
   griddep_wait();
   const bool live = (ctl->status == 0);
   const bool in = live && w.row < m.rows;
+  const int sub = threadIdx.x & (LPR - 1);   // lane of the row (LPR lanes share a long row)
+  const bool lead = in && sub == 0;          // the lane that owns the row's epilogue
   HaloView hv;
   hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
   unsigned int tag_out = 0u;
@@ -230,7 +236,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   }
   // row-local operands travel while the window lands
   double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
-  if (in) {
+  if (lead) {
     if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi) bi = a.b[w.row];
     if (OP == kOpPresmooth || OP == kOpJacobi) di = a.dinv[w.row];
     if (OP == kOpSpmvDot || OP == kOpJacobi) xi = a.x[w.row];
@@ -240,29 +246,46 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   mbar_wait(&bar, 0);
   if (!live) return;
   double d = 0.0;
+  double s = 0.0;
   if (in) {
-    double s;
+    const int top = SH ? hv.n_owned - 1 : 0x7fffffff;
     if (OP == kOpPresmooth) {
       // x_j = omega dinv_j b_j on the fly
-      s = 0.0;
       const int last = w.ke - 1;
-      for (int k = w.kb; k < w.ke; k += 2) {
-        const int k1 = min(k + 1, last);
+      for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
+        const int k1 = min(k + LPR, last);
+        const bool two = k + LPR < w.ke;
         const int j0 = si[k], j1 = si[k1];
-        double b0 = __ldg(a.b + (SH ? min(j0, hv.n_owned - 1) : j0)),
-               b1 = __ldg(a.b + (SH ? min(j1, hv.n_owned - 1) : j1));
-        if (SH && max(j0, j1) >= hv.n_owned) {
-          if (j0 >= hv.n_owned) b0 = halo_get(ctl, hv, a.b, j0);
-          if (j1 >= hv.n_owned) b1 = halo_get(ctl, hv, a.b, j1);
+        double b0 = __ldg(a.b + min(j0, top)), b1 = __ldg(a.b + min(j1, top));
+        if (SH && max(j0, j1) > top) {
+          if (j0 > top) b0 = halo_get(ctl, hv, a.b, j0);
+          if (j1 > top) b1 = halo_get(ctl, hv, a.b, j1);
         }
         const double t0 = __ldg(a.dinv + j0) * b0;
         const double t1 = __ldg(a.dinv + j1) * b1;
         s = fma(sv[k], a.omega * t0, s);
-        s = fma((k + 1 < w.ke) ? sv[k1] : 0.0, a.omega * t1, s);
+        s = fma(two ? sv[k1] : 0.0, a.omega * t1, s);
       }
-    } else {
+    } else if (LPR == 1) {
       s = row_dot<SH>(sv, si, w.kb, w.ke, a.x, ctl, hv);
+    } else {
+#pragma unroll 2
+      for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
+        const int k1 = k + LPR;
+        const bool two = k1 < w.ke;
+        const int j0 = si[k], j1 = two ? si[k1] : j0;
+        double x0 = __ldg(a.x + min(j0, top)), x1 = __ldg(a.x + min(j1, top));
+        if (SH && max(j0, j1) > top) {
+          if (j0 > top) x0 = halo_get(ctl, hv, a.x, j0);
+          if (j1 > top) x1 = halo_get(ctl, hv, a.x, j1);
+        }
+        s = fma(sv[k], x0, s);
+        s = fma(two ? sv[k1] : 0.0, x1, s);
+      }
     }
+  }
+  if (LPR > 1) s = group_sum<LPR>(s);
+  if (lead) {
     double out;  // the value other shards may need
     if (OP == kOpSpmvDot) {
       a.y[w.row] = out = s;
@@ -294,54 +317,6 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
       if (SH && comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
       if (threadIdx.x == 0) *a.red_out = total;
     }
-  }
-}
-
-// Restriction b' = R r.  The rows of R = P^T are long (~27 entries on the fine level) and
-// there are few of them: four lanes share a row (entries k, k + 4, ... each), so the chain of
-// dependent gathers per thread is a quarter as long and four times as many are in flight.
-template <bool SH>
-__global__ void __launch_bounds__(kWinRows)
-kw_restrict(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a) {
-  extern __shared__ __align__(128) unsigned char win_smem[];
-  __shared__ uint64_t bar;
-  const WinRow w = window_stage<8, 0, 4>(m, a.val, nullptr, win_smem, &bar);
-  const double* sv = reinterpret_cast<const double*>(win_smem);
-  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 8);
-  griddep_wait();
-  const bool live = (ctl->status == 0);
-  const bool in = live && w.row < m.rows;
-  const int sub = threadIdx.x & 3;
-  HaloView hv;
-  hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
-  unsigned int tag_out = 0u;
-  if (SH) {
-    hv = halo_view(ctl, comm, a.halo);
-    if (comm != nullptr && a.push.bnd != nullptr) tag_out = comm_tag(ctl, a.push.tag_mode);
-  }
-  mbar_wait(&bar, 0);
-  if (!live) return;
-  double s = 0.0;
-  if (in) {
-    const int top = SH ? hv.n_owned - 1 : 0x7fffffff;
-#pragma unroll 2
-    for (int k = w.kb + sub; k < w.ke; k += 8) {
-      const int k1 = k + 4;
-      const bool two = k1 < w.ke;
-      const int j0 = si[k], j1 = two ? si[k1] : j0;
-      double x0 = __ldg(a.x + min(j0, top)), x1 = __ldg(a.x + min(j1, top));
-      if (SH && max(j0, j1) > top) {
-        if (j0 > top) x0 = halo_get(ctl, hv, a.x, j0);
-        if (j1 > top) x1 = halo_get(ctl, hv, a.x, j1);
-      }
-      s = fma(sv[k], x0, s);
-      s = fma(two ? sv[k1] : 0.0, x1, s);
-    }
-  }
-  s = group_sum<4>(s);
-  if (in && sub == 0) {
-    a.y[w.row] = s;
-    if (SH && tag_out != 0u) push_row(comm, a.push, tag_out, w.row, s);
   }
 }
 

@@ -74,17 +74,18 @@ struct DevBuf {
 struct CsrView {
   WinCsr m;
   const double* val = nullptr;
-  int win = kWinRows;  // rows per window = threads per CTA
+  int win = kWinRows;  // rows per window
+  int lpr = 1;         // lanes per row: threads per CTA = win * lpr
 };
 
 struct DevCsr {
   int rows = 0, cols = 0, win = kWinRows, cap = 0;
-  int lpr = 1;            // lanes per row of the kernel that applies it (4: restriction)
+  int lpr = 1;            // lanes per row of the kernels that apply it (4: long rows)
   int64_t nnz = 0;
   DevBuf<int> ptr, idx;   // idx / val carry 4 padding elements (see csr_window.cuh)
   DevBuf<int2> wdesc;     // per window {first staged nnz, staged nnz count}
   DevBuf<double> val;
-  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p, wdesc.p}, val.p, win}; }
+  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p, wdesc.p}, val.p, win, lpr}; }
 };
 
 struct DevLevel {
@@ -296,8 +297,7 @@ class Engine {
     int g = (n + kBlock - 1) / kBlock;
     return g < 1 ? 1 : (g > 1184 ? 1184 : g);  // 148 SMs x 8 resident blocks
   }
-  void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 1);
-  void launch_restrict(const CsrView& A, const RealArgs& a);
+  void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 0);
   void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);
   void launch_plain(const CsrView& A, const double* x, double* y, bool add);
   void launch_presmooth(const CsrView& A, const double* dinv, double omega, const double* b,
@@ -324,7 +324,7 @@ class Engine {
   void sync_ctl_to_host();
   void push_ctl();
   DevBuf<double> aval_;  // level-0 mu matrix values; structure shared with ptr_/idx_
-  CsrView A0() const { return CsrView{site_csr(), aval_.p, win0_}; }
+  CsrView A0() const { return CsrView{site_csr(), aval_.p, win0_, 1}; }
   CsrView levelA(size_t l) const { return l == 0 ? A0() : levels_[l].A.view(); }
 };
 

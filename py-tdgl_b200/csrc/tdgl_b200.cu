@@ -45,6 +45,8 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row) 
   d.rows = static_cast<int>(h.rows);
   d.cols = static_cast<int>(h.cols);
   d.nnz = h.nnz();
+  if (lanes_per_row == 0)  // choose by the average row length
+    lanes_per_row = (h.rows > 0 && h.nnz() > 10 * h.rows) ? 4 : 1;
   d.lpr = lanes_per_row;
   // (a CTA has at most kWinRows threads: windows of a matrix with several lanes per row
   // hold correspondingly fewer rows)
@@ -333,7 +335,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     dl.nx = static_cast<int>(plan_.local_size(li, rank_));
     for (int64_t gr : rows) amg_nnz_ += hl.A.ptr[gr + 1] - hl.A.ptr[gr];
     if (l > 0) {
-      upload_csr(extract_rows(hl.A, rows, plan_, li, rank_), dl.A);
+      upload_csr(extract_rows(hl.A, rows, plan_, li, rank_), dl.A, 0);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.A.rows, dl.A.win));
     }
     {
@@ -352,8 +354,8 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       } else {
         rrows = compute_row_list(plan_, li + 1, rank_);
       }
-      upload_csr(extract_rows(hl.P, rows, plan_, li + 1, rank_), dl.P);
-      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R, 4);
+      upload_csr(extract_rows(hl.P, rows, plan_, li + 1, rank_), dl.P, 0);
+      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R, 0);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.P.rows, dl.P.win));
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.R.rows, dl.R.win));
     }
@@ -591,8 +593,10 @@ void Engine::configure_kernels() {
     TDGL_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   };
 #define TDGL_ALLOW_REAL(OP)                                            \
-  allow(reinterpret_cast<const void*>(&kw_real<OP, false>));           \
-  allow(reinterpret_cast<const void*>(&kw_real<OP, true>));
+  allow(reinterpret_cast<const void*>(&kw_real<OP, false, 1>));        \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, true, 1>));         \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, false, 4>));        \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, true, 4>));
   TDGL_ALLOW_REAL(kOpSpmvDot)
   TDGL_ALLOW_REAL(kOpResidual)
   TDGL_ALLOW_REAL(kOpPresmooth)
@@ -605,8 +609,6 @@ void Engine::configure_kernels() {
   allow(reinterpret_cast<const void*>(&kw_mu_rhs<false>));
   allow(reinterpret_cast<const void*>(&kw_mu_rhs<true>));
   allow(reinterpret_cast<const void*>(&kw_psi_laplacian));
-  allow(reinterpret_cast<const void*>(&kw_restrict<false>));
-  allow(reinterpret_cast<const void*>(&kw_restrict<true>));
 }
 
 #define TDGL_LAUNCH_CHECK()                                                                \
@@ -616,12 +618,18 @@ template <int OP>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
   const size_t smem = static_cast<size_t>(A.m.cap) * 12;
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
-  if (comm_on_)
-    launch_k(kw_real<OP, true>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
-             partials_.p, counter_.p);
-  else
-    launch_k(kw_real<OP, false>, grid_win(A.m.rows, A.win), A.win, smem, ctl_.p, comm(), A.m, a,
-             partials_.p, counter_.p);
+  const int grid = grid_win(A.m.rows, A.win), block = A.win * A.lpr;
+  if (A.lpr == 4) {
+    if (comm_on_)
+      launch_k(kw_real<OP, true, 4>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+    else
+      launch_k(kw_real<OP, false, 4>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+  } else {
+    if (comm_on_)
+      launch_k(kw_real<OP, true, 1>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+    else
+      launch_k(kw_real<OP, false, 1>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+  }
   TDGL_LAUNCH_CHECK();
 }
 
@@ -631,20 +639,10 @@ void Engine::launch_spmv(const CsrView& A, const double* x, double* y, double* d
   launch_real<kOpSpmvDot>(A, a);
 }
 
-void Engine::launch_restrict(const CsrView& A, const RealArgs& a) {
-  if (A.m.rows < 1) return;
-  const size_t smem = static_cast<size_t>(A.m.cap) * 12;
-  if (comm_on_)
-    launch_k(kw_restrict<true>, grid_win(A.m.rows, A.win), A.win * 4, smem, ctl_.p, comm(), A.m, a);
-  else
-    launch_k(kw_restrict<false>, grid_win(A.m.rows, A.win), A.win * 4, smem, ctl_.p, comm(), A.m, a);
-  TDGL_LAUNCH_CHECK();
-}
-
 void Engine::launch_plain(const CsrView& A, const double* x, double* y, bool add) {
   RealArgs a;
   a.val = A.val; a.x = x; a.y = y;
-  if (add) launch_real<kOpPlainAdd>(A, a); else launch_restrict(A, a);
+  if (add) launch_real<kOpPlainAdd>(A, a); else launch_real<kOpPlain>(A, a);
 }
 
 void Engine::launch_presmooth(const CsrView& A, const double* dinv, double omega,
@@ -718,7 +716,7 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
       a.val = lv.R.view().val; a.x = lv.r.p; a.y = levels_[li + 1].b.p;
       if (li < rep) a.halo = make_halo(li, chan(li, 1), kTagIter);
       if (li + 1 <= rep) a.push = make_push(li + 1, chan(li + 1, 2), kTagIter);
-      launch_restrict(lv.R.view(), a);
+      launch_real<kOpPlain>(lv.R.view(), a);
     }
     if (li + 1 == rep) enqueue_unpack(rep, chan(rep, 2), kTagIter, levels_[rep].b.p);
   }
