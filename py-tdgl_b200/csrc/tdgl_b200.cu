@@ -183,7 +183,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   const std::vector<int64_t> off0 = equal_offsets(Ng_, world_);
   AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24, &off0);
   if (H.nc > 4096) throw std::runtime_error("AMG coarsening stalled (coarsest level too large)");
-  plan_ = make_plan(H, cfg_.replicate_below > 0 ? cfg_.replicate_below : kReplicateBelow);
+  {
+    int64_t below = cfg_.replicate_below > 0 ? cfg_.replicate_below : kReplicateBelow;
+    if (const char* e = std::getenv("TDGL_B200_REPLICATE_BELOW")) below = std::max<int64_t>(1, std::atoll(e));
+    plan_ = make_plan(H, below);
+  }
   layouts_.resize(world_);
   for (int q = 0; q < world_; ++q) layouts_[q] = arena_layout(plan_, q);
   const size_t L = H.levels.size();
