@@ -41,6 +41,52 @@ static std::vector<int> morton_permutation(const double* xy, int64_t n) {
   return perm;
 }
 
+// Sharded numbering: Z-order, cut into `world` equal ranges, and inside every range the rows
+// near the cut (within `depth` edges of a row of another range) moved to the front.  A rank's
+// kernels then compute — and store into the neighbours' mailboxes — the rows the neighbours
+// wait for FIRST, and the CTAs that read halo columns (the same rows) run while the
+// neighbour's matching stores, issued at the start of its previous kernel, have long landed:
+// the exchange has a whole kernel of slack instead of sitting on the critical path.
+static std::vector<int> shard_permutation(const double* xy, int64_t n, int64_t n_edges,
+                                          const int64_t* edges, int world, int depth = 2) {
+  std::vector<int> perm = morton_permutation(xy, n);
+  if (world <= 1) return perm;
+  std::vector<int> inv(n);
+  for (int64_t i = 0; i < n; ++i) inv[perm[i]] = static_cast<int>(i);
+  std::vector<int64_t> off(world + 1);
+  for (int r = 0; r <= world; ++r) off[r] = n * r / world;
+  auto owner = [&](int pos) {
+    return static_cast<int>(std::upper_bound(off.begin(), off.end(), static_cast<int64_t>(pos)) - off.begin()) - 1;
+  };
+  // level[pos]: 0 = not near a cut, k = reached in the k-th sweep
+  std::vector<unsigned char> near(n, 0);
+  for (int64_t e = 0; e < 2 * n_edges; ++e)
+    if (edges[e] < 0 || edges[e] >= n) throw std::invalid_argument("edge index out of range");
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int a = inv[edges[2 * e]], b = inv[edges[2 * e + 1]];
+    if (owner(a) != owner(b)) near[a] = near[b] = 1;
+  }
+  for (int d = 2; d <= depth; ++d) {
+    std::vector<unsigned char> next(near);
+    for (int64_t e = 0; e < n_edges; ++e) {
+      const int a = inv[edges[2 * e]], b = inv[edges[2 * e + 1]];
+      if (owner(a) != owner(b)) continue;
+      if (near[a] && !near[b]) next[b] = static_cast<unsigned char>(d);
+      if (near[b] && !near[a]) next[a] = static_cast<unsigned char>(d);
+    }
+    near.swap(next);
+  }
+  std::vector<int> out(n);
+  for (int r = 0; r < world; ++r) {
+    int64_t w = off[r];
+    for (int64_t p = off[r]; p < off[r + 1]; ++p)
+      if (near[p]) out[w++] = perm[p];
+    for (int64_t p = off[r]; p < off[r + 1]; ++p)
+      if (!near[p]) out[w++] = perm[p];
+  }
+  return out;
+}
+
 void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row) {
   d.rows = static_cast<int>(h.rows);
   d.cols = static_cast<int>(h.cols);
@@ -132,7 +178,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
 
   // ---- site numbering (global) --------------------------------------------------------------
   if (cfg_.reorder == 1 && sites_xy != nullptr) {
-    perm_ = morton_permutation(sites_xy, Ng_);
+    perm_ = shard_permutation(sites_xy, Ng_, n_edges, edges, world_);
   } else {
     if (world_ > 1 && sites_xy == nullptr)
       throw std::invalid_argument("a sharded engine needs the site coordinates");
@@ -1727,7 +1773,7 @@ int tdgl_host_shard_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges
   using namespace tdgl;
   try {
     if (sites_xy == nullptr) throw std::invalid_argument("site coordinates required");
-    std::vector<int> perm = morton_permutation(sites_xy, n_sites), inv(n_sites);
+    std::vector<int> perm = shard_permutation(sites_xy, n_sites, n_edges, edges, world), inv(n_sites);
     for (int64_t i = 0; i < n_sites; ++i) inv[perm[i]] = static_cast<int>(i);
     std::vector<int32_t> e0(n_edges), e1(n_edges);
     for (int64_t e = 0; e < n_edges; ++e) { e0[e] = inv[edges[2 * e]]; e1[e] = inv[edges[2 * e + 1]]; }
@@ -1904,7 +1950,7 @@ int tdgl_host_shard_lists(int64_t n_sites, int64_t n_edges, const int64_t* edges
   using namespace tdgl;
   try {
     if (sites_xy == nullptr || rank < 0 || rank >= world) throw std::invalid_argument("bad arguments");
-    std::vector<int> perm = morton_permutation(sites_xy, n_sites), inv(n_sites);
+    std::vector<int> perm = shard_permutation(sites_xy, n_sites, n_edges, edges, world), inv(n_sites);
     for (int64_t i = 0; i < n_sites; ++i) inv[perm[i]] = static_cast<int>(i);
     std::vector<int32_t> e0(n_edges), e1(n_edges);
     for (int64_t e = 0; e < n_edges; ++e) { e0[e] = inv[edges[2 * e]]; e1[e] = inv[edges[2 * e + 1]]; }
