@@ -214,7 +214,7 @@ struct PsiComm {
 // few of them — a quarter of the dependent-gather chain per thread, four times the gathers in
 // flight; measured 25.8 -> ~12 us for the fine-level restriction).
 template <int OP, bool SH, int LPR>
-__global__ void __launch_bounds__(kWinRows)
+__global__ void __launch_bounds__(kWinRows, 8)   // 8 CTAs/SM = 2048 threads: <= 32 registers
 kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned int* counter) {
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
