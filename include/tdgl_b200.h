@@ -96,6 +96,13 @@ int tdgl_set_epsilon(tdgl_handle* h, const double* epsilon);
  * TDGLSolver.update_mu_boundary (solver.py:325-345). */
 int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary);
 
+/* dA_dt[E]: time derivative of the applied vector potential projected on the normalised
+ * edge directions, as TDGLSolver.update forms it for a time-dependent Parameter
+ * (solver.py:626-634); enters the rhs (solver.py:508) and the normal current (solver.py:519).
+ * NULL: static vector potential (dA_dt = 0).  Call tdgl_set_link_exponents with the new A
+ * as well (solver.py:635-639). */
+int tdgl_set_dA_dt(tdgl_handle* h, const double* dA_dt);
+
 /* psi[N] (complex128) and mu[N]: the `psi`, `mu` values Runner threads through update(). */
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu);
 

@@ -61,13 +61,24 @@ def operator_vectors(ref, solver, seed):
     return out
 
 
+def ramp_field(centers, b_max, t_ramp):
+    """Uniform field ramped linearly from 0 to ``b_max`` over ``t_ramp`` (the reference's
+    ``LinearRamp * ConstantField``), as a function t -> A[E, 2]."""
+    A1 = uniform_field_vector_potential(centers, 1.0)
+    return lambda t: min(max(t / t_ramp, 0.0), 1.0) * b_max * A1
+
+
 def case(name, *, width, height, h, b, disorder, terminals, currents, opts, end_time,
-         max_steps, holes=(), probe_xy=None, seed=0, record_every=250):
+         max_steps, holes=(), probe_xy=None, seed=0, record_every=250, ramp=None):
     ref = rl.load()
     pts = make_film_points(width, height, h, holes=holes, seed=seed)
     pts, tri = triangulate(pts, holes)
     mesh = rl.make_reference_mesh(pts, tri)          # the reference's own mesh arrays
     A = uniform_field_vector_potential(mesh.edge_mesh.centers, b)
+    A_func = None
+    if ramp is not None:      # (b_max, t_ramp): time-dependent vector potential
+        A_func = ramp_field(mesh.edge_mesh.centers, *ramp)
+        A = A_func(0.0)
     eps = gaussian_disorder(mesh.sites) if disorder else np.ones(len(mesh.sites))
     terms = ()
     if terminals:
@@ -84,8 +95,10 @@ def case(name, *, width, height, h, b, disorder, terminals, currents, opts, end_
     solver = rl.make_reference_solver(
         mesh, ro, A_applied=A, epsilon=eps,
         terminal_info=[ref.TerminalInfo(*t) for t in terms],
-        terminal_currents=currents, probe_points=probes)
+        terminal_currents=currents, probe_points=probes, A_func=A_func)
     data = mesh_arrays(mesh)
+    if ramp is not None:
+        data["ramp"] = np.asarray(ramp, float)
     data.update(A_applied=A, epsilon=eps, u=solver.u, gamma=solver.gamma)
     data.update(operator_vectors(ref, solver, seed + 1))
     for k, t in enumerate(terms):
@@ -141,6 +154,12 @@ if __name__ == "__main__":
          terminals=False, currents=None,
          opts=dict(solve_time=20.0, dt_init=1e-4, dt_max=1e-1),
          end_time=20.0, max_steps=None, probe_xy=[(-5.0, 0.0), (5.0, 0.0)])
+    # time-dependent vector potential: field ramped from 0 to 0.3 Bc2 over 2 time units,
+    # fixed dt (smooth regime: parity to roundoff-level tolerances at the end)
+    case("film20_ramp", width=20, height=20, h=0.35, b=0.0, disorder=True,
+         terminals=False, currents=None,
+         opts=dict(solve_time=1e9, adaptive=False, dt_init=2e-3, dt_max=2e-3),
+         end_time=1e9, max_steps=600, probe_xy=[(-5.0, 0.0), (5.0, 0.0)], ramp=(0.3, 2.0))
     # transport: terminals + holes + current, adaptive
     case("strip_transport", width=40, height=10, h=0.5, b=0.05, disorder=False,
          terminals=True, currents={"source": 2.0, "drain": -2.0},

@@ -148,8 +148,11 @@ def make_reference_solver(
     terminal_currents: Optional[Dict[str, float]] = None,
     current_func: Optional[Callable] = None,
     probe_points: Optional[Sequence[int]] = None,
+    A_func: Optional[Callable] = None,
 ):
     """Assemble a reference ``TDGLSolver`` without running its pint-dependent ``__init__``.
+    ``A_func``: t -> [E, 2] makes the vector potential time-dependent (the reference then
+    calls ``update_applied_vector_potential`` every step, solver.py:626-642).
 
     ``A_applied`` is the dimensionless (already ``A_scale``-d) vector potential at the edge
     centres, ``terminal_currents`` are already ``J_scale``-d (solver.py:176-185, 251-256).
@@ -208,6 +211,9 @@ def make_reference_solver(
     s.d_psi_sq_vals = []
     s.tentative_dt = options.dt_init
     s.dt_max = options.dt_max if options.adaptive else options.dt_init
+    if A_func is not None:
+        s.dynamic_vector_potential = True
+        s.update_applied_vector_potential = lambda time: np.asarray(A_func(time), float)
     return s
 
 
@@ -233,6 +239,8 @@ def run_reference(solver, *, end_time: float, max_steps: Optional[int] = None,
         normal_current=np.zeros(E),
         induced_vector_potential=np.zeros((E, 2)),
     )
+    if solver.dynamic_vector_potential:
+        values["applied_vector_potential"] = solver.current_A_applied
     time = 0.0
     dt = opts.dt_init
     dts = []
@@ -245,7 +253,7 @@ def run_reference(solver, *, end_time: float, max_steps: Optional[int] = None,
                           "mu": values["mu"].copy()})
         res = solver.update(state, running, dt, **values)
         new_dt = res[0]
-        values = dict(zip(values.keys(), res[1:6]))
+        values = dict(zip(values.keys(), res[1:1 + len(values)]))
         dts.append(float(new_dt))
         if time >= end_time or (max_steps is not None and i + 1 >= max_steps):
             break

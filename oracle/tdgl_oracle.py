@@ -200,6 +200,9 @@ class OracleSolver:
     current_func: Optional[Callable[[float], Dict[str, float]]] = None  # J_scale-d
     probe_points: Optional[Sequence[int]] = None
     d_psi_sq_vals: List[float] = field(default_factory=list)
+    # time-dependent vector potential: t -> [E, 2] (already A_scale-d); then ``A_applied``
+    # must be its value at t = 0 (solver.py:164-185)
+    A_func: Optional[Callable[[float], np.ndarray]] = None
 
     def __post_init__(self):
         o = self.options
@@ -213,6 +216,9 @@ class OracleSolver:
         self.operators = OracleOperators(self.mesh, self.fixed_sites,
                                          fix_psi=(o.terminal_psi is not None))
         self.operators.set_link_exponents(self.A_applied)
+        self.current_A_applied = np.asarray(self.A_applied, float)
+        d = np.asarray(self.mesh.edge_mesh.directions, float)
+        self.normalized_directions = d / np.linalg.norm(d, axis=1)[:, None]
         n = len(self.mesh.sites)
         self.psi_init = np.ones(n, dtype=np.complex128)       # solver.py:285-287
         if o.terminal_psi is not None:
@@ -261,15 +267,26 @@ class OracleSolver:
         jn = -(ops.mu_gradient @ mu) - dA_dt
         return mu, js, jn
 
-    def update(self, step: int, time: float, psi, mu):
-        """One time step — solver.py:580-714 (static A and epsilon, no screening).
-        Returns (dt, psi', mu', J_s, J_n)."""
+    def update(self, step: int, time: float, psi, mu, dt_prev: Optional[float] = None,
+               A_prev: Optional[np.ndarray] = None):
+        """One time step — solver.py:580-714 (static epsilon, no screening).  ``dt_prev`` is
+        the ``dt`` argument of the reference's ``update`` (the previous step's dt) and
+        ``A_prev`` the ``applied_vector_potential`` value Runner threads through; both only
+        matter for a time-dependent vector potential.  Returns (dt, psi', mu', J_s, J_n)."""
         o = self.options
         self.update_mu_boundary(time)
+        dA_dt = 0.0
+        if self.A_func is not None:                                      # :626-642
+            A = np.asarray(self.A_func(time), float)
+            prev = self.current_A_applied if A_prev is None else A_prev
+            dA_dt = np.einsum("ij, ij -> i", (A - prev) / dt_prev, self.normalized_directions)
+            if not np.allclose(A, self.current_A_applied):
+                self.operators.set_link_exponents(A)
+            self.current_A_applied = A
         old_sq = np.absolute(psi) ** 2                                   # :649
         dt = self.tentative_dt                                           # :668
         psi, new_sq, dt = self.adaptive_euler_step(step, psi, old_sq, mu, dt)
-        mu, js, jn = self.solve_for_observables(psi)
+        mu, js, jn = self.solve_for_observables(psi, dA_dt)
         if o.adaptive:                                                   # :698-707
             self.d_psi_sq_vals.append(float(np.absolute(new_sq - old_sq).max()))
             if step > o.adaptive_window:
@@ -289,8 +306,9 @@ def run(solver: OracleSolver, *, end_time: float, max_steps: Optional[int] = Non
     time = 0.0
     dts, mus, thetas = [], [], []
     i = 0
+    dt = solver.options.dt_init                                  # Runner's self.dt
     while True:
-        dt, psi, mu, js, jn = solver.update(i, time, psi, mu)
+        dt, psi, mu, js, jn = solver.update(i, time, psi, mu, dt_prev=dt)
         dts.append(float(dt))
         if solver.probe_points is not None:                      # solver.py:691-694
             mus.append(mu[list(solver.probe_points)])

@@ -167,6 +167,7 @@ class Engine {
   void set_link_exponents(const double* A);
   void set_epsilon(const double* eps);
   void set_mu_boundary(const double* mub);
+  void set_dA_dt(const double* dadt);
   void set_state(const double* psi, const double* mu);
   void set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
                    double multiplier);
@@ -235,7 +236,10 @@ class Engine {
   DevBuf<signed char> head_;
   DevBuf<double2> lval_;           // covariant Laplacian values (all rows kept)
   DevBuf<unsigned char> fixed_;    // rows the reference replaces by identity
-  DevBuf<double> areas_, eps_, bterm_;
+  DevBuf<double> areas_, eps_, bterm_;   // bterm_: what the rhs kernel subtracts per site
+  DevBuf<double> bterm_base_, dadt_;     // boundary-current term; dA/dt on the edges
+  bool has_dadt_ = false;
+  void refresh_site_terms();
   int win0_ = kWinRows, cap0_ = 0;  // window geometry of the site operators
   // ---- edges (caller edge order, internal site indices) -----------------------------------
   DevBuf<int> e0_, e1_;

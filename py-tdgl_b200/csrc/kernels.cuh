@@ -447,6 +447,29 @@ __global__ void k_boundary_term(int nb, const int* __restrict__ be0, const int* 
   if (j >= 0) atomicAdd(bterm + j, v / (2.0 * areas[j]));
 }
 
+// Time-dependent vector potential (reference solver.py:626-642, 507-510, 519): the rhs gains
+// -(divergence @ dA_dt).  divergence has (e0, e) = s_e / a[e0], (e1, e) = -s_e / a[e1]
+// (operators.py:59-84); gathered per site over its incident edges (deterministic), and folded
+// with the boundary-current term into the one site vector the rhs kernel subtracts:
+//   bterm_eff_i = bterm_i + sum_e (+-) s_e / a_i * dA_dt[e]
+__global__ void k_site_terms(int n, const int* __restrict__ ptr, const int* __restrict__ eidx,
+                             const signed char* __restrict__ head,
+                             const double* __restrict__ weight, const double* __restrict__ elen,
+                             const double* __restrict__ areas, const double* __restrict__ dadt,
+                             const double* __restrict__ bterm, double* __restrict__ bterm_eff) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  double s = 0.0;
+  if (dadt != nullptr)
+    for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
+      const int e = eidx[k];
+      if (e < 0) continue;
+      const double dual = weight[e] * elen[e];
+      s += (head[k] ? dual : -dual) / areas[row] * dadt[e];
+    }
+  bterm_eff[row] = bterm[row] + s;
+}
+
 // Values of the covariant Laplacian (all rows kept, see k_mu_rhs) from the link variables
 //   U_e = exp(-i A_e . d_e) ; off-diagonals w_e U_e / a_i (row = edges[e,0]) or
 //   w_e conj(U_e) / a_i (row = edges[e,1]) ; diagonal -sum w_e / a_i
@@ -481,6 +504,7 @@ __global__ void k_link_values(int n, const int* __restrict__ ptr, const int* __r
 __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __restrict__ e1,
                            const double* __restrict__ elen, const double* __restrict__ theta,
                            const double2* __restrict__ psi, const double* __restrict__ mu,
+                           const double* __restrict__ dadt /* may be null */,
                            double* __restrict__ js, double* __restrict__ jn) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
@@ -498,7 +522,7 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   const double gx = (c * pj.x - s * pj.y) * inv_l - pi.x * inv_l;
   const double gy = (c * pj.y + s * pj.x) * inv_l - pi.y * inv_l;
   js[e] = pi.x * gy - pi.y * gx;
-  jn[e] = -(mu[j] * inv_l - mu[i] * inv_l);
+  jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - (dadt != nullptr ? dadt[e] : 0.0);
 }
 
 template <typename T>

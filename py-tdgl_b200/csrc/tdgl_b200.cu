@@ -318,6 +318,9 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   }
   bterm_.alloc(Nx_);
   bterm_.zero(stream_);
+  bterm_base_.alloc(Nx_);
+  bterm_base_.zero(stream_);
+  dadt_.alloc(E_);
   {
     // edges keep the caller's (global) order; site indices are local, -1 = not on this shard.
     // An edge is owned by the shard that owns edges[e,0] (its e1 is then owned or in the halo).
@@ -990,9 +993,24 @@ void Engine::set_epsilon(const double* eps) {
 void Engine::set_mu_boundary(const double* mub) {
   if (Eb_ == 0) return;
   mub_.upload(mub, Eb_, stream_);
-  bterm_.zero(stream_);
+  bterm_base_.zero(stream_);
   k_boundary_term<<<(Eb_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-      Eb_, be0_.p, be1_.p, blen_.p, areas_.p, mub_.p, bterm_.p);
+      Eb_, be0_.p, be1_.p, blen_.p, areas_.p, mub_.p, bterm_base_.p);
+  TDGL_LAUNCH_CHECK();
+  refresh_site_terms();
+}
+
+// dA_dt[E] (caller edge order; nullptr: the vector potential is static again)
+void Engine::set_dA_dt(const double* dadt) {
+  has_dadt_ = dadt != nullptr;
+  if (has_dadt_) dadt_.upload(dadt, E_, stream_);
+  refresh_site_terms();
+}
+
+void Engine::refresh_site_terms() {
+  k_site_terms<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+      N_, ptr_.p, eidx_.p, head_.p, weight_.p, elen_.p, areas_.p, has_dadt_ ? dadt_.p : nullptr,
+      bterm_base_.p, bterm_.p);
   TDGL_LAUNCH_CHECK();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -1141,7 +1159,8 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
   if (js != nullptr || jn != nullptr) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, tmp_e_.p, tmp_e2_.p);
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
+        tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
     if (js != nullptr) tmp_e_.download(js, E_, stream_);
     if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
@@ -1174,7 +1193,8 @@ void Engine::get_currents(double* js, double* jn) {
   const int cur = h_ctl_->cur;
   unpack_state_halos(cur);
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, tmp_e_.p, tmp_e2_.p);
+      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
+        tmp_e_.p, tmp_e2_.p);
   TDGL_LAUNCH_CHECK();
   if (js != nullptr) tmp_e_.download(js, E_, stream_);
   if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
@@ -1536,6 +1556,9 @@ int tdgl_set_epsilon(tdgl_handle* h, const double* epsilon) {
 }
 int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary) {
   return guarded(h, [&](tdgl::Engine& e) { e.set_mu_boundary(mu_boundary); });
+}
+int tdgl_set_dA_dt(tdgl_handle* h, const double* dA_dt) {
+  return guarded(h, [&](tdgl::Engine& e) { e.set_dA_dt(dA_dt); });
 }
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu) {
   return guarded(h, [&](tdgl::Engine& e) { e.set_state(psi, mu); });

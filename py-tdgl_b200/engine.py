@@ -184,6 +184,11 @@ class DeviceEngine:
         self._check(self._lib.tdgl_set_mu_boundary(
             self._h, ptr(as_f64(mu_boundary, (self.n_boundary_edges,)))))
 
+    def set_dA_dt(self, dA_dt) -> None:
+        """``dA_dt`` [E] (or None for a static vector potential), solver.py:626-634."""
+        arr = None if dA_dt is None else as_f64(dA_dt, (self.n_edges,))
+        self._check(self._lib.tdgl_set_dA_dt(self._h, ptr(arr)))
+
     def set_state(self, psi, mu) -> None:
         self._check(self._lib.tdgl_set_state(
             self._h, ptr(as_c128(psi, (self.n_sites,))), ptr(as_f64(mu, (self.n_sites,)))))

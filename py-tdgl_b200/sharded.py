@@ -144,6 +144,9 @@ class LocalShardGroup:
     def set_mu_boundary(self, mub):
         self._all(lambda e: e.set_mu_boundary(mub))
 
+    def set_dA_dt(self, dA_dt):
+        self._all(lambda e: e.set_dA_dt(dA_dt))
+
     def set_state(self, psi, mu):
         self._all(lambda e: e.set_state(psi, mu))
 

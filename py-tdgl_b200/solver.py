@@ -105,10 +105,9 @@ class TDGLSolver:
         sites = xi * mesh.sites
         edge_centers = xi * mesh.edge_mesh.centers
         z0 = device.layer.z0 * np.ones(len(edge_centers))
-        # applied vector potential at the edge centres (solver.py:164-189)
-        if getattr(applied_vector_potential, "time_dependent", False):
-            raise NotImplementedError(
-                "time-dependent applied_vector_potential is not on the B200 path yet")
+        # applied vector potential at the edge centres (solver.py:164-189); a callable with
+        # ``time_dependent = True`` (the reference's ``Parameter``) is evaluated every step
+        dynamic_A = bool(getattr(applied_vector_potential, "time_dependent", False))
         if not callable(applied_vector_potential):
             b = float(applied_vector_potential)
 
@@ -116,8 +115,13 @@ class TDGLSolver:
                 return constant_field_vector_potential(x, y, z, Bz=_b)
 
         self.applied_vector_potential = applied_vector_potential
-        A = np.asarray(applied_vector_potential(edge_centers[:, 0], edge_centers[:, 1], z0))
-        A = scales.A_scale * A[:, :2]
+
+        def eval_A(t=None, _f=applied_vector_potential, _c=edge_centers, _z=z0,
+                   _s=scales.A_scale):
+            kw = dict(t=t) if dynamic_A else {}
+            return _s * np.asarray(_f(_c[:, 0], _c[:, 1], _z, **kw))[:, :2]
+
+        A = eval_A(0)
         if A.shape != edge_centers.shape:
             raise ValueError(f"Unexpected shape for vector_potential: {A.shape}.")
         # epsilon at the sites (solver.py:191-216)
@@ -164,7 +168,7 @@ class TDGLSolver:
         self._setup(mesh, options, A, eval_eps, dynamic_epsilon, terminal_info,
                     lambda t: {k: J_scale * v for k, v in user_func(t).items()},
                     static_currents, device.probe_point_indices, device.layer.u,
-                    device.layer.gamma)
+                    device.layer.gamma, eval_A=eval_A if dynamic_A else None)
 
     @classmethod
     def from_dimensionless(cls, mesh, options: SolverOptions, *, A_applied, epsilon,
@@ -173,7 +177,8 @@ class TDGLSolver:
                            probe_point_indices: Optional[Sequence[int]] = None,
                            u: float = 5.79, gamma: float = 10.0, device=None) -> "TDGLSolver":
         """Inputs as the reference holds them after ``__init__``: ``A_applied`` [E, 2] in
-        units of xi*Bc2, currents already multiplied by ``J_scale``."""
+        units of xi*Bc2 — or a callable ``t -> [E, 2]`` for a time-dependent vector
+        potential — currents already multiplied by ``J_scale``."""
         self = object.__new__(cls)
         self.device = device
         self.options = options
@@ -191,20 +196,28 @@ class TDGLSolver:
         else:
             filled = {n: terminal_currents.get(n, 0) for n in names}
             func, static = (lambda t, _c=filled: _c), True
+        eval_A = None
+        if callable(A_applied):
+            eval_A = lambda t, _f=A_applied: np.asarray(_f(t), float)  # noqa: E731
+            A_applied = eval_A(0.0)
         self._setup(mesh, options, np.asarray(A_applied, float), lambda t=None: eps, False,
-                    tuple(terminal_info), func, static, probe_point_indices, u, gamma)
+                    tuple(terminal_info), func, static, probe_point_indices, u, gamma,
+                    eval_A=eval_A)
         return self
 
     # ------------------------------------------------------------------------------------
     def _setup(self, mesh, options, A, eval_eps, dynamic_epsilon, terminal_info, current_func,
-               static_currents, probe_points, u, gamma):
+               static_currents, probe_points, u, gamma, eval_A=None):
         self.mesh = mesh
         self.u, self.gamma = u, gamma
         self.num_edges = len(mesh.edge_mesh.edges)
         self.current_A_applied = A
         self._eval_eps = eval_eps
         self.dynamic_epsilon = dynamic_epsilon
-        self.dynamic_vector_potential = False
+        self._eval_A = eval_A
+        self.dynamic_vector_potential = eval_A is not None
+        d = np.asarray(mesh.edge_mesh.directions, float)
+        self.normalized_directions = d / np.linalg.norm(d, axis=1)[:, None]
         epsilon = eval_eps(0.0) if dynamic_epsilon else eval_eps()
         if np.any(epsilon > 1):
             raise ValueError("The disorder parameter epsilon must be <= 1")
@@ -262,6 +275,20 @@ class TDGLSolver:
         if changed:
             self.engine.set_mu_boundary(self.mu_boundary)
 
+    def _update_vector_potential(self, time: float, dt_prev: float, prev_A=None) -> None:
+        """reference solver.py:626-642: A(t) at the edge centres, dA/dt as a backward
+        difference over the previous step's dt projected on the edge directions, new link
+        variables only if A changed."""
+        if not self.dynamic_vector_potential:
+            return
+        A = self._eval_A(time)
+        prev = self.current_A_applied if prev_A is None else np.asarray(prev_A, float)
+        dA_dt = np.einsum("ij, ij -> i", (A - prev) / dt_prev, self.normalized_directions)
+        if not np.allclose(A, self.current_A_applied):
+            self.engine.set_link_exponents(A)
+        self.engine.set_dA_dt(dA_dt)
+        self.current_A_applied = A
+
     def update(self, state: Dict[str, float], running_state, dt: float, *, psi, mu,
                supercurrent=None, normal_current=None, induced_vector_potential=None,
                applied_vector_potential=None, epsilon=None, out=None) -> SolverResult:
@@ -274,6 +301,7 @@ class TDGLSolver:
         on the device between save steps."""
         step, time = int(state["step"]), float(state["time"])
         self.update_mu_boundary(time)
+        self._update_vector_potential(time, float(dt), applied_vector_potential)
         if self.dynamic_epsilon:
             self.epsilon = self._eval_eps(time)
             self.engine.set_epsilon(self.epsilon)
@@ -296,8 +324,12 @@ class TDGLSolver:
         if induced_vector_potential is None:
             induced_vector_potential = np.zeros((self.num_edges, 2))
         results = [info.dt, psi1, mu1, js, jn, induced_vector_potential]
+        if self.dynamic_vector_potential:
+            results.append(self.current_A_applied)
         if self.dynamic_epsilon:
-            results.extend([None, self.epsilon])
+            if not self.dynamic_vector_potential:
+                results.append(None)
+            results.append(self.epsilon)
         return SolverResult(*results)
 
     # ------------------------------------------------------------------------------------
@@ -306,6 +338,8 @@ class TDGLSolver:
         js, jn = self.engine.get_currents()
         out = {"psi": psi, "mu": mu, "supercurrent": js, "normal_current": jn,
                "induced_vector_potential": np.zeros((self.num_edges, 2))}
+        if self.dynamic_vector_potential:
+            out["applied_vector_potential"] = self.current_A_applied
         if self.dynamic_epsilon:
             out["epsilon"] = self.epsilon
         return out
@@ -316,7 +350,8 @@ class TDGLSolver:
         next save step (or after one step when a host callback is time-dependent)."""
         opts = self.options
         every = max(int(opts.save_every), 1)
-        per_step_host = (not self.static_currents) or self.dynamic_epsilon
+        per_step_host = ((not self.static_currents) or self.dynamic_epsilon
+                         or self.dynamic_vector_potential)
         i, time = 0, 0.0
         cancelled = False
 
@@ -332,6 +367,7 @@ class TDGLSolver:
                         save_step(i)
                     running.clear()
                 self.update_mu_boundary(time)
+                self._update_vector_potential(time, self._prev_dt)
                 if self.dynamic_epsilon:
                     self.epsilon = self._eval_eps(time)
                     self.engine.set_epsilon(self.epsilon)
@@ -393,7 +429,11 @@ class TDGLSolver:
                      "induced_vector_potential": np.array(seed.induced_vector_potential)}
         self.engine.set_state(psi0, mu0)
         saved = SavedSteps()
-        fixed = {"applied_vector_potential": self.current_A_applied}
+        fixed = {}
+        if self.dynamic_vector_potential:
+            first["applied_vector_potential"] = self.current_A_applied
+        else:
+            fixed["applied_vector_potential"] = self.current_A_applied
         if self.dynamic_epsilon:
             first["epsilon"] = self.epsilon
         else:

@@ -9,6 +9,7 @@ from tdgl_b200.synthetic import TerminalInfo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["film20_fixed", "film20_adaptive", "strip_transport"]
+DYNAMIC_CASES = ["film20_ramp"]          # time-dependent vector potential
 
 
 def load_case(name):
@@ -26,7 +27,15 @@ def load_case(name):
         currents[name_k] = float(g[f"term{k}_current"])
     opts = {k[4:]: g[k].item() for k in g.files if k.startswith("opt_")}
     max_steps = int(g["max_steps"])
+    A_func = None
+    if "ramp" in g.files:                  # (b_max, t_ramp), see oracle/make_golden.py
+        from tdgl_b200.synthetic import uniform_field_vector_potential
+
+        b_max, t_ramp = (float(v) for v in g["ramp"])
+        A1 = uniform_field_vector_potential(g["centers"], 1.0)
+        A_func = lambda t: min(max(t / t_ramp, 0.0), 1.0) * b_max * A1  # noqa: E731
     return SimpleNamespace(
+        A_func=A_func,
         g=g, mesh=mesh, A=g["A_applied"], eps=g["epsilon"], u=float(g["u"]),
         gamma=float(g["gamma"]), terminals=tuple(terms), currents=currents, opts=opts,
         end_time=float(g["end_time"]), max_steps=None if max_steps < 0 else max_steps,

@@ -234,6 +234,36 @@ def test_transport_trajectory():
     del x_mid
 
 
+def test_time_dependent_vector_potential():
+    """Field ramp (the reference's ``LinearRamp * ConstantField``): A(t) re-evaluated every
+    step on the host like the reference does (solver.py:626-642), new link variables and the
+    dA/dt terms of the rhs and of J_n on the device.  600 fixed-dt steps, 1e-8 gauge-fixed."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    c = load_case("film20_ramp")
+    g = c.g
+    kw = {k: v for k, v in c.opts.items() if k != "solve_time"}
+    dt = kw["dt_init"]
+    # Runner performs ceil(T / dt) + 1 updates: end the run so that it makes 600
+    opts = SolverOptions(solve_time=dt * 598.5, save_every=300, **kw)
+    solver = TDGLSolver.from_dimensionless(c.mesh, opts, A_applied=c.A_func, epsilon=c.eps,
+                                           probe_point_indices=c.probes, u=c.u, gamma=c.gamma)
+    assert solver.dynamic_vector_potential
+    sol = solver.solve()
+    d = sol.tdgl_data
+    assert len(sol.dynamics.dt) == int(g["steps"]) == 600
+    ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
+               normal_current=g["normal_current"])
+    diff = orc.compare(dict(psi=d.psi, mu=d.mu, supercurrent=d.supercurrent,
+                            normal_current=d.normal_current), ref, c.mesh.areas)
+    print("film20_ramp", diff, sol.solver_stats)
+    for k, v in diff.items():
+        assert v < 1e-8, (k, diff)
+    # the vector potential saved with the last step is A(t_end)
+    np.testing.assert_allclose(d.applied_vector_potential, c.A_func(float(g["time"])),
+                               rtol=0, atol=1e-14)
+
+
 def test_step_failure_raises_like_reference():
     """Non-adaptive run with a too-large dt: RuntimeError with the reference's text."""
     from tdgl_b200 import SolverOptions, TDGLSolver

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "tdgl_b200.h")).read()
-    declared = set(re.findall(r"\b(tdgl_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(tdgl_[A-Za-z_0-9]+)\s*\(", header))
     declared -= {"tdgl_handle", "tdgl_config", "tdgl_advance_info"}
     assert declared, "no declarations found"
     lib = _lib.load()

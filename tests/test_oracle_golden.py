@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import tdgl_oracle as orc
-from helpers import CASES, load_case
+from helpers import CASES, DYNAMIC_CASES, load_case
 
 
 def make_oracle(c):
@@ -13,7 +13,7 @@ def make_oracle(c):
     return orc.OracleSolver(
         c.mesh, orc.OracleOptions(**kw), c.A, c.eps, u=c.u, gamma=c.gamma,
         terminal_info=[orc.TerminalInfo(*t) for t in c.terminals], current_func=cf,
-        probe_points=c.probes)
+        probe_points=c.probes, A_func=c.A_func)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -37,7 +37,7 @@ def test_operator_known_answers(name):
                                atol=1e-12)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + DYNAMIC_CASES)
 def test_trajectory_matches_reference(name):
     """Same SciPy/SuperLU => the restatement reproduces the reference's raw numbers
     (bit-identical in the build container); 1e-9 leaves room for another BLAS/SuperLU
