@@ -328,11 +328,7 @@ class Engine {
   void sync_ctl_to_host();
   void push_ctl();
   DevBuf<double> aval_;  // level-0 mu matrix values; structure shared with ptr_/idx_
-  DevBuf<int2> wdesc0r_;
-  int win0r_ = kWinRows, cap0r_ = 0, lpr0_ = 1;
-  CsrView A0() const {
-    return CsrView{WinCsr{N_, cap0r_, ptr_.p, idx_.p, wdesc0r_.p}, aval_.p, win0r_, lpr0_};
-  }
+  CsrView A0() const { return CsrView{site_csr(), aval_.p, win0_, 1}; }
   CsrView levelA(size_t l) const { return l == 0 ? A0() : levels_[l].A.view(); }
 };
 

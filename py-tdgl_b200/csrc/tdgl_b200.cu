@@ -285,13 +285,6 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   {
     const std::vector<int2> wd = window_descriptors(lptr, N_, win0_);
     wdesc0_.upload(wd, stream_);
-    // window geometry of the real (mu) operator on the site graph: same structure, but its
-    // kernels may use several lanes per row and then want correspondingly fewer rows per CTA
-    lpr0_ = 1;
-    if (const char* e = std::getenv("TDGL_B200_LPR0")) lpr0_ = (e[0] == '4') ? 4 : 1;
-    win0r_ = pick_window(lptr, N_, 12, 64 * 1024, &cap0r_, kWinRows / lpr0_);
-    const std::vector<int2> wdr = window_descriptors(lptr, N_, win0r_);
-    wdesc0r_.upload(wdr, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
   idx_.upload(lnbr, stream_);
@@ -384,7 +377,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   // every shard (shard.h); for a single shard everything is "replicated" = the whole matrix.
   levels_.resize(L);
   amg_nnz_ = 0;
-  int max_grid_rows = std::max(grid_win(N_, win0_), grid_win(N_, win0r_));
+  int max_grid_rows = grid_win(N_, win0_);
   const int rep_level = plan_.rep;
   for (size_t l = 0; l < L; ++l) {
     AmgLevel& hl = H.levels[l];

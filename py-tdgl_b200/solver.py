@@ -194,6 +194,8 @@ class TDGLSolver:
         if callable(terminal_currents):
             func, static = terminal_currents, False
         else:
+            if unknown := set(terminal_currents).difference(names):
+                raise ValueError(f"Unknown terminal(s) in terminal currents: {list(unknown)}.")
             filled = {n: terminal_currents.get(n, 0) for n in names}
             func, static = (lambda t, _c=filled: _c), True
         eval_A = None

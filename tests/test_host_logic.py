@@ -121,3 +121,62 @@ def test_saved_steps_dynamics_matches_reference_layout():
     np.testing.assert_allclose(dyn.dt, [1e-3, 2e-3])
     np.testing.assert_allclose(dyn.time, [1e-3, 3e-3])
     np.testing.assert_allclose(dyn.voltage(0, 1), [-2.0, -2.0])
+
+
+def _small_problem():
+    from tdgl_b200.synthetic import film_problem
+
+    return film_problem(8, 4, 0.5, b=0.1, terminals=True)
+
+
+def test_solver_input_errors_match_reference():
+    """The errors ``TDGLSolver.__init__`` raises before any device work, with the reference's
+    messages (solver.py:35-60, 186-189, 215-216, 228-232; tdgl/test/test_solve.py:34-79)."""
+    mesh, A, eps, terms = _small_problem()
+    opts = tdgl.SolverOptions(solve_time=1.0)
+    mk = tdgl.TDGLSolver.from_dimensionless
+    with pytest.raises(ValueError, match="epsilon must be <= 1"):
+        mk(mesh, opts, A_applied=A, epsilon=2.0 * eps, terminal_info=terms)
+    with pytest.raises(ValueError, match=r"Unknown terminal\(s\)"):
+        mk(mesh, opts, A_applied=A, epsilon=eps, terminal_info=terms,
+           terminal_currents={"source": 1.0, "nowhere": -1.0})
+    with pytest.raises(ValueError, match="sum of all terminal currents must be 0"):
+        mk(mesh, opts, A_applied=A, epsilon=eps, terminal_info=terms,
+           terminal_currents={"source": 1.0, "drain": -0.5})
+    with pytest.raises(ValueError, match="sum of all terminal currents must be 0"):
+        mk(mesh, opts, A_applied=A, epsilon=eps, terminal_info=terms,
+           terminal_currents=lambda t: {"source": 1.0 + t, "drain": -1.0})
+    empty = terms[0]._replace(name="ghost", length=0.0)
+    with pytest.raises(ValueError, match="does not contain any points"):
+        mk(mesh, opts, A_applied=A, epsilon=eps, terminal_info=(empty,))
+    with pytest.raises(tdgl.SolverOptionsError):
+        mk(mesh, tdgl.SolverOptions(solve_time=1.0, dt_init=1.0, dt_max=0.1), A_applied=A,
+           epsilon=eps)
+    with pytest.raises(tdgl.SolverOptionsError, match="include_screening"):
+        mk(mesh, tdgl.SolverOptions(solve_time=1.0, include_screening=True), A_applied=A,
+           epsilon=eps)
+
+
+def test_mesh_edge_cases():
+    """Mesh input contract (reference finite_volume/mesh.py:104-151): shape errors, boundary
+    edges = edges of exactly one triangle, areas tile the film."""
+    from tdgl_b200.mesh import Mesh
+
+    with pytest.raises(ValueError, match=r"shape \(n, 2\)"):
+        Mesh.from_triangulation(np.zeros((4, 3)), np.array([[0, 1, 2]]))
+    with pytest.raises(ValueError, match=r"shape \(m, 3\)"):
+        Mesh.from_triangulation(np.zeros((4, 2)), np.array([[0, 1, 2, 3]]))
+    # the smallest mesh: two triangles of the unit square
+    m = Mesh.from_triangulation(np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]]),
+                                np.array([[0, 1, 2], [0, 2, 3]]))
+    em = m.edge_mesh
+    assert len(em.edges) == 5 and len(em.boundary_edge_indices) == 4
+    assert sorted(m.boundary_indices) == [0, 1, 2, 3]
+    assert np.all(em.edges[:, 0] < em.edges[:, 1])
+    # values of the reference's own Mesh.from_triangulation on this mesh (its Voronoi cells
+    # of corner sites whose circumcentres fall on the hypotenuse do not tile the square)
+    np.testing.assert_allclose(m.areas, [0.125, 0.25, 0.125, 0.25])
+    np.testing.assert_allclose(em.dual_edge_lengths, [0.5, 0.0, 0.5, 0.5, 0.5])
+    mesh = make_film_mesh(12, 7, 0.5, holes=((1.0, 0.5, 2.0),))
+    assert abs(mesh.areas.sum() - (12 * 7 - np.pi * 2.0**2)) < 0.1
+    assert np.all(mesh.areas > 0) and np.all(mesh.edge_mesh.dual_edge_lengths >= 0)
