@@ -216,6 +216,16 @@ int tdgl_comm_export(tdgl_handle* h, void* handle_out /* 64 bytes */);
 int tdgl_comm_connect_ipc(tdgl_handle* h, const void* handles /* world x 64 bytes */,
                           int32_t world);
 int tdgl_comm_connect_local(tdgl_handle* h, tdgl_handle* const* peers, int32_t world);
+/* Sharded outputs without the detour through host memory: tdgl_stage_outputs leaves the
+ * whole-mesh psi (complex128), mu, supercurrent, normal current (what & 1: state, what & 2:
+ * currents) in device buffers — this shard's entries, zeros elsewhere — and returns their
+ * device pointers and lengths in doubles; the caller sums them over the shards on the
+ * devices (e.g. ncclAllReduce in place) and reads the result with tdgl_fetch_outputs (any
+ * pointer may be NULL). */
+int tdgl_stage_outputs(tdgl_handle* h, int32_t what, void** device_ptrs /* 4 */,
+                       int64_t* counts /* 4 */);
+int tdgl_fetch_outputs(tdgl_handle* h, double* psi, double* mu, double* supercurrent,
+                       double* normal_current);
 /* [0] world, [1] rank, [2] sites of the mesh, [3] sites owned, [4] level-0 halo sites,
  * [5] halo entries over all levels, [6] level-0 neighbour shards, [7] level-0 entries sent
  * per exchange. */

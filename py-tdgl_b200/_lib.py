@@ -95,6 +95,8 @@ SIGNATURES = {
     "tdgl_comm_connect_ipc": (C.c_int, [_P, _P, _I32]),
     "tdgl_comm_connect_local": (C.c_int, [_P, C.POINTER(_P), _I32]),
     "tdgl_shard_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
+    "tdgl_stage_outputs": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_I64)]),
+    "tdgl_fetch_outputs": (C.c_int, [_P, _P, _P, _P, _P]),
     "tdgl_host_shard_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _D, _I32, _I64,
                                         C.POINTER(_I32), _P, _P, _P, _P, _P, _I32, _D,
                                         C.POINTER(_I32)]),

@@ -179,6 +179,8 @@ class Engine {
   AdvanceInfo advance(int64_t max_steps, double t_end, int64_t step, double time);
   AdvanceInfo update(const double* psi, const double* mu, int64_t step, double time,
                      double* psi_out, double* mu_out, double* js, double* jn);
+  void stage_outputs(int what, void** ptrs, int64_t* counts);
+  void fetch_outputs(double* psi, double* mu, double* js, double* jn);
   void get_state(double* psi, double* mu);
   void get_currents(double* js, double* jn);
   void get_running(int64_t capacity, double* dt, double* mu_probe, double* theta_probe);

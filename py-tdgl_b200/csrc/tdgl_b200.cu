@@ -1162,6 +1162,41 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
   return info;
 }
 
+// Whole-mesh outputs staged in device buffers (this shard's sites / edges, zeros elsewhere):
+// a sharded caller sums them over the shards ON THE DEVICES (NCCL over NVLink) and fetches the
+// result once, instead of moving zero-padded arrays through host memory.
+void Engine::stage_outputs(int what, void** ptrs, int64_t* counts) {
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  const int g = (N_ + kBlock - 1) / kBlock;
+  if (what & 1) {
+    if (world_ > 1) { tmp_c_.zero(stream_); tmp_d_.zero(stream_); }
+    k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, psi_[cur].p, tmp_c_.p);
+    TDGL_LAUNCH_CHECK();
+    k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
+    TDGL_LAUNCH_CHECK();
+  }
+  if (what & 2) {
+    unpack_state_halos(cur);
+    k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
+        tmp_e_.p, tmp_e2_.p);
+    TDGL_LAUNCH_CHECK();
+  }
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  ptrs[0] = tmp_c_.p; ptrs[1] = tmp_d_.p; ptrs[2] = tmp_e_.p; ptrs[3] = tmp_e2_.p;
+  counts[0] = 2 * static_cast<int64_t>(Ng_); counts[1] = Ng_; counts[2] = E_; counts[3] = E_;
+}
+
+void Engine::fetch_outputs(double* psi, double* mu, double* js, double* jn) {
+  if (psi != nullptr)
+    TDGL_CUDA(cudaMemcpyAsync(psi, tmp_c_.p, sizeof(double2) * Ng_, cudaMemcpyDeviceToHost, stream_));
+  if (mu != nullptr) tmp_d_.download(mu, Ng_, stream_);
+  if (js != nullptr) tmp_e_.download(js, E_, stream_);
+  if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
 void Engine::get_state(double* psi, double* mu) {
   sync_ctl_to_host();
   const int cur = h_ctl_->cur;
@@ -1623,6 +1658,16 @@ int tdgl_get_state(tdgl_handle* h, double* psi, double* mu) {
 }
 int tdgl_get_currents(tdgl_handle* h, double* supercurrent, double* normal_current) {
   return guarded(h, [&](tdgl::Engine& e) { e.get_currents(supercurrent, normal_current); });
+}
+int tdgl_stage_outputs(tdgl_handle* h, int32_t what, void** device_ptrs, int64_t* counts) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (device_ptrs == nullptr || counts == nullptr) throw std::invalid_argument("null output");
+    e.stage_outputs(what, device_ptrs, counts);
+  });
+}
+int tdgl_fetch_outputs(tdgl_handle* h, double* psi, double* mu, double* supercurrent,
+                       double* normal_current) {
+  return guarded(h, [&](tdgl::Engine& e) { e.fetch_outputs(psi, mu, supercurrent, normal_current); });
 }
 int tdgl_get_running(tdgl_handle* h, int64_t capacity, double* dt, double* mu_probe,
                      double* theta_probe) {

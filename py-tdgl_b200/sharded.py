@@ -21,6 +21,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
+from ._lib import ptr
 from .engine import AdvanceInfo, DeviceEngine
 
 
@@ -58,6 +59,32 @@ class DistributedEngine(DeviceEngine):
             flat[:] = t.cpu().numpy()
         return arrays
 
+    def _outputs_on_device(self, what: int, psi=None, mu=None, js=None, jn=None):
+        """Sum the staged whole-mesh outputs over the shards on the devices (NCCL over
+        NVLink), then fetch them once."""
+        import ctypes as C
+
+        torch = self._torch
+        ptrs = (C.c_void_p * 4)()
+        counts = (C.c_int64 * 4)()
+        self._check(self._lib.tdgl_stage_outputs(self._h, what, ptrs, counts))
+
+        class _Dev:  # zero-copy view of an engine buffer
+            def __init__(self, p, n):
+                self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8",
+                                                 "data": (int(p), False), "version": 3}
+
+        want = [k for k, a in enumerate((psi, mu, js, jn)) if a is not None]
+        for k in want:
+            t = torch.as_tensor(_Dev(ptrs[k], counts[k]), device=self._reduce_device)
+            self._dist.all_reduce(t, group=self._group)
+        torch.cuda.current_stream(self._reduce_device).synchronize()
+        self._check(self._lib.tdgl_fetch_outputs(self._h, ptr(psi), ptr(mu), ptr(js), ptr(jn)))
+
+    @property
+    def _device_reduce(self) -> bool:
+        return self.world > 1 and self._reduce_device.type == "cuda"
+
     def set_state(self, psi, mu) -> None:
         # every shard fills its own halo mailboxes from the whole-mesh arrays; no shard may
         # still be stepping (and storing into a peer's mailbox) while that happens
@@ -68,10 +95,19 @@ class DistributedEngine(DeviceEngine):
             self._dist.barrier(group=self._group)
 
     def get_state(self):
-        return self._sum(*super().get_state())
+        if not self._device_reduce:
+            return self._sum(*super().get_state())
+        psi = np.empty(self.n_sites, dtype=np.complex128)
+        mu = np.empty(self.n_sites)
+        self._outputs_on_device(1, psi=psi, mu=mu)
+        return psi, mu
 
     def get_currents(self):
-        return self._sum(*super().get_currents())
+        if not self._device_reduce:
+            return self._sum(*super().get_currents())
+        js, jn = np.empty(self.n_edges), np.empty(self.n_edges)
+        self._outputs_on_device(2, js=js, jn=jn)
+        return js, jn
 
     def get_running(self, steps: int):
         dt, mu, th = super().get_running(steps)
@@ -81,8 +117,15 @@ class DistributedEngine(DeviceEngine):
         return dt, mu, th
 
     def update(self, psi, mu, step: int, time: float, out=None):
-        info, out = super().update(psi, mu, step, time, out=out)
-        self._sum(*out)
+        if not self._device_reduce:
+            info, out = super().update(psi, mu, step, time, out=out)
+            self._sum(*out)
+            return info, out
+        if out is None:
+            out = (np.empty(self.n_sites, np.complex128), np.empty(self.n_sites),
+                   np.empty(self.n_edges), np.empty(self.n_edges))
+        info, _ = super().update(psi, mu, step, time, out=(None, None, None, None))
+        self._outputs_on_device(3, *out)
         return info, out
 
 
