@@ -308,3 +308,52 @@ def test_large_mesh_properties():
         assert res < 1e-10 and its < 60, (its, res)
         assert _rel(sol, x - np.dot(a, x) / a.sum()) < 1e-7
         print("250k mesh: mu solve iterations", its, "info", eng.info())
+
+
+def test_full_size_workload_properties():
+    """BASELINE.json configs[2] at full size (1.0M sites, 4 holes, terminals, transport
+    current), where the CPU oracle would need ~40 s of SuperLU factorisation: properties that
+    hold at EVERY step for a correct step, whatever the mesh size.
+      * the Poisson solve makes J_s + J_n divergence-free, so the net current through any
+        cross-section of the film equals the terminal current (to the solver tolerance);
+      * psi stays exactly 0 on the terminal sites (identity rows, terminal_psi = 0);
+      * mu has area-weighted mean zero (the engine's gauge);
+      * the device step loop and the one-step seam (tdgl_update) give the same state."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+    from tdgl_b200.synthetic import film_problem
+
+    holes = ((100.0, 100.0, 20.0), (-100.0, 100.0, 20.0), (100.0, -100.0, 20.0),
+             (-100.0, -100.0, 20.0))
+    mesh, A, eps, terms = film_problem(400.0, 400.0, 0.4225, b=0.0, holes=holes, terminals=True)
+    n = len(mesh.sites)
+    assert n > 1_000_000
+    I = 80.0
+    opts = SolverOptions(solve_time=1e9, dt_init=1e-4, dt_max=1e-1, save_every=1000)
+    s = TDGLSolver.from_dimensionless(mesh, opts, A_applied=A, epsilon=eps, terminal_info=terms,
+                                      terminal_currents={"source": I, "drain": -I})
+    eng = s.engine
+    eng.set_state(s.psi_init, s.mu_init)
+    s.update_mu_boundary(0.0)
+    info = eng.advance(40, 1e300, 0, 0.0)
+    assert info.steps_done == 40 and info.mu_rel_residual < 1e-10
+    psi, mu = eng.get_state()
+    js, jn = eng.get_currents()
+    a = mesh.areas
+    assert abs(np.dot(a, mu)) / (a.sum() * np.abs(mu).max()) < 1e-12
+    fixed = np.concatenate([np.asarray(t.site_indices) for t in terms])
+    assert np.abs(psi[fixed]).max() == 0.0
+    em = mesh.edge_mesh
+    J = js + jn
+    x0, x1 = mesh.sites[em.edges[:, 0], 0], mesh.sites[em.edges[:, 1], 0]
+    for xc in (-150.3, -100.1, -20.7, 0.2, 77.7, 100.4, 180.9):     # also through the holes
+        cut = np.where((x0 - xc) * (x1 - xc) < 0)[0]
+        total = float(np.sum(J[cut] * em.dual_edge_lengths[cut] * np.sign(x1[cut] - x0[cut])))
+        assert abs(total - I) < 1e-6 * I, (xc, total)
+    # one more step through the reference's seam == one more step of the device loop
+    info2, (p2, m2, js2, jn2) = eng.update(psi, mu, info.step, info.time)
+    eng.set_state(psi, mu)
+    info3 = eng.advance(1, 1e300, info.step, info.time)
+    p3, m3 = eng.get_state()
+    assert info2.dt == info3.dt
+    assert np.abs(p2 - p3).max() < 1e-13 and np.abs(m2 - m3).max() < 1e-11 * np.abs(m3).max()
+    print("1M-site workload:", info, "cut currents ok")
