@@ -103,6 +103,16 @@ int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary);
  * as well (solver.py:635-639). */
 int tdgl_set_dA_dt(tdgl_handle* h, const double* dA_dt);
 
+/* Separable time-dependent vector potential A(r, t) = f(t) * A0(r) (what the reference's
+ * `LinearRamp(...) * ConstantField(...)` is, tdgl/sources, parameter.py:355-373), evaluated on
+ * the DEVICE every step instead of through a host callback (solver.py:626-642): A0[E][2]
+ * dimensionless at the edge centres, f piecewise linear through (t_knots[k], f_knots[k]),
+ * 2 <= n_knots <= 32, constant outside.  Link variables are rebuilt and dA/dt =
+ * (f(t) - f(t_prev)) / dt_prev * A0 enters the rhs and J_n exactly as in the reference.
+ * n_knots = 0 turns the ramp off. */
+int tdgl_set_vector_potential_ramp(tdgl_handle* h, const double* A0, int32_t n_knots,
+                                   const double* t_knots, const double* f_knots);
+
 /* psi[N] (complex128) and mu[N]: the `psi`, `mu` values Runner threads through update(). */
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu);
 

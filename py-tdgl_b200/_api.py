@@ -6,11 +6,12 @@ from .options import SolverOptions, SolverOptionsError, SparseSolver
 from .solution import DynamicsData, Solution, TDGLData
 from .sharded import DistributedEngine, LocalShardGroup
 from .solver import SolverResult, TDGLSolver, solve
+from .sources import ConstantField, LinearRamp
 from .synthetic import TerminalInfo
 
 __all__ = [
     "Device", "Layer", "Polygon", "box", "circle", "DeviceEngine", "StepFailed", "EdgeMesh",
     "Mesh", "make_film_mesh", "SolverOptions", "SolverOptionsError", "SparseSolver",
     "DynamicsData", "Solution", "TDGLData", "SolverResult", "TDGLSolver", "solve",
-    "TerminalInfo", "DistributedEngine", "LocalShardGroup",
+    "TerminalInfo", "DistributedEngine", "LocalShardGroup", "ConstantField", "LinearRamp",
 ]

@@ -74,6 +74,7 @@ SIGNATURES = {
     "tdgl_set_epsilon": (C.c_int, [_P, _P]),
     "tdgl_set_mu_boundary": (C.c_int, [_P, _P]),
     "tdgl_set_dA_dt": (C.c_int, [_P, _P]),
+    "tdgl_set_vector_potential_ramp": (C.c_int, [_P, _P, _I32, _P, _P]),
     "tdgl_set_state": (C.c_int, [_P, _P, _P]),
     "tdgl_set_stepper": (C.c_int, [_P, _D, _D, _I32, _I32, _I32, _D]),
     "tdgl_advance": (C.c_int, [_P, _I64, _D, _I64, _D, C.POINTER(tdgl_advance_info)]),

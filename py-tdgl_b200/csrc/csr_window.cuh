@@ -411,6 +411,7 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
           const double2* __restrict__ lval, const double* __restrict__ aval,
           const double2* psi_buf0, const double2* psi_buf1, const double* __restrict__ mu,
           const double* __restrict__ areas, const double* __restrict__ bterm,
+          const double* __restrict__ ramp_div /* null: no device-side ramp */,
           double* __restrict__ b, double* __restrict__ r,
           double* __restrict__ rhs_raw /* may be null: un-symmetrised rhs */, double* partials,
           unsigned int* counter) {
@@ -440,6 +441,8 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
     p = psi[w.row];
     ai = areas[w.row];
     bt = bterm[w.row];
+    // device-side ramp: + divergence @ dA_dt with dA_dt = ramp_dfdt * (A0 . e_hat)
+    if (ramp_div != nullptr) bt += ctl->ramp_dfdt * ramp_div[w.row];
   }
   mbar_wait(&bar, 0);
   if (!live) return;

@@ -168,6 +168,7 @@ class Engine {
   void set_epsilon(const double* eps);
   void set_mu_boundary(const double* mub);
   void set_dA_dt(const double* dadt);
+  void set_ramp(const double* A0, int n_knots, const double* t_knots, const double* f_knots);
   void set_state(const double* psi, const double* mu);
   void set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
                    double multiplier);
@@ -242,6 +243,10 @@ class Engine {
   DevBuf<double> bterm_base_, dadt_;     // boundary-current term; dA/dt on the edges
   bool has_dadt_ = false;
   void refresh_site_terms();
+  // device-side ramp A(r, t) = f(t) A0(r): A0 . e_hat per edge, divergence of it per site
+  bool ramp_on_ = false;
+  DevBuf<double> ramp_proj_, ramp_div_, ramp_zero_;
+  void enqueue_ramp_links();
   int win0_ = kWinRows, cap0_ = 0;  // window geometry of the site operators
   // ---- edges (caller edge order, internal site indices) -----------------------------------
   DevBuf<int> e0_, e1_;

@@ -19,6 +19,7 @@ constexpr int kMaxWindow = 1024;   // adaptive_window cap
 constexpr int kMaxProbes = 64;
 constexpr int kBlock = 256;
 constexpr int kMaxPartials = 8192;  // grid-size cap of reducing kernels
+constexpr int kMaxKnots = 32;       // knots of a device-side vector-potential ramp
 
 struct Ctl {
   // --- configuration (host writes) -----------------------------------------------------
@@ -54,6 +55,12 @@ struct Ctl {
   int solve_epoch;    // mu solves started so far (+1): bumped at the start of every step
   int psi_epoch;      // attempts of the psi step so far (+1)
   int psi_tag[2];     // psi_epoch of the attempt that produced each psi buffer
+  // --- separable time-dependent vector potential A(r, t) = f(t) A0(r) (device-side ramp) ----
+  // f is piecewise linear through (ramp_t[k], ramp_v[k]), constant outside
+  int ramp_on, ramp_changed, ramp_knots, ramp_pad;
+  double ramp_f;       // f at the current step
+  double ramp_dfdt;    // (f(t) - f(t_prev)) / dt_prev, the reference's backward difference
+  double ramp_t[kMaxKnots], ramp_v[kMaxKnots];
 };
 
 // Programmatic dependent launch: `griddep_wait` blocks until the kernels this launch depends
@@ -290,6 +297,25 @@ __device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu
 __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
   griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ctl->ramp_on) {
+    // TDGLSolver.update for a time-dependent vector potential (solver.py:626-642) with
+    // A(r, t) = f(t) A0(r): dA/dt = (f(t) - f_prev) / dt_prev * A0, dt_prev = Runner's dt
+    // argument (the previous step's dt); link variables are rebuilt only if f changed
+    const double t = ctl->time;
+    const int n = ctl->ramp_knots;
+    double f = ctl->ramp_v[0];
+    if (t >= ctl->ramp_t[n - 1]) {
+      f = ctl->ramp_v[n - 1];
+    } else if (t > ctl->ramp_t[0]) {
+      int k = 0;
+      while (k + 2 < n && t >= ctl->ramp_t[k + 1]) ++k;
+      const double w = (t - ctl->ramp_t[k]) / (ctl->ramp_t[k + 1] - ctl->ramp_t[k]);
+      f = ctl->ramp_v[k] + w * (ctl->ramp_v[k + 1] - ctl->ramp_v[k]);
+    }
+    ctl->ramp_dfdt = (f - ctl->ramp_f) / ctl->dt;
+    ctl->ramp_changed = (f != ctl->ramp_f) || ctl->ramp_changed == 2;  // 2: forced (set-up)
+    ctl->ramp_f = f;
+  }
   ctl->dt = ctl->tentative_dt;
   ctl->solve_epoch += 1;
   ctl->retries = 0;
@@ -470,6 +496,34 @@ __global__ void k_site_terms(int n, const int* __restrict__ ptr, const int* __re
   bterm_eff[row] = bterm[row] + s;
 }
 
+// Device-side ramp: the link variables for A = ramp_f * A0 (theta holds A0 . d), rebuilt by
+// the step that sees f change (one pass over the matrix values, ~3 % of a step at 1M sites).
+__global__ void k_link_values_ramp(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+                                   const int* __restrict__ eidx,
+                                   const signed char* __restrict__ head,
+                                   const double* __restrict__ weight,
+                                   const double* __restrict__ theta0,
+                                   const double* __restrict__ areas, double2* __restrict__ lval) {
+  griddep_enter();
+  if (ctl->status != 0 || !ctl->ramp_changed) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double f = ctl->ramp_f;
+  double diag = 0.0;
+  int kd = -1;
+  for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
+    const int e = eidx[k];
+    if (e < 0) { kd = k; continue; }
+    const double w = weight[e];
+    double s, c;
+    sincos(-(f * theta0[e]), &s, &c);
+    if (!head[k]) s = -s;
+    lval[k] = make_double2(w * c / areas[row], w * s / areas[row]);
+    diag += -w / areas[row];
+  }
+  if (kd >= 0) lval[kd] = make_double2(diag, 0.0);
+}
+
 // Values of the covariant Laplacian (all rows kept, see k_mu_rhs) from the link variables
 //   U_e = exp(-i A_e . d_e) ; off-diagonals w_e U_e / a_i (row = edges[e,0]) or
 //   w_e conj(U_e) / a_i (row = edges[e,1]) ; diagonal -sum w_e / a_i
@@ -505,6 +559,8 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
                            const double* __restrict__ elen, const double* __restrict__ theta,
                            const double2* __restrict__ psi, const double* __restrict__ mu,
                            const double* __restrict__ dadt /* may be null */,
+                           const Ctl* __restrict__ ctl,
+                           const double* __restrict__ ramp_proj /* null: no device-side ramp */,
                            double* __restrict__ js, double* __restrict__ jn) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
@@ -516,13 +572,16 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   }
   const double inv_l = 1.0 / elen[e];
   double s, c;
-  sincos(-theta[e], &s, &c);
+  // (device-side ramp: theta holds A0 . d, the current A is ramp_f * A0)
+  sincos(ramp_proj != nullptr ? -(ctl->ramp_f * theta[e]) : -theta[e], &s, &c);
   const double2 pi = psi[i], pj = psi[j];
   // g = (U psi_j) * (1/l) + psi_i * (-1/l)   as the CSR gradient row computes it
   const double gx = (c * pj.x - s * pj.y) * inv_l - pi.x * inv_l;
   const double gy = (c * pj.y + s * pj.x) * inv_l - pi.y * inv_l;
   js[e] = pi.x * gy - pi.y * gx;
-  jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - (dadt != nullptr ? dadt[e] : 0.0);
+  double da = dadt != nullptr ? dadt[e] : 0.0;
+  if (ramp_proj != nullptr) da = ctl->ramp_dfdt * ramp_proj[e];
+  jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
 }
 
 template <typename T>

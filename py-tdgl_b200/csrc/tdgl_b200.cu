@@ -826,11 +826,13 @@ void Engine::enqueue_mu_rhs(double* rhs_raw) {
     launch_k(kw_mu_rhs<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
              ctl_.p, comm(), make_psi_comm(), make_halo(0, kVecMu, kTagMuPrev),
              make_push(0, kVecCgR, kTagIter0), site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p,
-             mu_.p, areas_.p, bterm_.p, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
+             mu_.p, areas_.p, bterm_.p, ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw,
+             partials_.p, counter_.p);
   else
     launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
              ctl_.p, comm(), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p, aval_.p,
-             psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p, cg_b_.p, cg_r_.p, rhs_raw,
+             psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p, ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p,
+             cg_r_.p, rhs_raw,
              partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
 }
@@ -932,6 +934,7 @@ void Engine::build_graph() {
   sb.capture([&] {
     launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_);
     TDGL_LAUNCH_CHECK();
+    enqueue_ramp_links();
   });
   cudaGraph_t psi_body = sb.add_while(h_psi_);
   {
@@ -974,6 +977,72 @@ void Engine::set_link_exponents(const double* A) {
       N_, ptr_.p, eidx_.p, head_.p, weight_.p, theta_.p, areas_.p, lval_.p);
   TDGL_LAUNCH_CHECK();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::enqueue_ramp_links() {
+  if (!ramp_on_) return;
+  launch_k(k_link_values_ramp, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, ptr_.p, eidx_.p,
+           head_.p, weight_.p, theta_.p, areas_.p, lval_.p);
+  TDGL_LAUNCH_CHECK();
+}
+
+// Separable time-dependent vector potential A(r, t) = f(t) A0(r), f piecewise linear through
+// (t_knots[k], f_knots[k]): evaluated on the device every step (k_step_begin), no host
+// callback.  n_knots = 0 turns it off (A stays at its current value, as a static potential).
+void Engine::set_ramp(const double* A0, int n_knots, const double* t_knots, const double* f_knots) {
+  if (n_knots < 0 || n_knots > kMaxKnots || n_knots == 1) throw std::invalid_argument("ramp needs 2..32 knots");
+  for (int k = 1; k < n_knots; ++k)
+    if (!(t_knots[k] > t_knots[k - 1])) throw std::invalid_argument("ramp knots must increase");
+  const bool was_on = ramp_on_;
+  sync_ctl_to_host();
+  if (n_knots == 0) {
+    ramp_on_ = false;
+    h_ctl_->ramp_on = 0;
+    h_ctl_->ramp_dfdt = 0.0;
+    push_ctl();
+  } else {
+    std::vector<double> th(E_), proj(E_);
+    for (int e = 0; e < E_; ++e) {
+      const double dx = h_dirs_[2 * e], dy = h_dirs_[2 * e + 1];
+      th[e] = A0[2 * e] * dx + A0[2 * e + 1] * dy;
+      proj[e] = th[e] / std::sqrt(dx * dx + dy * dy);   // A0 . e_hat (solver.py:630-634)
+    }
+    theta_.upload(th, stream_);
+    ramp_proj_.upload(proj, stream_);
+    if (ramp_div_.n == 0) { ramp_div_.alloc(Nx_); ramp_zero_.alloc(Nx_); ramp_zero_.zero(stream_); }
+    k_site_terms<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+        N_, ptr_.p, eidx_.p, head_.p, weight_.p, elen_.p, areas_.p, ramp_proj_.p, ramp_zero_.p,
+        ramp_div_.p);
+    TDGL_LAUNCH_CHECK();
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+    has_dadt_ = false;
+    refresh_site_terms();
+    ramp_on_ = true;
+    h_ctl_->ramp_on = 1;
+    h_ctl_->ramp_knots = n_knots;
+    for (int k = 0; k < n_knots; ++k) { h_ctl_->ramp_t[k] = t_knots[k]; h_ctl_->ramp_v[k] = f_knots[k]; }
+    // f "before the first step" = f(0): the reference starts from A evaluated at t = 0
+    double f0 = f_knots[0];
+    if (0.0 >= t_knots[n_knots - 1]) f0 = f_knots[n_knots - 1];
+    else if (0.0 > t_knots[0]) {
+      int k = 0;
+      while (k + 2 < n_knots && 0.0 >= t_knots[k + 1]) ++k;
+      f0 = f_knots[k] + (0.0 - t_knots[k]) / (t_knots[k + 1] - t_knots[k]) * (f_knots[k + 1] - f_knots[k]);
+    }
+    h_ctl_->ramp_f = f0;
+    h_ctl_->ramp_dfdt = 0.0;
+    h_ctl_->ramp_changed = 2;   // the first step builds the link variables
+    push_ctl();
+  }
+  if (was_on != ramp_on_ && graph_mode_ == 1) {   // the step sequence changed: re-record it
+    cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
+    cudaGraphDestroy(graph_); graph_ = nullptr;
+    h_step_ = h_psi_ = h_cg_ = 0;
+    const bool on = comm_on_;
+    comm_on_ = world_ > 1;
+    build_graph();
+    comm_on_ = on;
+  }
 }
 
 void Engine::set_epsilon(const double* eps) {
@@ -1091,6 +1160,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     while (true) {
       launch_k(k_step_begin, 1, 32, 0, ctl_.p, 0);
       TDGL_LAUNCH_CHECK();
+      enqueue_ramp_links();
       do {
         enqueue_psi_step(nullptr, -1.0);
         launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), 0);
@@ -1153,7 +1223,7 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
-        tmp_e_.p, tmp_e2_.p);
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
     if (js != nullptr) tmp_e_.download(js, E_, stream_);
     if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
@@ -1180,7 +1250,7 @@ void Engine::stage_outputs(int what, void** ptrs, int64_t* counts) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
-        tmp_e_.p, tmp_e2_.p);
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
   }
   TDGL_CUDA(cudaStreamSynchronize(stream_));
@@ -1222,7 +1292,7 @@ void Engine::get_currents(double* js, double* jn) {
   unpack_state_halos(cur);
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
       E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
-        tmp_e_.p, tmp_e2_.p);
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, tmp_e_.p, tmp_e2_.p);
   TDGL_LAUNCH_CHECK();
   if (js != nullptr) tmp_e_.download(js, E_, stream_);
   if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
@@ -1327,7 +1397,8 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
   launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
            ctl_.p, static_cast<Comm*>(nullptr), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p,
-           aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, b.p, r.p, raw.p, partials_.p,
+           aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, static_cast<const double*>(nullptr), b.p, r.p,
+           raw.p, partials_.p,
            counter_.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
@@ -1587,6 +1658,13 @@ int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary) {
 }
 int tdgl_set_dA_dt(tdgl_handle* h, const double* dA_dt) {
   return guarded(h, [&](tdgl::Engine& e) { e.set_dA_dt(dA_dt); });
+}
+int tdgl_set_vector_potential_ramp(tdgl_handle* h, const double* A0, int32_t n_knots,
+                                   const double* t_knots, const double* f_knots) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (n_knots > 0 && (!A0 || !t_knots || !f_knots)) throw std::invalid_argument("null ramp argument");
+    e.set_ramp(A0, n_knots, t_knots, f_knots);
+  });
 }
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu) {
   return guarded(h, [&](tdgl::Engine& e) { e.set_state(psi, mu); });

@@ -189,6 +189,18 @@ class DeviceEngine:
         arr = None if dA_dt is None else as_f64(dA_dt, (self.n_edges,))
         self._check(self._lib.tdgl_set_dA_dt(self._h, ptr(arr)))
 
+    def set_vector_potential_ramp(self, A0, t_knots, f_knots) -> None:
+        """A(r, t) = f(t) * A0(r) evaluated on the device (f piecewise linear); ``A0`` None or
+        no knots turns it off."""
+        if A0 is None or len(t_knots) == 0:
+            self._check(self._lib.tdgl_set_vector_potential_ramp(self._h, None, 0, None, None))
+            return
+        t, f = as_f64(t_knots), as_f64(f_knots)
+        if t.shape != f.shape or t.ndim != 1:
+            raise ValueError("t_knots and f_knots must be 1-D arrays of the same length")
+        self._check(self._lib.tdgl_set_vector_potential_ramp(
+            self._h, ptr(as_f64(A0, (self.n_edges, 2))), len(t), ptr(t), ptr(f)))
+
     def set_state(self, psi, mu) -> None:
         self._check(self._lib.tdgl_set_state(
             self._h, ptr(as_c128(psi, (self.n_sites,))), ptr(as_f64(mu, (self.n_sites,)))))

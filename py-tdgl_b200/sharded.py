@@ -190,6 +190,9 @@ class LocalShardGroup:
     def set_dA_dt(self, dA_dt):
         self._all(lambda e: e.set_dA_dt(dA_dt))
 
+    def set_vector_potential_ramp(self, A0, t_knots, f_knots):
+        self._all(lambda e: e.set_vector_potential_ramp(A0, t_knots, f_knots))
+
     def set_state(self, psi, mu):
         self._all(lambda e: e.set_state(psi, mu))
 

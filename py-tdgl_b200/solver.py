@@ -124,6 +124,14 @@ class TDGLSolver:
         A = eval_A(0)
         if A.shape != edge_centers.shape:
             raise ValueError(f"Unexpected shape for vector_potential: {A.shape}.")
+        # scalar(t) * field(r) (tdgl_b200.sources): the device evaluates the ramp itself
+        ramp = None
+        sep = getattr(applied_vector_potential, "separable", None) if dynamic_A else None
+        if sep is not None:
+            spatial, t_knots, f_knots = sep
+            A0 = scales.A_scale * np.asarray(
+                spatial(edge_centers[:, 0], edge_centers[:, 1], z0))[:, :2]
+            ramp = (A0, np.asarray(t_knots, float), np.asarray(f_knots, float))
         # epsilon at the sites (solver.py:191-216)
         dynamic_epsilon = False
         if callable(disorder_epsilon):
@@ -168,17 +176,20 @@ class TDGLSolver:
         self._setup(mesh, options, A, eval_eps, dynamic_epsilon, terminal_info,
                     lambda t: {k: J_scale * v for k, v in user_func(t).items()},
                     static_currents, device.probe_point_indices, device.layer.u,
-                    device.layer.gamma, eval_A=eval_A if dynamic_A else None)
+                    device.layer.gamma, eval_A=eval_A if dynamic_A else None, ramp=ramp)
 
     @classmethod
     def from_dimensionless(cls, mesh, options: SolverOptions, *, A_applied, epsilon,
                            terminal_info: Sequence[TerminalInfo] = (),
                            terminal_currents: Union[Callable, Dict[str, float], None] = None,
                            probe_point_indices: Optional[Sequence[int]] = None,
-                           u: float = 5.79, gamma: float = 10.0, device=None) -> "TDGLSolver":
+                           u: float = 5.79, gamma: float = 10.0, device=None,
+                           A_ramp=None) -> "TDGLSolver":
         """Inputs as the reference holds them after ``__init__``: ``A_applied`` [E, 2] in
         units of xi*Bc2 — or a callable ``t -> [E, 2]`` for a time-dependent vector
-        potential — currents already multiplied by ``J_scale``."""
+        potential (host callback every step, like the reference) — currents already
+        multiplied by ``J_scale``.  ``A_ramp = (t_knots, f_knots)`` makes the potential
+        ``f(t) * A_applied`` with piecewise-linear f, evaluated on the device."""
         self = object.__new__(cls)
         self.device = device
         self.options = options
@@ -199,17 +210,24 @@ class TDGLSolver:
             filled = {n: terminal_currents.get(n, 0) for n in names}
             func, static = (lambda t, _c=filled: _c), True
         eval_A = None
-        if callable(A_applied):
+        ramp = None
+        if A_ramp is not None:
+            A0 = np.asarray(A_applied, float)
+            t_k, f_k = (np.asarray(k, float) for k in A_ramp)
+            ramp = (A0, t_k, f_k)
+            eval_A = lambda t, _A=A0, _t=t_k, _f=f_k: float(np.interp(t, _t, _f)) * _A  # noqa: E731
+            A_applied = eval_A(0.0)
+        elif callable(A_applied):
             eval_A = lambda t, _f=A_applied: np.asarray(_f(t), float)  # noqa: E731
             A_applied = eval_A(0.0)
         self._setup(mesh, options, np.asarray(A_applied, float), lambda t=None: eps, False,
                     tuple(terminal_info), func, static, probe_point_indices, u, gamma,
-                    eval_A=eval_A)
+                    eval_A=eval_A, ramp=ramp)
         return self
 
     # ------------------------------------------------------------------------------------
     def _setup(self, mesh, options, A, eval_eps, dynamic_epsilon, terminal_info, current_func,
-               static_currents, probe_points, u, gamma, eval_A=None):
+               static_currents, probe_points, u, gamma, eval_A=None, ramp=None):
         self.mesh = mesh
         self.u, self.gamma = u, gamma
         self.num_edges = len(mesh.edge_mesh.edges)
@@ -217,6 +235,7 @@ class TDGLSolver:
         self._eval_eps = eval_eps
         self.dynamic_epsilon = dynamic_epsilon
         self._eval_A = eval_A
+        self._ramp = ramp     # (A0, t_knots, f_knots): A = f(t) * A0 evaluated on the device
         self.dynamic_vector_potential = eval_A is not None
         d = np.asarray(mesh.edge_mesh.directions, float)
         self.normalized_directions = d / np.linalg.norm(d, axis=1)[:, None]
@@ -255,6 +274,8 @@ class TDGLSolver:
             use_graph=1 if options.use_cuda_graph else 2,
             running_capacity=max(int(options.save_every), 1))
         self.engine.set_link_exponents(A)
+        if ramp is not None:
+            self.engine.set_vector_potential_ramp(*ramp)
         self.engine.set_epsilon(epsilon)
         self.engine.set_stepper(
             dt_init=options.dt_init, dt_max=options.dt_max, adaptive=options.adaptive,
@@ -282,6 +303,9 @@ class TDGLSolver:
         difference over the previous step's dt projected on the edge directions, new link
         variables only if A changed."""
         if not self.dynamic_vector_potential:
+            return
+        if self._ramp is not None:      # the device evaluates the ramp; keep the host copy
+            self.current_A_applied = self._eval_A(time)
             return
         A = self._eval_A(time)
         prev = self.current_A_applied if prev_A is None else np.asarray(prev_A, float)
@@ -353,7 +377,7 @@ class TDGLSolver:
         opts = self.options
         every = max(int(opts.save_every), 1)
         per_step_host = ((not self.static_currents) or self.dynamic_epsilon
-                         or self.dynamic_vector_potential)
+                         or (self.dynamic_vector_potential and self._ramp is None))
         i, time = 0, 0.0
         cancelled = False
 
@@ -383,6 +407,10 @@ class TDGLSolver:
                         f" retries at step {fi.failed_step} with dt = {fi.failed_dt:.2e}."
                         f" Try using a smaller dt_init.") from None
                 k = info.steps_done
+                if self._ramp is not None:
+                    # the vector potential of the last step taken (saved with the results)
+                    t_last = info.time if info.finished else info.time - info.dt
+                    self.current_A_applied = self._eval_A(t_last)
                 dt, mu_p, th_p = self.engine.get_running(k)
                 pos = running.step
                 running.values["dt"][0, pos:pos + k] = dt

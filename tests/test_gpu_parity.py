@@ -264,6 +264,40 @@ def test_time_dependent_vector_potential():
                                rtol=0, atol=1e-14)
 
 
+def test_device_side_field_ramp():
+    """The same field ramp as a separable source (``LinearRamp * ConstantField``): evaluated
+    by the device inside the step loop (tdgl_set_vector_potential_ramp), no per-step host
+    work — same numbers as the reference, which calls back into Python every step."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+    from tdgl_b200.synthetic import uniform_field_vector_potential
+
+    c = load_case("film20_ramp")
+    g = c.g
+    b_max, t_ramp = (float(v) for v in g["ramp"])
+    A1 = uniform_field_vector_potential(c.mesh.edge_mesh.centers, 1.0)
+    kw = {k: v for k, v in c.opts.items() if k != "solve_time"}
+    dt = kw["dt_init"]
+    for use_graph in (True, False):
+        opts = SolverOptions(solve_time=dt * 598.5, save_every=300, use_cuda_graph=use_graph, **kw)
+        solver = TDGLSolver.from_dimensionless(
+            c.mesh, opts, A_applied=A1, A_ramp=([0.0, t_ramp], [0.0, b_max]), epsilon=c.eps,
+            probe_point_indices=c.probes, u=c.u, gamma=c.gamma)
+        sol = solver.solve()
+        d = sol.tdgl_data
+        assert len(sol.dynamics.dt) == 600
+        ref = dict(psi=g["psi"], mu=g["mu"], supercurrent=g["supercurrent"],
+                   normal_current=g["normal_current"])
+        diff = orc.compare(dict(psi=d.psi, mu=d.mu, supercurrent=d.supercurrent,
+                                normal_current=d.normal_current), ref, c.mesh.areas)
+        print("film20_ramp on the device, graph" if use_graph else "host-driven", diff)
+        for k, v in diff.items():
+            assert v < 1e-8, (k, diff)
+        np.testing.assert_allclose(d.applied_vector_potential, c.A_func(float(g["time"])),
+                                   rtol=0, atol=1e-13)
+        # two device launches for 600 steps (one per save interval), not 600 host round trips
+        assert sol.solver_stats["steps"] == 600
+
+
 def test_step_failure_raises_like_reference():
     """Non-adaptive run with a too-large dt: RuntimeError with the reference's text."""
     from tdgl_b200 import SolverOptions, TDGLSolver

@@ -180,3 +180,16 @@ def test_mesh_edge_cases():
     mesh = make_film_mesh(12, 7, 0.5, holes=((1.0, 0.5, 2.0),))
     assert abs(mesh.areas.sum() - (12 * 7 - np.pi * 2.0**2)) < 0.25   # polygonal hole outline
     assert np.all(mesh.areas > 0) and np.all(mesh.edge_mesh.dual_edge_lengths >= 0)
+
+
+def test_sources_ramp_times_field_is_separable():
+    """``LinearRamp * ConstantField`` (reference sources/scaling.py, sources/constant.py)."""
+    f = tdgl.LinearRamp(tmin=1.0, tmax=3.0, initial=0.5, final=2.0) * tdgl.ConstantField(0.2)
+    x, y, z = np.array([0.0, 1.0, 2.0]), np.array([0.0, 0.0, 1.0]), np.zeros(3)
+    A0 = tdgl.ConstantField(0.2)(x, y, z)
+    assert f.time_dependent and f.separable is not None
+    for t, s in [(0.0, 0.5), (1.0, 0.5), (2.0, 1.25), (3.0, 2.0), (9.0, 2.0)]:
+        np.testing.assert_allclose(f(x, y, z, t=t), s * A0, rtol=0, atol=1e-15)
+    assert not tdgl.ConstantField(0.2).time_dependent
+    with pytest.raises(ValueError):
+        tdgl.LinearRamp(tmin=1.0, tmax=1.0)
