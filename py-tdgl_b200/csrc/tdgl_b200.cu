@@ -810,6 +810,12 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
 }
 
 void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
+  // The window kernels request their CSR values BEFORE griddepcontrol.wait because the
+  // matrices are static — except under a device-side ramp, where k_link_values_ramp has just
+  // rewritten the Laplacian values: then this launch is an ordinary (fully ordered) one.
+  const bool pdl_saved = pdl_;
+  if (ramp_on_) pdl_ = false;
+  struct Restore { bool& ref; bool v; ~Restore() { ref = v; } } restore{pdl_, pdl_saved};
   if (comm_on_)
     launch_k(kw_psi_step<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
              ctl_.p, comm(), make_psi_comm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
