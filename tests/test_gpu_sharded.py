@@ -151,3 +151,34 @@ def test_one_process_per_gpu_torchrun():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_OK" in res.stdout
+
+
+def test_runs_are_bitwise_reproducible():
+    """Reductions are added in a fixed order (blocks, then ranks): like the reference, two
+    runs of the same problem give identical bits — single engine and 3 shards."""
+    from tdgl_b200.engine import DeviceEngine
+
+    c = load_case("film20_adaptive")
+    n = len(c.mesh.sites)
+
+    def run(e):
+        e.set_link_exponents(c.A)
+        e.set_epsilon(c.eps)
+        e.set_stepper(**_stepper(c))
+        e.set_state(np.ones(n, complex), np.zeros(n))
+        info = e.advance(60, 1e300, 0, 0.0)
+        return info[:7] + info[8:12], e.get_state(), e.get_currents()
+
+    def same(a, b):
+        assert a[0] == b[0]
+        for x, y in zip(a[1] + a[2], b[1] + b[2]):
+            np.testing.assert_array_equal(x, y)
+
+    with DeviceEngine(c.mesh, gamma=c.gamma, u=c.u, running_capacity=64) as e:
+        r1 = run(e)
+    with DeviceEngine(c.mesh, gamma=c.gamma, u=c.u, running_capacity=64) as e:
+        same(r1, run(e))
+    with _group(c, 3, running_capacity=64) as g:
+        s1 = run(g)
+    with _group(c, 3, running_capacity=64) as g:
+        same(s1, run(g))
