@@ -160,9 +160,12 @@ __device__ __forceinline__ void comm_allreduce(Ctl* ctl, Comm* c, double* v, int
 //   kTagPsiCur    psi_tag[cur]              the accepted psi
 //   kTagMu        solve_epoch               mu of this step's solve (after the gauge shift)
 //   kTagMuPrev    solve_epoch - 1           mu of the previous step (read by the rhs kernel)
+//   kTagMuPrev2   solve_epoch - 2           mu of the step before (still in the other parity
+//                                           buffer of the mailbox; the rhs kernel's mu_prev)
 // Each channel's mailbox is double-buffered by tag parity; between two stores into the same
 // buffer lies at least one all-reduce that every rank has passed, so its readers are done.
-enum : int { kTagIter = 0, kTagIterNext, kTagIter0, kTagPsiNew, kTagPsiCur, kTagMu, kTagMuPrev };
+enum : int { kTagIter = 0, kTagIterNext, kTagIter0, kTagPsiNew, kTagPsiCur, kTagMu, kTagMuPrev,
+             kTagMuPrev2 };
 
 __device__ __forceinline__ unsigned int comm_tag(const Ctl* ctl, int mode) {
   const unsigned int s = static_cast<unsigned int>(ctl->solve_epoch) << 10;
@@ -173,7 +176,8 @@ __device__ __forceinline__ unsigned int comm_tag(const Ctl* ctl, int mode) {
     case kTagPsiNew: return static_cast<unsigned int>(ctl->psi_epoch) + 1u;
     case kTagPsiCur: return static_cast<unsigned int>(ctl->psi_tag[ctl->cur]);
     case kTagMu: return static_cast<unsigned int>(ctl->solve_epoch);
-    default: return static_cast<unsigned int>(ctl->solve_epoch) - 1u;
+    case kTagMuPrev: return static_cast<unsigned int>(ctl->solve_epoch) - 1u;
+    default: return static_cast<unsigned int>(ctl->solve_epoch) - 2u;
   }
 }
 

@@ -407,9 +407,10 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
 // The complex and the real matrix share one CSR structure and are staged together.
 template <bool SH>
 __global__ void __launch_bounds__(kWinRows)
-kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, WinCsr m,
+kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_halo, WinCsr m,
           const double2* __restrict__ lval, const double* __restrict__ aval,
           const double2* psi_buf0, const double2* psi_buf1, const double* __restrict__ mu,
+          const double* __restrict__ mu_prev, double* __restrict__ d_out,
           const double* __restrict__ areas, const double* __restrict__ bterm,
           const double* __restrict__ ramp_div /* null: no device-side ramp */,
           double* __restrict__ b, double* __restrict__ r,
@@ -427,13 +428,14 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
   const bool live = (ctl->status == 0);
   const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
   const bool in = live && w.row < m.rows;
-  HaloView hpsi, hmu;
-  hpsi.n_owned = hmu.n_owned = 0x7fffffff; hpsi.box = hmu.box = nullptr; hpsi.tag = hmu.tag = 0u;
-  unsigned int tag_out = 0u;
+  HaloView hpsi, hmu, hmp;
+  hpsi.n_owned = hmu.n_owned = hmp.n_owned = 0x7fffffff;
+  hpsi.box = hmu.box = hmp.box = nullptr;
+  hpsi.tag = hmu.tag = hmp.tag = 0u;
   if (SH && comm != nullptr) {
     hpsi = halo_view(ctl, comm, pc.halo[ctl->cur]);
     hmu = halo_view(ctl, comm, mu_halo);
-    tag_out = comm_tag(ctl, r_push.tag_mode);
+    hmp = halo_view(ctl, comm, mu_prev_halo);   // (the other parity buffer of mu's mailbox)
   }
   double2 p = make_double2(0.0, 0.0);
   double ai = 0.0, bt = 0.0;
@@ -446,26 +448,36 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
   }
   mbar_wait(&bar, 0);
   if (!live) return;
-  double dbb = 0.0, drr = 0.0;
+  // Initial guess of the solve: mu_g = mu + c (mu - mu_prev) (mu, mu_prev: the last two
+  // solutions).  Its residual is r + c d with r = b - A mu, d = A mu_prev - A mu, so the c
+  // that minimises it follows from three dot products (k_cg_begin) — never worse than the
+  // plain warm start (c = 0), and 2-4 CG iterations cheaper while the dynamics are smooth.
+  double dbb = 0.0, drr = 0.0, drd = 0.0, ddd = 0.0;
   if (in) {
     const double2 lap = row_dot_c<SH>(sl, si, w.kb, w.ke, psi, ctl, hpsi);
     const double am = row_dot<SH>(sa, si, w.kb, w.ke, mu, ctl, hmu);
+    const double amp = row_dot<SH>(sa, si, w.kb, w.ke, mu_prev, ctl, hmp);
     const double rhs = (p.x * lap.y - p.y * lap.x) - bt;
     if (rhs_raw != nullptr) rhs_raw[w.row] = rhs;
     const double bi = -ai * rhs;
     const double ri = bi - am;
+    const double di = amp - am;
     b[w.row] = bi;
     r[w.row] = ri;
-    if (SH && comm != nullptr) push_row(comm, r_push, tag_out, w.row, ri);  // iteration 0's V-cycle input
+    d_out[w.row] = di;
     dbb = bi * bi;
     drr = ri * ri;
+    drd = ri * di;
+    ddd = di * di;
   }
-  // two sums through one deterministic reduction
-  const double sb = block_sum(dbb, red);
-  const double sr = block_sum(drr, red);
+  // four sums through one deterministic reduction
+  double v[4];
+  v[0] = block_sum(dbb, red);
+  v[1] = block_sum(drr, red);
+  v[2] = block_sum(drd, red);
+  v[3] = block_sum(ddd, red);
   if (threadIdx.x == 0) {
-    partials[2 * blockIdx.x] = sb;
-    partials[2 * blockIdx.x + 1] = sr;
+    for (int k = 0; k < 4; ++k) partials[4 * blockIdx.x + k] = v[k];
     __threadfence();
     const unsigned int t = atomicAdd(counter, 1u);
     s_last = (t == gridDim.x - 1);
@@ -473,23 +485,17 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, PushArgs r_push, W
   __syncthreads();
   if (s_last) {
     __threadfence();
-    double a0 = 0.0, a1 = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-      a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
-      a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
-    }
-    a0 = block_sum(a0, red);
-    a1 = block_sum(a1, red);
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+      for (int k = 0; k < 4; ++k) a[k] += reinterpret_cast<volatile double*>(partials)[4 * i + k];
+    for (int k = 0; k < 4; ++k) a[k] = block_sum(a[k], red);
     if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0
-      if (SH && comm != nullptr) {
-        double v[2] = {a0, a1};
-        comm_allreduce(ctl, comm, v, 2, false);
-        a0 = v[0];
-        a1 = v[1];
-      }
+      if (SH && comm != nullptr) comm_allreduce(ctl, comm, a, 4, false);
       if (threadIdx.x == 0) {
-        ctl->bb = a0;
-        ctl->rr = a1;
+        ctl->bb = a[0];
+        ctl->rr = a[1];
+        ctl->rd = a[2];
+        ctl->dd = a[3];
         *counter = 0u;
       }
     }

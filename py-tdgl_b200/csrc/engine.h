@@ -169,7 +169,7 @@ class Engine {
   void set_mu_boundary(const double* mub);
   void set_dA_dt(const double* dadt);
   void set_ramp(const double* A0, int n_knots, const double* t_knots, const double* f_knots);
-  void set_state(const double* psi, const double* mu);
+  void set_state(const double* psi, const double* mu, bool reset_history = true);
   void set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
                    double multiplier);
   struct AdvanceInfo {
@@ -266,6 +266,7 @@ class Engine {
   int nc_ = 0;
   int64_t amg_nnz_ = 0;
   DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_;
+  DevBuf<double> mu_prev_;   // the solution before the last one (extrapolated initial guess)
   DevBuf<double> partials_;
   DevBuf<unsigned int> counter_;
   // ---- scratch for IO ------------------------------------------------------------------------
@@ -321,7 +322,8 @@ class Engine {
   void enqueue_mu_rhs(double* rhs_raw);
   void enqueue_cg_iteration(cudaGraphConditionalHandle cond);
   void enqueue_mu_finish();
-  void host_solve_loop();   // host-driven CG loop on the current b/r
+  void host_solve_loop(bool with_guess = false);   // host-driven CG loop on the current b/r
+  void enqueue_solve_begin(cudaGraphConditionalHandle cond);
   Comm* comm() const { return comm_on_ ? comm_.p : nullptr; }
   PushArgs make_push(int level, int channel, int tag_mode) const;
   HaloArgs make_halo(int level, int channel, int tag_mode) const;

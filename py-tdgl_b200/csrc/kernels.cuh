@@ -46,6 +46,7 @@ struct Ctl {
   long long n_hist;
   // --- CG ---------------------------------------------------------------------------------
   double rz_new, rz_prev, pAp, rr, bb;
+  double rd, dd, guess_c;   // initial guess mu + c (mu - mu_prev): r.d, d.d, the optimal c
   int cg_it, cg_go;
   long long total_cg_it;
   int step_go;
@@ -234,10 +235,19 @@ k_cg_update(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict
 
 // Decide whether the CG loop has to run at all (warm start may already satisfy the
 // tolerance) and arm its counters.
-__global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond) {
+__global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond, int with_guess) {
   griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int go = 0;
+  // optimal extrapolation of the initial guess (see kw_mu_rhs): c = -r.d / d.d
+  double c = 0.0;
+  if (with_guess && ctl->dd > 0.0 && ctl->status == 0) {
+    c = -ctl->rd / ctl->dd;
+    if (!(c == c) || fabs(c) > 8.0) c = 0.0;   // (degenerate history: plain warm start)
+    const double rr = ctl->rr + c * (2.0 * ctl->rd + c * ctl->dd);
+    ctl->rr = rr > 0.0 ? rr : 0.0;
+  }
+  ctl->guess_c = c;
   if (ctl->status == 0) {
     const double tol2 = ctl->mu_rtol * ctl->mu_rtol * ctl->bb;
     go = (ctl->rr > tol2) ? 1 : 0;
@@ -248,6 +258,27 @@ __global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond) {
   ctl->cg_it = 0;
   ctl->cg_go = go;
   set_cond(cond, go);
+}
+
+// Applies the extrapolated initial guess chosen by k_cg_begin: mu <- mu + c (mu - mu_prev),
+// r <- r + c d, and keeps the old mu as the next step's mu_prev.  Sharded: the boundary rows
+// of r go to the neighbours (iteration 0's V-cycle input).
+__global__ void __launch_bounds__(kBlock)
+k_mu_guess(const Ctl* __restrict__ ctl, const Comm* comm, PushArgs push, int n,
+           double* __restrict__ mu, double* __restrict__ mu_prev, double* __restrict__ r,
+           const double* __restrict__ d) {
+  griddep_enter();
+  if (ctl->status != 0) return;
+  const double c = ctl->guess_c;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double old = mu[i];
+    mu[i] = old + c * (old - mu_prev[i]);
+    mu_prev[i] = old;
+    const double ri = r[i] + c * d[i];
+    r[i] = ri;
+    if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, ri);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

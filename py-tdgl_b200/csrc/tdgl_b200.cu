@@ -477,8 +477,10 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   }
 
   cg_b_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_);
+  mu_prev_.alloc(Nx_);
+  mu_prev_.zero(stream_);
   const size_t max_grid = static_cast<size_t>(max_grid_rows) + 2;
-  partials_.alloc(2 * std::max<size_t>(max_grid, 4096));
+  partials_.alloc(4 * std::max<size_t>(max_grid, 4096));
   counter_.alloc(4);
   counter_.zero(stream_);
   tmp_c_.alloc(Ng_);
@@ -831,15 +833,24 @@ void Engine::enqueue_mu_rhs(double* rhs_raw) {
   if (comm_on_)
     launch_k(kw_mu_rhs<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
              ctl_.p, comm(), make_psi_comm(), make_halo(0, kVecMu, kTagMuPrev),
-             make_push(0, kVecCgR, kTagIter0), site_csr(), lval_.p, aval_.p, psi_[0].p, psi_[1].p,
-             mu_.p, areas_.p, bterm_.p, ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw,
-             partials_.p, counter_.p);
+             make_halo(0, kVecMu, kTagMuPrev2), site_csr(), lval_.p, aval_.p, psi_[0].p,
+             psi_[1].p, mu_.p, mu_prev_.p, cg_Ap_.p, areas_.p, bterm_.p,
+             ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
   else
     launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
-             ctl_.p, comm(), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p, aval_.p,
-             psi_[0].p, psi_[1].p, mu_.p, areas_.p, bterm_.p, ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p,
-             cg_r_.p, rhs_raw,
-             partials_.p, counter_.p);
+             ctl_.p, comm(), PsiComm(), HaloArgs(), HaloArgs(), site_csr(), lval_.p, aval_.p,
+             psi_[0].p, psi_[1].p, mu_.p, mu_prev_.p, cg_Ap_.p, areas_.p, bterm_.p,
+             ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
+  TDGL_LAUNCH_CHECK();
+}
+
+// Start of the mu solve: decide the initial guess (k_cg_begin), apply it (k_mu_guess).
+void Engine::enqueue_solve_begin(cudaGraphConditionalHandle cond) {
+  launch_k(k_cg_begin, 1, 32, 0, ctl_.p, cond, 1);
+  TDGL_LAUNCH_CHECK();
+  launch_k(k_mu_guess, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
+           comm_on_ ? make_push(0, kVecCgR, kTagIter0) : PushArgs(), N_, mu_.p, mu_prev_.p,
+           cg_r_.p, cg_Ap_.p);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -873,9 +884,13 @@ void Engine::enqueue_mu_finish() {
   TDGL_LAUNCH_CHECK();
 }
 
-void Engine::host_solve_loop() {
-  launch_k(k_cg_begin, 1, 32, 0, ctl_.p, 0);
-  TDGL_LAUNCH_CHECK();
+void Engine::host_solve_loop(bool with_guess) {
+  if (with_guess) {
+    enqueue_solve_begin(0);
+  } else {
+    launch_k(k_cg_begin, 1, 32, 0, ctl_.p, 0, 0);
+    TDGL_LAUNCH_CHECK();
+  }
   sync_ctl_to_host();
   while (h_ctl_->cg_go) {
     enqueue_cg_iteration(0);
@@ -953,8 +968,7 @@ void Engine::build_graph() {
   }
   sb.capture([&] {
     enqueue_mu_rhs(nullptr);
-    launch_k(k_cg_begin, 1, 32, 0, ctl_.p, h_cg_);
-    TDGL_LAUNCH_CHECK();
+    enqueue_solve_begin(h_cg_);
   });
   cudaGraph_t cg_body = sb.add_while(h_cg_);
   {
@@ -1083,7 +1097,7 @@ void Engine::refresh_site_terms() {
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
 
-void Engine::set_state(const double* psi, const double* mu) {
+void Engine::set_state(const double* psi, const double* mu, bool reset_history) {
   sync_ctl_to_host();
   const int cur = h_ctl_->cur;
   TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi, sizeof(double2) * Ng_, cudaMemcpyHostToDevice, stream_));
@@ -1093,6 +1107,11 @@ void Engine::set_state(const double* psi, const double* mu) {
   tmp_d_.upload(mu, Ng_, stream_);
   k_gather<double><<<(Nx_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(Nx_, dperm_.p, tmp_d_.p, mu_.p);
   TDGL_LAUNCH_CHECK();
+  // no history for the extrapolated initial guess of the next solve: mu_prev = mu.  (The
+  // step seam keeps it: a caller that threads the results back in, as Runner does, gets
+  // exactly the steps of the device loop.)
+  if (reset_history)
+    TDGL_CUDA(cudaMemcpyAsync(mu_prev_.p, mu_.p, sizeof(double) * Nx_, cudaMemcpyDeviceToDevice, stream_));
   fill_state_boxes();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -1113,9 +1132,13 @@ void Engine::fill_state_boxes() {
   k_fill_box<double2><<<g, 256, 0, stream_>>>(comm_.p, lay.box_off[chp], lay.box_off[chp] + lay.box_cap[chp],
                                              static_cast<unsigned int>(h_ctl_->psi_epoch), N_, n_halo, psi_[cur].p);
   TDGL_LAUNCH_CHECK();
-  k_fill_box<double><<<g, 256, 0, stream_>>>(comm_.p, lay.box_off[kVecMu], lay.box_off[kVecMu] + lay.box_cap[kVecMu],
-                                            static_cast<unsigned int>(h_ctl_->solve_epoch), N_, n_halo, mu_.p);
-  TDGL_LAUNCH_CHECK();
+  // mu's mailbox holds the last two solutions (tags solve_epoch and solve_epoch - 1, one per
+  // parity buffer): the rhs kernel reads mu and mu_prev halos from them
+  for (int back = 0; back < 2; ++back) {
+    k_fill_box<double><<<g, 256, 0, stream_>>>(comm_.p, lay.box_off[kVecMu], lay.box_off[kVecMu] + lay.box_cap[kVecMu],
+                                              static_cast<unsigned int>(h_ctl_->solve_epoch - back), N_, n_halo, mu_.p);
+    TDGL_LAUNCH_CHECK();
+  }
 }
 
 void Engine::set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
@@ -1160,7 +1183,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     const int64_t L = static_cast<int64_t>(levels_.size());
     const int64_t ex_step = 0, ex_it = world_ > 1 ? 1 : 0;  // (the all-gather unpack of level rep)
     const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
-    launches_ += h_ctl_->steps_done * (6 + ex_step) + h_ctl_->total_retries * 2 +
+    launches_ += h_ctl_->steps_done * (7 + ex_step + (ramp_on_ ? 1 : 0)) + h_ctl_->total_retries * 2 +
                  h_ctl_->total_cg_it * (3 + 4 * split + 1 + ex_it);
   } else {
     while (true) {
@@ -1175,7 +1198,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
       } while (h_ctl_->psi_go);
       if (h_ctl_->status != 0) break;
       enqueue_mu_rhs(nullptr);
-      host_solve_loop();
+      host_solve_loop(true);
       enqueue_mu_finish();
       launch_k(k_step_end, 1, kMaxProbes, 0, ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
                                               run_dt_.p, run_mu_.p, run_theta_.p, 0);
@@ -1208,7 +1231,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
 
 Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t step, double time,
                                    double* psi_out, double* mu_out, double* js, double* jn) {
-  set_state(psi, mu);
+  set_state(psi, mu, /*reset_history=*/false);
   AdvanceInfo info = advance(1, 1e300, step, time);
   const int cur = h_ctl_->cur;
   const int g = (N_ + kBlock - 1) / kBlock;
@@ -1402,10 +1425,9 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   sync_ctl_to_host();
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
   launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
-           ctl_.p, static_cast<Comm*>(nullptr), PsiComm(), HaloArgs(), PushArgs(), site_csr(), lval_.p,
-           aval_.p, pin.p, pin.p, mu_.p, areas_.p, bterm_.p, static_cast<const double*>(nullptr), b.p, r.p,
-           raw.p, partials_.p,
-           counter_.p);
+           ctl_.p, static_cast<Comm*>(nullptr), PsiComm(), HaloArgs(), HaloArgs(), site_csr(),
+           lval_.p, aval_.p, pin.p, pin.p, mu_.p, mu_.p, cg_Ap_.p, areas_.p, bterm_.p,
+           static_cast<const double*>(nullptr), b.p, r.p, raw.p, partials_.p, counter_.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
   TDGL_LAUNCH_CHECK();
