@@ -404,7 +404,7 @@ def run_b200(args, rank, world, local_rank):
     levels = info0["amg_levels"]
     kern = {
         "kw_psi_step": (0, 20 * nnz + 52 * nl, 1.0),
-        "kw_mu_rhs": (1, 28 * nnz + 60 * nl, 1.0),
+        "kw_mu_rhs": (1, 28 * nnz + 76 * nl, 1.0),   # (+ mu_prev read, d written)
         "kw_real<spmv_dot> fine level": (2, 12 * nnz + 20 * nl, iters_per_step),
     }
     if levels > 1:

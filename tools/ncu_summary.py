@@ -28,9 +28,10 @@ OPS = {"kw_real<0>": "kw_real<spmv_dot>", "kw_real<1>": "kw_real<residual>",
 
 def short(name):
     name = re.sub(r"\(.*", "", name).replace("void ", "").replace("tdgl::", "").strip()
-    m = re.match(r"kw_real<\(?(?:int\))?(\d), \(?(?:bool\))?(\d)>", name)
+    m = re.match(r"kw_real<\(?(?:int\))?(\d), \(?(?:bool\))?(\d)(?:, \(?(?:int\))?(\d))?>", name)
     if m:
-        return OPS[f"kw_real<{m.group(1)}>"] + (" [sharded]" if m.group(2) == "1" else "")
+        return (OPS[f"kw_real<{m.group(1)}>"] + (" [sharded]" if m.group(2) == "1" else "")
+                + (" [4 lanes/row]" if m.group(3) == "4" else ""))
     return OPS.get(name, name)
 
 
