@@ -170,6 +170,29 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel's fine-level launch from the
+    committed `ncu --set full` capture of this command on the 1M-site workload
+    (profiles/r1_full.md, written by tools/ncu_summary.py); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "r1_full.md")
+    try:
+        best = None
+        with open(path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split("|")]
+                if len(c) < 6 or c[1] != kernel:
+                    continue
+                grid = int(c[2].strip("()").split(",")[0])
+                mb = float(c[-3])
+                if best is None or grid > best[0]:
+                    best = (grid, mb)
+        if best is not None:
+            return best[1] * 1e6, "profiles/r1_full.md (ncu --set full, 1M-site workload)"
+    except (OSError, ValueError, IndexError):
+        pass
+    return None, None
+
+
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
@@ -418,9 +441,13 @@ def run_b200(args, rank, world, local_rank):
                        "share_of_step": per_step * kms / (ms_total / K)}
     vc_ms = eng.time_kernel(3, 10, flush_l2=True) if levels > 1 else None
     dom = max(table, key=lambda k: table[k]["share_of_step"])
+    traffic, traffic_src = (ncu_traffic(dom.split(" fine level")[0])
+                            if world == 1 and args.workload == "film1m_holes_transport"
+                            else (None, None))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBps"], "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": table[dom]["frac"],
-                "traffic": None, "kernels": table, "vcycle_ms": vc_ms}
+                "traffic": traffic, "traffic_source": traffic_src, "kernels": table,
+                "vcycle_ms": vc_ms}
 
     line = {
         "metric": "tdgl_site_steps_per_sec", "value": steps_per_s * n, "unit": "site-steps/s",
