@@ -316,7 +316,6 @@ class Engine {
                         double* x, double* r);
   void launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
                      const double* x, double* y, const double* w, double* dot_out);
-  void launch_residual(const CsrView& A, const double* x, const double* b, double* r, double* rr);
   void enqueue_vcycle(double* r_in, double* z_out, double* rz_out);
   void enqueue_psi_step(double* sq_out, double dt_override);
   void enqueue_mu_rhs(double* rhs_raw);

@@ -653,7 +653,6 @@ void Engine::configure_kernels() {
   allow(reinterpret_cast<const void*>(&kw_real<OP, false, 4>));        \
   allow(reinterpret_cast<const void*>(&kw_real<OP, true, 4>));
   TDGL_ALLOW_REAL(kOpSpmvDot)
-  TDGL_ALLOW_REAL(kOpResidual)
   TDGL_ALLOW_REAL(kOpPresmooth)
   TDGL_ALLOW_REAL(kOpJacobi)
   TDGL_ALLOW_REAL(kOpPlain)
@@ -715,12 +714,6 @@ void Engine::launch_jacobi(const CsrView& A, const double* dinv, double omega, c
   launch_real<kOpJacobi>(A, a);
 }
 
-void Engine::launch_residual(const CsrView& A, const double* x, const double* b, double* r,
-                             double* rr) {
-  RealArgs a;
-  a.val = A.val; a.x = x; a.b = b; a.y = r; a.red_out = rr;
-  launch_real<kOpResidual>(A, a);
-}
 
 // z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
 // smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
@@ -1231,7 +1224,9 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
 
 Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t step, double time,
                                    double* psi_out, double* mu_out, double* js, double* jn) {
-  set_state(psi, mu, /*reset_history=*/false);
+  // (sharded: the mailbox copy of mu_prev's halo is refilled from the caller's mu, so the
+  // history is reset there to stay consistent across the cuts)
+  set_state(psi, mu, /*reset_history=*/world_ > 1);
   AdvanceInfo info = advance(1, 1e300, step, time);
   const int cur = h_ctl_->cur;
   const int g = (N_ + kBlock - 1) / kBlock;
