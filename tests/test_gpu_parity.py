@@ -174,7 +174,7 @@ def test_adaptive_vortex_trajectory():
 def test_transport_trajectory():
     """Terminals + holes + transport current.  The flow is smooth up to step ~170, then a
     symmetry-breaking instability (phase slips / vortex entry at the holes) amplifies
-    roundoff-level differences by ~x100 per 10 steps (tools/parity_trace.py; the reference
+    roundoff-level differences by ~x100 per 10 steps (tests/tools/parity_trace.py; the reference
     shows the same sensitivity to a 1e-13 perturbation of its own initial state, checked
     below).  Parity: 1e-8 on psi / mu at steps 50, 100, 150 and on the dt sequence up to
     there (required 1e-6); physics-level agreement at the end."""

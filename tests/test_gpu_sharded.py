@@ -147,7 +147,7 @@ def test_one_process_per_gpu_torchrun():
     port = 29500 + os.getpid() % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tools", "dist_check.py")]
+           os.path.join(ROOT, "tests", "tools", "dist_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_OK" in res.stdout

@@ -1,10 +1,10 @@
 """torchrun worker: film20_fixed on world shards, one process per GPU, through
 TDGLSolver(options.distributed=True); rank 0 checks parity with the golden fixture.
-  torchrun --nproc-per-node N tools/dist_check.py [steps]"""
+  torchrun --nproc-per-node N tests/tools/dist_check.py [steps]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

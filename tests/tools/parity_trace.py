@@ -1,10 +1,10 @@
 """Lock-step trace of the CUDA engine against the CPU oracle on a golden case: both advance
 their own trajectory; every `stride` steps the gauge-fixed differences are printed.
-Usage: python tools/parity_trace.py <case|smoke> [steps] [stride] [mu_rtol]"""
+Usage: python tests/tools/parity_trace.py <case|smoke> [steps] [stride] [mu_rtol]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

@@ -1,10 +1,10 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck):
-   compute-sanitizer --tool memcheck python tools/sanitize.py"""
+   compute-sanitizer --tool memcheck python tests/tools/sanitize.py"""
 import os
 import sys
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

@@ -1,9 +1,9 @@
-"""Debug driver for the in-process sharded engine: python tools/shard_check.py [world] [steps] [graph]"""
+"""Debug driver for the in-process sharded engine: python tests/tools/shard_check.py [world] [steps] [graph]"""
 import os
 import sys
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
