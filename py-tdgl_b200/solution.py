@@ -212,3 +212,30 @@ class Solution:
         np.savez_compressed(path, **out)
         self.path = path if path.endswith(".npz") else path + ".npz"
         return self.path
+
+    @classmethod
+    def from_npz(cls, path: str, device=None, options=None) -> "Solution":
+        """Load a tree written by :meth:`to_npz` (the counterpart of the reference's
+        ``Solution.from_hdf5``, solution/solution.py:933-1005, for the data this path
+        produces)."""
+        saved = SavedSteps()
+        groups: Dict[int, Dict[str, Any]] = {}
+        with np.load(path, allow_pickle=False) as f:
+            for key in f.files:
+                parts = key.split("/")
+                if parts[0] != "data":
+                    saved.fixed[key] = f[key]
+                    continue
+                grp = groups.setdefault(int(parts[1]), {"attrs": {}})
+                if parts[2] == "attrs":
+                    v = f[key]
+                    grp["attrs"][parts[3]] = v.item() if v.ndim == 0 else v
+                elif parts[2] == "running_state":
+                    grp.setdefault("running_state", {})[parts[3]] = f[key]
+                else:
+                    grp[parts[2]] = f[key]
+        saved.groups = [groups[k] for k in sorted(groups)]
+        sol = cls(device=device, options=options, saved=saved, path=path)
+        sol.load_tdgl_data(-1)
+        return sol
+

@@ -193,3 +193,37 @@ def test_sources_ramp_times_field_is_separable():
     assert not tdgl.ConstantField(0.2).time_dependent
     with pytest.raises(ValueError):
         tdgl.LinearRamp(tmin=1.0, tmax=1.0)
+
+
+def test_solution_npz_round_trip(tmp_path):
+    """Save / load equality of the output tree (reference test_solution.py:53-61, with the
+    .npz stand-in for HDF5: h5py is not in this image)."""
+    from tdgl_b200.solution import Solution
+
+    n, e = 5, 7
+    rng = np.random.default_rng(0)
+    s = SavedSteps()
+    s.save_fixed_values({"applied_vector_potential": rng.normal(size=(e, 2)), "epsilon": np.ones(n)})
+    for k in range(3):
+        vals = {"psi": rng.normal(size=n) + 1j * rng.normal(size=n), "mu": rng.normal(size=n),
+                "supercurrent": rng.normal(size=e), "normal_current": rng.normal(size=e),
+                "induced_vector_potential": np.zeros((e, 2))}
+        rs = None if k == 0 else {"dt": np.array([[1e-3, 2e-3]]),
+                                  "mu": rng.normal(size=(2, 2)), "theta": rng.normal(size=(2, 2))}
+        s.save_time_step({"step": 2 * k, "time": 3e-3 * k, "dt": 2e-3}, vals, rs)
+    opts = tdgl.SolverOptions(solve_time=1.0)
+    sol = Solution(device=None, options=opts, saved=s)
+    sol.load_tdgl_data(-1)
+    path = sol.to_npz(str(tmp_path / "out"))
+    back = Solution.from_npz(path, options=opts)
+    assert back.data_range == sol.data_range == (0, 2)
+    for step in range(3):
+        sol.solve_step = back.solve_step = step
+        a, b = sol.tdgl_data, back.tdgl_data
+        for name in ("psi", "mu", "supercurrent", "normal_current", "applied_vector_potential",
+                     "induced_vector_potential", "epsilon"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(b, name))
+        assert a.state["step"] == b.state["step"] and a.state["time"] == b.state["time"]
+    np.testing.assert_array_equal(sol.dynamics.dt, back.dynamics.dt)
+    np.testing.assert_array_equal(sol.dynamics.mu, back.dynamics.mu)
+    np.testing.assert_array_equal(sol.dynamics.voltage(0, 1), back.dynamics.voltage(0, 1))
