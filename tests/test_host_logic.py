@@ -227,3 +227,35 @@ def test_solution_npz_round_trip(tmp_path):
     np.testing.assert_array_equal(sol.dynamics.dt, back.dynamics.dt)
     np.testing.assert_array_equal(sol.dynamics.mu, back.dynamics.mu)
     np.testing.assert_array_equal(sol.dynamics.voltage(0, 1), back.dynamics.voltage(0, 1))
+
+
+def test_fp32_vcycle_keeps_iteration_count():
+    """Design study for the next round, on the SciPy prototype of the mu
+    solver (oracle/amg_proto.py): running the V-cycle — the preconditioner only — in fp32
+    leaves the fp64 CG at the same iteration count and the same final residual."""
+    from oracle import amg_proto as ap
+
+    mesh = make_film_mesh(80, 50, 0.43, holes=((5.0, 3.0, 6.0),))
+    n = len(mesh.sites)
+    em = mesh.edge_mesh
+    A = ap.sym_mu_matrix(em.edges, em.edge_lengths, em.dual_edge_lengths, n).tocsr()
+    levels = ap.build_hierarchy(A, theta=0.08)
+    b = A @ np.random.default_rng(0).normal(size=n)
+    _, h64 = ap.pcg(A, b, lambda r: ap.vcycle(levels, r))
+    lv32 = []
+    for lv in levels:
+        m = ap.Level()
+        m.A, m.d, m.rho = lv.A.astype(np.float32), lv.d.astype(np.float32), lv.rho
+        if hasattr(lv, "P"):
+            m.P, m.R = lv.P.astype(np.float32), lv.R.astype(np.float32)
+        if hasattr(lv, "pinv"):
+            m.pinv = lv.pinv.astype(np.float32)
+        lv32.append(m)
+
+    def m32(r):
+        s = np.abs(r).max()
+        return ap.vcycle(lv32, (r / s).astype(np.float32)).astype(np.float64) * s
+
+    _, h32 = ap.pcg(A, b, m32)
+    assert h64[-1] < 1e-10 and h32[-1] < 1e-10
+    assert abs(len(h32) - len(h64)) <= 1, (len(h32), len(h64))
