@@ -259,3 +259,36 @@ def test_fp32_vcycle_keeps_iteration_count():
     _, h32 = ap.pcg(A, b, m32)
     assert h64[-1] < 1e-10 and h32[-1] < 1e-10
     assert abs(len(h32) - len(h64)) <= 1, (len(h32), len(h64))
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/tdgl_b200.h is a plain C header and the library links from a C program
+    (the boundary a non-Python host would bind): version string, struct sizes and the
+    argument check of tdgl_create, which happens before any device work."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    _lib.load()
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include "tdgl_b200.h"
+#include <stdio.h>
+#include <string.h>
+int main(void) {
+  tdgl_config cfg; memset(&cfg, 0, sizeof cfg); cfg.struct_size = (int32_t)sizeof cfg;
+  printf("%s %zu %zu\n", tdgl_version(), sizeof cfg, sizeof(tdgl_advance_info));
+  tdgl_handle* h = 0;
+  int rc = tdgl_create(&h, 2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0, &cfg);
+  printf("%d %s\n", rc, tdgl_last_error(0));
+  return rc == TDGL_E_INVALID && h == 0 ? 0 : 1;
+}
+''')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-ltdgl_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in out and " 64 96" in out and "null array argument" in out
