@@ -160,3 +160,21 @@ def test_halo_exchange_world2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "GLOO_OK 2" in res.stdout
+
+
+def test_shard_plan_edge_cases(problem):
+    """What cannot be sharded is refused loudly: more than 8 shards, a mesh so small that its
+    AMG hierarchy has a single level; one shard is the identity plan."""
+    from tdgl_b200._lib import TDGLLibraryError
+    from tdgl_b200.mesh import make_film_mesh
+
+    mesh, rhs = problem
+    with pytest.raises(TDGLLibraryError, match="at most 8"):
+        host_shard_probe(mesh, 9)
+    tiny = make_film_mesh(4, 3, 0.5)          # ~60 sites: one level (<= 200 rows)
+    with pytest.raises(TDGLLibraryError, match="too small to shard"):
+        host_shard_probe(tiny, 2)
+    one = host_shard_probe(mesh, 1, rhs=rhs)
+    g = host_amg_probe(mesh, rhs=rhs)
+    assert one["iterations"] == g["iterations"] and one["halo_sizes"].sum() == 0
+    np.testing.assert_allclose(one["x"], g["x"], rtol=0, atol=1e-9 * np.abs(g["x"]).max())
