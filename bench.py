@@ -70,6 +70,18 @@ WORKLOADS = {
         holes=((141.5, 141.5, 28.3), (-141.5, 141.5, 28.3), (141.5, -141.5, 28.3),
                (-141.5, -141.5, 28.3)),
         terminals=True, current=113.2, opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    # the same film at 4x and 8x the area: the weak-scaling series is ONE geometry family
+    # (holes film, ~1M sites per GPU, same current density)
+    "film4m_holes_transport": dict(
+        width=800.0, height=800.0, h=0.4225, b=0.0,
+        holes=((200.0, 200.0, 40.0), (-200.0, 200.0, 40.0), (200.0, -200.0, 40.0),
+               (-200.0, -200.0, 40.0)),
+        terminals=True, current=160.0, opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
+    "film8m_holes_transport": dict(
+        width=1131.4, height=1131.4, h=0.4225, b=0.0,
+        holes=((282.85, 282.85, 56.57), (-282.85, 282.85, 56.57), (282.85, -282.85, 56.57),
+               (-282.85, -282.85, 56.57)),
+        terminals=True, current=226.28, opts=dict(dt_init=1e-4, dt_max=1e-1, adaptive=True)),
     # BASELINE.json configs[3]: long strip with transport current (4 GPUs)
     "strip4m_transport": dict(
         width=3200.0, height=200.0, h=0.4225, b=0.0, holes=(), terminals=True, current=40.0,
@@ -108,8 +120,30 @@ def auto_workload(n_gpus: int, mode: str) -> str:
     """BASELINE.json's configuration for this GPU count (weak mode) or the 1-GPU one."""
     if mode != "weak" or n_gpus == 1:
         return "film1m_holes_transport"
-    return {2: "film2m_holes_transport", 4: "strip4m_transport", 8: "film10m_field"}.get(
-        n_gpus, "film4m_field")
+    return {2: "film2m_holes_transport", 4: "film4m_holes_transport",
+            8: "film8m_holes_transport"}.get(n_gpus, "film4m_holes_transport")
+
+
+START = ("analytic developed state (tdgl_b200.synthetic.vortex_state: vortex/antivortex pairs at"
+         " the holes, edge vortices, transport phase gradient), identical in both arms,"
+         " then --warmup untimed steps")
+
+
+def start_state(work):
+    """The state both arms start from (see START)."""
+    from tdgl_b200.synthetic import vortex_state
+
+    w = WORKLOADS[work["name"]]
+    fixed = (np.concatenate([np.asarray(t.site_indices) for t in work["terms"]])
+             if work["terms"] else None)
+    q = 0.75 * w["current"] / w["width"] if w["terminals"] else 0.0   # J = |psi|^2 q
+    return vortex_state(work["mesh"], w["holes"], fixed, q=q, b=w["b"])
+
+
+def run_config(work):
+    """The `config` object: the same keys and values in both arms."""
+    return {"workload": work["name"], "sites": len(work["mesh"].sites),
+            "edges": len(work["mesh"].edge_mesh.edges), "start": START}
 
 
 def build_workload(name: str, rank: int = 0, barrier=None):
@@ -168,29 +202,6 @@ def hbm_peak():
     except Exception:
         pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-
-
-def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel's fine-level launch from the
-    committed `ncu --set full` capture of this command on the 1M-site workload
-    (profiles/r1_full.md, written by tools/ncu_summary.py); None if not captured."""
-    path = os.path.join(ROOT, "profiles", "r1_full.md")
-    try:
-        best = None
-        with open(path) as f:
-            for line in f:
-                c = [x.strip() for x in line.split("|")]
-                if len(c) < 6 or c[1] != kernel:
-                    continue
-                grid = int(c[2].strip("()").split(",")[0])
-                mb = float(c[-3])
-                if best is None or grid > best[0]:
-                    best = (grid, mb)
-        if best is not None:
-            return best[1] * 1e6, "profiles/r1_full.md (ncu --set full, 1M-site workload)"
-    except (OSError, ValueError, IndexError):
-        pass
-    return None, None
 
 
 # ------------------------------------------------------------------ clocks
@@ -253,8 +264,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ CPU path (oracle port)
 def cpu_path(work, steps: int, warmup: int, budget_s: float):
-    """The reference's scipy.sparse/SuperLU step (oracle port) on the host cores.  Steps
-    are capped by a time budget; returns steps/s over the steps actually timed."""
+    """The reference's scipy.sparse/SuperLU step (oracle port) on the host cores, from the
+    same start state as the b200 arm: `warmup` untimed steps, then `steps` timed ones (cut
+    short only if `budget_s` of stepping is exceeded; the count actually timed is returned)."""
     from oracle import tdgl_oracle as orc
 
     o = work["opts"]
@@ -266,7 +278,7 @@ def cpu_path(work, steps: int, warmup: int, budget_s: float):
                               terminal_info=[orc.TerminalInfo(*t) for t in work["terms"]],
                               current_func=cf)
     factor_s = time.perf_counter() - t0
-    psi, mu = solver.psi_init.copy(), solver.mu_init.copy()
+    psi, mu = start_state(work)
     t, i = 0.0, 0
     for _ in range(warmup):
         dt, psi, mu, _, _ = solver.update(i, t, psi, mu)
@@ -282,7 +294,8 @@ def cpu_path(work, steps: int, warmup: int, budget_s: float):
         if time.perf_counter() - t0 > budget_s:
             break
     el = time.perf_counter() - t0
-    return dict(steps=done, seconds=el, steps_per_s=done / el, factor_seconds=factor_s)
+    return dict(steps=done, seconds=el, steps_per_s=done / el, factor_seconds=factor_s,
+                warmup=warmup)
 
 
 def threads_used() -> int:
@@ -292,36 +305,43 @@ def threads_used() -> int:
 
 
 # ------------------------------------------------------------------ main arms
+CPU_FEASIBLE = ("film1m_holes_transport", "film250k_field", "film20_cpu")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     # The SuperLU factorisation of the reference's path needs ~10 GB and 25-40 s per million
-    # sites (fill grows faster than linearly): the multi-GPU configurations are sampled by
-    # their 1-GPU sibling (~1M sites); site-steps/s is what carries over.
-    sampled = args.workload not in ("film1m_holes_transport", "film250k_field", "film20_cpu")
+    # sites (fill grows faster than linearly): a multi-GPU configuration is timed on a bounded
+    # SAMPLE of it, the ~1M-site member of the same geometry family (site-steps/s is the unit
+    # that carries over); `config` names the configuration, `cpu_baseline.sample` the sample.
+    sampled = args.workload not in CPU_FEASIBLE
     name = "film1m_holes_transport" if sampled else args.workload
     work = build_workload(name)
     n = len(work["mesh"].sites)
-    res = cpu_path(work, args.steps, min(args.warmup, 3), budget_s=args.cpu_budget)
+    res = cpu_path(work, args.steps, args.warmup, budget_s=args.cpu_budget)
     ncores = os.cpu_count()
-    sample = (f"{res['steps']} of the {args.steps} requested steps of the {n}-site workload {name}"
-              + (f" standing in for {args.workload}" if sampled else "")
-              + f" (time budget {args.cpu_budget:.0f} s; SuperLU factorisation"
-              f" {res['factor_seconds']:.1f} s and mesh build excluded)")
+    sample = (f"{res['steps']} timed steps (of {args.steps}) after {res['warmup']} warm-up steps of"
+              f" the {n}-site workload {name}"
+              + (f", the 1-GPU member of the geometry family of {args.workload}" if sampled else "")
+              + f" (SuperLU factorisation {res['factor_seconds']:.1f} s and mesh build excluded)")
     value = res["steps_per_s"] * n
+    # (`config` is the configuration's, identical to the b200 arm's: for a sampled run the big
+    # mesh is built only to name its size)
+    config = run_config(build_workload(args.workload) if sampled else work)
     line = {
         "impl": "reference", "metric": "tdgl_site_steps_per_sec", "value": value,
         "unit": "site-steps/s", "n_gpus": args.gpus, "steps": res["steps"],
-        "steps_requested": args.steps, "warmup": min(args.warmup, 3),
+        "warmup": res["warmup"],
         "ms_per_step": 1e3 / res["steps_per_s"], "higher_is_better": True,
         "scaling": "strong" if args.mode == "strong" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sampled_by": name if sampled else None,
-                   "sites": n, "edges": len(work["mesh"].edge_mesh.edges)},
+        "config": config,
         "steps_per_sec": res["steps_per_s"],
         "cpu_baseline": {"value": value, "unit": "site-steps/s",
                          "steps_per_sec": res["steps_per_s"], "cores": threads_used(),
-                         "host_cores": ncores, "kind": "port", "sample": sample},
+                         "host_cores": ncores, "kind": "port", "sample": sample,
+                         "sample_workload": name, "sample_sites": n},
         "e2e": {"value": value, "unit": "site-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -362,7 +382,8 @@ def run_b200(args, rank, world, local_rank):
         terminal_currents=work["currents"])
     setup_s = time.perf_counter() - t0
     eng = solver.engine
-    eng.set_state(solver.psi_init, solver.mu_init)
+    psi0, mu0 = start_state(work)
+    eng.set_state(psi0, mu0)
     solver.update_mu_boundary(0.0)
     info0 = eng.info()
 
@@ -415,6 +436,24 @@ def run_b200(args, rank, world, local_rank):
     h2d = 24 * n                     # psi (16 B) + mu (8 B) per site (per rank)
     d2h = 24 * n + 16 * n_edges      # psi', mu' + J_s, J_n per edge (per rank)
 
+    # ---- the same measurement deep in the run (vortices nucleating and moving) ---------------
+    # the headline numbers start from a state both arms can construct; this record shows that
+    # they are not flattered by it: `developed_steps` more steps on the device, then K timed
+    developed = None
+    if args.developed_steps > 0:
+        barrier()
+        pre = eng.advance(args.developed_steps, 1e300, state["step"], state["time"])
+        barrier()
+        dv = eng.advance(K, 1e300, pre.step, pre.time)
+        barrier()
+        dms = torch.tensor([dv.device_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        developed = {"pre_roll_steps": int(args.developed_steps + W + K + 2 + Ke),
+                     "time_reached": pre.time, "steps": K, "ms_per_step": float(dms.item()) / K,
+                     "steps_per_sec": jobs * K / (float(dms.item()) / 1e3),
+                     "mu_iterations_per_step": dv.mu_iterations / K, "retries": dv.retries}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -441,13 +480,11 @@ def run_b200(args, rank, world, local_rank):
                        "share_of_step": per_step * kms / (ms_total / K)}
     vc_ms = eng.time_kernel(3, 10, flush_l2=True) if levels > 1 else None
     dom = max(table, key=lambda k: table[k]["share_of_step"])
-    traffic, traffic_src = (ncu_traffic(dom.split(" fine level")[0])
-                            if world == 1 and args.workload == "film1m_holes_transport"
-                            else (None, None))
+    # traffic: DRAM bytes need a profiler pass (ncu --set full), which a timed run may not be
+    # under; the captures of this command are summarised in profiles/ (r2_full.md)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBps"], "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": table[dom]["frac"],
-                "traffic": traffic, "traffic_source": traffic_src, "kernels": table,
-                "vcycle_ms": vc_ms}
+                "traffic": None, "kernels": table, "vcycle_ms": vc_ms}
 
     line = {
         "metric": "tdgl_site_steps_per_sec", "value": steps_per_s * n, "unit": "site-steps/s",
@@ -455,8 +492,8 @@ def run_b200(args, rank, world, local_rank):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
         "higher_is_better": True, "scaling": "strong" if args.mode == "strong" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sites": n, "edges": n_edges,
-                   "nnz_rank0": nnz,
+        "config": run_config(work),
+        "detail": {"nnz_rank0": nnz,
                    "parallelism": ("single GPU" if world == 1 else
                                    f"domain decomposition over {world} GPUs (Z-order ranges,"
                                    " halo exchange + all-reduce kernels on NVLink peer memory)"
@@ -466,6 +503,7 @@ def run_b200(args, rank, world, local_rank):
                          " roofline timings flush L2 before every launch",
                    "mu_rtol": opts.mu_rtol, "amg_levels": levels},
         "mu_iterations_per_step": iters_per_step, "retries": b.retries,
+        "developed": developed,
         "setup_seconds": {"mesh": work["mesh_seconds"], "engine": setup_s},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_steps_per_s * n, "unit": "site-steps/s",
@@ -475,14 +513,14 @@ def run_b200(args, rank, world, local_rank):
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu:
-        res = cpu_path(work, args.cpu_steps, 1, budget_s=args.cpu_budget)
+        res = cpu_path(work, args.cpu_steps, W, budget_s=args.cpu_budget)
         line["cpu_baseline"] = {
             "value": res["steps_per_s"] * n, "unit": "site-steps/s",
             "steps_per_sec": res["steps_per_s"], "cores": threads_used(),
             "host_cores": os.cpu_count(), "kind": "port",
-            "sample": (f"{res['steps']} steps of the same {n}-site workload from the same initial"
-                       f" state (SuperLU factorisation {res['factor_seconds']:.1f} s and mesh"
-                       " build excluded)")}
+            "sample": (f"{res['steps']} timed steps after {res['warmup']} warm-up steps of the"
+                       f" same {n}-site workload from the same start state (SuperLU"
+                       f" factorisation {res['factor_seconds']:.1f} s and mesh build excluded)")}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -496,9 +534,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=10)
-    ap.add_argument("--cpu-budget", type=float, default=60.0,
+    ap.add_argument("--cpu-budget", type=float, default=240.0,
                     help="seconds of CPU stepping allowed for the cpu baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--developed-steps", type=int, default=2000,
+                    help="untimed device steps before the `developed` re-measurement (0: skip)")
     ap.add_argument("--mode", default="weak", choices=["weak", "strong", "replicas"],
                     help="N > 1: domain decomposition of BASELINE.json's config for N GPUs"
                          " (weak, default), of the 1-GPU workload (strong), or replicas")

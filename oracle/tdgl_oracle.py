@@ -203,6 +203,9 @@ class OracleSolver:
     # time-dependent vector potential: t -> [E, 2] (already A_scale-d); then ``A_applied``
     # must be its value at t = 0 (solver.py:164-185)
     A_func: Optional[Callable[[float], np.ndarray]] = None
+    # time-dependent disorder: t -> [N]; then ``epsilon`` must be its value at t = 0
+    # (solver.py:191-216, 364-381, 644-646)
+    epsilon_func: Optional[Callable[[float], np.ndarray]] = None
 
     def __post_init__(self):
         o = self.options
@@ -283,6 +286,8 @@ class OracleSolver:
             if not np.allclose(A, self.current_A_applied):
                 self.operators.set_link_exponents(A)
             self.current_A_applied = A
+        if self.epsilon_func is not None:                                # :644-646
+            self.epsilon = np.asarray(self.epsilon_func(time), float)
         old_sq = np.absolute(psi) ** 2                                   # :649
         dt = self.tentative_dt                                           # :668
         psi, new_sq, dt = self.adaptive_euler_step(step, psi, old_sq, mu, dt)
@@ -297,16 +302,18 @@ class OracleSolver:
 
 
 def run(solver: OracleSolver, *, end_time: float, max_steps: Optional[int] = None,
-        psi0=None, mu0=None):
+        psi0=None, mu0=None, dt0: Optional[float] = None):
     """The loop of ``Runner._run_stage`` (runner.py:379-433) without disk output: one more
     update is performed after ``time >= end_time`` is first reached, ``dt <- new_dt``,
-    ``time += dt``.  Returns final fields, the dt sequence and the probe traces."""
+    ``time += dt``.  Returns final fields, the dt sequence and the probe traces.  ``dt0``:
+    Runner's ``self.dt`` on entry (``dt_init`` for the first stage, the thermalisation
+    stage's last dt for the second, runner.py:262,431)."""
     psi = solver.psi_init.copy() if psi0 is None else np.array(psi0, complex)
     mu = solver.mu_init.copy() if mu0 is None else np.array(mu0, float)
     time = 0.0
     dts, mus, thetas = [], [], []
     i = 0
-    dt = solver.options.dt_init                                  # Runner's self.dt
+    dt = solver.options.dt_init if dt0 is None else dt0          # Runner's self.dt
     while True:
         dt, psi, mu, js, jn = solver.update(i, time, psi, mu, dt_prev=dt)
         dts.append(float(dt))
@@ -322,6 +329,22 @@ def run(solver: OracleSolver, *, end_time: float, max_steps: Optional[int] = Non
     if solver.probe_points is not None:
         out["running"] = dict(mu=np.array(mus).T, theta=np.array(thetas).T)
     return out
+
+
+def run_stages(solver: OracleSolver, psi0=None, mu0=None):
+    """``Runner.run`` (runner.py:288-328): an optional thermalisation stage up to
+    ``skip_time`` whose results are not saved, then — with step and time reset to 0, the
+    solver's ``tentative_dt`` / |psi|^2 history and Runner's ``self.dt`` carried over — the
+    stage up to ``solve_time``.  Returns the second stage's ``run`` output."""
+    o = solver.options
+    dt0 = None
+    if o.skip_time:
+        th = run(solver, end_time=o.skip_time, psi0=psi0, mu0=mu0)
+        # (the loop breaks before ``self.dt = new_dt``, runner.py:429-431: Runner's dt on
+        # entry of the second stage is the dt of the LAST BUT ONE thermalisation step)
+        psi0, mu0 = th["psi"], th["mu"]
+        dt0 = float(th["dt"][-2]) if len(th["dt"]) >= 2 else o.dt_init
+    return run(solver, end_time=o.solve_time, psi0=psi0, mu0=mu0, dt0=dt0)
 
 
 # ------------------------------------------------------------------ gauge-fixed comparison

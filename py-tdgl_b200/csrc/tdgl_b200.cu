@@ -1606,6 +1606,29 @@ int guarded(tdgl_handle* h, F&& f) {
     return TDGL_E_MU_SOLVER;
   }
 }
+
+// Device-side status of a stepping call (Ctl::status) -> return code + error text; shared by
+// tdgl_advance and tdgl_update so that the two seams cannot disagree.
+int step_status_to_rc(tdgl_handle* h, int status) {
+  switch (status) {
+    case 0: return TDGL_OK;
+    case 1:
+      h->error = "Solver failed to converge (|psi|^2 discriminant < 0 after max_solve_retries)";
+      return TDGL_E_STEP_FAILED;
+    case 2:
+      h->error = "mu solver did not reach tolerance within mu_max_iter iterations";
+      return TDGL_E_MU_SOLVER;
+    case 3:
+      h->error = "shard exchange timed out (a peer shard stopped or was never connected)";
+      return TDGL_E_CUDA;
+    case 4:
+      h->error = "screening iteration did not converge within max_iterations_per_step";
+      return TDGL_E_MU_SOLVER;
+    default:
+      h->error = "unknown device status " + std::to_string(status);
+      return TDGL_E_CUDA;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -1716,10 +1739,7 @@ int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, 
     status = r.status;
   });
   if (rc != TDGL_OK) return rc;
-  if (status == 1) { h->error = "Solver failed to converge (|psi|^2 discriminant < 0 after max_solve_retries)"; return TDGL_E_STEP_FAILED; }
-  if (status == 2) { h->error = "mu solver did not reach tolerance within mu_max_iter iterations"; return TDGL_E_MU_SOLVER; }
-  if (status == 3) { h->error = "shard exchange timed out (a peer shard stopped or was never connected)"; return TDGL_E_CUDA; }
-  return TDGL_OK;
+  return step_status_to_rc(h, status);
 }
 
 int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t step, double time,
@@ -1739,9 +1759,7 @@ int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t ste
     status = r.status;
   });
   if (rc != TDGL_OK) return rc;
-  if (status == 1) { h->error = "Solver failed to converge (|psi|^2 discriminant < 0 after max_solve_retries)"; return TDGL_E_STEP_FAILED; }
-  if (status == 2) { h->error = "mu solver did not reach tolerance within mu_max_iter iterations"; return TDGL_E_MU_SOLVER; }
-  return TDGL_OK;
+  return step_status_to_rc(h, status);
 }
 
 void* tdgl_host_alloc(int64_t bytes) {

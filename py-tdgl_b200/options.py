@@ -11,7 +11,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 from enum import Enum
-from typing import Union
+from typing import Optional, Union
 
 
 class SolverOptionsError(ValueError):
@@ -56,7 +56,8 @@ class SolverOptions:
     # ---- B200 engine knobs (no counterpart in the reference) ----------------------------
     mu_rtol: float = 1e-10        # relative residual of the on-device mu solve
     mu_max_iterations: int = 500
-    cuda_device: int = 0
+    cuda_device: Optional[int] = None   # None: device 0, or (distributed) the rank's
+    #                               current CUDA device (torch.cuda.current_device())
     use_cuda_graph: bool = True   # device-side step / retry / CG loops in one CUDA graph
     distributed: bool = False     # True: this process is one shard of a torchrun job (the
     #                               mesh is domain-decomposed over torch.distributed's ranks)

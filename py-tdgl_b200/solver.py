@@ -60,6 +60,36 @@ def validate_terminal_currents(terminal_currents, terminal_info, solver_options,
         check_total_current(terminal_currents)
 
 
+class _DeferredInterrupt:
+    """Ctrl-C while a stage runs sets a flag instead of raising inside a device call: the
+    stage loop looks at it between chunks, where the host bookkeeping and the device state
+    agree, and then does what ``Runner._run_stage`` does in its ``except KeyboardInterrupt``
+    (runner.py:434-451)."""
+
+    def __init__(self):
+        self.pending = False
+        self._old = None
+
+    def _handler(self, signum, frame):
+        self.pending = True
+
+    def __enter__(self):
+        import signal
+        import threading
+
+        if threading.current_thread() is threading.main_thread():
+            self._old = signal.signal(signal.SIGINT, self._handler)
+        return self
+
+    def __exit__(self, *exc):
+        import signal
+
+        if self._old is not None:
+            signal.signal(signal.SIGINT, self._old)
+            self._old = None
+        return False
+
+
 class _RunningState:
     """reference ``RunningState`` (runner.py:186-221)."""
 
@@ -184,21 +214,29 @@ class TDGLSolver:
                            terminal_currents: Union[Callable, Dict[str, float], None] = None,
                            probe_point_indices: Optional[Sequence[int]] = None,
                            u: float = 5.79, gamma: float = 10.0, device=None,
-                           A_ramp=None) -> "TDGLSolver":
+                           A_ramp=None, seed_solution=None) -> "TDGLSolver":
         """Inputs as the reference holds them after ``__init__``: ``A_applied`` [E, 2] in
         units of xi*Bc2 — or a callable ``t -> [E, 2]`` for a time-dependent vector
         potential (host callback every step, like the reference) — currents already
         multiplied by ``J_scale``.  ``A_ramp = (t_knots, f_knots)`` makes the potential
-        ``f(t) * A_applied`` with piecewise-linear f, evaluated on the device."""
+        ``f(t) * A_applied`` with piecewise-linear f, evaluated on the device.  ``epsilon``
+        [N], or a callable ``t -> [N]`` for a time-dependent disorder (the reference's
+        ``disorder_epsilon(r, *, t)``, solver.py:364-381)."""
         self = object.__new__(cls)
         self.device = device
         self.options = options
         options.validate()
         self.terminal_currents = terminal_currents
-        self.seed_solution = None
+        self.seed_solution = seed_solution
         self.applied_vector_potential = None
         self.disorder_epsilon = None
-        eps = np.asarray(epsilon, dtype=float)
+        dynamic_epsilon = callable(epsilon)
+        if dynamic_epsilon:
+            eval_eps = lambda t=None, _f=epsilon: np.asarray(  # noqa: E731
+                _f(0.0 if t is None else t), dtype=float)
+        else:
+            eps = np.asarray(epsilon, dtype=float)
+            eval_eps = lambda t=None: eps  # noqa: E731
         names = [t.name for t in terminal_info]
         if terminal_currents is None:
             terminal_currents = {n: 0.0 for n in names}
@@ -220,7 +258,7 @@ class TDGLSolver:
         elif callable(A_applied):
             eval_A = lambda t, _f=A_applied: np.asarray(_f(t), float)  # noqa: E731
             A_applied = eval_A(0.0)
-        self._setup(mesh, options, np.asarray(A_applied, float), lambda t=None: eps, False,
+        self._setup(mesh, options, np.asarray(A_applied, float), eval_eps, dynamic_epsilon,
                     tuple(terminal_info), func, static, probe_point_indices, u, gamma,
                     eval_A=eval_A, ramp=ramp)
         return self
@@ -265,11 +303,16 @@ class TDGLSolver:
         self.mu_init = np.zeros(n)
         self.mu_boundary = np.zeros(len(mesh.edge_mesh.boundary_edge_indices))
         engine_cls = DeviceEngine
+        cuda_device = options.cuda_device
         if options.distributed:
+            # None -> DistributedEngine takes torch.cuda.current_device() (LOCAL_RANK under
+            # torchrun); an explicit ordinal is honoured but two ranks may not share it
             from .sharded import DistributedEngine as engine_cls
+        elif cuda_device is None:
+            cuda_device = 0
         self.engine = engine_cls(
             mesh, fixed_sites=fixed, fix_psi=(terminal_psi is not None), gamma=gamma, u=u,
-            probe_sites=self.probe_points, device=options.cuda_device, mu_rtol=options.mu_rtol,
+            probe_sites=self.probe_points, device=cuda_device, mu_rtol=options.mu_rtol,
             mu_max_iter=options.mu_max_iterations,
             use_graph=1 if options.use_cuda_graph else 2,
             running_capacity=max(int(options.save_every), 1))
@@ -353,9 +396,10 @@ class TDGLSolver:
         if self.dynamic_vector_potential:
             results.append(self.current_A_applied)
         if self.dynamic_epsilon:
-            if not self.dynamic_vector_potential:
-                results.append(None)
             results.append(self.epsilon)
+        # positional contract of the seam (reference solver.py:708-714): A_applied only if the
+        # vector potential is dynamic, then epsilon only if it is dynamic — Runner unpacks
+        # `new_dt, *values` against exactly that many names (runner.py:424-428)
         return SolverResult(*results)
 
     # ------------------------------------------------------------------------------------
@@ -386,12 +430,26 @@ class TDGLSolver:
             values = first_values if (step == 0 and first_values is not None) else self._values()
             saved.save_time_step(state, values, None if step == 0 else running.values)
 
-        try:
+        with _DeferredInterrupt() as intr:
             while True:
                 if i % every == 0:
                     if save:
                         save_step(i)
                     running.clear()
+                if intr.pending:                       # runner.py:434-451
+                    intr.pending = False
+                    msg = f"{{}} simulation at step {i} of stage {name!r}."
+                    resume = False
+                    if opts.pause_on_interrupt:
+                        response = input(f"Simulation paused at stage {name!r} (step {i})."
+                                         " Continue simulation? [yN]")
+                        resume = response.lower().startswith("y")
+                    if resume:
+                        logger.info(msg.format("Resuming"))
+                    else:
+                        logger.warning(msg.format("Cancelling"))
+                        cancelled = True
+                        break
                 self.update_mu_boundary(time)
                 self._update_vector_potential(time, self._prev_dt)
                 if self.dynamic_epsilon:
@@ -428,9 +486,6 @@ class TDGLSolver:
                     logger.info(f"{name}: Time {time}/{end_time}, dt={info.dt:.2e}")
                 if info.finished:
                     break
-        except KeyboardInterrupt:
-            logger.warning(f"Cancelling simulation at step {i} of stage {name!r}.")
-            cancelled = True
         if save and (i % every):
             save_step(i)
         return not cancelled

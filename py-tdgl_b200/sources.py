@@ -92,10 +92,15 @@ class Ramp:
     __rmul__ = __mul__
 
 
-def ConstantField(value: float = 0) -> Field:
-    """Uniform out-of-plane field ``value`` (in the solver's ``field_units``), symmetric gauge
-    (reference ``ConstantField``, sources/constant.py:25-39)."""
-    return Field(lambda x, y, z, _b=float(value): constant_field_vector_potential(x, y, z, Bz=_b))
+def ConstantField(value: float = 0, field_units: str = "mT", length_units: str = "um") -> Field:
+    """Uniform out-of-plane field ``value``, symmetric gauge (reference ``ConstantField``,
+    sources/constant.py:25-39, same signature).  The returned vector potential is in
+    ``field_units * length_units`` like the reference's; its magnitude ``B x r / 2`` does not
+    depend on the unit names (positions go to metres and back, constant.py:18-22), so they
+    are kept only as attributes."""
+    f = Field(lambda x, y, z, _b=float(value): constant_field_vector_potential(x, y, z, Bz=_b))
+    f.field_units, f.length_units = str(field_units), str(length_units)
+    return f
 
 
 def LinearRamp(*, tmin: float, tmax: float, initial: float = 0.0, final: float = 1.0) -> Ramp:

@@ -71,3 +71,38 @@ def film_problem(width, height, h, b=0.0, holes=(), seed=0, disorder=False,
                  box_terminal(mesh, "drain", x1 - tol, x1 + tol, -big, big))
         terms = tuple(sorted(terms, key=lambda t: t.length))
     return mesh, A, eps, terms
+
+
+def vortex_state(mesh: Mesh, holes=(), fixed_sites=None, q: float = 0.0, b: float = 0.0,
+                 seed: int = 0):
+    """A deterministic analytic state with the features of the developed dynamics — vortex /
+    antivortex pairs leaving the holes, a few vortices that entered from the film edges, and
+    the phase gradient ``q`` of a transport current — for benchmarks that have to start both
+    the CUDA engine and the CPU reference from the SAME developed-looking state without
+    running thousands of warm-up steps on the CPU.  Returns (psi [N] complex, mu [N] = 0).
+
+    psi = prod_k (z - z_k)^{+-1 direction} / sqrt(|z - z_k|^2 + 2)  *  exp(i q x)
+    (each factor is the usual single-vortex ansatz with a core of ~xi)."""
+    z = mesh.sites[:, 0] + 1j * mesh.sites[:, 1]
+    x0, x1 = mesh.sites[:, 0].min(), mesh.sites[:, 0].max()
+    y0, y1 = mesh.sites[:, 1].min(), mesh.sites[:, 1].max()
+    rng = np.random.default_rng(seed)
+    centres, signs = [], []
+    for (hx, hy, hr) in holes:
+        centres += [complex(hx, hy + 1.5 * hr), complex(hx, hy - 1.5 * hr)]
+        signs += [+1, -1]
+    n_edge = 8 if (holes or b) else 0
+    for k in range(n_edge):
+        centres.append(complex(x0 + (x1 - x0) * rng.uniform(0.1, 0.9),
+                               (y1 - 4.0 * (1 + k % 3)) if k % 2 == 0 else (y0 + 4.0 * (1 + k % 3))))
+        signs.append(+1 if (k % 2 == 0 or b) else -1)
+    psi = np.ones(len(z), dtype=np.complex128)
+    for c, s in zip(centres, signs):
+        d = z - c
+        f = d / np.sqrt(np.abs(d) ** 2 + 2.0)
+        psi *= f if s > 0 else np.conj(f)
+    if q:
+        psi *= np.exp(1j * q * mesh.sites[:, 0])
+    if fixed_sites is not None and len(fixed_sites):
+        psi[np.asarray(fixed_sites, dtype=np.int64)] = 0.0
+    return psi, np.zeros(len(z))

@@ -51,6 +51,12 @@ def test_operators_match_reference(name):
         eng.set_mu_boundary(g["op_mu_boundary"])
         assert _rel(eng.mu_rhs(psi), g["op_rhs"]) < 1e-12
         assert _rel(eng.mu_laplacian(mu), g["op_lap_mu"]) < 1e-12
+        # per-edge currents (build_gradient, get_supercurrent: operators.py:87-117,385-394;
+        # J_n = -grad mu: solver.py:519) of a given state
+        eng.set_state(psi, mu)
+        js, jn = eng.get_currents()
+        assert _rel(js, g["op_supercurrent"]) < 1e-12
+        assert _rel(jn, g["op_normal_current"]) < 1e-12
         # mu solve: L mu = rhs for a compatible rhs; compare with the rhs it reproduces and
         # with the known solution up to the constant
         rhs = g["op_lap_mu"]

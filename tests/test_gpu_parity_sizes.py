@@ -1,0 +1,287 @@
+"""Parity of the CUDA path with the oracle at the sizes the numbers are quoted on
+(BASELINE.json configs[1] and configs[2], built by bench.py's own builder), single engine and
+4-shard domain decomposition, plus the edge cases the reference's own tests exercise on this
+path (tdgl/test/test_solve.py:15-125): terminal_psi in {0, 1, None}, a thermalisation stage
+(``skip_time``), callable terminal currents, a time-dependent epsilon, a seeded restart.
+
+The oracle (oracle/tdgl_oracle.py: SciPy SuperLU, the reference's expression order) is pinned
+against the unmodified reference in the build container (tests/test_oracle_vs_reference.py,
+including these edge cases) and runs live here on the box's host cores.
+
+Tolerances: gauge-fixed psi, |psi|, mu, J_s, J_n <= 1e-8 relative (BASELINE.json asks 1e-6),
+dt sequence <= 1e-10 relative, all on the smooth start-up window of the workloads.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import load_case
+from oracle import tdgl_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+TOL, TOL_DT = 1e-8, 1e-10
+
+
+def _oracle_run(work, steps):
+    o = work["opts"]
+    opts = orc.OracleOptions(solve_time=1e9, dt_init=o["dt_init"], dt_max=o["dt_max"],
+                             adaptive=o["adaptive"])
+    cf = (lambda t, _c=work["currents"]: _c) if work["currents"] else None
+    solver = orc.OracleSolver(work["mesh"], opts, work["A"], work["eps"],
+                              terminal_info=[orc.TerminalInfo(*t) for t in work["terms"]],
+                              current_func=cf)
+    return orc.run(solver, end_time=1e9, max_steps=steps)
+
+
+def _cuda_run(work, steps, engine_factory=None):
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    opts = SolverOptions(solve_time=1e9, save_every=steps, **work["opts"])
+    solver = TDGLSolver.from_dimensionless(
+        work["mesh"], opts, A_applied=work["A"], epsilon=work["eps"],
+        terminal_info=work["terms"], terminal_currents=work["currents"])
+    eng = solver.engine
+    if engine_factory is not None:          # same inputs, another engine (sharded)
+        eng.close()
+        eng = engine_factory(solver)
+        solver.engine = eng
+        eng.set_link_exponents(work["A"])
+        eng.set_epsilon(work["eps"])
+        eng.set_stepper(dt_init=opts.dt_init, dt_max=opts.dt_max, adaptive=opts.adaptive)
+        solver.terminal_current_densities = {n: 0 for n in solver.terminal_names}
+    eng.set_state(solver.psi_init, solver.mu_init)
+    solver.update_mu_boundary(0.0)
+    info = eng.advance(steps, 1e300, 0, 0.0)
+    assert info.steps_done == steps
+    psi, mu = eng.get_state()
+    js, jn = eng.get_currents()
+    dt = eng.get_running(steps)[0]
+    out = dict(psi=psi, mu=mu, supercurrent=js, normal_current=jn, dt=np.array(dt),
+               info=info, stats=eng.info())
+    eng.close()
+    return out
+
+
+def _assert_parity(tag, got, ref, areas):
+    d = orc.compare(got, ref, areas)
+    print(tag, d, "mu iterations/step", got["info"].mu_iterations / got["info"].steps_done)
+    for k in ("psi", "abs_psi", "mu", "supercurrent", "normal_current"):
+        assert d[k] < TOL, (tag, k, d)
+    np.testing.assert_allclose(got["dt"], ref["dt"], rtol=TOL_DT)
+
+
+@pytest.fixture(scope="module")
+def film250k():
+    import bench
+
+    work = bench.build_workload("film250k_field")
+    return work, _oracle_run(work, 60)
+
+
+@pytest.fixture(scope="module")
+def film1m():
+    import bench
+
+    work = bench.build_workload("film1m_holes_transport")
+    assert len(work["mesh"].sites) > 1_000_000
+    return work, _oracle_run(work, 50)
+
+
+def _sharded(world):
+    def factory(solver):
+        from tdgl_b200.sharded import LocalShardGroup
+
+        fixed = (np.concatenate([np.asarray(t.site_indices) for t in solver.terminal_info])
+                 if solver.terminal_info else None)
+        return LocalShardGroup(solver.mesh, world, fixed_sites=fixed, fix_psi=True,
+                               gamma=solver.gamma, u=solver.u, mu_rtol=solver.options.mu_rtol,
+                               running_capacity=4096)
+    return factory
+
+
+def test_film250k_field_matches_oracle(film250k):
+    """BASELINE.json configs[1]: 200x200 xi film (~251k sites), B = 0.1, adaptive dt."""
+    work, ref = film250k
+    got = _cuda_run(work, 60)
+    _assert_parity("film250k_field, 60 steps", got, ref, work["mesh"].areas)
+
+
+def test_film250k_field_4_shards_match_oracle(film250k):
+    work, ref = film250k
+    got = _cuda_run(work, 60, _sharded(4))
+    _assert_parity("film250k_field, 4 shards, 60 steps", got, ref, work["mesh"].areas)
+
+
+def test_film1m_holes_transport_matches_oracle(film1m):
+    """BASELINE.json configs[2], the configuration the headline metric is quoted on: 1.0M
+    sites, four holes, source / drain terminals, transport current, adaptive dt."""
+    work, ref = film1m
+    got = _cuda_run(work, 50)
+    _assert_parity("film1m_holes_transport, 50 steps", got, ref, work["mesh"].areas)
+    fixed = np.concatenate([np.asarray(t.site_indices) for t in work["terms"]])
+    assert np.abs(got["psi"][fixed]).max() == 0.0
+
+
+def test_film1m_holes_transport_4_shards_match_oracle(film1m):
+    """The 4-shard decomposition against the ORACLE (not against the single engine)."""
+    work, ref = film1m
+    got = _cuda_run(work, 50, _sharded(4))
+    _assert_parity("film1m_holes_transport, 4 shards, 50 steps", got, ref, work["mesh"].areas)
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases of the reference's tests, on the transport strip of the golden fixture
+
+def _edge_case(terminal_psi=0.0, skip_time=0.0, callable_current=False, eps_t=False,
+               solve_time=1.5, use_graph=True):
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    c = load_case("strip_transport")
+    I = c.currents["source"]
+
+    def cur(t):
+        f = 1.0 + 0.25 * min(t, 1.0)
+        return {"source": I * f, "drain": -I * f}
+
+    def eps_func(t):
+        return c.eps * (1.0 - 0.1 * min(t / 1.0, 1.0))
+
+    okw = dict(solve_time=solve_time, skip_time=skip_time, dt_init=c.opts["dt_init"],
+               dt_max=c.opts["dt_max"], terminal_psi=terminal_psi)
+    o = orc.OracleSolver(c.mesh, orc.OracleOptions(**okw), c.A, eps_func(0.0) if eps_t else c.eps,
+                         u=c.u, gamma=c.gamma,
+                         terminal_info=[orc.TerminalInfo(*t) for t in c.terminals],
+                         current_func=cur if callable_current else (lambda t: c.currents),
+                         epsilon_func=eps_func if eps_t else None, probe_points=c.probes)
+    ref = orc.run_stages(o)
+    opts = SolverOptions(save_every=40, use_cuda_graph=use_graph, **okw)
+    solver = TDGLSolver.from_dimensionless(
+        c.mesh, opts, A_applied=c.A, epsilon=eps_func if eps_t else c.eps,
+        terminal_info=c.terminals, terminal_currents=cur if callable_current else c.currents,
+        probe_point_indices=c.probes, u=c.u, gamma=c.gamma)
+    sol = solver.solve()
+    d = sol.tdgl_data
+    got = dict(psi=d.psi, mu=d.mu, supercurrent=d.supercurrent, normal_current=d.normal_current,
+               dt=sol.dynamics.dt)
+    return c, sol, got, ref
+
+
+def _check_edge(tag, c, got, ref):
+    assert len(got["dt"]) == ref["steps"], (tag, len(got["dt"]), ref["steps"])
+    d = orc.compare(got, ref, c.mesh.areas)
+    print(tag, d, "steps", ref["steps"])
+    for k in ("psi", "abs_psi", "mu", "supercurrent", "normal_current"):
+        assert d[k] < TOL, (tag, k, d)
+    np.testing.assert_allclose(got["dt"], ref["dt"], rtol=TOL_DT)
+
+
+@pytest.mark.parametrize("terminal_psi", [1.0, None])
+def test_terminal_psi_one_and_none(terminal_psi):
+    """ref test_solve.py:19: terminal_psi = 1 sets the initial value on the (identity-row)
+    terminal sites; None leaves the covariant Laplacian without fixed rows."""
+    c, sol, got, ref = _edge_case(terminal_psi=terminal_psi)
+    _check_edge(f"terminal_psi={terminal_psi}", c, got, ref)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_skip_time_thermalisation_stage(use_graph):
+    """ref runner.py:303-314: the thermalisation stage is not saved, the second stage restarts
+    step and time at 0 with the controller state carried over."""
+    c, sol, got, ref = _edge_case(skip_time=0.5, use_graph=use_graph)
+    _check_edge("skip_time=0.5", c, got, ref)
+    # nothing of the thermalisation stage is in the output: the first saved group is step 0
+    # of the second stage, at time 0
+    sol.solve_step = 0
+    assert sol.tdgl_data.state["step"] == 0 and sol.tdgl_data.state["time"] == 0.0
+    assert abs(sol.dynamics.time[-1] - ref["dt"].sum()) < 1e-9
+
+
+def test_callable_terminal_currents():
+    """ref test_solve.py:64-67: terminal_currents(t)."""
+    c, sol, got, ref = _edge_case(callable_current=True)
+    _check_edge("callable terminal currents", c, got, ref)
+
+
+def test_time_dependent_epsilon():
+    """ref test_solve.py:106-109: disorder_epsilon(r, *, t); epsilon is saved per step."""
+    c, sol, got, ref = _edge_case(eps_t=True)
+    _check_edge("time-dependent epsilon", c, got, ref)
+    t_last = float(sol.dynamics.time[-1] - sol.dynamics.dt[-1])
+    expect = c.eps * (1.0 - 0.1 * min(t_last, 1.0))
+    np.testing.assert_allclose(sol.tdgl_data.epsilon, expect, rtol=0, atol=1e-12)
+
+
+def test_everything_dynamic_with_thermalisation():
+    c, sol, got, ref = _edge_case(terminal_psi=1.0, skip_time=0.3, callable_current=True,
+                                  eps_t=True, solve_time=1.2)
+    _check_edge("terminal_psi=1 + skip_time + I(t) + eps(t)", c, got, ref)
+
+
+def test_seed_solution_restart():
+    """ref solver.py:740-752: a solve seeded with a previous Solution starts from its last
+    psi / mu (the controller starts afresh, like a new TDGLSolver in the reference)."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    c = load_case("strip_transport")
+    okw = dict(dt_init=c.opts["dt_init"], dt_max=c.opts["dt_max"])
+
+    def make(solve_time, seed=None):
+        return TDGLSolver.from_dimensionless(
+            c.mesh, SolverOptions(solve_time=solve_time, save_every=50, **okw), A_applied=c.A,
+            epsilon=c.eps, terminal_info=c.terminals, terminal_currents=c.currents, u=c.u,
+            gamma=c.gamma, seed_solution=seed)
+
+    first = make(0.8).solve()
+    second = make(0.7, seed=first).solve()
+
+    def oracle(solve_time):
+        return orc.OracleSolver(c.mesh, orc.OracleOptions(solve_time=solve_time, **okw), c.A,
+                                c.eps, u=c.u, gamma=c.gamma,
+                                terminal_info=[orc.TerminalInfo(*t) for t in c.terminals],
+                                current_func=lambda t: c.currents)
+
+    r1 = orc.run(oracle(0.8), end_time=0.8)
+    r2 = orc.run(oracle(0.7), end_time=0.7, psi0=r1["psi"], mu0=r1["mu"])
+    d = second.tdgl_data
+    got = dict(psi=d.psi, mu=d.mu, supercurrent=d.supercurrent, normal_current=d.normal_current,
+               dt=second.dynamics.dt)
+    _check_edge("seed_solution restart", c, got, r2)
+    # the first saved group of the seeded run is the seed itself
+    second.solve_step = 0
+    np.testing.assert_array_equal(second.tdgl_data.psi, first.tdgl_data.psi)
+    np.testing.assert_array_equal(second.tdgl_data.supercurrent, first.tdgl_data.supercurrent)
+
+
+def test_update_seam_positional_contract_with_dynamic_epsilon():
+    """Runner unpacks ``new_dt, *values`` against the parameter names (runner.py:424-428):
+    with only epsilon dynamic the seam returns 7 items, epsilon last (solver.py:708-714)."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    c = load_case("strip_transport")
+
+    def eps_func(t):
+        return c.eps * (1.0 - 0.1 * min(t, 1.0))
+
+    solver = TDGLSolver.from_dimensionless(
+        c.mesh, SolverOptions(solve_time=1.0, dt_init=1e-3, dt_max=1e-1), A_applied=c.A,
+        epsilon=eps_func, terminal_info=c.terminals, terminal_currents=c.currents, u=c.u,
+        gamma=c.gamma)
+    E = len(c.mesh.edge_mesh.edges)
+    names = ["psi", "mu", "supercurrent", "normal_current", "induced_vector_potential", "epsilon"]
+    values = [solver.psi_init, solver.mu_init, np.zeros(E), np.zeros(E), np.zeros((E, 2)),
+              eps_func(0.0)]
+    time, dt = 0.0, 1e-3
+    for i in range(5):
+        res = solver.update({"step": i, "time": time, "dt": dt}, None, dt, **dict(zip(names, values)))
+        new_dt, *values = res
+        assert len(values) == len(names)
+        np.testing.assert_array_equal(values[-1], eps_func(time))
+        dt = new_dt
+        time += dt

@@ -42,3 +42,47 @@ def test_oracle_reproduces_reference(terminals):
     assert o["steps"] == r["steps"]
     for k in ("psi", "mu", "supercurrent", "normal_current", "dt"):
         np.testing.assert_allclose(o[k], r[k], rtol=0, atol=1e-12)
+
+
+def _two_stage_reference(rs, skip_time, solve_time):
+    """Runner.run (runner.py:288-328) with the reference's own update(): thermalise, then the
+    saved stage from step 0 / time 0 with the solver's controller state carried over."""
+    th = rl.run_reference(rs, end_time=skip_time)
+    return rl.run_reference(rs, end_time=solve_time, psi0=th["psi"], mu0=th["mu"])
+
+
+@pytest.mark.parametrize("terminal_psi", [0.0, 1.0, None])
+def test_oracle_edge_cases_of_the_reference_tests(terminal_psi):
+    """What tdgl/test/test_solve.py::test_source_drain_current exercises on this path:
+    terminal_psi in {0, 1, None}, a callable terminal current, a time-dependent epsilon
+    (``disorder_epsilon(r, *, t)``, solver.py:364-381) and a thermalisation stage."""
+    ref = rl.load()
+    mesh, A, eps, terms = film_problem(16, 8, 0.5, b=0.2, disorder=True, terminals=True)
+
+    def cur(t):
+        return {"source": 1.0 + 0.5 * min(t, 1.0), "drain": -(1.0 + 0.5 * min(t, 1.0))}
+
+    def eps_t(t):
+        return eps * (1.0 - 0.2 * min(t / 2.0, 1.0))
+
+    okw = dict(solve_time=2.0, skip_time=0.5, dt_init=1e-4, dt_max=1e-1,
+               terminal_psi=terminal_psi)
+    rs = rl.make_reference_solver(
+        mesh, ref.SolverOptions(**okw), A_applied=A, epsilon=eps_t(0.0),
+        terminal_info=[ref.TerminalInfo(*t) for t in terms], current_func=cur)
+    rs.dynamic_epsilon = True
+    rs.update_epsilon = eps_t
+    # (run_reference threads `epsilon` through update() like Runner does when it is dynamic)
+    r = _two_stage_reference(rs, 0.5, 2.0)
+    os_ = orc.OracleSolver(mesh, orc.OracleOptions(**okw), A, eps_t(0.0),
+                           terminal_info=[orc.TerminalInfo(*t) for t in terms],
+                           current_func=cur, epsilon_func=eps_t)
+    o = orc.run_stages(os_)
+    assert o["steps"] == r["steps"]
+    for k in ("psi", "mu", "supercurrent", "normal_current", "dt"):
+        np.testing.assert_allclose(o[k], r[k], rtol=0, atol=1e-12)
+    fixed = np.concatenate([np.asarray(t.site_indices) for t in terms])
+    # (identity rows keep psi = 0 exactly; a terminal_psi of 1 only sets the initial value —
+    # the reference's fixed rows still evolve through the local terms of the update)
+    if terminal_psi == 0.0:
+        assert np.abs(o["psi"][fixed]).max() == 0.0

@@ -1,24 +1,3 @@
-# INTEGRATION — binding `libtdgl_b200.so` from inside pyTDGL
-
-pyTDGL has no plugin/FFI layer.  Its backend seam for the step is one Python call:
-`Runner._run_stage` -> `self.function(state, running_state, dt, **values)`
-(`tdgl/solver/runner.py:417-423`) with `function = TDGLSolver.update`
-(`tdgl/solver/solver.py:580-714`, wired at `solver.py:791-804`), and one operator container,
-`MeshOperators` (`tdgl/finite_volume/operators.py:233-394`, built at `solver.py:270-279`).
-The reference already has an opt-in accelerator switch, `SolverOptions.gpu`
-(`options.py:76`, consumed at `solver.py:132-138`); the stub below hangs the B200 engine on
-the same kind of switch.  It is what a pyTDGL maintainer would add; nothing of it is
-needed to use this repository's own `tdgl_b200.solve()` (which mirrors `tdgl.solve`).
-
-## ctypes stub (reference side)
-
-The block below is `tools/reference_binding_b200.py` verbatim (a test keeps the two in sync);
-`tests/test_integration_stub.py` executes it: in the build container against the UNMODIFIED
-reference's `TDGLSolver` (binding, argument marshalling and the error path — there is no GPU
-there), on the GPU box against a solver object with the reference's attribute names, stepping
-through `B200Step.update` and comparing with the oracle.
-
-```python
 # tdgl/solver/b200.py  (new file in the reference; kept here as tools/reference_binding_b200.py
 # and executed by tests/test_integration_stub.py)
 """ctypes binding of libtdgl_b200.so at pyTDGL's step seam.
@@ -145,63 +124,3 @@ class B200Step:
         if s.dynamic_epsilon:
             results.append(epsilon)
         return self._result(*results)
-```
-
-and in `TDGLSolver.solve` (`solver.py:791`): `function=B200Step(self).update if
-options.b200 else self.update`.
-
-That binding is a literal drop-in at the reference's step seam (what `bench.py` times as
-`e2e`): 24 B/site go to the device and 24 B/site + 16 B/edge come back every step.  The fast
-path is `tdgl_advance(h, max_steps = steps until the next save, t_end, step, time, &info)`:
-the loop of `Runner._run_stage` (`runner.py:379-433`), the dt retries (`solver.py:475-485`)
-and the adaptive controller (`solver.py:698-707`) run on the device and the host only
-fetches `tdgl_get_state / tdgl_get_currents / tdgl_get_running` at save steps — that is how
-`py-tdgl_b200/solver.py::TDGLSolver._run_stage` drives it.
-
-## Entry points and the reference interface each one replaces
-
-| C entry point (`include/tdgl_b200.h`) | replaces (reference file:line) |
-|---|---|
-| `tdgl_create` | `MeshOperators.__init__` + `build_operators` incl. the SuperLU factorisation (`operators.py:245-308`) |
-| `tdgl_set_link_exponents` | `MeshOperators.set_link_exponents` (`operators.py:310-383`) |
-| `tdgl_set_epsilon` | `TDGLSolver.update_epsilon` / `epsilon` attribute (`solver.py:191-216,364-381`) |
-| `tdgl_set_mu_boundary` | the array written by `update_mu_boundary` (`solver.py:325-345`) |
-| `tdgl_set_dA_dt` | `dA_dt` of a time-dependent vector potential (`solver.py:626-634`), used in the rhs (`:508`) and J_n (`:519`) |
-| `tdgl_set_vector_potential_ramp` | `update_applied_vector_potential` (`solver.py:347-362`) for separable `scalar(t) * field(r)` Parameters (`sources/scaling.py:17-40`, `parameter.py:355-373`), evaluated on the device |
-| `tdgl_stage_outputs`, `tdgl_fetch_outputs` | sharded outputs summed on the devices before one D2H (no reference counterpart) |
-| `tdgl_set_state`, `tdgl_get_state` | the `psi`, `mu` values `Runner` threads through `update` (`runner.py:417-423`) |
-| `tdgl_set_stepper` | `SolverOptions` fields read by the step + `tentative_dt`/history init (`options.py:66-89`, `solver.py:316-320`) |
-| `tdgl_update` | `TDGLSolver.update` (`solver.py:580-714`) |
-| `tdgl_advance` | `Runner._run_stage` loop body x `max_steps` (`runner.py:379-433`) |
-| `tdgl_get_currents` | `get_supercurrent` (`operators.py:385-394`) and `normal_current` (`solver.py:519`) |
-| `tdgl_get_running` | `RunningState` buffers (`runner.py:186-221`, `solver.py:690-694`) |
-| `tdgl_op_*` | single operators for parity tests: `psi_laplacian @ psi` (`solver.py:426`), `solve_for_psi_squared` (`solver.py:383-439`), rhs (`solver.py:507-510`), `mu_laplacian @ mu`, `mu_laplacian_lu(rhs)` (`solver.py:513-516`) |
-| `tdgl_host_alloc/free` | page-locked host arrays for the per-step copies of `tdgl_update` |
-| `tdgl_time_kernel`, `tdgl_get_info` | measurement only (no reference counterpart) |
-| `tdgl_config.world/rank`, `tdgl_comm_export`, `tdgl_comm_connect_ipc`, `tdgl_comm_connect_local`, `tdgl_shard_info` | domain decomposition over 2-8 GPUs (no reference counterpart; the reference is single-device) |
-| `tdgl_host_amg_probe`, `tdgl_host_shard_probe`, `tdgl_host_shard_lists` | host-only validation of the AMG hierarchy and of the shard plan (CPU tests) |
-
-Error behaviour kept: `RuntimeError` text of a failed step (`solver.py:479-483`),
-`ValueError` for epsilon > 1 / bad A shape / unknown or non-conserving terminal currents
-(`solver.py:35-60,186-216`), `SolverOptionsError` messages of `validate()`
-(`options.py:91-166`).
-
-## Several GPUs
-
-The reference has no multi-device path.  Here every rank creates a handle on the SAME
-whole-mesh arrays with `tdgl_config.world = P`, `tdgl_config.rank = r` and wires the shards
-once (`py-tdgl_b200/sharded.py::DistributedEngine` does exactly this under `torchrun`):
-
-```python
-cfg.world, cfg.rank = dist.get_world_size(), dist.get_rank()
-_lib.tdgl_create(byref(h), ..., byref(cfg))
-buf = create_string_buffer(64); _lib.tdgl_comm_export(h, buf)            # CUDA IPC handle
-handles = [None] * cfg.world; dist.all_gather_object(handles, buf.raw)   # plumbing only
-_lib.tdgl_comm_connect_ipc(h, b"".join(handles), cfg.world)
-# from here on: the same tdgl_set_* / tdgl_advance / tdgl_get_* calls on every rank, with the
-# same arguments; outputs hold this shard's sites / edges and zeros elsewhere (sum them)
-```
-
-`SolverOptions(distributed=True)` selects this engine inside `TDGLSolver`; nothing else of the
-solve API changes.  The exchange steps are device code on NVLink peer memory
-(`csrc/comm.cuh`), NCCL is not on the data path.
