@@ -466,12 +466,16 @@ def run_b200(args, rank, world, local_rank):
     levels = info0["amg_levels"]
     kern = {
         "kw_psi_step": (0, 20 * nnz + 52 * nl, 1.0),
-        "kw_mu_rhs": (1, 28 * nnz + 76 * nl, 1.0),   # (+ mu_prev read, d written)
-        "kw_real<spmv_dot> fine level": (2, 12 * nnz + 20 * nl, iters_per_step),
+        # (complex + real matrix, psi, areas, bterm, mu / mu_prev / mu_pp, b, r, d1, d2)
+        "kw_mu_rhs": (1, 28 * nnz + 92 * nl, 1.0),
+        # w = A z with r.z and z.w: matrix, row pointers, z, r read, w written
+        "kw_real<spmv_cg> fine level": (2, 12 * nnz + 28 * nl, iters_per_step),
+        # p, s, x, r updated from z, w: 6 reads + 4 writes per row
+        "k_cg_fused": (9, 80 * nl, iters_per_step),
     }
     if levels > 1:
         kern["kw_real<presmooth> fine level"] = (5, 12 * nnz + 36 * nl, iters_per_step)
-        kern["kw_real<jacobi> fine level"] = (6, 12 * nnz + 44 * nl, iters_per_step)
+        kern["kw_real<jacobi> fine level"] = (6, 12 * nnz + 36 * nl, iters_per_step)
     table = {}
     for name, (which, nbytes, per_step) in kern.items():
         kms = eng.time_kernel(which, 20, flush_l2=True)

@@ -9,6 +9,8 @@
 // is amortised over 10^3..10^6 steps.
 #pragma once
 
+#include <thread>
+
 #include "host_csr.h"
 
 namespace tdgl {
@@ -86,34 +88,57 @@ inline int64_t aggregate(const HostCsr<double>& A, const std::vector<double>& d,
   return nagg;
 }
 
-// In-place Cholesky inverse of a dense SPD matrix (row-major n x n).
+// In-place Cholesky inverse of a dense SPD matrix (row-major n x n).  The coarsest level may
+// hold a couple of thousand rows (fewer, larger levels = fewer kernel launches per V-cycle), so
+// the O(n^3) work is arranged in contiguous dot products and the n right-hand sides of the
+// inverse are split over the host cores.
 inline void dense_spd_inverse(std::vector<double>& M, int64_t n) {
-  std::vector<double> L(M);
+  std::vector<double> L(M);   // lower triangle, row-major: row i = L[i*n .. i*n+i]
   for (int64_t j = 0; j < n; ++j) {
-    double s = L[j * n + j];
-    for (int64_t k = 0; k < j; ++k) s -= L[j * n + k] * L[j * n + k];
+    const double* lj = &L[j * n];
+    double s = lj[j];
+    for (int64_t k = 0; k < j; ++k) s -= lj[k] * lj[k];
     if (!(s > 0)) throw std::runtime_error("coarse matrix not positive definite");
     const double ljj = std::sqrt(s);
     L[j * n + j] = ljj;
+    const double inv = 1.0 / ljj;
     for (int64_t i = j + 1; i < n; ++i) {
-      double t = L[i * n + j];
-      for (int64_t k = 0; k < j; ++k) t -= L[i * n + k] * L[j * n + k];
-      L[i * n + j] = t / ljj;
+      const double* li = &L[i * n];
+      double t = li[j];
+      for (int64_t k = 0; k < j; ++k) t -= li[k] * lj[k];
+      L[i * n + j] = t * inv;
     }
   }
-  // solve L L^T X = I column by column
-  std::vector<double> y(n);
-  for (int64_t c = 0; c < n; ++c) {
-    for (int64_t i = 0; i < n; ++i) {
-      double t = (i == c) ? 1.0 : 0.0;
-      for (int64_t k = 0; k < i; ++k) t -= L[i * n + k] * y[k];
-      y[i] = t / L[i * n + i];
+  std::vector<double> Lt(n * n, 0.0);   // L^T, so that the back substitution reads rows too
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t k = 0; k <= i; ++k) Lt[k * n + i] = L[i * n + k];
+  // column c of the inverse: L y = e_c (y_i = 0 for i < c), L^T x = y
+  auto columns = [&](int64_t c0, int64_t c1) {
+    std::vector<double> y(n), x(n);
+    for (int64_t c = c0; c < c1; ++c) {
+      for (int64_t i = 0; i < c; ++i) y[i] = 0.0;
+      for (int64_t i = c; i < n; ++i) {
+        const double* li = &L[i * n];
+        double t = (i == c) ? 1.0 : 0.0;
+        for (int64_t k = c; k < i; ++k) t -= li[k] * y[k];
+        y[i] = t / li[i];
+      }
+      for (int64_t i = n - 1; i >= 0; --i) {
+        const double* ri = &Lt[i * n];
+        double t = y[i];
+        for (int64_t k = i + 1; k < n; ++k) t -= ri[k] * x[k];
+        x[i] = t / ri[i];
+      }
+      for (int64_t i = 0; i < n; ++i) M[i * n + c] = x[i];
     }
-    for (int64_t i = n - 1; i >= 0; --i) {
-      double t = y[i];
-      for (int64_t k = i + 1; k < n; ++k) t -= L[k * n + i] * M[k * n + c];
-      M[i * n + c] = t / L[i * n + i];
-    }
+  };
+  const int64_t nt = n < 256 ? 1 : std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+  if (nt <= 1) {
+    columns(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    for (int64_t t = 0; t < nt; ++t) pool.emplace_back(columns, n * t / nt, n * (t + 1) / nt);
+    for (auto& th : pool) th.join();
   }
   // symmetrise against roundoff
   for (int64_t i = 0; i < n; ++i)

@@ -154,7 +154,7 @@ __device__ __forceinline__ void comm_allreduce(Ctl* ctl, Comm* c, double* v, int
 // Tags are derived from counters of the control block that are identical on all ranks and
 // constant while the kernels that use them run, so nothing has to be signalled:
 //   kTagIter      (solve_epoch, cg_it)      vectors of the V-cycle / CG of iteration cg_it
-//   kTagIterNext  (solve_epoch, cg_it + 1)  the residual k_cg_update leaves for the next one
+//   kTagIterNext  (solve_epoch, cg_it + 1)  the residual k_cg_fused leaves for the next one
 //   kTagIter0     (solve_epoch, 0)          the residual the rhs kernel leaves for iteration 0
 //   kTagPsiNew    psi_epoch + 1             psi written by the current attempt of the psi step
 //   kTagPsiCur    psi_tag[cur]              the accepted psi

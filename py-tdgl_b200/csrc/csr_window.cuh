@@ -177,7 +177,8 @@ __device__ __forceinline__ double2 row_dot_c(const double2* __restrict__ sv,
 
 // ---- real operators (mu system, AMG levels) ----------------------------------------------------
 
-enum : int { kOpSpmvDot = 0, kOpResidual, kOpPresmooth, kOpJacobi, kOpPlain, kOpPlainAdd };
+enum : int { kOpSpmvDot = 0, kOpResidual, kOpPresmooth, kOpJacobi, kOpPlain, kOpPlainAdd,
+             kOpSpmvCg };
 
 struct RealArgs {
   const double* val = nullptr;
@@ -189,6 +190,7 @@ struct RealArgs {
   double* r = nullptr;           // kOpPresmooth: residual output
   double omega = 0.0;
   double* red_out = nullptr;     // reduction result (deterministic), may be null
+  double* red2_out = nullptr;    // kOpSpmvCg: the second sum
   // sharded engine: where the halo columns of the gathered vector (x; b for kOpPresmooth)
   // are found, and where the boundary rows of the output (r for kOpPresmooth, y otherwise)
   // go.  Defaults: no halo, nothing to send.
@@ -203,6 +205,8 @@ struct PsiComm {
 };
 
 //  kOpSpmvDot   y = A x ;                         red = dot(x, y)
+//  kOpSpmvCg    y = A x ;                         red = dot(b, x), red2 = dot(x, y)
+//               (the CG iteration's SpMV: x = z, b = r -> gamma = r.z and delta = z.Az)
 //  kOpResidual  y = b - A x ;                     red = ||y||^2
 //  kOpPresmooth y = omega D^-1 b ; r = b - A y    (smoothing from a zero guess + residual)
 //  kOpJacobi    y = x + omega D^-1 (b - A x) ;    red = dot(w, y)
@@ -237,15 +241,16 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   // row-local operands travel while the window lands
   double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
   if (lead) {
-    if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi) bi = a.b[w.row];
+    if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi || OP == kOpSpmvCg)
+      bi = a.b[w.row];
     if (OP == kOpPresmooth || OP == kOpJacobi) di = a.dinv[w.row];
-    if (OP == kOpSpmvDot || OP == kOpJacobi) xi = a.x[w.row];
+    if (OP == kOpSpmvDot || OP == kOpJacobi || OP == kOpSpmvCg) xi = a.x[w.row];
     if (OP == kOpPlainAdd) xi = a.y[w.row];
     if (OP == kOpJacobi && a.w != nullptr) wi = a.w[w.row];
   }
   mbar_wait(&bar, 0);
   if (!live) return;
-  double d = 0.0;
+  double d = 0.0, d2 = 0.0;
   double s = 0.0;
   if (in) {
     const int top = SH ? hv.n_owned - 1 : 0x7fffffff;
@@ -290,6 +295,10 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
     if (OP == kOpSpmvDot) {
       a.y[w.row] = out = s;
       d = s * xi;
+    } else if (OP == kOpSpmvCg) {
+      a.y[w.row] = out = s;
+      d = bi * xi;
+      d2 = s * xi;
     } else if (OP == kOpResidual) {
       const double ri = bi - s;
       a.y[w.row] = out = ri;
@@ -308,6 +317,21 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
     }
     if (SH && tag_out != 0u) push_row(comm, a.push, tag_out, w.row, out);
     (void)out;
+  }
+  if (OP == kOpSpmvCg) {
+    const double b0 = block_sum(d, red);
+    const double b1 = block_sum(d2, red);
+    double t0, t1;
+    if (grid_sum2_last(b0, b1, partials, counter, red, &t0, &t1) && threadIdx.x < 32) {
+      double v[2];
+      v[0] = __shfl_sync(0xffffffffu, t0, 0);
+      v[1] = __shfl_sync(0xffffffffu, t1, 0);
+      if (SH && comm != nullptr) comm_allreduce(ctl, comm, v, 2, false);
+      if (threadIdx.x == 0) {
+        *a.red_out = v[0];
+        *a.red2_out = v[1];
+      }
+    }
   }
   if ((OP == kOpSpmvDot || OP == kOpResidual || OP == kOpJacobi) && a.red_out != nullptr) {
     const double bs = block_sum(d, red);
@@ -410,7 +434,8 @@ __global__ void __launch_bounds__(kWinRows)
 kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_halo, WinCsr m,
           const double2* __restrict__ lval, const double* __restrict__ aval,
           const double2* psi_buf0, const double2* psi_buf1, const double* __restrict__ mu,
-          const double* __restrict__ mu_prev, double* __restrict__ d_out,
+          const double* __restrict__ mu_prev, const double* __restrict__ mu_pp /* plain halo */,
+          double* __restrict__ d_out, double* __restrict__ d2_out,
           const double* __restrict__ areas, const double* __restrict__ bterm,
           const double* __restrict__ ramp_div /* null: no device-side ramp */,
           double* __restrict__ b, double* __restrict__ r,
@@ -448,36 +473,43 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_h
   }
   mbar_wait(&bar, 0);
   if (!live) return;
-  // Initial guess of the solve: mu_g = mu + c (mu - mu_prev) (mu, mu_prev: the last two
-  // solutions).  Its residual is r + c d with r = b - A mu, d = A mu_prev - A mu, so the c
-  // that minimises it follows from three dot products (k_cg_begin) — never worse than the
-  // plain warm start (c = 0), and 2-4 CG iterations cheaper while the dynamics are smooth.
-  double dbb = 0.0, drr = 0.0, drd = 0.0, ddd = 0.0;
+  // Initial guess of the solve: mu_g = mu + c1 (mu - mu_prev) + c2 (mu - mu_pp) (mu, mu_prev,
+  // mu_pp: the last three solutions).  Its residual is r + c1 d1 + c2 d2 with r = b - A mu,
+  // d1 = A mu_prev - A mu, d2 = A mu_pp - A mu, so the c1, c2 that minimise it follow from
+  // seven dot products (k_cg_begin) — never worse than the plain warm start (c = 0), and
+  // several CG iterations cheaper while the dynamics are smooth.
+  double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (in) {
     const double2 lap = row_dot_c<SH>(sl, si, w.kb, w.ke, psi, ctl, hpsi);
     const double am = row_dot<SH>(sa, si, w.kb, w.ke, mu, ctl, hmu);
     const double amp = row_dot<SH>(sa, si, w.kb, w.ke, mu_prev, ctl, hmp);
+    HaloView plain;
+    plain.n_owned = 0x7fffffff; plain.box = nullptr; plain.tag = 0u;
+    const double ampp = row_dot<false>(sa, si, w.kb, w.ke, mu_pp, ctl, plain);
     const double rhs = (p.x * lap.y - p.y * lap.x) - bt;
     if (rhs_raw != nullptr) rhs_raw[w.row] = rhs;
     const double bi = -ai * rhs;
     const double ri = bi - am;
-    const double di = amp - am;
+    const double d1 = amp - am, d2 = ampp - am;
     b[w.row] = bi;
     r[w.row] = ri;
-    d_out[w.row] = di;
-    dbb = bi * bi;
-    drr = ri * ri;
-    drd = ri * di;
-    ddd = di * di;
+    d_out[w.row] = d1;
+    d2_out[w.row] = d2;
+    acc[0] = bi * bi;
+    acc[1] = ri * ri;
+    acc[2] = ri * d1;
+    acc[3] = d1 * d1;
+    acc[4] = ri * d2;
+    acc[5] = d1 * d2;
+    acc[6] = d2 * d2;
   }
-  // four sums through one deterministic reduction
-  double v[4];
-  v[0] = block_sum(dbb, red);
-  v[1] = block_sum(drr, red);
-  v[2] = block_sum(drd, red);
-  v[3] = block_sum(ddd, red);
+  // seven sums through one deterministic reduction
+  double v[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[k] = block_sum(acc[k], red);
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 4; ++k) partials[4 * blockIdx.x + k] = v[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) partials[8 * blockIdx.x + k] = v[k];
     __threadfence();
     const unsigned int t = atomicAdd(counter, 1u);
     s_last = (t == gridDim.x - 1);
@@ -485,17 +517,25 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_h
   __syncthreads();
   if (s_last) {
     __threadfence();
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
-      for (int k = 0; k < 4; ++k) a[k] += reinterpret_cast<volatile double*>(partials)[4 * i + k];
-    for (int k = 0; k < 4; ++k) a[k] = block_sum(a[k], red);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) a[k] += reinterpret_cast<volatile double*>(partials)[8 * i + k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a[k] = block_sum(a[k], red);
     if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0
-      if (SH && comm != nullptr) comm_allreduce(ctl, comm, a, 4, false);
+      if (SH && comm != nullptr) {
+        comm_allreduce(ctl, comm, a, 4, false);
+        comm_allreduce(ctl, comm, a + 4, 4, false);
+      }
       if (threadIdx.x == 0) {
         ctl->bb = a[0];
         ctl->rr = a[1];
         ctl->rd = a[2];
         ctl->dd = a[3];
+        ctl->rd2 = a[4];
+        ctl->d1d2 = a[5];
+        ctl->d2d2 = a[6];
         *counter = 0u;
       }
     }

@@ -265,8 +265,10 @@ class Engine {
   int fuse_from_ = -1;         // first level the cluster kernel handles (-1: none)
   int nc_ = 0;
   int64_t amg_nnz_ = 0;
-  DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_;
-  DevBuf<double> mu_prev_;   // the solution before the last one (extrapolated initial guess)
+  DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_, cg_s_;   // cg_Ap_: w = A z; cg_s_: A p
+  DevBuf<double> mu_prev_, mu_pp_;   // the two solutions before the last one (extrapolated
+                                     // initial guess of the next solve)
+  int guess_terms_ = 2;              // 0: warm start, 1: one-term, 2: two-term extrapolation
   DevBuf<double> partials_;
   DevBuf<unsigned int> counter_;
   // ---- scratch for IO ------------------------------------------------------------------------

@@ -45,8 +45,11 @@ struct Ctl {
   double dpsi_hist[kMaxWindow];
   long long n_hist;
   // --- CG ---------------------------------------------------------------------------------
-  double rz_new, rz_prev, pAp, rr, bb;
-  double rd, dd, guess_c;   // initial guess mu + c (mu - mu_prev): r.d, d.d, the optimal c
+  double rz_new, rz_prev, pAp, rr, bb;   // gamma = r.z (this / previous iteration), delta = z.Az
+  double alpha_prev;                     // step length of the previous iteration
+  // initial guess mu + c1 (mu - mu_prev) + c2 (mu - mu_pp) from the last three solutions:
+  // r.d1, d1.d1, r.d2, d1.d2, d2.d2 (d_k = A mu_history_k - A mu) and the optimal c1, c2
+  double rd, dd, rd2, d1d2, d2d2, guess_c, guess_c2;
   int cg_it, cg_go;
   long long total_cg_it;
   int step_go;
@@ -141,6 +144,36 @@ __device__ __forceinline__ bool grid_sum_last(double partial, double* partials,
   return true;
 }
 
+// Two sums through one pass (partials interleaved, 2 per block); same contract.
+__device__ __forceinline__ bool grid_sum2_last(double p0, double p1, double* partials,
+                                               unsigned int* counter, double* smem,
+                                               double* t0, double* t1) {
+  __shared__ int s_last2;
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = p0;
+    partials[2 * blockIdx.x + 1] = p1;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last2 = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last2) return false;
+  __threadfence();
+  double a0 = 0.0, a1 = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
+    a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
+  }
+  a0 = block_sum(a0, smem);
+  a1 = block_sum(a1, smem);
+  if (threadIdx.x == 0) {
+    *t0 = a0;
+    *t1 = a1;
+    *counter = 0u;
+  }
+  return true;
+}
+
 #define TDGL_COND_ARG cudaGraphConditionalHandle
 
 __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
@@ -170,39 +203,38 @@ k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const double* __re
 // ------------------------------------------------------------------------------------------
 // CG vector kernels
 
-// p = z + beta p   (beta = rz_new / rz_prev, 0 on the first iteration)
+// One iteration of the single-reduction form of preconditioned CG (Chronopoulos & Gear): with
+// z = M r, w = A z, gamma = r.z and delta = z.w from the SpMV kernel (ONE reduction),
+//   beta = gamma / gamma_prev ;  alpha = gamma / (delta - beta gamma / alpha_prev)
+//   p = z + beta p ;  s = w + beta s  (= A p) ;  x += alpha p ;  r -= alpha s ;  rr = ||r||^2
+// in one pass over the vectors.  The same iterates as textbook PCG (p = z + beta p, alpha =
+// r.z / p.Ap) in exact arithmetic, with one launch and one grid reduction less per iteration.
+// Last block: bookkeeping + loop condition of the CG loop.
 __global__ void __launch_bounds__(kBlock)
-k_cg_direction(const Ctl* __restrict__ ctl, const Comm* comm, PushArgs push, int n,
-               const double* __restrict__ z, double* __restrict__ p) {
-  griddep_enter();
-  if (ctl->status != 0) return;
-  const double beta = (ctl->cg_it == 0) ? 0.0 : ctl->rz_new / ctl->rz_prev;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const double pi = z[i] + beta * p[i];
-    p[i] = pi;
-    if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, pi);
-  }
-}
-
-// alpha = rz_new / pAp ; x += alpha p ; r -= alpha Ap ; rr = ||r||^2 ;
-// last block: bookkeeping + loop condition of the CG loop.
-__global__ void __launch_bounds__(kBlock)
-k_cg_update(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict__ p,
-            const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
-            double* partials, unsigned int* counter, cudaGraphConditionalHandle cond) {
+k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict__ z,
+           const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
+           double* __restrict__ x, double* __restrict__ r, double* partials,
+           unsigned int* counter, cudaGraphConditionalHandle cond) {
   griddep_enter();
   __shared__ double red[32];
   if (ctl->status != 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) set_cond(cond, 0);
     return;
   }
-  const double alpha = ctl->rz_new / ctl->pAp;
+  const double gamma = ctl->rz_new, delta = ctl->pAp;
+  const bool first = ctl->cg_it == 0;
+  const double beta = first ? 0.0 : gamma / ctl->rz_prev;
+  const double denom = first ? delta : delta - beta * gamma / ctl->alpha_prev;
+  const double alpha = gamma / denom;
   const unsigned int tag = comm != nullptr ? comm_tag(ctl, push.tag_mode) : 0u;
   double d = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    x[i] += alpha * p[i];
-    const double ri = r[i] - alpha * Ap[i];
+    const double pi = first ? z[i] : z[i] + beta * p[i];
+    const double si = first ? w[i] : w[i] + beta * s[i];
+    p[i] = pi;
+    s[i] = si;
+    x[i] += alpha * pi;
+    const double ri = r[i] - alpha * si;
     r[i] = ri;
     if (comm != nullptr) push_row(comm, push, tag, i, ri);  // next iteration's V-cycle input
     d += ri * ri;
@@ -214,7 +246,8 @@ k_cg_update(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict
     if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
     if (threadIdx.x == 0) {
       ctl->rr = total;
-      ctl->rz_prev = ctl->rz_new;
+      ctl->rz_prev = gamma;
+      ctl->alpha_prev = alpha;
       const int it = ctl->cg_it + 1;
       ctl->cg_it = it;
       ctl->total_cg_it += 1;
@@ -222,7 +255,7 @@ k_cg_update(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict
       int go = (total > tol2) ? 1 : 0;
       if (ctl->status != 0) {  // exchange failure raised meanwhile
         go = 0;
-      } else if (!(total == total)) {  // NaN: breakdown
+      } else if (!(total == total) || !(denom > 0.0)) {  // NaN / loss of positivity: breakdown
         ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
       } else if (go && it >= ctl->cg_max_iter) {
         ctl->status = 2; ctl->failed_step = ctl->step; ctl->failed_dt = ctl->dt; go = 0;
@@ -239,14 +272,30 @@ __global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond, int with_g
   griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int go = 0;
-  // optimal extrapolation of the initial guess (see kw_mu_rhs): c = -r.d / d.d
-  double c = 0.0;
+  // optimal extrapolation of the initial guess (see kw_mu_rhs): minimise
+  // || r + c1 d1 + c2 d2 ||^2 — a 2 x 2 least-squares problem; falls back to the one-term
+  // guess c1 = -r.d1 / d1.d1 when the history is degenerate (first steps, d2 ~ d1), and to
+  // the plain warm start when there is no history at all
+  double c = 0.0, c2 = 0.0;
   if (with_guess && ctl->dd > 0.0 && ctl->status == 0) {
-    c = -ctl->rd / ctl->dd;
-    if (!(c == c) || fabs(c) > 8.0) c = 0.0;   // (degenerate history: plain warm start)
-    const double rr = ctl->rr + c * (2.0 * ctl->rd + c * ctl->dd);
+    const double g11 = ctl->dd, g12 = ctl->d1d2, g22 = ctl->d2d2;
+    const double det = g11 * g22 - g12 * g12;
+    bool two = with_guess > 1 && g22 > 0.0 && det > 1e-8 * g11 * g22;
+    if (two) {
+      c = (-ctl->rd * g22 + ctl->rd2 * g12) / det;
+      c2 = (-ctl->rd2 * g11 + ctl->rd * g12) / det;
+      if (!(c == c) || !(c2 == c2) || fabs(c) > 16.0 || fabs(c2) > 16.0) two = false;
+    }
+    if (!two) {
+      c2 = 0.0;
+      c = -ctl->rd / ctl->dd;
+      if (!(c == c) || fabs(c) > 8.0) c = 0.0;   // (degenerate history: plain warm start)
+    }
+    const double rr = ctl->rr + 2.0 * (c * ctl->rd + c2 * ctl->rd2) + c * c * g11 +
+                      2.0 * c * c2 * g12 + c2 * c2 * g22;
     ctl->rr = rr > 0.0 ? rr : 0.0;
   }
+  ctl->guess_c2 = c2;
   ctl->guess_c = c;
   if (ctl->status == 0) {
     const double tol2 = ctl->mu_rtol * ctl->mu_rtol * ctl->bb;
@@ -260,24 +309,30 @@ __global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond, int with_g
   set_cond(cond, go);
 }
 
-// Applies the extrapolated initial guess chosen by k_cg_begin: mu <- mu + c (mu - mu_prev),
-// r <- r + c d, and keeps the old mu as the next step's mu_prev.  Sharded: the boundary rows
-// of r go to the neighbours (iteration 0's V-cycle input).
+// Applies the extrapolated initial guess chosen by k_cg_begin:
+//   mu <- mu + c1 (mu - mu_prev) + c2 (mu - mu_pp),  r <- r + c1 d1 + c2 d2,
+// and shifts the history (mu_pp <- mu_prev, mu_prev <- old mu).  Sharded: the boundary rows of
+// r go to the neighbours (iteration 0's V-cycle input), and the halo slots of mu_pp are filled
+// from mu_prev's mailbox copy (threads n .. nx-1) before this step's solution overwrites it.
 __global__ void __launch_bounds__(kBlock)
-k_mu_guess(const Ctl* __restrict__ ctl, const Comm* comm, PushArgs push, int n,
-           double* __restrict__ mu, double* __restrict__ mu_prev, double* __restrict__ r,
-           const double* __restrict__ d) {
+k_mu_guess(Ctl* ctl, const Comm* comm, PushArgs push, HaloArgs prev_halo, int n, int nx,
+           double* __restrict__ mu, double* __restrict__ mu_prev, double* __restrict__ mu_pp,
+           double* __restrict__ r, const double* __restrict__ d1, const double* __restrict__ d2) {
   griddep_enter();
   if (ctl->status != 0) return;
-  const double c = ctl->guess_c;
+  const double c1 = ctl->guess_c, c2 = ctl->guess_c2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const double old = mu[i];
-    mu[i] = old + c * (old - mu_prev[i]);
+    const double old = mu[i], prev = mu_prev[i];
+    mu[i] = old + c1 * (old - prev) + c2 * (old - mu_pp[i]);
+    mu_pp[i] = prev;
     mu_prev[i] = old;
-    const double ri = r[i] + c * d[i];
+    const double ri = r[i] + c1 * d1[i] + c2 * d2[i];
     r[i] = ri;
     if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, ri);
+  } else if (comm != nullptr && i < nx) {
+    const HaloView hv = halo_view(ctl, comm, prev_halo);
+    mu_pp[i] = halo_get(ctl, hv, mu_prev, i);
   }
 }
 

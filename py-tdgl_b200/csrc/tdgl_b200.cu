@@ -227,6 +227,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     A0.val[kd] = diag;
   }
   const std::vector<int64_t> off0 = equal_offsets(Ng_, world_);
+  if (const char* e = std::getenv("TDGL_B200_MAX_COARSE")) cfg_.amg_max_coarse = std::max(8, std::atoi(e));
   AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24, &off0);
   if (H.nc > 4096) throw std::runtime_error("AMG coarsening stalled (coarsest level too large)");
   {
@@ -267,7 +268,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       lnbr[k - base] = li;
     }
   }
-  win0_ = pick_window(lptr, N_, 28, 64 * 1024, &cap0_);
+  {
+    int max_rows = kWinRows;   // rows per CTA of the site operators (experiments: 64 / 128)
+    if (const char* e = std::getenv("TDGL_B200_WIN")) max_rows = std::max(32, std::min(kWinRows, std::atoi(e)));
+    win0_ = pick_window(lptr, N_, 28, 64 * 1024, &cap0_, max_rows);
+  }
 
   // ---- arena: every vector with a halo, plus flags and reduction slots ----------------------
   const ArenaLayout& lay = layouts_[rank_];
@@ -476,11 +481,15 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
 
-  cg_b_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_);
+  cg_b_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_); cg_s_.alloc(N_);
+  if (world_ > 1 && L < 2) throw std::invalid_argument("mesh too small to shard (single-level hierarchy)");
   mu_prev_.alloc(Nx_);
   mu_prev_.zero(stream_);
+  mu_pp_.alloc(Nx_);
+  mu_pp_.zero(stream_);
+  if (const char* e = std::getenv("TDGL_B200_GUESS")) guess_terms_ = std::max(0, std::min(2, std::atoi(e)));
   const size_t max_grid = static_cast<size_t>(max_grid_rows) + 2;
-  partials_.alloc(4 * std::max<size_t>(max_grid, 4096));
+  partials_.alloc(8 * std::max<size_t>(max_grid, 4096));
   counter_.alloc(4);
   counter_.zero(stream_);
   tmp_c_.alloc(Ng_);
@@ -653,6 +662,7 @@ void Engine::configure_kernels() {
   allow(reinterpret_cast<const void*>(&kw_real<OP, false, 4>));        \
   allow(reinterpret_cast<const void*>(&kw_real<OP, true, 4>));
   TDGL_ALLOW_REAL(kOpSpmvDot)
+  TDGL_ALLOW_REAL(kOpSpmvCg)
   TDGL_ALLOW_REAL(kOpPresmooth)
   TDGL_ALLOW_REAL(kOpJacobi)
   TDGL_ALLOW_REAL(kOpPlain)
@@ -733,8 +743,10 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
     launch_k(k_dense_matvec, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p, r_in, z_out);
     TDGL_LAUNCH_CHECK();
-    launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
-    TDGL_LAUNCH_CHECK();
+    if (rz_out != nullptr) {
+      launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
+      TDGL_LAUNCH_CHECK();
+    }
     return;
   }
   // Sharded: on a partitioned level (l < rep) every kernel stores the boundary rows of its
@@ -793,11 +805,12 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     {
       RealArgs a;
       a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.b = b; a.x = lv.x.p; a.y = y;
-      a.w = (li == 0) ? r_in : nullptr;
+      a.w = (li == 0 && rz_out != nullptr) ? r_in : nullptr;
       a.red_out = (li == 0) ? rz_out : nullptr;
       if (li < rep) {
         a.halo = make_halo(li, chan(li, 0), kTagIter);
-        if (li > 0) a.push = make_push(li, chan(li, 3), kTagIter);
+        // level 0: z, whose halo the CG iteration's SpMV reads, travels on p's old channel
+        a.push = li > 0 ? make_push(li, chan(li, 3), kTagIter) : make_push(0, kVecCgP, kTagIter);
       }
       launch_real<kOpJacobi>(levelA(li), a);
     }
@@ -827,40 +840,43 @@ void Engine::enqueue_mu_rhs(double* rhs_raw) {
     launch_k(kw_mu_rhs<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
              ctl_.p, comm(), make_psi_comm(), make_halo(0, kVecMu, kTagMuPrev),
              make_halo(0, kVecMu, kTagMuPrev2), site_csr(), lval_.p, aval_.p, psi_[0].p,
-             psi_[1].p, mu_.p, mu_prev_.p, cg_Ap_.p, areas_.p, bterm_.p,
+             psi_[1].p, mu_.p, mu_prev_.p, mu_pp_.p, cg_Ap_.p, cg_z_.p, areas_.p, bterm_.p,
              ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
   else
     launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
              ctl_.p, comm(), PsiComm(), HaloArgs(), HaloArgs(), site_csr(), lval_.p, aval_.p,
-             psi_[0].p, psi_[1].p, mu_.p, mu_prev_.p, cg_Ap_.p, areas_.p, bterm_.p,
-             ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw, partials_.p, counter_.p);
+             psi_[0].p, psi_[1].p, mu_.p, mu_prev_.p, mu_pp_.p, cg_Ap_.p, cg_z_.p, areas_.p,
+             bterm_.p, ramp_on_ ? ramp_div_.p : nullptr, cg_b_.p, cg_r_.p, rhs_raw, partials_.p,
+             counter_.p);
   TDGL_LAUNCH_CHECK();
 }
 
 // Start of the mu solve: decide the initial guess (k_cg_begin), apply it (k_mu_guess).
 void Engine::enqueue_solve_begin(cudaGraphConditionalHandle cond) {
-  launch_k(k_cg_begin, 1, 32, 0, ctl_.p, cond, 1);
+  launch_k(k_cg_begin, 1, 32, 0, ctl_.p, cond, guess_terms_);
   TDGL_LAUNCH_CHECK();
-  launch_k(k_mu_guess, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
-           comm_on_ ? make_push(0, kVecCgR, kTagIter0) : PushArgs(), N_, mu_.p, mu_prev_.p,
-           cg_r_.p, cg_Ap_.p);
+  const int nth = comm_on_ ? Nx_ : N_;   // (sharded: threads N_ .. Nx_-1 shift mu_pp's halo)
+  launch_k(k_mu_guess, (nth + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
+           comm_on_ ? make_push(0, kVecCgR, kTagIter0) : PushArgs(),
+           comm_on_ ? make_halo(0, kVecMu, kTagMuPrev2) : HaloArgs(), N_, Nx_, mu_.p, mu_prev_.p,
+           mu_pp_.p, cg_r_.p, cg_Ap_.p, cg_z_.p);
   TDGL_LAUNCH_CHECK();
 }
 
 void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
-  enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new);
-  launch_k(k_cg_direction, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
-           comm_on_ ? make_push(0, kVecCgP, kTagIter) : PushArgs(), N_, cg_z_.p, cg_p_.p);
-  TDGL_LAUNCH_CHECK();
+  // z = M r (the last smoother of the V-cycle sends z's boundary rows), then w = A z with
+  // gamma = r.z and delta = z.w in one reduction, then the fused vector update (k_cg_fused)
+  enqueue_vcycle(cg_r_.p, cg_z_.p, nullptr);
   {
     RealArgs a;
-    a.val = A0().val; a.x = cg_p_.p; a.y = cg_Ap_.p; a.red_out = &ctl_.p->pAp;
+    a.val = A0().val; a.x = cg_z_.p; a.b = cg_r_.p; a.y = cg_Ap_.p;
+    a.red_out = &ctl_.p->rz_new; a.red2_out = &ctl_.p->pAp;
     if (comm_on_) a.halo = make_halo(0, kVecCgP, kTagIter);
-    launch_real<kOpSpmvDot>(A0(), a);
+    launch_real<kOpSpmvCg>(A0(), a);
   }
-  launch_k(k_cg_update, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
-           comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_p_.p, cg_Ap_.p,
-           mu_.p, cg_r_.p, partials_.p, counter_.p, cond);
+  launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
+           comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_z_.p, cg_Ap_.p,
+           cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, partials_.p, counter_.p, cond);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -1103,8 +1119,10 @@ void Engine::set_state(const double* psi, const double* mu, bool reset_history) 
   // no history for the extrapolated initial guess of the next solve: mu_prev = mu.  (The
   // step seam keeps it: a caller that threads the results back in, as Runner does, gets
   // exactly the steps of the device loop.)
-  if (reset_history)
+  if (reset_history) {
     TDGL_CUDA(cudaMemcpyAsync(mu_prev_.p, mu_.p, sizeof(double) * Nx_, cudaMemcpyDeviceToDevice, stream_));
+    TDGL_CUDA(cudaMemcpyAsync(mu_pp_.p, mu_.p, sizeof(double) * Nx_, cudaMemcpyDeviceToDevice, stream_));
+  }
   fill_state_boxes();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -1177,7 +1195,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     const int64_t ex_step = 0, ex_it = world_ > 1 ? 1 : 0;  // (the all-gather unpack of level rep)
     const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
     launches_ += h_ctl_->steps_done * (7 + ex_step + (ramp_on_ ? 1 : 0)) + h_ctl_->total_retries * 2 +
-                 h_ctl_->total_cg_it * (3 + 4 * split + 1 + ex_it);
+                 h_ctl_->total_cg_it * (2 + 4 * split + 1 + ex_it);
   } else {
     while (true) {
       launch_k(k_step_begin, 1, 32, 0, ctl_.p, 0);
@@ -1421,8 +1439,9 @@ void Engine::op_mu_rhs(const double* psi, double* rhs) {
   const double bb = h_ctl_->bb, rr = h_ctl_->rr;
   launch_k(kw_mu_rhs<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 28,
            ctl_.p, static_cast<Comm*>(nullptr), PsiComm(), HaloArgs(), HaloArgs(), site_csr(),
-           lval_.p, aval_.p, pin.p, pin.p, mu_.p, mu_.p, cg_Ap_.p, areas_.p, bterm_.p,
-           static_cast<const double*>(nullptr), b.p, r.p, raw.p, partials_.p, counter_.p);
+           lval_.p, aval_.p, pin.p, pin.p, mu_.p, mu_.p, mu_.p, cg_Ap_.p, cg_z_.p, areas_.p,
+           bterm_.p, static_cast<const double*>(nullptr), b.p, r.p, raw.p, partials_.p,
+           counter_.p);
   TDGL_LAUNCH_CHECK();
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, raw.p, tmp_d_.p);
   TDGL_LAUNCH_CHECK();
@@ -1507,8 +1526,20 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
     switch (which) {
       case 0: enqueue_psi_step(nullptr, 1e-6); break;
       case 1: enqueue_mu_rhs(nullptr); break;
-      case 2: launch_spmv(A0(), cg_p_.p, cg_Ap_.p, &ctl_.p->pAp); break;
-      case 3: enqueue_vcycle(cg_r_.p, cg_z_.p, &ctl_.p->rz_new); break;
+      case 2: {
+        RealArgs a;
+        a.val = A0().val; a.x = cg_z_.p; a.b = cg_r_.p; a.y = cg_Ap_.p;
+        a.red_out = &ctl_.p->rz_new; a.red2_out = &ctl_.p->pAp;
+        launch_real<kOpSpmvCg>(A0(), a);
+        break;
+      }
+      case 9:
+        launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_z_.p,
+                 cg_Ap_.p, cg_p_.p, cg_s_.p, tmp_d2_.p, cg_b_.p, partials_.p, counter_.p,
+                 static_cast<cudaGraphConditionalHandle>(0));
+        TDGL_LAUNCH_CHECK();
+        break;
+      case 3: enqueue_vcycle(cg_r_.p, cg_z_.p, nullptr); break;
       case 4:
         mu_.zero(stream_);
         TDGL_CUDA(cudaMemcpyAsync(cg_r_.p, cg_b_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
@@ -1522,7 +1553,7 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
         break;
       case 6:
         if (!multi) throw std::invalid_argument("single-level hierarchy");
-        launch_jacobi(A0(), levels_[0].dinv.p, levels_[0].omega, cg_r_.p, levels_[0].x.p, cg_z_.p, cg_r_.p, &ctl_.p->rz_new);
+        launch_jacobi(A0(), levels_[0].dinv.p, levels_[0].omega, cg_r_.p, levels_[0].x.p, cg_z_.p, nullptr, nullptr);
         break;
       case 7:
         if (!multi) throw std::invalid_argument("single-level hierarchy");

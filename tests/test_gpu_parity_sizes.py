@@ -8,8 +8,11 @@ The oracle (oracle/tdgl_oracle.py: SciPy SuperLU, the reference's expression ord
 against the unmodified reference in the build container (tests/test_oracle_vs_reference.py,
 including these edge cases) and runs live here on the box's host cores.
 
-Tolerances: gauge-fixed psi, |psi|, mu, J_s, J_n <= 1e-8 relative (BASELINE.json asks 1e-6),
-dt sequence <= 1e-10 relative, all on the smooth start-up window of the workloads.
+Tolerances (BASELINE.json asks psi within 1e-6): gauge-fixed psi, |psi|, mu, J_s, J_n <= 1e-8
+relative and dt sequence <= 1e-10 relative with the mu solve converged tightly
+(``mu_rtol = 1e-13``), on the smooth start-up window of the workloads.  With the product's
+default ``mu_rtol = 1e-10`` the iterative solve's own truncation (amplified by the adaptive-dt
+controller, which divides by max |d|psi|^2|) is what remains: <= 1e-7 and dt <= 1e-9 asserted.
 """
 import os
 import sys
@@ -27,6 +30,9 @@ if ROOT not in sys.path:
 pytestmark = pytest.mark.gpu
 
 TOL, TOL_DT = 1e-8, 1e-10
+# (mu_rtol, field tolerance, dt tolerance)
+RTOLS = [pytest.param(1e-13, 1e-8, 1e-10, id="mu_rtol=1e-13"),
+         pytest.param(1e-10, 1e-7, 1e-9, id="mu_rtol=default")]
 
 
 def _oracle_run(work, steps):
@@ -40,10 +46,10 @@ def _oracle_run(work, steps):
     return orc.run(solver, end_time=1e9, max_steps=steps)
 
 
-def _cuda_run(work, steps, engine_factory=None):
+def _cuda_run(work, steps, engine_factory=None, mu_rtol=1e-10):
     from tdgl_b200 import SolverOptions, TDGLSolver
 
-    opts = SolverOptions(solve_time=1e9, save_every=steps, **work["opts"])
+    opts = SolverOptions(solve_time=1e9, save_every=steps, mu_rtol=mu_rtol, **work["opts"])
     solver = TDGLSolver.from_dimensionless(
         work["mesh"], opts, A_applied=work["A"], epsilon=work["eps"],
         terminal_info=work["terms"], terminal_currents=work["currents"])
@@ -69,12 +75,12 @@ def _cuda_run(work, steps, engine_factory=None):
     return out
 
 
-def _assert_parity(tag, got, ref, areas):
+def _assert_parity(tag, got, ref, areas, tol=TOL, tol_dt=TOL_DT):
     d = orc.compare(got, ref, areas)
     print(tag, d, "mu iterations/step", got["info"].mu_iterations / got["info"].steps_done)
     for k in ("psi", "abs_psi", "mu", "supercurrent", "normal_current"):
-        assert d[k] < TOL, (tag, k, d)
-    np.testing.assert_allclose(got["dt"], ref["dt"], rtol=TOL_DT)
+        assert d[k] < tol, (tag, k, d)
+    np.testing.assert_allclose(got["dt"], ref["dt"], rtol=tol_dt)
 
 
 @pytest.fixture(scope="module")
@@ -94,46 +100,54 @@ def film1m():
     return work, _oracle_run(work, 50)
 
 
-def _sharded(world):
+def _sharded(world, mu_rtol=1e-10):
     def factory(solver):
         from tdgl_b200.sharded import LocalShardGroup
 
         fixed = (np.concatenate([np.asarray(t.site_indices) for t in solver.terminal_info])
                  if solver.terminal_info else None)
         return LocalShardGroup(solver.mesh, world, fixed_sites=fixed, fix_psi=True,
-                               gamma=solver.gamma, u=solver.u, mu_rtol=solver.options.mu_rtol,
+                               gamma=solver.gamma, u=solver.u, mu_rtol=mu_rtol,
                                running_capacity=4096)
     return factory
 
 
-def test_film250k_field_matches_oracle(film250k):
+@pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
+def test_film250k_field_matches_oracle(film250k, mu_rtol, tol, tol_dt):
     """BASELINE.json configs[1]: 200x200 xi film (~251k sites), B = 0.1, adaptive dt."""
     work, ref = film250k
-    got = _cuda_run(work, 60)
-    _assert_parity("film250k_field, 60 steps", got, ref, work["mesh"].areas)
+    got = _cuda_run(work, 60, mu_rtol=mu_rtol)
+    _assert_parity(f"film250k_field, 60 steps, mu_rtol={mu_rtol}", got, ref,
+                   work["mesh"].areas, tol, tol_dt)
 
 
-def test_film250k_field_4_shards_match_oracle(film250k):
+@pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
+def test_film250k_field_4_shards_match_oracle(film250k, mu_rtol, tol, tol_dt):
     work, ref = film250k
-    got = _cuda_run(work, 60, _sharded(4))
-    _assert_parity("film250k_field, 4 shards, 60 steps", got, ref, work["mesh"].areas)
+    got = _cuda_run(work, 60, _sharded(4, mu_rtol), mu_rtol=mu_rtol)
+    _assert_parity(f"film250k_field, 4 shards, 60 steps, mu_rtol={mu_rtol}", got, ref,
+                   work["mesh"].areas, tol, tol_dt)
 
 
-def test_film1m_holes_transport_matches_oracle(film1m):
+@pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
+def test_film1m_holes_transport_matches_oracle(film1m, mu_rtol, tol, tol_dt):
     """BASELINE.json configs[2], the configuration the headline metric is quoted on: 1.0M
     sites, four holes, source / drain terminals, transport current, adaptive dt."""
     work, ref = film1m
-    got = _cuda_run(work, 50)
-    _assert_parity("film1m_holes_transport, 50 steps", got, ref, work["mesh"].areas)
+    got = _cuda_run(work, 50, mu_rtol=mu_rtol)
+    _assert_parity(f"film1m_holes_transport, 50 steps, mu_rtol={mu_rtol}", got, ref,
+                   work["mesh"].areas, tol, tol_dt)
     fixed = np.concatenate([np.asarray(t.site_indices) for t in work["terms"]])
     assert np.abs(got["psi"][fixed]).max() == 0.0
 
 
-def test_film1m_holes_transport_4_shards_match_oracle(film1m):
+@pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
+def test_film1m_holes_transport_4_shards_match_oracle(film1m, mu_rtol, tol, tol_dt):
     """The 4-shard decomposition against the ORACLE (not against the single engine)."""
     work, ref = film1m
-    got = _cuda_run(work, 50, _sharded(4))
-    _assert_parity("film1m_holes_transport, 4 shards, 50 steps", got, ref, work["mesh"].areas)
+    got = _cuda_run(work, 50, _sharded(4, mu_rtol), mu_rtol=mu_rtol)
+    _assert_parity(f"film1m_holes_transport, 4 shards, 50 steps, mu_rtol={mu_rtol}", got, ref,
+                   work["mesh"].areas, tol, tol_dt)
 
 
 # ------------------------------------------------------------------------------------------
