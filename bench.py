@@ -483,12 +483,29 @@ def run_b200(args, rank, world, local_rank):
                        "frac": nbytes / kms / 1e6 / peak, "launches_per_step": per_step,
                        "share_of_step": per_step * kms / (ms_total / K)}
     vc_ms = eng.time_kernel(3, 10, flush_l2=True) if levels > 1 else None
+    # comparator: cuSPARSE's generic CSR SpMV on the same device arrays
+    cusparse = None
+    if world == 1:
+        try:
+            cusparse = {}
+            for label, which, nbytes, ours in (
+                    ("real_f64", 0, 12 * nnz + 20 * nl, "kw_real<spmv_cg> fine level"),
+                    ("complex128", 1, 20 * nnz + 36 * nl, "kw_psi_step")):
+                cms = eng.time_cusparse(which, 20, flush_l2=True)
+                cusparse[label] = {"ms": cms, "bytes": nbytes, "GBps": nbytes / cms / 1e6,
+                                   "frac": nbytes / cms / 1e6 / peak,
+                                   "ours": ours, "ours_ms": table[ours]["ms"],
+                                   "note": "plain y = A x; ours also fuses the dot products /"
+                                           " the psi update into the same pass"}
+        except Exception as exc:  # the comparator is optional (library not present)
+            cusparse = {"unavailable": str(exc)}
     dom = max(table, key=lambda k: table[k]["share_of_step"])
     # traffic: DRAM bytes need a profiler pass (ncu --set full), which a timed run may not be
     # under; the captures of this command are summarised in profiles/ (r2_full.md)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBps"], "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": table[dom]["frac"],
-                "traffic": None, "kernels": table, "vcycle_ms": vc_ms}
+                "traffic": None, "kernels": table, "vcycle_ms": vc_ms,
+                "cusparse_spmv": cusparse}
 
     line = {
         "metric": "tdgl_site_steps_per_sec", "value": steps_per_s * n, "unit": "site-steps/s",

@@ -35,7 +35,9 @@ enum {
   TDGL_OK = 0,
   TDGL_E_STEP_FAILED = 1,  /* |psi|^2 solve failed max_solve_retries times
                               (reference RuntimeError, solver/solver.py:478-483) */
-  TDGL_E_MU_SOLVER = 2,    /* mu solver did not reach tolerance in max iterations */
+  TDGL_E_MU_SOLVER = 2,    /* mu solver did not reach tolerance in max iterations; also: the
+                              screening iteration did not converge (info.status == 4, reference
+                              RuntimeError solver/solver.py:657-663) */
   TDGL_E_CUDA = 3,         /* CUDA / NCCL runtime error */
   TDGL_E_INVALID = 4       /* bad argument */
 };
@@ -116,6 +118,25 @@ int tdgl_set_vector_potential_ramp(tdgl_handle* h, const double* A0, int32_t n_k
 /* psi[N] (complex128) and mu[N]: the `psi`, `mu` values Runner threads through update(). */
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu);
 
+/* Screening (SolverOptions.include_screening; reference solver/solver.py:304-314, 522-578,
+ * 650-688, solver/screening.py:12-42, finite_volume/mesh.py:203-243): every time step iterates
+ * Polyak's method on the induced vector potential
+ *     A_induced[e] = scale * sum_j J_site[j] * areas[j] / |edge_centers[e] - sites_xy[j]|,
+ * J_site = site average of the edge current J_s + J_n, with the link variables rebuilt from
+ * A_applied + A_induced in every pass, until the relative change is below `tolerance`
+ * (status 4 / TDGL_E_MU_SOLVER after `max_iterations` passes, like the reference's RuntimeError).
+ *   sites_xy[N][2], edge_centers[E][2]: the coordinates the reference uses (xi * mesh coordinates);
+ *   scale: the reference's mu_0 / (4 pi) * K0 / A0 (in 1 / length_units) * xi^2 per unit mesh area.
+ * enable = 0 turns screening off.  Not available on a sharded engine. */
+int tdgl_set_screening(tdgl_handle* h, int32_t enable, double scale, const double* sites_xy,
+                       const double* edge_centers, double tolerance, int32_t max_iterations,
+                       double step_size, double step_drag);
+/* The `induced_vector_potential` value Runner threads through update(): [E][2]. */
+int tdgl_set_induced_vector_potential(tdgl_handle* h, const double* A_induced);
+int tdgl_get_induced_vector_potential(tdgl_handle* h, double* A_induced);
+/* RunningState "screening_iterations" of the steps of the last advance() (solver.py:695-696). */
+int tdgl_get_running_screening(tdgl_handle* h, int64_t capacity, int64_t* iterations);
+
 /* The SolverOptions fields the step reads (options.py:66-89) and the controller state
  * TDGLSolver keeps between steps (solver.py:316-320): resets tentative_dt = dt_init and
  * clears the |psi|^2-change history. */
@@ -137,6 +158,8 @@ typedef struct tdgl_advance_info {
   int64_t mu_iterations;   /* total CG iterations in this call */
   double mu_rel_residual;  /* ||r||/||b|| of the last mu solve */
   double device_ms;        /* CUDA-event time of the stepping on the engine's stream */
+  int64_t screening_iterations; /* total passes of the screening (Polyak) loop in this call */
+  double screening_error;  /* relative change of A_induced in the last pass (solver.py:571-575) */
 } tdgl_advance_info;
 
 /* Runs the loop of Runner._run_stage (runner.py:379-433) on the device: up to
@@ -194,7 +217,7 @@ int tdgl_op_mu_solve(tdgl_handle* h, const double* rhs, double* mu, int32_t* ite
 /* Time one kernel (or kernel sequence) of the step with CUDA events on the engine's
  * stream; returns the mean milliseconds per launch over `reps` launches after one warm-up.
  *   which: 0 psi step (fused SpMV + update)        1 mu rhs (+ warm-start residual)
- *          2 fine-level mu SpMV with dot (A p)     3 one whole V-cycle
+ *          2 fine-level CG SpMV (w = A z, r.z, z.w) 3 one whole V-cycle
  *          4 one full mu solve from a zero guess   5 fine-level pre-smoothing + residual
  *          6 fine-level Jacobi post-smoothing      7 fine-level restriction
  *          8 fine-level prolongation
@@ -202,6 +225,19 @@ int tdgl_op_mu_solve(tdgl_handle* h, const double* rhs, double* mu, int32_t* ite
  *   scratch buffer, so that nothing of the operator is left in the 126 MB L2. */
 int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_l2,
                      double* mean_ms);
+
+/* Comparator, measurement only: NVIDIA cuSPARSE's generic CSR SpMV (cusparseSpMV) on the
+ * engine's own device-resident CSR arrays — the library kernel SURVEY.md section 2.3 names as
+ * the bar for the reference's sparse products (operators.py:291-293, 341-342).
+ *   which: 0 real f64 mu operator (what kw_real<spmv_cg> applies)
+ *          1 complex128 covariant Laplacian (what kw_psi_step applies)
+ * libcusparse is opened with dlopen() inside this call only; it is not a load-time dependency
+ * and never on the stepping path.  Returns TDGL_E_INVALID when the library is not present. */
+int tdgl_time_cusparse(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_l2,
+                       double* mean_ms);
+
+/* which = 2: fine-level CG SpMV w = A z with r.z and z.w (kw_real<spmv_cg>); 9: the fused CG
+ * vector update (k_cg_fused). */
 
 /* Sizes and setup facts: [0] N, [1] E, [2] nnz of a site operator, [3] AMG levels,
  * [4] sum of level nnz, [5] coarsest size, [6] kernels launched so far (host count),

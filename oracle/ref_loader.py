@@ -228,6 +228,8 @@ def run_reference(solver, *, end_time: float, max_steps: Optional[int] = None,
     if solver.probe_points is not None:
         names["mu"] = len(solver.probe_points)
         names["theta"] = len(solver.probe_points)
+    if opts.include_screening:
+        names["screening_iterations"] = 1                      # solver.py:777-778
     # one long buffer: never cleared, so it holds the full trace
     nbuf = (max_steps or 0) + 2 if max_steps else 1_000_000
     running = ref.RunningState(names, nbuf)

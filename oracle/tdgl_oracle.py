@@ -145,6 +145,35 @@ class OracleOperators:
         return (psi.conjugate()[self.edges[:, 0]] * (self.psi_gradient @ psi)).imag
 
 
+# ------------------------------------------------------------------ screening (row S)
+
+def get_quantity_on_site(edges, normalized_directions, n_sites, quantity_on_edge):
+    """Edge quantity -> site vector: the mean over the edges at a site of the quantity times
+    the edge's unit vector, divided by 2  — finite_volume/mesh.py:203-243 (vector=True)."""
+    flux_x = quantity_on_edge * normalized_directions[:, 0]
+    flux_y = quantity_on_edge * normalized_directions[:, 1]
+    vertices = np.concatenate([edges[:, 0], edges[:, 1]])
+    counts = np.bincount(vertices, minlength=n_sites)
+    x = np.bincount(vertices, weights=np.concatenate([flux_x, flux_x]), minlength=n_sites) / counts
+    y = np.bincount(vertices, weights=np.concatenate([flux_y, flux_y]), minlength=n_sites) / counts
+    return np.array([x, y]).T / 2
+
+
+def get_A_induced(J_site, site_areas, sites, edge_centers, chunk: int = 2048):
+    """A_induced[i, k] = sum_j J_site[j, k] * site_areas[j] / |edge_centers[i] - sites[j]|
+    — solver/screening.py:12-42 (the numba kernel; summed here in site order per edge like
+    its inner loop, in blocks of edges)."""
+    out = np.empty((len(edge_centers), 2))
+    w = J_site * site_areas[:, None]
+    for i0 in range(0, len(edge_centers), chunk):
+        c = edge_centers[i0:i0 + chunk]
+        dx = c[:, 0][:, None] - sites[:, 0][None, :]
+        dy = c[:, 1][:, None] - sites[:, 1][None, :]
+        inv = 1.0 / np.sqrt(dx * dx + dy * dy)
+        out[i0:i0 + chunk] = inv @ w
+    return out
+
+
 # ------------------------------------------------------------------ step physics (L1)
 
 def solve_for_psi_squared(psi, abs_sq_psi, mu, epsilon, gamma, u, dt, psi_laplacian):
@@ -183,6 +212,11 @@ class OracleOptions:
     adaptive_time_step_multiplier: float = 0.25
     terminal_psi: Optional[complex] = 0.0
     save_every: int = 100
+    include_screening: bool = False
+    max_iterations_per_step: int = 1000
+    screening_tolerance: float = 1e-3
+    screening_step_size: float = 0.1
+    screening_step_drag: float = 0.5
 
 
 @dataclass
@@ -206,6 +240,10 @@ class OracleSolver:
     # time-dependent disorder: t -> [N]; then ``epsilon`` must be its value at t = 0
     # (solver.py:191-216, 364-381, 644-646)
     epsilon_func: Optional[Callable[[float], np.ndarray]] = None
+    # screening (solver.py:304-314): A_induced = screening_scale * sum_j J_j a_j / |c_e - r_j|
+    # with a_j, c_e, r_j the mesh's own (dimensionless) areas and coordinates, i.e.
+    # screening_scale = [mu_0 / (4 pi) K0 / A0 in 1/length_units] * xi
+    screening_scale: float = 0.0
 
     def __post_init__(self):
         o = self.options
@@ -231,6 +269,29 @@ class OracleSolver:
         self.tentative_dt = o.dt_init                          # solver.py:318-320
         self.dt_max = o.dt_max if o.adaptive else o.dt_init
         self.epsilon = np.asarray(self.epsilon, float)
+        self.A_induced = np.zeros((len(self.mesh.edge_mesh.edges), 2))
+        self.screening_iterations = 0
+        self.screening_areas = self.screening_scale * np.asarray(self.mesh.areas, float)
+
+    def get_induced_vector_potential(self, current_density, A_induced_vals, velocity):
+        """One step of Polyak's method — solver.py:522-578."""
+        o = self.options
+        em = self.mesh.edge_mesh
+        J_site = get_quantity_on_site(np.asarray(em.edges), self.normalized_directions,
+                                      len(self.mesh.sites), current_density)
+        new_A = get_A_induced(J_site, self.screening_areas, np.asarray(self.mesh.sites, float),
+                              np.asarray(em.centers, float))
+        A_induced = A_induced_vals[-1]
+        dA = new_A - A_induced
+        velocity.append((1 - o.screening_step_drag) * velocity[-1] + o.screening_step_size * dA)
+        A_induced = A_induced + velocity[-1]
+        A_induced_vals.append(A_induced)
+        numerator = np.linalg.norm(dA, axis=1)
+        denominator = np.maximum(np.linalg.norm(A_induced, axis=1), 1e-20)
+        err = float(np.max(numerator / denominator))
+        del velocity[:-2]
+        del A_induced_vals[:-2]
+        return A_induced, err
 
     def update_mu_boundary(self, time: float) -> None:
         """J_ext,k = -(1/L_k) sum_{j != k} I_j  — solver.py:325-345"""
@@ -289,9 +350,36 @@ class OracleSolver:
         if self.epsilon_func is not None:                                # :644-646
             self.epsilon = np.asarray(self.epsilon_func(time), float)
         old_sq = np.absolute(psi) ** 2                                   # :649
-        dt = self.tentative_dt                                           # :668
-        psi, new_sq, dt = self.adaptive_euler_step(step, psi, old_sq, mu, dt)
-        mu, js, jn = self.solve_for_observables(psi, dA_dt)
+        if not o.include_screening:
+            dt = self.tentative_dt                                       # :668
+            psi, new_sq, dt = self.adaptive_euler_step(step, psi, old_sq, mu, dt)
+            mu, js, jn = self.solve_for_observables(psi, dA_dt)
+        else:
+            # Polyak iteration on the induced vector potential (:650-688).  As in the
+            # reference, psi and mu are re-assigned by every pass of the loop (the next pass
+            # steps from them) while |psi|^2 of the step's input stays fixed.
+            err = np.inf
+            A_vals, velocity = [self.A_induced], [0.0]
+            A_ind = self.A_induced
+            it = 0
+            while True:
+                if err < o.screening_tolerance:
+                    break
+                if it > o.max_iterations_per_step:
+                    raise RuntimeError(
+                        f"Screening calculation failed to converge at step {step} after"
+                        f" {o.max_iterations_per_step} iterations. Relative error in"
+                        f" induced vector potential: {err:.2e}"
+                        f" (tolerance: {o.screening_tolerance:.2e}).")
+                if it == 0:
+                    dt = self.tentative_dt
+                self.operators.set_link_exponents(self.current_A_applied + A_ind)
+                psi, new_sq, dt = self.adaptive_euler_step(step, psi, old_sq, mu, dt)
+                mu, js, jn = self.solve_for_observables(psi, dA_dt)
+                A_ind, err = self.get_induced_vector_potential(js + jn, A_vals, velocity)
+                it += 1
+            self.A_induced = A_ind
+            self.screening_iterations = it                               # :695-696
         if o.adaptive:                                                   # :698-707
             self.d_psi_sq_vals.append(float(np.absolute(new_sq - old_sq).max()))
             if step > o.adaptive_window:
@@ -311,12 +399,13 @@ def run(solver: OracleSolver, *, end_time: float, max_steps: Optional[int] = Non
     psi = solver.psi_init.copy() if psi0 is None else np.array(psi0, complex)
     mu = solver.mu_init.copy() if mu0 is None else np.array(mu0, float)
     time = 0.0
-    dts, mus, thetas = [], [], []
+    dts, mus, thetas, sits = [], [], [], []
     i = 0
     dt = solver.options.dt_init if dt0 is None else dt0          # Runner's self.dt
     while True:
         dt, psi, mu, js, jn = solver.update(i, time, psi, mu, dt_prev=dt)
         dts.append(float(dt))
+        sits.append(solver.screening_iterations)
         if solver.probe_points is not None:                      # solver.py:691-694
             mus.append(mu[list(solver.probe_points)])
             thetas.append(np.angle(psi[list(solver.probe_points)]))
@@ -326,6 +415,9 @@ def run(solver: OracleSolver, *, end_time: float, max_steps: Optional[int] = Non
         i += 1
     out = dict(psi=psi, mu=mu, supercurrent=js, normal_current=jn, dt=np.array(dts),
                steps=i + 1, time=time)
+    if solver.options.include_screening:
+        out["screening_iterations"] = np.array(sits)
+        out["induced_vector_potential"] = solver.A_induced
     if solver.probe_points is not None:
         out["running"] = dict(mu=np.array(mus).T, theta=np.array(thetas).T)
     return out

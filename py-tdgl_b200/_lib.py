@@ -55,6 +55,8 @@ class tdgl_advance_info(C.Structure):
         ("mu_iterations", C.c_int64),
         ("mu_rel_residual", C.c_double),
         ("device_ms", C.c_double),
+        ("screening_iterations", C.c_int64),
+        ("screening_error", C.c_double),
     ]
 
 
@@ -76,6 +78,10 @@ SIGNATURES = {
     "tdgl_set_dA_dt": (C.c_int, [_P, _P]),
     "tdgl_set_vector_potential_ramp": (C.c_int, [_P, _P, _I32, _P, _P]),
     "tdgl_set_state": (C.c_int, [_P, _P, _P]),
+    "tdgl_set_screening": (C.c_int, [_P, _I32, _D, _P, _P, _D, _I32, _D, _D]),
+    "tdgl_set_induced_vector_potential": (C.c_int, [_P, _P]),
+    "tdgl_get_induced_vector_potential": (C.c_int, [_P, _P]),
+    "tdgl_get_running_screening": (C.c_int, [_P, _I64, _P]),
     "tdgl_set_stepper": (C.c_int, [_P, _D, _D, _I32, _I32, _I32, _D]),
     "tdgl_advance": (C.c_int, [_P, _I64, _D, _I64, _D, C.POINTER(tdgl_advance_info)]),
     "tdgl_update": (C.c_int, [_P, _P, _P, _I64, _D, _P, _P, _P, _P,
@@ -91,6 +97,7 @@ SIGNATURES = {
     "tdgl_op_mu_laplacian": (C.c_int, [_P, _P, _P]),
     "tdgl_op_mu_solve": (C.c_int, [_P, _P, _P, C.POINTER(_I32), C.POINTER(_D)]),
     "tdgl_time_kernel": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_D)]),
+    "tdgl_time_cusparse": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_D)]),
     "tdgl_get_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
     "tdgl_comm_export": (C.c_int, [_P, _P]),
     "tdgl_comm_connect_ipc": (C.c_int, [_P, _P, _I32]),

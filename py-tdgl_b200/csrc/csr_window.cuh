@@ -354,7 +354,8 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
             const unsigned char* __restrict__ fixed, const double2* psi_buf0,
             const double2* psi_buf1, double2* out_buf0, double2* out_buf1,
             const double* __restrict__ mu, const double* __restrict__ eps,
-            double* __restrict__ sq_out /* may be null */, double dt_override /* < 0: ctl->dt */) {
+            double* __restrict__ sq_out /* may be null */, double dt_override /* < 0: ctl->dt */,
+            const double* __restrict__ old_sq /* screening: |psi|^2 of the step's input; else null */) {
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double s_max[8];
@@ -388,6 +389,8 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
     epsi = eps[w.row];
     fx = fixed[w.row] != 0;
   }
+  double abs2 = p.x * p.x + p.y * p.y;
+  if (in && old_sq != nullptr) abs2 = old_sq[w.row];
   mbar_wait(&bar, 0);
   if (!live) return;
   double dmax = 0.0;
@@ -395,12 +398,12 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
   if (in) {
     double2 lap = row_dot_c<SH>(sv, si, w.kb, w.ke, psi, ctl, hv);
     if (fx) lap = p;
-    const PsiOut o = psi_update(p, lap, mui, epsi, ctl->gamma, ctl->u, dt);
+    const PsiOut o = psi_update(p, lap, mui, epsi, ctl->gamma, ctl->u, dt, abs2);
     out[w.row] = o.psi;
     if (SH && comm != nullptr) push_row(comm, pc.push[cur ^ 1], tag_out, w.row, o.psi);
     if (sq_out != nullptr) sq_out[w.row] = o.sq;
     failed = o.failed;
-    const double d = fabs(o.sq - (p.x * p.x + p.y * p.y));
+    const double d = fabs(o.sq - abs2);
     dmax = (d == d) ? d : 0.0;
   }
   // max / any are order-free: warp shuffle, then one atomic per block

@@ -170,12 +170,18 @@ class Engine {
   void set_dA_dt(const double* dadt);
   void set_ramp(const double* A0, int n_knots, const double* t_knots, const double* f_knots);
   void set_state(const double* psi, const double* mu, bool reset_history = true);
+  void set_screening(int enable, double scale, const double* sites_xy, const double* edge_centers,
+                     double tolerance, int max_iterations, double step_size, double drag);
+  void set_induced(const double* A);
+  void get_induced(double* A);
+  void get_running_screening(int64_t capacity, int64_t* iterations);
   void set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
                    double multiplier);
   struct AdvanceInfo {
     int64_t steps_done, step; double time, dt, tentative_dt; int finished, status;
     int64_t failed_step; double failed_dt; int64_t retries, mu_iterations; double mu_rel_residual;
     double device_ms;
+    int64_t screening_iterations; double screening_error;
   };
   AdvanceInfo advance(int64_t max_steps, double t_end, int64_t step, double time);
   AdvanceInfo update(const double* psi, const double* mu, int64_t step, double time,
@@ -193,6 +199,7 @@ class Engine {
   void op_mu_laplacian(const double* x, double* y);
   void op_mu_solve(const double* rhs, double* mu, int* iterations, double* rel_res);
   double time_kernel(int which, int reps, int flush_l2);
+  double time_cusparse(int which, int reps, int flush_l2);
   void get_info(int64_t* out, int n);
 
   // ---- sharded engine: wiring of the peer arenas -------------------------------------------
@@ -248,6 +255,15 @@ class Engine {
   DevBuf<double> ramp_proj_, ramp_div_, ramp_zero_;
   void enqueue_ramp_links();
   int win0_ = kWinRows, cap0_ = 0;  // window geometry of the site operators
+  // ---- screening (row S): induced vector potential, Polyak iteration inside the step ---------
+  bool scr_on_ = false;
+  DevBuf<double2> aind_, aind_new_, vel_, edir_, ecent_, sxy_, wsite_;
+  DevBuf<double> old_sq_, scr_area_;
+  DevBuf<long long> run_scr_;
+  std::vector<double> h_areas_int_;   // areas in internal site order (host copy)
+  void enqueue_screening_pass_begin();
+  void enqueue_screening_pass_end(cudaGraphConditionalHandle cond_scr, cudaGraphConditionalHandle cond_psi);
+  void rebuild_graph();
   // ---- edges (caller edge order, internal site indices) -----------------------------------
   DevBuf<int> e0_, e1_;
   DevBuf<double> elen_, weight_, theta_;
@@ -280,7 +296,7 @@ class Engine {
   Ctl* h_ctl_ = nullptr;  // pinned mirror
   cudaGraph_t graph_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
-  cudaGraphConditionalHandle h_step_ = 0, h_psi_ = 0, h_cg_ = 0;
+  cudaGraphConditionalHandle h_step_ = 0, h_psi_ = 0, h_cg_ = 0, h_scr_ = 0;
 
   // ---- launch sequences ------------------------------------------------------------------
   // Every kernel of the stepping sequence is launched with programmatic stream

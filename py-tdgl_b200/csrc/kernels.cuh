@@ -59,6 +59,11 @@ struct Ctl {
   int solve_epoch;    // mu solves started so far (+1): bumped at the start of every step
   int psi_epoch;      // attempts of the psi step so far (+1)
   int psi_tag[2];     // psi_epoch of the attempt that produced each psi buffer
+  // --- screening: Polyak iteration on the induced vector potential (solver.py:650-688) -------
+  int scr_on, scr_it, scr_go, scr_max_it;
+  double scr_tol, scr_alpha, scr_beta, scr_err;
+  unsigned long long scr_err_bits;    // max over the edges of |dA| / |A_induced| (double bits)
+  long long total_scr_it;
   // --- separable time-dependent vector potential A(r, t) = f(t) A0(r) (device-side ramp) ----
   // f is piecewise linear through (ramp_t[k], ramp_v[k]), constant outside
   int ramp_on, ramp_changed, ramp_knots, ramp_pad;
@@ -346,13 +351,15 @@ struct PsiOut {
   int failed;
 };
 
+// abs2 = |psi|^2 of the step's INPUT state (solver.py:649): equal to |psi|^2 of the psi passed
+// here except in the 2nd, 3rd, ... pass of a screening iteration, where the reference steps
+// from the previous pass's psi but keeps the step's first |psi|^2 (solver.py:676-678).
 __device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu, double eps,
-                                             double gamma, double u, double dt) {
+                                             double gamma, double u, double dt, double abs2) {
   // U = exp(-i mu dt)
   double s, c;
   sincos(-mu * dt, &s, &c);
   const double2 U = make_double2(c, s);
-  const double abs2 = psi.x * psi.x + psi.y * psi.y;
   // z = U * gamma^2 / 2 * psi
   const double g2h = gamma * gamma / 2.0;
   const double2 Ug = make_double2(U.x * g2h, U.y * g2h);
@@ -380,7 +387,8 @@ __device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu
 }
 
 // Start of TDGLSolver.update (solver.py:649-668): dt <- tentative_dt, retries <- 0.
-__global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
+__global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi,
+                             cudaGraphConditionalHandle cond_scr) {
   griddep_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (ctl->ramp_on) {
@@ -403,13 +411,18 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi) {
     ctl->ramp_f = f;
   }
   ctl->dt = ctl->tentative_dt;
+  ctl->scr_it = 0;
+  ctl->scr_err_bits = 0ull;
+  ctl->scr_err = 1e300;
   ctl->solve_epoch += 1;
   ctl->retries = 0;
   ctl->disc_flag = 0;
   ctl->max_dpsi_bits = 0ull;
   const int go = (ctl->status == 0) ? 1 : 0;
   ctl->psi_go = go;
+  ctl->scr_go = go;
   set_cond(cond_psi, go);
+  set_cond(cond_scr, go);
 }
 
 // adaptive_euler_step's retry logic (solver.py:475-485)
@@ -491,7 +504,8 @@ k_shift(const Ctl* __restrict__ ctl, const Comm* comm, PushArgs push, int n,
 __global__ void k_step_end(Ctl* ctl, const double2* __restrict__ psi_buf0,
                            const double2* __restrict__ psi_buf1, const double* __restrict__ mu,
                            const int* __restrict__ probes, double* run_dt, double* run_mu,
-                           double* run_theta, cudaGraphConditionalHandle cond_step) {
+                           double* run_theta, long long* run_scr /* null: no screening */,
+                           cudaGraphConditionalHandle cond_step) {
   griddep_enter();
   if (blockIdx.x != 0) return;
   if (ctl->status != 0) {
@@ -510,6 +524,7 @@ __global__ void k_step_end(Ctl* ctl, const double2* __restrict__ psi_buf0,
   if (threadIdx.x != 0) return;
   const double dt = ctl->dt;
   if (pos < cap) run_dt[pos] = dt;
+  if (pos < cap && run_scr != nullptr) run_scr[pos] = ctl->scr_it;   // solver.py:695-696
   if (ctl->adaptive) {
     const double d = __longlong_as_double((long long)ctl->max_dpsi_bits);
     ctl->dpsi_hist[ctl->n_hist % kMaxWindow] = d;
@@ -647,6 +662,8 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
                            const double* __restrict__ dadt /* may be null */,
                            const Ctl* __restrict__ ctl,
                            const double* __restrict__ ramp_proj /* null: no device-side ramp */,
+                           const double2* __restrict__ aind /* null: no screening */,
+                           const double2* __restrict__ edir,
                            double* __restrict__ js, double* __restrict__ jn) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
@@ -659,7 +676,9 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   const double inv_l = 1.0 / elen[e];
   double s, c;
   // (device-side ramp: theta holds A0 . d, the current A is ramp_f * A0)
-  sincos(ramp_proj != nullptr ? -(ctl->ramp_f * theta[e]) : -theta[e], &s, &c);
+  double th = ramp_proj != nullptr ? ctl->ramp_f * theta[e] : theta[e];
+  if (aind != nullptr) th += aind[e].x * edir[e].x + aind[e].y * edir[e].y;
+  sincos(-th, &s, &c);
   const double2 pi = psi[i], pj = psi[j];
   // g = (U psi_j) * (1/l) + psi_i * (-1/l)   as the CSR gradient row computes it
   const double gx = (c * pj.x - s * pj.y) * inv_l - pi.x * inv_l;
@@ -668,6 +687,203 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   double da = dadt != nullptr ? dadt[e] : 0.0;
   if (ramp_proj != nullptr) da = ctl->ramp_dfdt * ramp_proj[e];
   jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
+}
+
+// ------------------------------------------------------------------------------------------
+// screening: the induced vector potential
+//   A_ind[e] = sum_j J_site[j] a~_j / |c_e - r_j|        (solver/screening.py:12-42)
+// with J_site the site average of the edge current J_s + J_n (finite_volume/mesh.py:203-243),
+// iterated with Polyak's method inside every time step (solver/solver.py:522-578, 650-688).
+
+// |psi|^2 of the step's input state, kept for all passes of the screening loop
+__global__ void __launch_bounds__(kBlock)
+k_scr_old_sq(const Ctl* __restrict__ ctl, int n, const double2* __restrict__ psi0,
+             const double2* __restrict__ psi1, double* __restrict__ old_sq) {
+  griddep_enter();
+  if (ctl->status != 0) return;
+  const double2* psi = ctl->cur ? psi1 : psi0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) old_sq[i] = psi[i].x * psi[i].x + psi[i].y * psi[i].y;
+}
+
+// Link variables for A = A_applied + A_induced (solver.py:670-673): theta holds A_applied . d
+// (times ramp_f under a device-side ramp), aind the current induced potential.
+__global__ void __launch_bounds__(kBlock)
+k_link_values_scr(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+                  const int* __restrict__ eidx, const signed char* __restrict__ head,
+                  const double* __restrict__ weight, const double* __restrict__ theta,
+                  const double2* __restrict__ aind, const double2* __restrict__ edir,
+                  const double* __restrict__ areas, double2* __restrict__ lval) {
+  griddep_enter();
+  if (ctl->status != 0) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double f = ctl->ramp_on ? ctl->ramp_f : 1.0;
+  double diag = 0.0;
+  int kd = -1;
+  for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
+    const int e = eidx[k];
+    if (e < 0) { kd = k; continue; }
+    const double w = weight[e];
+    const double th = f * theta[e] + aind[e].x * edir[e].x + aind[e].y * edir[e].y;
+    double s, c;
+    sincos(-th, &s, &c);
+    if (!head[k]) s = -s;
+    lval[k] = make_double2(w * c / areas[row], w * s / areas[row]);
+    diag += -w / areas[row];
+  }
+  if (kd >= 0) lval[kd] = make_double2(diag, 0.0);
+}
+
+// w_i = a~_i * J_site[i], J_site[i] = (1/2) mean over the edges at site i of (J_s + J_n)[e] e_hat
+// (Mesh.get_quantity_on_site, mesh.py:203-243).  One thread per site walks its incident edges
+// and evaluates each edge's current on the fly (operators.py:385-394, solver.py:519): no
+// edge-sized temporary, fixed summation order.
+__global__ void __launch_bounds__(kBlock)
+k_scr_site_current(const Ctl* __restrict__ ctl, int n, const int* __restrict__ ptr,
+                   const int* __restrict__ nbr, const int* __restrict__ eidx,
+                   const signed char* __restrict__ head, const double* __restrict__ elen,
+                   const double* __restrict__ theta, const double2* __restrict__ aind,
+                   const double2* __restrict__ edir, const double2* __restrict__ psi0,
+                   const double2* __restrict__ psi1, const double* __restrict__ mu,
+                   const double* __restrict__ dadt /* may be null */,
+                   const double* __restrict__ ramp_proj /* may be null */,
+                   const double* __restrict__ scr_area, double2* __restrict__ wsite) {
+  griddep_enter();
+  if (ctl->status != 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2* psi = ctl->cur ? psi1 : psi0;
+  const double f = ctl->ramp_on ? ctl->ramp_f : 1.0;
+  double sx = 0.0, sy = 0.0;
+  int cnt = 0;
+  for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
+    const int e = eidx[k];
+    if (e < 0) continue;
+    const int j = nbr[k];
+    const int a = head[k] ? i : j, b = head[k] ? j : i;   // the edge runs a -> b
+    const double inv_l = 1.0 / elen[e];
+    const double th = f * theta[e] + aind[e].x * edir[e].x + aind[e].y * edir[e].y;
+    double s, c;
+    sincos(-th, &s, &c);
+    const double2 pa = psi[a], pb = psi[b];
+    const double gx = (c * pb.x - s * pb.y) * inv_l - pa.x * inv_l;
+    const double gy = (c * pb.y + s * pb.x) * inv_l - pa.y * inv_l;
+    const double js = pa.x * gy - pa.y * gx;
+    double da = dadt != nullptr ? dadt[e] : 0.0;
+    if (ramp_proj != nullptr) da = ctl->ramp_dfdt * ramp_proj[e];
+    const double jn = -(mu[b] * inv_l - mu[a] * inv_l) - da;
+    const double J = js + jn;
+    const double dl = sqrt(edir[e].x * edir[e].x + edir[e].y * edir[e].y);
+    sx += J * (edir[e].x / dl);
+    sy += J * (edir[e].y / dl);
+    ++cnt;
+  }
+  const double sc = cnt > 0 ? scr_area[i] / (2.0 * cnt) : 0.0;
+  wsite[i] = make_double2(sx * sc, sy * sc);
+}
+
+// A_new[e] = sum_j w_j / |c_e - r_j|: all-pairs sum, tiled through shared memory (one tile of
+// kScrTile sites = positions + weights, 32 bytes per site, is read once per CTA and used by
+// every edge of the CTA).  Each thread owns one edge and adds the sites in index order, so the
+// result does not depend on the launch geometry.  fp64 compute-bound (sqrt + divide per
+// pair): the reference's algorithm is O(E N) and so is this.
+constexpr int kScrTile = 128;
+__global__ void __launch_bounds__(kScrTile)
+k_scr_a_induced(const Ctl* __restrict__ ctl, int n_edges, int n_sites,
+                const double2* __restrict__ ecent, const double2* __restrict__ sxy,
+                const double2* __restrict__ wsite, double2* __restrict__ a_new) {
+  griddep_enter();
+  __shared__ double2 s_r[kScrTile];
+  __shared__ double2 s_w[kScrTile];
+  if (ctl->status != 0) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const double2 c = e < n_edges ? ecent[e] : make_double2(0.0, 0.0);
+  double ax = 0.0, ay = 0.0;
+  for (int j0 = 0; j0 < n_sites; j0 += kScrTile) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    s_r[threadIdx.x] = j < n_sites ? sxy[j] : make_double2(1e300, 1e300);
+    s_w[threadIdx.x] = j < n_sites ? wsite[j] : make_double2(0.0, 0.0);
+    __syncthreads();
+    const int m = min(kScrTile, n_sites - j0);
+#pragma unroll 4
+    for (int t = 0; t < m; ++t) {
+      const double dx = c.x - s_r[t].x, dy = c.y - s_r[t].y;
+      const double inv = 1.0 / sqrt(dx * dx + dy * dy);
+      ax = fma(s_w[t].x, inv, ax);
+      ay = fma(s_w[t].y, inv, ay);
+    }
+  }
+  if (e < n_edges) a_new[e] = make_double2(ax, ay);
+}
+
+// Polyak update (solver.py:564-577): dA = A_new - A ; v = (1 - beta) v + alpha dA ; A += v ;
+// error = max_e |dA_e| / max(|A_e|, 1e-20).  The velocity starts from 0 in every time step.
+__global__ void __launch_bounds__(kBlock)
+k_scr_polyak(Ctl* ctl, int n_edges, const double2* __restrict__ a_new, double2* __restrict__ aind,
+             double2* __restrict__ vel) {
+  griddep_enter();
+  __shared__ double s_max[8];
+  if (ctl->status != 0) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool first = ctl->scr_it == 0;
+  double err = 0.0;
+  if (e < n_edges) {
+    const double2 a = aind[e], an = a_new[e];
+    const double2 v0 = first ? make_double2(0.0, 0.0) : vel[e];
+    const double dx = an.x - a.x, dy = an.y - a.y;
+    const double2 v = make_double2((1.0 - ctl->scr_beta) * v0.x + ctl->scr_alpha * dx,
+                                   (1.0 - ctl->scr_beta) * v0.y + ctl->scr_alpha * dy);
+    const double2 a1 = make_double2(a.x + v.x, a.y + v.y);
+    vel[e] = v;
+    aind[e] = a1;
+    err = sqrt(dx * dx + dy * dy) / fmax(sqrt(a1.x * a1.x + a1.y * a1.y), 1e-20);
+    if (!(err == err)) err = 1e300;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = err;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = s_max[0];
+    for (int k = 1; k < static_cast<int>(blockDim.x >> 5); ++k) mx = fmax(mx, s_max[k]);
+    if (mx > 0.0) atomicMax(&ctl->scr_err_bits, (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+// Loop control of the screening iteration (solver.py:654-663): stop when the error is below
+// the tolerance; give up (status 4) after max_iterations_per_step passes.  Re-arms the
+// per-pass state of the psi step (adaptive_euler_step starts with retries = 0 every pass).
+__global__ void k_scr_control(Ctl* ctl, cudaGraphConditionalHandle cond_scr,
+                              cudaGraphConditionalHandle cond_psi) {
+  griddep_enter();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int go = 0;
+  if (ctl->status == 0) {
+    const double err = __longlong_as_double((long long)ctl->scr_err_bits);
+    ctl->scr_err = err;
+    ctl->scr_it += 1;
+    ctl->total_scr_it += 1;
+    if (!(err < ctl->scr_tol)) {
+      if (ctl->scr_it > ctl->scr_max_it) {
+        ctl->status = 4;
+        ctl->failed_step = ctl->step;
+        ctl->failed_dt = ctl->dt;
+      } else {
+        go = 1;
+        ctl->scr_err_bits = 0ull;
+        ctl->retries = 0;
+        ctl->disc_flag = 0;
+        ctl->max_dpsi_bits = 0ull;
+        ctl->solve_epoch += 1;
+      }
+    }
+  }
+  ctl->scr_go = go;
+  ctl->psi_go = go;
+  set_cond(cond_scr, go);
+  set_cond(cond_psi, go);
 }
 
 template <typename T>

@@ -1,6 +1,9 @@
 // tdgl_b200: engine implementation + C ABI (see include/tdgl_b200.h).
 #include "../../include/tdgl_b200.h"
 
+#include <cusparse.h>   // types only: the comparator dlopen()s the library (time_cusparse)
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -207,6 +210,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     if (!(a_int[i] > 0)) throw std::invalid_argument("non-positive site area");
   }
   for (int i = 0; i < Ng_; ++i) total_area_ += a_int[i];
+  h_areas_int_ = a_int;
 
   SiteGraph g = build_site_graph(Ng_, E_, e0.data(), e1.data());
 
@@ -537,7 +541,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       cudaGetLastError();
       if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
       if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
-      h_step_ = h_psi_ = h_cg_ = 0;
+      h_step_ = h_psi_ = h_cg_ = h_scr_ = 0;
       if (std::getenv("TDGL_B200_VERBOSE")) fprintf(stderr, "[tdgl_b200] %s\n", last_error.c_str());
     }
   }
@@ -605,7 +609,7 @@ void Engine::comm_connect_local(Engine* const* engines) {
     if (graph_mode_ == 1) {
       cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
       cudaGraphDestroy(graph_); graph_ = nullptr;
-      h_step_ = h_psi_ = h_cg_ = 0;
+      h_step_ = h_psi_ = h_cg_ = h_scr_ = 0;
       comm_on_ = true;
       build_graph();
     }
@@ -822,16 +826,18 @@ void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
   // matrices are static — except under a device-side ramp, where k_link_values_ramp has just
   // rewritten the Laplacian values: then this launch is an ordinary (fully ordered) one.
   const bool pdl_saved = pdl_;
-  if (ramp_on_) pdl_ = false;
+  if (ramp_on_ || scr_on_) pdl_ = false;   // (screening rewrites them every pass, too)
   struct Restore { bool& ref; bool v; ~Restore() { ref = v; } } restore{pdl_, pdl_saved};
   if (comm_on_)
     launch_k(kw_psi_step<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
              ctl_.p, comm(), make_psi_comm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
-             psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override);
+             psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override,
+             scr_on_ ? old_sq_.p : nullptr);
   else
     launch_k(kw_psi_step<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
              ctl_.p, comm(), PsiComm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
-             psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override);
+             psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override,
+             scr_on_ ? old_sq_.p : nullptr);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -961,33 +967,54 @@ void Engine::build_graph() {
   cudaGraph_t step_body = root.add_while(h_step_);
 
   GraphBuilder sb{step_body, stream_, {}};
+  if (scr_on_)
+    TDGL_CUDA(cudaGraphConditionalHandleCreate(&h_scr_, graph_, 0, cudaGraphCondAssignDefault));
   sb.capture([&] {
-    launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_);
+    launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_, h_scr_);
     TDGL_LAUNCH_CHECK();
     enqueue_ramp_links();
-  });
-  cudaGraph_t psi_body = sb.add_while(h_psi_);
-  {
-    GraphBuilder pb{psi_body, stream_, {}};
-    pb.capture([&] {
-      enqueue_psi_step(nullptr, -1.0);
-      launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), h_psi_);
+    if (scr_on_) {
+      launch_k(k_scr_old_sq, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, psi_[0].p, psi_[1].p, old_sq_.p);
       TDGL_LAUNCH_CHECK();
-    });
-  }
-  sb.capture([&] {
-    enqueue_mu_rhs(nullptr);
-    enqueue_solve_begin(h_cg_);
+    }
   });
-  cudaGraph_t cg_body = sb.add_while(h_cg_);
-  {
-    GraphBuilder cb{cg_body, stream_, {}};
-    cb.capture([&] { enqueue_cg_iteration(h_cg_); });
+  // one pass of psi step + mu solve; with screening it is the body of the Polyak loop
+  auto pass = [&](GraphBuilder& gb) {
+    if (scr_on_) gb.capture([&] { enqueue_screening_pass_begin(); });
+    cudaGraph_t psi_body = gb.add_while(h_psi_);
+    {
+      GraphBuilder pb{psi_body, stream_, {}};
+      pb.capture([&] {
+        enqueue_psi_step(nullptr, -1.0);
+        launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), h_psi_);
+        TDGL_LAUNCH_CHECK();
+      });
+    }
+    gb.capture([&] {
+      enqueue_mu_rhs(nullptr);
+      enqueue_solve_begin(h_cg_);
+    });
+    cudaGraph_t cg_body = gb.add_while(h_cg_);
+    {
+      GraphBuilder cb{cg_body, stream_, {}};
+      cb.capture([&] { enqueue_cg_iteration(h_cg_); });
+    }
+    gb.capture([&] {
+      enqueue_mu_finish();
+      if (scr_on_) enqueue_screening_pass_end(h_scr_, h_psi_);
+    });
+  };
+  if (scr_on_) {
+    cudaGraph_t scr_body = sb.add_while(h_scr_);
+    GraphBuilder cb{scr_body, stream_, {}};
+    pass(cb);
+  } else {
+    pass(sb);
   }
   sb.capture([&] {
-    enqueue_mu_finish();
     launch_k(k_step_end, 1, kMaxProbes, 0, ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
-                                            run_dt_.p, run_mu_.p, run_theta_.p, h_step_);
+                                            run_dt_.p, run_mu_.p, run_theta_.p,
+                                            scr_on_ ? run_scr_.p : nullptr, h_step_);
     TDGL_LAUNCH_CHECK();
   });
   launches_ = launches_before;  // captured, not launched
@@ -1012,6 +1039,102 @@ void Engine::enqueue_ramp_links() {
   if (!ramp_on_) return;
   launch_k(k_link_values_ramp, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, ptr_.p, eidx_.p,
            head_.p, weight_.p, theta_.p, areas_.p, lval_.p);
+  TDGL_LAUNCH_CHECK();
+}
+
+// ---- screening (row S) -----------------------------------------------------------------------
+// tdgl/solver/solver.py:304-314 (scales), 522-578 (Polyak step), 650-688 (loop);
+// tdgl/solver/screening.py:12-42 (all-pairs kernel); finite_volume/mesh.py:203-243 (site average).
+//   scale: A_induced = scale * sum_j J_site[j] areas[j] / |edge_centers[e] - sites_xy[j]| with the
+//   coordinates as passed here (the reference passes xi * mesh coordinates and areas scaled by
+//   mu_0 / (4 pi) K0 / A0 * xi^2).
+void Engine::set_screening(int enable, double scale, const double* sites_xy,
+                           const double* edge_centers, double tolerance, int max_iterations,
+                           double step_size, double drag) {
+  if (enable && world_ > 1)
+    throw std::invalid_argument("screening is not available on a sharded engine (all-pairs sum over the whole mesh)");
+  const bool was_on = scr_on_;
+  sync_ctl_to_host();
+  if (!enable) {
+    scr_on_ = false;
+    h_ctl_->scr_on = 0;
+    push_ctl();
+  } else {
+    if (sites_xy == nullptr || edge_centers == nullptr) throw std::invalid_argument("screening needs site and edge-centre coordinates");
+    if (!(tolerance > 0) || !(step_size > 0) || !(drag > 0 && drag <= 1) || max_iterations < 0)
+      throw std::invalid_argument("bad screening parameters");
+    std::vector<double2> sx(N_), ec(E_), ed(E_);
+    std::vector<double> sa(N_);
+    for (int i = 0; i < N_; ++i) {
+      sx[i] = make_double2(sites_xy[2 * perm_[i]], sites_xy[2 * perm_[i] + 1]);
+      sa[i] = scale * h_areas_int_[i];
+    }
+    for (int e = 0; e < E_; ++e) {
+      ec[e] = make_double2(edge_centers[2 * e], edge_centers[2 * e + 1]);
+      ed[e] = make_double2(h_dirs_[2 * e], h_dirs_[2 * e + 1]);
+    }
+    sxy_.upload(sx, stream_);
+    ecent_.upload(ec, stream_);
+    edir_.upload(ed, stream_);
+    scr_area_.upload(sa, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+    if (aind_.n == 0) {
+      aind_.alloc(E_); aind_new_.alloc(E_); vel_.alloc(E_); wsite_.alloc(N_); old_sq_.alloc(N_);
+      run_scr_.alloc(static_cast<size_t>(cfg_.running_capacity));
+      aind_.zero(stream_); vel_.zero(stream_); run_scr_.zero(stream_);
+    }
+    scr_on_ = true;
+    h_ctl_->scr_on = 1;
+    h_ctl_->scr_tol = tolerance;
+    h_ctl_->scr_max_it = max_iterations;
+    h_ctl_->scr_alpha = step_size;
+    h_ctl_->scr_beta = drag;
+    push_ctl();
+  }
+  if (was_on != scr_on_) rebuild_graph();
+}
+
+void Engine::set_induced(const double* A) {
+  if (!scr_on_) throw std::invalid_argument("screening is off");
+  TDGL_CUDA(cudaMemcpyAsync(aind_.p, A, sizeof(double2) * E_, cudaMemcpyHostToDevice, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::get_induced(double* A) {
+  if (!scr_on_) throw std::invalid_argument("screening is off");
+  TDGL_CUDA(cudaMemcpyAsync(A, aind_.p, sizeof(double2) * E_, cudaMemcpyDeviceToHost, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::get_running_screening(int64_t capacity, int64_t* iterations) {
+  const int64_t k = std::min<int64_t>(last_steps_done_, cfg_.running_capacity);
+  if (capacity < k) throw std::invalid_argument("running-state output too small");
+  if (!scr_on_) { for (int64_t i = 0; i < k; ++i) iterations[i] = 0; return; }
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  TDGL_CUDA(cudaMemcpyAsync(iterations, run_scr_.p, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// start of a pass: link variables for A_applied + A_induced (solver.py:670-673)
+void Engine::enqueue_screening_pass_begin() {
+  launch_k(k_link_values_scr, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, ptr_.p, eidx_.p,
+           head_.p, weight_.p, theta_.p, aind_.p, edir_.p, areas_.p, lval_.p);
+  TDGL_LAUNCH_CHECK();
+}
+
+// end of a pass: site currents, all-pairs sum, Polyak update, loop control (solver.py:682-688)
+void Engine::enqueue_screening_pass_end(cudaGraphConditionalHandle cond_scr,
+                                        cudaGraphConditionalHandle cond_psi) {
+  launch_k(k_scr_site_current, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, ptr_.p, idx_.p,
+           eidx_.p, head_.p, elen_.p, theta_.p, aind_.p, edir_.p, psi_[0].p, psi_[1].p, mu_.p,
+           has_dadt_ ? dadt_.p : nullptr, ramp_on_ ? ramp_proj_.p : nullptr, scr_area_.p, wsite_.p);
+  TDGL_LAUNCH_CHECK();
+  launch_k(k_scr_a_induced, (E_ + kScrTile - 1) / kScrTile, kScrTile, 0, ctl_.p, E_, N_, ecent_.p,
+           sxy_.p, wsite_.p, aind_new_.p);
+  TDGL_LAUNCH_CHECK();
+  launch_k(k_scr_polyak, (E_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, E_, aind_new_.p, aind_.p, vel_.p);
+  TDGL_LAUNCH_CHECK();
+  launch_k(k_scr_control, 1, 32, 0, ctl_.p, cond_scr, cond_psi);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -1063,15 +1186,18 @@ void Engine::set_ramp(const double* A0, int n_knots, const double* t_knots, cons
     h_ctl_->ramp_changed = 2;   // the first step builds the link variables
     push_ctl();
   }
-  if (was_on != ramp_on_ && graph_mode_ == 1) {   // the step sequence changed: re-record it
-    cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
-    cudaGraphDestroy(graph_); graph_ = nullptr;
-    h_step_ = h_psi_ = h_cg_ = 0;
-    const bool on = comm_on_;
-    comm_on_ = world_ > 1;
-    build_graph();
-    comm_on_ = on;
-  }
+  if (was_on != ramp_on_) rebuild_graph();   // the step sequence changed: re-record it
+}
+
+void Engine::rebuild_graph() {
+  if (graph_mode_ != 1) return;
+  cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
+  cudaGraphDestroy(graph_); graph_ = nullptr;
+  h_step_ = h_psi_ = h_cg_ = h_scr_ = 0;
+  const bool on = comm_on_;
+  comm_on_ = world_ > 1;
+  build_graph();
+  comm_on_ = on;
 }
 
 void Engine::set_epsilon(const double* eps) {
@@ -1184,6 +1310,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   h_ctl_->failed_dt = 0.0;
   h_ctl_->total_retries = 0;
   h_ctl_->total_cg_it = 0;
+  h_ctl_->total_scr_it = 0;
   TDGL_CUDA(cudaMemcpyAsync(ctl_.p, h_ctl_, sizeof(Ctl), cudaMemcpyHostToDevice, stream_));
   TDGL_CUDA(cudaEventRecord(ev0_, stream_));
   if (graph_mode_ == 1) {
@@ -1194,25 +1321,44 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     const int64_t L = static_cast<int64_t>(levels_.size());
     const int64_t ex_step = 0, ex_it = world_ > 1 ? 1 : 0;  // (the all-gather unpack of level rep)
     const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
-    launches_ += h_ctl_->steps_done * (7 + ex_step + (ramp_on_ ? 1 : 0)) + h_ctl_->total_retries * 2 +
+    const int64_t passes = scr_on_ ? h_ctl_->total_scr_it : h_ctl_->steps_done;
+    // per step: k_step_begin, k_step_end (+ ramp links, + |psi|^2 snapshot); per pass: psi step +
+    // control, rhs, cg_begin, mu_guess, weighted_sum, shift (+ 5 screening kernels); per dt
+    // retry: psi step + control; per CG iteration: V-cycle (4 per level + coarsest) + SpMV + update
+    launches_ += h_ctl_->steps_done * (2 + ex_step + (ramp_on_ ? 1 : 0) + (scr_on_ ? 1 : 0)) +
+                 passes * (7 + (scr_on_ ? 5 : 0)) + h_ctl_->total_retries * 2 +
                  h_ctl_->total_cg_it * (2 + 4 * split + 1 + ex_it);
   } else {
     while (true) {
-      launch_k(k_step_begin, 1, 32, 0, ctl_.p, 0);
+      launch_k(k_step_begin, 1, 32, 0, ctl_.p, 0, 0);
       TDGL_LAUNCH_CHECK();
       enqueue_ramp_links();
-      do {
-        enqueue_psi_step(nullptr, -1.0);
-        launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), 0);
+      if (scr_on_) {
+        launch_k(k_scr_old_sq, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, psi_[0].p, psi_[1].p, old_sq_.p);
         TDGL_LAUNCH_CHECK();
-        sync_ctl_to_host();
-      } while (h_ctl_->psi_go);
-      if (h_ctl_->status != 0) break;
-      enqueue_mu_rhs(nullptr);
-      host_solve_loop(true);
-      enqueue_mu_finish();
+      }
+      bool failed = false;
+      do {   // (one pass; the Polyak loop of the screening iteration when screening is on)
+        if (scr_on_) enqueue_screening_pass_begin();
+        do {
+          enqueue_psi_step(nullptr, -1.0);
+          launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), 0);
+          TDGL_LAUNCH_CHECK();
+          sync_ctl_to_host();
+        } while (h_ctl_->psi_go);
+        if (h_ctl_->status != 0) { failed = true; break; }
+        enqueue_mu_rhs(nullptr);
+        host_solve_loop(true);
+        enqueue_mu_finish();
+        if (scr_on_) {
+          enqueue_screening_pass_end(0, 0);
+          sync_ctl_to_host();
+        }
+      } while (scr_on_ && h_ctl_->scr_go);
+      if (failed || h_ctl_->status != 0) break;
       launch_k(k_step_end, 1, kMaxProbes, 0, ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
-                                              run_dt_.p, run_mu_.p, run_theta_.p, 0);
+                                              run_dt_.p, run_mu_.p, run_theta_.p,
+                                              scr_on_ ? run_scr_.p : nullptr, 0);
       TDGL_LAUNCH_CHECK();
       sync_ctl_to_host();
       if (!h_ctl_->step_go) break;
@@ -1237,6 +1383,8 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   info.retries = h_ctl_->total_retries;
   info.mu_iterations = h_ctl_->total_cg_it;
   info.mu_rel_residual = h_ctl_->bb > 0 ? std::sqrt(h_ctl_->rr / h_ctl_->bb) : 0.0;
+  info.screening_iterations = h_ctl_->total_scr_it;
+  info.screening_error = h_ctl_->scr_err;
   return info;
 }
 
@@ -1265,7 +1413,8 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
-        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, tmp_e_.p, tmp_e2_.p);
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
+        tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
     if (js != nullptr) tmp_e_.download(js, E_, stream_);
     if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
@@ -1292,7 +1441,8 @@ void Engine::stage_outputs(int what, void** ptrs, int64_t* counts) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
-        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, tmp_e_.p, tmp_e2_.p);
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
+        tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
   }
   TDGL_CUDA(cudaStreamSynchronize(stream_));
@@ -1334,7 +1484,8 @@ void Engine::get_currents(double* js, double* jn) {
   unpack_state_halos(cur);
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
       E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
-        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, tmp_e_.p, tmp_e2_.p);
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
+        tmp_e_.p, tmp_e2_.p);
   TDGL_LAUNCH_CHECK();
   if (js != nullptr) tmp_e_.download(js, E_, stream_);
   if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
@@ -1411,7 +1562,7 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
   push_ctl();
   launch_k(kw_psi_step<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
            ctl_.p, static_cast<const Comm*>(nullptr), PsiComm(), site_csr(), lval_.p, fixed_.p, pin.p,
-           pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p, dt);
+           pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p, dt, static_cast<const double*>(nullptr));
   TDGL_LAUNCH_CHECK();
   k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, pout.p, tmp_c_.p);
   TDGL_LAUNCH_CHECK();
@@ -1600,6 +1751,75 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
   return total_ms / reps;
 }
 
+// cuSPARSE comparator (measurement only; see include/tdgl_b200.h).  The library is opened
+// here and nowhere else.
+double Engine::time_cusparse(int which, int reps, int flush_l2) {
+  if (world_ > 1) throw std::invalid_argument("the cuSPARSE comparator runs on a single shard");
+  if (which < 0 || which > 1) throw std::invalid_argument("unknown comparator id");
+  if (reps < 1) reps = 1;
+  void* lib = dlopen("libcusparse.so.12", RTLD_NOW | RTLD_LOCAL);
+  if (lib == nullptr) lib = dlopen("libcusparse.so", RTLD_NOW | RTLD_LOCAL);
+  if (lib == nullptr) throw std::invalid_argument("libcusparse not found (comparator unavailable)");
+  struct Closer { void* l; ~Closer() { dlclose(l); } } closer{lib};
+#define TDGL_SYM(name) auto p_##name = reinterpret_cast<decltype(&name)>(dlsym(lib, #name)); \
+  if (p_##name == nullptr) throw std::invalid_argument("libcusparse lacks " #name)
+  TDGL_SYM(cusparseCreate); TDGL_SYM(cusparseDestroy); TDGL_SYM(cusparseSetStream);
+  TDGL_SYM(cusparseCreateCsr); TDGL_SYM(cusparseDestroySpMat); TDGL_SYM(cusparseCreateDnVec);
+  TDGL_SYM(cusparseDestroyDnVec); TDGL_SYM(cusparseSpMV_bufferSize); TDGL_SYM(cusparseSpMV);
+#undef TDGL_SYM
+  auto ok = [](cusparseStatus_t st, const char* what) {
+    if (st != CUSPARSE_STATUS_SUCCESS) throw std::runtime_error(std::string("cuSPARSE: ") + what + " failed");
+  };
+  cusparseHandle_t hs = nullptr;
+  ok(p_cusparseCreate(&hs), "cusparseCreate");
+  ok(p_cusparseSetStream(hs, stream_), "cusparseSetStream");
+  const bool cplx = which == 1;
+  const cudaDataType dt = cplx ? CUDA_C_64F : CUDA_R_64F;
+  DevBuf<double2> xc, yc;
+  DevBuf<double> xr, yr;
+  void *x = nullptr, *y = nullptr;
+  if (cplx) { xc.alloc(N_); yc.alloc(N_); xc.zero(stream_); x = xc.p; y = yc.p; }
+  else { xr.alloc(N_); yr.alloc(N_); xr.zero(stream_); x = xr.p; y = yr.p; }
+  cusparseSpMatDescr_t A = nullptr;
+  cusparseDnVecDescr_t vx = nullptr, vy = nullptr;
+  ok(p_cusparseCreateCsr(&A, N_, N_, nnz_, ptr_.p, idx_.p, cplx ? static_cast<void*>(lval_.p) : static_cast<void*>(aval_.p),
+                         CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, dt), "cusparseCreateCsr");
+  ok(p_cusparseCreateDnVec(&vx, N_, x, dt), "cusparseCreateDnVec");
+  ok(p_cusparseCreateDnVec(&vy, N_, y, dt), "cusparseCreateDnVec");
+  const double2 one_c = make_double2(1.0, 0.0), zero_c = make_double2(0.0, 0.0);
+  const double one_r = 1.0, zero_r = 0.0;
+  const void* alpha = cplx ? static_cast<const void*>(&one_c) : static_cast<const void*>(&one_r);
+  const void* beta = cplx ? static_cast<const void*>(&zero_c) : static_cast<const void*>(&zero_r);
+  size_t ws = 0;
+  ok(p_cusparseSpMV_bufferSize(hs, CUSPARSE_OPERATION_NON_TRANSPOSE, alpha, A, vx, beta, vy, dt,
+                               CUSPARSE_SPMV_ALG_DEFAULT, &ws), "cusparseSpMV_bufferSize");
+  DevBuf<char> work;
+  work.alloc(std::max<size_t>(ws, 16));
+  auto one = [&]() {
+    ok(p_cusparseSpMV(hs, CUSPARSE_OPERATION_NON_TRANSPOSE, alpha, A, vx, beta, vy, dt,
+                      CUSPARSE_SPMV_ALG_DEFAULT, work.p), "cusparseSpMV");
+  };
+  const size_t flush_n = (256u << 20) / sizeof(double);
+  if (flush_l2 && flush_.n == 0) { flush_.alloc(flush_n); flush_.zero(stream_); }
+  one();  // warm-up (cuSPARSE may analyse the matrix on the first call)
+  one();
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  double total_ms = 0.0;
+  for (int i = 0; i < reps; ++i) {
+    if (flush_l2) k_flush_l2<<<1184, kBlock, 0, stream_>>>(flush_.p, flush_n, flush_.p);
+    TDGL_CUDA(cudaEventRecord(ev0_, stream_));
+    one();
+    TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+    TDGL_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0.f;
+    TDGL_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    total_ms += ms;
+  }
+  p_cusparseDestroyDnVec(vx); p_cusparseDestroyDnVec(vy); p_cusparseDestroySpMat(A);
+  p_cusparseDestroy(hs);
+  return total_ms / reps;
+}
+
 void Engine::get_info(int64_t* out, int n) {
   const int64_t vals[8] = {Ng_, E_, nnz_, static_cast<int64_t>(levels_.size()), amg_nnz_, nc_,
                            launches_, graph_mode_};
@@ -1743,6 +1963,31 @@ int tdgl_set_vector_potential_ramp(tdgl_handle* h, const double* A0, int32_t n_k
     e.set_ramp(A0, n_knots, t_knots, f_knots);
   });
 }
+int tdgl_set_screening(tdgl_handle* h, int32_t enable, double scale, const double* sites_xy,
+                       const double* edge_centers, double tolerance, int32_t max_iterations,
+                       double step_size, double step_drag) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    e.set_screening(enable, scale, sites_xy, edge_centers, tolerance, max_iterations, step_size, step_drag);
+  });
+}
+int tdgl_set_induced_vector_potential(tdgl_handle* h, const double* A_induced) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (A_induced == nullptr) throw std::invalid_argument("null A_induced");
+    e.set_induced(A_induced);
+  });
+}
+int tdgl_get_induced_vector_potential(tdgl_handle* h, double* A_induced) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (A_induced == nullptr) throw std::invalid_argument("null A_induced");
+    e.get_induced(A_induced);
+  });
+}
+int tdgl_get_running_screening(tdgl_handle* h, int64_t capacity, int64_t* iterations) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (iterations == nullptr) throw std::invalid_argument("null output");
+    e.get_running_screening(capacity, iterations);
+  });
+}
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu) {
   return guarded(h, [&](tdgl::Engine& e) { e.set_state(psi, mu); });
 }
@@ -1766,6 +2011,7 @@ int tdgl_advance(tdgl_handle* h, int64_t max_steps, double t_end, int64_t step, 
       info->failed_step = r.failed_step; info->failed_dt = r.failed_dt; info->retries = r.retries;
       info->mu_iterations = r.mu_iterations; info->mu_rel_residual = r.mu_rel_residual;
       info->device_ms = r.device_ms;
+      info->screening_iterations = r.screening_iterations; info->screening_error = r.screening_error;
     }
     status = r.status;
   });
@@ -1786,6 +2032,7 @@ int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t ste
       info->failed_step = r.failed_step; info->failed_dt = r.failed_dt; info->retries = r.retries;
       info->mu_iterations = r.mu_iterations; info->mu_rel_residual = r.mu_rel_residual;
       info->device_ms = r.device_ms;
+      info->screening_iterations = r.screening_iterations; info->screening_error = r.screening_error;
     }
     status = r.status;
   });
@@ -1855,6 +2102,13 @@ int tdgl_time_kernel(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_
                      double* mean_ms) {
   return guarded(h, [&](tdgl::Engine& e) {
     const double ms = e.time_kernel(which, reps, flush_l2);
+    if (mean_ms != nullptr) *mean_ms = ms;
+  });
+}
+int tdgl_time_cusparse(tdgl_handle* h, int32_t which, int32_t reps, int32_t flush_l2,
+                       double* mean_ms) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    const double ms = e.time_cusparse(which, reps, flush_l2);
     if (mean_ms != nullptr) *mean_ms = ms;
   });
 }

@@ -21,6 +21,11 @@ class StepFailed(RuntimeError):
     solver.py:478-483)."""
 
 
+class ScreeningFailed(RuntimeError):
+    """The screening iteration did not converge in ``max_iterations_per_step`` passes
+    (reference RuntimeError, solver.py:657-663)."""
+
+
 class AdvanceInfo(NamedTuple):
     steps_done: int
     step: int
@@ -35,6 +40,8 @@ class AdvanceInfo(NamedTuple):
     mu_iterations: int
     mu_rel_residual: float
     device_ms: float = 0.0
+    screening_iterations: int = 0
+    screening_error: float = 0.0
 
 
 class _PinnedBlock:
@@ -201,6 +208,28 @@ class DeviceEngine:
         self._check(self._lib.tdgl_set_vector_potential_ramp(
             self._h, ptr(as_f64(A0, (self.n_edges, 2))), len(t), ptr(t), ptr(f)))
 
+    def set_screening(self, scale: float, sites_xy, edge_centers, *, tolerance: float,
+                      max_iterations: int, step_size: float, step_drag: float) -> None:
+        """Turn on the screening iteration (include/tdgl_b200.h, tdgl_set_screening)."""
+        self._check(self._lib.tdgl_set_screening(
+            self._h, 1, float(scale), ptr(as_f64(sites_xy, (self.n_sites, 2))),
+            ptr(as_f64(edge_centers, (self.n_edges, 2))), float(tolerance), int(max_iterations),
+            float(step_size), float(step_drag)))
+
+    def set_induced_vector_potential(self, A) -> None:
+        self._check(self._lib.tdgl_set_induced_vector_potential(
+            self._h, ptr(as_f64(A, (self.n_edges, 2)))))
+
+    def get_induced_vector_potential(self) -> np.ndarray:
+        A = np.empty((self.n_edges, 2))
+        self._check(self._lib.tdgl_get_induced_vector_potential(self._h, ptr(A)))
+        return A
+
+    def get_running_screening(self, steps: int) -> np.ndarray:
+        its = np.zeros(max(int(steps), 1), dtype=np.int64)
+        self._check(self._lib.tdgl_get_running_screening(self._h, len(its), ptr(its)))
+        return its[:steps]
+
     def set_state(self, psi, mu) -> None:
         self._check(self._lib.tdgl_set_state(
             self._h, ptr(as_c128(psi, (self.n_sites,))), ptr(as_f64(mu, (self.n_sites,)))))
@@ -218,9 +247,12 @@ class DeviceEngine:
                                     float(time), C.byref(info))
         out = AdvanceInfo(info.steps_done, info.step, info.time, info.dt, info.tentative_dt,
                           bool(info.finished), info.status, info.failed_step, info.failed_dt,
-                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms)
+                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms,
+                          info.screening_iterations, info.screening_error)
         if rc == _lib.TDGL_E_STEP_FAILED:
             raise StepFailed(f"step {out.failed_step} dt {out.failed_dt:.2e}", out)
+        if out.status == 4:
+            raise ScreeningFailed(f"step {out.failed_step}", out)
         self._check(rc)
         return out
 
@@ -239,9 +271,12 @@ class DeviceEngine:
                                    C.byref(info))
         res = AdvanceInfo(info.steps_done, info.step, info.time, info.dt, info.tentative_dt,
                           bool(info.finished), info.status, info.failed_step, info.failed_dt,
-                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms)
+                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms,
+                          info.screening_iterations, info.screening_error)
         if rc == _lib.TDGL_E_STEP_FAILED:
             raise StepFailed(f"step {res.failed_step} dt {res.failed_dt:.2e}", res)
+        if res.status == 4:
+            raise ScreeningFailed(f"step {res.failed_step}", res)
         self._check(rc)
         return res, out
 
@@ -303,6 +338,13 @@ class DeviceEngine:
         ms = C.c_double(0)
         self._check(self._lib.tdgl_time_kernel(self._h, int(which), int(reps),
                                                1 if flush_l2 else 0, C.byref(ms)))
+        return ms.value
+
+    def time_cusparse(self, which: int, reps: int = 20, flush_l2: bool = True) -> float:
+        """cusparseSpMV on the engine's CSR arrays (comparator; 0: real f64, 1: complex128)."""
+        ms = C.c_double(0)
+        self._check(self._lib.tdgl_time_cusparse(self._h, int(which), int(reps),
+                                                 1 if flush_l2 else 0, C.byref(ms)))
         return ms.value
 
     def info(self) -> dict:

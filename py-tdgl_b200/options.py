@@ -92,10 +92,10 @@ class SolverOptions:
                 raise SolverOptionsError(
                     f"sparse solver must be one of {valid!r}, got {solver}.")
             self.sparse_solver = solver
-        if self.include_screening:
+        if self.include_screening and self.distributed:
             raise SolverOptionsError(
-                "include_screening=True is not supported by the B200 engine yet"
-                " (SURVEY.md §8 row S, scheduled after the hot path).")
+                "include_screening=True is not available with distributed=True: the induced"
+                " vector potential is an all-pairs sum over the whole mesh.")
         if not (self.mu_rtol > 0):
             raise SolverOptionsError(f"mu_rtol must be > 0 (got {self.mu_rtol}).")
         if self.adaptive_window < 1 or self.adaptive_window > 1024:

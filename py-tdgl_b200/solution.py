@@ -99,7 +99,7 @@ class SavedSteps:
     def dynamics(self) -> Optional[DynamicsData]:
         """Concatenate the running-state buffers exactly as ``DynamicsData.from_hdf5``
         does (data.py:396-425): unfilled entries have dt == 0 and are dropped."""
-        dts, mus, thetas = [], [], []
+        dts, mus, thetas, sits = [], [], [], []
         for grp in self.groups:
             rs = grp.get("running_state")
             if rs is None:
@@ -109,13 +109,16 @@ class SavedSteps:
                 mus.append(np.atleast_2d(rs["mu"]))
             if "theta" in rs:
                 thetas.append(np.atleast_2d(rs["theta"]))
+            if "screening_iterations" in rs:
+                sits.append(np.atleast_1d(rs["screening_iterations"]))
         if not dts:
             return None
         dt = np.concatenate(dts)
         mask = dt > 0
         mu = np.concatenate(mus, axis=1)[..., mask] if mus else None
         theta = np.concatenate(thetas, axis=1)[..., mask] if thetas else None
-        return DynamicsData(dt=dt[mask], mu=mu, theta=theta)
+        sit = np.concatenate(sits)[mask] if sits else None
+        return DynamicsData(dt=dt[mask], mu=mu, theta=theta, screening_iterations=sit)
 
 
 class Solution:

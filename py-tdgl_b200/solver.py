@@ -18,7 +18,7 @@ from typing import Callable, Dict, NamedTuple, Optional, Sequence, Union
 
 import numpy as np
 
-from .engine import DeviceEngine, StepFailed
+from .engine import DeviceEngine, ScreeningFailed, StepFailed
 from .options import SolverOptions
 from .solution import SavedSteps, Solution
 from .synthetic import TerminalInfo
@@ -203,10 +203,19 @@ class TDGLSolver:
 
             static_currents = True
         J_scale = scales.J_scale
+        screening = None
+        if options.include_screening:
+            # solver.py:306-309: A_scale = mu_0 / (4 pi) K0 / A0 in 1 / length_units,
+            # areas = A_scale * mesh.areas * xi^2, coordinates in length_units
+            from .device import MU_0, length_scale
+
+            a_scale = MU_0 / (4 * np.pi) * device.K0 / device.A0 * length_scale(device.length_units)
+            screening = (a_scale * xi**2, sites, edge_centers)
         self._setup(mesh, options, A, eval_eps, dynamic_epsilon, terminal_info,
                     lambda t: {k: J_scale * v for k, v in user_func(t).items()},
                     static_currents, device.probe_point_indices, device.layer.u,
-                    device.layer.gamma, eval_A=eval_A if dynamic_A else None, ramp=ramp)
+                    device.layer.gamma, eval_A=eval_A if dynamic_A else None, ramp=ramp,
+                    screening=screening)
 
     @classmethod
     def from_dimensionless(cls, mesh, options: SolverOptions, *, A_applied, epsilon,
@@ -214,14 +223,17 @@ class TDGLSolver:
                            terminal_currents: Union[Callable, Dict[str, float], None] = None,
                            probe_point_indices: Optional[Sequence[int]] = None,
                            u: float = 5.79, gamma: float = 10.0, device=None,
-                           A_ramp=None, seed_solution=None) -> "TDGLSolver":
+                           A_ramp=None, seed_solution=None,
+                           screening_scale: float = 0.0) -> "TDGLSolver":
         """Inputs as the reference holds them after ``__init__``: ``A_applied`` [E, 2] in
         units of xi*Bc2 — or a callable ``t -> [E, 2]`` for a time-dependent vector
         potential (host callback every step, like the reference) — currents already
         multiplied by ``J_scale``.  ``A_ramp = (t_knots, f_knots)`` makes the potential
         ``f(t) * A_applied`` with piecewise-linear f, evaluated on the device.  ``epsilon``
         [N], or a callable ``t -> [N]`` for a time-dependent disorder (the reference's
-        ``disorder_epsilon(r, *, t)``, solver.py:364-381)."""
+        ``disorder_epsilon(r, *, t)``, solver.py:364-381).  With
+        ``options.include_screening``: ``A_induced = screening_scale * sum_j J_j a_j / |c_e -
+        r_j|`` in the mesh's own (dimensionless) coordinates and areas."""
         self = object.__new__(cls)
         self.device = device
         self.options = options
@@ -260,12 +272,14 @@ class TDGLSolver:
             A_applied = eval_A(0.0)
         self._setup(mesh, options, np.asarray(A_applied, float), eval_eps, dynamic_epsilon,
                     tuple(terminal_info), func, static, probe_point_indices, u, gamma,
-                    eval_A=eval_A, ramp=ramp)
+                    eval_A=eval_A, ramp=ramp,
+                    screening=((screening_scale, mesh.sites, mesh.edge_mesh.centers)
+                               if options.include_screening else None))
         return self
 
     # ------------------------------------------------------------------------------------
     def _setup(self, mesh, options, A, eval_eps, dynamic_epsilon, terminal_info, current_func,
-               static_currents, probe_points, u, gamma, eval_A=None, ramp=None):
+               static_currents, probe_points, u, gamma, eval_A=None, ramp=None, screening=None):
         self.mesh = mesh
         self.u, self.gamma = u, gamma
         self.num_edges = len(mesh.edge_mesh.edges)
@@ -320,12 +334,32 @@ class TDGLSolver:
         if ramp is not None:
             self.engine.set_vector_potential_ramp(*ramp)
         self.engine.set_epsilon(epsilon)
+        self.include_screening = screening is not None
+        if screening is not None:
+            self.engine.set_screening(
+                screening[0], screening[1], screening[2], tolerance=options.screening_tolerance,
+                max_iterations=options.max_iterations_per_step,
+                step_size=options.screening_step_size, step_drag=options.screening_step_drag)
         self.engine.set_stepper(
             dt_init=options.dt_init, dt_max=options.dt_max, adaptive=options.adaptive,
             adaptive_window=options.adaptive_window,
             max_solve_retries=options.max_solve_retries,
             adaptive_time_step_multiplier=options.adaptive_time_step_multiplier)
-        self.stats = dict(steps=0, retries=0, mu_iterations=0)
+        self.stats = dict(steps=0, retries=0, mu_iterations=0, screening_iterations=0)
+
+    def _raise_like_reference(self, exc):
+        fi = exc.args[1]
+        if isinstance(exc, ScreeningFailed):                      # solver.py:657-663
+            o = self.options
+            raise RuntimeError(
+                f"Screening calculation failed to converge at step {fi.failed_step} after"
+                f" {o.max_iterations_per_step} iterations. Relative error in"
+                f" induced vector potential: {fi.screening_error:.2e}"
+                f" (tolerance: {o.screening_tolerance:.2e}).") from None
+        raise RuntimeError(                                       # solver.py:479-483
+            f"Solver failed to converge in {self.options.max_solve_retries}"
+            f" retries at step {fi.failed_step} with dt = {fi.failed_dt:.2e}."
+            f" Try using a smaller dt_init.") from None
 
     def update_mu_boundary(self, time: float) -> None:
         """reference solver.py:325-345; uploads only when a density changed."""
@@ -374,22 +408,25 @@ class TDGLSolver:
         if self.dynamic_epsilon:
             self.epsilon = self._eval_eps(time)
             self.engine.set_epsilon(self.epsilon)
+        if self.include_screening and induced_vector_potential is not None:
+            self.engine.set_induced_vector_potential(induced_vector_potential)
         try:
             info, (psi1, mu1, js, jn) = self.engine.update(psi, mu, step, time, out=out)
-        except StepFailed as exc:
-            fi = exc.args[1]
-            raise RuntimeError(
-                f"Solver failed to converge in {self.options.max_solve_retries}"
-                f" retries at step {fi.failed_step} with dt = {fi.failed_dt:.2e}."
-                f" Try using a smaller dt_init.") from None
+        except (StepFailed, ScreeningFailed) as exc:
+            self._raise_like_reference(exc)
+        if self.include_screening:
+            induced_vector_potential = self.engine.get_induced_vector_potential()
         if running_state is not None:
             running_state.append("dt", info.dt)
             if self.probe_points is not None:
                 running_state.append("mu", mu1[self.probe_points])
                 running_state.append("theta", np.angle(psi1[self.probe_points]))
+            if self.include_screening:
+                running_state.append("screening_iterations", info.screening_iterations)
         self.stats["steps"] += 1
         self.stats["retries"] += info.retries
         self.stats["mu_iterations"] += info.mu_iterations
+        self.stats["screening_iterations"] += info.screening_iterations
         if induced_vector_potential is None:
             induced_vector_potential = np.zeros((self.num_edges, 2))
         results = [info.dt, psi1, mu1, js, jn, induced_vector_potential]
@@ -407,7 +444,9 @@ class TDGLSolver:
         psi, mu = self.engine.get_state()
         js, jn = self.engine.get_currents()
         out = {"psi": psi, "mu": mu, "supercurrent": js, "normal_current": jn,
-               "induced_vector_potential": np.zeros((self.num_edges, 2))}
+               "induced_vector_potential": (self.engine.get_induced_vector_potential()
+                                            if self.include_screening
+                                            else np.zeros((self.num_edges, 2)))}
         if self.dynamic_vector_potential:
             out["applied_vector_potential"] = self.current_A_applied
         if self.dynamic_epsilon:
@@ -458,12 +497,8 @@ class TDGLSolver:
                 chunk = 1 if per_step_host else every - (i % every)
                 try:
                     info = self.engine.advance(chunk, end_time, i, time)
-                except StepFailed as exc:
-                    fi = exc.args[1]
-                    raise RuntimeError(
-                        f"Solver failed to converge in {opts.max_solve_retries}"
-                        f" retries at step {fi.failed_step} with dt = {fi.failed_dt:.2e}."
-                        f" Try using a smaller dt_init.") from None
+                except (StepFailed, ScreeningFailed) as exc:
+                    self._raise_like_reference(exc)
                 k = info.steps_done
                 if self._ramp is not None:
                     # the vector potential of the last step taken (saved with the results)
@@ -475,11 +510,15 @@ class TDGLSolver:
                 if self.probe_points is not None:
                     running.values["mu"][:, pos:pos + k] = mu_p
                     running.values["theta"][:, pos:pos + k] = th_p
+                if self.include_screening:
+                    running.values["screening_iterations"][0, pos:pos + k] = \
+                        self.engine.get_running_screening(k)
                 running.step = pos + (k - 1 if info.finished else k)
                 self._prev_dt = info.dt
                 self.stats["steps"] += k
                 self.stats["retries"] += info.retries
                 self.stats["mu_iterations"] += info.mu_iterations
+                self.stats["screening_iterations"] += info.screening_iterations
                 i, time = info.step, info.time
                 if opts.progress_interval and (i // opts.progress_interval
                                                != (i - k) // opts.progress_interval):
@@ -513,6 +552,8 @@ class TDGLSolver:
                      "normal_current": np.array(seed.normal_current),
                      "induced_vector_potential": np.array(seed.induced_vector_potential)}
         self.engine.set_state(psi0, mu0)
+        if self.include_screening:
+            self.engine.set_induced_vector_potential(first["induced_vector_potential"])
         saved = SavedSteps()
         fixed = {}
         if self.dynamic_vector_potential:
@@ -528,6 +569,8 @@ class TDGLSolver:
         if self.probe_points is not None:
             names["mu"] = len(self.probe_points)
             names["theta"] = len(self.probe_points)
+        if self.include_screening:
+            names["screening_iterations"] = 1                       # solver.py:777-778
         running = _RunningState(names, max(int(opts.save_every), 1))
         self._prev_dt = float(opts.dt_init)
         ok = True

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert b"sm_100a" in lib.tdgl_version()
     assert ctypes.sizeof(_lib.tdgl_config) == 64
-    assert ctypes.sizeof(_lib.tdgl_advance_info) == 96
+    assert ctypes.sizeof(_lib.tdgl_advance_info) == 112
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -152,9 +152,15 @@ def test_solver_input_errors_match_reference():
     with pytest.raises(tdgl.SolverOptionsError):
         mk(mesh, tdgl.SolverOptions(solve_time=1.0, dt_init=1.0, dt_max=0.1), A_applied=A,
            epsilon=eps)
+    # screening is an all-pairs sum over the whole mesh: rejected loudly on a sharded job
     with pytest.raises(tdgl.SolverOptionsError, match="include_screening"):
-        mk(mesh, tdgl.SolverOptions(solve_time=1.0, include_screening=True), A_applied=A,
-           epsilon=eps)
+        mk(mesh, tdgl.SolverOptions(solve_time=1.0, include_screening=True, distributed=True),
+           A_applied=A, epsilon=eps)
+    for bad in (dict(screening_step_drag=0.0), dict(screening_step_size=0.0),
+                dict(screening_tolerance=0.0)):                  # options.py:120-135
+        with pytest.raises(tdgl.SolverOptionsError):
+            mk(mesh, tdgl.SolverOptions(solve_time=1.0, include_screening=True, **bad),
+               A_applied=A, epsilon=eps)
 
 
 def test_mesh_edge_cases():
@@ -291,4 +297,4 @@ int main(void) {
                     str(src), "-o", str(exe), "-L", libdir, "-ltdgl_b200",
                     f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
-    assert "sm_100a" in out and " 64 96" in out and "null array argument" in out
+    assert "sm_100a" in out and " 64 112" in out and "null array argument" in out

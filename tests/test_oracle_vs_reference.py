@@ -86,3 +86,37 @@ def test_oracle_edge_cases_of_the_reference_tests(terminal_psi):
     # the reference's fixed rows still evolve through the local terms of the update)
     if terminal_psi == 0.0:
         assert np.abs(o["psi"][fixed]).max() == 0.0
+
+
+def test_oracle_screening_matches_reference():
+    """Row S: the Polyak iteration on the induced vector potential (solver.py:522-578,
+    650-688) with the reference's own numba kernel (screening.py:12-42) and
+    ``Mesh.get_quantity_on_site`` (mesh.py:203-243)."""
+    from types import SimpleNamespace
+
+    ref = rl.load()
+    mesh, A, eps, _ = film_problem(10, 6, 0.5, b=0.4, reorder=False)
+    rmesh = rl.make_reference_mesh(mesh.sites, mesh.elements)
+    scale = 0.2
+    okw = dict(solve_time=0.3, dt_init=1e-4, dt_max=1e-2, include_screening=True,
+               screening_tolerance=1e-3, max_iterations_per_step=1000)
+    rs = rl.make_reference_solver(mesh, ref.SolverOptions(**okw), A_applied=A, epsilon=eps)
+    rs.device = SimpleNamespace(mesh=rmesh)
+    rs.areas = scale * np.asarray(mesh.areas, float)          # solver.py:309
+    rs.sites = np.asarray(mesh.sites, float)
+    rs.edge_centers = np.asarray(mesh.edge_mesh.centers, float)
+    rs.new_A_induced = np.empty((len(mesh.edge_mesh.edges), 2))
+    r = rl.run_reference(rs, end_time=0.3)
+    os_ = orc.OracleSolver(mesh, orc.OracleOptions(**okw), A, eps, screening_scale=scale)
+    o = orc.run(os_, end_time=0.3)
+    assert o["steps"] == r["steps"]
+    # the numba kernel (fastmath, parallel) and the restatement differ in the last bit of
+    # A_induced; from there SuperLU's null-space component (the gauge) differs: compare
+    # gauge-fixed, as everywhere two solvers are compared (SURVEY.md section 8c)
+    d = orc.compare(o, r, mesh.areas)
+    for k, v in d.items():
+        assert v < 1e-9, (k, d)
+    np.testing.assert_allclose(os_.A_induced, r["induced_vector_potential"], rtol=0, atol=1e-11)
+    np.testing.assert_array_equal(o["screening_iterations"],
+                                  r["running"]["screening_iterations"][0])
+    assert np.abs(os_.A_induced).max() > 1e-4 and o["screening_iterations"].max() > 2

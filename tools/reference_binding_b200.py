@@ -27,7 +27,8 @@ class _Info(C.Structure):                  # tdgl_advance_info, include/tdgl_b20
                 ("dt", C.c_double), ("tentative_dt", C.c_double), ("finished", C.c_int32),
                 ("status", C.c_int32), ("failed_step", C.c_int64), ("failed_dt", C.c_double),
                 ("retries", C.c_int64), ("mu_iterations", C.c_int64),
-                ("mu_rel_residual", C.c_double), ("device_ms", C.c_double)]
+                ("mu_rel_residual", C.c_double), ("device_ms", C.c_double),
+                ("screening_iterations", C.c_int64), ("screening_error", C.c_double)]
 
 
 def _p(a):
