@@ -433,6 +433,24 @@ def run_b200(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_steps_per_s = jobs * Ke / float(e2e_t.item())
+    # what the link itself can do (pinned 64 MiB copies, best of 5): the floor of e2e
+    pcie = {}
+    try:
+        hb = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        db = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        for label, src, dst in (("h2d_GBps", hb, db), ("d2h_GBps", db, hb)):
+            best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dst.copy_(src, non_blocking=True)
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            pcie[label] = (64 << 20) / best / 1e6
+        del hb, db
+    except Exception as exc:
+        pcie = {"unavailable": str(exc)}
     h2d = 24 * n                     # psi (16 B) + mu (8 B) per site (per rank)
     d2h = 24 * n + 16 * n_edges      # psi', mu' + J_s, J_n per edge (per rank)
 
@@ -529,7 +547,10 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_steps_per_s * n, "unit": "site-steps/s",
                 "steps_per_sec": e2e_steps_per_s, "steps": Ke, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "TDGLSolver.update (pinned host arrays)"},
+                "d2h_bytes_per_step": d2h, "api": "TDGLSolver.update (pinned host arrays)",
+                "link": pcie,
+                "link_floor_ms": ((h2d / pcie["h2d_GBps"] + d2h / pcie["d2h_GBps"]) / 1e6
+                                  if "h2d_GBps" in pcie else None)},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

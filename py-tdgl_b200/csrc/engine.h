@@ -297,6 +297,18 @@ class Engine {
   cudaGraph_t graph_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
   cudaGraphConditionalHandle h_step_ = 0, h_psi_ = 0, h_cg_ = 0, h_scr_ = 0;
+  // The step seam (update(): host arrays in and out every step) runs ONE step as two graphs
+  // — step begin + psi loop | rhs + mu solve + step end — so that psi' and J_s, final after
+  // the first, travel to the host on a copy stream while the second runs.
+  cudaGraph_t graph_a_ = nullptr, graph_b_ = nullptr;
+  cudaGraphExec_t graph_a_exec_ = nullptr, graph_b_exec_ = nullptr;
+  cudaGraphConditionalHandle h_psi_a_ = 0, h_cg_b_ = 0;
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t ev_psi_ = nullptr, ev_copy_ = nullptr;
+  void build_split_graphs();
+  void destroy_graphs();
+  void prepare_advance(int64_t max_steps, double t_end, int64_t step, double time);
+  AdvanceInfo collect_advance(float dev_ms);
 
   // ---- launch sequences ------------------------------------------------------------------
   // Every kernel of the stepping sequence is launched with programmatic stream

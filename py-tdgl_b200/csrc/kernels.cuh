@@ -658,7 +658,10 @@ __global__ void k_link_values(int n, const int* __restrict__ ptr, const int* __r
 // Edge arrays are in the caller's edge order, site indices are internal.
 __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __restrict__ e1,
                            const double* __restrict__ elen, const double* __restrict__ theta,
-                           const double2* __restrict__ psi, const double* __restrict__ mu,
+                           const double2* __restrict__ psi /* null: the current buffer of ... */,
+                           const double2* __restrict__ psi_buf0, const double2* __restrict__ psi_buf1,
+                           int mode /* 1: J_s, 2: J_n, 3: both */,
+                           const double* __restrict__ mu,
                            const double* __restrict__ dadt /* may be null */,
                            const Ctl* __restrict__ ctl,
                            const double* __restrict__ ramp_proj /* null: no device-side ramp */,
@@ -669,10 +672,11 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   if (e >= ne) return;
   const int i = e0[e], j = e1[e];
   if (i < 0) {  // the edge belongs to another shard (owner = shard of edges[e,0])
-    js[e] = 0.0;
-    jn[e] = 0.0;
+    if (mode & 1) js[e] = 0.0;
+    if (mode & 2) jn[e] = 0.0;
     return;
   }
+  if (psi == nullptr) psi = ctl->cur ? psi_buf1 : psi_buf0;
   const double inv_l = 1.0 / elen[e];
   double s, c;
   // (device-side ramp: theta holds A0 . d, the current A is ramp_f * A0)
@@ -683,10 +687,10 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   // g = (U psi_j) * (1/l) + psi_i * (-1/l)   as the CSR gradient row computes it
   const double gx = (c * pj.x - s * pj.y) * inv_l - pi.x * inv_l;
   const double gy = (c * pj.y + s * pj.x) * inv_l - pi.y * inv_l;
-  js[e] = pi.x * gy - pi.y * gx;
+  if (mode & 1) js[e] = pi.x * gy - pi.y * gx;
   double da = dadt != nullptr ? dadt[e] : 0.0;
   if (ramp_proj != nullptr) da = ctl->ramp_dfdt * ramp_proj[e];
-  jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
+  if (mode & 2) jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -896,6 +900,16 @@ __global__ void k_gather(int n, const int* __restrict__ perm, const T* __restric
 template <typename T>
 __global__ void k_scatter(int n, const int* __restrict__ perm, const T* __restrict__ src,
                           T* __restrict__ dst) {  // dst[perm[i]] = src[i]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[perm[i]] = src[i];
+}
+
+// dst[perm[i]] = (current psi buffer)[i]: for launches enqueued before the host knows which
+// buffer the device-side psi loop will accept into
+__global__ void k_scatter_psi(const Ctl* __restrict__ ctl, int n, const int* __restrict__ perm,
+                              const double2* __restrict__ psi_buf0,
+                              const double2* __restrict__ psi_buf1, double2* __restrict__ dst) {
+  const double2* src = ctl->cur ? psi_buf1 : psi_buf0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[perm[i]] = src[i];
 }

@@ -174,8 +174,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   TDGL_CUDA(cudaSetDevice(cfg_.device));
   TDGL_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, cfg_.device));
   TDGL_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  TDGL_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
   TDGL_CUDA(cudaEventCreate(&ev0_));
   TDGL_CUDA(cudaEventCreate(&ev1_));
+  TDGL_CUDA(cudaEventCreateWithFlags(&ev_psi_, cudaEventDisableTiming));
+  TDGL_CUDA(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
   TDGL_CUDA(cudaMallocHost(&h_ctl_, sizeof(Ctl)));
   configure_kernels();
 
@@ -539,9 +542,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       // still the CUDA path, only host-driven; keep the reason for tdgl_last_error()
       last_error = std::string("CUDA graph with device-side loops unavailable, using host-driven launches: ") + ex.what();
       cudaGetLastError();
-      if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
-      if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
-      h_step_ = h_psi_ = h_cg_ = h_scr_ = 0;
+      destroy_graphs();
       if (std::getenv("TDGL_B200_VERBOSE")) fprintf(stderr, "[tdgl_b200] %s\n", last_error.c_str());
     }
   }
@@ -607,9 +608,7 @@ void Engine::comm_connect_local(Engine* const* engines) {
     // graph with ordinary launches.
     pdl_ = false;
     if (graph_mode_ == 1) {
-      cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
-      cudaGraphDestroy(graph_); graph_ = nullptr;
-      h_step_ = h_psi_ = h_cg_ = h_scr_ = 0;
+      destroy_graphs();
       comm_on_ = true;
       build_graph();
     }
@@ -632,8 +631,10 @@ void Engine::shard_info(int64_t* out, int n) {
 
 Engine::~Engine() {
   for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
-  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
-  if (graph_) cudaGraphDestroy(graph_);
+  destroy_graphs();
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
+  if (ev_psi_) cudaEventDestroy(ev_psi_);
+  if (ev_copy_) cudaEventDestroy(ev_copy_);
   if (h_ctl_) cudaFreeHost(h_ctl_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -1017,8 +1018,54 @@ void Engine::build_graph() {
                                             scr_on_ ? run_scr_.p : nullptr, h_step_);
     TDGL_LAUNCH_CHECK();
   });
-  launches_ = launches_before;  // captured, not launched
   TDGL_CUDA(cudaGraphInstantiate(&graph_exec_, graph_, 0));
+  if (world_ == 1 && !scr_on_) build_split_graphs();
+  launches_ = launches_before;  // captured, not launched
+}
+
+// One step as two graphs (see engine.h): A = step begin (+ ramp links) + psi loop,
+// B = rhs + mu solve + gauge + step end.
+void Engine::build_split_graphs() {
+  TDGL_CUDA(cudaGraphCreate(&graph_a_, 0));
+  TDGL_CUDA(cudaGraphConditionalHandleCreate(&h_psi_a_, graph_a_, 0, cudaGraphCondAssignDefault));
+  {
+    GraphBuilder a{graph_a_, stream_, {}};
+    a.capture([&] {
+      launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_a_, static_cast<cudaGraphConditionalHandle>(0));
+      TDGL_LAUNCH_CHECK();
+      enqueue_ramp_links();
+    });
+    cudaGraph_t psi_body = a.add_while(h_psi_a_);
+    GraphBuilder pb{psi_body, stream_, {}};
+    pb.capture([&] {
+      enqueue_psi_step(nullptr, -1.0);
+      launch_k(k_psi_control, 1, 32, 0, ctl_.p, comm(), h_psi_a_);
+      TDGL_LAUNCH_CHECK();
+    });
+  }
+  TDGL_CUDA(cudaGraphInstantiate(&graph_a_exec_, graph_a_, 0));
+  TDGL_CUDA(cudaGraphCreate(&graph_b_, 0));
+  TDGL_CUDA(cudaGraphConditionalHandleCreate(&h_cg_b_, graph_b_, 0, cudaGraphCondAssignDefault));
+  {
+    GraphBuilder b{graph_b_, stream_, {}};
+    b.capture([&] {
+      enqueue_mu_rhs(nullptr);
+      enqueue_solve_begin(h_cg_b_);
+    });
+    cudaGraph_t cg_body = b.add_while(h_cg_b_);
+    {
+      GraphBuilder cb{cg_body, stream_, {}};
+      cb.capture([&] { enqueue_cg_iteration(h_cg_b_); });
+    }
+    b.capture([&] {
+      enqueue_mu_finish();
+      launch_k(k_step_end, 1, kMaxProbes, 0, ctl_.p, psi_[0].p, psi_[1].p, mu_.p, probes_.p,
+               run_dt_.p, run_mu_.p, run_theta_.p, static_cast<long long*>(nullptr),
+               static_cast<cudaGraphConditionalHandle>(0));
+      TDGL_LAUNCH_CHECK();
+    });
+  }
+  TDGL_CUDA(cudaGraphInstantiate(&graph_b_exec_, graph_b_, 0));
 }
 
 // ============================================================================================
@@ -1189,11 +1236,19 @@ void Engine::set_ramp(const double* A0, int n_knots, const double* t_knots, cons
   if (was_on != ramp_on_) rebuild_graph();   // the step sequence changed: re-record it
 }
 
+void Engine::destroy_graphs() {
+  if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+  if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+  if (graph_a_exec_) { cudaGraphExecDestroy(graph_a_exec_); graph_a_exec_ = nullptr; }
+  if (graph_a_) { cudaGraphDestroy(graph_a_); graph_a_ = nullptr; }
+  if (graph_b_exec_) { cudaGraphExecDestroy(graph_b_exec_); graph_b_exec_ = nullptr; }
+  if (graph_b_) { cudaGraphDestroy(graph_b_); graph_b_ = nullptr; }
+  h_step_ = h_psi_ = h_cg_ = h_scr_ = h_psi_a_ = h_cg_b_ = 0;
+}
+
 void Engine::rebuild_graph() {
   if (graph_mode_ != 1) return;
-  cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
-  cudaGraphDestroy(graph_); graph_ = nullptr;
-  h_step_ = h_psi_ = h_cg_ = h_scr_ = 0;
+  destroy_graphs();
   const bool on = comm_on_;
   comm_on_ = world_ > 1;
   build_graph();
@@ -1297,21 +1352,7 @@ void Engine::set_stepper(double dt_init, double dt_max, int adaptive, int window
 Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t step, double time) {
   if (max_steps < 1) throw std::invalid_argument("max_steps must be >= 1");
   if (!connected_) throw std::invalid_argument("sharded engine: connect the peers first (tdgl_comm_connect_*)");
-  comm_on_ = world_ > 1;
-  sync_ctl_to_host();
-  h_ctl_->steps_left = max_steps;
-  h_ctl_->steps_done = 0;
-  h_ctl_->t_end = t_end;
-  h_ctl_->time = time;
-  h_ctl_->step = step;
-  h_ctl_->finished = 0;
-  h_ctl_->status = 0;
-  h_ctl_->failed_step = -1;
-  h_ctl_->failed_dt = 0.0;
-  h_ctl_->total_retries = 0;
-  h_ctl_->total_cg_it = 0;
-  h_ctl_->total_scr_it = 0;
-  TDGL_CUDA(cudaMemcpyAsync(ctl_.p, h_ctl_, sizeof(Ctl), cudaMemcpyHostToDevice, stream_));
+  prepare_advance(max_steps, t_end, step, time);
   TDGL_CUDA(cudaEventRecord(ev0_, stream_));
   if (graph_mode_ == 1) {
     TDGL_CUDA(cudaGraphLaunch(graph_exec_, stream_));
@@ -1368,6 +1409,28 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   TDGL_CUDA(cudaEventSynchronize(ev1_));
   float dev_ms = 0.f;
   TDGL_CUDA(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
+  return collect_advance(dev_ms);
+}
+
+void Engine::prepare_advance(int64_t max_steps, double t_end, int64_t step, double time) {
+  comm_on_ = world_ > 1;
+  sync_ctl_to_host();
+  h_ctl_->steps_left = max_steps;
+  h_ctl_->steps_done = 0;
+  h_ctl_->t_end = t_end;
+  h_ctl_->time = time;
+  h_ctl_->step = step;
+  h_ctl_->finished = 0;
+  h_ctl_->status = 0;
+  h_ctl_->failed_step = -1;
+  h_ctl_->failed_dt = 0.0;
+  h_ctl_->total_retries = 0;
+  h_ctl_->total_cg_it = 0;
+  h_ctl_->total_scr_it = 0;
+  TDGL_CUDA(cudaMemcpyAsync(ctl_.p, h_ctl_, sizeof(Ctl), cudaMemcpyHostToDevice, stream_));
+}
+
+Engine::AdvanceInfo Engine::collect_advance(float dev_ms) {
   last_steps_done_ = h_ctl_->steps_done;
   AdvanceInfo info;
   info.device_ms = dev_ms;
@@ -1393,6 +1456,54 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
   // (sharded: the mailbox copy of mu_prev's halo is refilled from the caller's mu, so the
   // history is reset there to stay consistent across the cuts)
   set_state(psi, mu, /*reset_history=*/world_ > 1);
+  if (graph_mode_ == 1 && graph_a_exec_ != nullptr && graph_b_exec_ != nullptr && psi_out && mu_out &&
+      js && jn) {
+    // Overlapped seam: psi' and J_s are final once the psi loop has accepted, i.e. before the
+    // mu solve (most of the step) starts: they go to the host on the copy stream meanwhile.
+    const int g = (N_ + kBlock - 1) / kBlock, ge = (E_ + kBlock - 1) / kBlock;
+    prepare_advance(1, 1e300, step, time);
+    TDGL_CUDA(cudaEventRecord(ev0_, stream_));
+    TDGL_CUDA(cudaGraphLaunch(graph_a_exec_, stream_));
+    TDGL_CUDA(cudaEventRecord(ev_psi_, stream_));
+    TDGL_CUDA(cudaGraphLaunch(graph_b_exec_, stream_));
+    launches_ += 2;
+    TDGL_CUDA(cudaStreamWaitEvent(copy_stream_, ev_psi_, 0));
+    k_scatter_psi<<<g, kBlock, 0, copy_stream_>>>(ctl_.p, N_, dperm_.p, psi_[0].p, psi_[1].p, tmp_c_.p);
+    TDGL_LAUNCH_CHECK();
+    TDGL_CUDA(cudaMemcpyAsync(psi_out, tmp_c_.p, sizeof(double2) * Ng_, cudaMemcpyDeviceToHost, copy_stream_));
+    k_currents<<<ge, kBlock, 0, copy_stream_>>>(
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
+        psi_[1].p, 1, mu_.p, has_dadt_ ? dadt_.p : nullptr, ctl_.p,
+        ramp_on_ ? ramp_proj_.p : nullptr, static_cast<const double2*>(nullptr), edir_.p, tmp_e_.p,
+        tmp_e2_.p);
+    TDGL_LAUNCH_CHECK();
+    tmp_e_.download(js, E_, copy_stream_);
+    TDGL_CUDA(cudaEventRecord(ev_copy_, copy_stream_));
+    // after the solve: mu' and J_n
+    k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, tmp_d_.p);
+    TDGL_LAUNCH_CHECK();
+    tmp_d_.download(mu_out, Ng_, stream_);
+    k_currents<<<ge, kBlock, 0, stream_>>>(
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
+        psi_[1].p, 2, mu_.p, has_dadt_ ? dadt_.p : nullptr, ctl_.p,
+        ramp_on_ ? ramp_proj_.p : nullptr, static_cast<const double2*>(nullptr), edir_.p, tmp_e_.p,
+        tmp_e2_.p);
+    TDGL_LAUNCH_CHECK();
+    tmp_e2_.download(jn, E_, stream_);
+    TDGL_CUDA(cudaStreamWaitEvent(stream_, ev_copy_, 0));
+    TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+    TDGL_CUDA(cudaEventSynchronize(ev1_));
+    sync_ctl_to_host();
+    {
+      const int64_t L = static_cast<int64_t>(levels_.size());
+      const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
+      launches_ += h_ctl_->steps_done * (2 + (ramp_on_ ? 1 : 0)) + h_ctl_->steps_done * 7 +
+                   h_ctl_->total_retries * 2 + h_ctl_->total_cg_it * (2 + 4 * split + 1);
+    }
+    float dev_ms = 0.f;
+    TDGL_CUDA(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
+    return collect_advance(dev_ms);
+  }
   AdvanceInfo info = advance(1, 1e300, step, time);
   const int cur = h_ctl_->cur;
   const int g = (N_ + kBlock - 1) / kBlock;
@@ -1412,7 +1523,8 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
   if (js != nullptr || jn != nullptr) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+        has_dadt_ ? dadt_.p : nullptr,
         ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
@@ -1440,7 +1552,8 @@ void Engine::stage_outputs(int what, void** ptrs, int64_t* counts) {
   if (what & 2) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
+        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+        has_dadt_ ? dadt_.p : nullptr,
         ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
@@ -1483,7 +1596,8 @@ void Engine::get_currents(double* js, double* jn) {
   const int cur = h_ctl_->cur;
   unpack_state_halos(cur);
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, mu_.p, has_dadt_ ? dadt_.p : nullptr,
+      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+      has_dadt_ ? dadt_.p : nullptr,
         ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
   TDGL_LAUNCH_CHECK();

@@ -9,10 +9,8 @@ against the unmodified reference in the build container (tests/test_oracle_vs_re
 including these edge cases) and runs live here on the box's host cores.
 
 Tolerances (BASELINE.json asks psi within 1e-6): gauge-fixed psi, |psi|, mu, J_s, J_n <= 1e-8
-relative and dt sequence <= 1e-10 relative with the mu solve converged tightly
-(``mu_rtol = 1e-13``), on the smooth start-up window of the workloads.  With the product's
-default ``mu_rtol = 1e-10`` the iterative solve's own truncation (amplified by the adaptive-dt
-controller, which divides by max |d|psi|^2|) is what remains: <= 1e-7 and dt <= 1e-9 asserted.
+relative and dt sequence <= 1e-10 relative, with the product's default ``mu_rtol = 1e-10``, on
+the smooth start-up window of the workloads (measured: 1.5e-11 at 1.0M sites, 5e-9 at 251k).
 """
 import os
 import sys
@@ -31,8 +29,7 @@ pytestmark = pytest.mark.gpu
 
 TOL, TOL_DT = 1e-8, 1e-10
 # (mu_rtol, field tolerance, dt tolerance)
-RTOLS = [pytest.param(1e-13, 1e-8, 1e-10, id="mu_rtol=1e-13"),
-         pytest.param(1e-10, 1e-7, 1e-9, id="mu_rtol=default")]
+RTOLS = [pytest.param(1e-10, 1e-8, 1e-10, id="mu_rtol=default")]
 
 
 def _oracle_run(work, steps):
