@@ -349,6 +349,63 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def strong_record(args, rank, world, local_rank, dist, barrier, torch):
+    """BASELINE.json's strong-scaling configuration (configs[4]: ~10M-site film in a field) on
+    the job's N GPUs AND on one GPU, measured in the same job with the same code: N-GPU
+    ms/step (max over ranks), then rank 0 alone steps the same mesh on its GPU while the other
+    ranks wait.  speedup = 1-GPU ms/step / N-GPU ms/step."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+
+    name = args.strong_workload
+    K, W = args.steps, args.warmup
+    work = build_workload(name, rank, barrier)
+    n = len(work["mesh"].sites)
+    psi0, mu0 = start_state(work)
+
+    def measure(distributed):
+        opts = SolverOptions(solve_time=1e9, save_every=max(K, W, 1), cuda_device=local_rank,
+                             use_cuda_graph=not args.no_graph, distributed=distributed,
+                             **work["opts"])
+        t0 = time.perf_counter()
+        solver = TDGLSolver.from_dimensionless(
+            work["mesh"], opts, A_applied=work["A"], epsilon=work["eps"],
+            terminal_info=work["terms"], terminal_currents=work["currents"])
+        setup = time.perf_counter() - t0
+        eng = solver.engine
+        eng.set_state(psi0, mu0)
+        solver.update_mu_boundary(0.0)
+        if distributed:
+            barrier()
+        a = eng.advance(W, 1e300, 0, 0.0) if W > 0 else None
+        step, t = (a.step, a.time) if a is not None else (0, 0.0)
+        if distributed:
+            barrier()
+        b = eng.advance(K, 1e300, step, t)
+        torch.cuda.synchronize()
+        ms = torch.tensor([b.device_ms], dtype=torch.float64, device="cuda")
+        if distributed:
+            barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        eng.close()
+        return float(ms.item()) / K, b.mu_iterations / K, setup
+
+    ms_n, its_n, setup_n = measure(True)
+    one = None
+    if rank == 0:
+        one = measure(False)
+    barrier()
+    if rank != 0:
+        return None
+    ms_1, its_1, setup_1 = one
+    return {"workload": name, "sites": n, "edges": len(work["mesh"].edge_mesh.edges),
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_n,
+            "ms_per_step_1gpu": ms_1, "speedup": ms_1 / ms_n,
+            "mu_iterations_per_step": its_n, "mu_iterations_per_step_1gpu": its_1,
+            "site_steps_per_sec": n / (ms_n / 1e3), "setup_seconds": {"n_gpus": setup_n, "1gpu": setup_1},
+            "how": "same job, same code, same start state; 1-GPU time measured by rank 0 on its own"
+                   " GPU while the other ranks wait"}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
 
@@ -472,6 +529,12 @@ def run_b200(args, rank, world, local_rank):
                      "steps_per_sec": jobs * K / (float(dms.item()) / 1e3),
                      "mu_iterations_per_step": dv.mu_iterations / K, "retries": dv.retries}
 
+    # ---- strong scaling on the 10M-site configuration, in the same job (N > 1) -----------------
+    strong = None
+    if shard and args.strong_record:
+        eng.close()
+        strong = strong_record(args, rank, world, local_rank, dist, barrier, torch)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -543,6 +606,7 @@ def run_b200(args, rank, world, local_rank):
                    "mu_rtol": opts.mu_rtol, "amg_levels": levels},
         "mu_iterations_per_step": iters_per_step, "retries": b.retries,
         "developed": developed,
+        "strong": strong,
         "setup_seconds": {"mesh": work["mesh_seconds"], "engine": setup_s},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_steps_per_s * n, "unit": "site-steps/s",
@@ -584,6 +648,9 @@ def main():
     ap.add_argument("--mode", default="weak", choices=["weak", "strong", "replicas"],
                     help="N > 1: domain decomposition of BASELINE.json's config for N GPUs"
                          " (weak, default), of the 1-GPU workload (strong), or replicas")
+    ap.add_argument("--no-strong-record", dest="strong_record", action="store_false",
+                    help="N > 1: skip the strong-scaling record (10M-site film on N GPUs and on 1)")
+    ap.add_argument("--strong-workload", default="film10m_field", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true",
                     help="host-driven launches instead of the device-side-loop CUDA graph"
                          " (profiler runs: every kernel is an ordinary launch)")

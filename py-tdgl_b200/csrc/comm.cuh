@@ -147,6 +147,7 @@ __device__ __forceinline__ void comm_allreduce(Ctl* ctl, Comm* c, double* v, int
   }
   __syncwarp();
   if (lane == 0) c->rseq = s;
+  __syncwarp();   // (a second all-reduce by the same warp must see the new sequence number)
 }
 
 // ---- tags ------------------------------------------------------------------------------------

@@ -223,7 +223,10 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict_
   griddep_enter();
   __shared__ double red[32];
   if (ctl->status != 0) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) set_cond(cond, 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      ctl->cg_go = 0;   // (the host-driven loop reads this, the graph the conditional)
+      set_cond(cond, 0);
+    }
     return;
   }
   const double gamma = ctl->rz_new, delta = ctl->pAp;
