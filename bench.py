@@ -530,12 +530,13 @@ def run_b200(args, rank, world, local_rank):
                      "mu_iterations_per_step": dv.mu_iterations / K, "retries": dv.retries}
 
     # ---- strong scaling on the 10M-site configuration, in the same job (N > 1) -----------------
+    # (rank 0 first times its kernels one by one for the roofline table, the others wait for it
+    # in the record's first barrier)
     strong = None
-    if shard and args.strong_record:
-        eng.close()
-        strong = strong_record(args, rank, world, local_rank, dist, barrier, torch)
-
     if rank != 0:
+        if shard and args.strong_record:
+            eng.close()
+            strong_record(args, rank, world, local_rank, dist, barrier, torch)
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -587,6 +588,10 @@ def run_b200(args, rank, world, local_rank):
                 "peak_source": peak_src, "unit": "GB/s", "frac": table[dom]["frac"],
                 "traffic": None, "kernels": table, "vcycle_ms": vc_ms,
                 "cusparse_spmv": cusparse}
+
+    if shard and args.strong_record:
+        eng.close()
+        strong = strong_record(args, rank, world, local_rank, dist, barrier, torch)
 
     line = {
         "metric": "tdgl_site_steps_per_sec", "value": steps_per_s * n, "unit": "site-steps/s",

@@ -77,7 +77,10 @@ __device__ __forceinline__ unsigned int poll_word(Ctl* ctl, const unsigned long 
     if ((++n & 255u) == 0) {
       if (global_ns() - t0 > kSpinTimeoutNs ||
           *reinterpret_cast<volatile int*>(&ctl->status) != 0) {
-        atomicCAS(&ctl->status, 0, 3);
+        if (atomicCAS(&ctl->status, 0, 3) == 0) {
+          ctl->fail_tag = tag;
+          ctl->fail_addr = reinterpret_cast<unsigned long long>(p);
+        }
         *ok = false;
         return 0u;
       }
@@ -111,7 +114,10 @@ __device__ __forceinline__ double poll_f64(Ctl* ctl, const unsigned long long* p
     if ((++n & 255u) == 0) {
       if (global_ns() - t0 > kSpinTimeoutNs ||
           *reinterpret_cast<volatile int*>(&ctl->status) != 0) {
-        atomicCAS(&ctl->status, 0, 3);
+        if (atomicCAS(&ctl->status, 0, 3) == 0) {
+          ctl->fail_tag = tag;
+          ctl->fail_addr = reinterpret_cast<unsigned long long>(p);
+        }
         *ok = false;
         return 0.0;
       }

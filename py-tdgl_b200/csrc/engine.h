@@ -211,6 +211,7 @@ class Engine {
   void make_current() { TDGL_CUDA(cudaSetDevice(cfg_.device)); }
 
   std::string last_error;
+  std::string failure_detail();   // what a shard-exchange timeout (status 3) was waiting for
 
  private:
   // ---- sizes / host copies --------------------------------------------------------------

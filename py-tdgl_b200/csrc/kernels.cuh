@@ -59,6 +59,9 @@ struct Ctl {
   int solve_epoch;    // mu solves started so far (+1): bumped at the start of every step
   int psi_epoch;      // attempts of the psi step so far (+1)
   int psi_tag[2];     // psi_epoch of the attempt that produced each psi buffer
+  // --- diagnostics of a shard-exchange timeout (status 3): what was waited for ----------------
+  unsigned int fail_tag;
+  unsigned long long fail_addr;
   // --- screening: Polyak iteration on the induced vector potential (solver.py:650-688) -------
   int scr_on, scr_it, scr_go, scr_max_it;
   double scr_tol, scr_alpha, scr_beta, scr_err;

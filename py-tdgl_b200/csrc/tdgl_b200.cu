@@ -1412,6 +1412,31 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   return collect_advance(dev_ms);
 }
 
+std::string Engine::failure_detail() {
+  if (h_ctl_ == nullptr || h_ctl_->status != 3 || world_ == 1) return "";
+  const long long off = (static_cast<long long>(h_ctl_->fail_addr) -
+                         static_cast<long long>(reinterpret_cast<unsigned long long>(arena_.p))) / 8;
+  std::string what = "unknown location";
+  const ArenaLayout& lay = layouts_[rank_];
+  if (off >= kArenaRedBox && off < kArenaHeader) {
+    what = "all-reduce mailbox";
+  } else {
+    static const char* names[] = {"psi[0]", "psi[1]", "mu", "cg r", "cg z"};
+    for (size_t ch = 0; ch < lay.box_off.size(); ++ch)
+      if (lay.box_off[ch] > 0 && off >= lay.box_off[ch] && off < lay.box_off[ch] + 2 * lay.box_cap[ch]) {
+        if (ch < 5) what = std::string("halo of ") + names[ch];
+        else what = "halo of AMG level " + std::to_string((ch - kVecLevel0) / 4) + " vector " +
+                    std::string(1, "xrby"[(ch - kVecLevel0) % 4]);
+        what += " (entry " + std::to_string((off - lay.box_off[ch]) % lay.box_cap[ch]) + ")";
+      }
+  }
+  char buf[256];
+  snprintf(buf, sizeof buf, " [rank %d waited for %s, tag 0x%x, step %lld, cg iteration %d, solve epoch %d]",
+           rank_, what.c_str(), h_ctl_->fail_tag, static_cast<long long>(h_ctl_->step), h_ctl_->cg_it,
+           h_ctl_->solve_epoch);
+  return buf;
+}
+
 void Engine::prepare_advance(int64_t max_steps, double t_end, int64_t step, double time) {
   comm_on_ = world_ > 1;
   sync_ctl_to_host();
@@ -1984,7 +2009,8 @@ int step_status_to_rc(tdgl_handle* h, int status) {
       h->error = "mu solver did not reach tolerance within mu_max_iter iterations";
       return TDGL_E_MU_SOLVER;
     case 3:
-      h->error = "shard exchange timed out (a peer shard stopped or was never connected)";
+      h->error = "shard exchange timed out (a peer shard stopped or was never connected)" +
+                 h->engine->failure_detail();
       return TDGL_E_CUDA;
     case 4:
       h->error = "screening iteration did not converge within max_iterations_per_step";

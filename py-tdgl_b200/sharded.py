@@ -28,7 +28,10 @@ from .engine import AdvanceInfo, DeviceEngine
 class DistributedEngine(DeviceEngine):
     """This process's shard; every rank must make the same calls in the same order."""
 
-    def __init__(self, mesh, *, group=None, device: Optional[int] = None, **kw):
+    def __init__(self, mesh, *, group=None, device: Optional[int] = None,
+                 allow_shared_device: bool = False, **kw):
+        import socket
+
         import torch
         import torch.distributed as dist
 
@@ -38,6 +41,16 @@ class DistributedEngine(DeviceEngine):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if device is None:
             device = torch.cuda.current_device()
+        if world > 1 and not allow_shared_device:
+            # one shard per GPU: two ranks on one device would serialise (and the NCCL
+            # communicator of the output sums is bound to the rank's own device)
+            where: List[Optional[tuple]] = [None] * world
+            dist.all_gather_object(where, (socket.gethostname(), int(device)), group=group)
+            if len(set(where)) != world:
+                raise RuntimeError(
+                    f"ranks share a CUDA device {where}: call torch.cuda.set_device(LOCAL_RANK)"
+                    " before building the solver (or set SolverOptions.cuda_device per rank);"
+                    " pass allow_shared_device=True to shard one GPU on purpose")
         super().__init__(mesh, device=device, world=world, rank=rank, **kw)
         self._reduce_device = (torch.device("cuda", device)
                                if dist.get_backend(group) == "nccl" else torch.device("cpu"))
