@@ -193,6 +193,18 @@ int tdgl_get_currents(tdgl_handle* h, double* supercurrent, double* normal_curre
 
 /* Running state of the last advance(): dt[k], mu[n_probe][k], theta[n_probe][k] for
  * k < steps_done (solver.py:690-694); `capacity` is the row stride of the outputs. */
+/* Asynchronous save pipeline (the reference saves synchronously from the stepping thread,
+ * DataHandler.save_time_step, solver/runner.py:155-183).  tdgl_snapshot_begin stages psi, mu,
+ * J_s, J_n of the current state in device buffers on the stepping stream and starts their copy
+ * into the slot's page-locked host buffers on a second stream; it returns at once and the
+ * next tdgl_advance overlaps the copy.  tdgl_snapshot_wait blocks until that slot's copy has
+ * landed and returns the host pointers (whole-mesh arrays in the caller's numbering: psi
+ * complex128[N], mu f64[N], currents f64[E]), valid until the slot's next tdgl_snapshot_begin.
+ * Two slots (0, 1).  tdgl_snapshot_wait may be called from a second host thread (a writer). */
+int tdgl_snapshot_begin(tdgl_handle* h, int32_t slot);
+int tdgl_snapshot_wait(tdgl_handle* h, int32_t slot, double** psi, double** mu,
+                       double** supercurrent, double** normal_current);
+
 int tdgl_get_running(tdgl_handle* h, int64_t capacity, double* dt, double* mu_probe,
                      double* theta_probe);
 

@@ -90,6 +90,9 @@ SIGNATURES = {
     "tdgl_host_free": (None, [_P]),
     "tdgl_get_state": (C.c_int, [_P, _P, _P]),
     "tdgl_get_currents": (C.c_int, [_P, _P, _P]),
+    "tdgl_snapshot_begin": (C.c_int, [_P, _I32]),
+    "tdgl_snapshot_wait": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                                     C.POINTER(_P)]),
     "tdgl_get_running": (C.c_int, [_P, _I64, _P, _P, _P]),
     "tdgl_op_psi_laplacian": (C.c_int, [_P, _P, _P]),
     "tdgl_op_psi_step": (C.c_int, [_P, _P, _P, _D, _P, _P, C.POINTER(_I32)]),

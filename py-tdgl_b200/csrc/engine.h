@@ -175,6 +175,11 @@ class Engine {
   void set_induced(const double* A);
   void get_induced(double* A);
   void get_running_screening(int64_t capacity, int64_t* iterations);
+  // asynchronous save pipeline: the state is staged in device buffers on the stepping stream
+  // (two scatter + one edge kernel), then drained to pinned host memory on the copy stream
+  // while the next chunk of steps runs; snapshot_wait blocks on that slot's copy only
+  void snapshot_begin(int slot);
+  void snapshot_wait(int slot, double** psi, double** mu, double** js, double** jn);
   void set_stepper(double dt_init, double dt_max, int adaptive, int window, int max_retries,
                    double multiplier);
   struct AdvanceInfo {
@@ -306,6 +311,14 @@ class Engine {
   cudaGraphConditionalHandle h_psi_a_ = 0, h_cg_b_ = 0;
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_psi_ = nullptr, ev_copy_ = nullptr;
+  struct SnapSlot {
+    DevBuf<double2> d_psi;
+    DevBuf<double> d_mu, d_js, d_jn;
+    double *h_psi = nullptr, *h_mu = nullptr, *h_js = nullptr, *h_jn = nullptr;   // pinned
+    cudaEvent_t staged = nullptr, done = nullptr;
+    bool pending = false;
+  };
+  SnapSlot snap_[2];
   void build_split_graphs();
   void destroy_graphs();
   void prepare_advance(int64_t max_steps, double t_end, int64_t step, double time);

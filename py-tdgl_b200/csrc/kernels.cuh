@@ -830,8 +830,10 @@ k_scr_a_induced(const Ctl* __restrict__ ctl, int n_edges, int n_sites,
 
 // Polyak update (solver.py:564-577): dA = A_new - A ; v = (1 - beta) v + alpha dA ; A += v ;
 // error = max_e |dA_e| / max(|A_e|, 1e-20).  The velocity starts from 0 in every time step.
+// a_new is left holding the OLD A: the potential the link variables of this pass were built
+// from, i.e. the one the supercurrent the reference returns belongs to (solver.py:670-681).
 __global__ void __launch_bounds__(kBlock)
-k_scr_polyak(Ctl* ctl, int n_edges, const double2* __restrict__ a_new, double2* __restrict__ aind,
+k_scr_polyak(Ctl* ctl, int n_edges, double2* __restrict__ a_new, double2* __restrict__ aind,
              double2* __restrict__ vel) {
   griddep_enter();
   __shared__ double s_max[8];
@@ -848,6 +850,7 @@ k_scr_polyak(Ctl* ctl, int n_edges, const double2* __restrict__ a_new, double2* 
     const double2 a1 = make_double2(a.x + v.x, a.y + v.y);
     vel[e] = v;
     aind[e] = a1;
+    a_new[e] = a;
     err = sqrt(dx * dx + dy * dy) / fmax(sqrt(a1.x * a1.x + a1.y * a1.y), 1e-20);
     if (!(err == err)) err = 1e300;
   }

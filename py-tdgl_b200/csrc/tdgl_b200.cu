@@ -632,6 +632,15 @@ void Engine::shard_info(int64_t* out, int n) {
 Engine::~Engine() {
   for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
   destroy_graphs();
+  for (SnapSlot& sl : snap_) {
+    if (sl.pending) cudaEventSynchronize(sl.done);
+    if (sl.h_psi) cudaFreeHost(sl.h_psi);
+    if (sl.h_mu) cudaFreeHost(sl.h_mu);
+    if (sl.h_js) cudaFreeHost(sl.h_js);
+    if (sl.h_jn) cudaFreeHost(sl.h_jn);
+    if (sl.staged) cudaEventDestroy(sl.staged);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (ev_psi_) cudaEventDestroy(ev_psi_);
   if (ev_copy_) cudaEventDestroy(ev_copy_);
@@ -1128,7 +1137,7 @@ void Engine::set_screening(int enable, double scale, const double* sites_xy,
     if (aind_.n == 0) {
       aind_.alloc(E_); aind_new_.alloc(E_); vel_.alloc(E_); wsite_.alloc(N_); old_sq_.alloc(N_);
       run_scr_.alloc(static_cast<size_t>(cfg_.running_capacity));
-      aind_.zero(stream_); vel_.zero(stream_); run_scr_.zero(stream_);
+      aind_.zero(stream_); aind_new_.zero(stream_); vel_.zero(stream_); run_scr_.zero(stream_);
     }
     scr_on_ = true;
     h_ctl_->scr_on = 1;
@@ -1144,6 +1153,8 @@ void Engine::set_screening(int enable, double scale, const double* sites_xy,
 void Engine::set_induced(const double* A) {
   if (!scr_on_) throw std::invalid_argument("screening is off");
   TDGL_CUDA(cudaMemcpyAsync(aind_.p, A, sizeof(double2) * E_, cudaMemcpyHostToDevice, stream_));
+  // (aind_new_ = the potential the current link variables / saved currents belong to)
+  TDGL_CUDA(cudaMemcpyAsync(aind_new_.p, aind_.p, sizeof(double2) * E_, cudaMemcpyDeviceToDevice, stream_));
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -1550,7 +1561,7 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
         has_dadt_ ? dadt_.p : nullptr,
-        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_new_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
     if (js != nullptr) tmp_e_.download(js, E_, stream_);
@@ -1579,7 +1590,7 @@ void Engine::stage_outputs(int what, void** ptrs, int64_t* counts) {
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
         E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
         has_dadt_ ? dadt_.p : nullptr,
-        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_new_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
   }
@@ -1616,6 +1627,51 @@ void Engine::get_state(double* psi, double* mu) {
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
 
+void Engine::snapshot_begin(int slot) {
+  if (slot < 0 || slot > 1) throw std::invalid_argument("snapshot slot must be 0 or 1");
+  if (world_ > 1) throw std::invalid_argument("asynchronous snapshots are per-device: not on a sharded engine");
+  SnapSlot& sl = snap_[slot];
+  if (sl.staged == nullptr) {
+    sl.d_psi.alloc(Ng_); sl.d_mu.alloc(Ng_); sl.d_js.alloc(E_); sl.d_jn.alloc(E_);
+    TDGL_CUDA(cudaMallocHost(&sl.h_psi, sizeof(double2) * Ng_));
+    TDGL_CUDA(cudaMallocHost(&sl.h_mu, sizeof(double) * Ng_));
+    TDGL_CUDA(cudaMallocHost(&sl.h_js, sizeof(double) * E_));
+    TDGL_CUDA(cudaMallocHost(&sl.h_jn, sizeof(double) * E_));
+    TDGL_CUDA(cudaEventCreateWithFlags(&sl.staged, cudaEventDisableTiming));
+    TDGL_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  if (sl.pending) TDGL_CUDA(cudaEventSynchronize(sl.done));   // (the host copy is being reused)
+  sync_ctl_to_host();
+  const int cur = h_ctl_->cur;
+  const int g = (N_ + kBlock - 1) / kBlock;
+  k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, psi_[cur].p, sl.d_psi.p);
+  TDGL_LAUNCH_CHECK();
+  k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, sl.d_mu.p);
+  TDGL_LAUNCH_CHECK();
+  k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+      has_dadt_ ? dadt_.p : nullptr, ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr,
+      scr_on_ ? aind_new_.p : nullptr, edir_.p, sl.d_js.p, sl.d_jn.p);
+  TDGL_LAUNCH_CHECK();
+  TDGL_CUDA(cudaEventRecord(sl.staged, stream_));
+  TDGL_CUDA(cudaStreamWaitEvent(copy_stream_, sl.staged, 0));
+  TDGL_CUDA(cudaMemcpyAsync(sl.h_psi, sl.d_psi.p, sizeof(double2) * Ng_, cudaMemcpyDeviceToHost, copy_stream_));
+  TDGL_CUDA(cudaMemcpyAsync(sl.h_mu, sl.d_mu.p, sizeof(double) * Ng_, cudaMemcpyDeviceToHost, copy_stream_));
+  TDGL_CUDA(cudaMemcpyAsync(sl.h_js, sl.d_js.p, sizeof(double) * E_, cudaMemcpyDeviceToHost, copy_stream_));
+  TDGL_CUDA(cudaMemcpyAsync(sl.h_jn, sl.d_jn.p, sizeof(double) * E_, cudaMemcpyDeviceToHost, copy_stream_));
+  TDGL_CUDA(cudaEventRecord(sl.done, copy_stream_));
+  sl.pending = true;
+}
+
+void Engine::snapshot_wait(int slot, double** psi, double** mu, double** js, double** jn) {
+  if (slot < 0 || slot > 1) throw std::invalid_argument("snapshot slot must be 0 or 1");
+  SnapSlot& sl = snap_[slot];
+  if (!sl.pending) throw std::invalid_argument("no snapshot in flight in this slot");
+  TDGL_CUDA(cudaEventSynchronize(sl.done));
+  sl.pending = false;
+  *psi = sl.h_psi; *mu = sl.h_mu; *js = sl.h_js; *jn = sl.h_jn;
+}
+
 void Engine::get_currents(double* js, double* jn) {
   sync_ctl_to_host();
   const int cur = h_ctl_->cur;
@@ -1623,7 +1679,7 @@ void Engine::get_currents(double* js, double* jn) {
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
       E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
       has_dadt_ ? dadt_.p : nullptr,
-        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_.p : nullptr, edir_.p,
+        ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_new_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
   TDGL_LAUNCH_CHECK();
   if (js != nullptr) tmp_e_.download(js, E_, stream_);
@@ -2205,6 +2261,24 @@ int tdgl_stage_outputs(tdgl_handle* h, int32_t what, void** device_ptrs, int64_t
 int tdgl_fetch_outputs(tdgl_handle* h, double* psi, double* mu, double* supercurrent,
                        double* normal_current) {
   return guarded(h, [&](tdgl::Engine& e) { e.fetch_outputs(psi, mu, supercurrent, normal_current); });
+}
+int tdgl_snapshot_begin(tdgl_handle* h, int32_t slot) {
+  return guarded(h, [&](tdgl::Engine& e) { e.snapshot_begin(slot); });
+}
+// (may be called from a second host thread — the writer — while the first one steps: it only
+// waits on the slot's copy event and touches no other engine state)
+int tdgl_snapshot_wait(tdgl_handle* h, int32_t slot, double** psi, double** mu,
+                       double** supercurrent, double** normal_current) {
+  if (h == nullptr || !h->engine || !psi || !mu || !supercurrent || !normal_current) return TDGL_E_INVALID;
+  try {
+    h->engine->make_current();
+    h->engine->snapshot_wait(slot, psi, mu, supercurrent, normal_current);
+    return TDGL_OK;
+  } catch (const tdgl::CudaError&) {
+    return TDGL_E_CUDA;
+  } catch (const std::exception&) {
+    return TDGL_E_INVALID;
+  }
 }
 int tdgl_get_running(tdgl_handle* h, int64_t capacity, double* dt, double* mu_probe,
                      double* theta_probe) {

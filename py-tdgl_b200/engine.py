@@ -293,6 +293,26 @@ class DeviceEngine:
         self._check(self._lib.tdgl_get_currents(self._h, ptr(js), ptr(jn)))
         return js, jn
 
+    def snapshot_begin(self, slot: int) -> None:
+        """Start an asynchronous copy of psi, mu, J_s, J_n into pinned host slot 0 / 1."""
+        self._check(self._lib.tdgl_snapshot_begin(self._h, int(slot)))
+
+    def snapshot_wait(self, slot: int):
+        """Block until the slot's copy has landed; returns NumPy views of the pinned buffers
+        (psi, mu, J_s, J_n), valid until the slot's next ``snapshot_begin``.  Safe to call
+        from a writer thread while the stepping thread keeps calling ``advance``."""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        rc = self._lib.tdgl_snapshot_wait(self._h, int(slot), *[C.byref(p) for p in ptrs])
+        if rc != _lib.TDGL_OK:
+            raise _lib.TDGLLibraryError(f"tdgl_snapshot_wait failed ({rc})")
+
+        def view(p, n, dtype):
+            buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(p.value)
+            return np.frombuffer(buf, dtype=dtype, count=n)
+
+        return (view(ptrs[0], self.n_sites, np.complex128), view(ptrs[1], self.n_sites, np.float64),
+                view(ptrs[2], self.n_edges, np.float64), view(ptrs[3], self.n_edges, np.float64))
+
     def get_running(self, steps: int):
         cap = max(int(steps), 1)
         dt = np.zeros(cap)

@@ -59,6 +59,7 @@ class SolverOptions:
     cuda_device: Optional[int] = None   # None: device 0, or (distributed) the rank's
     #                               current CUDA device (torch.cuda.current_device())
     use_cuda_graph: bool = True   # device-side step / retry / CG loops in one CUDA graph
+    async_save: bool = True       # saves go through pinned double buffers + a writer thread
     distributed: bool = False     # True: this process is one shard of a torchrun job (the
     #                               mesh is domain-decomposed over torch.distributed's ranks)
 

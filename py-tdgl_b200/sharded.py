@@ -185,9 +185,12 @@ class LocalShardGroup:
             t.start()
         for t in threads:
             t.join()
-        for e in err:
-            if e is not None:
-                raise e
+        failed = [(r, e) for r, e in enumerate(err) if e is not None]
+        if len(failed) > 1:    # usually one root cause and the others timing out on it
+            raise type(failed[0][1])(
+                "; ".join(f"shard {r}: {e}" for r, e in failed)) from failed[0][1]
+        if failed:
+            raise failed[0][1]
         return out
 
     # inputs are whole-mesh arrays, every shard takes its part

@@ -90,6 +90,67 @@ class _DeferredInterrupt:
         return False
 
 
+class _AsyncSaver:
+    """Save pipeline of a stage: the stepping thread only starts a device->pinned-host copy
+    (``tdgl_snapshot_begin``, two slots) and goes on stepping; this writer thread waits for
+    the copy, moves the arrays into the output container (``SavedSteps`` — the counterpart of
+    ``DataHandler.save_time_step``, runner.py:155-183) and frees the slot.  Jobs are
+    processed in order, so the groups come out as the reference numbers them."""
+
+    def __init__(self, engine, saved: SavedSteps):
+        import queue
+        import threading
+
+        self.engine, self.saved = engine, saved
+        self.jobs: "queue.Queue" = queue.Queue()
+        self.free: "queue.Queue" = queue.Queue()
+        for slot in (0, 1):
+            self.free.put(slot)
+        self.error: Optional[BaseException] = None
+        self.thread = threading.Thread(target=self._run, name="tdgl-b200-writer", daemon=True)
+        self.thread.start()
+
+    def _check(self) -> None:
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err
+
+    def save_host(self, state, values, running) -> None:
+        """Values that are already on the host (step 0 of a run)."""
+        self._check()
+        self.jobs.put((None, state, values, running))
+
+    def save_device(self, state, extra, running) -> None:
+        """Snapshot the engine's current state; ``extra``: the host-side entries of the group."""
+        slot = self.free.get()        # blocks only while both slots are still being written
+        self._check()
+        self.engine.snapshot_begin(slot)
+        self.jobs.put((slot, state, extra, running))
+
+    def _run(self) -> None:
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                return
+            slot, state, values, running = job
+            try:
+                if slot is not None:
+                    psi, mu, js, jn = self.engine.snapshot_wait(slot)
+                    values = dict({"psi": psi, "mu": mu, "supercurrent": js,
+                                   "normal_current": jn}, **values)
+                self.saved.save_time_step(state, values, running)   # copies out of the views
+            except BaseException as exc:  # noqa: BLE001  (re-raised on the stepping thread)
+                self.error = exc
+            finally:
+                if slot is not None:
+                    self.free.put(slot)
+
+    def close(self) -> None:
+        self.jobs.put(None)
+        self.thread.join()
+        self._check()
+
+
 class _RunningState:
     """reference ``RunningState`` (runner.py:186-221)."""
 
@@ -453,10 +514,34 @@ class TDGLSolver:
             out["epsilon"] = self.epsilon
         return out
 
+    def _host_values(self) -> Dict[str, np.ndarray]:
+        """The entries of a saved group that live on the host (the rest comes from the
+        engine's snapshot)."""
+        out = {"induced_vector_potential": (self.engine.get_induced_vector_potential()
+                                            if self.include_screening
+                                            else np.zeros((self.num_edges, 2)))}
+        if self.dynamic_vector_potential:
+            out["applied_vector_potential"] = self.current_A_applied
+        if self.dynamic_epsilon:
+            out["epsilon"] = self.epsilon
+        return out
+
     def _run_stage(self, name: str, end_time: float, save: bool, saved: SavedSteps,
                    running: _RunningState, first_values: Optional[dict]) -> bool:
         """The loop of ``Runner._run_stage`` (runner.py:379-453) in chunks that end at the
         next save step (or after one step when a host callback is time-dependent)."""
+        opts = self.options
+        # single-device engines save through the asynchronous pipeline; sharded ones (whose
+        # outputs are summed over the shards) synchronously
+        saver = (_AsyncSaver(self.engine, saved)
+                 if save and opts.async_save and type(self.engine) is DeviceEngine else None)
+        try:
+            return self._stage_loop(name, end_time, save, saved, running, first_values, saver)
+        finally:
+            if saver is not None:
+                saver.close()
+
+    def _stage_loop(self, name, end_time, save, saved, running, first_values, saver) -> bool:
         opts = self.options
         every = max(int(opts.save_every), 1)
         per_step_host = ((not self.static_currents) or self.dynamic_epsilon
@@ -466,8 +551,16 @@ class TDGLSolver:
 
         def save_step(step):
             state = {"step": step, "time": time, "dt": self._prev_dt}
-            values = first_values if (step == 0 and first_values is not None) else self._values()
-            saved.save_time_step(state, values, None if step == 0 else running.values)
+            run_vals = None if step == 0 else running.values
+            if step == 0 and first_values is not None:
+                if saver is not None:
+                    saver.save_host(state, first_values, run_vals)
+                else:
+                    saved.save_time_step(state, first_values, run_vals)
+            elif saver is not None:
+                saver.save_device(state, self._host_values(), run_vals)
+            else:
+                saved.save_time_step(state, self._values(), run_vals)
 
         with _DeferredInterrupt() as intr:
             while True:

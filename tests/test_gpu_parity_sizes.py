@@ -319,8 +319,9 @@ def test_update_seam_positional_contract_with_dynamic_epsilon():
     time, dt = 0.0, 1e-3
     for i in range(5):
         res = solver.update({"step": i, "time": time, "dt": dt}, None, dt, **dict(zip(names, values)))
-        new_dt, *values = res
-        assert len(values) == len(names)
-        np.testing.assert_array_equal(values[-1], eps_func(time))
+        new_dt, *values = res                    # runner.py:424: 7 values, zipped with 6 names
+        threaded = dict(zip(names, values))      # runner.py:420
+        np.testing.assert_array_equal(threaded["epsilon"], eps_func(time))
+        assert threaded["induced_vector_potential"].shape == (E, 2)
         dt = new_dt
         time += dt
