@@ -243,6 +243,13 @@ __device__ __forceinline__ double halo_get(Ctl* ctl, const HaloView& h, const do
   bool ok = true;
   return poll_f64(ctl, h.box + static_cast<long long>(j - h.n_owned) * 2, h.tag, &ok);
 }
+// (float arrays of the V-cycle: the mailbox carries the owner's float value widened to double)
+__device__ __forceinline__ float halo_get(Ctl* ctl, const HaloView& h, const float* __restrict__ x,
+                                          int j) {
+  if (j < h.n_owned) return __ldg(x + j);
+  bool ok = true;
+  return static_cast<float>(poll_f64(ctl, h.box + static_cast<long long>(j - h.n_owned) * 2, h.tag, &ok));
+}
 __device__ __forceinline__ double2 halo_get(Ctl* ctl, const HaloView& h,
                                             const double2* __restrict__ x, int j) {
   if (j < h.n_owned) return __ldg(x + j);

@@ -111,15 +111,24 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
   return w;
 }
 
+// Halo-aware load of a gathered vector entry as double (the mailbox always carries doubles).
+template <typename T>
+__device__ __forceinline__ double halo_val(Ctl* ctl, const HaloView& h, const T* __restrict__ x, int j) {
+  if (j < h.n_owned) return static_cast<double>(__ldg(x + j));
+  bool ok = true;
+  return poll_f64(ctl, h.box + static_cast<long long>(j - h.n_owned) * 2, h.tag, &ok);
+}
+
 // sum_k val[k] * x[idx[k]] over the staged row, four gathers in flight per thread, added in
-// column order.
+// column order, accumulated in double whatever the storage types (TV: matrix values, TX: the
+// gathered vector — float for the operators of the V-cycle, see kw_real).
 // Halo columns — sharded engine only — come out of the mailbox (comm.cuh).  The gathers are
 // issued unconditionally from the array (index clamped), so that they stay independent and
 // in flight together; the rare halo entries are patched afterwards.
-template <bool SH>
-__device__ __forceinline__ double row_dot(const double* __restrict__ sv,
+template <bool SH, typename TV = double, typename TX = double>
+__device__ __forceinline__ double row_dot(const TV* __restrict__ sv,
                                           const int* __restrict__ si, int kb, int ke,
-                                          const double* __restrict__ x, Ctl* ctl,
+                                          const TX* __restrict__ x, Ctl* ctl,
                                           const HaloView& h) {
   double s = 0.0;
   const int last = ke - 1;
@@ -131,13 +140,14 @@ __device__ __forceinline__ double row_dot(const double* __restrict__ sv,
     double x0 = __ldg(x + min(j0, top)), x1 = __ldg(x + min(j1, top)), x2 = __ldg(x + min(j2, top)),
            x3 = __ldg(x + min(j3, top));
     if (SH && max(max(j0, j1), max(j2, j3)) > top) {
-      if (j0 > top) x0 = halo_get(ctl, h, x, j0);
-      if (j1 > top) x1 = halo_get(ctl, h, x, j1);
-      if (j2 > top) x2 = halo_get(ctl, h, x, j2);
-      if (j3 > top) x3 = halo_get(ctl, h, x, j3);
+      if (j0 > top) x0 = halo_val(ctl, h, x, j0);
+      if (j1 > top) x1 = halo_val(ctl, h, x, j1);
+      if (j2 > top) x2 = halo_val(ctl, h, x, j2);
+      if (j3 > top) x3 = halo_val(ctl, h, x, j3);
     }
-    const double v0 = sv[k], v1 = (k + 1 < ke) ? sv[k1] : 0.0, v2 = (k + 2 < ke) ? sv[k2] : 0.0,
-                 v3 = (k + 3 < ke) ? sv[k3] : 0.0;
+    const double v0 = sv[k], v1 = (k + 1 < ke) ? static_cast<double>(sv[k1]) : 0.0,
+                 v2 = (k + 2 < ke) ? static_cast<double>(sv[k2]) : 0.0,
+                 v3 = (k + 3 < ke) ? static_cast<double>(sv[k3]) : 0.0;
     s = fma(v0, x0, s);
     s = fma(v1, x1, s);
     s = fma(v2, x2, s);
@@ -181,13 +191,14 @@ enum : int { kOpSpmvDot = 0, kOpResidual, kOpPresmooth, kOpJacobi, kOpPlain, kOp
              kOpSpmvCg };
 
 struct RealArgs {
-  const double* val = nullptr;
-  const double* x = nullptr;     // gathered vector
-  double* y = nullptr;           // row output
-  const double* b = nullptr;     // right-hand side (residual / smoothers)
-  const double* dinv = nullptr;  // 1 / diag (smoothers)
-  const double* w = nullptr;     // kOpJacobi: dot(w, y) -> *red_out
-  double* r = nullptr;           // kOpPresmooth: residual output
+  // element types are fixed by the kernel instantiation (RealTypes below)
+  const void* val = nullptr;
+  const void* x = nullptr;       // gathered vector
+  void* y = nullptr;             // row output
+  const void* b = nullptr;       // right-hand side (residual / smoothers; gathered by kOpPresmooth)
+  const void* dinv = nullptr;    // 1 / diag (smoothers)
+  const void* w = nullptr;       // kOpJacobi: dot(w, y) -> *red_out (type of b)
+  void* r = nullptr;             // kOpPresmooth: residual output
   double omega = 0.0;
   double* red_out = nullptr;     // reduction result (deterministic), may be null
   double* red2_out = nullptr;    // kOpSpmvCg: the second sum
@@ -197,6 +208,26 @@ struct RealArgs {
   HaloArgs halo;
   PushArgs push;
 };
+
+// Storage types of one kw_real instantiation.  The CG iteration works in double (kTypesD).
+// The V-cycle is only a preconditioner: its operators (A, P, R, 1/diag of every level) and its
+// vectors are stored in float — two thirds of the matrix bytes (4 + 4 instead of 8 + 4 per
+// entry) and half of the vector bytes of the kernels that dominate the step — while every row
+// is still accumulated in double.  The two places where the cycle touches CG's double vectors
+// have their own type sets: the fine-level pre-smoother reads the residual r (kTypesP0), the
+// fine-level post-smoother reads r and writes z (kTypesJ0).
+template <typename TV_, typename TX_, typename TB_, typename TY_, typename TR_>
+struct RealTypes {
+  using V = TV_;   // matrix values, 1 / diag
+  using X = TX_;   // gathered vector x
+  using B = TB_;   // right-hand side b (and w)
+  using Y = TY_;   // output y
+  using R = TR_;   // residual output r (kOpPresmooth)
+};
+using kTypesD = RealTypes<double, double, double, double, double>;
+using kTypesF = RealTypes<float, float, float, float, float>;
+using kTypesP0 = RealTypes<float, float, double, float, float>;
+using kTypesJ0 = RealTypes<float, float, double, double, float>;
 
 // psi is double-buffered, and so are its mailboxes: [b] belongs to buffer b
 struct PsiComm {
@@ -217,15 +248,26 @@ struct PsiComm {
 // lanes share a row, entries k, k + 4, ... each (the AMG operators: rows of 15-30 entries and
 // few of them — a quarter of the dependent-gather chain per thread, four times the gathers in
 // flight; measured 25.8 -> ~12 us for the fine-level restriction).
-template <int OP, bool SH, int LPR>
+template <int OP, bool SH, int LPR, typename T = kTypesD>
 __global__ void __launch_bounds__(kWinRows, 8)   // 8 CTAs/SM = 2048 threads: <= 32 registers
 kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned int* counter) {
+  using TV = typename T::V;
+  using TX = typename T::X;
+  using TB = typename T::B;
+  using TY = typename T::Y;
+  using TR = typename T::R;
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double red[32];
-  const WinRow w = window_stage<8, 0, LPR>(m, a.val, nullptr, win_smem, &bar);
-  const double* sv = reinterpret_cast<const double*>(win_smem);
-  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * 8);
+  const WinRow w = window_stage<sizeof(TV), 0, LPR>(m, a.val, nullptr, win_smem, &bar);
+  const TV* sv = reinterpret_cast<const TV*>(win_smem);
+  const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * sizeof(TV));
+  const TX* ax = static_cast<const TX*>(a.x);
+  const TB* ab = static_cast<const TB*>(a.b);
+  const TB* aw = static_cast<const TB*>(a.w);
+  const TV* adinv = static_cast<const TV*>(a.dinv);
+  TY* ay = static_cast<TY*>(a.y);
+  TR* ar = static_cast<TR*>(a.r);
   griddep_wait();
   const bool live = (ctl->status == 0);
   const bool in = live && w.row < m.rows;
@@ -242,11 +284,11 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
   if (lead) {
     if (OP == kOpResidual || OP == kOpPresmooth || OP == kOpJacobi || OP == kOpSpmvCg)
-      bi = a.b[w.row];
-    if (OP == kOpPresmooth || OP == kOpJacobi) di = a.dinv[w.row];
-    if (OP == kOpSpmvDot || OP == kOpJacobi || OP == kOpSpmvCg) xi = a.x[w.row];
-    if (OP == kOpPlainAdd) xi = a.y[w.row];
-    if (OP == kOpJacobi && a.w != nullptr) wi = a.w[w.row];
+      bi = ab[w.row];
+    if (OP == kOpPresmooth || OP == kOpJacobi) di = adinv[w.row];
+    if (OP == kOpSpmvDot || OP == kOpJacobi || OP == kOpSpmvCg) xi = ax[w.row];
+    if (OP == kOpPlainAdd) xi = ay[w.row];
+    if (OP == kOpJacobi && aw != nullptr) wi = aw[w.row];
   }
   mbar_wait(&bar, 0);
   if (!live) return;
@@ -261,31 +303,31 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
         const int k1 = min(k + LPR, last);
         const bool two = k + LPR < w.ke;
         const int j0 = si[k], j1 = si[k1];
-        double b0 = __ldg(a.b + min(j0, top)), b1 = __ldg(a.b + min(j1, top));
+        double b0 = __ldg(ab + min(j0, top)), b1 = __ldg(ab + min(j1, top));
         if (SH && max(j0, j1) > top) {
-          if (j0 > top) b0 = halo_get(ctl, hv, a.b, j0);
-          if (j1 > top) b1 = halo_get(ctl, hv, a.b, j1);
+          if (j0 > top) b0 = halo_val(ctl, hv, ab, j0);
+          if (j1 > top) b1 = halo_val(ctl, hv, ab, j1);
         }
-        const double t0 = __ldg(a.dinv + j0) * b0;
-        const double t1 = __ldg(a.dinv + j1) * b1;
-        s = fma(sv[k], a.omega * t0, s);
-        s = fma(two ? sv[k1] : 0.0, a.omega * t1, s);
+        const double t0 = static_cast<double>(__ldg(adinv + j0)) * b0;
+        const double t1 = static_cast<double>(__ldg(adinv + j1)) * b1;
+        s = fma(static_cast<double>(sv[k]), a.omega * t0, s);
+        s = fma(two ? static_cast<double>(sv[k1]) : 0.0, a.omega * t1, s);
       }
     } else if (LPR == 1) {
-      s = row_dot<SH>(sv, si, w.kb, w.ke, a.x, ctl, hv);
+      s = row_dot<SH, TV, TX>(sv, si, w.kb, w.ke, ax, ctl, hv);
     } else {
 #pragma unroll 2
       for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
         const int k1 = k + LPR;
         const bool two = k1 < w.ke;
         const int j0 = si[k], j1 = two ? si[k1] : j0;
-        double x0 = __ldg(a.x + min(j0, top)), x1 = __ldg(a.x + min(j1, top));
+        double x0 = __ldg(ax + min(j0, top)), x1 = __ldg(ax + min(j1, top));
         if (SH && max(j0, j1) > top) {
-          if (j0 > top) x0 = halo_get(ctl, hv, a.x, j0);
-          if (j1 > top) x1 = halo_get(ctl, hv, a.x, j1);
+          if (j0 > top) x0 = halo_val(ctl, hv, ax, j0);
+          if (j1 > top) x1 = halo_val(ctl, hv, ax, j1);
         }
-        s = fma(sv[k], x0, s);
-        s = fma(two ? sv[k1] : 0.0, x1, s);
+        s = fma(static_cast<double>(sv[k]), x0, s);
+        s = fma(two ? static_cast<double>(sv[k1]) : 0.0, x1, s);
       }
     }
   }
@@ -293,29 +335,35 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   if (lead) {
     double out;  // the value other shards may need
     if (OP == kOpSpmvDot) {
-      a.y[w.row] = out = s;
+      ay[w.row] = static_cast<TY>(out = s);
       d = s * xi;
     } else if (OP == kOpSpmvCg) {
-      a.y[w.row] = out = s;
+      ay[w.row] = static_cast<TY>(out = s);
       d = bi * xi;
       d2 = s * xi;
     } else if (OP == kOpResidual) {
       const double ri = bi - s;
-      a.y[w.row] = out = ri;
+      ay[w.row] = static_cast<TY>(out = ri);
       d = ri * ri;
     } else if (OP == kOpPresmooth) {
-      a.y[w.row] = a.omega * di * bi;
-      a.r[w.row] = out = bi - s;
+      ay[w.row] = static_cast<TY>(a.omega * di * bi);
+      ar[w.row] = static_cast<TR>(out = bi - s);
     } else if (OP == kOpJacobi) {
       const double yi = xi + a.omega * di * (bi - s);
-      a.y[w.row] = out = yi;
+      ay[w.row] = static_cast<TY>(out = yi);
       d = wi * yi;
     } else if (OP == kOpPlain) {
-      a.y[w.row] = out = s;
+      ay[w.row] = static_cast<TY>(out = s);
     } else {
-      a.y[w.row] = out = xi + s;
+      ay[w.row] = static_cast<TY>(out = xi + s);
     }
-    if (SH && tag_out != 0u) push_row(comm, a.push, tag_out, w.row, out);
+    // (what travels is what the owner stored: a float-typed output is rounded first, so that
+    // a halo copy equals the owner's value bit for bit)
+    if (SH && tag_out != 0u) {
+      const double sent = (OP == kOpPresmooth) ? static_cast<double>(static_cast<TR>(out))
+                                               : static_cast<double>(static_cast<TY>(out));
+      push_row(comm, a.push, tag_out, w.row, sent);
+    }
     (void)out;
   }
   if (OP == kOpSpmvCg) {
@@ -562,133 +610,6 @@ kw_psi_laplacian(WinCsr m, const double2* __restrict__ lval,
     none.n_owned = 0x7fffffff; none.box = nullptr; none.tag = 0;
     const double2 lap = row_dot_c<false>(sv, si, w.kb, w.ke, x, nullptr, none);
     y[w.row] = fixed[w.row] ? x[w.row] : lap;
-  }
-}
-
-}  // namespace tdgl
-
-namespace tdgl {
-
-// ---- fused coarse levels -------------------------------------------------------------------------
-// The coarse part of the V-cycle — every level with at most kFuseBelow rows, down to the dense
-// coarsest solve and back up — as ONE kernel: a single thread-block cluster of 8 CTAs walks
-// through the phases with hardware cluster barriers between them instead of one kernel launch
-// per operator per level.  These levels hold ~0.2 % of the unknowns but, launched one by one,
-// cost a third of the V-cycle's launches; their matrices and vectors stay L2-resident,
-// so no shared-memory staging is needed — a phase is a few dependent L2 round trips.
-//   down:  x = w D^-1 b ; r = b - A x ; b' = R r          (per level)
-//   coarsest: y = Minv b (dense)
-//   up:    x += P y' ; y = x + w D^-1 (b - A x)            (per level)
-// Input: b of level `first`; output: y of level `first`.  In the sharded engine these levels
-// are replicated on every shard (shard.h), so the kernel contains no exchange.
-
-constexpr int kFuseBelow = 4096;    // rows: what one 8-CTA cluster turns around in a few microseconds
-constexpr int kFuseCtas = 8;        // portable cluster size
-constexpr int kFuseThreads = 1024;
-
-struct FusedCsr {
-  int rows = 0;
-  const int* ptr = nullptr;
-  const int* idx = nullptr;
-  const double* val = nullptr;
-};
-struct FusedLevel {
-  int n = 0;
-  FusedCsr A, P, R;   // P: n x n_coarse, R: n_coarse x n
-  const double* dinv = nullptr;
-  double omega = 0.0;
-  double *b = nullptr, *x = nullptr, *r = nullptr, *y = nullptr;
-};
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// One row = one group of 8 lanes (the rows of these levels are long, 15-30 entries, and there
-// are few of them: spreading a row over lanes keeps the dependent-load chains short).
-// `term(k)` returns the k-th product of the row.  All 32 lanes of a warp must call this.
-template <typename F>
-__device__ __forceinline__ double fused_row_sum(const FusedCsr& m, int row, bool live, int sub,
-                                                F term) {
-  double s = 0.0;
-  if (live) {
-    const int kb = __ldg(m.ptr + row), ke = __ldg(m.ptr + row + 1);
-    for (int k = kb + sub; k < ke; k += 8) s += term(k);
-  }
-  return group_sum<8>(s);
-}
-
-__global__ void __cluster_dims__(kFuseCtas, 1, 1) __launch_bounds__(kFuseThreads)
-k_coarse_cycle(const Ctl* __restrict__ ctl, const FusedLevel* __restrict__ lv, int first,
-               int n_levels, const double* __restrict__ coarse_inv, int nc) {
-  griddep_enter();
-  if (ctl->status != 0) return;  // uniform over the cluster
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nth = gridDim.x * blockDim.x;
-  const int grp = tid >> 3, sub = tid & 7, ngrp = nth >> 3;
-  for (int l = first; l + 1 < n_levels; ++l) {
-    const FusedLevel L = lv[l];
-    // x = w D^-1 b ; r = b - A x  (x_j formed on the fly from b_j, as kw_real<presmooth>)
-    for (int base = 0; base < L.n; base += ngrp) {
-      const int i = base + grp;
-      const bool live = i < L.n;
-      const double s = fused_row_sum(L.A, i, live, sub, [&](int k) {
-        const int j = __ldg(L.A.idx + k);
-        return __ldg(L.A.val + k) * (L.omega * (__ldg(L.dinv + j) * __ldcg(L.b + j)));
-      });
-      if (live && sub == 0) {
-        const double bi = __ldcg(L.b + i);
-        __stcg(L.x + i, L.omega * __ldg(L.dinv + i) * bi);
-        __stcg(L.r + i, bi - s);
-      }
-    }
-    cluster_sync_all();
-    const FusedLevel C = lv[l + 1];
-    for (int base = 0; base < L.R.rows; base += ngrp) {
-      const int i = base + grp;
-      const bool live = i < L.R.rows;
-      const double s = fused_row_sum(L.R, i, live, sub, [&](int k) {
-        return __ldg(L.R.val + k) * __ldcg(L.r + __ldg(L.R.idx + k));
-      });
-      if (live && sub == 0) __stcg(C.b + i, s);
-    }
-    cluster_sync_all();
-  }
-  {
-    const FusedLevel C = lv[n_levels - 1];
-    const int warp = tid >> 5, lane = threadIdx.x & 31, nwarp = nth >> 5;
-    for (int i = warp; i < nc; i += nwarp) {
-      const double* row = coarse_inv + static_cast<size_t>(i) * nc;
-      double s = 0.0;
-      for (int j = lane; j < nc; j += 32) s += __ldg(row + j) * __ldcg(C.b + j);
-      s = warp_sum(s);
-      if (lane == 0) __stcg(C.y + i, s);
-    }
-    cluster_sync_all();
-  }
-  for (int l = n_levels - 2; l >= first; --l) {
-    const FusedLevel L = lv[l];
-    const FusedLevel C = lv[l + 1];
-    for (int base = 0; base < L.n; base += ngrp) {
-      const int i = base + grp;
-      const bool live = i < L.n;
-      const double s = fused_row_sum(L.P, i, live, sub, [&](int k) {
-        return __ldg(L.P.val + k) * __ldcg(C.y + __ldg(L.P.idx + k));
-      });
-      if (live && sub == 0) __stcg(L.x + i, __ldcg(L.x + i) + s);
-    }
-    cluster_sync_all();
-    for (int base = 0; base < L.n; base += ngrp) {
-      const int i = base + grp;
-      const bool live = i < L.n;
-      const double s = fused_row_sum(L.A, i, live, sub, [&](int k) {
-        return __ldg(L.A.val + k) * __ldcg(L.x + __ldg(L.A.idx + k));
-      });
-      if (live && sub == 0)
-        __stcg(L.y + i, __ldcg(L.x + i) + L.omega * __ldg(L.dinv + i) * (__ldcg(L.b + i) - s));
-    }
-    if (l > first) cluster_sync_all();
   }
 }
 

@@ -73,28 +73,31 @@ struct DevBuf {
 // A real CSR matrix as the window kernels see it: structure + values + rows per CTA.
 struct CsrView {
   WinCsr m;
-  const double* val = nullptr;
+  const void* val = nullptr;   // float (operators of the V-cycle) or double (level-0 CG matrix)
   int win = kWinRows;  // rows per window
   int lpr = 1;         // lanes per row: threads per CTA = win * lpr
+  int vbytes = 8;      // bytes per value
 };
 
+// The operators of the V-cycle (A of the levels >= 1, P and R of every level) are stored in
+// float: the cycle is a preconditioner, CG itself runs in double (csr_window.cuh, RealTypes).
 struct DevCsr {
   int rows = 0, cols = 0, win = kWinRows, cap = 0;
   int lpr = 1;            // lanes per row of the kernels that apply it (4: long rows)
   int64_t nnz = 0;
   DevBuf<int> ptr, idx;   // idx / val carry 4 padding elements (see csr_window.cuh)
   DevBuf<int2> wdesc;     // per window {first staged nnz, staged nnz count}
-  DevBuf<double> val;
-  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p, wdesc.p}, val.p, win, lpr}; }
+  DevBuf<float> val;
+  CsrView view() const { return CsrView{WinCsr{rows, cap, ptr.p, idx.p, wdesc.p}, val.p, win, lpr, 4}; }
 };
 
 struct DevLevel {
   int n = 0;            // rows owned by this shard
   int nx = 0;           // owned + halo entries of a vector on this level
   DevCsr A, P, R;       // P: n x n_coarse, R: n_coarse x n
-  DevBuf<double> dinv;  // nx entries (the halo part is static, filled at setup)
+  DevBuf<float> dinv;   // nx entries (the halo part is static, filled at setup)
   double omega = 0.0;   // Jacobi weight (4/3) / rho(D^-1 A)
-  DevBuf<double> b, x, y, r;  // work vectors in the arena (level 0 uses the CG vectors for b / y)
+  DevBuf<float> b, x, y, r;   // work vectors in the arena (level 0: b = CG's r, y = CG's z, double)
   // sharded engine, partitioned / gathered levels: per owned row the (peer, halo entry)
   // pairs its value is stored to, and a per-32-rows "anything to send" byte
   DevBuf<int> push_rptr;
@@ -152,7 +155,8 @@ struct Config {
   int world = 1;   // number of shards (one GPU / process each, or several per process)
   int rank = 0;    // this engine's shard
   int replicate_below = 0;  // AMG levels with at most this many rows are replicated (0: 32768)
-  int fuse_coarse = 0;      // 1: levels <= 4096 rows run as one cluster kernel (k_coarse_cycle)
+  int fuse_coarse = 0;      // (accepted, ignored: the fused coarse-level kernel of round 1 was
+                            // measured not to be faster and removed)
 };
 
 class Engine {
@@ -282,9 +286,7 @@ class Engine {
   DevBuf<double> run_dt_, run_mu_, run_theta_;
   // ---- mu solver ----------------------------------------------------------------------------
   std::vector<DevLevel> levels_;
-  DevBuf<double> coarse_inv_;
-  DevBuf<FusedLevel> fused_;   // per-level operator table of the fused coarse-level kernel
-  int fuse_from_ = -1;         // first level the cluster kernel handles (-1: none)
+  DevBuf<float> coarse_inv_;
   int nc_ = 0;
   int64_t amg_nnz_ = 0;
   DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_, cg_s_;   // cg_Ap_: w = A z; cg_s_: A p
@@ -347,7 +349,7 @@ class Engine {
   static int grid_win(int rows, int win) { return (rows + win - 1) / win; }
   WinCsr site_csr() const { return WinCsr{N_, cap0_, ptr_.p, idx_.p, wdesc0_.p}; }
   int sm_count_ = 148;
-  template <int OP>
+  template <int OP, typename T = kTypesD>
   void launch_real(const CsrView& A, const RealArgs& a);
   int grid_flat(int n) const {
     int g = (n + kBlock - 1) / kBlock;
@@ -355,11 +357,6 @@ class Engine {
   }
   void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 0);
   void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);
-  void launch_plain(const CsrView& A, const double* x, double* y, bool add);
-  void launch_presmooth(const CsrView& A, const double* dinv, double omega, const double* b,
-                        double* x, double* r);
-  void launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
-                     const double* x, double* y, const double* w, double* dot_out);
   void enqueue_vcycle(double* r_in, double* z_out, double* rz_out);
   void enqueue_psi_step(double* sq_out, double dt_override);
   void enqueue_mu_rhs(double* rhs_raw);
@@ -371,7 +368,7 @@ class Engine {
   PushArgs make_push(int level, int channel, int tag_mode) const;
   HaloArgs make_halo(int level, int channel, int tag_mode) const;
   PsiComm make_psi_comm() const;
-  void enqueue_unpack(int level, int channel, int tag_mode, double* vec);
+  void enqueue_unpack(int level, int channel, int tag_mode, float* vec);
   void fill_state_boxes();
   void unpack_state_halos(int cur);
   void upload_comm(double* const* peers);
@@ -379,9 +376,11 @@ class Engine {
   void build_graph();
   void sync_ctl_to_host();
   void push_ctl();
-  DevBuf<double> aval_;  // level-0 mu matrix values; structure shared with ptr_/idx_
-  CsrView A0() const { return CsrView{site_csr(), aval_.p, win0_, 1}; }
-  CsrView levelA(size_t l) const { return l == 0 ? A0() : levels_[l].A.view(); }
+  DevBuf<double> aval_;   // level-0 mu matrix values (CG, rhs); structure shared with ptr_/idx_
+  DevBuf<float> aval32_;  // the same values in float: the fine-level smoothers of the V-cycle
+  CsrView A0() const { return CsrView{site_csr(), aval_.p, win0_, 1, 8}; }
+  CsrView A0f() const { return CsrView{site_csr(), aval32_.p, win0_, 1, 4}; }
+  CsrView levelA(size_t l) const { return l == 0 ? A0f() : levels_[l].A.view(); }
 };
 
 }  // namespace tdgl

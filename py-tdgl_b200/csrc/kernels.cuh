@@ -193,19 +193,20 @@ __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
 
 // Coarsest level: x = Minv b with a dense row-major rows x nc matrix (rows = the rows this
 // shard owns, all nc for a single shard); one warp per row.
+template <typename TM, typename TB, typename TX>
 __global__ void __launch_bounds__(kBlock)
-k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const double* __restrict__ M,
-               const double* __restrict__ b, double* __restrict__ x) {
+k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const TM* __restrict__ M,
+               const TB* __restrict__ b, TX* __restrict__ x) {
   griddep_enter();
   if (ctl->status != 0) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const double* row = M + static_cast<size_t>(warp) * nc;
+  const TM* row = M + static_cast<size_t>(warp) * nc;
   double s = 0.0;
-  for (int j = lane; j < nc; j += 32) s += row[j] * b[j];
+  for (int j = lane; j < nc; j += 32) s = fma(static_cast<double>(row[j]), static_cast<double>(b[j]), s);
   s = warp_sum(s);
-  if (lane == 0) x[warp] = s;
+  if (lane == 0) x[warp] = static_cast<TX>(s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -99,11 +99,11 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row) 
   d.lpr = lanes_per_row;
   // (a CTA has at most kWinRows threads: windows of a matrix with several lanes per row
   // hold correspondingly fewer rows)
-  d.win = pick_window(h.ptr, h.rows, 12, 64 * 1024, &d.cap, kWinRows / lanes_per_row);
+  d.win = pick_window(h.ptr, h.rows, 8, 64 * 1024, &d.cap, kWinRows / lanes_per_row);
   std::vector<int32_t> idx(h.idx);
-  std::vector<double> val(h.val);
+  std::vector<float> val(h.val.begin(), h.val.end());   // V-cycle operators live in float
   idx.resize(idx.size() + 4, 0);   // bulk copies round the window up to 4 entries
-  val.resize(val.size() + 4, 0.0);
+  val.resize(val.size() + 4, 0.0f);
   d.ptr.upload(h.ptr, stream_);
   d.idx.upload(idx, stream_);
   d.val.upload(val, stream_);
@@ -303,6 +303,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   eidx_.upload(ledge, stream_);
   head_.upload(lhead, stream_);
   aval_.upload(aval_host, stream_);
+  {
+    std::vector<float> a32(aval_host.begin(), aval_host.end());
+    aval32_.upload(a32, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
   lval_.alloc(nnz_ + 4);
   lval_.zero(stream_);
   {
@@ -404,8 +409,8 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.A.rows, dl.A.win));
     }
     {
-      std::vector<double> dloc(dl.nx);
-      for (int k = 0; k < dl.nx; ++k) dloc[k] = hl.dinv[plan_.global_index(li, rank_, k)];
+      std::vector<float> dloc(dl.nx);
+      for (int k = 0; k < dl.nx; ++k) dloc[k] = static_cast<float>(hl.dinv[plan_.global_index(li, rank_, k)]);
       dl.dinv.upload(dloc, stream_);
       TDGL_CUDA(cudaStreamSynchronize(stream_));
     }
@@ -451,38 +456,15 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     }
   }
   {
-    // levels small enough to run fused in one cluster kernel (replicated levels only)
-    fuse_from_ = -1;
-    if (cfg_.fuse_coarse == 1 || std::getenv("TDGL_B200_FUSE") != nullptr)
-      for (size_t l = 1; l + 1 < L; ++l)
-        if (H.levels[l].A.rows <= kFuseBelow && (world_ == 1 || static_cast<int>(l) >= rep_level)) {
-          fuse_from_ = static_cast<int>(l);
-          break;
-        }
-    std::vector<FusedLevel> fl(L);
-    for (size_t l = 1; l < L; ++l) {
-      DevLevel& dl = levels_[l];
-      FusedLevel& f = fl[l];
-      f.n = dl.n;
-      f.A = FusedCsr{dl.A.rows, dl.A.ptr.p, dl.A.idx.p, dl.A.val.p};
-      f.P = FusedCsr{dl.P.rows, dl.P.ptr.p, dl.P.idx.p, dl.P.val.p};
-      f.R = FusedCsr{dl.R.rows, dl.R.ptr.p, dl.R.idx.p, dl.R.val.p};
-      f.dinv = dl.dinv.p;
-      f.omega = dl.omega;
-      f.b = dl.b.p; f.x = dl.x.p; f.r = dl.r.p; f.y = dl.y.p;
-    }
-    fused_.upload(fl, stream_);
-    TDGL_CUDA(cudaStreamSynchronize(stream_));
-  }
-  {
     // coarsest level: dense inverse with rows and columns in this shard's local order
     const int lc = static_cast<int>(L) - 1;
     nc_ = static_cast<int>(H.nc);
-    std::vector<double> loc(static_cast<size_t>(nc_) * nc_, 0.0);
+    std::vector<float> loc(static_cast<size_t>(nc_) * nc_, 0.0f);
     for (int i = 0; i < nc_; ++i) {
       const int64_t gi = plan_.global_index(lc, rank_, i);
       for (int j = 0; j < nc_; ++j)
-        loc[static_cast<size_t>(i) * nc_ + j] = H.coarse_inv[gi * nc_ + plan_.global_index(lc, rank_, j)];
+        loc[static_cast<size_t>(i) * nc_ + j] =
+            static_cast<float>(H.coarse_inv[gi * nc_ + plan_.global_index(lc, rank_, j)]);
     }
     coarse_inv_.upload(loc, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
@@ -670,17 +652,19 @@ void Engine::configure_kernels() {
   auto allow = [&](const void* f) {
     TDGL_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   };
-#define TDGL_ALLOW_REAL(OP)                                            \
-  allow(reinterpret_cast<const void*>(&kw_real<OP, false, 1>));        \
-  allow(reinterpret_cast<const void*>(&kw_real<OP, true, 1>));         \
-  allow(reinterpret_cast<const void*>(&kw_real<OP, false, 4>));        \
-  allow(reinterpret_cast<const void*>(&kw_real<OP, true, 4>));
-  TDGL_ALLOW_REAL(kOpSpmvDot)
-  TDGL_ALLOW_REAL(kOpSpmvCg)
-  TDGL_ALLOW_REAL(kOpPresmooth)
-  TDGL_ALLOW_REAL(kOpJacobi)
-  TDGL_ALLOW_REAL(kOpPlain)
-  TDGL_ALLOW_REAL(kOpPlainAdd)
+#define TDGL_ALLOW_REAL(OP, T)                                          \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, false, 1, T>));     \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, true, 1, T>));      \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, false, 4, T>));     \
+  allow(reinterpret_cast<const void*>(&kw_real<OP, true, 4, T>));
+  TDGL_ALLOW_REAL(kOpSpmvDot, kTypesD)
+  TDGL_ALLOW_REAL(kOpSpmvCg, kTypesD)
+  TDGL_ALLOW_REAL(kOpPresmooth, kTypesF)
+  TDGL_ALLOW_REAL(kOpPresmooth, kTypesP0)
+  TDGL_ALLOW_REAL(kOpJacobi, kTypesF)
+  TDGL_ALLOW_REAL(kOpJacobi, kTypesJ0)
+  TDGL_ALLOW_REAL(kOpPlain, kTypesF)
+  TDGL_ALLOW_REAL(kOpPlainAdd, kTypesF)
 #undef TDGL_ALLOW_REAL
   allow(reinterpret_cast<const void*>(&kw_psi_step<false>));
   allow(reinterpret_cast<const void*>(&kw_psi_step<true>));
@@ -692,21 +676,23 @@ void Engine::configure_kernels() {
 #define TDGL_LAUNCH_CHECK()                                                                \
   do { ++launches_; TDGL_CUDA(cudaGetLastError()); } while (0)
 
-template <int OP>
+template <int OP, typename T>
 void Engine::launch_real(const CsrView& A, const RealArgs& a) {
-  const size_t smem = static_cast<size_t>(A.m.cap) * 12;
+  if (A.vbytes != static_cast<int>(sizeof(typename T::V)))
+    throw std::logic_error("kw_real: value type of the matrix and of the kernel differ");
+  const size_t smem = static_cast<size_t>(A.m.cap) * (A.vbytes + 4);
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
   const int grid = grid_win(A.m.rows, A.win), block = A.win * A.lpr;
   if (A.lpr == 4) {
     if (comm_on_)
-      launch_k(kw_real<OP, true, 4>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+      launch_k(kw_real<OP, true, 4, T>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
     else
-      launch_k(kw_real<OP, false, 4>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+      launch_k(kw_real<OP, false, 4, T>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
   } else {
     if (comm_on_)
-      launch_k(kw_real<OP, true, 1>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+      launch_k(kw_real<OP, true, 1, T>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
     else
-      launch_k(kw_real<OP, false, 1>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
+      launch_k(kw_real<OP, false, 1, T>, grid, block, smem, ctl_.p, comm(), A.m, a, partials_.p, counter_.p);
   }
   TDGL_LAUNCH_CHECK();
 }
@@ -717,36 +703,15 @@ void Engine::launch_spmv(const CsrView& A, const double* x, double* y, double* d
   launch_real<kOpSpmvDot>(A, a);
 }
 
-void Engine::launch_plain(const CsrView& A, const double* x, double* y, bool add) {
-  RealArgs a;
-  a.val = A.val; a.x = x; a.y = y;
-  if (add) launch_real<kOpPlainAdd>(A, a); else launch_real<kOpPlain>(A, a);
-}
-
-void Engine::launch_presmooth(const CsrView& A, const double* dinv, double omega,
-                              const double* b, double* x, double* r) {
-  RealArgs a;
-  a.val = A.val; a.dinv = dinv; a.omega = omega; a.b = b; a.y = x; a.r = r;
-  launch_real<kOpPresmooth>(A, a);
-}
-
-void Engine::launch_jacobi(const CsrView& A, const double* dinv, double omega, const double* b,
-                           const double* x, double* y, const double* w, double* dot_out) {
-  RealArgs a;
-  a.val = A.val; a.dinv = dinv; a.omega = omega; a.b = b; a.x = x; a.y = y; a.w = w;
-  a.red_out = dot_out;
-  launch_real<kOpJacobi>(A, a);
-}
-
 
 // z = M r : one V(1,1) cycle of the smoothed-aggregation hierarchy, weighted Jacobi
 // smoothing, dense solve on the coarsest level.  rz_out <- dot(r, z).
 // Mailbox -> halo slots of a plain array (the consumers that do not read mailboxes).
-void Engine::enqueue_unpack(int level, int channel, int tag_mode, double* vec) {
+void Engine::enqueue_unpack(int level, int channel, int tag_mode, float* vec) {
   if (!comm_on_ || level > plan_.rep) return;
   const int n_halo = static_cast<int>(plan_.halo[level][rank_].size());
   if (n_halo == 0) return;
-  launch_k(k_unpack<double>, std::min((n_halo + 1023) / 1024, 64), 1024, 0, ctl_.p, comm_.p,
+  launch_k(k_unpack<float>, std::min((n_halo + 1023) / 1024, 64), 1024, 0, ctl_.p, comm_.p,
            make_halo(level, channel, tag_mode), n_halo, vec);
   TDGL_LAUNCH_CHECK();
 }
@@ -755,7 +720,8 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   const size_t L = levels_.size();
   if (L == 1) {
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    launch_k(k_dense_matvec, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p, r_in, z_out);
+    launch_k(k_dense_matvec<float, double, double>, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p,
+             r_in, z_out);
     TDGL_LAUNCH_CHECK();
     if (rz_out != nullptr) {
       launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
@@ -763,62 +729,60 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     }
     return;
   }
+  // The cycle's operators and vectors are float (engine.h, csr_window.cuh RealTypes); only its
+  // input r and its output z, CG's vectors, are double.
   // Sharded: on a partitioned level (l < rep) every kernel stores the boundary rows of its
   // output into the neighbours' mailboxes and reads the halo columns of its input out of its
   // own (comm.cuh) — there is no exchange step.  The right-hand side of level rep is
   // all-gathered the same way and unpacked into a plain array, and everything from there
   // down is computed redundantly by every shard.
-  // Levels fuse_from_ .. L-1 (the small ones) can run as ONE cluster kernel.
   const int rep = comm_on_ ? plan_.rep : -1;
   const int Li = static_cast<int>(L);
-  const int split = (fuse_from_ >= 1 && fuse_from_ <= Li - 2) ? fuse_from_ : Li - 1;
+  const int split = Li - 1;
   auto chan = [](int l, int which) { return vec_id(l, which); };
   for (int li = 0; li < split; ++li) {
     DevLevel& lv = levels_[li];
-    double* b = (li == 0) ? r_in : lv.b.p;
     {
       RealArgs a;
-      a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.b = b; a.y = lv.x.p; a.r = lv.r.p;
+      a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.y = lv.x.p; a.r = lv.r.p;
+      a.b = (li == 0) ? static_cast<const void*>(r_in) : static_cast<const void*>(lv.b.p);
       if (li < rep) {
         a.halo = make_halo(li, li == 0 ? kVecCgR : chan(li, 2), kTagIter);
         a.push = make_push(li, chan(li, 1), kTagIter);
       }
-      launch_real<kOpPresmooth>(levelA(li), a);
+      if (li == 0) launch_real<kOpPresmooth, kTypesP0>(levelA(li), a);
+      else launch_real<kOpPresmooth, kTypesF>(levelA(li), a);
     }
     {
       RealArgs a;
       a.val = lv.R.view().val; a.x = lv.r.p; a.y = levels_[li + 1].b.p;
       if (li < rep) a.halo = make_halo(li, chan(li, 1), kTagIter);
       if (li + 1 <= rep) a.push = make_push(li + 1, chan(li + 1, 2), kTagIter);
-      launch_real<kOpPlain>(lv.R.view(), a);
+      launch_real<kOpPlain, kTypesF>(lv.R.view(), a);
     }
     if (li + 1 == rep) enqueue_unpack(rep, chan(rep, 2), kTagIter, levels_[rep].b.p);
   }
   {
     DevLevel& c = levels_[split];
-    if (split < Li - 1) {
-      launch_k(k_coarse_cycle, kFuseCtas, kFuseThreads, 0, ctl_.p, fused_.p, split, Li,
-                                                             coarse_inv_.p, nc_);
-    } else {
-      const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-      launch_k(k_dense_matvec, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p, c.b.p, c.y.p);
-    }
+    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
+    launch_k(k_dense_matvec<float, float, float>, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p,
+             c.b.p, c.y.p);
     TDGL_LAUNCH_CHECK();
   }
   for (int li = split - 1; li >= 0; --li) {
     DevLevel& lv = levels_[li];
-    const double* b = (li == 0) ? r_in : lv.b.p;
-    double* y = (li == 0) ? z_out : lv.y.p;
     {
       RealArgs a;
       a.val = lv.P.view().val; a.x = levels_[li + 1].y.p; a.y = lv.x.p;
       if (li + 1 < rep) a.halo = make_halo(li + 1, chan(li + 1, 3), kTagIter);
       if (li < rep) a.push = make_push(li, chan(li, 0), kTagIter);
-      launch_real<kOpPlainAdd>(lv.P.view(), a);
+      launch_real<kOpPlainAdd, kTypesF>(lv.P.view(), a);
     }
     {
       RealArgs a;
-      a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.b = b; a.x = lv.x.p; a.y = y;
+      a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.x = lv.x.p;
+      a.b = (li == 0) ? static_cast<const void*>(r_in) : static_cast<const void*>(lv.b.p);
+      a.y = (li == 0) ? static_cast<void*>(z_out) : static_cast<void*>(lv.y.p);
       a.w = (li == 0 && rz_out != nullptr) ? r_in : nullptr;
       a.red_out = (li == 0) ? rz_out : nullptr;
       if (li < rep) {
@@ -826,7 +790,8 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
         // level 0: z, whose halo the CG iteration's SpMV reads, travels on p's old channel
         a.push = li > 0 ? make_push(li, chan(li, 3), kTagIter) : make_push(0, kVecCgP, kTagIter);
       }
-      launch_real<kOpJacobi>(levelA(li), a);
+      if (li == 0) launch_real<kOpJacobi, kTypesJ0>(levelA(li), a);
+      else launch_real<kOpJacobi, kTypesF>(levelA(li), a);
     }
   }
 }
@@ -1372,7 +1337,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     // the graph's kernels were launched by the device-side loops; account for them
     const int64_t L = static_cast<int64_t>(levels_.size());
     const int64_t ex_step = 0, ex_it = world_ > 1 ? 1 : 0;  // (the all-gather unpack of level rep)
-    const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
+    const int64_t split = L - 1;
     const int64_t passes = scr_on_ ? h_ctl_->total_scr_it : h_ctl_->steps_done;
     // per step: k_step_begin, k_step_end (+ ramp links, + |psi|^2 snapshot); per pass: psi step +
     // control, rhs, cg_begin, mu_guess, weighted_sum, shift (+ 5 screening kernels); per dt
@@ -1532,7 +1497,7 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     sync_ctl_to_host();
     {
       const int64_t L = static_cast<int64_t>(levels_.size());
-      const int64_t split = (fuse_from_ >= 1 && fuse_from_ <= L - 2) ? fuse_from_ : L - 1;
+      const int64_t split = L - 1;
       launches_ += h_ctl_->steps_done * (2 + (ramp_on_ ? 1 : 0)) + h_ctl_->steps_done * 7 +
                    h_ctl_->total_retries * 2 + h_ctl_->total_cg_it * (2 + 4 * split + 1);
     }
@@ -1893,22 +1858,36 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
         TDGL_LAUNCH_CHECK();
         host_solve_loop();
         break;
-      case 5:
+      case 5: {
         if (!multi) throw std::invalid_argument("single-level hierarchy");
-        launch_presmooth(A0(), levels_[0].dinv.p, levels_[0].omega, cg_r_.p, levels_[0].x.p, levels_[0].r.p);
+        RealArgs a;
+        a.val = A0f().val; a.dinv = levels_[0].dinv.p; a.omega = levels_[0].omega; a.b = cg_r_.p;
+        a.y = levels_[0].x.p; a.r = levels_[0].r.p;
+        launch_real<kOpPresmooth, kTypesP0>(A0f(), a);
         break;
-      case 6:
+      }
+      case 6: {
         if (!multi) throw std::invalid_argument("single-level hierarchy");
-        launch_jacobi(A0(), levels_[0].dinv.p, levels_[0].omega, cg_r_.p, levels_[0].x.p, cg_z_.p, nullptr, nullptr);
+        RealArgs a;
+        a.val = A0f().val; a.dinv = levels_[0].dinv.p; a.omega = levels_[0].omega; a.b = cg_r_.p;
+        a.x = levels_[0].x.p; a.y = cg_z_.p;
+        launch_real<kOpJacobi, kTypesJ0>(A0f(), a);
         break;
-      case 7:
+      }
+      case 7: {
         if (!multi) throw std::invalid_argument("single-level hierarchy");
-        launch_plain(levels_[0].R.view(), levels_[0].r.p, levels_[1].b.p, false);
+        RealArgs a;
+        a.val = levels_[0].R.view().val; a.x = levels_[0].r.p; a.y = levels_[1].b.p;
+        launch_real<kOpPlain, kTypesF>(levels_[0].R.view(), a);
         break;
-      case 8:
+      }
+      case 8: {
         if (!multi) throw std::invalid_argument("single-level hierarchy");
-        launch_plain(levels_[0].P.view(), levels_[1].y.p, levels_[0].x.p, true);
+        RealArgs a;
+        a.val = levels_[0].P.view().val; a.x = levels_[1].y.p; a.y = levels_[0].x.p;
+        launch_real<kOpPlainAdd, kTypesF>(levels_[0].P.view(), a);
         break;
+      }
       default: throw std::invalid_argument("unknown kernel id");
     }
   };

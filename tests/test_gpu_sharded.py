@@ -43,16 +43,16 @@ def _stepper(c):
     return dict(dt_init=o["dt_init"], dt_max=o["dt_max"], adaptive=o.get("adaptive", True))
 
 
-@pytest.mark.parametrize("world,use_graph,replicate_below,fuse",
-                         [(2, 1, 0, 0), (4, 1, 1, 0), (3, 2, 100, 0), (8, 1, 0, 0), (2, 1, 0, 1)])
-def test_sharded_smooth_trajectory_matches_reference(world, use_graph, replicate_below, fuse):
+@pytest.mark.parametrize("world,use_graph,replicate_below",
+                         [(2, 1, 0), (4, 1, 1), (3, 2, 100), (8, 1, 0), (2, 2, 0)])
+def test_sharded_smooth_trajectory_matches_reference(world, use_graph, replicate_below):
     """film20_fixed, 1000 fixed-dt steps on `world` shards: same 1e-8 gauge-fixed parity with
     the reference as the single-GPU engine.  replicate_below = 1 partitions every AMG level
     but the coarsest, 100 all but the last two, 0 (default) only the fine level here."""
     c = load_case("film20_fixed")
     g = c.g
     with _group(c, world, use_graph=use_graph, running_capacity=1000,
-                replicate_below=replicate_below, fuse_coarse=fuse) as grp:
+                replicate_below=replicate_below) as grp:
         grp.set_stepper(**_stepper(c))
         grp.set_state(np.ones(len(c.mesh.sites), complex), np.zeros(len(c.mesh.sites)))
         info = grp.advance(1000, 1e300, 0, 0.0)
