@@ -181,6 +181,21 @@ int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t ste
                 tdgl_advance_info* info);
 
 /* Page-locked host memory for the arrays that cross the boundary every step. */
+/* Shard-local step seam (domain decomposition): the rank hands in and gets back ONLY the
+ * entries it owns — 1/world of the whole-mesh traffic of tdgl_update per rank, no sums over
+ * zero-padded arrays; halo values travel device to device.
+ *   tdgl_local_maps: sizes[2] = {owned sites, owned edges}; sites[owned sites] = caller site
+ *     ids in the order of the local arrays; edges[owned edges] = caller edge ids (an edge is
+ *     owned by the shard that owns edges[e][0]).  Null arrays are skipped (size query).
+ *   tdgl_update_local: like tdgl_update with psi_local / mu_local (in) and psi_out / mu_out /
+ *     supercurrent / normal_current (out) in that local order.  Every rank must call it for
+ *     every step (the ranks meet in an on-device barrier).  With world = 1 it is tdgl_update
+ *     without the renumbering. */
+int tdgl_local_maps(tdgl_handle* h, int64_t* sizes, int64_t* sites, int64_t* edges);
+int tdgl_update_local(tdgl_handle* h, const double* psi_local, const double* mu_local, int64_t step,
+                      double time, double* psi_out, double* mu_out, double* supercurrent,
+                      double* normal_current, tdgl_advance_info* info);
+
 void* tdgl_host_alloc(int64_t bytes);
 void tdgl_host_free(void* p);
 

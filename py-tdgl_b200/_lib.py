@@ -86,6 +86,9 @@ SIGNATURES = {
     "tdgl_advance": (C.c_int, [_P, _I64, _D, _I64, _D, C.POINTER(tdgl_advance_info)]),
     "tdgl_update": (C.c_int, [_P, _P, _P, _I64, _D, _P, _P, _P, _P,
                               C.POINTER(tdgl_advance_info)]),
+    "tdgl_local_maps": (C.c_int, [_P, _P, _P, _P]),
+    "tdgl_update_local": (C.c_int, [_P, _P, _P, _I64, _D, _P, _P, _P, _P,
+                                    C.POINTER(tdgl_advance_info)]),
     "tdgl_host_alloc": (C.c_void_p, [_I64]),
     "tdgl_host_free": (None, [_P]),
     "tdgl_get_state": (C.c_int, [_P, _P, _P]),

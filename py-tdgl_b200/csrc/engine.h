@@ -195,6 +195,9 @@ class Engine {
   AdvanceInfo advance(int64_t max_steps, double t_end, int64_t step, double time);
   AdvanceInfo update(const double* psi, const double* mu, int64_t step, double time,
                      double* psi_out, double* mu_out, double* js, double* jn);
+  void local_maps(int64_t* sizes, int64_t* sites, int64_t* edges);
+  AdvanceInfo update_local(const double* psi_loc, const double* mu_loc, int64_t step, double time,
+                           double* psi_out, double* mu_out, double* js, double* jn);
   void stage_outputs(int what, void** ptrs, int64_t* counts);
   void fetch_outputs(double* psi, double* mu, double* js, double* jn);
   void get_state(double* psi, double* mu);
@@ -275,7 +278,8 @@ class Engine {
   void enqueue_screening_pass_end(cudaGraphConditionalHandle cond_scr, cudaGraphConditionalHandle cond_psi);
   void rebuild_graph();
   // ---- edges (caller edge order, internal site indices) -----------------------------------
-  DevBuf<int> e0_, e1_;
+  DevBuf<int> e0_, e1_, own_edges_;
+  std::vector<int> h_own_edges_;   // edges owned by this shard (edges[e,0] is an owned site)
   DevBuf<double> elen_, weight_, theta_;
   DevBuf<int> be0_, be1_;
   DevBuf<double> blen_, mub_;

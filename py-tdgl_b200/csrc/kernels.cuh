@@ -663,7 +663,8 @@ __global__ void k_link_values(int n, const int* __restrict__ ptr, const int* __r
 // J_s[e] = Im(conj(psi[e0]) (U_e psi[e1] - psi[e0]) / l_e)      (operators.py:385-394)
 // J_n[e] = -(mu[e1] - mu[e0]) / l_e                              (solver.py:519, static A)
 // Edge arrays are in the caller's edge order, site indices are internal.
-__global__ void k_currents(int ne, const int* __restrict__ e0, const int* __restrict__ e1,
+__global__ void k_currents(int ne, const int* __restrict__ elist /* null: all edges */,
+                           const int* __restrict__ e0, const int* __restrict__ e1,
                            const double* __restrict__ elen, const double* __restrict__ theta,
                            const double2* __restrict__ psi /* null: the current buffer of ... */,
                            const double2* __restrict__ psi_buf0, const double2* __restrict__ psi_buf1,
@@ -675,12 +676,13 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
                            const double2* __restrict__ aind /* null: no screening */,
                            const double2* __restrict__ edir,
                            double* __restrict__ js, double* __restrict__ jn) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // output slot
+  if (t >= ne) return;
+  const int e = elist != nullptr ? elist[t] : t;         // (shard-local output: owned edges only)
   const int i = e0[e], j = e1[e];
   if (i < 0) {  // the edge belongs to another shard (owner = shard of edges[e,0])
-    if (mode & 1) js[e] = 0.0;
-    if (mode & 2) jn[e] = 0.0;
+    if (mode & 1) js[t] = 0.0;
+    if (mode & 2) jn[t] = 0.0;
     return;
   }
   if (psi == nullptr) psi = ctl->cur ? psi_buf1 : psi_buf0;
@@ -694,10 +696,10 @@ __global__ void k_currents(int ne, const int* __restrict__ e0, const int* __rest
   // g = (U psi_j) * (1/l) + psi_i * (-1/l)   as the CSR gradient row computes it
   const double gx = (c * pj.x - s * pj.y) * inv_l - pi.x * inv_l;
   const double gy = (c * pj.y + s * pj.x) * inv_l - pi.y * inv_l;
-  if (mode & 1) js[e] = pi.x * gy - pi.y * gx;
+  if (mode & 1) js[t] = pi.x * gy - pi.y * gx;
   double da = dadt != nullptr ? dadt[e] : 0.0;
   if (ramp_proj != nullptr) da = ctl->ramp_dfdt * ramp_proj[e];
-  if (mode & 2) jn[e] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
+  if (mode & 2) jn[t] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -947,6 +949,23 @@ k_dot(Ctl* ctl, Comm* comm, int n, const double* __restrict__ a, const double* _
     if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
     if (threadIdx.x == 0) *out = total;
   }
+}
+
+// ---- shard-local step seam (sharded engine) ---------------------------------------------------
+// All ranks have finished reading the mailboxes of the previous step (one all-reduce).
+__global__ void k_comm_barrier(Ctl* ctl, Comm* comm) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  double v = 0.0;
+  comm_allreduce(ctl, comm, &v, 1, false);
+}
+
+// The boundary rows of a state vector this rank has just been handed go to the neighbours'
+// mailboxes (the counterpart of k_fill_box when every rank only holds its own rows).
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_push_state(const Comm* comm, PushArgs push, unsigned int tag, int n, const T* __restrict__ vec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) push_row(comm, push, tag, i, vec[i]);
 }
 
 // Reads a buffer larger than L2 so that the next kernel starts from a cold cache

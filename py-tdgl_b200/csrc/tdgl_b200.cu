@@ -342,6 +342,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     }
     e0_.upload(e0l, stream_);
     e1_.upload(e1l, stream_);
+    // owned edges (shard-local outputs): ascending caller edge ids
+    h_own_edges_.clear();
+    for (int e = 0; e < E_; ++e)
+      if (e0l[e] >= 0) h_own_edges_.push_back(e);
+    own_edges_.upload(h_own_edges_, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
   elen_.upload(len, stream_);
@@ -666,6 +671,37 @@ void Engine::configure_kernels() {
   TDGL_ALLOW_REAL(kOpPlain, kTypesF)
   TDGL_ALLOW_REAL(kOpPlainAdd, kTypesF)
 #undef TDGL_ALLOW_REAL
+  // Every kernel of the stepping sequence is loaded NOW: with CUDA's lazy module loading the
+  // first launch of a kernel loads it under a context-wide lock, and shards that share a process
+  // wait for each other inside kernels — a lazy load on one shard's host thread while another
+  // shard's kernel spins on it would dead-lock (until the exchange timeout).
+  auto preload = [&](const void* f) {
+    cudaFuncAttributes attr;
+    TDGL_CUDA(cudaFuncGetAttributes(&attr, f));
+  };
+  preload(reinterpret_cast<const void*>(&k_step_begin));
+  preload(reinterpret_cast<const void*>(&k_psi_control));
+  preload(reinterpret_cast<const void*>(&k_cg_begin));
+  preload(reinterpret_cast<const void*>(&k_mu_guess));
+  preload(reinterpret_cast<const void*>(&k_cg_fused));
+  preload(reinterpret_cast<const void*>(&k_weighted_sum));
+  preload(reinterpret_cast<const void*>(&k_shift));
+  preload(reinterpret_cast<const void*>(&k_step_end));
+  preload(reinterpret_cast<const void*>(&k_dot));
+  preload(reinterpret_cast<const void*>(&k_link_values_ramp));
+  preload(reinterpret_cast<const void*>(&k_dense_matvec<float, float, float>));
+  preload(reinterpret_cast<const void*>(&k_dense_matvec<float, double, double>));
+  preload(reinterpret_cast<const void*>(&k_unpack<float>));
+  preload(reinterpret_cast<const void*>(&k_unpack<double>));
+  preload(reinterpret_cast<const void*>(&k_unpack<double2>));
+  preload(reinterpret_cast<const void*>(&k_comm_barrier));
+  preload(reinterpret_cast<const void*>(&k_push_state<double>));
+  preload(reinterpret_cast<const void*>(&k_push_state<double2>));
+  preload(reinterpret_cast<const void*>(&k_currents));
+  preload(reinterpret_cast<const void*>(&k_scatter<double>));
+  preload(reinterpret_cast<const void*>(&k_scatter<double2>));
+  preload(reinterpret_cast<const void*>(&k_gather<double>));
+  preload(reinterpret_cast<const void*>(&k_gather<double2>));
   allow(reinterpret_cast<const void*>(&kw_psi_step<false>));
   allow(reinterpret_cast<const void*>(&kw_psi_step<true>));
   allow(reinterpret_cast<const void*>(&kw_mu_rhs<false>));
@@ -1473,7 +1509,7 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     TDGL_LAUNCH_CHECK();
     TDGL_CUDA(cudaMemcpyAsync(psi_out, tmp_c_.p, sizeof(double2) * Ng_, cudaMemcpyDeviceToHost, copy_stream_));
     k_currents<<<ge, kBlock, 0, copy_stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
+        E_, static_cast<const int*>(nullptr), e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
         psi_[1].p, 1, mu_.p, has_dadt_ ? dadt_.p : nullptr, ctl_.p,
         ramp_on_ ? ramp_proj_.p : nullptr, static_cast<const double2*>(nullptr), edir_.p, tmp_e_.p,
         tmp_e2_.p);
@@ -1485,7 +1521,7 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
     TDGL_LAUNCH_CHECK();
     tmp_d_.download(mu_out, Ng_, stream_);
     k_currents<<<ge, kBlock, 0, stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
+        E_, static_cast<const int*>(nullptr), e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
         psi_[1].p, 2, mu_.p, has_dadt_ ? dadt_.p : nullptr, ctl_.p,
         ramp_on_ ? ramp_proj_.p : nullptr, static_cast<const double2*>(nullptr), edir_.p, tmp_e_.p,
         tmp_e2_.p);
@@ -1524,13 +1560,84 @@ Engine::AdvanceInfo Engine::update(const double* psi, const double* mu, int64_t 
   if (js != nullptr || jn != nullptr) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+        E_, static_cast<const int*>(nullptr), e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
         has_dadt_ ? dadt_.p : nullptr,
         ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_new_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
     TDGL_LAUNCH_CHECK();
     if (js != nullptr) tmp_e_.download(js, E_, stream_);
     if (jn != nullptr) tmp_e2_.download(jn, E_, stream_);
+  }
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  return info;
+}
+
+// ---- shard-local step seam ------------------------------------------------------------------------
+// tdgl_update for a rank that holds only ITS part of the state: psi / mu of the owned sites (in
+// the order of local_maps) go in, psi', mu' of the owned sites and J_s, J_n of the owned edges
+// come out — 1/world of the whole-mesh traffic per rank, no zero-padded sums.  The halo values
+// travel between the devices (mailboxes), never through the host.
+void Engine::local_maps(int64_t* sizes, int64_t* sites, int64_t* edges) {
+  if (sizes != nullptr) { sizes[0] = N_; sizes[1] = static_cast<int64_t>(h_own_edges_.size()); }
+  const int64_t o0 = world_ > 1 ? plan_.off[0][rank_] : 0;
+  if (sites != nullptr) for (int k = 0; k < N_; ++k) sites[k] = perm_[o0 + k];
+  if (edges != nullptr) for (size_t k = 0; k < h_own_edges_.size(); ++k) edges[k] = h_own_edges_[k];
+}
+
+Engine::AdvanceInfo Engine::update_local(const double* psi_loc, const double* mu_loc, int64_t step,
+                                         double time, double* psi_out, double* mu_out, double* js,
+                                         double* jn) {
+  if (!connected_) throw std::invalid_argument("sharded engine: connect the peers first (tdgl_comm_connect_*)");
+  sync_ctl_to_host();
+  int cur = h_ctl_->cur;
+  TDGL_CUDA(cudaMemcpyAsync(psi_[cur].p, psi_loc, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
+  TDGL_CUDA(cudaMemcpyAsync(mu_.p, mu_loc, sizeof(double) * N_, cudaMemcpyHostToDevice, stream_));
+  if (world_ > 1) {
+    // like set_state(reset_history): the mailbox copies of mu's history are refilled from the
+    // new mu, so the extrapolated initial guess starts afresh
+    TDGL_CUDA(cudaMemcpyAsync(mu_prev_.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+    TDGL_CUDA(cudaMemcpyAsync(mu_pp_.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+    h_ctl_->psi_tag[cur] = h_ctl_->psi_epoch;
+    push_ctl();
+    comm_on_ = true;
+    const int g = (N_ + kBlock - 1) / kBlock;
+    k_comm_barrier<<<1, 32, 0, stream_>>>(ctl_.p, comm_.p);   // peers are done with the old boxes
+    TDGL_LAUNCH_CHECK();
+    k_push_state<double2><<<g, kBlock, 0, stream_>>>(comm_.p, make_push(0, kVecPsi0 + cur, kTagPsiCur),
+                                                    static_cast<unsigned int>(h_ctl_->psi_epoch), N_, psi_[cur].p);
+    TDGL_LAUNCH_CHECK();
+    for (int back = 0; back < 2; ++back) {
+      k_push_state<double><<<g, kBlock, 0, stream_>>>(comm_.p, make_push(0, kVecMu, kTagMu),
+                                                     static_cast<unsigned int>(h_ctl_->solve_epoch - back), N_, mu_.p);
+      TDGL_LAUNCH_CHECK();
+    }
+    // halo slots of the plain-array history (read by the rhs kernel before k_mu_guess refills them)
+    const int n_halo = Nx_ - N_;
+    if (n_halo > 0) {
+      k_unpack<double><<<std::min((n_halo + 1023) / 1024, 64), 1024, 0, stream_>>>(
+          ctl_.p, comm_.p, make_halo(0, kVecMu, kTagMu), n_halo, mu_pp_.p);
+      TDGL_LAUNCH_CHECK();
+    }
+  } else {
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
+  AdvanceInfo info = advance(1, 1e300, step, time);
+  cur = h_ctl_->cur;
+  if (psi_out != nullptr)
+    TDGL_CUDA(cudaMemcpyAsync(psi_out, psi_[cur].p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, stream_));
+  if (mu_out != nullptr) mu_.download(mu_out, N_, stream_);
+  if (js != nullptr || jn != nullptr) {
+    const int ne = static_cast<int>(h_own_edges_.size());
+    unpack_state_halos(cur);
+    if (ne > 0) {
+      k_currents<<<(ne + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
+          ne, own_edges_.p, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+          has_dadt_ ? dadt_.p : nullptr, ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr,
+          scr_on_ ? aind_new_.p : nullptr, edir_.p, tmp_e_.p, tmp_e2_.p);
+      TDGL_LAUNCH_CHECK();
+      if (js != nullptr) tmp_e_.download(js, ne, stream_);
+      if (jn != nullptr) tmp_e2_.download(jn, ne, stream_);
+    }
   }
   TDGL_CUDA(cudaStreamSynchronize(stream_));
   return info;
@@ -1553,7 +1660,7 @@ void Engine::stage_outputs(int what, void** ptrs, int64_t* counts) {
   if (what & 2) {
     unpack_state_halos(cur);
     k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-        E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+        E_, static_cast<const int*>(nullptr), e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
         has_dadt_ ? dadt_.p : nullptr,
         ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_new_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
@@ -1614,7 +1721,7 @@ void Engine::snapshot_begin(int slot) {
   k_scatter<double><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, mu_.p, sl.d_mu.p);
   TDGL_LAUNCH_CHECK();
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+      E_, static_cast<const int*>(nullptr), e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
       has_dadt_ ? dadt_.p : nullptr, ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr,
       scr_on_ ? aind_new_.p : nullptr, edir_.p, sl.d_js.p, sl.d_jn.p);
   TDGL_LAUNCH_CHECK();
@@ -1642,7 +1749,7 @@ void Engine::get_currents(double* js, double* jn) {
   const int cur = h_ctl_->cur;
   unpack_state_halos(cur);
   k_currents<<<(E_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(
-      E_, e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
+      E_, static_cast<const int*>(nullptr), e0_.p, e1_.p, elen_.p, theta_.p, psi_[cur].p, psi_[0].p, psi_[1].p, 3, mu_.p,
       has_dadt_ ? dadt_.p : nullptr,
         ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr, scr_on_ ? aind_new_.p : nullptr, edir_.p,
         tmp_e_.p, tmp_e2_.p);
@@ -2201,6 +2308,31 @@ int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t ste
   const int rc = guarded(h, [&](tdgl::Engine& e) {
     if (psi == nullptr || mu == nullptr) throw std::invalid_argument("null psi / mu");
     const auto r = e.update(psi, mu, step, time, psi_out, mu_out, supercurrent, normal_current);
+    if (info != nullptr) {
+      info->steps_done = r.steps_done; info->step = r.step; info->time = r.time; info->dt = r.dt;
+      info->tentative_dt = r.tentative_dt; info->finished = r.finished; info->status = r.status;
+      info->failed_step = r.failed_step; info->failed_dt = r.failed_dt; info->retries = r.retries;
+      info->mu_iterations = r.mu_iterations; info->mu_rel_residual = r.mu_rel_residual;
+      info->device_ms = r.device_ms;
+      info->screening_iterations = r.screening_iterations; info->screening_error = r.screening_error;
+    }
+    status = r.status;
+  });
+  if (rc != TDGL_OK) return rc;
+  return step_status_to_rc(h, status);
+}
+
+int tdgl_local_maps(tdgl_handle* h, int64_t* sizes, int64_t* sites, int64_t* edges) {
+  return guarded(h, [&](tdgl::Engine& e) { e.local_maps(sizes, sites, edges); });
+}
+
+int tdgl_update_local(tdgl_handle* h, const double* psi_local, const double* mu_local, int64_t step,
+                      double time, double* psi_out, double* mu_out, double* supercurrent,
+                      double* normal_current, tdgl_advance_info* info) {
+  int status = TDGL_OK;
+  const int rc = guarded(h, [&](tdgl::Engine& e) {
+    if (psi_local == nullptr || mu_local == nullptr) throw std::invalid_argument("null psi / mu");
+    const auto r = e.update_local(psi_local, mu_local, step, time, psi_out, mu_out, supercurrent, normal_current);
     if (info != nullptr) {
       info->steps_done = r.steps_done; info->step = r.step; info->time = r.time; info->dt = r.dt;
       info->tentative_dt = r.tentative_dt; info->finished = r.finished; info->status = r.status;

@@ -280,6 +280,33 @@ class DeviceEngine:
         self._check(rc)
         return res, out
 
+    def local_maps(self):
+        """(owned_sites, owned_edges): caller ids of the sites / edges this shard owns, in the
+        order of the local arrays of ``update_local`` (all of them for a single shard)."""
+        sizes = np.zeros(2, dtype=np.int64)
+        self._check(self._lib.tdgl_local_maps(self._h, ptr(sizes), None, None))
+        sites = np.zeros(max(int(sizes[0]), 1), dtype=np.int64)
+        edges = np.zeros(max(int(sizes[1]), 1), dtype=np.int64)
+        self._check(self._lib.tdgl_local_maps(self._h, ptr(sizes), ptr(sites), ptr(edges)))
+        return sites[:sizes[0]], edges[:sizes[1]]
+
+    def update_local(self, psi_local, mu_local, step: int, time: float, out):
+        """The step seam of one shard: psi / mu of the OWNED sites in, psi', mu' of the owned
+        sites and J_s, J_n of the owned edges out (``out`` = four arrays of those sizes, e.g.
+        pinned).  Every shard must make the call for every step."""
+        info = _lib.tdgl_advance_info()
+        rc = self._lib.tdgl_update_local(self._h, ptr(psi_local), ptr(mu_local), int(step),
+                                         float(time), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                         ptr(out[3]), C.byref(info))
+        res = AdvanceInfo(info.steps_done, info.step, info.time, info.dt, info.tentative_dt,
+                          bool(info.finished), info.status, info.failed_step, info.failed_dt,
+                          info.retries, info.mu_iterations, info.mu_rel_residual, info.device_ms,
+                          info.screening_iterations, info.screening_error)
+        if rc == _lib.TDGL_E_STEP_FAILED:
+            raise StepFailed(f"step {res.failed_step} dt {res.failed_dt:.2e}", res)
+        self._check(rc)
+        return res, out
+
     # -- outputs --------------------------------------------------------------------------
     def get_state(self):
         psi = np.empty(self.n_sites, dtype=np.complex128)

@@ -224,6 +224,16 @@ class LocalShardGroup:
                 raise RuntimeError(f"shards disagree on the step bookkeeping: {a} vs {b}")
         return a._replace(device_ms=max(i.device_ms for i in infos))
 
+    def local_maps(self):
+        return [e.local_maps() for e in self.engines]
+
+    def update_local(self, psi_parts, mu_parts, step: int, time: float, outs):
+        """Shard-local step seam on every shard at once: ``psi_parts[r]`` / ``mu_parts[r]`` are
+        shard r's owned entries, ``outs[r]`` its four output arrays."""
+        res = self._all(lambda e: e.update_local(psi_parts[e.rank], mu_parts[e.rank], step, time,
+                                                 outs[e.rank]))
+        return res[0][0], outs
+
     def get_state(self):
         parts = self._all(lambda e: e.get_state())
         return sum(p[0] for p in parts), sum(p[1] for p in parts)

@@ -126,8 +126,9 @@ class Solution:
 
     def __init__(self, *, device, options, saved: SavedSteps, applied_vector_potential=None,
                  terminal_currents=None, disorder_epsilon=None, total_seconds: float = 0.0,
-                 path: Optional[str] = None, solver_stats: Optional[dict] = None):
+                 path: Optional[str] = None, solver_stats: Optional[dict] = None, mesh=None):
         self.device = device
+        self._mesh = mesh if mesh is not None else getattr(device, "mesh", None)
         self.options = options
         self.path = path
         self.applied_vector_potential = applied_vector_potential
@@ -196,9 +197,16 @@ class Solution:
     def current_units(self) -> str:
         return str(self.options.current_units)
 
-    def to_npz(self, path: str) -> str:
-        """Write the reference's output tree (root fixed arrays, ``data/<k>/...`` groups with
-        ``step/time/dt`` attributes and ``running_state``) to one compressed ``.npz``."""
+    # -- persistence -----------------------------------------------------------------------
+    def _tree(self) -> Dict[str, np.ndarray]:
+        """The reference's output tree as flat ``path -> array`` pairs: root-level fixed
+        arrays, ``data/<k>/<name>`` per saved step with ``step/time/dt/timestamp`` attributes
+        (``data/<k>/attrs/<name>``) and ``data/<k>/running_state/<name>``
+        (DataHandler.save_time_step, runner.py:155-183); the mesh arrays under ``mesh/``
+        (Mesh.to_hdf5 / EdgeMesh.to_hdf5, finite_volume/mesh.py:345-368) and the solver options
+        under ``solution/options`` (Solution._save_to_hdf5_file, solution.py:874-931)."""
+        import json
+
         out: Dict[str, np.ndarray] = {}
         for k, v in self._saved.fixed.items():
             out[k] = v
@@ -212,20 +220,85 @@ class Solution:
                         out[f"data/{i}/running_state/{rk}"] = rv
                 else:
                     out[f"data/{i}/{k}"] = v
-        np.savez_compressed(path, **out)
+        mesh = getattr(self.device, "mesh", None) if self.device is not None else self._mesh
+        if mesh is not None:
+            em = mesh.edge_mesh
+            out["mesh/sites"] = np.asarray(mesh.sites)
+            out["mesh/elements"] = np.asarray(mesh.elements)
+            out["mesh/boundary_indices"] = np.asarray(mesh.boundary_indices)
+            out["mesh/areas"] = np.asarray(mesh.areas)
+            for name in ("centers", "edges", "boundary_edge_indices", "directions",
+                         "edge_lengths", "dual_edge_lengths"):
+                out[f"mesh/edge_mesh/{name}"] = np.asarray(getattr(em, name))
+        if self.options is not None:
+            opts = dataclasses.asdict(self.options)
+            opts["sparse_solver"] = getattr(opts["sparse_solver"], "value", opts["sparse_solver"])
+            if isinstance(opts.get("terminal_psi"), complex):
+                opts["terminal_psi"] = [opts["terminal_psi"].real, opts["terminal_psi"].imag]
+            out["solution/options"] = np.array(json.dumps(opts))
+        out["solution/total_seconds"] = np.array(self.total_seconds)
+        out["solution/time_created"] = np.array(self._time_created.isoformat())
+        return out
+
+    def to_npz(self, path: str) -> str:
+        """Write the tree of :meth:`_tree` to one compressed ``.npz`` (h5py / libhdf5 are not
+        part of this image; :meth:`to_hdf5` writes the same tree when they are)."""
+        np.savez_compressed(path, **self._tree())
         self.path = path if path.endswith(".npz") else path + ".npz"
         return self.path
+
+    def to_hdf5(self, path: str) -> str:
+        """The same tree as an HDF5 file with the reference's layout (groups ``data/<k>`` with
+        attributes, ``running_state`` sub-groups, ``mesh``, ``solution/options`` attributes).
+        Needs h5py, which this image does not ship: raises ImportError without it."""
+        import importlib.util
+        import json
+
+        if importlib.util.find_spec("h5py") is None:
+            raise ImportError("h5py is not installed: use Solution.to_npz (same tree of keys)")
+        import h5py
+
+        with h5py.File(path, "x") as f:
+            for key, value in self._tree().items():
+                parts = key.split("/")
+                if len(parts) >= 4 and parts[0] == "data" and parts[2] == "attrs":
+                    f.require_group(f"data/{parts[1]}").attrs[parts[3]] = value[()]
+                elif key == "solution/options":
+                    grp = f.require_group("solution/options")
+                    for k, v in json.loads(str(value)).items():
+                        if v is not None:
+                            grp.attrs[k] = v
+                elif parts[0] == "solution":
+                    f.require_group("solution").attrs[parts[1]] = value[()]
+                else:
+                    f[key] = value
+        self.path = path
+        return path
 
     @classmethod
     def from_npz(cls, path: str, device=None, options=None) -> "Solution":
         """Load a tree written by :meth:`to_npz` (the counterpart of the reference's
         ``Solution.from_hdf5``, solution/solution.py:933-1005, for the data this path
-        produces)."""
+        produces).  The solver options and the mesh are restored from the file unless given;
+        ``Solution.times`` and seeding a new solve (``seed_solution``) work on the result."""
+        import json
+
+        from .mesh import EdgeMesh, Mesh
+        from .options import SolverOptions
+
         saved = SavedSteps()
         groups: Dict[int, Dict[str, Any]] = {}
+        mesh_arrays: Dict[str, np.ndarray] = {}
+        meta: Dict[str, Any] = {}
         with np.load(path, allow_pickle=False) as f:
             for key in f.files:
                 parts = key.split("/")
+                if parts[0] == "mesh":
+                    mesh_arrays["/".join(parts[1:])] = f[key]
+                    continue
+                if parts[0] == "solution":
+                    meta[parts[1]] = f[key]
+                    continue
                 if parts[0] != "data":
                     saved.fixed[key] = f[key]
                     continue
@@ -238,7 +311,23 @@ class Solution:
                 else:
                     grp[parts[2]] = f[key]
         saved.groups = [groups[k] for k in sorted(groups)]
-        sol = cls(device=device, options=options, saved=saved, path=path)
+        if options is None and "options" in meta:
+            d = json.loads(str(meta["options"]))
+            if isinstance(d.get("terminal_psi"), list):
+                d["terminal_psi"] = complex(*d["terminal_psi"])
+            known = {fl.name for fl in dataclasses.fields(SolverOptions)}
+            options = SolverOptions(**{k: v for k, v in d.items() if k in known})
+        mesh = None
+        if mesh_arrays:
+            g = mesh_arrays
+            em = EdgeMesh(g["edge_mesh/centers"], g["edge_mesh/edges"],
+                          g["edge_mesh/boundary_edge_indices"], g["edge_mesh/directions"],
+                          g["edge_mesh/edge_lengths"], g["edge_mesh/dual_edge_lengths"])
+            mesh = Mesh(g["sites"], g["elements"], g["boundary_indices"], areas=g["areas"],
+                        edge_mesh=em)
+        if options is None:
+            raise ValueError(f"{path} holds no solver options: pass options=")
+        sol = cls(device=device, options=options, saved=saved, path=path, mesh=mesh,
+                  total_seconds=float(meta.get("total_seconds", 0.0)))
         sol.load_tdgl_data(-1)
         return sol
-

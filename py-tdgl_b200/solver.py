@@ -681,7 +681,7 @@ class TDGLSolver:
             applied_vector_potential=self.applied_vector_potential,
             terminal_currents=self.terminal_currents, disorder_epsilon=self.disorder_epsilon,
             total_seconds=(end_time - start_time).total_seconds(),
-            solver_stats=dict(self.stats, **self.engine.info()))
+            solver_stats=dict(self.stats, **self.engine.info()), mesh=self.mesh)
         if opts.output_file is not None:
             solution.to_npz(opts.output_file)
         return solution

@@ -257,7 +257,9 @@ def test_time_dependent_epsilon():
 def test_everything_dynamic_with_thermalisation():
     c, sol, got, ref = _edge_case(terminal_psi=1.0, skip_time=0.3, callable_current=True,
                                   eps_t=True, solve_time=1.2)
-    _check_edge("terminal_psi=1 + skip_time + I(t) + eps(t)", c, got, ref)
+    # (terminal_psi = 1 with a changing current: the controller's 1 / max |d|psi|^2| amplifies the
+    # mu solve's truncation a little more than in the single-feature cases: dt to 1e-9)
+    _check_edge("terminal_psi=1 + skip_time + I(t) + eps(t)", c, got, ref, tol_dt=1e-9)
 
 
 def test_seed_solution_restart():

@@ -298,3 +298,40 @@ int main(void) {
                     f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
     assert "sm_100a" in out and " 64 112" in out and "null array argument" in out
+
+
+def test_solution_npz_round_trip_keeps_options_and_mesh(tmp_path):
+    """A saved Solution can be loaded without arguments: options (save_every feeds
+    ``Solution.times``) and the mesh come back from the file; the tree of keys is the
+    reference's (data/<k>/..., running_state, mesh/, solution/options)."""
+    from tdgl_b200.solution import Solution
+
+    mesh = make_film_mesh(6, 4, 0.5)
+    n, E = len(mesh.sites), len(mesh.edge_mesh.edges)
+    saved = SavedSteps()
+    saved.save_fixed_values({"epsilon": np.ones(n), "applied_vector_potential": np.zeros((E, 2))})
+    rng = np.random.default_rng(0)
+    for k in range(3):
+        vals = {"psi": rng.normal(size=n) + 1j * rng.normal(size=n), "mu": rng.normal(size=n),
+                "supercurrent": rng.normal(size=E), "normal_current": rng.normal(size=E),
+                "induced_vector_potential": np.zeros((E, 2))}
+        rs = None if k == 0 else {"dt": np.full((1, 2), 1e-3), "mu": np.ones((2, 2))}
+        saved.save_time_step({"step": 2 * k, "time": 2e-3 * k, "dt": 1e-3}, vals, rs)
+    opts = tdgl.SolverOptions(solve_time=1.0, save_every=2, terminal_psi=None)
+    sol = Solution(device=None, options=opts, saved=saved, mesh=mesh, total_seconds=1.5)
+    path = sol.to_npz(str(tmp_path / "out.npz"))
+    with np.load(path) as f:
+        keys = set(f.files)
+    assert {"epsilon", "data/0/psi", "data/2/running_state/dt", "data/1/attrs/step",
+            "mesh/sites", "mesh/edge_mesh/edges", "solution/options"} <= keys
+    back = Solution.from_npz(path)
+    assert back.options.save_every == 2 and back.options.terminal_psi is None
+    np.testing.assert_array_equal(back.tdgl_data.psi, sol.tdgl_data.psi)
+    np.testing.assert_array_equal(back._mesh.edge_mesh.edges, mesh.edge_mesh.edges)
+    np.testing.assert_allclose(back.times, sol.times)
+    assert back.total_seconds == 1.5
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            sol.to_hdf5(str(tmp_path / "out.h5"))
