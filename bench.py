@@ -465,25 +465,49 @@ def run_b200(args, rank, world, local_rank):
     sh = eng.shard_info() if shard else None
 
     # ---- end to end through the reference's step seam --------------------------------------
-    psi_h = pinned_empty(n, np.complex128)
-    mu_h = pinned_empty(n, np.float64)
-    out = (pinned_empty(n, np.complex128), pinned_empty(n, np.float64),
-           pinned_empty(n_edges, np.float64), pinned_empty(n_edges, np.float64))
-    p0, m0 = eng.get_state()
-    psi_h[:] = p0
-    mu_h[:] = m0
+    # one GPU: TDGLSolver.update with whole-mesh host arrays (the reference's seam, literally);
+    # sharded: every rank moves only the entries it owns through tdgl_update_local (the seam of a
+    # job whose state is distributed over the ranks' hosts) — no whole-mesh copies or sums
     state = {"step": b.step, "time": b.time, "dt": b.dt}
-    Ke = K if n <= 2_500_000 else min(K, 40)   # (whole-mesh host copies every step)
+    if shard:
+        own_s, own_e = eng.local_maps()
+        n_loc, e_loc = len(own_s), len(own_e)
+        p0, m0 = eng.get_state()
+        psi_h = pinned_empty(n_loc, np.complex128)
+        mu_h = pinned_empty(n_loc, np.float64)
+        psi_h[:] = p0[own_s]
+        mu_h[:] = m0[own_s]
+        del p0, m0
+        out = (pinned_empty(n_loc, np.complex128), pinned_empty(n_loc, np.float64),
+               pinned_empty(max(e_loc, 1), np.float64), pinned_empty(max(e_loc, 1), np.float64))
+        Ke = K
+        api = "tdgl_update_local (owned entries per rank, pinned host arrays)"
+    else:
+        n_loc, e_loc = n, n_edges
+        psi_h = pinned_empty(n, np.complex128)
+        mu_h = pinned_empty(n, np.float64)
+        out = (pinned_empty(n, np.complex128), pinned_empty(n, np.float64),
+               pinned_empty(n_edges, np.float64), pinned_empty(n_edges, np.float64))
+        p0, m0 = eng.get_state()
+        psi_h[:] = p0
+        mu_h[:] = m0
+        Ke = K if n <= 2_500_000 else min(K, 40)   # (whole-mesh host copies every step)
+        api = "TDGLSolver.update (pinned host arrays)"
     for phase in ("warm", "timed"):
         nsteps = 2 if phase == "warm" else Ke
         barrier()
         t0 = time.perf_counter()
         for _ in range(nsteps):
-            res = solver.update(state, None, state["dt"], psi=psi_h, mu=mu_h, out=out)
+            if shard:
+                solver.update_mu_boundary(state["time"])
+                info, _ = eng.update_local(psi_h, mu_h, state["step"], state["time"], out)
+                dt_new = info.dt
+            else:
+                dt_new = solver.update(state, None, state["dt"], psi=psi_h, mu=mu_h, out=out).dt
             # the step's outputs are the next step's host inputs, as in Runner._run_stage
             # (swap the pinned buffers instead of copying host -> host)
             psi_h, mu_h, out = out[0], out[1], (psi_h, mu_h, out[2], out[3])
-            state = {"step": state["step"] + 1, "time": state["time"] + res.dt, "dt": res.dt}
+            state = {"step": state["step"] + 1, "time": state["time"] + dt_new, "dt": dt_new}
         barrier()
         e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -508,8 +532,10 @@ def run_b200(args, rank, world, local_rank):
         del hb, db
     except Exception as exc:
         pcie = {"unavailable": str(exc)}
-    h2d = 24 * n                     # psi (16 B) + mu (8 B) per site (per rank)
-    d2h = 24 * n + 16 * n_edges      # psi', mu' + J_s, J_n per edge (per rank)
+    # psi (16 B) + mu (8 B) per site in; psi', mu' + J_s, J_n (8 B per edge each) out: whole job
+    # (sharded: every site / edge is moved by exactly one rank)
+    h2d = 24 * n
+    d2h = 24 * n + 16 * n_edges
 
     # ---- the same measurement deep in the run (vortices nucleating and moving) ---------------
     # the headline numbers start from a state both arms can construct; this record shows that
@@ -616,7 +642,8 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_steps_per_s * n, "unit": "site-steps/s",
                 "steps_per_sec": e2e_steps_per_s, "steps": Ke, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "TDGLSolver.update (pinned host arrays)",
+                "d2h_bytes_per_step": d2h, "api": api,
+                "per_rank": {"sites": n_loc, "edges": e_loc} if shard else None,
                 "link": pcie,
                 "link_floor_ms": ((h2d / pcie["h2d_GBps"] + d2h / pcie["d2h_GBps"]) / 1e6
                                   if "h2d_GBps" in pcie else None)},
