@@ -118,6 +118,21 @@ int tdgl_set_vector_potential_ramp(tdgl_handle* h, const double* A0, int32_t n_k
 /* psi[N] (complex128) and mu[N]: the `psi`, `mu` values Runner threads through update(). */
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu);
 
+/* Time-dependent terminal currents without the per-step host callback (the reference calls
+ * current_func(t) from Python every step, solver.py:325-345): I_k(t) piecewise linear through
+ * (t_knots[j], currents[k][j]) (constant outside), already J_scale-d, terminals in the caller's
+ * order; terminal_of_boundary_edge[Eb] = terminal index of every boundary edge or -1;
+ * terminal_lengths[n_terminals].  The device evaluates J_ext,k = -(1 / L_k) sum_{j != k} I_j(t)
+ * at the start of every step and rewrites the boundary term of the sites at the terminals when
+ * a density changed.  n_knots = 0 turns the table off (tdgl_set_mu_boundary applies again). */
+int tdgl_set_terminal_current_table(tdgl_handle* h, int32_t n_terminals, const int32_t* terminal_of_boundary_edge,
+                                    const double* terminal_lengths, int32_t n_knots,
+                                    const double* t_knots, const double* currents);
+/* epsilon(r, t) = epsilon0(r) + g(t) * epsilon1(r), g piecewise linear through the knots
+ * (update_epsilon, solver.py:364-381, 644-646, evaluated inside the psi step).  n_knots = 0: off. */
+int tdgl_set_epsilon_table(tdgl_handle* h, const double* epsilon0, const double* epsilon1,
+                           int32_t n_knots, const double* t_knots, const double* g_knots);
+
 /* Screening (SolverOptions.include_screening; reference solver/solver.py:304-314, 522-578,
  * 650-688, solver/screening.py:12-42, finite_volume/mesh.py:203-243): every time step iterates
  * Polyak's method on the induced vector potential

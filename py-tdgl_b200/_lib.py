@@ -78,6 +78,8 @@ SIGNATURES = {
     "tdgl_set_dA_dt": (C.c_int, [_P, _P]),
     "tdgl_set_vector_potential_ramp": (C.c_int, [_P, _P, _I32, _P, _P]),
     "tdgl_set_state": (C.c_int, [_P, _P, _P]),
+    "tdgl_set_terminal_current_table": (C.c_int, [_P, _I32, _P, _P, _I32, _P, _P]),
+    "tdgl_set_epsilon_table": (C.c_int, [_P, _P, _P, _I32, _P, _P]),
     "tdgl_set_screening": (C.c_int, [_P, _I32, _D, _P, _P, _D, _I32, _D, _D]),
     "tdgl_set_induced_vector_potential": (C.c_int, [_P, _P]),
     "tdgl_get_induced_vector_potential": (C.c_int, [_P, _P]),

@@ -403,7 +403,8 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
             const double2* psi_buf1, double2* out_buf0, double2* out_buf1,
             const double* __restrict__ mu, const double* __restrict__ eps,
             double* __restrict__ sq_out /* may be null */, double dt_override /* < 0: ctl->dt */,
-            const double* __restrict__ old_sq /* screening: |psi|^2 of the step's input; else null */) {
+            const double* __restrict__ old_sq /* screening: |psi|^2 of the step's input; else null */,
+            const double* __restrict__ eps1 /* epsilon = eps + eps_g(t) * eps1; null: static */) {
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double s_max[8];
@@ -435,6 +436,8 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
     p = psi[w.row];
     mui = mu[w.row];
     epsi = eps[w.row];
+    // (no FMA contraction: the host evaluates e0 + g * e1 with a rounded product)
+    if (eps1 != nullptr) epsi = __dadd_rn(epsi, __dmul_rn(ctl->eps_g, eps1[w.row]));
     fx = fixed[w.row] != 0;
   }
   double abs2 = p.x * p.x + p.y * p.y;

@@ -174,6 +174,10 @@ class Engine {
   void set_dA_dt(const double* dadt);
   void set_ramp(const double* A0, int n_knots, const double* t_knots, const double* f_knots);
   void set_state(const double* psi, const double* mu, bool reset_history = true);
+  void set_terminal_currents(int n_term, const int32_t* term_of_bedge, const double* lengths,
+                             int n_knots, const double* t_knots, const double* values);
+  void set_epsilon_table(const double* eps0, const double* eps1, int n_knots, const double* t_knots,
+                         const double* g_knots);
   void set_screening(int enable, double scale, const double* sites_xy, const double* edge_centers,
                      double tolerance, int max_iterations, double step_size, double drag);
   void set_induced(const double* A);
@@ -268,6 +272,13 @@ class Engine {
   DevBuf<double> ramp_proj_, ramp_div_, ramp_zero_;
   void enqueue_ramp_links();
   int win0_ = kWinRows, cap0_ = 0;  // window geometry of the site operators
+  // ---- device-side tables: terminal currents I_k(t), epsilon(r, t) = e0(r) + g(t) e1(r) ----------
+  bool cur_on_ = false, eps_dyn_ = false;
+  DevBuf<int> ts_site_, ts_ptr_, ts_bedge_, bedge_term_;
+  DevBuf<double> eps1_;
+  int n_ts_ = 0;
+  std::vector<int> h_b0_, h_b1_;   // local site indices of the boundary edges' ends (-1: not owned)
+  void enqueue_step_inputs();      // what follows k_step_begin: ramp links, terminal sites
   // ---- screening (row S): induced vector potential, Polyak iteration inside the step ---------
   bool scr_on_ = false;
   DevBuf<double2> aind_, aind_new_, vel_, edir_, ecent_, sxy_, wsite_;

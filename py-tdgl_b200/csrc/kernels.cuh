@@ -19,7 +19,8 @@ constexpr int kMaxWindow = 1024;   // adaptive_window cap
 constexpr int kMaxProbes = 64;
 constexpr int kBlock = 256;
 constexpr int kMaxPartials = 8192;  // grid-size cap of reducing kernels
-constexpr int kMaxKnots = 32;       // knots of a device-side vector-potential ramp
+constexpr int kMaxKnots = 32;       // knots of a device-side piecewise-linear table
+constexpr int kMaxTerminals = 8;    // terminals with device-side current tables
 
 struct Ctl {
   // --- configuration (host writes) -----------------------------------------------------
@@ -59,6 +60,16 @@ struct Ctl {
   int solve_epoch;    // mu solves started so far (+1): bumped at the start of every step
   int psi_epoch;      // attempts of the psi step so far (+1)
   int psi_tag[2];     // psi_epoch of the attempt that produced each psi buffer
+  // --- time-dependent terminal currents I_k(t) and epsilon(r, t) = e0(r) + g(t) e1(r), both as
+  //     piecewise-linear tables evaluated by k_step_begin (solver.py:325-345, 364-381, 644-646) --
+  int cur_on, cur_nterm, cur_knots, cur_changed;
+  double cur_t[kMaxKnots];
+  double cur_v[kMaxTerminals][kMaxKnots];   // J_scale-d currents, terminal order of the caller
+  double cur_len[kMaxTerminals];            // terminal lengths
+  double cur_dens[kMaxTerminals];           // current densities in use (mu_boundary values)
+  int eps_on, eps_knots;
+  double eps_g;                             // g at the current step
+  double eps_t[kMaxKnots], eps_v[kMaxKnots];
   // --- diagnostics of a shard-exchange timeout (status 3): what was waited for ----------------
   unsigned int fail_tag;
   unsigned long long fail_addr;
@@ -393,6 +404,18 @@ __device__ __forceinline__ PsiOut psi_update(double2 psi, double2 lap, double mu
   return o;
 }
 
+// Piecewise-linear table lookup, constant outside the knots (the same arithmetic as the host
+// classes in tdgl_b200/sources.py, which the parity tests feed to the oracle).
+__device__ __forceinline__ double table_lookup(const double* __restrict__ t, const double* __restrict__ v,
+                                               int n, double x) {
+  if (x >= t[n - 1]) return v[n - 1];
+  if (x <= t[0]) return v[0];
+  int k = 0;
+  while (k + 2 < n && x >= t[k + 1]) ++k;
+  const double w = __ddiv_rn(__dsub_rn(x, t[k]), __dsub_rn(t[k + 1], t[k]));
+  return __dadd_rn(v[k], __dmul_rn(w, __dsub_rn(v[k + 1], v[k])));
+}
+
 // Start of TDGLSolver.update (solver.py:649-668): dt <- tentative_dt, retries <- 0.
 __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi,
                              cudaGraphConditionalHandle cond_scr) {
@@ -417,6 +440,19 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi,
     ctl->ramp_changed = (f != ctl->ramp_f) || ctl->ramp_changed == 2;  // 2: forced (set-up)
     ctl->ramp_f = f;
   }
+  if (ctl->cur_on) {
+    // update_mu_boundary (solver.py:325-345): J_ext,k = -(1 / L_k) sum_{j != k} I_j(t)
+    int changed = ctl->cur_changed == 2;   // 2: forced (set-up)
+    for (int k = 0; k < ctl->cur_nterm; ++k) {
+      double sum = 0.0;
+      for (int j = 0; j < ctl->cur_nterm; ++j)
+        if (j != k) sum = __dadd_rn(sum, table_lookup(ctl->cur_t, ctl->cur_v[j], ctl->cur_knots, ctl->time));
+      const double dens = __dmul_rn(__ddiv_rn(-1.0, ctl->cur_len[k]), sum);
+      if (dens != ctl->cur_dens[k]) { ctl->cur_dens[k] = dens; changed = 1; }
+    }
+    ctl->cur_changed = changed;
+  }
+  if (ctl->eps_on) ctl->eps_g = table_lookup(ctl->eps_t, ctl->eps_v, ctl->eps_knots, ctl->time);
   ctl->dt = ctl->tentative_dt;
   ctl->scr_it = 0;
   ctl->scr_err_bits = 0ull;
@@ -700,6 +736,45 @@ __global__ void k_currents(int ne, const int* __restrict__ elist /* null: all ed
   double da = dadt != nullptr ? dadt[e] : 0.0;
   if (ramp_proj != nullptr) da = ctl->ramp_dfdt * ramp_proj[e];
   if (mode & 2) jn[t] = -(mu[j] * inv_l - mu[i] * inv_l) - da;
+}
+
+// Device-side terminal currents: the boundary term of the rhs on the sites that touch a terminal
+// edge, rewritten by the step that sees a current density change —
+//   bterm_i = sum over the boundary edges b at site i of (l_b * mu_boundary[b]) / (2 a_i)
+//             (mu_boundary_laplacian @ mu_boundary, operators.py:188-230, as k_boundary_term)
+//           + the dA/dt part of the site (as k_site_terms).
+// One thread per listed site; site_ptr / site_bedge: its boundary edges.
+__global__ void __launch_bounds__(kBlock)
+k_terminal_sites(const Ctl* __restrict__ ctl, int n_list, const int* __restrict__ site,
+                 const int* __restrict__ site_ptr, const int* __restrict__ site_bedge,
+                 const int* __restrict__ bedge_term, const double* __restrict__ blen,
+                 const double* __restrict__ areas, const int* __restrict__ ptr,
+                 const int* __restrict__ eidx, const signed char* __restrict__ head,
+                 const double* __restrict__ weight, const double* __restrict__ elen,
+                 const double* __restrict__ dadt /* may be null */, double* __restrict__ bterm_base,
+                 double* __restrict__ bterm) {
+  griddep_enter();
+  if (ctl->status != 0 || !ctl->cur_changed) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_list) return;
+  const int row = site[t];
+  double base = 0.0;
+  for (int k = site_ptr[t]; k < site_ptr[t + 1]; ++k) {
+    const int b = site_bedge[k];
+    const int term = bedge_term[b];
+    if (term < 0) continue;
+    base += (blen[b] * ctl->cur_dens[term]) / (2.0 * areas[row]);
+  }
+  double s = 0.0;
+  if (dadt != nullptr)
+    for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
+      const int e = eidx[k];
+      if (e < 0) continue;
+      const double dual = weight[e] * elen[e];
+      s += (head[k] ? dual : -dual) / areas[row] * dadt[e];
+    }
+  bterm_base[row] = base;
+  bterm[row] = base + s;
 }
 
 // ------------------------------------------------------------------------------------------

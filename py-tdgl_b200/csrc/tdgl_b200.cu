@@ -365,6 +365,8 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     }
     be0_.upload(b0, stream_);
     be1_.upload(b1, stream_);
+    h_b0_ = b0;
+    h_b1_ = b1;
     blen_.upload(bl, stream_);
     mub_.alloc(Eb_ > 0 ? Eb_ : 1);
     mub_.zero(stream_);
@@ -843,12 +845,12 @@ void Engine::enqueue_psi_step(double* sq_out, double dt_override) {
     launch_k(kw_psi_step<true>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
              ctl_.p, comm(), make_psi_comm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
              psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override,
-             scr_on_ ? old_sq_.p : nullptr);
+             scr_on_ ? old_sq_.p : nullptr, eps_dyn_ ? eps1_.p : nullptr);
   else
     launch_k(kw_psi_step<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
              ctl_.p, comm(), PsiComm(), site_csr(), lval_.p, fixed_.p, psi_[0].p, psi_[1].p,
              psi_[0].p, psi_[1].p, mu_.p, eps_.p, sq_out, dt_override,
-             scr_on_ ? old_sq_.p : nullptr);
+             scr_on_ ? old_sq_.p : nullptr, eps_dyn_ ? eps1_.p : nullptr);
   TDGL_LAUNCH_CHECK();
 }
 
@@ -983,7 +985,7 @@ void Engine::build_graph() {
   sb.capture([&] {
     launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_, h_scr_);
     TDGL_LAUNCH_CHECK();
-    enqueue_ramp_links();
+    enqueue_step_inputs();
     if (scr_on_) {
       launch_k(k_scr_old_sq, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, psi_[0].p, psi_[1].p, old_sq_.p);
       TDGL_LAUNCH_CHECK();
@@ -1043,7 +1045,7 @@ void Engine::build_split_graphs() {
     a.capture([&] {
       launch_k(k_step_begin, 1, 32, 0, ctl_.p, h_psi_a_, static_cast<cudaGraphConditionalHandle>(0));
       TDGL_LAUNCH_CHECK();
-      enqueue_ramp_links();
+      enqueue_step_inputs();
     });
     cudaGraph_t psi_body = a.add_while(h_psi_a_);
     GraphBuilder pb{psi_body, stream_, {}};
@@ -1090,6 +1092,108 @@ void Engine::set_link_exponents(const double* A) {
       N_, ptr_.p, eidx_.p, head_.p, weight_.p, theta_.p, areas_.p, lval_.p);
   TDGL_LAUNCH_CHECK();
   TDGL_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::enqueue_step_inputs() {
+  enqueue_ramp_links();
+  if (cur_on_ && n_ts_ > 0) {
+    launch_k(k_terminal_sites, (n_ts_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, n_ts_, ts_site_.p,
+             ts_ptr_.p, ts_bedge_.p, bedge_term_.p, blen_.p, areas_.p, ptr_.p, eidx_.p, head_.p,
+             weight_.p, elen_.p, has_dadt_ ? dadt_.p : nullptr, bterm_base_.p, bterm_.p);
+    TDGL_LAUNCH_CHECK();
+  }
+}
+
+// Time-dependent terminal currents as piecewise-linear tables evaluated on the device
+// (update_mu_boundary, solver.py:325-345, without the per-step host callback).
+//   term_of_bedge[Eb]: terminal index of every boundary edge (-1: none); lengths[n_term];
+//   values[n_term][n_knots]: J_scale-d currents at the knots.  n_knots = 0 turns it off.
+void Engine::set_terminal_currents(int n_term, const int32_t* term_of_bedge, const double* lengths,
+                                   int n_knots, const double* t_knots, const double* values) {
+  const bool was_on = cur_on_;
+  sync_ctl_to_host();
+  if (n_knots == 0) {
+    cur_on_ = false;
+    h_ctl_->cur_on = 0;
+    push_ctl();
+  } else {
+    if (n_term < 1 || n_term > kMaxTerminals) throw std::invalid_argument("1..8 terminals");
+    if (n_knots < 2 || n_knots > kMaxKnots) throw std::invalid_argument("current tables need 2..32 knots");
+    for (int k = 1; k < n_knots; ++k)
+      if (!(t_knots[k] > t_knots[k - 1])) throw std::invalid_argument("knots must increase");
+    std::vector<int> term(std::max(Eb_, 1), -1);
+    for (int b = 0; b < Eb_; ++b) {
+      if (term_of_bedge[b] >= n_term) throw std::invalid_argument("terminal index out of range");
+      term[b] = term_of_bedge[b];
+    }
+    // owned sites that touch a terminal edge, each with ALL its boundary edges
+    std::vector<std::vector<int>> at(N_);
+    std::vector<char> touched(N_, 0);
+    for (int b = 0; b < Eb_; ++b)
+      for (int s_ : {h_b0_[b], h_b1_[b]})
+        if (s_ >= 0) {
+          at[s_].push_back(b);
+          if (term[b] >= 0) touched[s_] = 1;
+        }
+    std::vector<int> site, sptr{0}, sb;
+    for (int i = 0; i < N_; ++i)
+      if (touched[i]) {
+        site.push_back(i);
+        for (int b : at[i]) sb.push_back(b);
+        sptr.push_back(static_cast<int>(sb.size()));
+      }
+    n_ts_ = static_cast<int>(site.size());
+    if (site.empty()) { site.push_back(0); }
+    if (sb.empty()) sb.push_back(0);
+    ts_site_.upload(site, stream_);
+    ts_ptr_.upload(sptr, stream_);
+    ts_bedge_.upload(sb, stream_);
+    bedge_term_.upload(term, stream_);
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+    cur_on_ = true;
+    h_ctl_->cur_on = 1;
+    h_ctl_->cur_nterm = n_term;
+    h_ctl_->cur_knots = n_knots;
+    for (int k = 0; k < n_knots; ++k) h_ctl_->cur_t[k] = t_knots[k];
+    for (int j = 0; j < n_term; ++j) {
+      h_ctl_->cur_len[j] = lengths[j];
+      h_ctl_->cur_dens[j] = 0.0;
+      for (int k = 0; k < n_knots; ++k) h_ctl_->cur_v[j][k] = values[static_cast<size_t>(j) * n_knots + k];
+    }
+    h_ctl_->cur_changed = 2;   // the first step writes the boundary term
+    push_ctl();
+  }
+  if (was_on != cur_on_) rebuild_graph();
+}
+
+// epsilon(r, t) = eps0(r) + g(t) eps1(r), g piecewise linear: evaluated inside the psi step
+// (update_epsilon, solver.py:364-381, 644-646, without the per-step host callback).
+void Engine::set_epsilon_table(const double* eps0, const double* eps1, int n_knots,
+                               const double* t_knots, const double* g_knots) {
+  const bool was_on = eps_dyn_;
+  sync_ctl_to_host();
+  if (n_knots == 0) {
+    eps_dyn_ = false;
+    h_ctl_->eps_on = 0;
+    push_ctl();
+  } else {
+    if (n_knots < 2 || n_knots > kMaxKnots) throw std::invalid_argument("epsilon tables need 2..32 knots");
+    for (int k = 1; k < n_knots; ++k)
+      if (!(t_knots[k] > t_knots[k - 1])) throw std::invalid_argument("knots must increase");
+    set_epsilon(eps0);
+    tmp_d_.upload(eps1, Ng_, stream_);
+    if (eps1_.n == 0) eps1_.alloc(Nx_);
+    k_gather<double><<<(Nx_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(Nx_, dperm_.p, tmp_d_.p, eps1_.p);
+    TDGL_LAUNCH_CHECK();
+    TDGL_CUDA(cudaStreamSynchronize(stream_));
+    eps_dyn_ = true;
+    h_ctl_->eps_on = 1;
+    h_ctl_->eps_knots = n_knots;
+    for (int k = 0; k < n_knots; ++k) { h_ctl_->eps_t[k] = t_knots[k]; h_ctl_->eps_v[k] = g_knots[k]; }
+    h_ctl_->eps_g = g_knots[0];
+    push_ctl();
+  }
+  if (was_on != eps_dyn_) rebuild_graph();
 }
 
 void Engine::enqueue_ramp_links() {
@@ -1378,14 +1482,14 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
     // per step: k_step_begin, k_step_end (+ ramp links, + |psi|^2 snapshot); per pass: psi step +
     // control, rhs, cg_begin, mu_guess, weighted_sum, shift (+ 5 screening kernels); per dt
     // retry: psi step + control; per CG iteration: V-cycle (4 per level + coarsest) + SpMV + update
-    launches_ += h_ctl_->steps_done * (2 + ex_step + (ramp_on_ ? 1 : 0) + (scr_on_ ? 1 : 0)) +
+    launches_ += h_ctl_->steps_done * (2 + ex_step + (ramp_on_ ? 1 : 0) + (scr_on_ ? 1 : 0) + (cur_on_ ? 1 : 0)) +
                  passes * (7 + (scr_on_ ? 5 : 0)) + h_ctl_->total_retries * 2 +
                  h_ctl_->total_cg_it * (2 + 4 * split + 1 + ex_it);
   } else {
     while (true) {
       launch_k(k_step_begin, 1, 32, 0, ctl_.p, 0, 0);
       TDGL_LAUNCH_CHECK();
-      enqueue_ramp_links();
+      enqueue_step_inputs();
       if (scr_on_) {
         launch_k(k_scr_old_sq, (N_ + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, N_, psi_[0].p, psi_[1].p, old_sq_.p);
         TDGL_LAUNCH_CHECK();
@@ -1829,7 +1933,8 @@ void Engine::op_psi_step(const double* psi, const double* mu, double dt, double*
   push_ctl();
   launch_k(kw_psi_step<false>, grid_win(N_, win0_), win0_, static_cast<size_t>(cap0_) * 20,
            ctl_.p, static_cast<const Comm*>(nullptr), PsiComm(), site_csr(), lval_.p, fixed_.p, pin.p,
-           pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p, dt, static_cast<const double*>(nullptr));
+           pin.p, pout.p, pout.p, muin.p, eps_.p, sq.p, dt, static_cast<const double*>(nullptr),
+           static_cast<const double*>(nullptr));
   TDGL_LAUNCH_CHECK();
   k_scatter<double2><<<g, kBlock, 0, stream_>>>(N_, dperm_.p, pout.p, tmp_c_.p);
   TDGL_LAUNCH_CHECK();
@@ -2243,6 +2348,23 @@ int tdgl_set_vector_potential_ramp(tdgl_handle* h, const double* A0, int32_t n_k
   return guarded(h, [&](tdgl::Engine& e) {
     if (n_knots > 0 && (!A0 || !t_knots || !f_knots)) throw std::invalid_argument("null ramp argument");
     e.set_ramp(A0, n_knots, t_knots, f_knots);
+  });
+}
+int tdgl_set_terminal_current_table(tdgl_handle* h, int32_t n_terminals, const int32_t* terminal_of_boundary_edge,
+                                    const double* terminal_lengths, int32_t n_knots,
+                                    const double* t_knots, const double* currents) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (n_knots > 0 && (!terminal_of_boundary_edge || !terminal_lengths || !t_knots || !currents))
+      throw std::invalid_argument("null table argument");
+    e.set_terminal_currents(n_terminals, terminal_of_boundary_edge, terminal_lengths, n_knots, t_knots, currents);
+  });
+}
+int tdgl_set_epsilon_table(tdgl_handle* h, const double* epsilon0, const double* epsilon1,
+                           int32_t n_knots, const double* t_knots, const double* g_knots) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (n_knots > 0 && (!epsilon0 || !epsilon1 || !t_knots || !g_knots))
+      throw std::invalid_argument("null table argument");
+    e.set_epsilon_table(epsilon0, epsilon1, n_knots, t_knots, g_knots);
   });
 }
 int tdgl_set_screening(tdgl_handle* h, int32_t enable, double scale, const double* sites_xy,

@@ -208,6 +208,30 @@ class DeviceEngine:
         self._check(self._lib.tdgl_set_vector_potential_ramp(
             self._h, ptr(as_f64(A0, (self.n_edges, 2))), len(t), ptr(t), ptr(f)))
 
+    def set_terminal_current_table(self, terminal_of_boundary_edge, lengths, t_knots, currents) -> None:
+        """Device-side I_k(t) tables (``currents`` [n_terminals, n_knots], J_scale-d); empty
+        ``t_knots`` turns them off."""
+        if t_knots is None or len(t_knots) == 0:
+            self._check(self._lib.tdgl_set_terminal_current_table(self._h, 0, None, None, 0, None, None))
+            return
+        term = np.ascontiguousarray(terminal_of_boundary_edge, dtype=np.int32)
+        if term.shape != (self.n_boundary_edges,):
+            raise ValueError("one terminal index per boundary edge")
+        L, t = as_f64(lengths), as_f64(t_knots)
+        cur = as_f64(currents, (len(L), len(t)))
+        self._check(self._lib.tdgl_set_terminal_current_table(
+            self._h, len(L), ptr(term), ptr(L), len(t), ptr(t), ptr(cur)))
+
+    def set_epsilon_table(self, eps0, eps1, t_knots, g_knots) -> None:
+        """epsilon(r, t) = eps0 + g(t) eps1 evaluated on the device; empty knots: off."""
+        if t_knots is None or len(t_knots) == 0:
+            self._check(self._lib.tdgl_set_epsilon_table(self._h, None, None, 0, None, None))
+            return
+        t, g = as_f64(t_knots), as_f64(g_knots)
+        self._check(self._lib.tdgl_set_epsilon_table(
+            self._h, ptr(as_f64(eps0, (self.n_sites,))), ptr(as_f64(eps1, (self.n_sites,))),
+            len(t), ptr(t), ptr(g)))
+
     def set_screening(self, scale: float, sites_xy, edge_centers, *, tolerance: float,
                       max_iterations: int, step_size: float, step_drag: float) -> None:
         """Turn on the screening iteration (include/tdgl_b200.h, tdgl_set_screening)."""

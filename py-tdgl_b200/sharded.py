@@ -209,6 +209,12 @@ class LocalShardGroup:
     def set_vector_potential_ramp(self, A0, t_knots, f_knots):
         self._all(lambda e: e.set_vector_potential_ramp(A0, t_knots, f_knots))
 
+    def set_terminal_current_table(self, *a):
+        self._all(lambda e: e.set_terminal_current_table(*a))
+
+    def set_epsilon_table(self, *a):
+        self._all(lambda e: e.set_epsilon_table(*a))
+
     def set_state(self, psi, mu):
         self._all(lambda e: e.set_state(psi, mu))
 

@@ -264,6 +264,10 @@ class TDGLSolver:
 
             static_currents = True
         J_scale = scales.J_scale
+        if hasattr(user_func, "knots"):      # a table (sources.PiecewiseLinearCurrents)
+            scaled_currents = user_func.scaled(J_scale)
+        else:
+            scaled_currents = lambda t: {k: J_scale * v for k, v in user_func(t).items()}  # noqa: E731
         screening = None
         if options.include_screening:
             # solver.py:306-309: A_scale = mu_0 / (4 pi) K0 / A0 in 1 / length_units,
@@ -272,8 +276,16 @@ class TDGLSolver:
 
             a_scale = MU_0 / (4 * np.pi) * device.K0 / device.A0 * length_scale(device.length_units)
             screening = (a_scale * xi**2, sites, edge_centers)
+        eps_table = None
+        if hasattr(disorder_epsilon, "arrays"):          # sources.SeparableEpsilon
+            e0, e1 = disorder_epsilon.arrays(sites)
+            eps_table = (e0, e1, disorder_epsilon.times, disorder_epsilon.g)
+            eval_eps = lambda t=None, _e=disorder_epsilon, _a=(e0, e1): (  # noqa: E731
+                _a[0] + np.float64(_e.scale(0.0 if t is None else t)) * _a[1])
+            dynamic_epsilon = True
+        self._eps_table = eps_table
         self._setup(mesh, options, A, eval_eps, dynamic_epsilon, terminal_info,
-                    lambda t: {k: J_scale * v for k, v in user_func(t).items()},
+                    scaled_currents,
                     static_currents, device.probe_point_indices, device.layer.u,
                     device.layer.gamma, eval_A=eval_A if dynamic_A else None, ramp=ramp,
                     screening=screening)
@@ -303,8 +315,14 @@ class TDGLSolver:
         self.seed_solution = seed_solution
         self.applied_vector_potential = None
         self.disorder_epsilon = None
+        self._eps_table = None
         dynamic_epsilon = callable(epsilon)
-        if dynamic_epsilon:
+        if hasattr(epsilon, "arrays"):                   # sources.SeparableEpsilon
+            e0, e1 = epsilon.arrays(mesh.sites)
+            self._eps_table = (e0, e1, epsilon.times, epsilon.g)
+            eval_eps = lambda t=None, _e=epsilon, _a=(e0, e1): (  # noqa: E731
+                _a[0] + np.float64(_e.scale(0.0 if t is None else t)) * _a[1])
+        elif dynamic_epsilon:
             eval_eps = lambda t=None, _f=epsilon: np.asarray(  # noqa: E731
                 _f(0.0 if t is None else t), dtype=float)
         else:
@@ -395,6 +413,23 @@ class TDGLSolver:
         if ramp is not None:
             self.engine.set_vector_potential_ramp(*ramp)
         self.engine.set_epsilon(epsilon)
+        # tables the device evaluates itself (no per-step host work)
+        self._current_table = False
+        knots = getattr(current_func, "knots", None)
+        if knots is not None and self.terminal_info:
+            t_knots, table = knots
+            if unknown := set(table).difference(self.terminal_names):
+                raise ValueError(f"Unknown terminal(s) in terminal currents: {list(unknown)}.")
+            nb = len(mesh.edge_mesh.boundary_edge_indices)
+            term_of = np.full(nb, -1, dtype=np.int32)
+            for k, term in enumerate(self.terminal_info):
+                term_of[np.asarray(term.boundary_edge_indices, dtype=np.int64)] = k
+            cur = np.array([table.get(name, np.zeros(len(t_knots))) for name in self.terminal_names])
+            self.engine.set_terminal_current_table(
+                term_of, [t.length for t in self.terminal_info], t_knots, cur)
+            self._current_table = True
+        if getattr(self, "_eps_table", None) is not None:
+            self.engine.set_epsilon_table(*self._eps_table)
         self.include_screening = screening is not None
         if screening is not None:
             self.engine.set_screening(
@@ -426,6 +461,13 @@ class TDGLSolver:
         """reference solver.py:325-345; uploads only when a density changed."""
         currents = self.current_func(time)
         changed = False
+        if self._current_table:      # the device evaluates the table itself (k_step_begin)
+            for term in self.terminal_info:
+                dens = (-1 / term.length) * sum(
+                    currents.get(name, 0) for name in self.terminal_names if name != term.name)
+                self.terminal_current_densities[term.name] = dens
+                self.mu_boundary[np.asarray(term.boundary_edge_indices)] = dens
+            return
         for term in self.terminal_info:
             dens = (-1 / term.length) * sum(
                 currents.get(name, 0) for name in self.terminal_names if name != term.name)
@@ -468,7 +510,8 @@ class TDGLSolver:
         self._update_vector_potential(time, float(dt), applied_vector_potential)
         if self.dynamic_epsilon:
             self.epsilon = self._eval_eps(time)
-            self.engine.set_epsilon(self.epsilon)
+            if self._eps_table is None:
+                self.engine.set_epsilon(self.epsilon)
         if self.include_screening and induced_vector_potential is not None:
             self.engine.set_induced_vector_potential(induced_vector_potential)
         try:
@@ -544,7 +587,9 @@ class TDGLSolver:
     def _stage_loop(self, name, end_time, save, saved, running, first_values, saver) -> bool:
         opts = self.options
         every = max(int(opts.save_every), 1)
-        per_step_host = ((not self.static_currents) or self.dynamic_epsilon
+        host_currents = (not self.static_currents) and not self._current_table
+        host_epsilon = self.dynamic_epsilon and self._eps_table is None
+        per_step_host = (host_currents or host_epsilon
                          or (self.dynamic_vector_potential and self._ramp is None))
         i, time = 0, 0.0
         cancelled = False
@@ -584,7 +629,7 @@ class TDGLSolver:
                         break
                 self.update_mu_boundary(time)
                 self._update_vector_potential(time, self._prev_dt)
-                if self.dynamic_epsilon:
+                if host_epsilon:
                     self.epsilon = self._eval_eps(time)
                     self.engine.set_epsilon(self.epsilon)
                 chunk = 1 if per_step_host else every - (i % every)
@@ -593,10 +638,12 @@ class TDGLSolver:
                 except (StepFailed, ScreeningFailed) as exc:
                     self._raise_like_reference(exc)
                 k = info.steps_done
+                t_last = info.time if info.finished else info.time - info.dt
                 if self._ramp is not None:
                     # the vector potential of the last step taken (saved with the results)
-                    t_last = info.time if info.finished else info.time - info.dt
                     self.current_A_applied = self._eval_A(t_last)
+                if self._eps_table is not None:     # epsilon of the last step taken
+                    self.epsilon = self._eval_eps(t_last)
                 dt, mu_p, th_p = self.engine.get_running(k)
                 pos = running.step
                 running.values["dt"][0, pos:pos + k] = dt

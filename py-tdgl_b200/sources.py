@@ -106,3 +106,78 @@ def ConstantField(value: float = 0, field_units: str = "mT", length_units: str =
 def LinearRamp(*, tmin: float, tmax: float, initial: float = 0.0, final: float = 1.0) -> Ramp:
     """reference ``LinearRamp`` (sources/scaling.py:17-40)."""
     return Ramp(tmin, tmax, initial, final)
+
+
+def _table_lookup(t_knots: np.ndarray, values: np.ndarray, t: float) -> float:
+    """Piecewise-linear interpolation, constant outside the knots — the arithmetic of the
+    device's ``table_lookup`` (csrc/kernels.cuh), operation for operation."""
+    n = len(t_knots)
+    if t >= t_knots[n - 1]:
+        return float(values[n - 1])
+    if t <= t_knots[0]:
+        return float(values[0])
+    k = 0
+    while k + 2 < n and t >= t_knots[k + 1]:
+        k += 1
+    w = (np.float64(t) - t_knots[k]) / (t_knots[k + 1] - t_knots[k])
+    return float(values[k] + w * (values[k + 1] - values[k]))
+
+
+class PiecewiseLinearCurrents:
+    """Time-dependent terminal currents ``t -> {name: I}`` given by knots.  Usable wherever the
+    reference takes a callable ``terminal_currents`` (solver.py:234-249); because it is a table,
+    ``TDGLSolver`` hands it to the device (``tdgl_set_terminal_current_table``) and the run needs
+    no per-step host callback — a generic callable is evaluated from Python every step, like in
+    the reference.
+
+    ``times``: increasing knots; ``currents``: ``{terminal name: values at the knots}``."""
+
+    def __init__(self, times: Sequence[float], currents):
+        t = np.asarray(times, dtype=np.float64)
+        if t.ndim != 1 or len(t) < 2 or np.any(np.diff(t) <= 0):
+            raise ValueError("times must be at least two increasing knots")
+        self.times = t
+        self.currents = {str(k): np.asarray(v, dtype=np.float64) for k, v in currents.items()}
+        for k, v in self.currents.items():
+            if v.shape != t.shape:
+                raise ValueError(f"currents[{k!r}] must have one value per knot")
+
+    @property
+    def knots(self):
+        return self.times, self.currents
+
+    def scaled(self, factor: float) -> "PiecewiseLinearCurrents":
+        return PiecewiseLinearCurrents(self.times, {k: factor * v for k, v in self.currents.items()})
+
+    def __call__(self, t: float):
+        return {k: _table_lookup(self.times, v, t) for k, v in self.currents.items()}
+
+
+class SeparableEpsilon:
+    """``epsilon(r, t) = e0(r) + g(t) * e1(r)`` with piecewise-linear ``g``: a time-dependent
+    disorder parameter (the reference's ``disorder_epsilon(r, *, t)``, solver.py:364-381) in a
+    form the device evaluates inside the psi step (``tdgl_set_epsilon_table``).  ``e0`` / ``e1``:
+    callables ``r -> value`` evaluated at the sites (vectorised: ``r`` is [N, 2]) or arrays
+    [N]; ``times`` / ``g``: the knots of g."""
+
+    def __init__(self, e0, e1, times: Sequence[float], g: Sequence[float]):
+        self.e0, self.e1 = e0, e1
+        self.times = np.asarray(times, dtype=np.float64)
+        self.g = np.asarray(g, dtype=np.float64)
+        if self.times.ndim != 1 or len(self.times) < 2 or np.any(np.diff(self.times) <= 0):
+            raise ValueError("times must be at least two increasing knots")
+        if self.g.shape != self.times.shape:
+            raise ValueError("g must have one value per knot")
+
+    def arrays(self, sites: np.ndarray):
+        def ev(f):
+            return (np.asarray(f(sites), dtype=np.float64) if callable(f)
+                    else np.asarray(f, dtype=np.float64))
+        return ev(self.e0), ev(self.e1)
+
+    def scale(self, t: float) -> float:
+        return _table_lookup(self.times, self.g, t)
+
+    def __call__(self, r, *, t: float, vectorized: bool = True):
+        e0, e1 = self.arrays(np.atleast_2d(r))
+        return e0 + np.float64(self.scale(t)) * e1

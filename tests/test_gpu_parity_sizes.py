@@ -327,3 +327,42 @@ def test_update_seam_positional_contract_with_dynamic_epsilon():
         assert threaded["induced_vector_potential"].shape == (E, 2)
         dt = new_dt
         time += dt
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_device_side_current_and_epsilon_tables(use_graph):
+    """Time-dependent terminal currents and epsilon given as tables
+    (sources.PiecewiseLinearCurrents / SeparableEpsilon) are evaluated by the device inside the
+    step loop: same numbers as the reference's per-step Python callbacks (solver.py:325-345,
+    364-381), but the host is only woken at save steps."""
+    from tdgl_b200 import SolverOptions, TDGLSolver
+    from tdgl_b200.sources import PiecewiseLinearCurrents, SeparableEpsilon
+
+    c = load_case("strip_transport")
+    I = c.currents["source"]
+    cur = PiecewiseLinearCurrents([0.0, 0.4, 1.0], {"source": [I, 1.1 * I, 1.25 * I],
+                                                     "drain": [-I, -1.1 * I, -1.25 * I]})
+    eps = SeparableEpsilon(c.eps, c.eps, [0.0, 1.0], [0.0, -0.1])
+    e0, e1 = eps.arrays(c.mesh.sites)
+    okw = dict(solve_time=1.3, skip_time=0.2, dt_init=c.opts["dt_init"], dt_max=c.opts["dt_max"])
+    o = orc.OracleSolver(c.mesh, orc.OracleOptions(**okw), c.A, e0 + eps.scale(0.0) * e1, u=c.u,
+                         gamma=c.gamma, terminal_info=[orc.TerminalInfo(*t) for t in c.terminals],
+                         current_func=cur, epsilon_func=lambda t: e0 + np.float64(eps.scale(t)) * e1,
+                         probe_points=c.probes)
+    ref = orc.run_stages(o)
+    solver = TDGLSolver.from_dimensionless(
+        c.mesh, SolverOptions(save_every=40, use_cuda_graph=use_graph, **okw), A_applied=c.A,
+        epsilon=eps, terminal_info=c.terminals, terminal_currents=cur,
+        probe_point_indices=c.probes, u=c.u, gamma=c.gamma)
+    calls = []
+    advance = solver.engine.advance
+    solver.engine.advance = lambda *a: (calls.append(a[0]), advance(*a))[1]
+    sol = solver.solve()
+    d = sol.tdgl_data
+    got = dict(psi=d.psi, mu=d.mu, supercurrent=d.supercurrent, normal_current=d.normal_current,
+               dt=sol.dynamics.dt)
+    _check_edge("device-side I(t) and eps(t) tables", c, got, ref)
+    # chunks of save_every steps, not one host round trip per step
+    assert len(calls) <= 2 + ref["steps"] // 40 + 2 and max(calls) == 40, calls
+    t_last = float(sol.dynamics.time[-1] - sol.dynamics.dt[-1])
+    np.testing.assert_allclose(d.epsilon, e0 + eps.scale(t_last) * e1, rtol=0, atol=1e-15)
