@@ -251,16 +251,38 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict_
   const double alpha = gamma / denom;
   const unsigned int tag = comm != nullptr ? comm_tag(ctl, push.tag_mode) : 0u;
   double d = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double pi = first ? z[i] : z[i] + beta * p[i];
-    const double si = first ? w[i] : w[i] + beta * s[i];
+  // two independent elements per trip: twelve loads in flight per thread
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    const int j = i + stride;
+    const bool two = j < n;
+    const double zi = z[i], wi = w[i], xi = x[i], ri0 = r[i];
+    const double pi0 = first ? 0.0 : p[i], si0 = first ? 0.0 : s[i];
+    double zj = 0.0, wj = 0.0, xj = 0.0, rj0 = 0.0, pj0 = 0.0, sj0 = 0.0;
+    if (two) {
+      zj = z[j]; wj = w[j]; xj = x[j]; rj0 = r[j];
+      if (!first) { pj0 = p[j]; sj0 = s[j]; }
+    }
+    const double pi = first ? zi : zi + beta * pi0;
+    const double si = first ? wi : wi + beta * si0;
     p[i] = pi;
     s[i] = si;
-    x[i] += alpha * pi;
-    const double ri = r[i] - alpha * si;
+    x[i] = xi + alpha * pi;
+    const double ri = ri0 - alpha * si;
     r[i] = ri;
     if (comm != nullptr) push_row(comm, push, tag, i, ri);  // next iteration's V-cycle input
     d += ri * ri;
+    if (two) {
+      const double pj = first ? zj : zj + beta * pj0;
+      const double sj = first ? wj : wj + beta * sj0;
+      p[j] = pj;
+      s[j] = sj;
+      x[j] = xj + alpha * pj;
+      const double rj = rj0 - alpha * sj;
+      r[j] = rj;
+      if (comm != nullptr) push_row(comm, push, tag, j, rj);
+      d += rj * rj;
+    }
   }
   const double bs = block_sum(d, red);
   double total;
