@@ -174,7 +174,13 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   TDGL_CUDA(cudaSetDevice(cfg_.device));
   TDGL_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, cfg_.device));
   TDGL_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  TDGL_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  {
+    // the copy stream's few small kernels (scatter, edge currents) must not queue behind the
+    // CTAs of the solve they overlap with: highest priority
+    int lo = 0, hi = 0;
+    TDGL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TDGL_CUDA(cudaStreamCreateWithPriority(&copy_stream_, cudaStreamNonBlocking, hi));
+  }
   TDGL_CUDA(cudaEventCreate(&ev0_));
   TDGL_CUDA(cudaEventCreate(&ev1_));
   TDGL_CUDA(cudaEventCreateWithFlags(&ev_psi_, cudaEventDisableTiming));

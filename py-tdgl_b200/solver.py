@@ -532,7 +532,12 @@ class TDGLSolver:
         self.stats["mu_iterations"] += info.mu_iterations
         self.stats["screening_iterations"] += info.screening_iterations
         if induced_vector_potential is None:
-            induced_vector_potential = np.zeros((self.num_edges, 2))
+            # (one shared read-only zero array: a fresh 16 B/edge allocation per step costs
+            # more than the device-to-host copies of a step at 1M sites)
+            if getattr(self, "_zero_A_induced", None) is None:
+                self._zero_A_induced = np.zeros((self.num_edges, 2))
+                self._zero_A_induced.setflags(write=False)
+            induced_vector_potential = self._zero_A_induced
         results = [info.dt, psi1, mu1, js, jn, induced_vector_potential]
         if self.dynamic_vector_potential:
             results.append(self.current_A_applied)
