@@ -207,6 +207,7 @@ struct RealArgs {
   // go.  Defaults: no halo, nothing to send.
   HaloArgs halo;
   PushArgs push;
+  int trace_id = 0;              // debug timeline slot (kernels.cuh trace_in / trace_out)
 };
 
 // Storage types of one kw_real instantiation.  The CG iteration works in double (kTypesD).
@@ -259,6 +260,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
   __shared__ double red[32];
+  trace_in(ctl, a.trace_id, 0);
   const WinRow w = window_stage<sizeof(TV), 0, LPR>(m, a.val, nullptr, win_smem, &bar);
   const TV* sv = reinterpret_cast<const TV*>(win_smem);
   const int* si = reinterpret_cast<const int*>(win_smem + static_cast<size_t>(m.cap) * sizeof(TV));
@@ -269,6 +271,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   TY* ay = static_cast<TY*>(a.y);
   TR* ar = static_cast<TR*>(a.r);
   griddep_wait();
+  trace_in(ctl, a.trace_id, 1);
   const bool live = (ctl->status == 0);
   const bool in = live && w.row < m.rows;
   const int sub = threadIdx.x & (LPR - 1);   // lane of the row (LPR lanes share a long row)
@@ -390,6 +393,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
       if (threadIdx.x == 0) *a.red_out = total;
     }
   }
+  trace_out(ctl, a.trace_id);
 }
 
 // ---- psi step ----------------------------------------------------------------------------------

@@ -347,6 +347,15 @@ class Engine {
   // bulk copies of its (static) CSR window, and blocks in griddepcontrol.wait until the
   // predecessor's results are visible.  TDGL_B200_PDL=0 turns the attribute off.
   bool pdl_ = true;
+  // debug timeline (TDGL_B200_TRACE=1): one slot per enqueued (captured) launch of the CG
+  // iteration's kernels; trace_report() prints the last pass through every slot
+  bool trace_on_ = false;
+  DevBuf<unsigned long long> trace_;
+  std::vector<std::string> trace_names_;
+  int trace_slot(const char* name, int rows);
+ public:
+  void trace_report();
+ private:
   template <typename... KArgs, typename... Args>
   void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

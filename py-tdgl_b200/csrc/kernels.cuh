@@ -84,6 +84,9 @@ struct Ctl {
   double ramp_f;       // f at the current step
   double ramp_dfdt;    // (f(t) - f(t_prev)) / dt_prev, the reference's backward difference
   double ramp_t[kMaxKnots], ramp_v[kMaxKnots];
+  // --- debug timeline (TDGL_B200_TRACE=1): 4 words per traced launch {first CTA in, first CTA
+  //     past griddepcontrol.wait, last CTA out, launches}, %globaltimer ns; null = off ----------
+  unsigned long long* trace;
 };
 
 // Programmatic dependent launch: `griddep_wait` blocks until the kernels this launch depends
@@ -92,6 +95,21 @@ struct Ctl {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// Debug timeline of the stepping kernels (Ctl::trace; Engine::trace_report).  `id` 0 = untraced.
+__device__ __forceinline__ unsigned long long trace_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_in(const Ctl* ctl, int id, int word) {
+  if (id > 0 && ctl->trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->trace[4 * id + word] = trace_ns();
+    if (word == 0) ctl->trace[4 * id + 3] += 1ull;
+  }
+}
+__device__ __forceinline__ void trace_out(const Ctl* ctl, int id) {
+  if (id > 0 && ctl->trace != nullptr && threadIdx.x == 0) atomicMax(ctl->trace + 4 * id + 2, trace_ns());
 }
 // kernels without a static prologue: let the successor in, then wait for the predecessor
 __device__ __forceinline__ void griddep_enter() {
@@ -207,17 +225,21 @@ __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
 template <typename TM, typename TB, typename TX>
 __global__ void __launch_bounds__(kBlock)
 k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const TM* __restrict__ M,
-               const TB* __restrict__ b, TX* __restrict__ x) {
+               const TB* __restrict__ b, TX* __restrict__ x, int trace_id) {
+  trace_in(ctl, trace_id, 0);
   griddep_enter();
+  trace_in(ctl, trace_id, 1);
   if (ctl->status != 0) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const TM* row = M + static_cast<size_t>(warp) * nc;
-  double s = 0.0;
-  for (int j = lane; j < nc; j += 32) s = fma(static_cast<double>(row[j]), static_cast<double>(b[j]), s);
-  s = warp_sum(s);
-  if (lane == 0) x[warp] = static_cast<TX>(s);
+  if (warp < rows) {
+    const TM* row = M + static_cast<size_t>(warp) * nc;
+    double s = 0.0;
+    for (int j = lane; j < nc; j += 32) s = fma(static_cast<double>(row[j]), static_cast<double>(b[j]), s);
+    s = warp_sum(s);
+    if (lane == 0) x[warp] = static_cast<TX>(s);
+  }
+  trace_out(ctl, trace_id);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -234,8 +256,10 @@ __global__ void __launch_bounds__(kBlock)
 k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict__ z,
            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
            double* __restrict__ x, double* __restrict__ r, double* partials,
-           unsigned int* counter, cudaGraphConditionalHandle cond) {
+           unsigned int* counter, cudaGraphConditionalHandle cond, int trace_id) {
+  trace_in(ctl, trace_id, 0);
   griddep_enter();
+  trace_in(ctl, trace_id, 1);
   __shared__ double red[32];
   if (ctl->status != 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -309,6 +333,7 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict_
       set_cond(cond, go);
     }
   }
+  trace_out(ctl, trace_id);
 }
 
 // Decide whether the CG loop has to run at all (warm start may already satisfy the

@@ -509,6 +509,13 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   h_ctl_->n_probe = nprobe_; h_ctl_->running_capacity = cfg_.running_capacity;
   h_ctl_->tentative_dt = 1e-6; h_ctl_->dt = 1e-6;
   h_ctl_->solve_epoch = 1; h_ctl_->psi_epoch = 1; h_ctl_->psi_tag[0] = h_ctl_->psi_tag[1] = 1;
+  if (const char* e = std::getenv("TDGL_B200_TRACE")) trace_on_ = e[0] != '0';
+  if (trace_on_) {
+    trace_.alloc(4 * 512);
+    trace_.zero(stream_);
+    trace_names_.assign(1, "");
+    h_ctl_->trace = trace_.p;
+  }
   ctl_.alloc(1);
   push_ctl();
   {
@@ -720,12 +727,57 @@ void Engine::configure_kernels() {
 #define TDGL_LAUNCH_CHECK()                                                                \
   do { ++launches_; TDGL_CUDA(cudaGetLastError()); } while (0)
 
+int Engine::trace_slot(const char* name, int rows) {
+  if (!trace_on_ || trace_names_.size() >= 512) return 0;
+  char buf[96];
+  snprintf(buf, sizeof buf, "%-22s rows=%d", name, rows);
+  trace_names_.push_back(buf);
+  return static_cast<int>(trace_names_.size()) - 1;
+}
+
+// Timeline of the last pass through every traced launch: times in us relative to the earliest
+// entry; `in` = first CTA resident, `go` = first CTA past griddepcontrol.wait (its predecessor
+// has drained), `out` = last CTA done.
+void Engine::trace_report() {
+  if (!trace_on_ || trace_names_.size() < 2) return;
+  std::vector<unsigned long long> h(4 * trace_names_.size());
+  TDGL_CUDA(cudaMemcpy(h.data(), trace_.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+  std::vector<int> order;
+  unsigned long long t0 = ~0ull;
+  for (size_t i = 1; i < trace_names_.size(); ++i)
+    if (h[4 * i + 3] > 0) { order.push_back(static_cast<int>(i)); t0 = std::min(t0, h[4 * i]); }
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return h[4 * a] < h[4 * b]; });
+  fprintf(stderr, "[tdgl_b200 trace] %-34s %9s %9s %9s %8s %8s %8s\n", "launch", "in us", "go us", "out us",
+          "go-in", "out-go", "count");
+  for (int i : order) {
+    const double in = (h[4 * i] - t0) * 1e-3, go = (h[4 * i + 1] - t0) * 1e-3, out = (h[4 * i + 2] - t0) * 1e-3;
+    fprintf(stderr, "[tdgl_b200 trace] %-34s %9.2f %9.2f %9.2f %8.2f %8.2f %8llu\n", trace_names_[i].c_str(),
+            in, go, out, go - in, out - go, h[4 * i + 3]);
+  }
+  TDGL_CUDA(cudaMemset(trace_.p, 0, sizeof(unsigned long long) * trace_.n));
+}
+
+static const char* real_op_name(int op) {
+  switch (op) {
+    case kOpSpmvDot: return "spmv_dot";
+    case kOpResidual: return "residual";
+    case kOpPresmooth: return "presmooth";
+    case kOpJacobi: return "jacobi";
+    case kOpPlain: return "restrict";
+    case kOpPlainAdd: return "prolong_add";
+    case kOpSpmvCg: return "spmv_cg";
+  }
+  return "?";
+}
+
 template <int OP, typename T>
-void Engine::launch_real(const CsrView& A, const RealArgs& a) {
+void Engine::launch_real(const CsrView& A, const RealArgs& a_in) {
   if (A.vbytes != static_cast<int>(sizeof(typename T::V)))
     throw std::logic_error("kw_real: value type of the matrix and of the kernel differ");
   const size_t smem = static_cast<size_t>(A.m.cap) * (A.vbytes + 4);
   if (A.m.rows < 1) return;  // a shard may own no rows of a coarse level
+  RealArgs a = a_in;
+  a.trace_id = trace_slot(real_op_name(OP), A.m.rows);
   const int grid = grid_win(A.m.rows, A.win), block = A.win * A.lpr;
   if (A.lpr == 4) {
     if (comm_on_)
@@ -765,7 +817,7 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   if (L == 1) {
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
     launch_k(k_dense_matvec<float, double, double>, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p,
-             r_in, z_out);
+             r_in, z_out, trace_slot("dense", nc_));
     TDGL_LAUNCH_CHECK();
     if (rz_out != nullptr) {
       launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
@@ -810,7 +862,7 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
     DevLevel& c = levels_[split];
     const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
     launch_k(k_dense_matvec<float, float, float>, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p,
-             c.b.p, c.y.p);
+             c.b.p, c.y.p, trace_slot("dense", nc_));
     TDGL_LAUNCH_CHECK();
   }
   for (int li = split - 1; li >= 0; --li) {
@@ -901,7 +953,7 @@ void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   }
   launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
            comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_z_.p, cg_Ap_.p,
-           cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, partials_.p, counter_.p, cond);
+           cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, partials_.p, counter_.p, cond, trace_slot("cg_fused", N_));
   TDGL_LAUNCH_CHECK();
 }
 
@@ -1531,6 +1583,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   TDGL_CUDA(cudaEventSynchronize(ev1_));
   float dev_ms = 0.f;
   TDGL_CUDA(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
+  if (trace_on_) trace_report();
   return collect_advance(dev_ms);
 }
 
@@ -2065,7 +2118,7 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
       case 9:
         launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_z_.p,
                  cg_Ap_.p, cg_p_.p, cg_s_.p, tmp_d2_.p, cg_b_.p, partials_.p, counter_.p,
-                 static_cast<cudaGraphConditionalHandle>(0));
+                 static_cast<cudaGraphConditionalHandle>(0), 0);
         TDGL_LAUNCH_CHECK();
         break;
       case 3: enqueue_vcycle(cg_r_.p, cg_z_.p, nullptr); break;
