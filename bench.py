@@ -578,12 +578,17 @@ def run_b200(args, rank, world, local_rank):
         "kw_mu_rhs": (1, 28 * nnz + 92 * nl, 1.0),
         # w = A z with r.z and z.w: matrix, row pointers, z, r read, w written
         "kw_real<spmv_cg> fine level": (2, 12 * nnz + 28 * nl, iters_per_step),
-        # p, s, x, r updated from z, w: 6 reads + 4 writes per row
-        "k_cg_fused": (9, 80 * nl, iters_per_step),
+        # p, s, x, r updated from z, w (6 reads + 4 writes of 8 B per row) + 1/diag read and
+        # x0 = omega D^-1 r written (4 B each)
+        "k_cg_fused": (9, 88 * nl, iters_per_step),
     }
     if levels > 1:
-        kern["kw_real<presmooth> fine level"] = (5, 12 * nnz + 36 * nl, iters_per_step)
-        kern["kw_real<jacobi> fine level"] = (6, 12 * nnz + 36 * nl, iters_per_step)
+        # the V-cycle's operators are stored in fp32: 4 B value + 4 B column per entry;
+        # pre-smoother = residual of x0 (written by k_cg_fused): row pointers 4, r (f64) 8, x0 4
+        # read, r1 (f32) 4 written per row;
+        # post-smoother: row pointers 4, r 8, 1/diag 4, x 4 read, z (f64) 8 written per row
+        kern["kw_real<residual> fine level (pre-smoother)"] = (5, 8 * nnz + 20 * nl, iters_per_step)
+        kern["kw_real<jacobi> fine level"] = (6, 8 * nnz + 28 * nl, iters_per_step)
     table = {}
     for name, (which, nbytes, per_step) in kern.items():
         kms = eng.time_kernel(which, 20, flush_l2=True)

@@ -13,7 +13,9 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtdgl_b200.so")
+# (TDGL_B200_LIB: development only — a side-by-side build of the same sources, see
+# tools/build_variant.sh; there is still no fallback if it is missing)
+LIB_PATH = os.environ.get("TDGL_B200_LIB") or os.path.join(_HERE, "libtdgl_b200.so")
 
 TDGL_OK, TDGL_E_STEP_FAILED, TDGL_E_MU_SOLVER, TDGL_E_CUDA, TDGL_E_INVALID = range(5)
 

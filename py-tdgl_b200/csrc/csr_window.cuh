@@ -26,6 +26,10 @@
 namespace tdgl {
 
 constexpr int kWinRows = 256;  // default rows per window (= threads per CTA)
+// flags in the top bits of a window descriptor's count (engine.h window_descriptors)
+constexpr int kWinFlagShift = 28;
+constexpr int kWinHalo = 1;    // the window references a halo column
+constexpr int kWinPush = 2;    // the window holds a row that is sent to a peer
 
 struct WinCsr {
   int rows = 0;
@@ -71,6 +75,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 struct WinRow {
   int row;     // global row of this thread (may be >= rows)
   int kb, ke;  // extent of the row inside the staged arrays
+  int flags;   // kWinHalo | kWinPush of the window (uniform over the CTA)
 };
 
 // Issues the window's bulk copies and returns this thread's row extent.  SA / SB are the
@@ -87,7 +92,7 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
   const int2 wd = __ldg(m.win + blockIdx.x);
   const int k0a = wd.x;
   if (threadIdx.x == 0) {
-    const uint32_t n = static_cast<uint32_t>(wd.y);
+    const uint32_t n = static_cast<uint32_t>(wd.y) & ((1u << kWinFlagShift) - 1u);
     mbar_init(bar, 1);
     mbar_arrive_expect_tx(bar, n * (SA + SB + 4));
     if (n > 0) {
@@ -102,6 +107,7 @@ __device__ __forceinline__ WinRow window_stage(const WinCsr& m, const void* valA
   }
   WinRow w;
   w.row = r0 + threadIdx.x / LPR;
+  w.flags = wd.y >> kWinFlagShift;
   w.kb = w.ke = 0;
   if (w.row < m.rows) {
     w.kb = __ldg(m.ptr + w.row) - k0a;
@@ -236,6 +242,68 @@ struct PsiComm {
   PushArgs push[2];
 };
 
+// The accumulated part of one row of kw_real (this lane's share of it when LPR lanes split the
+// row).  HALO: the window references halo columns (sharded engine) — they come out of the
+// mailbox; without it the loop carries no exchange code at all.
+template <int OP, bool HALO, int LPR, typename T>
+__device__ __forceinline__ double real_row_sum(const typename T::V* __restrict__ sv,
+                                               const int* __restrict__ si, const WinRow& w, int sub,
+                                               const RealArgs& a, Ctl* ctl, const HaloView& hv) {
+  using TV = typename T::V;
+  using TX = typename T::X;
+  using TB = typename T::B;
+  const TX* ax = static_cast<const TX*>(a.x);
+  const TB* ab = static_cast<const TB*>(a.b);
+  const TV* adinv = static_cast<const TV*>(a.dinv);
+  const int top = HALO ? hv.n_owned - 1 : 0x7fffffff;
+  double s = 0.0;
+  if (OP == kOpPresmooth) {
+    // x_j = omega dinv_j b_j on the fly
+    const int last = w.ke - 1;
+    for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
+      const int k1 = min(k + LPR, last);
+      const bool two = k + LPR < w.ke;
+      const int j0 = si[k], j1 = si[k1];
+      double b0, b1;
+      if (HALO) {
+        b0 = __ldg(ab + min(j0, top)); b1 = __ldg(ab + min(j1, top));
+        if (max(j0, j1) > top) {
+          if (j0 > top) b0 = halo_val(ctl, hv, ab, j0);
+          if (j1 > top) b1 = halo_val(ctl, hv, ab, j1);
+        }
+      } else {
+        b0 = __ldg(ab + j0); b1 = __ldg(ab + j1);
+      }
+      const double t0 = static_cast<double>(__ldg(adinv + j0)) * b0;
+      const double t1 = static_cast<double>(__ldg(adinv + j1)) * b1;
+      s = fma(static_cast<double>(sv[k]), a.omega * t0, s);
+      s = fma(two ? static_cast<double>(sv[k1]) : 0.0, a.omega * t1, s);
+    }
+  } else if (LPR == 1) {
+    s = row_dot<HALO, TV, TX>(sv, si, w.kb, w.ke, ax, ctl, hv);
+  } else {
+#pragma unroll 2
+    for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
+      const int k1 = k + LPR;
+      const bool two = k1 < w.ke;
+      const int j0 = si[k], j1 = two ? si[k1] : j0;
+      double x0, x1;
+      if (HALO) {
+        x0 = __ldg(ax + min(j0, top)); x1 = __ldg(ax + min(j1, top));
+        if (max(j0, j1) > top) {
+          if (j0 > top) x0 = halo_val(ctl, hv, ax, j0);
+          if (j1 > top) x1 = halo_val(ctl, hv, ax, j1);
+        }
+      } else {
+        x0 = __ldg(ax + j0); x1 = __ldg(ax + j1);
+      }
+      s = fma(static_cast<double>(sv[k]), x0, s);
+      s = fma(two ? static_cast<double>(sv[k1]) : 0.0, x1, s);
+    }
+  }
+  return s;
+}
+
 //  kOpSpmvDot   y = A x ;                         red = dot(x, y)
 //  kOpSpmvCg    y = A x ;                         red = dot(b, x), red2 = dot(x, y)
 //               (the CG iteration's SpMV: x = z, b = r -> gamma = r.z and delta = z.Az)
@@ -276,12 +344,17 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   const bool in = live && w.row < m.rows;
   const int sub = threadIdx.x & (LPR - 1);   // lane of the row (LPR lanes share a long row)
   const bool lead = in && sub == 0;          // the lane that owns the row's epilogue
+  // sharded: only the CTAs whose window references a halo column / holds a row that is sent
+  // (flags of the window descriptor; the rows near the cuts are numbered first) run the
+  // exchange-aware code — every other CTA runs the single-GPU instruction stream
+  const bool hcta = SH && (w.flags & kWinHalo) != 0;
   HaloView hv;
   hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
   unsigned int tag_out = 0u;
   if (SH) {
-    hv = halo_view(ctl, comm, a.halo);
-    if (comm != nullptr && a.push.bnd != nullptr) tag_out = comm_tag(ctl, a.push.tag_mode);
+    if (hcta) hv = halo_view(ctl, comm, a.halo);
+    if ((w.flags & kWinPush) != 0 && comm != nullptr && a.push.bnd != nullptr)
+      tag_out = comm_tag(ctl, a.push.tag_mode);
   }
   // row-local operands travel while the window lands
   double bi = 0.0, di = 0.0, xi = 0.0, wi = 0.0;
@@ -298,41 +371,10 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   double d = 0.0, d2 = 0.0;
   double s = 0.0;
   if (in) {
-    const int top = SH ? hv.n_owned - 1 : 0x7fffffff;
-    if (OP == kOpPresmooth) {
-      // x_j = omega dinv_j b_j on the fly
-      const int last = w.ke - 1;
-      for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
-        const int k1 = min(k + LPR, last);
-        const bool two = k + LPR < w.ke;
-        const int j0 = si[k], j1 = si[k1];
-        double b0 = __ldg(ab + min(j0, top)), b1 = __ldg(ab + min(j1, top));
-        if (SH && max(j0, j1) > top) {
-          if (j0 > top) b0 = halo_val(ctl, hv, ab, j0);
-          if (j1 > top) b1 = halo_val(ctl, hv, ab, j1);
-        }
-        const double t0 = static_cast<double>(__ldg(adinv + j0)) * b0;
-        const double t1 = static_cast<double>(__ldg(adinv + j1)) * b1;
-        s = fma(static_cast<double>(sv[k]), a.omega * t0, s);
-        s = fma(two ? static_cast<double>(sv[k1]) : 0.0, a.omega * t1, s);
-      }
-    } else if (LPR == 1) {
-      s = row_dot<SH, TV, TX>(sv, si, w.kb, w.ke, ax, ctl, hv);
-    } else {
-#pragma unroll 2
-      for (int k = w.kb + sub; k < w.ke; k += 2 * LPR) {
-        const int k1 = k + LPR;
-        const bool two = k1 < w.ke;
-        const int j0 = si[k], j1 = two ? si[k1] : j0;
-        double x0 = __ldg(ax + min(j0, top)), x1 = __ldg(ax + min(j1, top));
-        if (SH && max(j0, j1) > top) {
-          if (j0 > top) x0 = halo_val(ctl, hv, ax, j0);
-          if (j1 > top) x1 = halo_val(ctl, hv, ax, j1);
-        }
-        s = fma(static_cast<double>(sv[k]), x0, s);
-        s = fma(two ? static_cast<double>(sv[k1]) : 0.0, x1, s);
-      }
-    }
+    if (hcta)
+      s = real_row_sum<OP, true, LPR, T>(sv, si, w, sub, a, ctl, hv);
+    else
+      s = real_row_sum<OP, false, LPR, T>(sv, si, w, sub, a, ctl, hv);
   }
   if (LPR > 1) s = group_sum<LPR>(s);
   if (lead) {
@@ -426,13 +468,13 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
   const bool in = live && w.row < m.rows;
   // sharded: halo columns of the current psi come out of its buffer's mailbox, the boundary
   // rows of the new psi go into the other buffer's mailbox on the neighbours
+  const bool hcta = SH && comm != nullptr && (w.flags & kWinHalo) != 0;
+  const bool pcta = SH && comm != nullptr && (w.flags & kWinPush) != 0;
   HaloView hv;
   hv.n_owned = 0x7fffffff; hv.box = nullptr; hv.tag = 0u;
   unsigned int tag_out = 0u;
-  if (SH && comm != nullptr) {
-    hv = halo_view(ctl, comm, pc.halo[cur]);
-    tag_out = comm_tag(ctl, kTagPsiNew);
-  }
+  if (hcta) hv = halo_view(ctl, comm, pc.halo[cur]);
+  if (pcta) tag_out = comm_tag(ctl, kTagPsiNew);
   double2 p = make_double2(0.0, 0.0);
   double mui = 0.0, epsi = 0.0;
   bool fx = false;
@@ -451,11 +493,12 @@ kw_psi_step(Ctl* ctl, const Comm* comm, PsiComm pc, WinCsr m, const double2* __r
   double dmax = 0.0;
   int failed = 0;
   if (in) {
-    double2 lap = row_dot_c<SH>(sv, si, w.kb, w.ke, psi, ctl, hv);
+    double2 lap = hcta ? row_dot_c<true>(sv, si, w.kb, w.ke, psi, ctl, hv)
+                       : row_dot_c<false>(sv, si, w.kb, w.ke, psi, ctl, hv);
     if (fx) lap = p;
     const PsiOut o = psi_update(p, lap, mui, epsi, ctl->gamma, ctl->u, dt, abs2);
     out[w.row] = o.psi;
-    if (SH && comm != nullptr) push_row(comm, pc.push[cur ^ 1], tag_out, w.row, o.psi);
+    if (pcta) push_row(comm, pc.push[cur ^ 1], tag_out, w.row, o.psi);
     if (sq_out != nullptr) sq_out[w.row] = o.sq;
     failed = o.failed;
     const double d = fabs(o.sq - abs2);
@@ -515,7 +558,8 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_h
   hpsi.n_owned = hmu.n_owned = hmp.n_owned = 0x7fffffff;
   hpsi.box = hmu.box = hmp.box = nullptr;
   hpsi.tag = hmu.tag = hmp.tag = 0u;
-  if (SH && comm != nullptr) {
+  const bool hcta = SH && comm != nullptr && (w.flags & kWinHalo) != 0;
+  if (hcta) {
     hpsi = halo_view(ctl, comm, pc.halo[ctl->cur]);
     hmu = halo_view(ctl, comm, mu_halo);
     hmp = halo_view(ctl, comm, mu_prev_halo);   // (the other parity buffer of mu's mailbox)
@@ -538,12 +582,44 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_h
   // several CG iterations cheaper while the dynamics are smooth.
   double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (in) {
-    const double2 lap = row_dot_c<SH>(sl, si, w.kb, w.ke, psi, ctl, hpsi);
-    const double am = row_dot<SH>(sa, si, w.kb, w.ke, mu, ctl, hmu);
-    const double amp = row_dot<SH>(sa, si, w.kb, w.ke, mu_prev, ctl, hmp);
     HaloView plain;
     plain.n_owned = 0x7fffffff; plain.box = nullptr; plain.tag = 0u;
-    const double ampp = row_dot<false>(sa, si, w.kb, w.ke, mu_pp, ctl, plain);
+    double2 lap;
+    double am, amp, ampp;
+    if (hcta) {
+      lap = row_dot_c<true>(sl, si, w.kb, w.ke, psi, ctl, hpsi);
+      am = row_dot<true>(sa, si, w.kb, w.ke, mu, ctl, hmu);
+      amp = row_dot<true>(sa, si, w.kb, w.ke, mu_prev, ctl, hmp);
+      ampp = row_dot<false>(sa, si, w.kb, w.ke, mu_pp, ctl, plain);
+    } else {
+      // one walk over the row for all four products: per entry one complex and three real
+      // gathers at the same column, two entries in flight (added in column order like row_dot)
+      double lx = 0.0, ly = 0.0;
+      am = amp = ampp = 0.0;
+      const int last = w.ke - 1;
+#pragma unroll 1
+      for (int k = w.kb; k < w.ke; k += 2) {
+        const int k1 = min(k + 1, last);
+        const bool two = k + 1 < w.ke;
+        const int j0 = si[k], j1 = si[k1];
+        const double2 p0 = __ldg(psi + j0), p1 = __ldg(psi + j1);
+        const double m0 = __ldg(mu + j0), m1 = __ldg(mu + j1);
+        const double q0 = __ldg(mu_prev + j0), q1 = __ldg(mu_prev + j1);
+        const double r0 = __ldg(mu_pp + j0), r1 = __ldg(mu_pp + j1);
+        const double2 l0 = sl[k];
+        double2 l1 = sl[k1];
+        const double a0 = sa[k], a1 = two ? sa[k1] : 0.0;
+        if (!two) l1 = make_double2(0.0, 0.0);
+        lx += l0.x * p0.x - l0.y * p0.y;
+        ly += l0.x * p0.y + l0.y * p0.x;
+        lx += l1.x * p1.x - l1.y * p1.y;
+        ly += l1.x * p1.y + l1.y * p1.x;
+        am = fma(a0, m0, am); am = fma(a1, m1, am);
+        amp = fma(a0, q0, amp); amp = fma(a1, q1, amp);
+        ampp = fma(a0, r0, ampp); ampp = fma(a1, r1, ampp);
+      }
+      lap = make_double2(lx, ly);
+    }
     const double rhs = (p.x * lap.y - p.y * lap.x) - bt;
     if (rhs_raw != nullptr) rhs_raw[w.row] = rhs;
     const double bi = -ai * rhs;
@@ -576,9 +652,28 @@ kw_mu_rhs(Ctl* ctl, Comm* comm, PsiComm pc, HaloArgs mu_halo, HaloArgs mu_prev_h
   if (s_last) {
     __threadfence();
     double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+    {
+      // four blocks' partials (16 x 16-byte loads) in flight per trip; same order of additions
+      const double2* p2 = reinterpret_cast<const double2*>(partials);
+      const unsigned int n = gridDim.x, bd = blockDim.x;
+      unsigned int i = threadIdx.x;
+      for (; i + 3u * bd < n; i += 4u * bd) {
+        double2 v[4][4];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) a[k] += reinterpret_cast<volatile double*>(partials)[8 * i + k];
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[q][k] = __ldcg(p2 + 4 * (i + q * bd) + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[0] += v[q][0].x; a[1] += v[q][0].y; a[2] += v[q][1].x; a[3] += v[q][1].y;
+          a[4] += v[q][2].x; a[5] += v[q][2].y; a[6] += v[q][3].x;
+        }
+      }
+      for (; i < n; i += bd) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a[k] += __ldcg(partials + 8 * i + k);
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) a[k] = block_sum(a[k], red);
     if (threadIdx.x < 32) {  // block_sum leaves the total in every lane of warp 0

@@ -116,13 +116,29 @@ inline int window_cap(const std::vector<int32_t>& ptr, int64_t rows, int win) {
   return cap;
 }
 
-// {first staged nnz, staged nnz count} of every window of `win` rows.
-inline std::vector<int2> window_descriptors(const std::vector<int32_t>& ptr, int64_t rows, int win) {
+// {first staged nnz, staged nnz count | flags} of every window of `win` rows.  Flags (sharded
+// engine; csr_window.cuh kWinHalo / kWinPush): the window references a halo column
+// (idx >= n_owned_cols), the window holds a row whose value is sent to a peer (push_rptr: the
+// per-row ranges of the row space's send list).  CTAs whose window has neither run the plain
+// single-GPU instruction stream.
+inline std::vector<int2> window_descriptors(const std::vector<int32_t>& ptr, int64_t rows, int win,
+                                            const int32_t* idx = nullptr, int64_t n_owned_cols = 0,
+                                            const std::vector<int>* push_rptr = nullptr) {
   std::vector<int2> d;
   for (int64_t r0 = 0; r0 < rows; r0 += win) {
     const int64_t r1 = std::min<int64_t>(r0 + win, rows);
     const int k0a = ptr[r0] & ~3, k1a = (ptr[r1] + 3) & ~3;
-    d.push_back(make_int2(k0a, k1a - k0a));
+    int flags = 0;
+    if (idx != nullptr)
+      for (int32_t k = ptr[r0]; k < ptr[r1]; ++k)
+        if (idx[k] >= n_owned_cols) { flags |= kWinHalo; break; }
+    if (push_rptr != nullptr && !push_rptr->empty()) {
+      const int64_t n = static_cast<int64_t>(push_rptr->size()) - 1;
+      const int64_t a = std::min(r0, n), b = std::min(r1, n);
+      if ((*push_rptr)[b] > (*push_rptr)[a]) flags |= kWinPush;
+    }
+    if (k1a - k0a >= (1 << kWinFlagShift)) throw std::runtime_error("CSR window too large");
+    d.push_back(make_int2(k0a, (k1a - k0a) | (flags << kWinFlagShift)));
   }
   if (d.empty()) d.push_back(make_int2(0, 0));
   return d;
@@ -148,7 +164,7 @@ struct Config {
   double mu_rtol = 1e-10;
   int mu_max_iter = 500;
   double amg_theta = 0.08;
-  int amg_max_coarse = 200;
+  int amg_max_coarse = 2000;
   int use_graph = 1;
   int reorder = 1;
   int running_capacity = 4096;
@@ -302,6 +318,7 @@ class Engine {
   // ---- mu solver ----------------------------------------------------------------------------
   std::vector<DevLevel> levels_;
   DevBuf<float> coarse_inv_;
+  int nc_ld_ = 0;               // leading dimension of coarse_inv_ (nc_ rounded up to 4)
   int nc_ = 0;
   int64_t amg_nnz_ = 0;
   DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_, cg_s_;   // cg_Ap_: w = A z; cg_s_: A p
@@ -347,6 +364,11 @@ class Engine {
   // bulk copies of its (static) CSR window, and blocks in griddepcontrol.wait until the
   // predecessor's results are visible.  TDGL_B200_PDL=0 turns the attribute off.
   bool pdl_ = true;
+  // fine-level pre-smoothed iterate x0 = omega D^-1 r, written by the kernels that produce r
+  // (null for a single-level hierarchy: the dense solve needs no smoother)
+  const float* x0_dinv() const { return levels_.size() > 1 ? levels_[0].dinv.p : nullptr; }
+  float* x0_out() const { return levels_.size() > 1 ? levels_[0].x.p : nullptr; }
+  double x0_omega() const { return levels_.size() > 1 ? levels_[0].omega : 0.0; }
   // debug timeline (TDGL_B200_TRACE=1): one slot per enqueued (captured) launch of the CG
   // iteration's kernels; trace_report() prints the last pass through every slot
   bool trace_on_ = false;
@@ -379,7 +401,8 @@ class Engine {
     int g = (n + kBlock - 1) / kBlock;
     return g < 1 ? 1 : (g > 1184 ? 1184 : g);  // 148 SMs x 8 resident blocks
   }
-  void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 0);
+  void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 0,
+                  int64_t n_owned_cols = -1, const std::vector<int>* push_rptr = nullptr);
   void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);
   void enqueue_vcycle(double* r_in, double* z_out, double* rz_out);
   void enqueue_psi_step(double* sq_out, double dt_override);

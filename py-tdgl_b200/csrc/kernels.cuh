@@ -170,9 +170,19 @@ __device__ __forceinline__ bool grid_sum_last(double partial, double* partials,
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
+  // (the tail of every reducing kernel: all loads of a trip are issued before the first add —
+  // one L2 round trip per eight partials instead of one per partial; same order of additions)
   double acc = 0.0;
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
-    acc += reinterpret_cast<volatile double*>(partials)[i];
+  const unsigned int n = gridDim.x, bd = blockDim.x;
+  unsigned int i = threadIdx.x;
+  for (; i + 7u * bd < n; i += 8u * bd) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(partials + i + k * bd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  for (; i < n; i += bd) acc += __ldcg(partials + i);
   acc = block_sum(acc, smem);
   if (threadIdx.x == 0) {
     *total = acc;
@@ -197,9 +207,20 @@ __device__ __forceinline__ bool grid_sum2_last(double p0, double p1, double* par
   if (!s_last2) return false;
   __threadfence();
   double a0 = 0.0, a1 = 0.0;
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-    a0 += reinterpret_cast<volatile double*>(partials)[2 * i];
-    a1 += reinterpret_cast<volatile double*>(partials)[2 * i + 1];
+  const double2* p2 = reinterpret_cast<const double2*>(partials);
+  const unsigned int n = gridDim.x, bd = blockDim.x;
+  unsigned int i = threadIdx.x;
+  for (; i + 7u * bd < n; i += 8u * bd) {
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(p2 + i + k * bd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0 += v[k].x; a1 += v[k].y; }
+  }
+  for (; i < n; i += bd) {
+    const double2 v = __ldcg(p2 + i);
+    a0 += v.x;
+    a1 += v.y;
   }
   a0 = block_sum(a0, smem);
   a1 = block_sum(a1, smem);
@@ -220,24 +241,46 @@ __device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int v) {
 // ------------------------------------------------------------------------------------------
 // (the CSR kernels live in csr_window.cuh)
 
-// Coarsest level: x = Minv b with a dense row-major rows x nc matrix (rows = the rows this
-// shard owns, all nc for a single shard); one warp per row.
-template <typename TM, typename TB, typename TX>
+// Coarsest level: x = Minv b with a dense row-major rows x ld float matrix (ld = nc rounded up
+// to a multiple of 4, zero padded).  The level may hold a couple of thousand rows (fewer AMG
+// levels = fewer dependent launches per V-cycle), i.e. ~10 MB per application: two rows per
+// CTA, four warps per row, each warp streaming 512-byte pieces of its quarter of the row with
+// 16-byte loads — rows x 4 warps keep the whole machine loading.  Partial sums are combined in
+// a fixed order (bitwise reproducible).
+template <typename TB, typename TX>
 __global__ void __launch_bounds__(kBlock)
-k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const TM* __restrict__ M,
+k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, int ld, const float* __restrict__ M,
                const TB* __restrict__ b, TX* __restrict__ x, int trace_id) {
   trace_in(ctl, trace_id, 0);
   griddep_enter();
   trace_in(ctl, trace_id, 1);
   if (ctl->status != 0) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp < rows) {
-    const TM* row = M + static_cast<size_t>(warp) * nc;
-    double s = 0.0;
-    for (int j = lane; j < nc; j += 32) s = fma(static_cast<double>(row[j]), static_cast<double>(b[j]), s);
-    s = warp_sum(s);
-    if (lane == 0) x[warp] = static_cast<TX>(s);
+  __shared__ double part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 2 + (warp >> 2);
+  double s = 0.0;
+  if (row < rows) {
+    const float4* __restrict__ m4 = reinterpret_cast<const float4*>(M + static_cast<size_t>(row) * ld);
+#pragma unroll 4
+    for (int j = (warp & 3) * 128 + lane * 4; j < nc; j += 512) {
+      const float4 m = __ldg(m4 + (j >> 2));
+      const double b0 = static_cast<double>(b[j]);
+      const double b1 = j + 1 < nc ? static_cast<double>(b[j + 1]) : 0.0;
+      const double b2 = j + 2 < nc ? static_cast<double>(b[j + 2]) : 0.0;
+      const double b3 = j + 3 < nc ? static_cast<double>(b[j + 3]) : 0.0;
+      s = fma(static_cast<double>(m.x), b0, s);
+      s = fma(static_cast<double>(m.y), b1, s);
+      s = fma(static_cast<double>(m.z), b2, s);
+      s = fma(static_cast<double>(m.w), b3, s);
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) part[warp] = s;
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int r = blockIdx.x * 2 + threadIdx.x;
+    const double* q = part + 4 * threadIdx.x;
+    if (r < rows) x[r] = static_cast<TX>(((q[0] + q[1]) + q[2]) + q[3]);
   }
   trace_out(ctl, trace_id);
 }
@@ -255,8 +298,9 @@ k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, const TM* __restri
 __global__ void __launch_bounds__(kBlock)
 k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict__ z,
            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
-           double* __restrict__ x, double* __restrict__ r, double* partials,
-           unsigned int* counter, cudaGraphConditionalHandle cond, int trace_id) {
+           double* __restrict__ x, double* __restrict__ r, const float* __restrict__ dinv,
+           float* __restrict__ x0, double omega, double* partials, unsigned int* counter,
+           cudaGraphConditionalHandle cond, int trace_id) {
   trace_in(ctl, trace_id, 0);
   griddep_enter();
   trace_in(ctl, trace_id, 1);
@@ -294,7 +338,14 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict_
     x[i] = xi + alpha * pi;
     const double ri = ri0 - alpha * si;
     r[i] = ri;
-    if (comm != nullptr) push_row(comm, push, tag, i, ri);  // next iteration's V-cycle input
+    // the next V-cycle's pre-smoothed iterate from a zero guess, x0 = omega D^-1 r, is formed
+    // here (one float per row), so that its residual kernel gathers ONE float per matrix entry
+    // instead of r and 1/diag; sharded: x0's boundary rows travel, not r's
+    if (x0 != nullptr) {
+      const float ti = static_cast<float>(omega * static_cast<double>(dinv[i]) * ri);
+      x0[i] = ti;
+      if (comm != nullptr) push_row(comm, push, tag, i, static_cast<double>(ti));
+    }
     d += ri * ri;
     if (two) {
       const double pj = first ? zj : zj + beta * pj0;
@@ -304,7 +355,11 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict_
       x[j] = xj + alpha * pj;
       const double rj = rj0 - alpha * sj;
       r[j] = rj;
-      if (comm != nullptr) push_row(comm, push, tag, j, rj);
+      if (x0 != nullptr) {
+        const float tj = static_cast<float>(omega * static_cast<double>(dinv[j]) * rj);
+        x0[j] = tj;
+        if (comm != nullptr) push_row(comm, push, tag, j, static_cast<double>(tj));
+      }
       d += rj * rj;
     }
   }
@@ -379,15 +434,23 @@ __global__ void k_cg_begin(Ctl* ctl, cudaGraphConditionalHandle cond, int with_g
   set_cond(cond, go);
 }
 
+// x0 = omega D^-1 r for a residual that no stepping kernel produced (single-operator calls)
+__global__ void k_x0_from_r(int n, const double* __restrict__ r, const float* __restrict__ dinv,
+                            double omega, float* __restrict__ x0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x0[i] = static_cast<float>(omega * static_cast<double>(dinv[i]) * r[i]);
+}
+
 // Applies the extrapolated initial guess chosen by k_cg_begin:
 //   mu <- mu + c1 (mu - mu_prev) + c2 (mu - mu_pp),  r <- r + c1 d1 + c2 d2,
 // and shifts the history (mu_pp <- mu_prev, mu_prev <- old mu).  Sharded: the boundary rows of
-// r go to the neighbours (iteration 0's V-cycle input), and the halo slots of mu_pp are filled
+// x0 = omega D^-1 r go to the neighbours (iteration 0's V-cycle input), and the halo slots of mu_pp are filled
 // from mu_prev's mailbox copy (threads n .. nx-1) before this step's solution overwrites it.
 __global__ void __launch_bounds__(kBlock)
 k_mu_guess(Ctl* ctl, const Comm* comm, PushArgs push, HaloArgs prev_halo, int n, int nx,
            double* __restrict__ mu, double* __restrict__ mu_prev, double* __restrict__ mu_pp,
-           double* __restrict__ r, const double* __restrict__ d1, const double* __restrict__ d2) {
+           double* __restrict__ r, const double* __restrict__ d1, const double* __restrict__ d2,
+           const float* __restrict__ dinv, float* __restrict__ x0, double omega) {
   griddep_enter();
   if (ctl->status != 0) return;
   const double c1 = ctl->guess_c, c2 = ctl->guess_c2;
@@ -399,7 +462,11 @@ k_mu_guess(Ctl* ctl, const Comm* comm, PushArgs push, HaloArgs prev_halo, int n,
     mu_prev[i] = old;
     const double ri = r[i] + c1 * d1[i] + c2 * d2[i];
     r[i] = ri;
-    if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, ri);
+    if (x0 != nullptr) {   // iteration 0's pre-smoothed iterate (see k_cg_fused)
+      const float ti = static_cast<float>(omega * static_cast<double>(dinv[i]) * ri);
+      x0[i] = ti;
+      if (comm != nullptr) push_row(comm, push, comm_tag(ctl, push.tag_mode), i, static_cast<double>(ti));
+    }
   } else if (comm != nullptr && i < nx) {
     const HaloView hv = halo_view(ctl, comm, prev_halo);
     mu_pp[i] = halo_get(ctl, hv, mu_prev, i);

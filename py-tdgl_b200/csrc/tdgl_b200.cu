@@ -90,7 +90,8 @@ static std::vector<int> shard_permutation(const double* xy, int64_t n, int64_t n
   return out;
 }
 
-void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row) {
+void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row, int64_t n_owned_cols,
+                        const std::vector<int>* push_rptr) {
   d.rows = static_cast<int>(h.rows);
   d.cols = static_cast<int>(h.cols);
   d.nnz = h.nnz();
@@ -107,7 +108,9 @@ void Engine::upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row) 
   d.ptr.upload(h.ptr, stream_);
   d.idx.upload(idx, stream_);
   d.val.upload(val, stream_);
-  const std::vector<int2> wd = window_descriptors(h.ptr, h.rows, d.win);
+  const std::vector<int2> wd = window_descriptors(h.ptr, h.rows, d.win,
+                                                  n_owned_cols >= 0 ? h.idx.data() : nullptr,
+                                                  n_owned_cols, push_rptr);
   d.wdesc.upload(wd, stream_);
   TDGL_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -241,6 +244,9 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   }
   const std::vector<int64_t> off0 = equal_offsets(Ng_, world_);
   if (const char* e = std::getenv("TDGL_B200_MAX_COARSE")) cfg_.amg_max_coarse = std::max(8, std::atoi(e));
+  // (a sharded engine needs at least two levels: the partition lives on level 0, the dense
+  // coarsest solve is replicated)
+  if (world_ > 1) cfg_.amg_max_coarse = std::min(cfg_.amg_max_coarse, std::max(8, Ng_ / 8));
   AmgHierarchy H = build_amg(std::move(A0), cfg_.amg_theta, cfg_.amg_max_coarse, 24, &off0);
   if (H.nc > 4096) throw std::runtime_error("AMG coarsening stalled (coarsest level too large)");
   {
@@ -298,10 +304,37 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   cg_p_.view(arena_.p + lay.off[kVecCgP], Nx_);
   comm_.alloc(1);
 
+  // ---- per level: which owned rows are sent to which peers (comm.cuh push_row) ----------------
+  // (also decides which CSR windows carry the kWinPush flag)
+  const int rep_level = plan_.rep;
+  std::vector<std::vector<int>> push_rptr_h(L);
+  std::vector<std::vector<int2>> push_ent_h(L);
+  if (world_ > 1)
+    for (int li = 0; li < static_cast<int>(L) && li <= rep_level; ++li) {
+      const int n_own = static_cast<int>(plan_.off[li][rank_ + 1] - plan_.off[li][rank_]);
+      std::vector<int>& rptr = push_rptr_h[li];
+      rptr.assign(n_own + 1, 0);
+      const std::vector<SendBlock> blocks = send_blocks(plan_, li, rank_);
+      for (const SendBlock& b : blocks)
+        for (int32_t row : b.idx) rptr[row + 1]++;
+      for (int i = 0; i < n_own; ++i) rptr[i + 1] += rptr[i];
+      std::vector<int2>& ent = push_ent_h[li];
+      ent.resize(std::max(rptr[n_own], 1));
+      std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+      for (const SendBlock& b : blocks)
+        for (size_t k = 0; k < b.idx.size(); ++k)
+          ent[fill[b.idx[k]]++] = make_int2(b.peer, static_cast<int>(b.dst_pos + k));
+    }
+  auto own_of = [&](int li) { return plan_.off[li][rank_ + 1] - plan_.off[li][rank_]; };
+  auto push_of = [&](int li) -> const std::vector<int>* {
+    return (world_ > 1 && li <= rep_level) ? &push_rptr_h[li] : nullptr;
+  };
+
   // ---- uploads --------------------------------------------------------------------------
   ptr_.upload(lptr, stream_);
   {
-    const std::vector<int2> wd = window_descriptors(lptr, N_, win0_);
+    const std::vector<int2> wd = window_descriptors(lptr, N_, win0_, world_ > 1 ? lnbr.data() : nullptr,
+                                                    N_, push_of(0));
     wdesc0_.upload(wd, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
@@ -408,7 +441,6 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   levels_.resize(L);
   amg_nnz_ = 0;
   int max_grid_rows = grid_win(N_, win0_);
-  const int rep_level = plan_.rep;
   for (size_t l = 0; l < L; ++l) {
     AmgLevel& hl = H.levels[l];
     DevLevel& dl = levels_[l];
@@ -417,8 +449,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     dl.n = static_cast<int>(rows.size());
     dl.nx = static_cast<int>(plan_.local_size(li, rank_));
     for (int64_t gr : rows) amg_nnz_ += hl.A.ptr[gr + 1] - hl.A.ptr[gr];
+    // (window flags: halo columns exist where enqueue_vcycle wires a halo — partitioned levels)
+    const bool part = world_ > 1 && li < rep_level;
     if (l > 0) {
-      upload_csr(extract_rows(hl.A, rows, plan_, li, rank_), dl.A, 0);
+      upload_csr(extract_rows(hl.A, rows, plan_, li, rank_), dl.A, 0, part ? own_of(li) : -1,
+                 part ? push_of(li) : nullptr);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.A.rows, dl.A.win));
     }
     {
@@ -437,8 +472,11 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
       } else {
         rrows = compute_row_list(plan_, li + 1, rank_);
       }
-      upload_csr(extract_rows(hl.P, rows, plan_, li + 1, rank_), dl.P, 0);
-      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R, 0);
+      const bool part1 = world_ > 1 && li + 1 < rep_level;
+      upload_csr(extract_rows(hl.P, rows, plan_, li + 1, rank_), dl.P, 0, part1 ? own_of(li + 1) : -1,
+                 part ? push_of(li) : nullptr);
+      upload_csr(extract_rows(hl.R, rrows, plan_, li, rank_), dl.R, 0, part ? own_of(li) : -1,
+                 (world_ > 1 && li + 1 <= rep_level) ? push_of(li + 1) : nullptr);
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.P.rows, dl.P.win));
       max_grid_rows = std::max(max_grid_rows, grid_win(dl.R.rows, dl.R.win));
     }
@@ -448,22 +486,13 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     dl.y.view(arena_.p + lay.off[vec_id(li, 3)], dl.nx);
     if (world_ > 1 && li <= rep_level) {
       // per owned row: the (peer, halo entry) pairs its value is stored to (comm.cuh push_row)
-      const int n_own = static_cast<int>(plan_.off[l][rank_ + 1] - plan_.off[l][rank_]);
-      std::vector<int> rptr(n_own + 1, 0);
-      const std::vector<SendBlock> blocks = send_blocks(plan_, li, rank_);
-      for (const SendBlock& b : blocks)
-        for (int32_t row : b.idx) rptr[row + 1]++;
-      for (int i = 0; i < n_own; ++i) rptr[i + 1] += rptr[i];
-      std::vector<int2> ent(std::max(rptr[n_own], 1));
-      std::vector<int> fill(rptr.begin(), rptr.end() - 1);
-      for (const SendBlock& b : blocks)
-        for (size_t k = 0; k < b.idx.size(); ++k)
-          ent[fill[b.idx[k]]++] = make_int2(b.peer, static_cast<int>(b.dst_pos + k));
+      const std::vector<int>& rptr = push_rptr_h[li];
+      const int n_own = static_cast<int>(rptr.size()) - 1;
       std::vector<unsigned char> bnd((n_own + 31) / 32 + 1, 0);
       for (int i = 0; i < n_own; ++i)
         if (rptr[i + 1] > rptr[i]) bnd[i >> 5] = 1;
       dl.push_rptr.upload(rptr, stream_);
-      dl.push_ent.upload(ent, stream_);
+      dl.push_ent.upload(push_ent_h[li], stream_);
       dl.push_bnd.upload(bnd, stream_);
       TDGL_CUDA(cudaStreamSynchronize(stream_));
     }
@@ -472,12 +501,14 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     // coarsest level: dense inverse with rows and columns in this shard's local order
     const int lc = static_cast<int>(L) - 1;
     nc_ = static_cast<int>(H.nc);
-    std::vector<float> loc(static_cast<size_t>(nc_) * nc_, 0.0f);
+    nc_ld_ = (nc_ + 3) & ~3;   // rows start 16-byte aligned (k_dense_matvec loads float4)
+    std::vector<int64_t> gidx(nc_);
+    for (int j = 0; j < nc_; ++j) gidx[j] = plan_.global_index(lc, rank_, j);
+    std::vector<float> loc(static_cast<size_t>(nc_) * nc_ld_, 0.0f);
     for (int i = 0; i < nc_; ++i) {
-      const int64_t gi = plan_.global_index(lc, rank_, i);
-      for (int j = 0; j < nc_; ++j)
-        loc[static_cast<size_t>(i) * nc_ + j] =
-            static_cast<float>(H.coarse_inv[gi * nc_ + plan_.global_index(lc, rank_, j)]);
+      const double* src = &H.coarse_inv[gidx[i] * nc_];
+      float* dst = &loc[static_cast<size_t>(i) * nc_ld_];
+      for (int j = 0; j < nc_; ++j) dst[j] = static_cast<float>(src[gidx[j]]);
     }
     coarse_inv_.upload(loc, stream_);
     TDGL_CUDA(cudaStreamSynchronize(stream_));
@@ -680,7 +711,7 @@ void Engine::configure_kernels() {
   TDGL_ALLOW_REAL(kOpSpmvDot, kTypesD)
   TDGL_ALLOW_REAL(kOpSpmvCg, kTypesD)
   TDGL_ALLOW_REAL(kOpPresmooth, kTypesF)
-  TDGL_ALLOW_REAL(kOpPresmooth, kTypesP0)
+  TDGL_ALLOW_REAL(kOpResidual, kTypesP0)
   TDGL_ALLOW_REAL(kOpJacobi, kTypesF)
   TDGL_ALLOW_REAL(kOpJacobi, kTypesJ0)
   TDGL_ALLOW_REAL(kOpPlain, kTypesF)
@@ -704,8 +735,8 @@ void Engine::configure_kernels() {
   preload(reinterpret_cast<const void*>(&k_step_end));
   preload(reinterpret_cast<const void*>(&k_dot));
   preload(reinterpret_cast<const void*>(&k_link_values_ramp));
-  preload(reinterpret_cast<const void*>(&k_dense_matvec<float, float, float>));
-  preload(reinterpret_cast<const void*>(&k_dense_matvec<float, double, double>));
+  preload(reinterpret_cast<const void*>(&k_dense_matvec<float, float>));
+  preload(reinterpret_cast<const void*>(&k_dense_matvec<double, double>));
   preload(reinterpret_cast<const void*>(&k_unpack<float>));
   preload(reinterpret_cast<const void*>(&k_unpack<double>));
   preload(reinterpret_cast<const void*>(&k_unpack<double2>));
@@ -747,12 +778,12 @@ void Engine::trace_report() {
   for (size_t i = 1; i < trace_names_.size(); ++i)
     if (h[4 * i + 3] > 0) { order.push_back(static_cast<int>(i)); t0 = std::min(t0, h[4 * i]); }
   std::sort(order.begin(), order.end(), [&](int a, int b) { return h[4 * a] < h[4 * b]; });
-  fprintf(stderr, "[tdgl_b200 trace] %-34s %9s %9s %9s %8s %8s %8s\n", "launch", "in us", "go us", "out us",
-          "go-in", "out-go", "count");
+  fprintf(stderr, "[tdgl_b200 trace r%d] %-34s %9s %9s %9s %8s %8s %8s\n", rank_, "launch", "in us", "go us",
+          "out us", "go-in", "out-go", "count");
   for (int i : order) {
     const double in = (h[4 * i] - t0) * 1e-3, go = (h[4 * i + 1] - t0) * 1e-3, out = (h[4 * i + 2] - t0) * 1e-3;
-    fprintf(stderr, "[tdgl_b200 trace] %-34s %9.2f %9.2f %9.2f %8.2f %8.2f %8llu\n", trace_names_[i].c_str(),
-            in, go, out, go - in, out - go, h[4 * i + 3]);
+    fprintf(stderr, "[tdgl_b200 trace r%d] %-34s %9.2f %9.2f %9.2f %8.2f %8.2f %8llu\n", rank_,
+            trace_names_[i].c_str(), in, go, out, go - in, out - go, h[4 * i + 3]);
   }
   TDGL_CUDA(cudaMemset(trace_.p, 0, sizeof(unsigned long long) * trace_.n));
 }
@@ -815,9 +846,8 @@ void Engine::enqueue_unpack(int level, int channel, int tag_mode, float* vec) {
 void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   const size_t L = levels_.size();
   if (L == 1) {
-    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    launch_k(k_dense_matvec<float, double, double>, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p,
-             r_in, z_out, trace_slot("dense", nc_));
+    launch_k(k_dense_matvec<double, double>, (nc_ + 1) / 2, kBlock, 0, ctl_.p, nc_, nc_, nc_ld_,
+             coarse_inv_.p, r_in, z_out, trace_slot("dense", nc_));
     TDGL_LAUNCH_CHECK();
     if (rz_out != nullptr) {
       launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
@@ -846,8 +876,14 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
         a.halo = make_halo(li, li == 0 ? kVecCgR : chan(li, 2), kTagIter);
         a.push = make_push(li, chan(li, 1), kTagIter);
       }
-      if (li == 0) launch_real<kOpPresmooth, kTypesP0>(levelA(li), a);
-      else launch_real<kOpPresmooth, kTypesF>(levelA(li), a);
+      if (li == 0) {
+        // fine level: x0 = omega D^-1 r was written by the kernel that produced r (k_cg_fused,
+        // k_mu_guess); what is left of the pre-smoother is the residual r1 = r - A x0
+        a.x = lv.x.p; a.y = lv.r.p; a.r = nullptr; a.dinv = nullptr;
+        launch_real<kOpResidual, kTypesP0>(levelA(li), a);
+      } else {
+        launch_real<kOpPresmooth, kTypesF>(levelA(li), a);
+      }
     }
     {
       RealArgs a;
@@ -860,9 +896,8 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
   }
   {
     DevLevel& c = levels_[split];
-    const int grid = (nc_ * 32 + kBlock - 1) / kBlock;
-    launch_k(k_dense_matvec<float, float, float>, grid, kBlock, 0, ctl_.p, nc_, nc_, coarse_inv_.p,
-             c.b.p, c.y.p, trace_slot("dense", nc_));
+    launch_k(k_dense_matvec<float, float>, (nc_ + 1) / 2, kBlock, 0, ctl_.p, nc_, nc_, nc_ld_,
+             coarse_inv_.p, c.b.p, c.y.p, trace_slot("dense", nc_));
     TDGL_LAUNCH_CHECK();
   }
   for (int li = split - 1; li >= 0; --li) {
@@ -936,7 +971,7 @@ void Engine::enqueue_solve_begin(cudaGraphConditionalHandle cond) {
   launch_k(k_mu_guess, (nth + kBlock - 1) / kBlock, kBlock, 0, ctl_.p, comm(),
            comm_on_ ? make_push(0, kVecCgR, kTagIter0) : PushArgs(),
            comm_on_ ? make_halo(0, kVecMu, kTagMuPrev2) : HaloArgs(), N_, Nx_, mu_.p, mu_prev_.p,
-           mu_pp_.p, cg_r_.p, cg_Ap_.p, cg_z_.p);
+           mu_pp_.p, cg_r_.p, cg_Ap_.p, cg_z_.p, x0_dinv(), x0_out(), x0_omega());
   TDGL_LAUNCH_CHECK();
 }
 
@@ -953,7 +988,8 @@ void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   }
   launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
            comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_z_.p, cg_Ap_.p,
-           cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, partials_.p, counter_.p, cond, trace_slot("cg_fused", N_));
+           cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, x0_dinv(), x0_out(), x0_omega(), partials_.p, counter_.p,
+           cond, trace_slot("cg_fused", N_));
   TDGL_LAUNCH_CHECK();
 }
 
@@ -976,6 +1012,10 @@ void Engine::host_solve_loop(bool with_guess) {
   } else {
     launch_k(k_cg_begin, 1, 32, 0, ctl_.p, 0, 0);
     TDGL_LAUNCH_CHECK();
+    if (x0_out() != nullptr) {   // (r came from a copy, not from k_mu_guess)
+      k_x0_from_r<<<(N_ + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(N_, cg_r_.p, x0_dinv(), x0_omega(), x0_out());
+      TDGL_LAUNCH_CHECK();
+    }
   }
   sync_ctl_to_host();
   while (h_ctl_->cg_go) {
@@ -2117,8 +2157,8 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
       }
       case 9:
         launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_z_.p,
-                 cg_Ap_.p, cg_p_.p, cg_s_.p, tmp_d2_.p, cg_b_.p, partials_.p, counter_.p,
-                 static_cast<cudaGraphConditionalHandle>(0), 0);
+                 cg_Ap_.p, cg_p_.p, cg_s_.p, tmp_d2_.p, cg_b_.p, x0_dinv(), x0_out(), x0_omega(),
+                 partials_.p, counter_.p, static_cast<cudaGraphConditionalHandle>(0), 0);
         TDGL_LAUNCH_CHECK();
         break;
       case 3: enqueue_vcycle(cg_r_.p, cg_z_.p, nullptr); break;
@@ -2132,9 +2172,8 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
       case 5: {
         if (!multi) throw std::invalid_argument("single-level hierarchy");
         RealArgs a;
-        a.val = A0f().val; a.dinv = levels_[0].dinv.p; a.omega = levels_[0].omega; a.b = cg_r_.p;
-        a.y = levels_[0].x.p; a.r = levels_[0].r.p;
-        launch_real<kOpPresmooth, kTypesP0>(A0f(), a);
+        a.val = A0f().val; a.b = cg_r_.p; a.x = levels_[0].x.p; a.y = levels_[0].r.p;
+        launch_real<kOpResidual, kTypesP0>(A0f(), a);
         break;
       }
       case 6: {
