@@ -576,19 +576,20 @@ def run_b200(args, rank, world, local_rank):
         "kw_psi_step": (0, 20 * nnz + 52 * nl, 1.0),
         # (complex + real matrix, psi, areas, bterm, mu / mu_prev / mu_pp, b, r, d1, d2)
         "kw_mu_rhs": (1, 28 * nnz + 92 * nl, 1.0),
-        # w = A z with r.z and z.w: matrix, row pointers, z, r read, w written
-        "kw_real<spmv_cg> fine level": (2, 12 * nnz + 28 * nl, iters_per_step),
-        # p, s, x, r updated from z, w (6 reads + 4 writes of 8 B per row) + 1/diag read and
-        # x0 = omega D^-1 r written (4 B each)
-        "k_cg_fused": (9, 88 * nl, iters_per_step),
+        # w = A z with r.z and z.w: matrix (8 + 4 B per entry), row pointers 4, z (f32) 4, r 8
+        # read, w 8 written per row
+        "kw_real<spmv_cg> fine level": (2, 12 * nnz + 24 * nl, iters_per_step),
+        # p, s, x, r updated from z (f32), w: 4 + 5 x 8 B read, 4 x 8 B written per row, + 1/diag
+        # read and x0 = omega D^-1 r written (4 B each)
+        "k_cg_fused": (9, 84 * nl, iters_per_step),
     }
     if levels > 1:
         # the V-cycle's operators are stored in fp32: 4 B value + 4 B column per entry;
         # pre-smoother = residual of x0 (written by k_cg_fused): row pointers 4, r (f64) 8, x0 4
         # read, r1 (f32) 4 written per row;
-        # post-smoother: row pointers 4, r 8, 1/diag 4, x 4 read, z (f64) 8 written per row
+        # post-smoother: row pointers 4, r 8, 1/diag 4, x 4 read, z (f32) 4 written per row
         kern["kw_real<residual> fine level (pre-smoother)"] = (5, 8 * nnz + 20 * nl, iters_per_step)
-        kern["kw_real<jacobi> fine level"] = (6, 8 * nnz + 28 * nl, iters_per_step)
+        kern["kw_real<jacobi> fine level"] = (6, 8 * nnz + 24 * nl, iters_per_step)
     table = {}
     for name, (which, nbytes, per_step) in kern.items():
         kms = eng.time_kernel(which, 20, flush_l2=True)

@@ -221,8 +221,8 @@ struct RealArgs {
 // vectors are stored in float — two thirds of the matrix bytes (4 + 4 instead of 8 + 4 per
 // entry) and half of the vector bytes of the kernels that dominate the step — while every row
 // is still accumulated in double.  The two places where the cycle touches CG's double vectors
-// have their own type sets: the fine-level pre-smoother reads the residual r (kTypesP0), the
-// fine-level post-smoother reads r and writes z (kTypesJ0).
+// read CG's double residual r have their own type set (kTypesP0: the fine-level smoothers; the
+// post-smoother's output z is float too), and CG's SpMV gathers that float z (kTypesZ).
 template <typename TV_, typename TX_, typename TB_, typename TY_, typename TR_>
 struct RealTypes {
   using V = TV_;   // matrix values, 1 / diag
@@ -234,7 +234,7 @@ struct RealTypes {
 using kTypesD = RealTypes<double, double, double, double, double>;
 using kTypesF = RealTypes<float, float, float, float, float>;
 using kTypesP0 = RealTypes<float, float, double, float, float>;
-using kTypesJ0 = RealTypes<float, float, double, double, float>;
+using kTypesZ = RealTypes<double, float, double, double, double>;   // CG's SpMV: w = A z, z float
 
 // psi is double-buffered, and so are its mailboxes: [b] belongs to buffer b
 struct PsiComm {

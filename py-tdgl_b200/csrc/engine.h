@@ -322,6 +322,10 @@ class Engine {
   int nc_ = 0;
   int64_t amg_nnz_ = 0;
   DevBuf<double> cg_b_, cg_r_, cg_p_, cg_Ap_, cg_z_, cg_s_;   // cg_Ap_: w = A z; cg_s_: A p
+  // z = M r, the V-cycle's output, is stored in float like everything else the cycle computes
+  // (its entries carry float accuracy anyway); CG forms gamma, delta, p from exactly these
+  // values in double.  (cg_z_ survives as the rhs kernel's scratch for the guess's d2.)
+  DevBuf<float> cg_zf_;
   DevBuf<double> mu_prev_, mu_pp_;   // the two solutions before the last one (extrapolated
                                      // initial guess of the next solve)
   int guess_terms_ = 2;              // 0: warm start, 1: one-term, 2: two-term extrapolation
@@ -404,7 +408,7 @@ class Engine {
   void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 0,
                   int64_t n_owned_cols = -1, const std::vector<int>* push_rptr = nullptr);
   void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);
-  void enqueue_vcycle(double* r_in, double* z_out, double* rz_out);
+  void enqueue_vcycle(double* r_in, float* z_out);
   void enqueue_psi_step(double* sq_out, double dt_override);
   void enqueue_mu_rhs(double* rhs_raw);
   void enqueue_cg_iteration(cudaGraphConditionalHandle cond);

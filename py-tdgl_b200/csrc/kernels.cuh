@@ -296,7 +296,7 @@ k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, int ld, const floa
 // r.z / p.Ap) in exact arithmetic, with one launch and one grid reduction less per iteration.
 // Last block: bookkeeping + loop condition of the CG loop.
 __global__ void __launch_bounds__(kBlock)
-k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const double* __restrict__ z,
+k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const float* __restrict__ z,
            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
            double* __restrict__ x, double* __restrict__ r, const float* __restrict__ dinv,
            float* __restrict__ x0, double omega, double* partials, unsigned int* counter,
@@ -1146,6 +1146,32 @@ __global__ void k_comm_barrier(Ctl* ctl, Comm* comm) {
   if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   double v = 0.0;
   comm_allreduce(ctl, comm, &v, 1, false);
+}
+
+// Does the state the caller hands in equal the state the engine already holds (bit for bit)?
+// The reference's Runner feeds every step's output back as the next step's input
+// (runner.py:417-423): then nothing has to be replaced, and the history of the mu solve's
+// initial guess and the mailboxes stay valid.  *differ is set when any word differs.
+__global__ void __launch_bounds__(kBlock)
+k_state_differs(int n, const double2* __restrict__ psi_in, const double2* psi_buf0,
+                const double2* psi_buf1, const Ctl* __restrict__ ctl, const double* __restrict__ mu_in,
+                const double* __restrict__ mu, int* differ) {
+  const double2* __restrict__ psi = ctl->cur ? psi_buf1 : psi_buf0;
+  bool d = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double2 a = psi_in[i], b = psi[i];
+    d |= __double_as_longlong(a.x) != __double_as_longlong(b.x) ||
+         __double_as_longlong(a.y) != __double_as_longlong(b.y) ||
+         __double_as_longlong(mu_in[i]) != __double_as_longlong(mu[i]);
+  }
+  if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) atomicOr(differ, 1);
+}
+// ... on ANY rank (all ranks must take the same path): max over the ranks, left in *differ.
+__global__ void k_state_vote(Ctl* ctl, Comm* comm, int* differ) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  double v = static_cast<double>(*differ);
+  if (comm != nullptr) comm_allreduce(ctl, comm, &v, 1, true);
+  if (threadIdx.x == 0) *differ = v != 0.0 ? 1 : 0;
 }
 
 // The boundary rows of a state vector this rank has just been handed go to the neighbours'

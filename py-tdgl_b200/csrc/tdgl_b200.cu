@@ -514,7 +514,7 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
     TDGL_CUDA(cudaStreamSynchronize(stream_));
   }
 
-  cg_b_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_); cg_s_.alloc(N_);
+  cg_b_.alloc(N_); cg_Ap_.alloc(N_); cg_z_.alloc(N_); cg_s_.alloc(N_); cg_zf_.alloc(N_);
   if (world_ > 1 && L < 2) throw std::invalid_argument("mesh too small to shard (single-level hierarchy)");
   mu_prev_.alloc(Nx_);
   mu_prev_.zero(stream_);
@@ -709,11 +709,11 @@ void Engine::configure_kernels() {
   allow(reinterpret_cast<const void*>(&kw_real<OP, false, 4, T>));     \
   allow(reinterpret_cast<const void*>(&kw_real<OP, true, 4, T>));
   TDGL_ALLOW_REAL(kOpSpmvDot, kTypesD)
-  TDGL_ALLOW_REAL(kOpSpmvCg, kTypesD)
+  TDGL_ALLOW_REAL(kOpSpmvCg, kTypesZ)
   TDGL_ALLOW_REAL(kOpPresmooth, kTypesF)
   TDGL_ALLOW_REAL(kOpResidual, kTypesP0)
   TDGL_ALLOW_REAL(kOpJacobi, kTypesF)
-  TDGL_ALLOW_REAL(kOpJacobi, kTypesJ0)
+  TDGL_ALLOW_REAL(kOpJacobi, kTypesP0)
   TDGL_ALLOW_REAL(kOpPlain, kTypesF)
   TDGL_ALLOW_REAL(kOpPlainAdd, kTypesF)
 #undef TDGL_ALLOW_REAL
@@ -736,7 +736,7 @@ void Engine::configure_kernels() {
   preload(reinterpret_cast<const void*>(&k_dot));
   preload(reinterpret_cast<const void*>(&k_link_values_ramp));
   preload(reinterpret_cast<const void*>(&k_dense_matvec<float, float>));
-  preload(reinterpret_cast<const void*>(&k_dense_matvec<double, double>));
+  preload(reinterpret_cast<const void*>(&k_dense_matvec<double, float>));
   preload(reinterpret_cast<const void*>(&k_unpack<float>));
   preload(reinterpret_cast<const void*>(&k_unpack<double>));
   preload(reinterpret_cast<const void*>(&k_unpack<double2>));
@@ -843,16 +843,12 @@ void Engine::enqueue_unpack(int level, int channel, int tag_mode, float* vec) {
   TDGL_LAUNCH_CHECK();
 }
 
-void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
+void Engine::enqueue_vcycle(double* r_in, float* z_out) {
   const size_t L = levels_.size();
   if (L == 1) {
-    launch_k(k_dense_matvec<double, double>, (nc_ + 1) / 2, kBlock, 0, ctl_.p, nc_, nc_, nc_ld_,
+    launch_k(k_dense_matvec<double, float>, (nc_ + 1) / 2, kBlock, 0, ctl_.p, nc_, nc_, nc_ld_,
              coarse_inv_.p, r_in, z_out, trace_slot("dense", nc_));
     TDGL_LAUNCH_CHECK();
-    if (rz_out != nullptr) {
-      launch_k(k_dot, grid_flat(N_), kBlock, 0, ctl_.p, comm(), N_, r_in, z_out, partials_.p, counter_.p, rz_out);
-      TDGL_LAUNCH_CHECK();
-    }
     return;
   }
   // The cycle's operators and vectors are float (engine.h, csr_window.cuh RealTypes); only its
@@ -914,14 +910,12 @@ void Engine::enqueue_vcycle(double* r_in, double* z_out, double* rz_out) {
       a.val = levelA(li).val; a.dinv = lv.dinv.p; a.omega = lv.omega; a.x = lv.x.p;
       a.b = (li == 0) ? static_cast<const void*>(r_in) : static_cast<const void*>(lv.b.p);
       a.y = (li == 0) ? static_cast<void*>(z_out) : static_cast<void*>(lv.y.p);
-      a.w = (li == 0 && rz_out != nullptr) ? r_in : nullptr;
-      a.red_out = (li == 0) ? rz_out : nullptr;
       if (li < rep) {
         a.halo = make_halo(li, chan(li, 0), kTagIter);
         // level 0: z, whose halo the CG iteration's SpMV reads, travels on p's old channel
         a.push = li > 0 ? make_push(li, chan(li, 3), kTagIter) : make_push(0, kVecCgP, kTagIter);
       }
-      if (li == 0) launch_real<kOpJacobi, kTypesJ0>(levelA(li), a);
+      if (li == 0) launch_real<kOpJacobi, kTypesP0>(levelA(li), a);
       else launch_real<kOpJacobi, kTypesF>(levelA(li), a);
     }
   }
@@ -978,16 +972,16 @@ void Engine::enqueue_solve_begin(cudaGraphConditionalHandle cond) {
 void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
   // z = M r (the last smoother of the V-cycle sends z's boundary rows), then w = A z with
   // gamma = r.z and delta = z.w in one reduction, then the fused vector update (k_cg_fused)
-  enqueue_vcycle(cg_r_.p, cg_z_.p, nullptr);
+  enqueue_vcycle(cg_r_.p, cg_zf_.p);
   {
     RealArgs a;
-    a.val = A0().val; a.x = cg_z_.p; a.b = cg_r_.p; a.y = cg_Ap_.p;
+    a.val = A0().val; a.x = cg_zf_.p; a.b = cg_r_.p; a.y = cg_Ap_.p;
     a.red_out = &ctl_.p->rz_new; a.red2_out = &ctl_.p->pAp;
     if (comm_on_) a.halo = make_halo(0, kVecCgP, kTagIter);
-    launch_real<kOpSpmvCg>(A0(), a);
+    launch_real<kOpSpmvCg, kTypesZ>(A0(), a);
   }
   launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
-           comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_z_.p, cg_Ap_.p,
+           comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_zf_.p, cg_Ap_.p,
            cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, x0_dinv(), x0_out(), x0_omega(), partials_.p, counter_.p,
            cond, trace_slot("cg_fused", N_));
   TDGL_LAUNCH_CHECK();
@@ -1129,7 +1123,7 @@ void Engine::build_graph() {
     TDGL_LAUNCH_CHECK();
   });
   TDGL_CUDA(cudaGraphInstantiate(&graph_exec_, graph_, 0));
-  if (world_ == 1 && !scr_on_) build_split_graphs();
+  if (!scr_on_) build_split_graphs();
   launches_ = launches_before;  // captured, not launched
 }
 
@@ -1793,16 +1787,34 @@ Engine::AdvanceInfo Engine::update_local(const double* psi_loc, const double* mu
   if (!connected_) throw std::invalid_argument("sharded engine: connect the peers first (tdgl_comm_connect_*)");
   sync_ctl_to_host();
   int cur = h_ctl_->cur;
-  TDGL_CUDA(cudaMemcpyAsync(psi_[cur].p, psi_loc, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
-  TDGL_CUDA(cudaMemcpyAsync(mu_.p, mu_loc, sizeof(double) * N_, cudaMemcpyHostToDevice, stream_));
-  if (world_ > 1) {
+  // The caller's state lands in scratch first: when it is, bit for bit, the state this engine
+  // already holds on EVERY rank — a Runner-style loop that feeds each step's output back in —
+  // nothing is replaced, so the mu solve keeps its initial-guess history and the step equals a
+  // step of the device-resident loop.
+  TDGL_CUDA(cudaMemcpyAsync(tmp_c_.p, psi_loc, sizeof(double2) * N_, cudaMemcpyHostToDevice, stream_));
+  TDGL_CUDA(cudaMemcpyAsync(tmp_d_.p, mu_loc, sizeof(double) * N_, cudaMemcpyHostToDevice, stream_));
+  if (world_ > 1) comm_on_ = true;
+  int* differ = reinterpret_cast<int*>(counter_.p + 2);
+  TDGL_CUDA(cudaMemsetAsync(differ, 0, sizeof(int), stream_));
+  k_state_differs<<<grid_flat(N_), kBlock, 0, stream_>>>(N_, tmp_c_.p, psi_[0].p, psi_[1].p, ctl_.p, tmp_d_.p,
+                                                        mu_.p, differ);
+  TDGL_LAUNCH_CHECK();
+  k_state_vote<<<1, 32, 0, stream_>>>(ctl_.p, comm(), differ);
+  TDGL_LAUNCH_CHECK();
+  int h_differ = 1;
+  TDGL_CUDA(cudaMemcpyAsync(&h_differ, differ, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  if (h_differ) {
+    TDGL_CUDA(cudaMemcpyAsync(psi_[cur].p, tmp_c_.p, sizeof(double2) * N_, cudaMemcpyDeviceToDevice, stream_));
+    TDGL_CUDA(cudaMemcpyAsync(mu_.p, tmp_d_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
+  }
+  if (h_differ && world_ > 1) {
     // like set_state(reset_history): the mailbox copies of mu's history are refilled from the
     // new mu, so the extrapolated initial guess starts afresh
     TDGL_CUDA(cudaMemcpyAsync(mu_prev_.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
     TDGL_CUDA(cudaMemcpyAsync(mu_pp_.p, mu_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
     h_ctl_->psi_tag[cur] = h_ctl_->psi_epoch;
     push_ctl();
-    comm_on_ = true;
     const int g = (N_ + kBlock - 1) / kBlock;
     k_comm_barrier<<<1, 32, 0, stream_>>>(ctl_.p, comm_.p);   // peers are done with the old boxes
     TDGL_LAUNCH_CHECK();
@@ -1821,8 +1833,66 @@ Engine::AdvanceInfo Engine::update_local(const double* psi_loc, const double* mu
           ctl_.p, comm_.p, make_halo(0, kVecMu, kTagMu), n_halo, mu_pp_.p);
       TDGL_LAUNCH_CHECK();
     }
-  } else {
+  } else if (h_differ) {
     TDGL_CUDA(cudaStreamSynchronize(stream_));
+  }
+  if (graph_mode_ == 1 && graph_a_exec_ != nullptr && graph_b_exec_ != nullptr && psi_out && mu_out &&
+      js && jn && !scr_on_) {
+    // Overlapped seam (as Engine::update): psi' and J_s of the owned sites / edges are final
+    // once the psi loop has accepted; they drain on the copy stream under the mu solve.
+    const int ne = static_cast<int>(h_own_edges_.size());
+    const int ge = (std::max(ne, 1) + kBlock - 1) / kBlock;
+    const int n_halo = Nx_ - N_;
+    const int gh = std::min((std::max(n_halo, 1) + 1023) / 1024, 64);
+    const int nxt = cur ^ 1;   // the accepted psi lands in the other buffer
+    prepare_advance(1, 1e300, step, time);
+    TDGL_CUDA(cudaEventRecord(ev0_, stream_));
+    TDGL_CUDA(cudaGraphLaunch(graph_a_exec_, stream_));
+    TDGL_CUDA(cudaEventRecord(ev_psi_, stream_));
+    TDGL_CUDA(cudaGraphLaunch(graph_b_exec_, stream_));
+    launches_ += 2;
+    TDGL_CUDA(cudaStreamWaitEvent(copy_stream_, ev_psi_, 0));
+    TDGL_CUDA(cudaMemcpyAsync(psi_out, psi_[nxt].p, sizeof(double2) * N_, cudaMemcpyDeviceToHost, copy_stream_));
+    if (world_ > 1 && n_halo > 0) {
+      k_unpack<double2><<<gh, 1024, 0, copy_stream_>>>(ctl_.p, comm_.p, make_halo(0, kVecPsi0 + nxt, kTagPsiCur),
+                                                       n_halo, psi_[nxt].p);
+      TDGL_LAUNCH_CHECK();
+    }
+    if (ne > 0) {
+      k_currents<<<ge, kBlock, 0, copy_stream_>>>(
+          ne, own_edges_.p, e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
+          psi_[1].p, 1, mu_.p, has_dadt_ ? dadt_.p : nullptr, ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr,
+          static_cast<const double2*>(nullptr), edir_.p, tmp_e_.p, tmp_e2_.p);
+      TDGL_LAUNCH_CHECK();
+      tmp_e_.download(js, ne, copy_stream_);
+    }
+    TDGL_CUDA(cudaEventRecord(ev_copy_, copy_stream_));
+    // after the solve: mu' and J_n
+    mu_.download(mu_out, N_, stream_);
+    if (world_ > 1 && n_halo > 0) {
+      k_unpack<double><<<gh, 1024, 0, stream_>>>(ctl_.p, comm_.p, make_halo(0, kVecMu, kTagMu), n_halo, mu_.p);
+      TDGL_LAUNCH_CHECK();
+    }
+    if (ne > 0) {
+      k_currents<<<ge, kBlock, 0, stream_>>>(
+          ne, own_edges_.p, e0_.p, e1_.p, elen_.p, theta_.p, static_cast<const double2*>(nullptr), psi_[0].p,
+          psi_[1].p, 2, mu_.p, has_dadt_ ? dadt_.p : nullptr, ctl_.p, ramp_on_ ? ramp_proj_.p : nullptr,
+          static_cast<const double2*>(nullptr), edir_.p, tmp_e_.p, tmp_e2_.p);
+      TDGL_LAUNCH_CHECK();
+      tmp_e2_.download(jn, ne, stream_);
+    }
+    TDGL_CUDA(cudaStreamWaitEvent(stream_, ev_copy_, 0));
+    TDGL_CUDA(cudaEventRecord(ev1_, stream_));
+    TDGL_CUDA(cudaEventSynchronize(ev1_));
+    sync_ctl_to_host();
+    {
+      const int64_t split = static_cast<int64_t>(levels_.size()) - 1;
+      launches_ += h_ctl_->steps_done * (2 + (ramp_on_ ? 1 : 0)) + h_ctl_->steps_done * 7 +
+                   h_ctl_->total_retries * 2 + h_ctl_->total_cg_it * (2 + 4 * split + 1);
+    }
+    float dev_ms = 0.f;
+    TDGL_CUDA(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
+    return collect_advance(dev_ms);
   }
   AdvanceInfo info = advance(1, 1e300, step, time);
   cur = h_ctl_->cur;
@@ -2150,18 +2220,18 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
       case 1: enqueue_mu_rhs(nullptr); break;
       case 2: {
         RealArgs a;
-        a.val = A0().val; a.x = cg_z_.p; a.b = cg_r_.p; a.y = cg_Ap_.p;
+        a.val = A0().val; a.x = cg_zf_.p; a.b = cg_r_.p; a.y = cg_Ap_.p;
         a.red_out = &ctl_.p->rz_new; a.red2_out = &ctl_.p->pAp;
-        launch_real<kOpSpmvCg>(A0(), a);
+        launch_real<kOpSpmvCg, kTypesZ>(A0(), a);
         break;
       }
       case 9:
-        launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_z_.p,
+        launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_zf_.p,
                  cg_Ap_.p, cg_p_.p, cg_s_.p, tmp_d2_.p, cg_b_.p, x0_dinv(), x0_out(), x0_omega(),
                  partials_.p, counter_.p, static_cast<cudaGraphConditionalHandle>(0), 0);
         TDGL_LAUNCH_CHECK();
         break;
-      case 3: enqueue_vcycle(cg_r_.p, cg_z_.p, nullptr); break;
+      case 3: enqueue_vcycle(cg_r_.p, cg_zf_.p); break;
       case 4:
         mu_.zero(stream_);
         TDGL_CUDA(cudaMemcpyAsync(cg_r_.p, cg_b_.p, sizeof(double) * N_, cudaMemcpyDeviceToDevice, stream_));
@@ -2180,8 +2250,8 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
         if (!multi) throw std::invalid_argument("single-level hierarchy");
         RealArgs a;
         a.val = A0f().val; a.dinv = levels_[0].dinv.p; a.omega = levels_[0].omega; a.b = cg_r_.p;
-        a.x = levels_[0].x.p; a.y = cg_z_.p;
-        launch_real<kOpJacobi, kTypesJ0>(A0f(), a);
+        a.x = levels_[0].x.p; a.y = cg_zf_.p;
+        launch_real<kOpJacobi, kTypesP0>(A0f(), a);
         break;
       }
       case 7: {
