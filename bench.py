@@ -206,7 +206,10 @@ def hbm_peak():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons with nvidia-smi while the device is under load.
+    `start()` before the warm-up steps, `stop()` after the end-to-end loop: the timed region of
+    a default run is only tens of milliseconds long (shorter than nvidia-smi's start-up), so the
+    samples cover warm-up + timed steps + the end-to-end steps, all of them stepping load."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -217,14 +220,19 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # (the first sample takes nvidia-smi a few hundred ms: wait for it, bounded)
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 3.0:
+                time.sleep(0.02)
+            self.rows.clear()   # idle samples before the load starts do not count
         except OSError:
             self.proc = None
         return self
@@ -233,14 +241,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def __exit__(self, *exc):
+    def stop(self):
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.06)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -259,7 +268,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "warm-up + timed steps + end-to-end steps (50 ms period)"}
 
 
 # ------------------------------------------------------------------ CPU path (oracle port)
@@ -446,13 +456,13 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- device-resident throughput -----------------------------------------------------
     barrier()
+    clocks = ClockSampler(local_rank).start()   # (stopped after the end-to-end loop)
     a = eng.advance(W, 1e300, 0, 0.0) if W > 0 else None
     step, t = (a.step, a.time) if a is not None else (0, 0.0)
     launches_before = eng.info()["launches"]
     barrier()
-    with ClockSampler(local_rank) as clocks:
-        b = eng.advance(K, 1e300, step, t)
-        torch.cuda.synchronize()
+    b = eng.advance(K, 1e300, step, t)
+    torch.cuda.synchronize()
     barrier()
     launches = eng.info()["launches"] - launches_before
     ms = torch.tensor([b.device_ms], dtype=torch.float64, device="cuda")
@@ -510,6 +520,7 @@ def run_b200(args, rank, world, local_rank):
             state = {"step": state["step"] + 1, "time": state["time"] + dt_new, "dt": dt_new}
         barrier()
         e2e_s = time.perf_counter() - t0
+    clocks.stop()
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)

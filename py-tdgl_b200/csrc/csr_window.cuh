@@ -327,7 +327,7 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
   using TR = typename T::R;
   extern __shared__ __align__(128) unsigned char win_smem[];
   __shared__ uint64_t bar;
-  __shared__ double red[32];
+  __shared__ double red[64];
   trace_in(ctl, a.trace_id, 0);
   const WinRow w = window_stage<sizeof(TV), 0, LPR>(m, a.val, nullptr, win_smem, &bar);
   const TV* sv = reinterpret_cast<const TV*>(win_smem);
@@ -412,10 +412,8 @@ kw_real(Ctl* ctl, Comm* comm, WinCsr m, RealArgs a, double* partials, unsigned i
     (void)out;
   }
   if (OP == kOpSpmvCg) {
-    const double b0 = block_sum(d, red);
-    const double b1 = block_sum(d2, red);
     double t0, t1;
-    if (grid_sum2_last(b0, b1, partials, counter, red, &t0, &t1) && threadIdx.x < 32) {
+    if (grid_sum2_fused(d, d2, partials, counter, red, &t0, &t1) && threadIdx.x < 32) {
       double v[2];
       v[0] = __shfl_sync(0xffffffffu, t0, 0);
       v[1] = __shfl_sync(0xffffffffu, t1, 0);

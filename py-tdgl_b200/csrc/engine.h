@@ -405,6 +405,11 @@ class Engine {
     int g = (n + kBlock - 1) / kBlock;
     return g < 1 ? 1 : (g > 1184 ? 1184 : g);  // 148 SMs x 8 resident blocks
   }
+  // k_cg_fused: 48 registers -> 5 resident blocks per SM, one wave, two elements per trip
+  int grid_fused(int n) const {
+    const int g = (n + 2 * kBlock - 1) / (2 * kBlock);
+    return g < 1 ? 1 : (g > 5 * sm_count_ ? 5 * sm_count_ : g);
+  }
   void upload_csr(const HostCsr<double>& h, DevCsr& d, int lanes_per_row = 0,
                   int64_t n_owned_cols = -1, const std::vector<int>* push_rptr = nullptr);
   void launch_spmv(const CsrView& A, const double* x, double* y, double* dot_out);

@@ -191,6 +191,58 @@ __device__ __forceinline__ bool grid_sum_last(double partial, double* partials,
   return true;
 }
 
+// Deterministic grid reduction of TWO sums with two block barriers in all (a CTA's warps reach
+// them at different times — every barrier is a wait for the slowest warp): warp sums -> shared
+// memory -> thread 0 adds them in warp order and publishes the block's pair -> last block adds
+// the pairs in block order.  v0 / v1: every thread's contributions.  Same contract as
+// grid_sum2_last otherwise (smem: >= 64 doubles).
+__device__ __forceinline__ bool grid_sum2_fused(double v0, double v1, double* partials,
+                                                unsigned int* counter, double* smem, double* t0,
+                                                double* t1) {
+  __shared__ int s_last2f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v0 = warp_sum(v0);
+  v1 = warp_sum(v1);
+  if (lane == 0) { smem[warp] = v0; smem[32 + warp] = v1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nw; ++k) { a += smem[k]; b += smem[32 + k]; }
+    reinterpret_cast<double2*>(partials)[blockIdx.x] = make_double2(a, b);
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last2f = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last2f) return false;
+  __threadfence();
+  double a0 = 0.0, a1 = 0.0;
+  const double2* p2 = reinterpret_cast<const double2*>(partials);
+  const unsigned int n = gridDim.x, bd = blockDim.x;
+  unsigned int i = threadIdx.x;
+  for (; i + 7u * bd < n; i += 8u * bd) {
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(p2 + i + k * bd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0 += v[k].x; a1 += v[k].y; }
+  }
+  for (; i < n; i += bd) {
+    const double2 v = __ldcg(p2 + i);
+    a0 += v.x;
+    a1 += v.y;
+  }
+  a0 = block_sum(a0, smem);
+  a1 = block_sum(a1, smem);
+  if (threadIdx.x == 0) {
+    *t0 = a0;
+    *t1 = a1;
+    *counter = 0u;
+  }
+  return true;
+}
+
 // Two sums through one pass (partials interleaved, 2 per block); same contract.
 __device__ __forceinline__ bool grid_sum2_last(double p0, double p1, double* partials,
                                                unsigned int* counter, double* smem,
@@ -295,7 +347,8 @@ k_dense_matvec(const Ctl* __restrict__ ctl, int rows, int nc, int ld, const floa
 // in one pass over the vectors.  The same iterates as textbook PCG (p = z + beta p, alpha =
 // r.z / p.Ap) in exact arithmetic, with one launch and one grid reduction less per iteration.
 // Last block: bookkeeping + loop condition of the CG loop.
-__global__ void __launch_bounds__(kBlock)
+template <bool SH>
+__global__ void __launch_bounds__(kBlock, 5)
 k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const float* __restrict__ z,
            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
            double* __restrict__ x, double* __restrict__ r, const float* __restrict__ dinv,
@@ -317,7 +370,7 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const float* __restrict__
   const double beta = first ? 0.0 : gamma / ctl->rz_prev;
   const double denom = first ? delta : delta - beta * gamma / ctl->alpha_prev;
   const double alpha = gamma / denom;
-  const unsigned int tag = comm != nullptr ? comm_tag(ctl, push.tag_mode) : 0u;
+  const unsigned int tag = (SH && comm != nullptr) ? comm_tag(ctl, push.tag_mode) : 0u;
   double d = 0.0;
   // two independent elements per trip: twelve loads in flight per thread
   const int stride = gridDim.x * blockDim.x;
@@ -344,7 +397,7 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const float* __restrict__
     if (x0 != nullptr) {
       const float ti = static_cast<float>(omega * static_cast<double>(dinv[i]) * ri);
       x0[i] = ti;
-      if (comm != nullptr) push_row(comm, push, tag, i, static_cast<double>(ti));
+      if (SH && comm != nullptr) push_row(comm, push, tag, i, static_cast<double>(ti));
     }
     d += ri * ri;
     if (two) {
@@ -358,7 +411,7 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const float* __restrict__
       if (x0 != nullptr) {
         const float tj = static_cast<float>(omega * static_cast<double>(dinv[j]) * rj);
         x0[j] = tj;
-        if (comm != nullptr) push_row(comm, push, tag, j, static_cast<double>(tj));
+        if (SH && comm != nullptr) push_row(comm, push, tag, j, static_cast<double>(tj));
       }
       d += rj * rj;
     }
@@ -367,7 +420,7 @@ k_cg_fused(Ctl* ctl, Comm* comm, PushArgs push, int n, const float* __restrict__
   double total;
   if (grid_sum_last(bs, partials, counter, red, &total) && threadIdx.x < 32) {
     total = __shfl_sync(0xffffffffu, total, 0);
-    if (comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
+    if (SH && comm != nullptr) comm_allreduce(ctl, comm, &total, 1, false);
     if (threadIdx.x == 0) {
       ctl->rr = total;
       ctl->rz_prev = gamma;

@@ -729,7 +729,8 @@ void Engine::configure_kernels() {
   preload(reinterpret_cast<const void*>(&k_psi_control));
   preload(reinterpret_cast<const void*>(&k_cg_begin));
   preload(reinterpret_cast<const void*>(&k_mu_guess));
-  preload(reinterpret_cast<const void*>(&k_cg_fused));
+  preload(reinterpret_cast<const void*>(&k_cg_fused<false>));
+  preload(reinterpret_cast<const void*>(&k_cg_fused<true>));
   preload(reinterpret_cast<const void*>(&k_weighted_sum));
   preload(reinterpret_cast<const void*>(&k_shift));
   preload(reinterpret_cast<const void*>(&k_step_end));
@@ -980,10 +981,14 @@ void Engine::enqueue_cg_iteration(cudaGraphConditionalHandle cond) {
     if (comm_on_) a.halo = make_halo(0, kVecCgP, kTagIter);
     launch_real<kOpSpmvCg, kTypesZ>(A0(), a);
   }
-  launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(),
-           comm_on_ ? make_push(0, kVecCgR, kTagIterNext) : PushArgs(), N_, cg_zf_.p, cg_Ap_.p,
-           cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, x0_dinv(), x0_out(), x0_omega(), partials_.p, counter_.p,
-           cond, trace_slot("cg_fused", N_));
+  if (comm_on_)
+    launch_k(k_cg_fused<true>, grid_fused(N_), kBlock, 0, ctl_.p, comm(), make_push(0, kVecCgR, kTagIterNext),
+             N_, cg_zf_.p, cg_Ap_.p, cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, x0_dinv(), x0_out(), x0_omega(),
+             partials_.p, counter_.p, cond, trace_slot("cg_fused", N_));
+  else
+    launch_k(k_cg_fused<false>, grid_fused(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_zf_.p,
+             cg_Ap_.p, cg_p_.p, cg_s_.p, mu_.p, cg_r_.p, x0_dinv(), x0_out(), x0_omega(), partials_.p,
+             counter_.p, cond, trace_slot("cg_fused", N_));
   TDGL_LAUNCH_CHECK();
 }
 
@@ -2226,7 +2231,7 @@ double Engine::time_kernel(int which, int reps, int flush_l2) {
         break;
       }
       case 9:
-        launch_k(k_cg_fused, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_zf_.p,
+        launch_k(k_cg_fused<false>, grid_flat(N_), kBlock, 0, ctl_.p, comm(), PushArgs(), N_, cg_zf_.p,
                  cg_Ap_.p, cg_p_.p, cg_s_.p, tmp_d2_.p, cg_b_.p, x0_dinv(), x0_out(), x0_omega(),
                  partials_.p, counter_.p, static_cast<cudaGraphConditionalHandle>(0), 0);
         TDGL_LAUNCH_CHECK();

@@ -23,15 +23,22 @@ os.makedirs(out, exist_ok=True)
 
 OPS = {"kw_real<0>": "kw_real<spmv_dot>", "kw_real<1>": "kw_real<residual>",
        "kw_real<2>": "kw_real<presmooth>", "kw_real<3>": "kw_real<jacobi>",
-       "kw_real<4>": "kw_real<plain> (restriction)", "kw_real<5>": "kw_real<plain_add> (prolongation)"}
+       "kw_real<4>": "kw_real<plain> (restriction)", "kw_real<5>": "kw_real<plain_add> (prolongation)",
+       "kw_real<6>": "kw_real<spmv_cg>"}
 
 
 def short(name):
-    name = re.sub(r"\(.*", "", name).replace("void ", "").replace("tdgl::", "").strip()
-    m = re.match(r"kw_real<\(?(?:int\))?(\d), \(?(?:bool\))?(\d)(?:, \(?(?:int\))?(\d))?>", name)
+    name = name.replace("void ", "").replace("tdgl::", "").strip()
+    m = re.match(r"kw_real<\(?(?:int\))?(\d), \(?(?:bool\))?(\d)(?:, \(?(?:int\))?(\d))?(?:, RealTypes<([^>]*)>)?", name)
     if m:
+        types = (m.group(4) or "").replace(" ", "")
+        tag = {"double,double,double,double,double": "f64", "float,float,float,float,float": "f32",
+               "float,float,double,float,float": "f32 matrix, f64 rhs",
+               "double,float,double,double,double": "f64 matrix, f32 x"}.get(types, types)
         return (OPS[f"kw_real<{m.group(1)}>"] + (" [sharded]" if m.group(2) == "1" else "")
-                + (" [4 lanes/row]" if m.group(3) == "4" else ""))
+                + (" [4 lanes/row]" if m.group(3) == "4" else "") + (f" [{tag}]" if tag else ""))
+    name = re.sub(r"\([^()]*\)\s*$", "", name)           # the argument list
+    name = re.sub(r"\((?:int|bool)\)", "", name)
     return OPS.get(name, name)
 
 

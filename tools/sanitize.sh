@@ -8,7 +8,7 @@ for tool in memcheck racecheck synccheck; do
     extra=""
     [ "$tool" = "synccheck" ] && extra="--num-cuda-barriers 16384"
     out=gpurun_out/san_${tool}_${world}.log
-    timeout 600 $CS --tool $tool $extra --print-limit 20 python tests/tools/sanitize_target.py $world 2 > $out 2>&1
+    timeout 240 $CS --tool $tool $extra --print-limit 20 python tests/tools/sanitize_target.py $world 2 > $out 2>&1
     echo "== $tool, $world shard(s): exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize target|Error|error" $out | head -8
   done
 done
