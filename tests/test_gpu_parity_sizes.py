@@ -32,7 +32,10 @@ TOL, TOL_DT = 1e-8, 1e-10
 RTOLS = [pytest.param(1e-10, 1e-8, 1e-10, id="mu_rtol=default")]
 
 
-def _oracle_run(work, steps):
+def _oracle_run(work, steps, perturb=0.0):
+    """The oracle on a bench workload; `perturb` > 0: from an initial psi perturbed by that
+    relative amount (how far the reference itself moves under a roundoff-sized change of its
+    input is the floor of what two correct solvers can agree to)."""
     o = work["opts"]
     opts = orc.OracleOptions(solve_time=1e9, dt_init=o["dt_init"], dt_max=o["dt_max"],
                              adaptive=o["adaptive"])
@@ -40,6 +43,10 @@ def _oracle_run(work, steps):
     solver = orc.OracleSolver(work["mesh"], opts, work["A"], work["eps"],
                               terminal_info=[orc.TerminalInfo(*t) for t in work["terms"]],
                               current_func=cf)
+    if perturb > 0.0:
+        n = len(work["mesh"].sites)
+        psi0 = solver.psi_init * (1 + perturb * np.random.default_rng(1).normal(size=n))
+        return orc.run(solver, end_time=1e9, max_steps=steps, psi0=psi0)
     return orc.run(solver, end_time=1e9, max_steps=steps)
 
 
@@ -88,7 +95,16 @@ def film250k():
     import bench
 
     work = bench.build_workload("film250k_field")
-    return work, _oracle_run(work, 60)
+    ref = _oracle_run(work, 60)
+    # vortices are entering this film: the reference moves by ~7.5e-9 (psi) after 60 steps when
+    # its own initial psi is perturbed by 1e-13, which is where the GPU lands as well (5-7e-9).
+    # The tolerance is therefore 10x the reference's own sensitivity (floor 1e-8, cap
+    # BASELINE.json's 1e-6) instead of a bare 1e-8 at the noise floor.
+    self_d = orc.compare(_oracle_run(work, 60, perturb=1e-13), ref, work["mesh"].areas)
+    print("film250k_field: reference vs itself (1e-13 perturbation)", self_d)
+    tol = min(1e-6, max(TOL, 10.0 * self_d["psi"]))
+    tol_dt = min(1e-6, max(TOL_DT, 10.0 * self_d["dt"]))
+    return work, ref, (tol, tol_dt)
 
 
 @pytest.fixture(scope="module")
@@ -115,18 +131,18 @@ def _sharded(world, mu_rtol=1e-10):
 @pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
 def test_film250k_field_matches_oracle(film250k, mu_rtol, tol, tol_dt):
     """BASELINE.json configs[1]: 200x200 xi film (~251k sites), B = 0.1, adaptive dt."""
-    work, ref = film250k
+    work, ref, tol_s = film250k
     got = _cuda_run(work, 60, mu_rtol=mu_rtol)
     _assert_parity(f"film250k_field, 60 steps, mu_rtol={mu_rtol}", got, ref,
-                   work["mesh"].areas, tol, tol_dt)
+                   work["mesh"].areas, max(tol, tol_s[0]), max(tol_dt, tol_s[1]))
 
 
 @pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
 def test_film250k_field_4_shards_match_oracle(film250k, mu_rtol, tol, tol_dt):
-    work, ref = film250k
+    work, ref, tol_s = film250k
     got = _cuda_run(work, 60, _sharded(4, mu_rtol), mu_rtol=mu_rtol)
     _assert_parity(f"film250k_field, 4 shards, 60 steps, mu_rtol={mu_rtol}", got, ref,
-                   work["mesh"].areas, tol, tol_dt)
+                   work["mesh"].areas, max(tol, tol_s[0]), max(tol_dt, tol_s[1]))
 
 
 @pytest.mark.parametrize("mu_rtol,tol,tol_dt", RTOLS)
@@ -202,15 +218,13 @@ def test_terminal_psi_one_and_none(terminal_psi):
     """ref test_solve.py:19: terminal_psi = 1 sets the initial value on the (identity-row)
     terminal sites; None leaves the covariant Laplacian without fixed rows."""
     c, sol, got, ref = _edge_case(terminal_psi=terminal_psi)
-    if terminal_psi is not None:
-        _check_edge(f"terminal_psi={terminal_psi}", c, got, ref)
-        return
-    # Without fixed rows the superconducting ends take the injected current themselves and the
-    # flow is far more sensitive: the reference moves by ~1e-7 when its own initial psi is
-    # perturbed by 1e-13 (asserted here), so 1e-6 — BASELINE.json's tolerance — is what two
-    # correct solvers can be asked to agree to.
+    # With superconducting ends (psi = 1 held on the terminal sites, or no fixed rows at all) the
+    # ends take the injected current themselves and the flow is far more sensitive than with
+    # normal-metal ends: the reference moves by ~1e-7 (psi = 1: 7.5e-8, None: 1.6e-7) when its
+    # own initial psi is perturbed by 1e-13 (asserted here), so 1e-6 — BASELINE.json's tolerance —
+    # is what two correct solvers can be asked to agree to.  (Measured on the GPU: 0.5-1e-8.)
     okw = dict(solve_time=1.5, dt_init=c.opts["dt_init"], dt_max=c.opts["dt_max"],
-               terminal_psi=None)
+               terminal_psi=terminal_psi)
 
     def oracle():
         return orc.OracleSolver(c.mesh, orc.OracleOptions(**okw), c.A, c.eps, u=c.u,
@@ -221,9 +235,9 @@ def test_terminal_psi_one_and_none(terminal_psi):
     o2 = oracle()
     psi0 = o2.psi_init * (1 + 1e-13 * np.random.default_rng(1).normal(size=len(c.mesh.sites)))
     self_d = orc.compare(orc.run(o2, end_time=1.5, psi0=psi0), ref, c.mesh.areas)
-    print("terminal_psi=None: reference vs itself (1e-13 perturbation)", self_d)
+    print(f"terminal_psi={terminal_psi}: reference vs itself (1e-13 perturbation)", self_d)
     assert self_d["psi"] > 1e-9, "expected the reference to amplify a 1e-13 perturbation"
-    _check_edge("terminal_psi=None", c, got, ref, tol=1e-6, tol_dt=1e-6)
+    _check_edge(f"terminal_psi={terminal_psi}", c, got, ref, tol=1e-6, tol_dt=1e-6)
 
 
 @pytest.mark.parametrize("use_graph", [True, False])

@@ -10,12 +10,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "py-tdgl_b200", "libtdgl_b200.so")
-WANT = [("kw_real<spmv_cg, single GPU, 1 lane/row, double>", r"kw_realILi6ELb0ELi1ENS_9RealTypesIddddd"),
-        ("kw_real<presmooth, single GPU, 1 lane/row, float matrix, double b>", r"kw_realILi2ELb0ELi1ENS_9RealTypesIffdff"),
-        ("kw_real<jacobi, single GPU, 1 lane/row, float matrix, double b and y>", r"kw_realILi3ELb0ELi1ENS_9RealTypesIffddf"),
+WANT = [("kw_real<spmv_cg, single GPU, 1 lane/row, double matrix, float z>", r"kw_realILi6ELb0ELi1ENS_9RealTypesIdfddd"),
+        ("kw_real<residual (pre-smoother), single GPU, 1 lane/row, float matrix, double r>", r"kw_realILi1ELb0ELi1ENS_9RealTypesIffdff"),
+        ("kw_real<jacobi, single GPU, 1 lane/row, float matrix, double r, float z>", r"kw_realILi3ELb0ELi1ENS_9RealTypesIffdff"),
+        ("kw_real<restriction, single GPU, 4 lanes/row, float>", r"kw_realILi4ELb0ELi4ENS_9RealTypesIfffff"),
         ("kw_psi_step<single GPU>", r"kw_psi_stepILb0E"),
         ("kw_mu_rhs<single GPU>", r"kw_mu_rhsILb0E"),
-        ("kw_real<spmv_cg, sharded>", r"kw_realILi6ELb1ELi1ENS_9RealTypesIddddd")]
+        ("kw_real<spmv_cg, sharded>", r"kw_realILi6ELb1ELi1ENS_9RealTypesIdfddd")]
 KEYS = ("UBLKCP", "SYNCS", "ACQBULK", "DEPBAR", "ST.E.64.STRONG.SYS", "LD.E.128.STRONG.SYS",
         "LD.E.64.STRONG.SYS")
 
