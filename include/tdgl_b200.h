@@ -205,7 +205,12 @@ int tdgl_update(tdgl_handle* h, const double* psi, const double* mu, int64_t ste
  *   tdgl_update_local: like tdgl_update with psi_local / mu_local (in) and psi_out / mu_out /
  *     supercurrent / normal_current (out) in that local order.  Every rank must call it for
  *     every step (the ranks meet in an on-device barrier).  With world = 1 it is tdgl_update
- *     without the renumbering. */
+ *     without the renumbering.  When the state handed in equals, bit for bit and on every rank,
+ *     the state the engine holds — a Runner-style loop feeding each step's output back
+ *     (reference runner.py:417-423) — nothing is replaced and the step is identical to a step
+ *     of tdgl_advance (the mu solve keeps its initial-guess history); any other state resets
+ *     that history like tdgl_set_state.  psi_out / supercurrent are final before the mu solve
+ *     and are copied out under it. */
 int tdgl_local_maps(tdgl_handle* h, int64_t* sizes, int64_t* sites, int64_t* edges);
 int tdgl_update_local(tdgl_handle* h, const double* psi_local, const double* mu_local, int64_t step,
                       double time, double* psi_out, double* mu_out, double* supercurrent,

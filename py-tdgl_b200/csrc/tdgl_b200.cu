@@ -2794,7 +2794,8 @@ int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
       if (level_nnz) level_nnz[l] = H.levels[l].A.nnz();
     }
     if (rhs == nullptr || x == nullptr) return TDGL_OK;
-    // host PCG with the same V(1,1) cycle the device runs (validation of the hierarchy)
+    // host PCG with the same V(1,1) cycle the device runs (validation of the hierarchy);
+    // TDGL_PROBE_NU0 / TDGL_PROBE_NUC: smoothing sweeps on level 0 / the coarser levels (design studies)
     std::vector<std::vector<double>> bx(L), xx(L), rr(L), yy(L);
     for (int l = 0; l < L; ++l) { const size_t n = H.levels[l].A.rows; bx[l].resize(n); xx[l].resize(n); rr[l].resize(n); yy[l].resize(n); }
     std::vector<double> tmp;
@@ -2806,15 +2807,25 @@ int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,
         return;
       }
       const double om = (4.0 / 3.0) / lv.rho;
+      static const int nu0 = std::getenv("TDGL_PROBE_NU0") ? std::atoi(std::getenv("TDGL_PROBE_NU0")) : 1;
+      static const int nuc = std::getenv("TDGL_PROBE_NUC") ? std::atoi(std::getenv("TDGL_PROBE_NUC")) : 1;
+      const int nu = l == 0 ? nu0 : nuc;
       for (int64_t i = 0; i < n; ++i) xx[l][i] = om * lv.dinv[i] * bx[l][i];
+      for (int sw = 1; sw < nu; ++sw) {
+        spmv(lv.A, xx[l], tmp);
+        for (int64_t i = 0; i < n; ++i) xx[l][i] += om * lv.dinv[i] * (bx[l][i] - tmp[i]);
+      }
       spmv(lv.A, xx[l], tmp);
       for (int64_t i = 0; i < n; ++i) rr[l][i] = bx[l][i] - tmp[i];
       spmv(lv.R, rr[l], bx[l + 1]);
       cycle(l + 1);
       spmv(lv.P, yy[l + 1], tmp);
       for (int64_t i = 0; i < n; ++i) xx[l][i] += tmp[i];
-      spmv(lv.A, xx[l], tmp);
-      for (int64_t i = 0; i < n; ++i) yy[l][i] = xx[l][i] + om * lv.dinv[i] * (bx[l][i] - tmp[i]);
+      for (int sw = 0; sw < nu; ++sw) {
+        spmv(lv.A, xx[l], tmp);
+        for (int64_t i = 0; i < n; ++i) xx[l][i] += om * lv.dinv[i] * (bx[l][i] - tmp[i]);
+      }
+      for (int64_t i = 0; i < n; ++i) yy[l][i] = xx[l][i];
     };
     const int64_t n = n_sites;
     std::vector<double> r(rhs, rhs + n), p(n, 0.0), Ap, sol(n, 0.0);
