@@ -235,3 +235,66 @@ def test_shard_local_step_seam_matches_reference(world):
     for k, v in d.items():
         assert v < 1e-8, (k, d)
     del g
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_shard_local_seam_fed_back_equals_the_resident_loop(world):
+    """A Runner-style loop through tdgl_update_local that feeds every step's output back as
+    the next input must be the device-resident loop, bit for bit: the engine recognises the
+    state it already holds (bitwise compare + a vote of all ranks), replaces nothing and keeps
+    the initial-guess history of the mu solve.  A state that differs in one bit takes the other
+    path (state replaced, history reset) and still agrees to solver accuracy."""
+    c = load_case("strip_transport")
+    n, E = len(c.mesh.sites), len(c.mesh.edge_mesh.edges)
+    fixed = np.concatenate([np.asarray(t.site_indices) for t in c.terminals])
+    psi0 = np.ones(n, complex)
+    psi0[fixed] = 0.0
+    mub = np.zeros(len(c.mesh.edge_mesh.boundary_edge_indices))
+    names = [t.name for t in c.terminals]
+    for t in c.terminals:
+        dens = (-1 / t.length) * sum(c.currents[m] for m in names if m != t.name)
+        mub[np.asarray(t.boundary_edge_indices)] = dens
+    steps = 24
+
+    def prepare(grp):
+        grp.set_stepper(**_stepper(c))
+        grp.set_mu_boundary(mub)
+        grp.set_state(psi0, np.zeros(n))
+
+    with _group(c, world, running_capacity=64) as grp:
+        prepare(grp)
+        a = grp.advance(steps, 1e300, 0, 0.0)
+        psi_loop, mu_loop = grp.get_state()
+
+    def seam(perturb_at=None):
+        with _group(c, world, running_capacity=64) as grp:
+            prepare(grp)
+            maps = grp.local_maps()
+            psi = [psi0[m[0]].copy() for m in maps]
+            mu = [np.zeros(len(m[0])) for m in maps]
+            outs = [(np.empty(len(m[0]), complex), np.empty(len(m[0])), np.empty(len(m[1])),
+                     np.empty(len(m[1]))) for m in maps]
+            step, time, its = 0, 0.0, 0
+            for k in range(steps):
+                if k == perturb_at:     # one bit of one entry on one shard
+                    v = mu[-1][:1].view(np.uint64)
+                    v ^= np.uint64(1)
+                info, outs = grp.update_local(psi, mu, step, time, outs)
+                psi = [o[0].copy() for o in outs]
+                mu = [o[1].copy() for o in outs]
+                step, time = info.step, info.time
+                its += info.mu_iterations
+            full_psi, full_mu = np.zeros(n, complex), np.zeros(n)
+            for m, o in zip(maps, outs):
+                full_psi[m[0]], full_mu[m[0]] = o[0], o[1]
+        return full_psi, full_mu, its, time
+
+    psi_s, mu_s, its_s, t_s = seam()
+    assert t_s == a.time and its_s == a.mu_iterations, (t_s, a.time, its_s, a.mu_iterations)
+    assert np.array_equal(psi_s, psi_loop) and np.array_equal(mu_s, mu_loop)
+    psi_p, mu_p, its_p, _ = seam(perturb_at=steps // 2)
+    d = orc.compare(dict(psi=psi_p, mu=mu_p), dict(psi=psi_loop, mu=mu_loop), c.mesh.areas)
+    print("seam with one flipped bit at step", steps // 2, "vs the loop:", d, "mu iterations",
+          its_p, "vs", its_s)
+    assert d["psi"] < 1e-8 and d["mu"] < 1e-8, d
+    assert its_p >= its_s - 2   # (the reset guess costs iterations, it does not save them)
