@@ -283,21 +283,81 @@ class Device:
             inside &= ~hole.contains_points(points, radius=-1e-9)
         return inside
 
-    def make_mesh(self, max_edge_length: Optional[float] = None, min_points: int = 0,
-                  jitter: float = 0.15, seed: int = 0, reorder: bool = True, **_ignored) -> None:
-        """Triangulate the film: outline points of film and holes resampled at the target
-        edge length + a jittered hexagonal interior lattice, Delaunay-triangulated, elements
-        outside the film or inside holes removed (stand-in for the Triangle-based
-        ``generate_mesh``, tdgl/device/meshing.py:15-123)."""
-        from scipy.spatial import Delaunay
+    def make_mesh(self, max_edge_length: Optional[float] = None,
+                  min_points: Optional[int] = None, smooth: int = 0, jitter: float = 0.15,
+                  seed: int = 0, reorder: bool = True, **_ignored) -> None:
+        """Generates the triangular mesh with the reference's contract (``Device.make_mesh``,
+        tdgl/device/device.py:520-566; ``generate_mesh``, tdgl/device/meshing.py:15-123):
 
+        * ``max_edge_length``: no edge of the result is longer (default 1.0 x coherence length;
+          <= 0: the density follows the point density of the film / hole polygons only);
+        * ``min_points``: the result has at least this many vertices;
+        * ``smooth``: that many Laplacian smoothing sweeps of the interior vertices
+          (``Mesh.smooth``) afterwards;
+        * like the reference the generator refines until both bounds hold.
+
+        The generator itself is not Triangle (meshpy is a setup-time dependency this package
+        does not take): outline points of film and holes resampled at the pitch + a jittered
+        hexagonal interior lattice, Delaunay-triangulated (Qhull), elements outside the film
+        or inside holes removed.  ``meshpy_kwargs`` such as ``min_angle`` are accepted and
+        ignored (a jittered hexagonal lattice has angles of 40-80 degrees)."""
         xi = self.layer.coherence_length
         w, hgt = self.film.extents
         if max_edge_length is None:
-            max_edge_length = xi / 2 if not min_points else np.sqrt(w * hgt / max(min_points, 1))
-        h = float(max_edge_length) * 0.8
+            max_edge_length = 1.0 * xi
+        max_edge_length = float(max_edge_length)
+        min_points = int(min_points) if min_points else 0
+        if max_edge_length <= 0:
+            # density of the polygons' own points (reference: "determined solely by the density
+            # of points in the Device's film and holes"), still subject to min_points
+            seg = np.concatenate([np.linalg.norm(np.diff(np.vstack([p.points, p.points[:1]]),
+                                                         axis=0), axis=1)
+                                  for p in [self.film] + list(self.holes)])
+            h = float(np.median(seg[seg > 0]))
+            max_edge_length = np.inf
+        else:
+            h = 0.8 * max_edge_length
         if min_points:
-            h = min(h, np.sqrt(w * hgt / min_points / (2 / np.sqrt(3))))
+            # a hexagonal lattice of pitch h has 2 / (sqrt(3) h^2) points per unit area
+            h = min(h, np.sqrt(self._area() * 2 / np.sqrt(3) / min_points))
+        for attempt in range(40):
+            pts, tri = self._triangulate(h, jitter, seed)
+            longest = _max_edge_length(pts, tri)
+            if len(pts) >= min_points and longest <= max_edge_length:
+                break
+            # (the reference shrinks Triangle's max_volume by min(0.98, sqrt(target / longest))
+            # per pass, meshing.py:117-120; the pitch is a length, so the same factor applies
+            # to it directly and converges in a pass or two)
+            shrink = 0.98
+            if np.isfinite(max_edge_length) and longest > max_edge_length:
+                shrink = min(shrink, 0.98 * max_edge_length / longest)
+            if len(pts) < min_points:
+                shrink = min(shrink, 0.98 * np.sqrt(len(pts) / min_points))
+            h *= shrink
+        else:
+            raise RuntimeError("make_mesh: could not satisfy min_points / max_edge_length")
+        if smooth:
+            m = Mesh.from_triangulation(pts, tri, create_submesh=False).smooth(
+                int(smooth), create_submesh=False)
+            pts, tri = m.sites, m.elements
+        if reorder:
+            perm = morton_order(pts)
+            inv = np.empty_like(perm)
+            inv[perm] = np.arange(len(perm))
+            pts, tri = pts[perm], inv[tri]
+        self.mesh = Mesh.from_triangulation(pts / xi, tri)
+
+    def _area(self) -> float:
+        def poly_area(v):
+            x, y = v[:, 0], v[:, 1]
+            return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+        return poly_area(self.film.points) - sum(poly_area(hh.points) for hh in self.holes)
+
+    def _triangulate(self, h: float, jitter: float, seed: int):
+        """Points (length units) and counter-clockwise triangles at lattice pitch ``h``."""
+        from scipy.spatial import Delaunay
+
+        from .mesh import _hex_lattice
 
         def resample(poly):
             v = poly.points
@@ -313,8 +373,6 @@ class Device:
         boundary = np.concatenate(outlines)
         xmin, ymin = self.film.points.min(axis=0)
         xmax, ymax = self.film.points.max(axis=0)
-        from .mesh import _hex_lattice
-
         rng = np.random.default_rng(seed)
         pts = _hex_lattice(xmin, xmax, ymin, ymax, h)
         pts = pts + rng.uniform(-jitter * h, jitter * h, size=pts.shape)
@@ -338,13 +396,7 @@ class Device:
         used = np.zeros(len(allpts), dtype=bool)
         used[tri.ravel()] = True
         remap = np.cumsum(used) - 1
-        allpts, tri = allpts[used], remap[tri]
-        if reorder:
-            perm = morton_order(allpts)
-            inv = np.empty_like(perm)
-            inv[perm] = np.arange(len(perm))
-            allpts, tri = allpts[perm], inv[tri]
-        self.mesh = Mesh.from_triangulation(allpts / xi, tri)
+        return allpts[used], remap[tri]
 
     def copy(self) -> "Device":
         d = Device(self.name, layer=self.layer.copy(), film=self.film.copy(),
@@ -364,6 +416,12 @@ class Device:
                 and self.film == other.film and self.holes == other.holes
                 and list(self.terminals) == list(other.terminals)
                 and self.length_units == other.length_units)
+
+
+def _max_edge_length(points: np.ndarray, elements: np.ndarray) -> float:
+    """reference ``get_max_edge_length`` (finite_volume/util.py:45-56)."""
+    e = np.concatenate([elements[:, c] for c in ((0, 1), (1, 2), (2, 0))])
+    return float(np.linalg.norm(points[e[:, 1]] - points[e[:, 0]], axis=1).max())
 
 
 def _min_distance(pts: np.ndarray, outline: np.ndarray) -> np.ndarray:

@@ -92,6 +92,30 @@ class Mesh:
         """reference ``mesh.py:92-101``"""
         return int(np.argmin(np.linalg.norm(self.sites - np.atleast_2d(xy), axis=1)))
 
+    def smooth(self, iterations: int, create_submesh: bool = True) -> "Mesh":
+        """Laplacian smoothing: every interior vertex moves to the arithmetic mean of its
+        neighbours, boundary vertices stay (reference ``Mesh.smooth``, ``mesh.py:245-283``;
+        here the neighbour sums are two ``bincount`` passes per coordinate over the unique
+        edges and the dual mesh is built once, after the last sweep)."""
+        sites = np.array(self.sites, dtype=np.float64)
+        if iterations <= 0:
+            return Mesh.from_triangulation(sites, self.elements, create_submesh=create_submesh)
+        n = len(sites)
+        edges = get_edges(self.elements, n)[0]
+        e0, e1 = edges[:, 0], edges[:, 1]
+        num_neighbors = np.bincount(edges.ravel(), minlength=n).astype(np.float64)
+        boundary = self.boundary_indices
+        for _ in range(int(iterations)):
+            new = np.empty_like(sites)
+            for d in range(2):
+                # (same order of accumulation as the reference: edge[:, 0] targets first)
+                acc = np.bincount(e0, sites[e1, d], minlength=n)
+                acc += np.bincount(e1, sites[e0, d], minlength=n)
+                new[:, d] = acc / num_neighbors
+            new[boundary] = sites[boundary]
+            sites = new
+        return Mesh.from_triangulation(sites, self.elements, create_submesh=create_submesh)
+
     @staticmethod
     def from_triangulation(sites, elements, create_submesh: bool = True) -> "Mesh":
         """Vectorised equivalent of reference ``Mesh.from_triangulation``

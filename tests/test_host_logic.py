@@ -91,8 +91,10 @@ def test_solver_options_validation_matches_reference():
 def test_device_terminals_and_units():
     layer = tdgl.Layer(london_lambda=2.0, coherence_length=0.5, thickness=0.1)
     film = tdgl.Polygon("film", points=tdgl.box(10, 4))
-    src = tdgl.Polygon("source", points=tdgl.box(0.1, 4, center=(-5, 0)))
-    drn = tdgl.Polygon("drain", points=tdgl.box(0.1, 4, center=(5, 0)))
+    # (thin terminal polygons: boundary edges belong to a terminal when their CENTRES lie in
+    # it, ref device.py:243-245 — the horizontal edges next to the corners must stay out)
+    src = tdgl.Polygon("source", points=tdgl.box(0.02, 4, center=(-5, 0)))
+    drn = tdgl.Polygon("drain", points=tdgl.box(0.02, 4, center=(5, 0)))
     hole = tdgl.Polygon("hole", points=tdgl.circle(0.8, points=40))
     dev = tdgl.Device("bar", layer=layer, film=film, holes=[hole], terminals=[src, drn],
                       probe_points=[(-3, 0), (3, 0)])
@@ -109,6 +111,49 @@ def test_device_terminals_and_units():
     assert abs(dev.Bc2 - 2.067833848e-15 / (2 * np.pi * (0.5e-6) ** 2)) < 1e-12
     assert len(dev.probe_point_indices) == 2
     assert dev == dev.copy()
+
+
+def test_make_mesh_contract_of_the_reference():
+    """Device.make_mesh (ref device.py:520-566, meshing.py:15-123): the result has at least
+    `min_points` vertices and no edge longer than `max_edge_length` (default 1.0 x xi);
+    `smooth` runs Laplacian sweeps that keep the boundary; same seed, same mesh."""
+    layer = tdgl.Layer(london_lambda=2.0, coherence_length=0.5, thickness=0.1)
+    film = tdgl.Polygon("film", points=tdgl.box(10, 4))
+    hole = tdgl.Polygon("hole", points=tdgl.circle(0.8, points=40))
+
+    def device():
+        return tdgl.Device("bar", layer=layer, film=film, holes=[hole])
+
+    def longest(mesh):      # in length units (mesh sites are in units of xi)
+        return mesh.edge_mesh.edge_lengths.max() * layer.coherence_length
+
+    d = device()
+    d.make_mesh()                                         # default: max_edge_length = xi
+    assert longest(d.mesh) <= 0.5 + 1e-12
+    n_default = len(d.mesh.sites)
+    d.make_mesh(max_edge_length=0.2)
+    assert longest(d.mesh) <= 0.2 + 1e-12 and len(d.mesh.sites) > 2 * n_default
+    d.make_mesh(max_edge_length=1.0, min_points=3000)     # min_points decides
+    assert len(d.mesh.sites) >= 3000 and longest(d.mesh) <= 1.0
+    d.make_mesh(max_edge_length=0.1, min_points=100)      # max_edge_length decides
+    assert longest(d.mesh) <= 0.1 + 1e-12
+    d.make_mesh(max_edge_length=-1)                       # polygon point density only
+    seg = 2 * np.pi * 0.8 / 40
+    assert 0.3 * seg < np.median(d.mesh.edge_mesh.edge_lengths) * 0.5 < 3 * seg
+    # smoothing: boundary sites stay, interior sites move, areas still tile the film
+    a, b = device(), device()
+    a.make_mesh(max_edge_length=0.25, reorder=False)
+    b.make_mesh(max_edge_length=0.25, smooth=20, reorder=False)
+    assert a.mesh.elements.shape == b.mesh.elements.shape
+    bi = a.mesh.boundary_indices
+    assert np.array_equal(a.mesh.sites[bi], b.mesh.sites[bi])
+    assert np.abs(a.mesh.sites - b.mesh.sites).max() > 1e-3
+    assert abs(b.mesh.areas.sum() * 0.25 - (40 - np.pi * 0.8**2)) < 0.05
+    # (a smoothed jittered lattice is more uniform: smaller spread of the edge lengths)
+    assert b.mesh.edge_mesh.edge_lengths.std() < a.mesh.edge_mesh.edge_lengths.std()
+    c = device()
+    c.make_mesh(max_edge_length=0.25, smooth=20, reorder=False)
+    assert np.array_equal(b.mesh.sites, c.mesh.sites)
 
 
 def test_saved_steps_dynamics_matches_reference_layout():

@@ -24,6 +24,22 @@ def test_mesh_arrays_match_reference():
     np.testing.assert_allclose(mesh.areas, rm.areas, rtol=1e-12)
 
 
+def test_mesh_smooth_matches_reference():
+    """Mesh.smooth against the unmodified reference's (finite_volume/mesh.py:245-283): the
+    same vertex positions after 1 and 5 Laplacian sweeps, boundary vertices untouched."""
+    mesh, *_ = film_problem(12, 8, 0.4, holes=((2.0, 0.5, 1.5),), reorder=False)
+    rm = rl.make_reference_mesh(mesh.sites, mesh.elements)
+    for it in (1, 5):
+        ours = mesh.smooth(it)
+        theirs = rm.smooth(it)
+        np.testing.assert_allclose(ours.sites, theirs.sites, rtol=0, atol=1e-13)
+        assert np.array_equal(ours.elements, theirs.elements)
+        np.testing.assert_allclose(ours.areas, theirs.areas, rtol=1e-11)
+        b = mesh.boundary_indices
+        assert np.array_equal(ours.sites[b], mesh.sites[b])
+    assert np.abs(mesh.smooth(5).sites - mesh.sites).max() > 1e-3    # it did move
+
+
 @pytest.mark.parametrize("terminals", [False, True])
 def test_oracle_reproduces_reference(terminals):
     ref = rl.load()
