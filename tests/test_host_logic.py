@@ -4,6 +4,7 @@ behaves like the reference (option validation, errors, Runner bookkeeping contai
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -380,3 +381,88 @@ def test_solution_npz_round_trip_keeps_options_and_mesh(tmp_path):
     except ImportError:
         with pytest.raises(ImportError, match="h5py"):
             sol.to_hdf5(str(tmp_path / "out.h5"))
+
+
+class _FakeH5Group(dict):
+    """The slice of the h5py API Solution.to_hdf5 uses (h5py / libhdf5 are not in this image):
+    groups are dicts with an ``attrs`` dict, ``f["a/b/c"] = array`` creates the parents."""
+
+    def __init__(self):
+        super().__init__()
+        self.attrs = {}
+
+    def require_group(self, path):
+        g = self
+        for part in path.split("/"):
+            if part not in g:
+                dict.__setitem__(g, part, _FakeH5Group())
+            g = dict.__getitem__(g, part)
+        return g
+
+    def __setitem__(self, path, value):
+        *parents, leaf = path.split("/")
+        g = self.require_group("/".join(parents)) if parents else self
+        dict.__setitem__(g, leaf, np.asarray(value))
+
+    def __getitem__(self, path):
+        g = self
+        for part in path.split("/"):
+            g = dict.__getitem__(g, part)
+        return g
+
+
+def test_solution_to_hdf5_writes_the_reference_layout(tmp_path, monkeypatch):
+    """Solution.to_hdf5 against a stand-in for h5py: the layout of the reference's files —
+    `data/<k>` groups carrying step / time / dt as ATTRIBUTES and the fields as datasets,
+    `data/<k>/running_state/<name>` (runner.py:155-183), `mesh/...` (mesh.py:345-368), solver
+    options as attributes of `solution/options` (solution.py:874-931)."""
+    import importlib.machinery
+    import types
+
+    from tdgl_b200.solution import Solution
+
+    files = {}
+
+    class File(_FakeH5Group):
+        def __init__(self, path, mode):
+            super().__init__()
+            assert mode == "x"
+            files[path] = self
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    fake = types.ModuleType("h5py")
+    fake.File = File
+    fake.__spec__ = importlib.machinery.ModuleSpec("h5py", None)
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+
+    mesh = make_film_mesh(6, 4, 0.5)
+    n, E = len(mesh.sites), len(mesh.edge_mesh.edges)
+    saved = SavedSteps()
+    saved.save_fixed_values({"epsilon": np.ones(n)})
+    for k in range(2):
+        vals = {"psi": np.full(n, 1.0 + 1j * k), "mu": np.full(n, float(k)),
+                "supercurrent": np.zeros(E), "normal_current": np.zeros(E)}
+        rs = None if k == 0 else {"dt": np.full((1, 3), 1e-3), "mu": np.ones((2, 3))}
+        saved.save_time_step({"step": 3 * k, "time": 3e-3 * k, "dt": 1e-3}, vals, rs)
+    opts = tdgl.SolverOptions(solve_time=1.0, save_every=3)
+    sol = Solution(device=None, options=opts, saved=saved, mesh=mesh, total_seconds=2.0)
+    path = sol.to_hdf5(str(tmp_path / "out.h5"))
+    f = files[path]
+    assert set(f) >= {"data", "mesh", "solution", "epsilon"}
+    assert set(f["data"]) == {"0", "1"}
+    g1 = f["data/1"]
+    assert g1.attrs["step"] == 3 and g1.attrs["time"] == 3e-3 and g1.attrs["dt"] == 1e-3
+    assert "attrs" not in g1                       # attributes, not datasets
+    np.testing.assert_array_equal(g1["psi"], np.full(n, 1.0 + 1j))
+    assert set(g1["running_state"]) == {"dt", "mu"} and "running_state" not in f["data/0"]
+    np.testing.assert_array_equal(f["mesh/edge_mesh/edges"], mesh.edge_mesh.edges)
+    np.testing.assert_array_equal(f["mesh/sites"], mesh.sites)
+    o = f["solution/options"].attrs
+    assert o["save_every"] == 3 and o["solve_time"] == 1.0 and o["sparse_solver"] == "superlu"
+    assert "output_file" not in o                  # None values are not attributes (h5py has no null)
+    assert f["solution"].attrs["total_seconds"] == 2.0
