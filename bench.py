@@ -632,6 +632,50 @@ def run_b200(args, rank, world, local_rank):
                 "traffic": None, "kernels": table, "vcycle_ms": vc_ms,
                 "cusparse_spmv": cusparse}
 
+    # ---- the same kernels INSIDE the stepping loop (one GPU) ------------------------------------
+    # A second engine created under TDGL_B200_TRACE lets the kernels of the CG iteration write
+    # %globaltimer inside the captured CUDA graph (first CTA past griddepcontrol.wait -> last CTA
+    # out, tdgl_get_trace): back to back, warm L2, programmatic dependent launch — what a step
+    # of `value` consists of, which events around a single launch cannot see.  The timeline
+    # costs ~1-3 %, so the timed engine above runs without it.
+    in_loop = None
+    if world == 1 and not args.no_in_loop:
+        try:
+            os.environ["TDGL_B200_TRACE"] = "2"
+            s2 = TDGLSolver.from_dimensionless(
+                mesh, opts, A_applied=work["A"], epsilon=work["eps"], terminal_info=work["terms"],
+                terminal_currents=work["currents"])
+        finally:
+            os.environ.pop("TDGL_B200_TRACE", None)
+        e2 = s2.engine
+        e2.set_state(psi0, mu0)
+        s2.update_mu_boundary(0.0)
+        tr_info = e2.advance(W + K, 1e300, 0, 0.0)
+        tr = e2.get_trace()
+        e2.close()
+        if tr:
+            fine = {"spmv_cg": "kw_real<spmv_cg> fine level", "cg_fused": "k_cg_fused",
+                    "residual": "kw_real<residual> fine level (pre-smoother)",
+                    "jacobi": "kw_real<jacobi> fine level"}
+            rows = {}
+            for t in tr:
+                if t["rows"] == nl and t["name"] in fine:
+                    us = t["t_out"] - t["t_go"]
+                    nb = table[fine[t["name"]]]["bytes"]
+                    rows[fine[t["name"]]] = {"us": us, "bytes": nb, "GBps": nb / us / 1e3,
+                                             "frac": nb / us / 1e3 / peak}
+            in_loop = {
+                "method": "%globaltimer inside the captured CUDA graph of a second, traced engine"
+                          " (TDGL_B200_TRACE, tdgl_get_trace): first CTA past griddepcontrol.wait"
+                          " -> last CTA out, last pass through the loop body",
+                "iteration_us": max(t["t_out"] for t in tr) - min(t["t_in"] for t in tr),
+                "launches_per_iteration": len(tr),
+                "ms_per_step_with_trace": tr_info.device_ms / (W + K),
+                "kernels": rows,
+                "timeline": [[t["name"], t["rows"], round(t["t_in"], 2), round(t["t_go"], 2),
+                              round(t["t_out"], 2)] for t in tr]}
+    roofline["in_loop"] = in_loop
+
     if shard and args.strong_record:
         eng.close()
         strong = strong_record(args, rank, world, local_rank, dist, barrier, torch)
@@ -692,6 +736,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=240.0,
                     help="seconds of CPU stepping allowed for the cpu baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-in-loop", action="store_true",
+                    help="skip the in-loop timeline of the CG iteration's kernels (second engine)")
     ap.add_argument("--developed-steps", type=int, default=2000,
                     help="untimed device steps before the `developed` re-measurement (0: skip)")
     ap.add_argument("--mode", default="weak", choices=["weak", "strong", "replicas"],

@@ -291,6 +291,18 @@ int tdgl_time_cusparse(tdgl_handle* h, int32_t which, int32_t reps, int32_t flus
  * [7] graph mode actually in use (1/2). */
 int tdgl_get_info(tdgl_handle* h, int64_t* out, int32_t n);
 
+/* Measurement only: the in-loop timeline of the kernels of the CG iteration (V-cycle, SpMV,
+ * vector update).  A handle created while the environment variable TDGL_B200_TRACE is set (1:
+ * also printed to stderr after every tdgl_advance, 2: recorded only) lets these kernels write
+ * %globaltimer when their first CTA becomes resident (in), when it passes griddepcontrol.wait
+ * (go: the predecessor has drained) and when their last CTA is done (out) — inside the captured
+ * CUDA graph, i.e. back to back with warm caches, which no host-side timer can see.  Returns
+ * the launches passed since the last call (the LAST pass through each slot of a loop body),
+ * ordered by `in`, times in microseconds from the earliest `in`; names: capacity x 64 chars.
+ * n_out = 0 when the handle was created without the variable. */
+int tdgl_get_trace(tdgl_handle* h, int32_t capacity, int32_t* n_out, char* names, double* in_us,
+                   double* go_us, double* out_us, int64_t* counts);
+
 /* ---- domain decomposition (no counterpart in the reference) ------
  * A handle created with tdgl_config.world = P > 1 computes shard `rank` of the mesh: every
  * rank passes the SAME whole-mesh arrays to tdgl_create (and to the tdgl_set_* calls); the

@@ -109,6 +109,7 @@ SIGNATURES = {
     "tdgl_time_kernel": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_D)]),
     "tdgl_time_cusparse": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(_D)]),
     "tdgl_get_info": (C.c_int, [_P, C.POINTER(_I64), _I32]),
+    "tdgl_get_trace": (C.c_int, [_P, _I32, C.POINTER(_I32), _P, _P, _P, _P, _P]),
     "tdgl_comm_export": (C.c_int, [_P, _P]),
     "tdgl_comm_connect_ipc": (C.c_int, [_P, _P, _I32]),
     "tdgl_comm_connect_local": (C.c_int, [_P, C.POINTER(_P), _I32]),

@@ -376,11 +376,14 @@ class Engine {
   // debug timeline (TDGL_B200_TRACE=1): one slot per enqueued (captured) launch of the CG
   // iteration's kernels; trace_report() prints the last pass through every slot
   bool trace_on_ = false;
+  bool trace_print_ = false;
   DevBuf<unsigned long long> trace_;
   std::vector<std::string> trace_names_;
   int trace_slot(const char* name, int rows);
  public:
   void trace_report();
+  int trace_collect(int capacity, char* names, double* in_us, double* go_us, double* out_us,
+                    int64_t* counts);
  private:
   template <typename... KArgs, typename... Args>
   void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {

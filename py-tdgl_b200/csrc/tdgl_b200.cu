@@ -540,7 +540,9 @@ Engine::Engine(int64_t n_sites, int64_t n_edges, int64_t n_bedges, const int64_t
   h_ctl_->n_probe = nprobe_; h_ctl_->running_capacity = cfg_.running_capacity;
   h_ctl_->tentative_dt = 1e-6; h_ctl_->dt = 1e-6;
   h_ctl_->solve_epoch = 1; h_ctl_->psi_epoch = 1; h_ctl_->psi_tag[0] = h_ctl_->psi_tag[1] = 1;
-  if (const char* e = std::getenv("TDGL_B200_TRACE")) trace_on_ = e[0] != '0';
+  // TDGL_B200_TRACE=1: record the timeline and print it after every advance; =2: record only
+  // (read back with tdgl_get_trace)
+  if (const char* e = std::getenv("TDGL_B200_TRACE")) { trace_on_ = e[0] != '0'; trace_print_ = e[0] == '1'; }
   if (trace_on_) {
     trace_.alloc(4 * 512);
     trace_.zero(stream_);
@@ -787,6 +789,36 @@ void Engine::trace_report() {
             trace_names_[i].c_str(), in, go, out, go - in, out - go, h[4 * i + 3]);
   }
   TDGL_CUDA(cudaMemset(trace_.p, 0, sizeof(unsigned long long) * trace_.n));
+}
+
+// The same data for the caller (tdgl_get_trace): the traced launches passed since the last call,
+// ordered by first-CTA-in time; times in microseconds from the earliest one.  Clears the record.
+int Engine::trace_collect(int capacity, char* names, double* in_us, double* go_us, double* out_us,
+                          int64_t* counts) {
+  if (!trace_on_ || trace_names_.size() < 2) return 0;
+  TDGL_CUDA(cudaStreamSynchronize(stream_));
+  std::vector<unsigned long long> h(4 * trace_names_.size());
+  TDGL_CUDA(cudaMemcpy(h.data(), trace_.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+  std::vector<int> order;
+  unsigned long long t0 = ~0ull;
+  for (size_t i = 1; i < trace_names_.size(); ++i)
+    if (h[4 * i + 3] > 0) { order.push_back(static_cast<int>(i)); t0 = std::min(t0, h[4 * i]); }
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return h[4 * a] < h[4 * b]; });
+  int n = 0;
+  for (int i : order) {
+    if (n >= capacity) break;
+    if (names != nullptr) {
+      std::memset(names + 64 * n, 0, 64);
+      std::strncpy(names + 64 * n, trace_names_[i].c_str(), 63);
+    }
+    if (in_us != nullptr) in_us[n] = (h[4 * i] - t0) * 1e-3;
+    if (go_us != nullptr) go_us[n] = (h[4 * i + 1] - t0) * 1e-3;
+    if (out_us != nullptr) out_us[n] = (h[4 * i + 2] - t0) * 1e-3;
+    if (counts != nullptr) counts[n] = static_cast<int64_t>(h[4 * i + 3]);
+    ++n;
+  }
+  TDGL_CUDA(cudaMemset(trace_.p, 0, sizeof(unsigned long long) * trace_.n));
+  return n;
 }
 
 static const char* real_op_name(int op) {
@@ -1622,7 +1654,7 @@ Engine::AdvanceInfo Engine::advance(int64_t max_steps, double t_end, int64_t ste
   TDGL_CUDA(cudaEventSynchronize(ev1_));
   float dev_ms = 0.f;
   TDGL_CUDA(cudaEventElapsedTime(&dev_ms, ev0_, ev1_));
-  if (trace_on_) trace_report();
+  if (trace_on_ && trace_print_) trace_report();
   return collect_advance(dev_ms);
 }
 
@@ -2734,6 +2766,13 @@ int tdgl_time_cusparse(tdgl_handle* h, int32_t which, int32_t reps, int32_t flus
 }
 int tdgl_get_info(tdgl_handle* h, int64_t* out, int32_t n) {
   return guarded(h, [&](tdgl::Engine& e) { e.get_info(out, n); });
+}
+int tdgl_get_trace(tdgl_handle* h, int32_t capacity, int32_t* n_out, char* names, double* in_us,
+                   double* go_us, double* out_us, int64_t* counts) {
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (n_out == nullptr || capacity < 0) throw std::invalid_argument("bad trace buffers");
+    *n_out = e.trace_collect(capacity, names, in_us, go_us, out_us, counts);
+  });
 }
 
 int tdgl_comm_export(tdgl_handle* h, void* handle_out) {

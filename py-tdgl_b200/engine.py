@@ -418,6 +418,27 @@ class DeviceEngine:
                                                  1 if flush_l2 else 0, C.byref(ms)))
         return ms.value
 
+    def get_trace(self, capacity: int = 512):
+        """In-loop timeline of the CG iteration's kernels (``tdgl_get_trace``; needs the engine
+        to have been created under ``TDGL_B200_TRACE``): list of dicts with name, rows, in / go /
+        out in microseconds from the earliest launch of the pass, and the pass count."""
+        n = C.c_int32(0)
+        names = C.create_string_buffer(64 * capacity)
+        t_in = np.zeros(capacity)
+        t_go = np.zeros(capacity)
+        t_out = np.zeros(capacity)
+        cnt = np.zeros(capacity, dtype=np.int64)
+        self._check(self._lib.tdgl_get_trace(self._h, capacity, C.byref(n), names, ptr(t_in),
+                                             ptr(t_go), ptr(t_out), ptr(cnt)))
+        out = []
+        for k in range(n.value):
+            label = names.raw[64 * k:64 * (k + 1)].split(b"\0", 1)[0].decode()
+            name, _, rows = label.partition("rows=")
+            out.append(dict(name=name.strip(), rows=int(rows) if rows.strip() else 0,
+                            t_in=float(t_in[k]), t_go=float(t_go[k]), t_out=float(t_out[k]),
+                            count=int(cnt[k])))
+        return out
+
     def info(self) -> dict:
         out = (C.c_int64 * 8)()
         self._check(self._lib.tdgl_get_info(self._h, out, 8))
