@@ -18,7 +18,8 @@ b200 arm
           own step seam (tdgl/solver/runner.py:417-423) — with host psi/mu in pinned
           memory copied to the device and psi', mu', J_s, J_n copied back EVERY step.
   roofline  dominant kernel of the step, timed on its own with CUDA events after an L2
-          flush; algorithmic bytes per DESIGN.md.
+          flush; algorithmic bytes per DESIGN.md.  roofline.in_loop: the same kernels'
+          durations INSIDE the stepping CUDA graph (%globaltimer, tdgl_get_trace).
   cpu_baseline  the oracle port of the reference's scipy.sparse/SuperLU step on this
           box's host cores (N=1 only; bounded number of steps of the same workload).
 reference arm (--impl reference): that CPU path alone, same workload/metric.
@@ -637,7 +638,7 @@ def run_b200(args, rank, world, local_rank):
     # %globaltimer inside the captured CUDA graph (first CTA past griddepcontrol.wait -> last CTA
     # out, tdgl_get_trace): back to back, warm L2, programmatic dependent launch — what a step
     # of `value` consists of, which events around a single launch cannot see.  The timeline
-    # costs ~1-3 %, so the timed engine above runs without it.
+    # costs ~5 % (2.02 -> 2.14 ms/step), so the timed engine above runs without it.
     in_loop = None
     if world == 1 and not args.no_in_loop:
         try:
