@@ -84,6 +84,8 @@ struct Ctl {
   double ramp_f;       // f at the current step
   double ramp_dfdt;    // (f(t) - f(t_prev)) / dt_prev, the reference's backward difference
   double ramp_t[kMaxKnots], ramp_v[kMaxKnots];
+  double ramp_amax;    // max |component of A0|: decides the reference's allclose() test, see k_step_begin
+  double ramp_f_links; // f of the last rebuild of the link variables (what the operators hold)
   // --- debug timeline (TDGL_B200_TRACE=1): 4 words per traced launch {first CTA in, first CTA
   //     past griddepcontrol.wait, last CTA out, launches}, %globaltimer ns; null = off ----------
   unsigned long long* trace;
@@ -195,7 +197,7 @@ __device__ __forceinline__ bool grid_sum_last(double partial, double* partials,
 // them at different times — every barrier is a wait for the slowest warp): warp sums -> shared
 // memory -> thread 0 adds them in warp order and publishes the block's pair -> last block adds
 // the pairs in block order.  v0 / v1: every thread's contributions.  Same contract as
-// grid_sum2_last otherwise (smem: >= 64 doubles).
+// grid_sum_last otherwise (smem: >= 64 doubles).
 __device__ __forceinline__ bool grid_sum2_fused(double v0, double v1, double* partials,
                                                 unsigned int* counter, double* smem, double* t0,
                                                 double* t1) {
@@ -216,47 +218,6 @@ __device__ __forceinline__ bool grid_sum2_fused(double v0, double v1, double* pa
   }
   __syncthreads();
   if (!s_last2f) return false;
-  __threadfence();
-  double a0 = 0.0, a1 = 0.0;
-  const double2* p2 = reinterpret_cast<const double2*>(partials);
-  const unsigned int n = gridDim.x, bd = blockDim.x;
-  unsigned int i = threadIdx.x;
-  for (; i + 7u * bd < n; i += 8u * bd) {
-    double2 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldcg(p2 + i + k * bd);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { a0 += v[k].x; a1 += v[k].y; }
-  }
-  for (; i < n; i += bd) {
-    const double2 v = __ldcg(p2 + i);
-    a0 += v.x;
-    a1 += v.y;
-  }
-  a0 = block_sum(a0, smem);
-  a1 = block_sum(a1, smem);
-  if (threadIdx.x == 0) {
-    *t0 = a0;
-    *t1 = a1;
-    *counter = 0u;
-  }
-  return true;
-}
-
-// Two sums through one pass (partials interleaved, 2 per block); same contract.
-__device__ __forceinline__ bool grid_sum2_last(double p0, double p1, double* partials,
-                                               unsigned int* counter, double* smem,
-                                               double* t0, double* t1) {
-  __shared__ int s_last2;
-  if (threadIdx.x == 0) {
-    partials[2 * blockIdx.x] = p0;
-    partials[2 * blockIdx.x + 1] = p1;
-    __threadfence();
-    const unsigned int t = atomicAdd(counter, 1u);
-    s_last2 = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last2) return false;
   __threadfence();
   double a0 = 0.0, a1 = 0.0;
   const double2* p2 = reinterpret_cast<const double2*>(partials);
@@ -604,8 +565,17 @@ __global__ void k_step_begin(Ctl* ctl, cudaGraphConditionalHandle cond_psi,
       f = ctl->ramp_v[k] + w * (ctl->ramp_v[k + 1] - ctl->ramp_v[k]);
     }
     ctl->ramp_dfdt = (f - ctl->ramp_f) / ctl->dt;
-    ctl->ramp_changed = (f != ctl->ramp_f) || ctl->ramp_changed == 2;  // 2: forced (set-up)
+    // The reference rebuilds the link variables only `if not allclose(A_new, A_prev)`
+    // (solver.py:635-638; numpy's rtol = 1e-5, atol = 1e-8; A_prev = the previous step's A
+    // whether or not it was used), i.e. when some component violates
+    // |df| |A0| <= atol + rtol |f_prev| |A0|.  With A = f A0 the component with the largest |A0|
+    // decides: rebuild iff (|df| - rtol |f_prev|) max|A0| > atol.  (A slow ramp therefore keeps
+    // the link variables of an older f — the reference's behaviour, reproduced on purpose.)
+    const double df = fabs(f - ctl->ramp_f);
+    const bool moved = (df - 1e-5 * fabs(ctl->ramp_f)) * ctl->ramp_amax > 1e-8;
+    ctl->ramp_changed = moved || ctl->ramp_changed == 2;  // 2: forced (set-up)
     ctl->ramp_f = f;
+    if (ctl->ramp_changed) ctl->ramp_f_links = f;
   }
   if (ctl->cur_on) {
     // update_mu_boundary (solver.py:325-345): J_ext,k = -(1 / L_k) sum_{j != k} I_j(t)
@@ -891,8 +861,11 @@ __global__ void k_currents(int ne, const int* __restrict__ elist /* null: all ed
   if (psi == nullptr) psi = ctl->cur ? psi_buf1 : psi_buf0;
   const double inv_l = 1.0 / elen[e];
   double s, c;
-  // (device-side ramp: theta holds A0 . d, the current A is ramp_f * A0)
-  double th = ramp_proj != nullptr ? ctl->ramp_f * theta[e] : theta[e];
+  // (device-side ramp: theta holds A0 . d; the gradient operator carries the link exponents of
+  // the last rebuild, ramp_f_links * A0, like the reference's — with screening they are rebuilt
+  // every pass from the current A, ramp_f * A0)
+  double th = theta[e];
+  if (ramp_proj != nullptr) th *= (aind != nullptr) ? ctl->ramp_f : ctl->ramp_f_links;
   if (aind != nullptr) th += aind[e].x * edir[e].x + aind[e].y * edir[e].y;
   sincos(-th, &s, &c);
   const double2 pi = psi[i], pj = psi[j];

@@ -1474,7 +1474,11 @@ void Engine::set_ramp(const double* A0, int n_knots, const double* t_knots, cons
       f0 = f_knots[k] + (0.0 - t_knots[k]) / (t_knots[k + 1] - t_knots[k]) * (f_knots[k + 1] - f_knots[k]);
     }
     h_ctl_->ramp_f = f0;
+    h_ctl_->ramp_f_links = f0;
     h_ctl_->ramp_dfdt = 0.0;
+    double amax = 0.0;
+    for (size_t k = 0; k < 2 * static_cast<size_t>(E_); ++k) amax = std::max(amax, std::fabs(A0[k]));
+    h_ctl_->ramp_amax = amax;
     h_ctl_->ramp_changed = 2;   // the first step builds the link variables
     push_ctl();
   }
