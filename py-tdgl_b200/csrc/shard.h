@@ -62,6 +62,97 @@ inline std::vector<int64_t> equal_offsets(int64_t n, int world) {
   return off;
 }
 
+// ---- site numbering ---------------------------------------------------------------------------
+// Z-order (Morton) numbering of the sites: a window of consecutive CSR rows references mostly
+// itself, and a contiguous range of the numbering is a compact subdomain.
+inline std::vector<int> morton_permutation(const double* xy, int64_t n) {
+  double xmin = xy[0], xmax = xy[0], ymin = xy[1], ymax = xy[1];
+  for (int64_t i = 0; i < n; ++i) {
+    xmin = std::min(xmin, xy[2 * i]); xmax = std::max(xmax, xy[2 * i]);
+    ymin = std::min(ymin, xy[2 * i + 1]); ymax = std::max(ymax, xy[2 * i + 1]);
+  }
+  const double span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-300);
+  auto spread = [](uint64_t v) {
+    v &= 0xFFFFFFFFull;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+  };
+  std::vector<std::pair<uint64_t, int>> key(n);
+  const double scale = static_cast<double>((1u << 20) - 1) / span;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t qx = static_cast<uint64_t>((xy[2 * i] - xmin) * scale);
+    const uint64_t qy = static_cast<uint64_t>((xy[2 * i + 1] - ymin) * scale);
+    key[i] = {spread(qx) | (spread(qy) << 1), static_cast<int>(i)};
+  }
+  // (keys are unique pairs: chunk sorts + merges give the same order as one sort)
+  const int chunks = chunks_for(n, 1 << 17);
+  std::vector<int64_t> cut(chunks + 1);
+  for (int c = 0; c <= chunks; ++c) cut[c] = n * c / chunks;
+  parallel_chunks(n, chunks, [&](int, int64_t lo, int64_t hi) { std::sort(key.begin() + lo, key.begin() + hi); });
+  for (int width = 1; width < chunks; width *= 2) {
+    const int pairs = (chunks + 2 * width - 1) / (2 * width);
+    parallel_chunks(pairs, pairs, [&](int, int64_t p0, int64_t p1) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int a = static_cast<int>(p) * 2 * width, m = std::min(a + width, chunks), b = std::min(a + 2 * width, chunks);
+        if (m < b) std::inplace_merge(key.begin() + cut[a], key.begin() + cut[m], key.begin() + cut[b]);
+      }
+    });
+  }
+  std::vector<int> perm(n);
+  for (int64_t i = 0; i < n; ++i) perm[i] = key[i].second;
+  return perm;
+}
+
+// Sharded numbering: Z-order, cut into `world` equal ranges, and inside every range the rows
+// near the cut (within `depth` edges of a row of another range) moved to the front.  A rank's
+// kernels then compute — and store into the neighbours' mailboxes — the rows the neighbours
+// wait for FIRST, and the CTAs that read halo columns (the same rows) run while the
+// neighbour's matching stores, issued at the start of its previous kernel, have long landed:
+// the exchange has a whole kernel of slack instead of sitting on the critical path.
+inline std::vector<int> shard_permutation(const double* xy, int64_t n, int64_t n_edges,
+                                          const int64_t* edges, int world, int depth = 2) {
+  std::vector<int> perm = morton_permutation(xy, n);
+  if (world <= 1) return perm;
+  std::vector<int> inv(n);
+  for (int64_t i = 0; i < n; ++i) inv[perm[i]] = static_cast<int>(i);
+  std::vector<int64_t> off(world + 1);
+  for (int r = 0; r <= world; ++r) off[r] = n * r / world;
+  auto owner = [&](int pos) {
+    return static_cast<int>(std::upper_bound(off.begin(), off.end(), static_cast<int64_t>(pos)) - off.begin()) - 1;
+  };
+  // level[pos]: 0 = not near a cut, k = reached in the k-th sweep
+  std::vector<unsigned char> near(n, 0);
+  for (int64_t e = 0; e < 2 * n_edges; ++e)
+    if (edges[e] < 0 || edges[e] >= n) throw std::invalid_argument("edge index out of range");
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int a = inv[edges[2 * e]], b = inv[edges[2 * e + 1]];
+    if (owner(a) != owner(b)) near[a] = near[b] = 1;
+  }
+  for (int d = 2; d <= depth; ++d) {
+    std::vector<unsigned char> next(near);
+    for (int64_t e = 0; e < n_edges; ++e) {
+      const int a = inv[edges[2 * e]], b = inv[edges[2 * e + 1]];
+      if (owner(a) != owner(b)) continue;
+      if (near[a] && !near[b]) next[b] = static_cast<unsigned char>(d);
+      if (near[b] && !near[a]) next[a] = static_cast<unsigned char>(d);
+    }
+    near.swap(next);
+  }
+  std::vector<int> out(n);
+  for (int r = 0; r < world; ++r) {
+    int64_t w = off[r];
+    for (int64_t p = off[r]; p < off[r + 1]; ++p)
+      if (near[p]) out[w++] = perm[p];
+    for (int64_t p = off[r]; p < off[r + 1]; ++p)
+      if (!near[p]) out[w++] = perm[p];
+  }
+  return out;
+}
+
 // Adds to halo[r] the non-owned columns of the rows row_off[r]..row_off[r+1] of G, whose
 // columns live on a level partitioned by col_off.
 inline void collect_halo(const HostCsr<double>& G, const std::vector<int64_t>& row_off,
@@ -131,15 +222,17 @@ inline HostCsr<double> extract_rows(const HostCsr<double>& G, const std::vector<
   for (int64_t i = 0; i < L.rows; ++i) L.ptr[i + 1] = L.ptr[i] + (G.ptr[rows[i] + 1] - G.ptr[rows[i]]);
   L.idx.resize(L.ptr[L.rows]);
   L.val.resize(L.ptr[L.rows]);
-  for (int64_t i = 0; i < L.rows; ++i) {
-    int32_t d = L.ptr[i];
-    for (int32_t k = G.ptr[rows[i]]; k < G.ptr[rows[i] + 1]; ++k, ++d) {
-      const int64_t li = plan.local_index(cl, rank, G.idx[k]);
-      if (li < 0) throw std::runtime_error("halo plan misses a column");
-      L.idx[d] = static_cast<int32_t>(li);
-      L.val[d] = G.val[k];
+  parallel_chunks(L.rows, chunks_for(L.rows), [&](int, int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      int32_t d = L.ptr[i];
+      for (int32_t k = G.ptr[rows[i]]; k < G.ptr[rows[i] + 1]; ++k, ++d) {
+        const int64_t li = plan.local_index(cl, rank, G.idx[k]);
+        if (li < 0) throw std::runtime_error("halo plan misses a column");
+        L.idx[d] = static_cast<int32_t>(li);
+        L.val[d] = G.val[k];
+      }
     }
-  }
+  });
   return L;
 }
 

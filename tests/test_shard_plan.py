@@ -178,3 +178,29 @@ def test_shard_plan_edge_cases(problem):
     g = host_amg_probe(mesh, rhs=rhs)
     assert one["iterations"] == g["iterations"] and one["halo_sizes"].sum() == 0
     np.testing.assert_allclose(one["x"], g["x"], rtol=0, atol=1e-9 * np.abs(g["x"]).max())
+
+
+def test_setup_is_bitwise_independent_of_the_thread_count(monkeypatch):
+    """The setup-time loops (site graph, power iteration, sparse products, Z-order sort, shard
+    extraction: csrc/host_csr.h `parallel_chunks`) split rows over host threads; every rank
+    of a sharded run must still build the SAME hierarchy, whatever cores it was given.  The
+    host probes run the whole setup + AMG-PCG, so equal solutions bit for bit and equal
+    permutations / halo plans mean equal hierarchies."""
+    mesh = film_problem(110, 100, 0.4, b=0.1, holes=((5.0, 3.0, 9.0),))[0]   # ~79k sites
+    assert len(mesh.sites) > 4 * 16384   # enough rows for several chunks
+    rng = np.random.default_rng(5)
+    rhs = _sym_mu_matrix(mesh) @ rng.normal(size=len(mesh.sites))
+    got = {}
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("TDGL_B200_HOST_THREADS", threads)
+        got[threads] = (host_amg_probe(mesh, rhs=rhs), host_shard_probe(mesh, 4, rhs=rhs))
+    g1, p1 = got["1"]
+    for threads in ("3", "8"):
+        g, p = got[threads]
+        assert g["rows"] == g1["rows"] and g["nnz"] == g1["nnz"]
+        assert g["iterations"] == g1["iterations"] and p["iterations"] == p1["iterations"]
+        assert np.array_equal(g["x"], g1["x"])
+        assert np.array_equal(p["x"], p1["x"])
+        assert np.array_equal(p["perm"], p1["perm"])
+        assert np.array_equal(p["offsets"], p1["offsets"])
+        assert np.array_equal(p["halo_sizes"], p1["halo_sizes"])
