@@ -132,14 +132,7 @@ inline void dense_spd_inverse(std::vector<double>& M, int64_t n) {
       for (int64_t i = 0; i < n; ++i) M[i * n + c] = x[i];
     }
   };
-  const int64_t nt = n < 256 ? 1 : std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
-  if (nt <= 1) {
-    columns(0, n);
-  } else {
-    std::vector<std::thread> pool;
-    for (int64_t t = 0; t < nt; ++t) pool.emplace_back(columns, n * t / nt, n * (t + 1) / nt);
-    for (auto& th : pool) th.join();
-  }
+  parallel_chunks(n, n < 256 ? 1 : host_threads(), [&](int, int64_t c0, int64_t c1) { columns(c0, c1); });
   // symmetrise against roundoff
   for (int64_t i = 0; i < n; ++i)
     for (int64_t j = i + 1; j < n; ++j) {

@@ -13,6 +13,7 @@
 #include <numeric>
 #include <cstdlib>
 #include <stdexcept>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -44,7 +45,11 @@ inline void parallel_chunks(int64_t n, int chunks, F&& fn) {
   auto run = [&](int c) {
     try { fn(c, n * c / chunks, n * (c + 1) / chunks); } catch (...) { err[c] = std::current_exception(); }
   };
-  for (int c = 0; c + 1 < chunks; ++c) pool.emplace_back(run, c);
+  pool.reserve(chunks);
+  for (int c = 0; c + 1 < chunks; ++c) {
+    // (no thread to be had — a pids limit, say: the chunk runs here)
+    try { pool.emplace_back(run, c); } catch (const std::system_error&) { run(c); }
+  }
   run(chunks - 1);
   for (auto& t : pool) t.join();
   for (auto& e : err) if (e) std::rethrow_exception(e);
