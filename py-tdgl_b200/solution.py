@@ -240,6 +240,20 @@ class Solution:
         out["solution/time_created"] = np.array(self._time_created.isoformat())
         return out
 
+    def save(self, path: str) -> str:
+        """What ``SolverOptions.output_file`` means here: the reference's HDF5 layout when h5py
+        can be imported and the name does not end in ``.npz``, otherwise the same tree as one
+        ``.npz`` (said in the log, because the file then is not what the name promises)."""
+        import importlib.util
+        import logging
+
+        if not path.endswith(".npz") and importlib.util.find_spec("h5py") is not None:
+            return self.to_hdf5(path)
+        if not path.endswith(".npz"):
+            logging.getLogger("solver").warning(
+                "h5py is not installed: writing %s.npz (same tree of keys as the HDF5 file)", path)
+        return self.to_npz(path)
+
     def to_npz(self, path: str) -> str:
         """Write the tree of :meth:`_tree` to one compressed ``.npz`` (h5py / libhdf5 are not
         part of this image; :meth:`to_hdf5` writes the same tree when they are)."""

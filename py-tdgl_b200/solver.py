@@ -502,9 +502,9 @@ class TDGLSolver:
         solver.py:580-714), i.e. the function ``Runner._run_stage`` calls once per step
         (runner.py:417-423): host ``psi`` / ``mu`` in, ``SolverResult`` of host arrays out.
         ``supercurrent`` / ``normal_current`` inputs are ignored as in the reference; ``dt``
-        (the previous step's dt) only matters for time-dependent vector potentials, which
-        this path does not take.  ``solve()`` does not use this seam — it keeps the state
-        on the device between save steps."""
+        (the previous step's dt) only matters for time-dependent vector potentials (the
+        backward difference dA/dt, solver.py:632).  ``solve()`` does not use this seam — it
+        keeps the state on the device between save steps."""
         step, time = int(state["step"]), float(state["time"])
         self.update_mu_boundary(time)
         self._update_vector_potential(time, float(dt), applied_vector_potential)
@@ -735,7 +735,7 @@ class TDGLSolver:
             total_seconds=(end_time - start_time).total_seconds(),
             solver_stats=dict(self.stats, **self.engine.info()), mesh=self.mesh)
         if opts.output_file is not None:
-            solution.to_npz(opts.output_file)
+            solution.save(opts.output_file)
         return solution
 
 

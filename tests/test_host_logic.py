@@ -466,3 +466,28 @@ def test_solution_to_hdf5_writes_the_reference_layout(tmp_path, monkeypatch):
     assert o["save_every"] == 3 and o["solve_time"] == 1.0 and o["sparse_solver"] == "superlu"
     assert "output_file" not in o                  # None values are not attributes (h5py has no null)
     assert f["solution"].attrs["total_seconds"] == 2.0
+
+
+def test_solution_save_picks_the_backend(tmp_path, caplog):
+    """``SolverOptions.output_file`` goes through ``Solution.save``: HDF5 when h5py exists,
+    otherwise the npz tree under ``<name>.npz`` with a warning (never a silent change)."""
+    import importlib.util
+    import logging
+
+    from tdgl_b200.solution import SavedSteps, Solution
+
+    mesh = make_film_mesh(6, 4, 0.5)
+    n, E = len(mesh.sites), len(mesh.edge_mesh.edges)
+    saved = SavedSteps()
+    saved.save_fixed_values({"epsilon": np.ones(n)})
+    saved.save_time_step({"step": 0, "time": 0.0, "dt": 1e-3},
+                         {"psi": np.ones(n, complex), "mu": np.zeros(n),
+                          "supercurrent": np.zeros(E), "normal_current": np.zeros(E)}, None)
+    sol = Solution(device=None, options=tdgl.SolverOptions(solve_time=1.0), saved=saved, mesh=mesh)
+    assert sol.save(str(tmp_path / "a.npz")) == str(tmp_path / "a.npz")
+    if importlib.util.find_spec("h5py") is None:
+        with caplog.at_level(logging.WARNING, logger="solver"):
+            path = sol.save(str(tmp_path / "b.h5"))
+        assert path == str(tmp_path / "b.h5.npz") and os.path.exists(path)
+        assert any("h5py is not installed" in r.message for r in caplog.records)
+        np.testing.assert_array_equal(Solution.from_npz(path).tdgl_data.psi, np.ones(n))
