@@ -338,6 +338,21 @@ int tdgl_shard_info(tdgl_handle* h, int64_t* out, int32_t n);
 
 /* ---- host-only helpers (no GPU needed): used by CPU tests ---------------------------- */
 
+/* Finite-volume (dual) mesh arrays of a triangulation — what the reference computes in
+ * Mesh.from_triangulation / EdgeMesh.from_mesh (tdgl/finite_volume/mesh.py:104-151,
+ * edge_mesh.py:54-92, util.py:15-28,59-124) with Python loops: unique sorted edges, the
+ * is-boundary flag (edge of exactly one triangle), circumcentres, edge centres / directions /
+ * lengths, dual (Voronoi) edge lengths, and per site the sum of length * dual_length / 4 over
+ * its edges (the Voronoi area of an interior site; the caller redoes boundary sites with the
+ * reference's convex-hull convention).  Multi-threaded; the edge arrays need room for
+ * 3 * n_triangles rows, *n_edges returns the number filled. */
+int tdgl_host_mesh_dual(int64_t n_sites, int64_t n_triangles, const double* sites_xy,
+                        const int64_t* elements /* [n_triangles,3] */, int64_t* n_edges,
+                        int64_t* edges /* [.,2] */, uint8_t* is_boundary,
+                        double* dual_sites /* [n_triangles,2] */, double* centers /* [.,2] */,
+                        double* directions /* [.,2] */, double* edge_lengths,
+                        double* dual_edge_lengths, double* areas /* [n_sites] */);
+
 /* Builds the AMG hierarchy on the host and reports per-level sizes; optionally applies
  * `n_cycles` of preconditioned CG on the host to rhs to validate the hierarchy.
  * level_rows/level_nnz have room for 32 entries. */

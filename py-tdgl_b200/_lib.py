@@ -121,6 +121,8 @@ SIGNATURES = {
                                         C.POINTER(_I32)]),
     "tdgl_host_shard_lists": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P,
                                         _P]),
+    "tdgl_host_mesh_dual": (C.c_int, [_I64, _I64, _P, _P, C.POINTER(_I64), _P, _P, _P, _P, _P,
+                                      _P, _P, _P]),
     "tdgl_host_amg_probe": (C.c_int, [_I64, _I64, _P, _P, _P, _D, _I32, C.POINTER(_I32),
                                       C.POINTER(_I64), C.POINTER(_I64), _P, _P, _I32, _D,
                                       C.POINTER(_I32)]),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "engine.h"
+#include "host_mesh.h"
 
 namespace tdgl {
 
@@ -2729,6 +2730,25 @@ int tdgl_comm_connect_local(tdgl_handle* h, tdgl_handle* const* peers, int32_t w
 }
 int tdgl_shard_info(tdgl_handle* h, int64_t* out, int32_t n) {
   return guarded(h, [&](tdgl::Engine& e) { e.shard_info(out, n); });
+}
+
+int tdgl_host_mesh_dual(int64_t n_sites, int64_t n_triangles, const double* sites_xy,
+                        const int64_t* elements, int64_t* n_edges, int64_t* edges,
+                        uint8_t* is_boundary, double* dual_sites, double* centers,
+                        double* directions, double* edge_lengths, double* dual_edge_lengths,
+                        double* areas) {
+  try {
+    if (!sites_xy || !elements || !n_edges || !edges || !is_boundary || !dual_sites || !centers ||
+        !directions || !edge_lengths || !dual_edge_lengths || !areas)
+      throw std::invalid_argument("null argument");
+    *n_edges = tdgl::build_dual_mesh(n_sites, n_triangles, sites_xy, elements, edges, is_boundary,
+                                     dual_sites, centers, directions, edge_lengths,
+                                     dual_edge_lengths, areas);
+    return TDGL_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return TDGL_E_INVALID;
+  }
 }
 
 int tdgl_host_amg_probe(int64_t n_sites, int64_t n_edges, const int64_t* edges,

@@ -10,6 +10,7 @@ NumPy (the reference loops over edges and sites in Python, ``util.py:59-97,169-2
 
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -118,15 +119,54 @@ class Mesh:
 
     @staticmethod
     def from_triangulation(sites, elements, create_submesh: bool = True) -> "Mesh":
-        """Vectorised equivalent of reference ``Mesh.from_triangulation``
-        (``mesh.py:104-151``) + ``EdgeMesh.from_mesh`` (``edge_mesh.py:54-92``)."""
-        sites = np.asarray(sites, dtype=np.float64).squeeze()
-        elements = np.asarray(elements, dtype=np.int64).squeeze()
-        if sites.ndim != 2 or sites.shape[1] != 2:
-            raise ValueError(
-                f"The site coordinates must have shape (n, 2), got {sites.shape!r}")
-        if elements.ndim != 2 or elements.shape[1] != 3:
-            raise ValueError(f"The elements must have shape (m, 3), got {elements.shape!r}.")
+        """Equivalent of reference ``Mesh.from_triangulation`` (``mesh.py:104-151``) +
+        ``EdgeMesh.from_mesh`` (``edge_mesh.py:54-92``): the edge / dual-mesh arrays come from
+        the library's multi-threaded host builder (``tdgl_host_mesh_dual``,
+        ``csrc/host_mesh.h``), the Voronoi areas of the boundary sites from
+        :func:`_voronoi_areas`.  :meth:`_from_triangulation_numpy` is the same construction
+        in vectorised NumPy and gives the same arrays bit for bit (tests)."""
+        sites, elements = _check_triangulation(sites, elements)
+        if not create_submesh or len(elements) == 0:
+            return Mesh._from_triangulation_numpy(sites, elements, create_submesh)
+        from . import _lib
+
+        lib = _lib.load()
+        n, T = len(sites), len(elements)
+        sites = np.ascontiguousarray(sites)
+        elements = np.ascontiguousarray(elements)
+        cap = 3 * T
+        edges = np.empty((cap, 2), dtype=np.int64)
+        is_boundary = np.empty(cap, dtype=np.uint8)
+        dual = np.empty((T, 2))
+        centers = np.empty((cap, 2))
+        directions = np.empty((cap, 2))
+        lengths = np.empty(cap)
+        dual_len = np.empty(cap)
+        areas = np.empty(n)
+        n_edges = C.c_int64(0)
+        rc = lib.tdgl_host_mesh_dual(n, T, _lib.ptr(sites), _lib.ptr(elements), C.byref(n_edges),
+                                     _lib.ptr(edges), _lib.ptr(is_boundary), _lib.ptr(dual),
+                                     _lib.ptr(centers), _lib.ptr(directions), _lib.ptr(lengths),
+                                     _lib.ptr(dual_len), _lib.ptr(areas))
+        if rc != 0:
+            raise ValueError(lib.tdgl_last_error(None).decode())
+        E = n_edges.value
+        edges, centers, directions = edges[:E].copy(), centers[:E].copy(), directions[:E].copy()
+        lengths, dual_len = lengths[:E].copy(), dual_len[:E].copy()
+        is_boundary = is_boundary[:E].astype(bool)
+        boundary_edge_indices = np.where(is_boundary)[0]
+        boundary_indices = np.unique(edges[is_boundary].ravel())
+        edge_mesh = EdgeMesh(centers, edges, boundary_edge_indices, directions, lengths, dual_len)
+        areas = _voronoi_areas(sites, dual, elements, edges, lengths, dual_len,
+                               boundary_indices, boundary_edge_indices, interior=areas)
+        return Mesh(sites, elements, boundary_indices, areas=areas, dual_sites=dual,
+                    edge_mesh=edge_mesh)
+
+    @staticmethod
+    def _from_triangulation_numpy(sites, elements, create_submesh: bool = True) -> "Mesh":
+        """The construction of :meth:`from_triangulation` in vectorised NumPy (packed-key
+        unique edges, searchsorted adjacency, bincount areas)."""
+        sites, elements = _check_triangulation(sites, elements)
         n = len(sites)
         edges, is_boundary, tri_keys, ukey = get_edges(elements, n)
         boundary_edge_indices = np.where(is_boundary)[0]
@@ -161,8 +201,19 @@ class Mesh:
                     edge_mesh=edge_mesh)
 
 
+def _check_triangulation(sites, elements):
+    sites = np.asarray(sites, dtype=np.float64).squeeze()
+    elements = np.asarray(elements, dtype=np.int64).squeeze()
+    if sites.ndim != 2 or sites.shape[1] != 2:
+        raise ValueError(
+            f"The site coordinates must have shape (n, 2), got {sites.shape!r}")
+    if elements.ndim != 2 or elements.shape[1] != 3:
+        raise ValueError(f"The elements must have shape (m, 3), got {elements.shape!r}.")
+    return sites, elements
+
+
 def _voronoi_areas(sites, dual, elements, edges, lengths, dual_len, boundary_indices,
-                   boundary_edge_indices) -> np.ndarray:
+                   boundary_edge_indices, interior=None) -> np.ndarray:
     """Voronoi cell areas.
 
     Interior sites: the cell is the convex polygon of the surrounding circumcentres,
@@ -176,8 +227,11 @@ def _voronoi_areas(sites, dual, elements, edges, lengths, dual_len, boundary_ind
     from scipy.spatial import ConvexHull, QhullError
 
     n = len(sites)
-    quarter = 0.25 * lengths * dual_len
-    areas = np.bincount(edges[:, 0], quarter, n) + np.bincount(edges[:, 1], quarter, n)
+    if interior is not None:       # the same sums, already formed by the native builder
+        areas = interior
+    else:
+        quarter = 0.25 * lengths * dual_len
+        areas = np.bincount(edges[:, 0], quarter, n) + np.bincount(edges[:, 1], quarter, n)
     if len(boundary_indices) == 0:
         return areas
     # incident triangles of boundary sites

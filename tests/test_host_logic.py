@@ -491,3 +491,36 @@ def test_solution_save_picks_the_backend(tmp_path, caplog):
         assert path == str(tmp_path / "b.h5.npz") and os.path.exists(path)
         assert any("h5py is not installed" in r.message for r in caplog.records)
         np.testing.assert_array_equal(Solution.from_npz(path).tdgl_data.psi, np.ones(n))
+
+
+def test_native_dual_mesh_equals_the_numpy_construction():
+    """Mesh.from_triangulation (library: tdgl_host_mesh_dual, several host threads) against
+    the vectorised NumPy construction of the same arrays: bit for bit, on a film with a hole
+    (enough triangles for several sort chunks and merges), for 1, 3 and 8 host threads; and
+    the error behaviour of the native entry point."""
+    from tdgl_b200.mesh import Mesh, make_film_points, triangulate
+
+    holes = ((5.0, 3.0, 9.0),)
+    pts, tri = triangulate(make_film_points(150, 120, 0.4, holes), holes)
+    assert 3 * len(tri) > 4 * (1 << 17)
+    ref = Mesh._from_triangulation_numpy(pts, tri)
+    for threads in ("1", "3", "8"):
+        os.environ["TDGL_B200_HOST_THREADS"] = threads
+        try:
+            got = Mesh.from_triangulation(pts, tri)
+        finally:
+            del os.environ["TDGL_B200_HOST_THREADS"]
+        for k in ("sites", "elements", "boundary_indices", "areas", "dual_sites"):
+            a, b = getattr(got, k), getattr(ref, k)
+            assert a.dtype == b.dtype and np.array_equal(a, b), (threads, k)
+        for k in ("centers", "edges", "boundary_edge_indices", "directions",
+                  "normalized_directions", "edge_lengths", "dual_edge_lengths"):
+            a, b = getattr(got.edge_mesh, k), getattr(ref.edge_mesh, k)
+            assert a.dtype == b.dtype and np.array_equal(a, b), (threads, k)
+    bad = tri.copy()
+    bad[7, 1] = len(pts)
+    with pytest.raises(ValueError, match="element index out of range"):
+        Mesh.from_triangulation(pts, bad)
+    # without the dual mesh nothing native is needed (reference create_submesh=False)
+    m = Mesh.from_triangulation(pts, tri, create_submesh=False)
+    assert m.edge_mesh is None and np.array_equal(m.boundary_indices, ref.boundary_indices)
