@@ -63,6 +63,22 @@ class _PinnedBlock:
             pass
 
 
+def _check_out(out, sizes) -> None:
+    """Output arrays the library writes through raw pointers: (psi c128, mu f64, J_s f64, J_n
+    f64), each None (not wanted) or a C-contiguous 1-D array of at least the given length."""
+    if len(out) != 4:
+        raise ValueError("out must be (psi, mu, supercurrent, normal_current)")
+    names = ("psi", "mu", "supercurrent", "normal_current")
+    dtypes = (np.complex128, np.float64, np.float64, np.float64)
+    for a, n, name, dt in zip(out, sizes, names, dtypes):
+        if a is None:
+            continue
+        if (not isinstance(a, np.ndarray) or a.dtype != dt or a.ndim != 1 or a.shape[0] < n
+                or not a.flags.c_contiguous):
+            raise ValueError(f"out[{name}] must be a C-contiguous {np.dtype(dt).name} array of"
+                             f" length {n}")
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """NumPy array in page-locked host memory: the copies of ``DeviceEngine.update`` from /
     to such arrays are true asynchronous DMA transfers."""
@@ -287,6 +303,8 @@ class DeviceEngine:
         if out is None:
             out = (np.empty(self.n_sites, np.complex128), np.empty(self.n_sites),
                    np.empty(self.n_edges), np.empty(self.n_edges))
+        else:
+            _check_out(out, (self.n_sites, self.n_sites, self.n_edges, self.n_edges))
         info = _lib.tdgl_advance_info()
         psi = as_c128(psi, (self.n_sites,))
         mu = as_f64(mu, (self.n_sites,))
@@ -318,6 +336,14 @@ class DeviceEngine:
         """The step seam of one shard: psi / mu of the OWNED sites in, psi', mu' of the owned
         sites and J_s, J_n of the owned edges out (``out`` = four arrays of those sizes, e.g.
         pinned).  Every shard must make the call for every step."""
+        if getattr(self, "_local_sizes", None) is None:
+            sizes = np.zeros(2, dtype=np.int64)
+            self._check(self._lib.tdgl_local_maps(self._h, ptr(sizes), None, None))
+            self._local_sizes = (int(sizes[0]), int(sizes[1]))
+        ns, ne = self._local_sizes
+        psi_local = as_c128(psi_local, (ns,))
+        mu_local = as_f64(mu_local, (ns,))
+        _check_out(out, (ns, ns, ne, ne))
         info = _lib.tdgl_advance_info()
         rc = self._lib.tdgl_update_local(self._h, ptr(psi_local), ptr(mu_local), int(step),
                                          float(time), ptr(out[0]), ptr(out[1]), ptr(out[2]),

@@ -524,3 +524,25 @@ def test_native_dual_mesh_equals_the_numpy_construction():
     # without the dual mesh nothing native is needed (reference create_submesh=False)
     m = Mesh.from_triangulation(pts, tri, create_submesh=False)
     assert m.edge_mesh is None and np.array_equal(m.boundary_indices, ref.boundary_indices)
+
+
+def test_output_arrays_of_the_step_seam_are_validated():
+    """DeviceEngine.update / update_local hand `out` to the library as raw pointers: wrong
+    dtype, length or layout is a ValueError, None entries and pinned-style views pass."""
+    from tdgl_b200.engine import _check_out
+
+    n, e = 10, 25
+    good = (np.empty(n, complex), np.empty(n), np.empty(e), np.empty(e))
+    _check_out(good, (n, n, e, e))
+    _check_out((None, None, None, None), (n, n, e, e))
+    buf = (ctypes.c_char * (16 * n))()                       # what pinned_empty builds on
+    view = np.frombuffer(buf, dtype=np.complex128, count=n)
+    _check_out((view, good[1], np.empty(e + 3), good[3]), (n, n, e, e))
+    for bad in ((np.empty(n), good[1], good[2], good[3]),                    # dtype
+                (good[0], np.empty(n - 1), good[2], good[3]),                # too short
+                (good[0], good[1], np.empty(2 * e)[::2], good[3]),           # strided
+                (good[0], good[1], np.empty((e, 1)), good[3]),               # 2-D
+                (good[0], good[1], list(range(e)), good[3]),                 # not an array
+                good[:3]):
+        with pytest.raises(ValueError):
+            _check_out(bad, (n, n, e, e))
