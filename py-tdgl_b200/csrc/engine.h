@@ -240,6 +240,7 @@ class Engine {
   void comm_connect_local(Engine* const* peers /* world engines of this process */);
   void shard_info(int64_t* out, int n);
   int world() const { return world_; }
+  int n_boundary_edges() const { return Eb_; }
   void make_current() { TDGL_CUDA(cudaSetDevice(cfg_.device)); }
 
   std::string last_error;

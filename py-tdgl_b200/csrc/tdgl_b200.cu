@@ -2467,13 +2467,22 @@ const char* tdgl_last_error(const tdgl_handle* h) {
 }
 
 int tdgl_set_link_exponents(tdgl_handle* h, const double* A) {
-  return guarded(h, [&](tdgl::Engine& e) { e.set_link_exponents(A); });
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (A == nullptr) throw std::invalid_argument("null vector potential");
+    e.set_link_exponents(A);
+  });
 }
 int tdgl_set_epsilon(tdgl_handle* h, const double* epsilon) {
-  return guarded(h, [&](tdgl::Engine& e) { e.set_epsilon(epsilon); });
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (epsilon == nullptr) throw std::invalid_argument("null epsilon");
+    e.set_epsilon(epsilon);
+  });
 }
 int tdgl_set_mu_boundary(tdgl_handle* h, const double* mu_boundary) {
-  return guarded(h, [&](tdgl::Engine& e) { e.set_mu_boundary(mu_boundary); });
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (mu_boundary == nullptr && e.n_boundary_edges() > 0) throw std::invalid_argument("null mu_boundary");
+    e.set_mu_boundary(mu_boundary);
+  });
 }
 int tdgl_set_dA_dt(tdgl_handle* h, const double* dA_dt) {
   return guarded(h, [&](tdgl::Engine& e) { e.set_dA_dt(dA_dt); });
@@ -2528,7 +2537,10 @@ int tdgl_get_running_screening(tdgl_handle* h, int64_t capacity, int64_t* iterat
   });
 }
 int tdgl_set_state(tdgl_handle* h, const double* psi, const double* mu) {
-  return guarded(h, [&](tdgl::Engine& e) { e.set_state(psi, mu); });
+  return guarded(h, [&](tdgl::Engine& e) {
+    if (psi == nullptr || mu == nullptr) throw std::invalid_argument("null psi / mu");
+    e.set_state(psi, mu);
+  });
 }
 int tdgl_set_stepper(tdgl_handle* h, double dt_init, double dt_max, int32_t adaptive,
                      int32_t adaptive_window, int32_t max_solve_retries,
