@@ -36,11 +36,36 @@ class FakeEngine:
         self.begun = []
         self.fail_wait = False
         self.interrupt_at = None  # raise SIGINT inside the advance that starts at this step
+        self.log = []             # setter calls, in order
         FakeEngine.instances.append(self)
 
-    def set_link_exponents(self, A): pass
-    def set_epsilon(self, eps): pass
-    def set_mu_boundary(self, mub): pass
+    def set_link_exponents(self, A):
+        self.log.append(("link", np.array(A)))
+
+    def set_epsilon(self, eps):
+        self.log.append(("eps", np.array(eps)))
+
+    def set_mu_boundary(self, mub):
+        self.log.append(("mub", np.array(mub)))
+
+    def set_dA_dt(self, v):
+        self.log.append(("dadt", np.array(v)))
+
+    def set_vector_potential_ramp(self, A0, t, f):
+        self.log.append(("ramp", np.array(A0), np.array(t), np.array(f)))
+
+    def set_terminal_current_table(self, term_of, lengths, t, cur):
+        self.log.append(("cur_table", np.array(term_of), np.array(lengths), np.array(t),
+                         np.array(cur)))
+
+    def set_epsilon_table(self, e0, e1, t, g):
+        self.log.append(("eps_table", np.array(e0), np.array(e1), np.array(t), np.array(g)))
+
+    def update(self, psi, mu, step, time, out=None):
+        self.set_state(psi, mu)
+        info = self.advance(1, 1e300, step, time)
+        return info, (self.psi.copy(), self.mu.copy(), *self.get_currents())
+
     def close(self): pass
 
     def set_stepper(self, *, dt_init, **kw):
@@ -196,3 +221,144 @@ def test_interrupt_while_thermalising_returns_none(fake, monkeypatch):
     s, eng = fake(skip_time=0.02, solve_time=0.01, pause_on_interrupt=False)
     eng.interrupt_at = 4
     assert s.solve() is None                                 # runner.py:313-314
+
+
+# ------------------------------------------------------------------------------------------
+# time-dependent inputs: what reaches the engine, and when
+
+def _strip(monkeypatch):
+    from tdgl_b200.synthetic import film_problem
+
+    FakeEngine.instances.clear()
+    monkeypatch.setattr(solver_mod, "DeviceEngine", FakeEngine)
+    mesh, A, eps, terms = film_problem(8, 4, 0.5, terminals=True)
+    return mesh, A, eps, terms
+
+
+def test_callable_currents_step_one_at_a_time_and_upload_on_change(monkeypatch):
+    """reference solver.py:325-345: J_ext,k = -(1 / L_k) sum_{j != k} I_j(t), written to the
+    terminal's boundary edges, only when a density changed; a callable current makes the host
+    wake up every step (runner.py:417-423 calls update once per step)."""
+    mesh, A, eps, terms = _strip(monkeypatch)
+    I = 0.3
+
+    def cur(t):
+        f = 1.0 if t < 3.5e-3 else 2.0
+        return {"source": I * f, "drain": -I * f}
+
+    o = tdgl.SolverOptions(solve_time=0.0065, dt_init=1e-3, adaptive=False, save_every=4)
+    s = tdgl.TDGLSolver.from_dimensionless(mesh, o, A_applied=A, epsilon=eps, terminal_info=terms,
+                                           terminal_currents=cur)
+    eng = FakeEngine.instances[-1]
+    s.solve()
+    assert all(n == 1 for n, _, _ in eng.calls)                    # chunk = 1
+    ups = [e[1] for e in eng.log if e[0] == "mub"]
+    assert len(ups) == 2                                           # t = 0 and the jump at 4e-3
+    for k, f in enumerate((1.0, 2.0)):
+        want = np.zeros(len(mesh.edge_mesh.boundary_edge_indices))
+        for t in terms:
+            other = sum(v for n, v in cur(1.0 if f == 2.0 else 0.0).items() if n != t.name)
+            want[np.asarray(t.boundary_edge_indices)] = -other / t.length
+        np.testing.assert_array_equal(ups[k], want)
+    # a dict of currents is uploaded once and the chunks run to the save steps
+    s2 = tdgl.TDGLSolver.from_dimensionless(mesh, o, A_applied=A, epsilon=eps, terminal_info=terms,
+                                            terminal_currents={"source": I, "drain": -I})
+    eng2 = FakeEngine.instances[-1]
+    s2.solve()
+    assert [n for n, _, _ in eng2.calls] == [4, 4] and len([e for e in eng2.log if e[0] == "mub"]) == 1
+    # non-conserving and unknown terminals are the reference's ValueErrors (solver.py:45-53)
+    with pytest.raises(ValueError, match="sum of all terminal currents must be 0"):
+        tdgl.TDGLSolver.from_dimensionless(mesh, o, A_applied=A, epsilon=eps, terminal_info=terms,
+                                           terminal_currents={"source": I, "drain": 0.0})
+    with pytest.raises(ValueError, match="Unknown terminal"):
+        tdgl.TDGLSolver.from_dimensionless(mesh, o, A_applied=A, epsilon=eps, terminal_info=terms,
+                                           terminal_currents={"source": I, "gate": -I})
+
+
+def test_host_vector_potential_callback_follows_the_reference(monkeypatch):
+    """reference solver.py:626-642: dA/dt = (A(t) - A_prev) / dt_prev projected on the
+    normalised edge directions every step; the link variables are rebuilt only
+    `if not allclose(A, A_prev)`."""
+    mesh, A, eps, terms = _strip(monkeypatch)
+    A1 = np.ones_like(A) * 0.05
+
+    def A_of_t(t):          # constant up to 2.5e-3, then growing by 20 % per step
+        return A1 * (1.0 + 0.2 * max(0.0, round((t - 2e-3) / 1e-3)))
+
+    o = tdgl.SolverOptions(solve_time=0.0045, dt_init=1e-3, adaptive=False, save_every=100)
+    s = tdgl.TDGLSolver.from_dimensionless(mesh, o, A_applied=A_of_t, epsilon=eps)
+    eng = FakeEngine.instances[-1]
+    sol = s.solve()
+    links = [e[1] for e in eng.log if e[0] == "link"]
+    dadt = [e[1] for e in eng.log if e[0] == "dadt"]
+    n_updates = len(eng.calls)
+    assert len(dadt) == n_updates and all(n == 1 for n, _, _ in eng.calls)
+    d = np.asarray(mesh.edge_mesh.directions)
+    nd = d / np.linalg.norm(d, axis=1)[:, None]
+    times = [c[2] for c in eng.calls]
+    prev = A_of_t(0.0)
+    changes = 0
+    for k, t in enumerate(times):
+        cur = A_of_t(t)
+        np.testing.assert_allclose(dadt[k], np.einsum("ij,ij->i", (cur - prev) / 1e-3, nd),
+                                   rtol=0, atol=1e-15)
+        changes += not np.allclose(cur, prev)
+        prev = cur
+    assert changes >= 2 and len(links) == 1 + changes      # setup + one rebuild per change
+    # the vector potential of every saved step travels with the results (dynamic => per group)
+    assert "applied_vector_potential" in sol._saved.groups[-1]
+    assert "applied_vector_potential" not in sol._saved.fixed
+
+
+def test_device_side_tables_are_handed_over_once(monkeypatch):
+    """Separable inputs (f(t) A0(r), I_k(t) tables, eps0 + g(t) eps1) go to the engine at setup
+    and the stage loop runs whole chunks (no per-step host callback)."""
+    from tdgl_b200.sources import PiecewiseLinearCurrents, SeparableEpsilon
+
+    mesh, A, eps, terms = _strip(monkeypatch)
+    tk = np.array([0.0, 0.004, 0.01])
+    table = PiecewiseLinearCurrents(tk, {"source": [0.1, 0.3, 0.3], "drain": [-0.1, -0.3, -0.3]})
+    e = SeparableEpsilon(eps, -0.1 * eps, tk, np.array([0.0, 1.0, 1.0]))
+    o = tdgl.SolverOptions(solve_time=0.0075, dt_init=1e-3, adaptive=False, save_every=4)
+    s = tdgl.TDGLSolver.from_dimensionless(mesh, o, A_applied=A, epsilon=e, terminal_info=terms,
+                                           terminal_currents=table, A_ramp=(tk, [0.0, 1.0, 1.0]))
+    eng = FakeEngine.instances[-1]
+    sol = s.solve()
+    kinds = [x[0] for x in eng.log]
+    assert kinds.count("ramp") == 1 and kinds.count("cur_table") == 1 and kinds.count("eps_table") == 1
+    assert [c[1] for c in eng.calls] == [0, 4, 8]                  # whole chunks, no per-step callback
+    ct = next(x for x in eng.log if x[0] == "cur_table")
+    names = [t.name for t in s.terminal_info]
+    np.testing.assert_array_equal(ct[4], np.array([table.knots[1][n] for n in names]))
+    np.testing.assert_array_equal(ct[2], [t.length for t in s.terminal_info])
+    for k, t in enumerate(s.terminal_info):
+        assert np.all(ct[1][np.asarray(t.boundary_edge_indices)] == k)
+    assert np.sum(ct[1] >= 0) == sum(len(t.boundary_edge_indices) for t in s.terminal_info)
+    # saved epsilon / A follow the tables at the time of the last step taken
+    g = sol._saved.groups[-1]
+    t_last = g["attrs"]["time"]
+    np.testing.assert_allclose(g["epsilon"], eps * (1 - 0.1 * min(t_last / 0.004, 1.0)), rtol=1e-12)
+    np.testing.assert_allclose(g["applied_vector_potential"], A * min(t_last / 0.004, 1.0), rtol=1e-12)
+
+
+def test_update_seam_tuple_layout(monkeypatch):
+    """`SolverResult` is positional for the reference's Runner (`new_dt, *values`,
+    runner.py:424-428): A_applied is present only for a dynamic vector potential, epsilon only
+    for a dynamic epsilon, in that order (solver.py:708-714)."""
+    mesh, A, eps, terms = _strip(monkeypatch)
+    o = tdgl.SolverOptions(solve_time=1.0, dt_init=1e-3, adaptive=False)
+    n, E = len(mesh.sites), len(mesh.edge_mesh.edges)
+    for dyn_A, dyn_eps, length in ((False, False, 6), (True, False, 7), (False, True, 7), (True, True, 8)):
+        s = tdgl.TDGLSolver.from_dimensionless(
+            mesh, o, A_applied=(lambda t: A) if dyn_A else A,
+            epsilon=(lambda t: eps) if dyn_eps else eps)
+        res = s.update({"step": 0, "time": 0.0, "dt": 1e-3}, None, 1e-3,
+                       psi=np.ones(n, complex), mu=np.zeros(n))
+        got = [x for x in res if x is not None]
+        assert len(got) == length
+        assert res.dt == 1e-3 and res.psi.shape == (n,) and res.supercurrent.shape == (E,)
+        assert res.A_induced.shape == (E, 2) and not res.A_induced.any()
+        if dyn_A:
+            assert got[6].shape == (E, 2)
+        if dyn_eps:
+            assert got[-1].shape == (n,)
